@@ -1,0 +1,124 @@
+// C API of the host-side driver library (libh3dhost.so): mesh, connectivity, nodal operators, geometry,
+// partitioning.  Consumed by the Python/ctypes front end and by C++ drivers; the arrays it produces are
+// exactly the inputs of the device C-ABI (include/h3d_gpu.h).
+#include <cstring>
+#include <string>
+
+#include "geometry.hpp"
+#include "partition.hpp"
+
+using namespace h3d;
+
+namespace {
+thread_local std::string g_err;
+struct Host {
+    HostMesh mesh;
+    HostGeometry geom;
+    HaloInfo halo;
+    bool connected = false, hasGeom = false;
+};
+}  // namespace
+
+extern "C" {
+
+const char* h3dhost_last_error() { return g_err.c_str(); }
+
+void* h3dhost_mesh_box(int nex, int ney, int nez, double L, double amp, int bFaceOrder, int shuffle, unsigned seed) {
+    Host* h = new Host();
+    boxMesh(h->mesh, nex, L, amp, bFaceOrder, shuffle, seed, nex, ney, nez);
+    return h;
+}
+
+void* h3dhost_mesh_read(const char* path) {
+    Host* h = new Host();
+    if (!readSpecMesh(path, h->mesh, g_err)) { delete h; return nullptr; }
+    return h;
+}
+
+int h3dhost_mesh_write(void* hp, const char* path) { writeSpecMesh(path, ((Host*)hp)->mesh); return 0; }
+
+void h3dhost_mesh_free(void* hp) { delete (Host*)hp; }
+
+// bc table: names/types/coupled are nbc C strings each; params is 16 doubles per bc
+int h3dhost_mesh_connect(void* hp, int nbc, const char** names, const char** types, const char** coupled, const double* params) {
+    Host* h = (Host*)hp;
+    std::vector<BCSpec> bcs(nbc);
+    for (int i = 0; i < nbc; ++i) {
+        bcs[i].name = toLower(names[i]); bcs[i].type = toLower(types[i]); bcs[i].coupled = coupled[i] ? toLower(coupled[i]) : "";
+        if (params) std::memcpy(bcs[i].params, params + 16 * i, 16 * sizeof(double));
+    }
+    if (!buildConnectivity(h->mesh, bcs, g_err)) return 1;
+    h->connected = true;
+    return 0;
+}
+
+int h3dhost_mesh_geometry(void* hp, int N, int nodeType) {
+    Host* h = (Host*)hp;
+    if (!h->connected) { g_err = "mesh connectivity has not been built"; return 1; }
+    if (N < 1 || N > 15) { g_err = "polynomial order out of range"; return 1; }
+    try { buildGeometry(h->mesh, N, nodeType, h->geom); } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
+    h->hasGeom = true;
+    return 0;
+}
+
+int h3dhost_mesh_sizes(void* hp, int* nElem, int* nFaces, int* nNodes, int* N) {
+    Host* h = (Host*)hp;
+    *nElem = h->mesh.nElem(); *nFaces = h->mesh.nFaces; *nNodes = h->mesh.nNodes(); *N = h->hasGeom ? h->geom.N : -1;
+    return 0;
+}
+
+// name -> pointer/count/type (0 = double, 1 = int32).  Pointers stay valid until the mesh is freed/rebuilt.
+int h3dhost_get_array(void* hp, const char* name, void** ptr, long long* count, int* isInt) {
+    Host* h = (Host*)hp;
+    std::string s(name);
+#define DARR(nm, vec) if (s == nm) { *ptr = (void*)(vec).data(); *count = (long long)(vec).size(); *isInt = 0; return 0; }
+#define IARR(nm, vec) if (s == nm) { *ptr = (void*)(vec).data(); *count = (long long)(vec).size(); *isInt = 1; return 0; }
+    DARR("nodes", h->mesh.nodes) IARR("elemNodes", h->mesh.elemNodes)
+    IARR("faceNodes", h->mesh.faceNodes) IARR("faceElem", h->mesh.faceElem) IARR("faceElemSide", h->mesh.faceElemSide)
+    IARR("faceRot", h->mesh.faceRot) IARR("faceType", h->mesh.faceType) IARR("faceZone", h->mesh.faceZone)
+    IARR("elemFace", h->mesh.elemFace) IARR("elemFaceSide", h->mesh.elemFaceSide)
+    DARR("x", h->geom.x) DARR("jGradXi", h->geom.jGradXi) DARR("jGradEta", h->geom.jGradEta) DARR("jGradZeta", h->geom.jGradZeta)
+    DARR("jacobian", h->geom.jac) DARR("invJacobian", h->geom.invJac) DARR("volume", h->geom.volume)
+    DARR("faceX", h->geom.fx) DARR("faceNormal", h->geom.fnormal) DARR("faceT1", h->geom.ft1) DARR("faceT2", h->geom.ft2)
+    DARR("faceJacobian", h->geom.fjac) DARR("faceSurface", h->geom.fsurface)
+    IARR("haloRank", h->halo.rank) IARR("haloCount", h->halo.count) IARR("haloFace", h->halo.face) IARR("haloSide", h->halo.side)
+    IARR("globalElem", h->halo.globalElem) IARR("globalFace", h->halo.globalFace)
+#undef DARR
+#undef IARR
+    g_err = "unknown array: " + s;
+    return 1;
+}
+
+// 1-D operators: x,w (n); D,hatD,sharpD (n*n row-major M(i,l)); v,b (2*n: side-major)
+int h3dhost_nodal(int N, int nodeType, double* x, double* w, double* D, double* hatD, double* sharpD, double* v, double* b) {
+    try {
+        NodalStorage sp; sp.construct(nodeType, N);
+        const int n = N + 1;
+        std::memcpy(x, sp.x.data(), n * sizeof(double)); std::memcpy(w, sp.w.data(), n * sizeof(double));
+        std::memcpy(D, sp.D.data(), n * n * sizeof(double)); std::memcpy(hatD, sp.hatD.data(), n * n * sizeof(double));
+        std::memcpy(sharpD, sp.sharpD.data(), n * n * sizeof(double));
+        std::memcpy(v, sp.v.data(), 2 * n * sizeof(double)); std::memcpy(b, sp.b.data(), 2 * n * sizeof(double));
+    } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
+    return 0;
+}
+
+// Element partition: method 0 = METIS_PartMeshDual (ncommon = 4, as METISPartitioning.f90:151), 1 = contiguous
+// blocks of the element list.  part[nElem] receives 0-based ranks.
+int h3dhost_partition(void* hp, int nparts, int method, int* part) {
+    Host* h = (Host*)hp;
+    return partitionElements(h->mesh, nparts, method, part, g_err) ? 0 : 1;
+}
+
+// Extracts the local mesh of `rank`: returns a new handle whose faces on partition cuts are HMESH_MPI
+// (single local side, rotation kept), with geometry rebuilt when the parent has it.  Halo tables are
+// exposed through h3dhost_get_array on the child: "haloRank","haloCount","haloFace","haloSide","globalElem".
+void* h3dhost_extract_partition(void* hp, const int* part, int rank) {
+    Host* h = (Host*)hp;
+    if (!h->connected) { g_err = "mesh connectivity has not been built"; return nullptr; }
+    Host* c = new Host();
+    extractPartition(h->mesh, part, rank, c->mesh, c->halo);
+    c->connected = true;
+    return c;
+}
+
+}  // extern "C"

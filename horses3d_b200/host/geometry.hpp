@@ -1,0 +1,283 @@
+// Host-side metric terms: element mapping, conservative (curl-form) metrics, face normals/tangents.
+// This is driver-side pre-processing (the reference keeps it in Fortran); the device receives the arrays.
+//
+// Reference behaviour followed (paths relative to /root/reference/Solver/src/libs/mesh):
+//   TransfiniteMaps3D.f90:186-281   Hex8 map and gradient
+//   TransfiniteMaps3D.f90:300-430   general transfinite map from six face patches
+//   FacePatchClass.f90:189-268      patch evaluation (bilinear shortcut for 2x2 patches)
+//   MappedGeometry.f90:82-152       node coordinates, volume
+//   MappedGeometry.f90:174-384      curl-form metrics on Chebyshev-Lobatto points, interpolated to the nodes
+//   MappedGeometry.f90:482-756      face normal, surface Jacobian, tangents (from the LEFT element, HexMesh.f90:2990-3030)
+// Deviation (round-off level only): the mapping gradient of curved elements is obtained by differentiating
+// the nodal interpolant of the mapping on the Chebyshev-Lobatto grid (exact for patch order <= N, which the
+// reference enforces by projecting patches down, HexMesh.f90:2830-2840) instead of the analytic blend
+// derivative, and the CGL->node interpolation is sum-factorised.
+#pragma once
+#include <cstring>
+
+#include "mesh.hpp"
+
+namespace h3d {
+
+struct HostGeometry {
+    int N = 0, n = 0, nodeType = GAUSS;
+    NodalStorage sp;
+    // element arrays in the reference's per-element order: [e][k][j][i][c]
+    std::vector<double> x, jGradXi, jGradEta, jGradZeta;   // 3*n^3 per element
+    std::vector<double> jac, invJac;                        // n^3 per element
+    std::vector<double> volume;                             // per element
+    // face arrays: [f][j][i][c]
+    std::vector<double> fx, fnormal, ft1, ft2;              // 3*n^2 per face
+    std::vector<double> fjac;                               // n^2 per face
+    std::vector<double> fsurface;                           // per face
+};
+
+struct ElemMap {
+    const HostMesh* m; int e; double corners[8][3];
+    std::vector<double> wb[6][2];  // barycentric weights of the patch knots
+    std::vector<double> knots[6][2];
+    void init(const HostMesh& mesh, int e_) {
+        m = &mesh; e = e_;
+        for (int k = 0; k < 8; ++k) for (int c = 0; c < 3; ++c) corners[k][c] = mesh.nodes[3 * mesh.elemNodes[8 * e + k] + c];
+        if (!mesh.isHex8[e]) for (int f = 0; f < 6; ++f) {
+            const FacePatch& p = mesh.patches[e][f];
+            const int nn[2] = {p.nu, p.nv};
+            for (int d = 0; d < 2; ++d) {
+                knots[f][d].resize(nn[d]); wb[f][d].resize(nn[d]);
+                for (int i = 0; i < nn[d]; ++i) knots[f][d][i] = (nn[d] == 2) ? (i ? 1.0 : -1.0) : -std::cos(i * PI_RP / (nn[d] - 1.0));
+                barycentricWeights(nn[d] - 1, knots[f][d].data(), wb[f][d].data());
+            }
+        }
+    }
+    void facePoint(int f, double u, double v, double* p) const {
+        const FacePatch& fp = m->patches[e][f];
+        if (fp.nu == 2 && fp.nv == 2) {
+            for (int c = 0; c < 3; ++c)
+                p[c] = 0.25 * (fp.pts[0 * 3 + c] * (1 - u) * (1 - v) + fp.pts[1 * 3 + c] * (1 + u) * (1 - v) +
+                               fp.pts[3 * 3 + c] * (1 + u) * (1 + v) + fp.pts[2 * 3 + c] * (1 - u) * (1 + v));
+            return;
+        }
+        double li[32], lj[32];
+        interpolatingPolynomialVector(u, fp.nu - 1, knots[f][0].data(), wb[f][0].data(), li);
+        interpolatingPolynomialVector(v, fp.nv - 1, knots[f][1].data(), wb[f][1].data(), lj);
+        p[0] = p[1] = p[2] = 0.0;
+        for (int j = 0; j < fp.nv; ++j) for (int i = 0; i < fp.nu; ++i) {
+            double l = li[i] * lj[j];
+            for (int c = 0; c < 3; ++c) p[c] += fp.pts[(j * fp.nu + i) * 3 + c] * l;
+        }
+    }
+    void at(const double* u, double* x) const {
+        double xi[3] = {0.5 * (u[0] + 1.0), 0.5 * (u[1] + 1.0), 0.5 * (u[2] + 1.0)};
+        if (m->isHex8[e]) {
+            for (int j = 0; j < 3; ++j)
+                x[j] = corners[0][j] * (1 - xi[0]) * (1 - xi[1]) * (1 - xi[2]) + corners[1][j] * xi[0] * (1 - xi[1]) * (1 - xi[2]) +
+                       corners[2][j] * xi[0] * xi[1] * (1 - xi[2]) + corners[3][j] * (1 - xi[0]) * xi[1] * (1 - xi[2]) +
+                       corners[4][j] * (1 - xi[0]) * (1 - xi[1]) * xi[2] + corners[5][j] * xi[0] * (1 - xi[1]) * xi[2] +
+                       corners[6][j] * xi[0] * xi[1] * xi[2] + corners[7][j] * (1 - xi[0]) * xi[1] * xi[2];
+            return;
+        }
+        double face[6][3], edge[12][3];
+        facePoint(0, u[0], -1.0, edge[0]); facePoint(0, 1.0, u[2], edge[1]); facePoint(0, u[0], 1.0, edge[2]); facePoint(0, -1.0, u[2], edge[3]);
+        facePoint(1, u[0], -1.0, edge[4]); facePoint(1, 1.0, u[2], edge[5]); facePoint(1, u[0], 1.0, edge[6]); facePoint(1, -1.0, u[2], edge[7]);
+        facePoint(3, u[1], -1.0, edge[9]); facePoint(5, u[1], -1.0, edge[8]); facePoint(3, u[1], 1.0, edge[10]); facePoint(5, u[1], 1.0, edge[11]);
+        facePoint(0, u[0], u[2], face[0]); facePoint(1, u[0], u[2], face[1]); facePoint(2, u[0], u[1], face[2]);
+        facePoint(3, u[1], u[2], face[3]); facePoint(4, u[0], u[1], face[4]); facePoint(5, u[1], u[2], face[5]);
+        for (int j = 0; j < 3; ++j) {
+            double r = face[5][j] * (1 - xi[0]) + face[3][j] * xi[0] + face[0][j] * (1 - xi[1]) + face[1][j] * xi[1] + face[2][j] * (1 - xi[2]) + face[4][j] * xi[2];
+            r = r - edge[0][j] * (1 - xi[1]) * (1 - xi[2]) - edge[2][j] * (1 - xi[1]) * xi[2] - edge[4][j] * xi[1] * (1 - xi[2]) - edge[6][j] * xi[1] * xi[2]
+                  - edge[8][j] * (1 - xi[0]) * (1 - xi[2]) - edge[11][j] * (1 - xi[0]) * xi[2] - edge[9][j] * (1 - xi[2]) * xi[0] - edge[10][j] * xi[0] * xi[2]
+                  - edge[3][j] * (1 - xi[0]) * (1 - xi[1]) - edge[7][j] * (1 - xi[0]) * xi[1] - edge[1][j] * xi[0] * (1 - xi[1]) - edge[5][j] * xi[0] * xi[1];
+            r = r + corners[0][j] * (1 - xi[0]) * (1 - xi[1]) * (1 - xi[2]) + corners[4][j] * (1 - xi[0]) * (1 - xi[1]) * xi[2]
+                  + corners[3][j] * (1 - xi[0]) * xi[1] * (1 - xi[2]) + corners[7][j] * (1 - xi[0]) * xi[1] * xi[2]
+                  + corners[1][j] * xi[0] * (1 - xi[1]) * (1 - xi[2]) + corners[5][j] * xi[0] * (1 - xi[1]) * xi[2]
+                  + corners[2][j] * xi[0] * xi[1] * (1 - xi[2]) + corners[6][j] * xi[0] * xi[1] * xi[2];
+            x[j] = r;
+        }
+    }
+    // gradient of the hex8 map: g[i][j] = d x_i / d xi_j
+    void gradHex8(const double* u, double g[3][3]) const {
+        double xi[3] = {0.5 * (u[0] + 1.0), 0.5 * (u[1] + 1.0), 0.5 * (u[2] + 1.0)};
+        for (int i = 0; i < 3; ++i) {
+            g[i][0] = 0.5 * (-corners[0][i] * (1 - xi[1]) * (1 - xi[2]) + corners[1][i] * (1 - xi[1]) * (1 - xi[2]) + corners[2][i] * xi[1] * (1 - xi[2]) - corners[3][i] * xi[1] * (1 - xi[2])
+                             - corners[4][i] * (1 - xi[1]) * xi[2] + corners[5][i] * (1 - xi[1]) * xi[2] + corners[6][i] * xi[1] * xi[2] - corners[7][i] * xi[1] * xi[2]);
+            g[i][1] = 0.5 * (-corners[0][i] * (1 - xi[0]) * (1 - xi[2]) - corners[1][i] * xi[0] * (1 - xi[2]) + corners[2][i] * xi[0] * (1 - xi[2]) + corners[3][i] * (1 - xi[0]) * (1 - xi[2])
+                             - corners[4][i] * (1 - xi[0]) * xi[2] - corners[5][i] * xi[0] * xi[2] + corners[6][i] * xi[0] * xi[2] + corners[7][i] * (1 - xi[0]) * xi[2]);
+            g[i][2] = 0.5 * (-corners[0][i] * (1 - xi[0]) * (1 - xi[1]) - corners[1][i] * xi[0] * (1 - xi[1]) - corners[2][i] * xi[0] * xi[1] - corners[3][i] * (1 - xi[0]) * xi[1]
+                             + corners[4][i] * (1 - xi[0]) * (1 - xi[1]) + corners[5][i] * xi[0] * (1 - xi[1]) + corners[6][i] * xi[0] * xi[1] + corners[7][i] * (1 - xi[0]) * xi[1]);
+        }
+    }
+};
+
+// local element trace index of face node (a,b) on local face f -> (i,j,k) with the normal index left free
+inline void faceNodeToElem(int f, int a, int b, int nrm, int& i, int& j, int& k) {
+    int idx[3]; idx[axisMap[f][0]] = a; idx[axisMap[f][1]] = b; idx[faceNormalAxis[f]] = nrm;
+    i = idx[0]; j = idx[1]; k = idx[2];
+}
+
+inline void buildGeometry(const HostMesh& m, int N, int nodeType, HostGeometry& g) {
+    g.N = N; g.n = N + 1; g.nodeType = nodeType; g.sp.construct(nodeType, N);
+    const NodalStorage& sp = g.sp;
+    const int n = g.n, n3 = n * n * n, n2 = n * n;
+    const int nE = m.nElem();
+    g.x.assign(3 * (size_t)n3 * nE, 0.0); g.jGradXi.assign(3 * (size_t)n3 * nE, 0.0); g.jGradEta.assign(3 * (size_t)n3 * nE, 0.0);
+    g.jGradZeta.assign(3 * (size_t)n3 * nE, 0.0); g.jac.assign((size_t)n3 * nE, 0.0); g.invJac.assign((size_t)n3 * nE, 0.0); g.volume.assign(nE, 0.0);
+#pragma omp parallel
+    {
+        std::vector<double> xC(3 * n3), gradx(9 * n3), cp(3 * n3), aux(9 * n3), Ja[3], JC(n3), tmp1(3 * n3), tmp2(3 * n3);
+        for (int d = 0; d < 3; ++d) Ja[d].assign(3 * n3, 0.0);
+        ElemMap map;
+#pragma omp for schedule(static)
+        for (int e = 0; e < nE; ++e) {
+            map.init(m, e);
+            auto I = [&](int i, int j, int k) { return (k * n + j) * n + i; };
+            // node coordinates
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                double u[3] = {sp.x[i], sp.x[j], sp.x[k]};
+                map.at(u, &g.x[3 * ((size_t)e * n3 + I(i, j, k))]);
+            }
+            // mapping and its gradient on the Chebyshev-Gauss-Lobatto grid
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                double u[3] = {sp.xCGL[i], sp.xCGL[j], sp.xCGL[k]};
+                map.at(u, &xC[3 * I(i, j, k)]);
+            }
+            if (m.isHex8[e]) {
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                    double u[3] = {sp.xCGL[i], sp.xCGL[j], sp.xCGL[k]}, gg[3][3];
+                    map.gradHex8(u, gg);
+                    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) gradx[9 * I(i, j, k) + 3 * a + b] = gg[a][b];
+                }
+            } else {
+                const double eps = 100.0 * 2.220446049250313e-16;
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) {
+                    double d0 = 0, d1 = 0, d2 = 0;
+                    for (int l = 0; l < n; ++l) {
+                        d0 += sp.DCGL[i * n + l] * xC[3 * I(l, j, k) + a];
+                        d1 += sp.DCGL[j * n + l] * xC[3 * I(i, l, k) + a];
+                        d2 += sp.DCGL[k * n + l] * xC[3 * I(i, j, l) + a];
+                    }
+                    double* gp = &gradx[9 * I(i, j, k) + 3 * a];
+                    gp[0] = std::fabs(d0) <= eps ? 0.0 : d0; gp[1] = std::fabs(d1) <= eps ? 0.0 : d1; gp[2] = std::fabs(d2) <= eps ? 0.0 : d2;
+                }
+            }
+            // curl form: component c of Ja^d = -1/2 [curl( X_l grad X_m - X_m grad X_l )]_d, (c,m,l) cyclic
+            for (int c = 0; c < 3; ++c) {
+                const int l_ = (c + 2) % 3, m_ = (c + 1) % 3;   // c=0: X3 grad X2 - X2 grad X3
+                for (int q = 0; q < n3; ++q) for (int d = 0; d < 3; ++d)
+                    cp[3 * q + d] = xC[3 * q + l_] * gradx[9 * q + 3 * m_ + d] - xC[3 * q + m_] * gradx[9 * q + 3 * l_ + d];
+                std::fill(aux.begin(), aux.end(), 0.0);
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                    double* a = &aux[9 * I(i, j, k)];  // a[3*comp + dir]
+                    for (int l = 0; l < n; ++l) for (int d = 0; d < 3; ++d) {
+                        a[3 * d + 0] += cp[3 * I(l, j, k) + d] * sp.DCGL[i * n + l];
+                        a[3 * d + 1] += cp[3 * I(i, l, k) + d] * sp.DCGL[j * n + l];
+                        a[3 * d + 2] += cp[3 * I(i, j, l) + d] * sp.DCGL[k * n + l];
+                    }
+                }
+                for (int q = 0; q < n3; ++q) {
+                    const double* a = &aux[9 * q];
+                    double J1 = a[3 * 2 + 1] - a[3 * 1 + 2], J2 = a[3 * 0 + 2] - a[3 * 2 + 0], J3 = a[3 * 1 + 0] - a[3 * 0 + 1];
+                    Ja[0][3 * q + c] = -0.5 * J1; Ja[1][3 * q + c] = -0.5 * J2; Ja[2][3 * q + c] = -0.5 * J3;
+                }
+            }
+            for (int q = 0; q < n3; ++q) {
+                const double* G = &gradx[9 * q];   // G[3*i + j] = dx_i/dxi_j ; a_j = column j
+                double a1[3] = {G[0], G[3], G[6]}, a2[3] = {G[1], G[4], G[7]}, a3[3] = {G[2], G[5], G[8]};
+                JC[q] = a1[0] * (a2[1] * a3[2] - a2[2] * a3[1]) + a1[1] * (a2[2] * a3[0] - a2[0] * a3[2]) + a1[2] * (a2[0] * a3[1] - a2[1] * a3[0]);
+            }
+            // back to the solution nodes (sum-factorised TCheb2Gauss in xi, eta, zeta)
+            auto interp3 = [&](const double* src, int nc, double* dst) {
+                double* t1 = tmp1.data(); double* t2 = tmp2.data();
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int c = 0; c < nc; ++c) {
+                    double s = 0; for (int l = 0; l < n; ++l) s += src[nc * I(l, j, k) + c] * sp.TCheb2Gauss[i * n + l];
+                    t1[nc * I(i, j, k) + c] = s;
+                }
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int c = 0; c < nc; ++c) {
+                    double s = 0; for (int l = 0; l < n; ++l) s += t1[nc * I(i, l, k) + c] * sp.TCheb2Gauss[j * n + l];
+                    t2[nc * I(i, j, k) + c] = s;
+                }
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int c = 0; c < nc; ++c) {
+                    double s = 0; for (int l = 0; l < n; ++l) s += t2[nc * I(i, j, l) + c] * sp.TCheb2Gauss[k * n + l];
+                    dst[nc * I(i, j, k) + c] = s;
+                }
+            };
+            interp3(Ja[0].data(), 3, &g.jGradXi[3 * (size_t)e * n3]);
+            interp3(Ja[1].data(), 3, &g.jGradEta[3 * (size_t)e * n3]);
+            interp3(Ja[2].data(), 3, &g.jGradZeta[3 * (size_t)e * n3]);
+            interp3(JC.data(), 1, &g.jac[(size_t)e * n3]);
+            double vol = 0.0;
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                size_t q = (size_t)e * n3 + I(i, j, k);
+                g.invJac[q] = 1.0 / g.jac[q];
+                vol += sp.w[i] * sp.w[j] * sp.w[k] * g.jac[q];
+            }
+            g.volume[e] = vol;
+        }
+    }
+    // ---- faces (geometry from the LEFT element; MPI faces are rebuilt per partition by the caller)
+    const int nF = m.nFaces;
+    g.fx.assign(3 * (size_t)n2 * nF, 0.0); g.fnormal.assign(3 * (size_t)n2 * nF, 0.0); g.ft1.assign(3 * (size_t)n2 * nF, 0.0);
+    g.ft2.assign(3 * (size_t)n2 * nF, 0.0); g.fjac.assign((size_t)n2 * nF, 0.0); g.fsurface.assign(nF, 0.0);
+#pragma omp parallel
+    {
+        ElemMap map;
+#pragma omp for schedule(static)
+        for (int f = 0; f < nF; ++f) {
+            int side = 0;
+            if (m.faceElem[2 * f] < 0) side = 1;
+            const int e = m.faceElem[2 * f + side], lf = m.faceElemSide[2 * f + side];
+            const int rot = side == 0 ? 0 : m.faceRot[f];
+            map.init(m, e);
+            const double* v = &sp.v[faceNormalEnd[lf] * n];
+            const double* Jd = (faceNormalAxis[lf] == 0 ? g.jGradXi.data() : faceNormalAxis[lf] == 1 ? g.jGradEta.data() : g.jGradZeta.data()) + 3 * (size_t)e * n3;
+            std::vector<double> dS(3 * n2, 0.0);
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                int idx[3] = {i, j, k};
+                int a = idx[axisMap[lf][0]], b = idx[axisMap[lf][1]], nr = idx[faceNormalAxis[lf]];
+                for (int c = 0; c < 3; ++c) dS[3 * (b * n + a) + c] += Jd[3 * ((k * n + j) * n + i) + c] * v[nr];
+            }
+            double sgn = faceNormalEnd[lf] ? 1.0 : -1.0;
+            if (side == 1) sgn = -sgn;
+            for (int b = 0; b < n; ++b) for (int a = 0; a < n; ++a) {
+                int aa = a, bb = b;
+                if (rot != 0) leftIndexes2Right(a, b, N, N, rot, aa, bb);
+                const size_t q = (size_t)f * n2 + b * n + a;
+                double nv[3] = {sgn * dS[3 * (bb * n + aa)], sgn * dS[3 * (bb * n + aa) + 1], sgn * dS[3 * (bb * n + aa) + 2]};
+                double nrm = std::sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+                g.fjac[q] = nrm;
+                for (int c = 0; c < 3; ++c) g.fnormal[3 * q + c] = nv[c] / nrm;
+                // face coordinates (coordRotation: face node -> element face coordinates)
+                double xi = sp.x[a], eta = sp.x[b], xr, er;
+                switch (rot) {   // MeshTypes.f90 coordRotation
+                    case 0: xr = xi; er = eta; break;
+                    case 1: xr = -eta; er = xi; break;
+                    case 2: xr = -xi; er = -eta; break;
+                    case 3: xr = eta; er = -xi; break;
+                    case 4: xr = eta; er = xi; break;
+                    case 5: xr = -xi; er = eta; break;
+                    case 6: xr = -eta; er = -xi; break;
+                    default: xr = xi; er = -eta; break;
+                }
+                double u[3]; u[axisMap[lf][0]] = xr; u[axisMap[lf][1]] = er; u[faceNormalAxis[lf]] = faceNormalEnd[lf] ? 1.0 : -1.0;
+                map.at(u, &g.fx[3 * q]);
+            }
+            double surf = 0.0;
+            for (int b = 0; b < n; ++b) for (int a = 0; a < n; ++a) {
+                const size_t q = (size_t)f * n2 + b * n + a;
+                double t1[3] = {0, 0, 0};
+                for (int l = 0; l < n; ++l) for (int c = 0; c < 3; ++c) t1[c] += sp.D[a * n + l] * g.fx[3 * ((size_t)f * n2 + b * n + l) + c];
+                const double* nh = &g.fnormal[3 * q];
+                double dot = t1[0] * nh[0] + t1[1] * nh[1] + t1[2] * nh[2];
+                for (int c = 0; c < 3; ++c) t1[c] -= dot * nh[c];
+                double nt = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+                for (int c = 0; c < 3; ++c) { t1[c] /= nt; g.ft1[3 * q + c] = t1[c]; }
+                g.ft2[3 * q + 0] = nh[1] * t1[2] - nh[2] * t1[1];
+                g.ft2[3 * q + 1] = nh[2] * t1[0] - nh[0] * t1[2];
+                g.ft2[3 * q + 2] = nh[0] * t1[1] - nh[1] * t1[0];
+                surf += sp.w[a] * sp.w[b] * g.fjac[q];
+            }
+            g.fsurface[f] = surf;
+        }
+    }
+}
+
+}  // namespace h3d

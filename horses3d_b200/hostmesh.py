@@ -1,0 +1,154 @@
+"""ctypes front end of libh3dhost.so: the driver-side mesh/geometry the reference keeps in Fortran.
+
+Mirrors what the reference driver does before the time loop (sem%construct, DGSEMClass.f90:268-468):
+read or generate the mesh, build face connectivity with the boundary table of the control file,
+construct nodal storage and metric terms.  The arrays exposed here are, one to one, the arguments of
+the device C-ABI (include/h3d_gpu.h).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+GAUSS = 1
+GAUSSLOBATTO = 2
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build_host()
+        L = C.CDLL(path)
+        L.h3dhost_last_error.restype = C.c_char_p
+        L.h3dhost_mesh_box.restype = C.c_void_p
+        L.h3dhost_mesh_box.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_uint]
+        L.h3dhost_mesh_read.restype = C.c_void_p
+        L.h3dhost_mesh_read.argtypes = [C.c_char_p]
+        L.h3dhost_mesh_write.argtypes = [C.c_void_p, C.c_char_p]
+        L.h3dhost_mesh_free.argtypes = [C.c_void_p]
+        L.h3dhost_mesh_connect.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p]
+        L.h3dhost_mesh_geometry.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.h3dhost_mesh_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.h3dhost_get_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+        L.h3dhost_nodal.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7
+        L.h3dhost_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.h3dhost_extract_partition.restype = C.c_void_p
+        L.h3dhost_extract_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise HostError(lib().h3dhost_last_error().decode())
+
+
+PERIODIC_BOX_BCS = [
+    ("front", "periodic", "back"), ("back", "periodic", "front"),
+    ("bottom", "periodic", "top"), ("top", "periodic", "bottom"),
+    ("left", "periodic", "right"), ("right", "periodic", "left"),
+]
+
+
+class NodalStorage:
+    """1-D operators of one polynomial order (NodalStorageClass.f90:24-52)."""
+
+    def __init__(self, N, nodes=GAUSS):
+        n = N + 1
+        self.N, self.nodes, self.n = N, nodes, n
+        self.x, self.w = np.zeros(n), np.zeros(n)
+        self.D, self.hatD, self.sharpD = np.zeros((n, n)), np.zeros((n, n)), np.zeros((n, n))
+        self.v, self.b = np.zeros((2, n)), np.zeros((2, n))
+        _check(lib().h3dhost_nodal(N, nodes, *[a.ctypes.data for a in (self.x, self.w, self.D, self.hatD, self.sharpD, self.v, self.b)]))
+
+
+class HostMesh:
+    """Driver-side HexMesh: raw mesh -> connectivity -> geometry (flat numpy views on C++ storage)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise HostError(lib().h3dhost_last_error().decode())
+        self._h = C.c_void_p(handle)
+        self.halo = None
+
+    # --- constructors
+    @classmethod
+    def box(cls, ne, L=2.0 * np.pi, amp=0.0, bFaceOrder=2, shuffle=False, seed=1234, ney=None, nez=None):
+        return cls(lib().h3dhost_mesh_box(ne, ney or ne, nez or ne, L, amp, bFaceOrder, int(shuffle), seed))
+
+    @classmethod
+    def read(cls, path):
+        return cls(lib().h3dhost_mesh_read(os.fsencode(path)))
+
+    def write(self, path):
+        _check(lib().h3dhost_mesh_write(self._h, os.fsencode(path)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().h3dhost_mesh_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # --- pipeline
+    def connect(self, bcs=PERIODIC_BOX_BCS, params=None):
+        nb = len(bcs)
+        names = (C.c_char_p * nb)(*[b[0].encode() for b in bcs])
+        types = (C.c_char_p * nb)(*[b[1].encode() for b in bcs])
+        coupled = (C.c_char_p * nb)(*[(b[2] or "").encode() for b in bcs])
+        p = None
+        if params is not None:
+            p = np.ascontiguousarray(params, dtype=np.float64).reshape(nb, 16)
+        _check(lib().h3dhost_mesh_connect(self._h, nb, names, types, coupled, p.ctypes.data if p is not None else None))
+        self.bcs = list(bcs)
+        self.bc_params = p
+        return self
+
+    def geometry(self, N, nodes=GAUSS):
+        _check(lib().h3dhost_mesh_geometry(self._h, N, nodes))
+        self.N, self.nodes = N, nodes
+        return self
+
+    def sizes(self):
+        a = [C.c_int() for _ in range(4)]
+        lib().h3dhost_mesh_sizes(self._h, *[C.byref(x) for x in a])
+        return tuple(x.value for x in a)
+
+    @property
+    def nElem(self):
+        return self.sizes()[0]
+
+    @property
+    def nFaces(self):
+        return self.sizes()[1]
+
+    def array(self, name):
+        ptr, cnt, isint = C.c_void_p(), C.c_longlong(), C.c_int()
+        _check(lib().h3dhost_get_array(self._h, name.encode(), C.byref(ptr), C.byref(cnt), C.byref(isint)))
+        if cnt.value == 0:
+            return np.zeros(0, dtype=np.int32 if isint.value else np.float64)
+        ct = C.c_int32 if isint.value else C.c_double
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(cnt.value,))
+        return arr   # a VIEW of the C++ storage: keep this HostMesh alive while it is in use
+
+    # --- partitioning
+    def partition(self, nparts, method="metis"):
+        part = np.zeros(self.nElem, dtype=np.int32)
+        _check(lib().h3dhost_partition(self._h, nparts, 0 if method == "metis" else 1, part.ctypes.data))
+        return part
+
+    def extract(self, part, rank):
+        part = np.ascontiguousarray(part, dtype=np.int32)
+        child = HostMesh(lib().h3dhost_extract_partition(self._h, part.ctypes.data, rank))
+        child.bcs = getattr(self, "bcs", [])
+        child.bc_params = getattr(self, "bc_params", None)
+        return child
