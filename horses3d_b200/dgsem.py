@@ -1,0 +1,159 @@
+"""Host-side mirror of the reference's driver objects for the explicit NS path.
+
+`DGSem` plays the part of the reference's DGSem + TimeIntegrator_t for the hot path only: it hands mesh,
+basis and physics to a backend that implements the C ABI of include/h3d_gpu.h and exposes the reference's
+procedure names with the reference's argument meaning:
+
+    ComputeTimeDerivative(time)              SpatialDiscretization.f90:227   (ComputeTimeDerivative_f)
+    TakeRK3Step(t, dt) / TakeRK5Step(t, dt)  ExplicitMethods.f90:667, 790    (TimeStep_FCN)
+    MaxTimeStep(cfl, dcfl)                   DGSEMClass.f90:870
+    ComputeMaxResiduals()                    DGSEMClass.f90:770
+    ScalarVolumeIntegral(kind)               VolumeIntegrals.f90:76
+    checkForNan()                            ExplicitMethods.f90:1856
+    integrate(...)                           TimeIntegrator.f90:667-673, 737-959 (explicit branch)
+
+The backend is an `Api` (capi.py).  The product backend is GpuApi; tests pass the CPU oracle's Api to run
+the very same driver code against the restated reference algorithm.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import physics as P
+from .capi import _ptr
+from .hostmesh import NodalStorage
+
+
+def taylor_green_ic(x, gamma=1.4, L=1.0, u0=1.0, rho0=1.0, p0=100.0):
+    """UserDefinedInitialCondition of test/NavierStokes/TaylorGreen/SETUP/ProblemFile.f90:107-138.  x: [...,3]."""
+    X, Y, Z = x[..., 0], x[..., 1], x[..., 2]
+    rho = rho0 * np.ones_like(X)
+    u = u0 * np.sin(X / L) * np.cos(Y / L) * np.cos(Z / L)
+    v = -u0 * np.cos(X / L) * np.sin(Y / L) * np.cos(Z / L)
+    w = np.zeros_like(X)
+    p = p0 + rho0 / 16.0 * (np.cos(2.0 * X / L) * np.cos(2.0 * Z / L) + 2.0 * np.cos(2.0 * Y / L) + 2.0 * np.cos(2.0 * X / L)
+                            + np.cos(2.0 * Y / L) * np.cos(2.0 * Z / L))
+    Q = np.empty(x.shape[:-1] + (5,))
+    Q[..., 0] = rho
+    Q[..., 1] = rho * u
+    Q[..., 2] = rho * v
+    Q[..., 3] = rho * w
+    Q[..., 4] = p / (gamma - 1.0) + 0.5 * rho * (u * u + v * v + w * w)
+    return Q
+
+
+class DGSem:
+    def __init__(self, api, mesh, physics):
+        self.api, self.mesh, self.physics = api, mesh, physics
+        self.N, self.n = mesh.N, mesh.N + 1
+        self.nElem, self.nFaces = mesh.nElem, mesh.nFaces
+        self.NDOF = self.nElem * self.n ** 3            # nodes, as the reference counts them (main.f90:360)
+        self.sp = NodalStorage(mesh.N, mesh.nodes)
+        api.set_physics(physics)
+        api.set_basis(self.sp)
+        api.set_mesh(mesh)
+        bcs = getattr(mesh, "bcs", [])
+        if bcs:
+            types = [P.BC_TYPES[b[1].lower()] for b in bcs]
+            params = mesh.bc_params if mesh.bc_params is not None else np.zeros((len(bcs), 16))
+            api.set_boundary_conditions(types, params)
+        counts = mesh.array("haloCount")
+        if len(counts) and hasattr(api, "set_halo"):
+            api.set_halo(mesh.array("haloRank"), counts, mesh.array("haloFace"), mesh.array("haloSide"))
+        self._shape = (self.nElem, self.n, self.n, self.n, 5)
+
+    # ---- state
+    def node_coordinates(self):
+        return self.mesh.array("x").reshape(self.nElem, self.n, self.n, self.n, 3)
+
+    def set_Q(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(self._shape)
+        self.api.call("upload_Q", _ptr(Q, np.float64))
+
+    def set_initial_condition(self, fn, **kw):
+        self.set_Q(fn(self.node_coordinates(), **kw))
+
+    def set_source(self, S):
+        if S is None:
+            self.api.call("set_source", None)
+        else:
+            S = np.ascontiguousarray(S, dtype=np.float64).reshape(self._shape)
+            self.api.call("set_source", _ptr(S, np.float64))
+
+    def download(self, Q=False, QDot=False, gradients=False):
+        out = {}
+        bufs = [None] * 5
+        names = ["Q", "QDot", "U_x", "U_y", "U_z"]
+        want = [Q, QDot, gradients, gradients, gradients]
+        for i, wnt in enumerate(want):
+            if wnt:
+                out[names[i]] = np.empty(self._shape)
+                bufs[i] = _ptr(out[names[i]], np.float64)
+        self.api.call("download", *bufs)
+        return out
+
+    def Q(self):
+        return self.download(Q=True)["Q"]
+
+    def QDot(self):
+        return self.download(QDot=True)["QDot"]
+
+    # ---- the reference's procedures
+    def ComputeTimeDerivative(self, time=0.0):
+        self.api.call("compute_time_derivative", float(time))
+
+    def TakeRK3Step(self, t, dt, ctd_after_step=False):
+        self.api.call("rk_step", P.RK3, float(t), float(dt), int(ctd_after_step))
+
+    def TakeRK5Step(self, t, dt, ctd_after_step=False):
+        self.api.call("rk_step", P.RK5, float(t), float(dt), int(ctd_after_step))
+
+    def MaxTimeStep(self, cfl, dcfl):
+        a, b = C.c_double(), C.c_double()
+        self.api.call("max_timestep", float(cfl), float(dcfl), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def ComputeMaxResiduals(self):
+        r = np.zeros(5)
+        self.api.call("max_residuals", _ptr(r, np.float64))
+        return r
+
+    def ScalarVolumeIntegral(self, kind):
+        v = C.c_double()
+        self.api.call("volume_integral", int(kind), C.byref(v))
+        return v.value
+
+    def checkForNan(self):
+        f = C.c_int()
+        self.api.call("has_nan", C.byref(f))
+        return bool(f.value)
+
+    def volume_monitors(self):
+        """VolumeMonitor_Update (libs/monitors/VolumeMonitor.f90:297-309)."""
+        vol = self.ScalarVolumeIntegral(P.INT_VOLUME)
+        return {
+            "kinetic energy": self.ScalarVolumeIntegral(P.INT_KINETIC_ENERGY) / vol,
+            "kinetic energy rate": self.ScalarVolumeIntegral(P.INT_KINETIC_ENERGY_RATE) / vol,
+            "enstrophy": 0.5 * self.ScalarVolumeIntegral(P.INT_ENSTROPHY) / vol,
+        }
+
+    def integrate(self, nsteps, cfl=None, dcfl=None, dt=None, t0=0.0, scheme="RK3", monitors=True):
+        """Explicit branch of TimeIntegrator_t%integrate: initial residual, then per step
+        MaxTimeStep -> RKStep -> ComputeMaxResiduals -> monitors (TimeIntegrator.f90:667-673, 737-959).
+        Returns a list of per-step records (the reference's monitor buffer lines)."""
+        step = self.TakeRK3Step if scheme.upper() == "RK3" else self.TakeRK5Step
+        t = t0
+        self.ComputeTimeDerivative(t)
+        rec = [dict(iter=0, t=t, dt=0.0, residuals=self.ComputeMaxResiduals(), **(self.volume_monitors() if monitors else {}))]
+        for k in range(nsteps):
+            if dt is None:
+                dtc, dtv = self.MaxTimeStep(cfl, dcfl if dcfl is not None else cfl)
+                step_dt = dtc if dtc < dtv else dtv       # DGSEMClass.f90:1025-1031
+            else:
+                step_dt = dt
+            step(t, step_dt)
+            t = t + step_dt
+            if self.checkForNan():
+                raise FloatingPointError("Numerical divergence obtained in solver.")
+            rec.append(dict(iter=k + 1, t=t, dt=step_dt, residuals=self.ComputeMaxResiduals(), **(self.volume_monitors() if monitors else {})))
+        return rec

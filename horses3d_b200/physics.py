@@ -1,0 +1,59 @@
+"""H3dPhysics (include/h3d_gpu.h) and its construction from control-file values.
+
+Follows ConstructPhysicsStorage_NS (libs/physics/navierstokes/PhysicsStorage_NS.f90:143-435) and
+SetRiemannSolver (RiemannSolvers_NS.f90:120-286): same defaults, same arithmetic for the derived constants.
+"""
+import ctypes as C
+
+STANDARD_DG, SPLIT_DG = 0, 1
+RIEMANN = {"roe": 0, "lax-friedrichs": 1, "central": 2, "rusanov": 3, "standard roe": 4}
+AVERAGING = {"standard": 0, "kennedy-gruber": 1, "pirozzoli": 2, "ducros": 3, "morinishi": 4}
+LES = {"none": 0, "smagorinsky": 1}
+
+INT_VOLUME, INT_KINETIC_ENERGY, INT_KINETIC_ENERGY_RATE, INT_ENSTROPHY = 0, 1, 2, 3
+RK3, RK5 = 3, 5
+FACE_INTERIOR, FACE_BOUNDARY, FACE_MPI = 1, 2, 3
+BC_TYPES = {"periodic": 0, "noslipwall": 1, "freeslipwall": 2, "inflow": 3, "outflow": 4}
+
+
+class H3dPhysics(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "gamma", "gammaMinus1", "Mach", "Re", "Pr", "mu", "kappa", "mu_to_kappa", "gammaM2",
+        "S_div_Tref", "T_renorm", "lambdaStab", "smagorinsky_Cs", "Prt")] + [(k, C.c_int) for k in (
+        "flowIsNavierStokes", "computeGradients", "inviscid", "riemann", "averaging", "les")] + [("reserved", C.c_int * 2)]
+
+
+def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="standard", riemann="roe",
+                 averaging="standard", lambda_stab=1.0, compute_gradients=None, les="none", smagorinsky_cs=0.2,
+                 sutherland_temperature=None, reference_temperature=None, sutherland_ref_temperature=None):
+    p = H3dPhysics()
+    gamma = 1.4
+    gm1 = 1.4 - 1.0                                   # PhysicsStorage_NS.f90:120 (not 0.4)
+    p.gamma, p.gammaMinus1, p.Mach, p.Pr, p.Prt = gamma, gm1, mach, prandtl, prandtl
+    ns = flow.lower() != "euler"
+    if ns:
+        p.Re = reynolds
+        if reynolds != 0.0:
+            p.mu = 1.0 / reynolds                      # :240
+            p.kappa = 1.0 / (gm1 * (mach * mach) * reynolds * prandtl)   # :241-243
+        p.mu_to_kappa = 1.0 / (gm1 * (mach * mach) * prandtl)            # :250
+    if les.lower() != "none":
+        ns = True                                      # :405-414
+        compute_gradients = True
+    p.flowIsNavierStokes = int(ns)
+    if compute_gradients is None:
+        compute_gradients = ns                         # :255-275
+    p.computeGradients = int(bool(compute_gradients) or ns)
+    p.gammaM2 = gamma * (mach * mach)                  # :285
+    Tref = reference_temperature if reference_temperature is not None else 520.0 * 5.0 / 9.0       # :294
+    S = sutherland_temperature if sutherland_temperature is not None else 198.6 * 5.0 / 9.0          # :419
+    TrefS = sutherland_ref_temperature if sutherland_ref_temperature is not None else Tref         # :425
+    p.S_div_Tref = S / TrefS
+    p.T_renorm = Tref / TrefS
+    p.inviscid = {"standard": STANDARD_DG, "split-form": SPLIT_DG}[inviscid.lower()]
+    p.riemann = RIEMANN[riemann.lower()]
+    p.averaging = AVERAGING[averaging.lower()]
+    p.lambdaStab = 0.0 if p.riemann == RIEMANN["central"] else lambda_stab    # RiemannSolvers_NS.f90:211-224
+    p.les = LES[les.lower()]
+    p.smagorinsky_Cs = smagorinsky_cs
+    return p

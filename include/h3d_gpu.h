@@ -1,0 +1,191 @@
+/* h3d_gpu.h -- C ABI of libh3dgpu.so, the B200 (sm_100a) replacement for HORSES3D's explicit
+ * compressible Navier-Stokes residual and low-storage Runge-Kutta step.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to
+ * /root/reference/Solver/src).  A Fortran driver binds these through ISO_C_BINDING (see
+ * INTEGRATION.md); nothing here depends on torch, C++ or CUDA types.
+ *
+ * Conventions
+ *   - all entry points return 0 on success, non-zero on error; h3d_last_error() gives the message
+ *     (reference: errorMessage(STD_OUT) + error stop, libs/foundation/Includes.h:5).
+ *   - indices are 0-based; "none" is -1 (the Fortran adapter subtracts 1 in its gather loops).
+ *   - local faces 0..5 = EFRONT,EBACK,EBOTTOM,ERIGHT,ETOP,ELEFT (libs/mesh/MeshTypes.f90:17-18).
+ *   - face sides 0/1 = left/right (FaceClass.f90:76).
+ *   - element fields use the reference's own per-element order, elements concatenated in local ID
+ *     order: A[e][k][j][i][c], c fastest (StorageClass.f90:63-67,423-429).  Face fields: A[f][j][i][c].
+ *   - all floating point is double (RP, libs/foundation/SMConstants.f90:9-12).
+ *   - one context <-> one rank <-> one GPU; calls are asynchronous on the context's CUDA streams and
+ *     synchronise only where a scalar or a host buffer is returned.
+ */
+#ifndef H3D_GPU_H
+#define H3D_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct h3d_context* h3d_handle;
+
+/* node sets (libs/spectral/NodalStorageClass.f90:16-17) */
+#define H3D_GAUSS 1
+#define H3D_GAUSSLOBATTO 2
+
+/* inviscid discretization (NavierStokesSolver/SpatialDiscretization.f90:85-99) */
+#define H3D_STANDARD_DG 0
+#define H3D_SPLIT_DG 1
+
+/* Riemann solvers (libs/physics/navierstokes/RiemannSolvers_NS.f90:120-206) */
+#define H3D_RIEMANN_ROE 0
+#define H3D_RIEMANN_LXF 1
+#define H3D_RIEMANN_CENTRAL 2
+#define H3D_RIEMANN_RUSANOV 3
+#define H3D_RIEMANN_STDROE 4
+
+/* averaging / two-point flux (RiemannSolvers_NS.f90:233-285) */
+#define H3D_AVG_STANDARD 0
+#define H3D_AVG_KENNEDYGRUBER 1
+#define H3D_AVG_PIROZZOLI 2
+#define H3D_AVG_DUCROS 3
+#define H3D_AVG_MORINISHI 4
+
+/* LES (libs/physics/common/LESModels.f90) */
+#define H3D_LES_NONE 0
+#define H3D_LES_SMAGORINSKY 1
+
+/* face types (libs/mesh/MeshTypes.f90:21-25) */
+#define H3D_FACE_INTERIOR 1
+#define H3D_FACE_BOUNDARY 2
+#define H3D_FACE_MPI 3
+
+/* boundary conditions (libs/physics/common, the BC class files); parameters: 16 doubles per zone */
+#define H3D_BC_PERIODIC 0      /* never reaches the device: merged into interior faces at mesh build */
+#define H3D_BC_NOSLIPWALL 1    /* params: [0..2] wall velocity, [3] isAdiabatic (1) or isothermal (0) */
+#define H3D_BC_FREESLIPWALL 2  /* params: [3] isAdiabatic */
+#define H3D_BC_INFLOW 3        /* params: [0] rho, [1..3] u,v,w, [4] p  (non-dimensional) */
+#define H3D_BC_OUTFLOW 4       /* params: [0] rho, [1..3] u,v,w, [4] p  (non-dimensional external state) */
+
+/* volume integrals (libs/monitors/VolumeIntegrals.f90:30-60) */
+#define H3D_INT_VOLUME 0
+#define H3D_INT_KINETIC_ENERGY 1
+#define H3D_INT_KINETIC_ENERGY_RATE 2
+#define H3D_INT_ENSTROPHY 3
+
+/* RK schemes (libs/timeintegrator/ExplicitMethods.f90:667,790) */
+#define H3D_RK3 3
+#define H3D_RK5 5
+
+/* Run-time physics: the protected module variables the reference's kernels read
+ * (libs/physics/navierstokes/PhysicsStorage_NS.f90:81-131,190-250,285,416-429;
+ *  FluidData_NS thermodynamics/dimensionless; RiemannSolvers_NS.f90:107-113). */
+typedef struct H3dPhysics {
+    double gamma;            /* thermodynamics % gamma                          */
+    double gammaMinus1;      /* thermodynamics % gammaMinus1  (1.4 - 1.0)       */
+    double Mach;             /* dimensionless % Mach                            */
+    double Re;               /* dimensionless % Re                              */
+    double Pr;               /* dimensionless % Pr                              */
+    double mu;               /* dimensionless % mu     = 1/Re                   */
+    double kappa;            /* dimensionless % kappa                           */
+    double mu_to_kappa;      /* dimensionless % mu_to_kappa                     */
+    double gammaM2;          /* dimensionless % gammaM2                         */
+    double S_div_Tref;       /* S_div_TRef_Sutherland                           */
+    double T_renorm;         /* TemperatureReNormalization_Sutherland           */
+    double lambdaStab;       /* RiemannSolvers_NS lambdaStab (0 for central)    */
+    double smagorinsky_Cs;   /* LESModels.f90 Smagorinsky CS                    */
+    double Prt;              /* dimensionless % Prt                             */
+    int flowIsNavierStokes;  /* 0 = Euler                                       */
+    int computeGradients;    /* PhysicsStorage_NS computeGradients              */
+    int inviscid;            /* H3D_STANDARD_DG | H3D_SPLIT_DG                  */
+    int riemann;             /* H3D_RIEMANN_*                                   */
+    int averaging;           /* H3D_AVG_*                                       */
+    int les;                 /* H3D_LES_*                                       */
+    int reserved[2];
+} H3dPhysics;
+
+/* ---- life cycle ------------------------------------------------------------------------------
+ * replaces MPI_Process % Init / mpi_init (libs/mpiutils/process_info.f90:24-64).  nccl_unique_id is the
+ * 128-byte ncclUniqueId broadcast by the host (NULL when nranks == 1). */
+int h3d_get_nccl_unique_id(void* id128);
+int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nccl_unique_id);
+int h3d_destroy(h3d_handle h);
+const char* h3d_last_error(h3d_handle h);                 /* h may be NULL: creation errors */
+int h3d_last_error_copy(h3d_handle h, char* buf, int len); /* Fortran-friendly copy           */
+
+/* ---- set-up (once) ---------------------------------------------------------------------------*/
+/* ConstructPhysicsStorage + Initialize_SpaceAndTimeMethods (NavierStokesSolver/main.f90:90,144) */
+int h3d_set_physics(h3d_handle h, const H3dPhysics* p);
+
+/* NodalStorage(N) (libs/spectral/NodalStorageClass.f90:24-52).  Matrices row-major M[i*(N+1)+l] = M(i,l);
+ * v,b: [side*(N+1)+i], side 0 = LEFT/FRONT/BOTTOM (-1 end), 1 = RIGHT/BACK/TOP (+1 end).  Uniform order only. */
+int h3d_set_basis(h3d_handle h, int N, int nodeType, const double* x, const double* w, const double* D,
+                  const double* hatD, const double* sharpD, const double* v, const double* b);
+
+/* HexMesh connectivity + MappedGeometry / MappedGeometryFace (libs/mesh/HexMesh.f90:2399,2677;
+ * MappedGeometry.f90:24-55; FaceClass.f90:63-81; HexElementClass.f90:60-75). */
+int h3d_set_mesh(h3d_handle h, int nElem, int nFace,
+                 const int* elemFace,      /* [nElem][6]  face id of each local face          (e % faceIDs)   */
+                 const int* elemFaceSide,  /* [nElem][6]  side of the element on that face     (e % faceSide)  */
+                 const int* faceElem,      /* [nFace][2]  element ids, -1 = none               (f % elementIDs)*/
+                 const int* faceElemSide,  /* [nFace][2]  local face ids                        (f % elementSide)*/
+                 const int* faceRot,       /* [nFace]     0..7                                  (f % rotation)  */
+                 const int* faceType,      /* [nFace]     H3D_FACE_*                            (f % faceType)  */
+                 const int* faceZone,      /* [nFace]     boundary zone or -1                   (f % zone)      */
+                 const double* jGradXi, const double* jGradEta, const double* jGradZeta, /* [e][k][j][i][3] */
+                 const double* jacobian,   /* [e][k][j][i]                                                     */
+                 const double* x,          /* [e][k][j][i][3]  node coordinates (sources, BCs) - may be NULL   */
+                 const double* volume,     /* [e]              e % geom % Volume (LES filter width) - may be NULL */
+                 const double* faceNormal, const double* faceT1, const double* faceT2, /* [f][j][i][3]       */
+                 const double* faceJacobian, /* [f][j][i]                                                       */
+                 const double* faceX,      /* [f][j][i][3]  may be NULL                                        */
+                 const double* faceSurface /* [f]           f % geom % surface (LES) - may be NULL             */);
+
+/* BCs(zone) % bc (libs/physics/common/BoundaryConditions.f90): type + 16 parameters per zone */
+int h3d_set_boundary_conditions(h3d_handle h, int nZones, const int* bcType, const double* bcParams);
+
+/* MPIfaces (libs/mpiutils/MPI_Face.f90:16-57; HexMesh.f90:2571-2668).  For each neighbour rank the list of
+ * local MPI faces IN EXCHANGE ORDER (both ranks must list the shared faces in the same order) and the side
+ * the local element occupies on each. */
+int h3d_set_halo(h3d_handle h, int nNeighbors, const int* neighborRank, const int* faceCount,
+                 const int* faceIDs, const int* thisSide);
+
+/* ---- state ---------------------------------------------------------------------------------- */
+/* global2LocalQ / local2GlobalQ (libs/mesh/StorageClass.f90:390-440,549-579): packed [e][k][j][i][5] */
+int h3d_upload_Q(h3d_handle h, const double* Q);
+/* any pointer may be NULL.  Ux,Uy,Uz are e % storage % U_x,U_y,U_z of the last residual evaluation. */
+int h3d_download(h3d_handle h, double* Q, double* QDot, double* Ux, double* Uy, double* Uz);
+/* e % storage % S_NS evaluated by the host (UserDefinedSourceTermNS, SpatialDiscretization.f90:569-577);
+ * NULL clears it.  Kept until replaced. */
+int h3d_set_source(h3d_handle h, const double* S);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* ComputeTimeDerivative(mesh, particles, time, mode)  (SpatialDiscretization.f90:227-320;
+ * interface ComputeTimeDerivative_f, libs/discretization/DGSEMClass.f90:77-95).  Result: QDot (device). */
+int h3d_compute_time_derivative(h3d_handle h, double time);
+
+/* TakeRK3Step / TakeRK5Step (libs/timeintegrator/ExplicitMethods.f90:667-788,790-882; interface
+ * TimeStep_FCN, TimeIntegratorDefinitions.f90:10-35).  ctd_after_step = CTD_AFTER_STEPS (:784). */
+int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_step);
+
+/* ---- per-step reductions (all globally reduced over ranks) ----------------------------------- */
+/* ComputeMaxResiduals (libs/discretization/DGSEMClass.f90:770-856) */
+int h3d_max_residuals(h3d_handle h, double out[5]);
+/* MaxTimeStep (DGSEMClass.f90:870-1034): returns both restrictions, caller takes the min */
+int h3d_max_timestep(h3d_handle h, double cfl, double dcfl, double* dt_conv, double* dt_visc);
+/* ScalarVolumeIntegral (libs/monitors/VolumeIntegrals.f90:76-120,167-286): raw integral, H3D_INT_* */
+int h3d_volume_integral(h3d_handle h, int kind, double* val);
+/* checkForNan (ExplicitMethods.f90:1856-1905): flag = 1 if any NaN in Q on any rank */
+int h3d_has_nan(h3d_handle h, int* flag);
+
+/* ---- utilities ------------------------------------------------------------------------------ */
+int h3d_synchronize(h3d_handle h);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long h3d_kernel_launches(h3d_handle h);
+/* CUDA-event timing of work enqueued between begin/end on the compute stream, in milliseconds */
+int h3d_timer_begin(h3d_handle h);
+int h3d_timer_end(h3d_handle h, double* ms);
+/* option string "key=value" (e.g. "store_qdot_every_stage=1"); unknown keys are an error */
+int h3d_set_option(h3d_handle h, const char* key_value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H3D_GPU_H */

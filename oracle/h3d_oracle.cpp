@@ -1,0 +1,999 @@
+// ======================================================================================================
+//  TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+//  CPU restatement ("oracle") of HORSES3D's explicit compressible Navier-Stokes residual and RK step.
+//  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+//
+//  It restates the reference algorithm loop by loop, in the reference's own accumulation order, in plain
+//  C++ compiled with -ffp-contract=off (the reference's gfortran RELEASE build emits no FMA).  Every
+//  routine cites the Fortran it follows (paths relative to /root/reference/Solver/src).
+//
+//  Parity pins (see tests/test_oracle_pins.py): K6 quadrature/derivative exactness
+//  (test/Components/NodalStorage/src/NodalStorageTests.f90:23-59) and K1 Taylor-Green residuals and
+//  monitors after 5 RK3 steps (test/NavierStokes/TaylorGreen/SETUP/ProblemFile.f90:317-366).
+//  The reference itself cannot be built in this container (no Fortran compiler), so there is no
+//  oracle/_ref; parity with the reference rests on those pins.
+// ======================================================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../include/h3d_gpu.h"
+
+namespace {
+
+constexpr int NCONS = 5, NGRAD = 5, NDIM = 3;
+constexpr int IRHO = 0, IRHOU = 1, IRHOV = 2, IRHOW = 3, IRHOE = 4;
+constexpr int IX = 0, IY = 1, IZ = 2;
+enum { EFRONT = 0, EBACK = 1, EBOTTOM = 2, ERIGHT = 3, ETOP = 4, ELEFT = 5 };
+inline double POW2(double x) { return x * x; }
+
+// ---- MeshTypes.f90:70-108
+inline void leftIndexes2Right(int i, int j, int Nx, int Ny, int rot, int& ii, int& jj) {
+    switch (rot) {
+        case 0: ii = i; jj = j; break;
+        case 1: ii = Ny - j; jj = i; break;
+        case 2: ii = Nx - i; jj = Ny - j; break;
+        case 3: ii = j; jj = Nx - i; break;
+        case 4: ii = j; jj = i; break;
+        case 5: ii = Nx - i; jj = j; break;
+        case 6: ii = Ny - j; jj = Nx - i; break;
+        default: ii = i; jj = Ny - j; break;
+    }
+}
+
+struct Oracle {
+    std::string err;
+    H3dPhysics ph{};
+    // basis
+    int N = -1, n = 0, nodeType = H3D_GAUSS;
+    std::vector<double> x, w, D, hatD, sharpD, v, b;
+    // mesh
+    int nElem = 0, nFace = 0;
+    std::vector<int> elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone;
+    std::vector<double> JaXi, JaEta, JaZeta, jac, invJac, xyz, volume;
+    std::vector<double> fNormal, fT1, fT2, fJac, fX, fSurface;
+    int nZones = 0; std::vector<int> bcType; std::vector<double> bcParams;
+    // element storage (reference order [e][k][j][i][eq])
+    std::vector<double> Q, QDot, G, S, Ux, Uy, Uz, mu;   // mu: [e][node][2] = (mu, kappa)
+    bool hasSource = false;
+    // face storage [f][side][j][i][...]
+    std::vector<double> fQ, fUx, fUy, fUz, fStar, fmu, unStar;  // unStar: [f][side][j][i][3][5]
+    int n2() const { return n * n; }
+    int n3() const { return n * n * n; }
+};
+
+// ------------------------------------------------------------------------------------------------
+//  Physics (libs/physics/navierstokes)
+// ------------------------------------------------------------------------------------------------
+// Physics_NS.f90:51-97
+inline void EulerFlux(const Oracle& o, const double* Q, double F[NCONS][NDIM]) {
+    const double gm1 = o.ph.gammaMinus1;
+    double u = Q[IRHOU] / Q[IRHO], v = Q[IRHOV] / Q[IRHO], w = Q[IRHOW] / Q[IRHO];
+    double p = gm1 * (Q[IRHOE] - 0.5 * (Q[IRHOU] * u + Q[IRHOV] * v + Q[IRHOW] * w));
+    F[IRHO][IX] = Q[IRHOU]; F[IRHOU][IX] = Q[IRHOU] * u + p; F[IRHOV][IX] = Q[IRHOU] * v; F[IRHOW][IX] = Q[IRHOU] * w; F[IRHOE][IX] = (Q[IRHOE] + p) * u;
+    F[IRHO][IY] = Q[IRHOV]; F[IRHOU][IY] = F[IRHOV][IX]; F[IRHOV][IY] = Q[IRHOV] * v + p; F[IRHOW][IY] = Q[IRHOV] * w; F[IRHOE][IY] = (Q[IRHOE] + p) * v;
+    F[IRHO][IZ] = Q[IRHOW]; F[IRHOU][IZ] = F[IRHOW][IX]; F[IRHOV][IZ] = F[IRHOW][IY]; F[IRHOW][IZ] = Q[IRHOW] * w + p; F[IRHOE][IZ] = (Q[IRHOE] + p) * w;
+}
+
+// Physics_NS.f90:246-304
+inline void ViscousFlux_STATE(const Oracle& o, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z,
+                              double mu, double beta, double kappa, double F[NCONS][NDIM]) {
+    const double gm1 = o.ph.gammaMinus1, gM2 = o.ph.gammaM2;
+    double invRho = 1.0 / Q[IRHO];
+    double u = Q[IRHOU] * invRho, v = Q[IRHOV] * invRho, w = Q[IRHOW] * invRho;
+    double uDivRho[3] = {u * invRho, v * invRho, w * invRho};
+    double u_x[3], u_y[3], u_z[3], nablaT[3];
+    for (int c = 0; c < 3; ++c) {
+        u_x[c] = invRho * Q_x[IRHOU + c] - uDivRho[c] * Q_x[IRHO];
+        u_y[c] = invRho * Q_y[IRHOU + c] - uDivRho[c] * Q_y[IRHO];
+        u_z[c] = invRho * Q_z[IRHOU + c] - uDivRho[c] * Q_z[IRHO];
+    }
+    nablaT[IX] = gm1 * gM2 * (invRho * Q_x[IRHOE] - Q[IRHOE] * invRho * invRho * Q_x[IRHO] - u * u_x[IX] - v * u_x[IY] - w * u_x[IZ]);
+    nablaT[IY] = gm1 * gM2 * (invRho * Q_y[IRHOE] - Q[IRHOE] * invRho * invRho * Q_y[IRHO] - u * u_y[IX] - v * u_y[IY] - w * u_y[IZ]);
+    nablaT[IZ] = gm1 * gM2 * (invRho * Q_z[IRHOE] - Q[IRHOE] * invRho * invRho * Q_z[IRHO] - u * u_z[IX] - v * u_z[IY] - w * u_z[IZ]);
+    double divV = u_x[IX] + u_y[IY] + u_z[IZ];
+    F[IRHO][IX] = 0.0;
+    F[IRHOU][IX] = mu * (2.0 * u_x[IX] - 2.0 / 3.0 * divV) + beta * divV;
+    F[IRHOV][IX] = mu * (u_x[IY] + u_y[IX]);
+    F[IRHOW][IX] = mu * (u_x[IZ] + u_z[IX]);
+    F[IRHOE][IX] = F[IRHOU][IX] * u + F[IRHOV][IX] * v + F[IRHOW][IX] * w + kappa * nablaT[IX];
+    F[IRHO][IY] = 0.0;
+    F[IRHOU][IY] = F[IRHOV][IX];
+    F[IRHOV][IY] = mu * (2.0 * u_y[IY] - 2.0 / 3.0 * divV) + beta * divV;
+    F[IRHOW][IY] = mu * (u_y[IZ] + u_z[IY]);
+    F[IRHOE][IY] = F[IRHOU][IY] * u + F[IRHOV][IY] * v + F[IRHOW][IY] * w + kappa * nablaT[IY];
+    F[IRHO][IZ] = 0.0;
+    F[IRHOU][IZ] = F[IRHOW][IX];
+    F[IRHOV][IZ] = F[IRHOW][IY];
+    F[IRHOW][IZ] = mu * (2.0 * u_z[IZ] - 2.0 / 3.0 * divV) + beta * divV;
+    F[IRHOE][IZ] = F[IRHOU][IZ] * u + F[IRHOV][IZ] * v + F[IRHOW][IZ] * w + kappa * nablaT[IZ];
+}
+
+// VariableConversion_NS.f90:50-64, 99-115, 166-186, 147-164
+inline double Pressure(const Oracle& o, const double* Q) {
+    return o.ph.gammaMinus1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
+}
+inline double Temperature(const Oracle& o, const double* Q) { return o.ph.gammaM2 * Pressure(o, Q) / Q[0]; }
+inline double SutherlandsLaw(const Oracle& o, double T) {
+    double tildeT = T * o.ph.T_renorm;
+    return (1.0 + o.ph.S_div_Tref) / (tildeT + o.ph.S_div_Tref) * tildeT * std::sqrt(tildeT);
+}
+inline void get_laminar_mu_kappa(const Oracle& o, const double* Q, double& mu, double& kappa) {
+    double T = Temperature(o, Q);
+    double suther = SutherlandsLaw(o, T);
+    mu = o.ph.mu * suther;
+    kappa = mu * o.ph.mu_to_kappa;
+}
+
+// VariableConversion_NS.f90:373-392
+inline void getVelocityGradients_State(const double* Q, const double* Q_x, const double* Q_y, const double* Q_z, double* U_x, double* U_y, double* U_z) {
+    double invRho = 1.0 / Q[IRHO], invRho2 = invRho * invRho;
+    double uDivRho[3] = {Q[IRHOU] * invRho2, Q[IRHOV] * invRho2, Q[IRHOW] * invRho2};
+    for (int c = 0; c < 3; ++c) {
+        U_x[c] = invRho * Q_x[IRHOU + c] - uDivRho[c] * Q_x[IRHO];
+        U_y[c] = invRho * Q_y[IRHOU + c] - uDivRho[c] * Q_y[IRHO];
+        U_z[c] = invRho * Q_z[IRHOU + c] - uDivRho[c] * Q_z[IRHO];
+    }
+}
+
+// LESModels.f90:256-305 (Smagorinsky, no wall damping: LESModels.f90:162-165 default)
+inline double SmagorinskyViscosity(const Oracle& o, double delta, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z) {
+    double U_x[3], U_y[3], U_z[3];
+    getVelocityGradients_State(Q, Q_x, Q_y, Q_z, U_x, U_y, U_z);
+    // |S|^2 = 2 Sij Sij
+    double normS = POW2(U_x[0]) + POW2(U_y[1]) + POW2(U_z[2]);
+    normS = 2.0 * normS + POW2(U_x[1] + U_y[0]) + POW2(U_x[2] + U_z[0]) + POW2(U_y[2] + U_z[1]);
+    normS = std::sqrt(normS);
+    double LS = o.ph.smagorinsky_Cs * delta;
+    return Q[IRHO] * POW2(LS) * normS;
+}
+
+// ---- averaging functions on rotated states (RiemannSolvers_NS.f90:1784-1962)
+inline void AveragedStates(const Oracle& o, const double* QL, const double* QR, double pL, double pR, double invRhoL, double invRhoR, double* flux) {
+    double uL = invRhoL * QL[IRHOU], uR = invRhoR * QR[IRHOU];
+    double vL = invRhoL * QL[IRHOV], vR = invRhoR * QR[IRHOV];
+    double wL = invRhoL * QL[IRHOW], wR = invRhoR * QR[IRHOW];
+    switch (o.ph.averaging) {
+        case H3D_AVG_STANDARD:
+            flux[IRHO] = 0.5 * (QL[IRHOU] + QR[IRHOU]);
+            flux[IRHOU] = 0.5 * (QL[IRHOU] * uL + QR[IRHOU] * uR + pL + pR);
+            flux[IRHOV] = 0.5 * (QL[IRHOU] * vL + QR[IRHOU] * vR);
+            flux[IRHOW] = 0.5 * (QL[IRHOU] * wL + QR[IRHOU] * wR);
+            flux[IRHOE] = 0.5 * (uL * (QL[IRHOE] + pL) + uR * (QR[IRHOE] + pR));
+            break;
+        case H3D_AVG_KENNEDYGRUBER: {
+            double rho = 0.5 * (QL[IRHO] + QR[IRHO]), u = 0.5 * (uL + uR), v = 0.5 * (vL + vR), w = 0.5 * (wL + wR), p = 0.5 * (pL + pR);
+            double e = 0.5 * (QL[IRHOE] * invRhoL + QR[IRHOE] * invRhoR);
+            flux[IRHO] = rho * u; flux[IRHOU] = rho * u * u + p; flux[IRHOV] = rho * u * v; flux[IRHOW] = rho * u * w; flux[IRHOE] = rho * u * e + p * u;
+        } break;
+        case H3D_AVG_PIROZZOLI: {
+            double rho = 0.5 * (QL[IRHO] + QR[IRHO]), u = 0.5 * (uL + uR), v = 0.5 * (vL + vR), w = 0.5 * (wL + wR), p = 0.5 * (pL + pR);
+            double h = 0.5 * ((QL[IRHOE] + pL) * invRhoL + (QR[IRHOE] + pR) * invRhoR);
+            flux[IRHO] = rho * u; flux[IRHOU] = rho * u * u + p; flux[IRHOV] = rho * u * v; flux[IRHOW] = rho * u * w; flux[IRHOE] = rho * u * h;
+        } break;
+        default: for (int q = 0; q < 5; ++q) flux[q] = std::numeric_limits<double>::quiet_NaN();
+    }
+}
+
+// RiemannSolvers_NS.f90:375-428
+inline void CentralRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, const double* t1, const double* t2, double* flux) {
+    const double gm1 = o.ph.gammaMinus1;
+    double rhoL = QLeft[0], rhoR = QRight[0], invRhoL = 1.0 / rhoL, invRhoR = 1.0 / rhoR;
+    double rhouL = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    double rhovL = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    double rhowL = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    double rhouR = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    double rhovR = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    double rhowR = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    double rhoeL = QLeft[4], rhoeR = QRight[4];
+    double rhoV2L = (POW2(rhouL) + POW2(rhovL) + POW2(rhowL)) * invRhoL;
+    double rhoV2R = (POW2(rhouR) + POW2(rhovR) + POW2(rhowR)) * invRhoR;
+    double pL = gm1 * (rhoeL - 0.5 * rhoV2L), pR = gm1 * (rhoeR - 0.5 * rhoV2R);
+    double QLRot[5] = {rhoL, rhouL, rhovL, rhowL, rhoeL}, QRRot[5] = {rhoR, rhouR, rhovR, rhowR, rhoeR};
+    AveragedStates(o, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
+// RiemannSolvers_NS.f90:1251-1334
+inline void LxFRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, const double* t1, const double* t2, double* flux) {
+    const double gamma = o.ph.gamma, gm1 = o.ph.gammaMinus1;
+    double rhoL = QLeft[0], rhoR = QRight[0], invRhoL = 1.0 / rhoL, invRhoR = 1.0 / rhoR;
+    double rhouL = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    double rhouR = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    double rhovL = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    double rhovR = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    double rhowL = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    double rhowR = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    double rhoV2L = (POW2(rhouL) + POW2(rhovL) + POW2(rhowL)) * invRhoL;
+    double rhoV2R = (POW2(rhouR) + POW2(rhovR) + POW2(rhowR)) * invRhoR;
+    double rhoeL = QLeft[4], rhoeR = QRight[4];
+    double pL = gm1 * (rhoeL - 0.5 * rhoV2L), pR = gm1 * (rhoeR - 0.5 * rhoV2R);
+    double aL = std::sqrt(gamma * pL * invRhoL), aR = std::sqrt(gamma * pR * invRhoR);
+    double lambda = std::fmax(std::fabs(rhouL * invRhoL) + aL, std::fabs(rhouR * invRhoR) + aR);
+    double QLRot[5] = {rhoL, rhouL, rhovL, rhowL, rhoeL}, QRRot[5] = {rhoR, rhouR, rhovR, rhowR, rhoeR};
+    AveragedStates(o, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    for (int q = 0; q < 5; ++q) { double stab = 0.5 * lambda * (QRRot[q] - QLRot[q]); flux[q] = flux[q] - o.ph.lambdaStab * stab; }
+    double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
+// RiemannSolvers_NS.f90:1541-1656
+inline void RoeRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, double* flux) {
+    const double gamma = o.ph.gamma, ds = 1.0;
+    double rho = QLeft[0], rhou = QLeft[1], rhov = QLeft[2], rhow = QLeft[3], rhoe = QLeft[4];
+    double rhon = QRight[0], rhoun = QRight[1], rhovn = QRight[2], rhown = QRight[3], rhoen = QRight[4];
+    double ul = rhou / rho, vl = rhov / rho, wl = rhow / rho;
+    double pleft = (gamma - 1.0) * (rhoe - 0.5 / rho * (rhou * rhou + rhov * rhov + rhow * rhow));
+    double ur = rhoun / rhon, vr = rhovn / rhon, wr = rhown / rhon;
+    double pright = (gamma - 1.0) * (rhoen - 0.5 / rhon * (rhoun * rhoun + rhovn * rhovn + rhown * rhown));
+    double ql = nHat[0] * ul + nHat[1] * vl + nHat[2] * wl;
+    double qr = nHat[0] * ur + nHat[1] * vr + nHat[2] * wr;
+    double hl = 0.5 * (ul * ul + vl * vl + wl * wl) + gamma / (gamma - 1.0) * pleft / rho;
+    double hr = 0.5 * (ur * ur + vr * vr + wr * wr) + gamma / (gamma - 1.0) * pright / rhon;
+    double rtd = std::sqrt(rho * rhon);
+    double betal = rho / (rho + rtd), betar = 1.0 - betal;
+    double utd = betal * ul + betar * ur, vtd = betal * vl + betar * vr, wtd = betal * wl + betar * wr, htd = betal * hl + betar * hr;
+    double atd2 = (gamma - 1.0) * (htd - 0.5 * (utd * utd + vtd * vtd + wtd * wtd));
+    double atd = std::sqrt(atd2);
+    double qtd = utd * nHat[0] + vtd * nHat[1] + wtd * nHat[2];
+    if (qtd >= 0.0) {
+        double dw1 = 0.5 * ((pright - pleft) / atd2 - (qr - ql) * rtd / atd);
+        double sp1 = qtd - atd;
+        double sp1m = std::fmin(sp1, 0.0);
+        double hd1m = ((gamma + 1.0) / 4.0 * atd / rtd) * dw1;
+        double eta1 = std::fmax(-std::fabs(sp1) - hd1m, 0.0);
+        double udw1 = dw1 * (sp1m - 0.5 * eta1);
+        double rql = rho * ql;
+        flux[0] = ds * (rql + udw1);
+        flux[1] = ds * (rql * ul + pleft * nHat[0] + udw1 * (utd - atd * nHat[0]));
+        flux[2] = ds * (rql * vl + pleft * nHat[1] + udw1 * (vtd - atd * nHat[1]));
+        flux[3] = ds * (rql * wl + pleft * nHat[2] + udw1 * (wtd - atd * nHat[2]));
+        flux[4] = ds * (rql * hl + udw1 * (htd - qtd * atd));
+    } else {
+        double dw4 = 0.5 * ((pright - pleft) / atd2 + (qr - ql) * rtd / atd);
+        double sp4 = qtd + atd;
+        double sp4p = std::fmax(sp4, 0.0);
+        double hd4 = ((gamma + 1.0) / 4.0 * atd / rtd) * dw4;
+        double eta4 = std::fmax(-std::fabs(sp4) + hd4, 0.0);
+        double udw4 = dw4 * (sp4p + 0.5 * eta4);
+        double rqr = rhon * qr;
+        flux[0] = ds * (rqr - udw4);
+        flux[1] = ds * (rqr * ur + pright * nHat[0] - udw4 * (utd + atd * nHat[0]));
+        flux[2] = ds * (rqr * vr + pright * nHat[1] - udw4 * (vtd + atd * nHat[1]));
+        flux[3] = ds * (rqr * wr + pright * nHat[2] - udw4 * (wtd + atd * nHat[2]));
+        flux[4] = ds * (rqr * hr - udw4 * (htd + qtd * atd));
+    }
+}
+
+inline void RiemannSolver(const Oracle& o, const double* QL, const double* QR, const double* nHat, const double* t1, const double* t2, double* flux) {
+    switch (o.ph.riemann) {
+        case H3D_RIEMANN_ROE: RoeRiemannSolver(o, QL, QR, nHat, flux); break;
+        case H3D_RIEMANN_LXF: LxFRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
+        case H3D_RIEMANN_CENTRAL: CentralRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
+        default: for (int q = 0; q < 5; ++q) flux[q] = std::numeric_limits<double>::quiet_NaN();
+    }
+}
+
+// ---- two-point fluxes (RiemannSolvers_NS.f90:2085-2145, 2296-2367, 2369-2437)
+inline void TwoPointFlux(const Oracle& o, const double* QL, const double* QR, const double* JaL, const double* JaR, double* fSharp) {
+    const double gm1 = o.ph.gammaMinus1;
+    double invRhoL = 1.0 / QL[IRHO], invRhoR = 1.0 / QR[IRHO];
+    double uL = invRhoL * QL[IRHOU], uR = invRhoR * QR[IRHOU];
+    double vL = invRhoL * QL[IRHOV], vR = invRhoR * QR[IRHOV];
+    double wL = invRhoL * QL[IRHOW], wR = invRhoR * QR[IRHOW];
+    double pL = gm1 * (QL[IRHOE] - 0.5 * (QL[IRHOU] * uL + QL[IRHOV] * vL + QL[IRHOW] * wL));
+    double pR = gm1 * (QR[IRHOE] - 0.5 * (QR[IRHOU] * uR + QR[IRHOV] * vR + QR[IRHOW] * wR));
+    double f[5], g[5], h[5], Ja[3];
+    if (o.ph.averaging == H3D_AVG_STANDARD) {
+        for (int c = 0; c < 3; ++c) Ja[c] = (JaL[c] + JaR[c]);
+        f[IRHO] = (QL[IRHOU] + QR[IRHOU]);
+        f[IRHOU] = (QL[IRHOU] * uL + QR[IRHOU] * uR + pL + pR);
+        f[IRHOV] = (QL[IRHOU] * vL + QR[IRHOU] * vR);
+        f[IRHOW] = (QL[IRHOU] * wL + QR[IRHOU] * wR);
+        f[IRHOE] = (uL * (QL[IRHOE] + pL) + uR * (QR[IRHOE] + pR));
+        g[IRHO] = (QL[IRHOV] + QR[IRHOV]);
+        g[IRHOU] = (QL[IRHOV] * uL + QR[IRHOV] * uR);
+        g[IRHOV] = (QL[IRHOV] * vL + QR[IRHOV] * vR + pL + pR);
+        g[IRHOW] = (QL[IRHOV] * wL + QR[IRHOV] * wR);
+        g[IRHOE] = (vL * (QL[IRHOE] + pL) + vR * (QR[IRHOE] + pR));
+        h[IRHO] = (QL[IRHOW] + QR[IRHOW]);
+        h[IRHOU] = (QL[IRHOW] * uL + QR[IRHOW] * uR);
+        h[IRHOV] = (QL[IRHOW] * vL + QR[IRHOW] * vR);
+        h[IRHOW] = (QL[IRHOW] * wL + QR[IRHOW] * wR + pL + pR);
+        h[IRHOE] = (wL * (QL[IRHOE] + pL) + wR * (QR[IRHOE] + pR));
+        for (int q = 0; q < 5; ++q) fSharp[q] = 0.25 * (f[q] * Ja[IX] + g[q] * Ja[IY] + h[q] * Ja[IZ]);
+        return;
+    }
+    double rho = 0.5 * (QL[IRHO] + QR[IRHO]), u = 0.5 * (uL + uR), v = 0.5 * (vL + vR), w = 0.5 * (wL + wR), p = 0.5 * (pL + pR);
+    for (int c = 0; c < 3; ++c) Ja[c] = 0.5 * (JaL[c] + JaR[c]);
+    if (o.ph.averaging == H3D_AVG_KENNEDYGRUBER) {
+        double e = 0.5 * (QL[IRHOE] * invRhoL + QR[IRHOE] * invRhoR);
+        f[IRHO] = rho * u; f[IRHOU] = rho * u * u + p; f[IRHOV] = rho * u * v; f[IRHOW] = rho * u * w; f[IRHOE] = rho * u * e + p * u;
+        g[IRHO] = rho * v; g[IRHOU] = rho * v * u; g[IRHOV] = rho * v * v + p; g[IRHOW] = rho * v * w; g[IRHOE] = rho * v * e + p * v;
+        h[IRHO] = rho * w; h[IRHOU] = rho * w * u; h[IRHOV] = rho * w * v; h[IRHOW] = rho * w * w + p; h[IRHOE] = rho * w * e + p * w;
+    } else if (o.ph.averaging == H3D_AVG_PIROZZOLI) {
+        double hh = 0.5 * ((QL[IRHOE] + pL) * invRhoL + (QR[IRHOE] + pR) * invRhoR);
+        f[IRHO] = rho * u; f[IRHOU] = rho * u * u + p; f[IRHOV] = rho * u * v; f[IRHOW] = rho * u * w; f[IRHOE] = rho * u * hh;
+        g[IRHO] = rho * v; g[IRHOU] = rho * v * u; g[IRHOV] = rho * v * v + p; g[IRHOW] = rho * v * w; g[IRHOE] = rho * v * hh;
+        h[IRHO] = rho * w; h[IRHOU] = rho * w * u; h[IRHOV] = rho * w * v; h[IRHOW] = rho * w * w + p; h[IRHOE] = rho * w * hh;
+    } else {
+        for (int q = 0; q < 5; ++q) f[q] = g[q] = h[q] = std::numeric_limits<double>::quiet_NaN();
+    }
+    for (int q = 0; q < 5; ++q) fSharp[q] = f[q] * Ja[IX] + g[q] * Ja[IY] + h[q] * Ja[IZ];
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Boundary conditions (libs/physics/common): state, gradient variables, Neumann flux
+// ------------------------------------------------------------------------------------------------
+// NoSlipWallBC.f90:265-296 (FlowState), :298-337 (FlowGradVars, STATE variables), :339-372 (FlowNeumann)
+// FreeSlipWallBC.f90:249-351 ; InflowBC.f90:363-425 ; OutflowBC.f90:226-300
+inline void BC_FlowState(const Oracle& o, int zone, const double* nHat, double* Q) {
+    const double* P = &o.bcParams[16 * zone];
+    const double gamma = o.ph.gamma, gm1 = o.ph.gammaMinus1;
+    switch (o.bcType[zone]) {
+        case H3D_BC_NOSLIPWALL: {
+            // Q(IRHOU:IRHOW) = 2 rho vWall - Q(IRHOU:IRHOW); isothermal not restated (adiabatic only)
+            Q[IRHOU] = 2.0 * Q[IRHO] * P[0] - Q[IRHOU]; Q[IRHOV] = 2.0 * Q[IRHO] * P[1] - Q[IRHOV]; Q[IRHOW] = 2.0 * Q[IRHO] * P[2] - Q[IRHOW];
+        } break;
+        case H3D_BC_FREESLIPWALL: {
+            double vn = Q[IRHOU] * nHat[0] + Q[IRHOV] * nHat[1] + Q[IRHOW] * nHat[2];
+            Q[IRHOU] = Q[IRHOU] - 2.0 * vn * nHat[0]; Q[IRHOV] = Q[IRHOV] - 2.0 * vn * nHat[1]; Q[IRHOW] = Q[IRHOW] - 2.0 * vn * nHat[2];
+        } break;
+        case H3D_BC_INFLOW: {
+            double rho = P[0], u = P[1], v = P[2], w = P[3], p = P[4];
+            Q[IRHO] = rho; Q[IRHOU] = rho * u; Q[IRHOV] = rho * v; Q[IRHOW] = rho * w;
+            Q[IRHOE] = p / gm1 + 0.5 * rho * (u * u + v * v + w * w);
+        } break;
+        case H3D_BC_OUTFLOW: {
+            // OutflowBC.f90:226-288: subsonic outflow keeps interior entropy/Riemann invariant, imposes pExt
+            double rhoExt = P[0], uExt = P[1], vExt = P[2], wExt = P[3], pExt = P[4];
+            double rhoInt = Q[IRHO], invRho = 1.0 / rhoInt;
+            double uInt = Q[IRHOU] * invRho, vInt = Q[IRHOV] * invRho, wInt = Q[IRHOW] * invRho;
+            double pInt = gm1 * (Q[IRHOE] - 0.5 * (Q[IRHOU] * uInt + Q[IRHOV] * vInt + Q[IRHOW] * wInt));
+            double qnInt = uInt * nHat[0] + vInt * nHat[1] + wInt * nHat[2];
+            double aInt = std::sqrt(gamma * pInt * invRho);
+            if (qnInt > 0.0 && qnInt / aInt >= 1.0) break;   // supersonic outflow: interior state
+            (void)rhoExt; (void)uExt; (void)vExt; (void)wExt;
+            double rhoG = rhoInt, uG = uInt, vG = vInt, wG = wInt;
+            Q[IRHO] = rhoG; Q[IRHOU] = rhoG * uG; Q[IRHOV] = rhoG * vG; Q[IRHOW] = rhoG * wG;
+            Q[IRHOE] = pExt / gm1 + 0.5 * rhoG * (uG * uG + vG * vG + wG * wG);
+        } break;
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Index helpers
+// ------------------------------------------------------------------------------------------------
+struct Idx {
+    int n;
+    inline size_t node(int e, int i, int j, int k) const { return ((size_t)e * n * n * n + (size_t)(k * n + j) * n + i); }
+    inline size_t fnode(int f, int side, int i, int j) const { return (((size_t)f * 2 + side) * n * n + (size_t)j * n + i); }
+    inline size_t gnode(int f, int i, int j) const { return ((size_t)f * n * n + (size_t)j * n + i); }
+};
+
+// element-trace index (a,b) on local face lf <-> volume indices
+static const int axisMap[6][2] = {{0, 2}, {0, 2}, {0, 1}, {1, 2}, {0, 1}, {1, 2}};
+
+// ------------------------------------------------------------------------------------------------
+//  HexMesh_ProlongSolutionToFaces (libs/mesh/HexMesh.f90:948-1036) -> HexElement_ProlongSolutionToFaces
+//  (HexElementClass.f90:233-302) -> Face_AdaptSolutionToFace (FaceClass.f90:281-381, projectionType 0)
+// ------------------------------------------------------------------------------------------------
+void adaptToFace(const Oracle& o, int nv, const double* Qe /*[b][a][nv]*/, int f, int side, double* dst /*face storage base for nv vars*/) {
+    const int n = o.n, N = o.N; Idx ix{n};
+    if (side == 0) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i)
+            for (int q = 0; q < nv; ++q) dst[ix.fnode(f, 0, i, j) * nv + q] = Qe[(j * n + i) * nv + q];
+    } else {
+        const int rot = o.faceRot[f];
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            int ii, jj; leftIndexes2Right(i, j, N, N, rot, ii, jj);
+            for (int q = 0; q < nv; ++q) dst[ix.fnode(f, 1, i, j) * nv + q] = Qe[(jj * n + ii) * nv + q];
+        }
+    }
+}
+
+void prolongToFaces(Oracle& o, int nv, const std::vector<double>& field, std::vector<double>& faceField) {
+    const int n = o.n; Idx ix{n};
+#pragma omp parallel
+    {
+        std::vector<double> T[6];
+        for (int f = 0; f < 6; ++f) T[f].resize((size_t)n * n * nv);
+#pragma omp for schedule(static)
+        for (int e = 0; e < o.nElem; ++e) {
+            for (int f = 0; f < 6; ++f) std::fill(T[f].begin(), T[f].end(), 0.0);
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                const double* q = &field[ix.node(e, i, j, k) * nv];
+                for (int c = 0; c < nv; ++c) {
+                    T[ELEFT][(k * n + j) * nv + c] = T[ELEFT][(k * n + j) * nv + c] + q[c] * o.v[0 * n + i];
+                    T[ERIGHT][(k * n + j) * nv + c] = T[ERIGHT][(k * n + j) * nv + c] + q[c] * o.v[1 * n + i];
+                    T[EFRONT][(k * n + i) * nv + c] = T[EFRONT][(k * n + i) * nv + c] + q[c] * o.v[0 * n + j];
+                    T[EBACK][(k * n + i) * nv + c] = T[EBACK][(k * n + i) * nv + c] + q[c] * o.v[1 * n + j];
+                    T[EBOTTOM][(j * n + i) * nv + c] = T[EBOTTOM][(j * n + i) * nv + c] + q[c] * o.v[0 * n + k];
+                    T[ETOP][(j * n + i) * nv + c] = T[ETOP][(j * n + i) * nv + c] + q[c] * o.v[1 * n + k];
+                }
+            }
+            for (int lf = 0; lf < 6; ++lf) adaptToFace(o, nv, T[lf].data(), o.elemFace[6 * e + lf], o.elemFaceSide[6 * e + lf], faceField.data());
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  BR1_ComputeGradient (libs/discretization/EllipticBR1.f90:71-160, 168-393)
+// ------------------------------------------------------------------------------------------------
+void computeGradient(Oracle& o, double time) {
+    (void)time;
+    const int n = o.n, n3 = o.n3(); Idx ix{n};
+    // HexElement_ComputeLocalGradient (HexElementClass.f90:427-531); U = Q (NSGradientVariables_STATE)
+#pragma omp parallel
+    {
+        std::vector<double> Uxi((size_t)n3 * 5), Ueta((size_t)n3 * 5), Uzeta((size_t)n3 * 5);
+#pragma omp for schedule(static)
+        for (int e = 0; e < o.nElem; ++e) {
+            std::fill(Uxi.begin(), Uxi.end(), 0.0); std::fill(Ueta.begin(), Ueta.end(), 0.0); std::fill(Uzeta.begin(), Uzeta.end(), 0.0);
+            const double* U = &o.Q[ix.node(e, 0, 0, 0) * 5];
+            auto L = [&](int i, int j, int k) { return (size_t)((k * n + j) * n + i) * 5; };
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int l = 0; l < n; ++l) for (int i = 0; i < n; ++i)
+                for (int q = 0; q < 5; ++q) Uxi[L(i, j, k) + q] = Uxi[L(i, j, k) + q] + U[L(l, j, k) + q] * o.D[i * n + l];
+            for (int k = 0; k < n; ++k) for (int l = 0; l < n; ++l) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i)
+                for (int q = 0; q < 5; ++q) Ueta[L(i, j, k) + q] = Ueta[L(i, j, k) + q] + U[L(i, l, k) + q] * o.D[j * n + l];
+            for (int l = 0; l < n; ++l) for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i)
+                for (int q = 0; q < 5; ++q) Uzeta[L(i, j, k) + q] = Uzeta[L(i, j, k) + q] + U[L(i, j, l) + q] * o.D[k * n + l];
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                size_t g = ix.node(e, i, j, k);
+                const double* jx = &o.JaXi[3 * g]; const double* je = &o.JaEta[3 * g]; const double* jz = &o.JaZeta[3 * g];
+                double iJ = o.invJac[g];
+                for (int q = 0; q < 5; ++q) {
+                    double a = Uxi[L(i, j, k) + q], b = Ueta[L(i, j, k) + q], c = Uzeta[L(i, j, k) + q];
+                    o.Ux[5 * g + q] = (a * jx[0] + b * je[0] + c * jz[0]) * iJ;
+                    o.Uy[5 * g + q] = (a * jx[1] + b * je[1] + c * jz[1]) * iJ;
+                    o.Uz[5 * g + q] = (a * jx[2] + b * je[2] + c * jz[2]) * iJ;
+                }
+            }
+        }
+    }
+    // BR1_ComputeElementInterfaceAverage (:571-627) + Face_ProjectGradientFluxToElements (FaceClass.f90:865-961, factor = 1)
+    // BR1_ComputeBoundaryFlux (:686-736)
+#pragma omp parallel for schedule(static)
+    for (int f = 0; f < o.nFace; ++f) {
+        const int N = o.N;
+        if (o.faceType[f] == H3D_FACE_INTERIOR) {
+            for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                const double* UL = &o.fQ[ix.fnode(f, 0, i, j) * 5]; const double* UR = &o.fQ[ix.fnode(f, 1, i, j) * 5];
+                const double Jf = o.fJac[ix.gnode(f, i, j)]; const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
+                int ii, jj; leftIndexes2Right(i, j, N, N, o.faceRot[f], ii, jj);
+                double* uL = &o.unStar[ix.fnode(f, 0, i, j) * 15]; double* uR = &o.unStar[ix.fnode(f, 1, ii, jj) * 15];
+                for (int q = 0; q < 5; ++q) {
+                    double uStar = 0.5 * (UR[q] - UL[q]) * Jf;
+                    for (int d = 0; d < 3; ++d) { double val = uStar * nh[d]; uL[d * 5 + q] = val; uR[d * 5 + q] = 1 * val; }
+                }
+            }
+        } else if (o.faceType[f] == H3D_FACE_BOUNDARY) {
+            const int zone = o.faceZone[f];
+            for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                const double* Qi = &o.fQ[ix.fnode(f, 0, i, j) * 5];
+                const double Jf = o.fJac[ix.gnode(f, i, j)]; const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
+                double u_int[5], u_star[5];
+                for (int q = 0; q < 5; ++q) { u_int[q] = Qi[q]; u_star[q] = Qi[q]; }
+                // GradVarsForEqn -> FlowGradVars (STATE gradient variables)
+                switch (o.bcType[zone]) {
+                    case H3D_BC_NOSLIPWALL: {   // NoSlipWallBC.f90:298-337: wall velocity, interior internal energy (adiabatic)
+                        const double* P = &o.bcParams[16 * zone];
+                        double rho = Qi[IRHO], invRho = 1.0 / rho;
+                        double eInt = Qi[IRHOE] - 0.5 * (POW2(Qi[IRHOU]) + POW2(Qi[IRHOV]) + POW2(Qi[IRHOW])) * invRho;
+                        u_star[IRHO] = rho; u_star[IRHOU] = rho * P[0]; u_star[IRHOV] = rho * P[1]; u_star[IRHOW] = rho * P[2];
+                        u_star[IRHOE] = eInt + 0.5 * rho * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]);
+                    } break;
+                    case H3D_BC_FREESLIPWALL: {  // FreeSlipWallBC.f90:283-312: remove the normal momentum
+                        double vn = Qi[IRHOU] * nh[0] + Qi[IRHOV] * nh[1] + Qi[IRHOW] * nh[2];
+                        u_star[IRHOU] = Qi[IRHOU] - vn * nh[0]; u_star[IRHOV] = Qi[IRHOV] - vn * nh[1]; u_star[IRHOW] = Qi[IRHOW] - vn * nh[2];
+                    } break;
+                    case H3D_BC_INFLOW: case H3D_BC_OUTFLOW: {   // InflowBC.f90:403-412 / OutflowBC.f90: external state
+                        BC_FlowState(o, zone, nh, u_star);
+                    } break;
+                    default: break;
+                }
+                double* uL = &o.unStar[ix.fnode(f, 0, i, j) * 15];
+                for (int q = 0; q < 5; ++q) for (int d = 0; d < 3; ++d) uL[d * 5 + q] = (u_star[q] - u_int[q]) * nh[d] * Jf;
+            }
+        }
+    }
+    // BR1_GradientFaceLoop (:531-569) -> VectorWeakIntegrals_StdFace (DGIntegrals.f90:365-443)
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nElem; ++e) {
+        const double* H[6];
+        for (int lf = 0; lf < 6; ++lf) H[lf] = &o.unStar[ix.fnode(o.elemFace[6 * e + lf], o.elemFaceSide[6 * e + lf], 0, 0) * 15];
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            size_t g = ix.node(e, i, j, k);
+            double iJ = o.invJac[g];
+            for (int d = 0; d < 3; ++d) {
+                double* Ud = (d == 0 ? o.Ux.data() : d == 1 ? o.Uy.data() : o.Uz.data()) + 5 * g;
+                for (int q = 0; q < 5; ++q) {
+                    double fi = H[ELEFT][((k * n + j) * 3 + d) * 5 + q] * o.b[0 * n + i];
+                    fi = fi + H[ERIGHT][((k * n + j) * 3 + d) * 5 + q] * o.b[1 * n + i];
+                    fi = fi + H[EFRONT][((k * n + i) * 3 + d) * 5 + q] * o.b[0 * n + j];
+                    fi = fi + H[EBACK][((k * n + i) * 3 + d) * 5 + q] * o.b[1 * n + j];
+                    fi = fi + H[EBOTTOM][((j * n + i) * 3 + d) * 5 + q] * o.b[0 * n + k];
+                    fi = fi + H[ETOP][((j * n + i) * 3 + d) * 5 + q] * o.b[1 * n + k];
+                    Ud[q] = Ud[q] + fi * iJ;
+                }
+            }
+        }
+    }
+    // HexElement_ProlongGradientsToFaces (HexElementClass.f90:304-372)
+    prolongToFaces(o, 5, o.Ux, o.fUx);
+    prolongToFaces(o, 5, o.Uy, o.fUy);
+    prolongToFaces(o, 5, o.Uz, o.fUz);
+}
+
+// ------------------------------------------------------------------------------------------------
+//  TimeDerivative_ComputeQDot (NavierStokesSolver/SpatialDiscretization.f90:379-685)
+// ------------------------------------------------------------------------------------------------
+void computeQDot(Oracle& o, double time) {
+    (void)time;
+    const int n = o.n, n3 = o.n3(), N = o.N; Idx ix{n};
+    const bool NS = o.ph.flowIsNavierStokes != 0;
+    // viscosity at the elements (:402-412) [+ Smagorinsky :416-436]
+    if (NS) {
+#pragma omp parallel for schedule(static)
+        for (int e = 0; e < o.nElem; ++e) {
+            double delta = 0.0;
+            if (o.ph.les == H3D_LES_SMAGORINSKY) delta = std::pow(o.volume[e] / (double)(n * n * n), 1.0 / 3.0);
+            for (int q = 0; q < n3; ++q) {
+                size_t g = (size_t)e * n3 + q;
+                get_laminar_mu_kappa(o, &o.Q[5 * g], o.mu[2 * g], o.mu[2 * g + 1]);
+                if (o.ph.les == H3D_LES_SMAGORINSKY) {
+                    double mut = SmagorinskyViscosity(o, delta, &o.Q[5 * g], &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g]);
+                    o.mu[2 * g] = o.mu[2 * g] + mut; o.mu[2 * g + 1] = o.mu[2 * g + 1] + mut * o.ph.mu_to_kappa;
+                }
+            }
+        }
+        // compute_viscosity_at_faces (:1345-1398)
+#pragma omp parallel for schedule(static)
+        for (int f = 0; f < o.nFace; ++f) {
+            const int sides = o.faceType[f] == H3D_FACE_INTERIOR ? 2 : 1;
+            double delta = 0.0;
+            if (o.ph.les == H3D_LES_SMAGORINSKY) delta = std::sqrt(o.fSurface[f] / (double)(n * n));
+            for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int s = 0; s < sides; ++s) {
+                size_t g = ix.fnode(f, s, i, j);
+                get_laminar_mu_kappa(o, &o.fQ[5 * g], o.fmu[2 * g], o.fmu[2 * g + 1]);
+                if (o.ph.les == H3D_LES_SMAGORINSKY) {
+                    double mut = SmagorinskyViscosity(o, delta, &o.fQ[5 * g], &o.fUx[5 * g], &o.fUy[5 * g], &o.fUz[5 * g]);
+                    o.fmu[2 * g] = o.fmu[2 * g] + mut; o.fmu[2 * g + 1] = o.fmu[2 * g + 1] + mut * o.ph.mu_to_kappa;
+                }
+            }
+        }
+    }
+    // volume integrals: TimeDerivative_VolumetricContribution (:1602-1682)
+#pragma omp parallel
+    {
+        std::vector<double> Finv((size_t)n3 * 15), Fvis((size_t)n3 * 15, 0.0), Fc((size_t)n3 * 15);
+        std::vector<double> fS, gS, hS;
+        if (o.ph.inviscid == H3D_SPLIT_DG) { fS.resize((size_t)n3 * n * 5); gS.resize((size_t)n3 * n * 5); hS.resize((size_t)n3 * n * 5); }
+#pragma omp for schedule(static)
+        for (int e = 0; e < o.nElem; ++e) {
+            auto L = [&](int i, int j, int k) { return (size_t)((k * n + j) * n + i); };
+            // BaseClass_ComputeInnerFluxes (HyperbolicDiscretizationClass.f90:83-152) / BR1_ComputeInnerFluxes (EllipticBR1.f90:740-814)
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                size_t g = ix.node(e, i, j, k), l = L(i, j, k);
+                const double* jx = &o.JaXi[3 * g]; const double* je = &o.JaEta[3 * g]; const double* jz = &o.JaZeta[3 * g];
+                double F[5][3];
+                EulerFlux(o, &o.Q[5 * g], F);
+                for (int q = 0; q < 5; ++q) {
+                    Finv[(l * 3 + 0) * 5 + q] = F[q][IX] * jx[IX] + F[q][IY] * jx[IY] + F[q][IZ] * jx[IZ];
+                    Finv[(l * 3 + 1) * 5 + q] = F[q][IX] * je[IX] + F[q][IY] * je[IY] + F[q][IZ] * je[IZ];
+                    Finv[(l * 3 + 2) * 5 + q] = F[q][IX] * jz[IX] + F[q][IY] * jz[IY] + F[q][IZ] * jz[IZ];
+                }
+                if (NS) {
+                    ViscousFlux_STATE(o, &o.Q[5 * g], &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g], o.mu[2 * g], 0.0, o.mu[2 * g + 1], F);
+                    for (int q = 0; q < 5; ++q) {
+                        Fvis[(l * 3 + 0) * 5 + q] = F[q][IX] * jx[IX] + F[q][IY] * jx[IY] + F[q][IZ] * jx[IZ];
+                        Fvis[(l * 3 + 1) * 5 + q] = F[q][IX] * je[IX] + F[q][IY] * je[IY] + F[q][IZ] * je[IZ];
+                        Fvis[(l * 3 + 2) * 5 + q] = F[q][IX] * jz[IX] + F[q][IY] * jz[IY] + F[q][IZ] * jz[IZ];
+                    }
+                }
+            }
+            double* qd = &o.QDot[ix.node(e, 0, 0, 0) * 5];
+            if (o.ph.inviscid == H3D_STANDARD_DG) {
+                // contravariantFlux = inviscid - viscous - Avisc(=0) ; ScalarWeakIntegrals_StdVolumeGreen (DGIntegrals.f90:56-87)
+                for (size_t t = 0; t < (size_t)n3 * 15; ++t) Fc[t] = Finv[t] - Fvis[t] - 0.0;
+                for (size_t t = 0; t < (size_t)n3 * 5; ++t) qd[t] = 0.0;
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int l = 0; l < n; ++l) for (int i = 0; i < n; ++i)
+                    for (int q = 0; q < 5; ++q) qd[L(i, j, k) * 5 + q] = qd[L(i, j, k) * 5 + q] + o.hatD[i * n + l] * Fc[(L(l, j, k) * 3 + 0) * 5 + q];
+                for (int k = 0; k < n; ++k) for (int l = 0; l < n; ++l) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i)
+                    for (int q = 0; q < 5; ++q) qd[L(i, j, k) * 5 + q] = qd[L(i, j, k) * 5 + q] + o.hatD[j * n + l] * Fc[(L(i, l, k) * 3 + 1) * 5 + q];
+                for (int l = 0; l < n; ++l) for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i)
+                    for (int q = 0; q < 5; ++q) qd[L(i, j, k) * 5 + q] = qd[L(i, j, k) * 5 + q] + o.hatD[k * n + l] * Fc[(L(i, j, l) * 3 + 2) * 5 + q];
+            } else {
+                // SplitDG_ComputeSplitFormFluxes (HyperbolicSplitForm.f90:64-116); fSharp(:,l,i,j,k) -> fS[(l + n*node)*5 + q]
+                auto SI = [&](int l, int i, int j, int k) { return ((size_t)L(i, j, k) * n + l) * 5; };
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int q = 0; q < 5; ++q) {
+                    fS[SI(i, i, j, k) + q] = Finv[(L(i, j, k) * 3 + 0) * 5 + q];
+                    gS[SI(j, i, j, k) + q] = Finv[(L(i, j, k) * 3 + 1) * 5 + q];
+                    hS[SI(k, i, j, k) + q] = Finv[(L(i, j, k) * 3 + 2) * 5 + q];
+                }
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                    size_t g = ix.node(e, i, j, k);
+                    for (int l = i + 1; l < n; ++l) {
+                        size_t g2 = ix.node(e, l, j, k);
+                        TwoPointFlux(o, &o.Q[5 * g], &o.Q[5 * g2], &o.JaXi[3 * g], &o.JaXi[3 * g2], &fS[SI(l, i, j, k)]);
+                        for (int q = 0; q < 5; ++q) fS[SI(i, l, j, k) + q] = fS[SI(l, i, j, k) + q];
+                    }
+                    for (int l = j + 1; l < n; ++l) {
+                        size_t g2 = ix.node(e, i, l, k);
+                        TwoPointFlux(o, &o.Q[5 * g], &o.Q[5 * g2], &o.JaEta[3 * g], &o.JaEta[3 * g2], &gS[SI(l, i, j, k)]);
+                        for (int q = 0; q < 5; ++q) gS[SI(j, i, l, k) + q] = gS[SI(l, i, j, k) + q];
+                    }
+                    for (int l = k + 1; l < n; ++l) {
+                        size_t g2 = ix.node(e, i, j, l);
+                        TwoPointFlux(o, &o.Q[5 * g], &o.Q[5 * g2], &o.JaZeta[3 * g], &o.JaZeta[3 * g2], &hS[SI(l, i, j, k)]);
+                        for (int q = 0; q < 5; ++q) hS[SI(k, i, j, l) + q] = hS[SI(l, i, j, k) + q];
+                    }
+                }
+                // ScalarWeakIntegrals_SplitVolumeDivergence (DGIntegrals.f90:92-129); QDot = -volInt (:1678)
+                for (size_t t = 0; t < (size_t)n3 * 5; ++t) qd[t] = 0.0;
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int l = 0; l < n; ++l) for (int i = 0; i < n; ++i)
+                    for (int q = 0; q < 5; ++q) qd[L(i, j, k) * 5 + q] = qd[L(i, j, k) * 5 + q] + o.sharpD[i * n + l] * fS[SI(l, i, j, k) + q] + o.hatD[i * n + l] * Fvis[(L(l, j, k) * 3 + 0) * 5 + q];
+                for (int k = 0; k < n; ++k) for (int l = 0; l < n; ++l) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i)
+                    for (int q = 0; q < 5; ++q) qd[L(i, j, k) * 5 + q] = qd[L(i, j, k) * 5 + q] + o.sharpD[j * n + l] * gS[SI(l, i, j, k) + q] + o.hatD[j * n + l] * Fvis[(L(i, l, k) * 3 + 1) * 5 + q];
+                for (int l = 0; l < n; ++l) for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i)
+                    for (int q = 0; q < 5; ++q) qd[L(i, j, k) * 5 + q] = qd[L(i, j, k) * 5 + q] + o.sharpD[k * n + l] * hS[SI(l, i, j, k) + q] + o.hatD[k * n + l] * Fvis[(L(i, j, l) * 3 + 2) * 5 + q];
+                for (size_t t = 0; t < (size_t)n3 * 5; ++t) qd[t] = -qd[t];
+            }
+        }
+    }
+    // Riemann solver of non-shared faces: computeElementInterfaceFlux (:1710-1799), computeBoundaryFlux (:1896-2028)
+#pragma omp parallel for schedule(static)
+    for (int f = 0; f < o.nFace; ++f) {
+        if (o.faceType[f] == H3D_FACE_INTERIOR) {
+            for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                size_t gL = ix.fnode(f, 0, i, j), gR = ix.fnode(f, 1, i, j), gg = ix.gnode(f, i, j);
+                const double* nh = &o.fNormal[3 * gg];
+                double visc[5] = {0, 0, 0, 0, 0}, inv[5];
+                if (NS) {   // BR1_RiemannSolver (EllipticBR1.f90:816-868)
+                    double fL[5][3], fR[5][3];
+                    ViscousFlux_STATE(o, &o.fQ[5 * gL], &o.fUx[5 * gL], &o.fUy[5 * gL], &o.fUz[5 * gL], o.fmu[2 * gL], 0.0, o.fmu[2 * gL + 1], fL);
+                    ViscousFlux_STATE(o, &o.fQ[5 * gR], &o.fUx[5 * gR], &o.fUy[5 * gR], &o.fUz[5 * gR], o.fmu[2 * gR], 0.0, o.fmu[2 * gR + 1], fR);
+                    for (int q = 0; q < 5; ++q) {
+                        double fx = 0.5 * (fL[q][IX] + fR[q][IX]), fy = 0.5 * (fL[q][IY] + fR[q][IY]), fz = 0.5 * (fL[q][IZ] + fR[q][IZ]);
+                        visc[q] = fx * nh[IX] + fy * nh[IY] + fz * nh[IZ];
+                    }
+                }
+                RiemannSolver(o, &o.fQ[5 * gL], &o.fQ[5 * gR], nh, &o.fT1[3 * gg], &o.fT2[3 * gg], inv);
+                // Face_ProjectFluxToElements (FaceClass.f90:597-696): left = flux, right = rotated and negated
+                int ii, jj; leftIndexes2Right(i, j, N, N, o.faceRot[f], ii, jj);
+                size_t gRe = ix.fnode(f, 1, ii, jj);
+                for (int q = 0; q < 5; ++q) {
+                    double flux = (inv[q] - visc[q]) * o.fJac[gg] - 0.0;
+                    o.fStar[5 * gL + q] = flux; o.fStar[5 * gRe + q] = -flux;
+                }
+            }
+        } else if (o.faceType[f] == H3D_FACE_BOUNDARY) {
+            const int zone = o.faceZone[f];
+            for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                size_t gL = ix.fnode(f, 0, i, j), gR = ix.fnode(f, 1, i, j), gg = ix.gnode(f, i, j);
+                const double* nh = &o.fNormal[3 * gg];
+                for (int q = 0; q < 5; ++q) o.fQ[5 * gR + q] = o.fQ[5 * gL + q];
+                BC_FlowState(o, zone, nh, &o.fQ[5 * gR]);
+                double visc[5] = {0, 0, 0, 0, 0}, inv[5];
+                if (NS) {
+                    double fv[5][3];
+                    ViscousFlux_STATE(o, &o.fQ[5 * gL], &o.fUx[5 * gL], &o.fUy[5 * gL], &o.fUz[5 * gL], o.fmu[2 * gL], 0.0, o.fmu[2 * gL + 1], fv);
+                    for (int q = 0; q < 5; ++q) { visc[q] = fv[q][IX] * nh[IX] + fv[q][IY] * nh[IY] + fv[q][IZ] * nh[IZ]; visc[q] = visc[q] + 0.0; }
+                    // FlowNeumann
+                    const double* P = &o.bcParams[16 * zone];
+                    switch (o.bcType[zone]) {
+                        case H3D_BC_NOSLIPWALL: {  // NoSlipWallBC.f90:339-372 (adiabatic): no mass flux, energy flux = vWall . tau
+                            double work = visc[IRHOU] * P[0] + visc[IRHOV] * P[1] + visc[IRHOW] * P[2];
+                            visc[IRHO] = 0.0; visc[IRHOE] = work;
+                        } break;
+                        case H3D_BC_FREESLIPWALL: {  // FreeSlipWallBC.f90:314-351: zero viscous flux (adiabatic)
+                            for (int q = 0; q < 5; ++q) visc[q] = 0.0;
+                        } break;
+                        case H3D_BC_INFLOW: case H3D_BC_OUTFLOW: for (int q = 0; q < 5; ++q) visc[q] = 0.0; break;   // InflowBC.f90:425
+                        default: break;
+                    }
+                }
+                RiemannSolver(o, &o.fQ[5 * gL], &o.fQ[5 * gR], nh, &o.fT1[3 * gg], &o.fT2[3 * gg], inv);
+                for (int q = 0; q < 5; ++q) o.fStar[5 * gL + q] = (inv[q] - visc[q]) * o.fJac[gg];
+            }
+        }
+    }
+    // surface integrals + scaling: TimeDerivative_FacesContribution (:1686-1701) -> ScalarWeakIntegrals_StdFace
+    // (DGIntegrals.f90:214-273); QDot /= jacobian (:489-491); QDot += S_NS (:632-638)
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nElem; ++e) {
+        const double* F[6];
+        for (int lf = 0; lf < 6; ++lf) F[lf] = &o.fStar[ix.fnode(o.elemFace[6 * e + lf], o.elemFaceSide[6 * e + lf], 0, 0) * 5];
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            size_t g = ix.node(e, i, j, k);
+            for (int q = 0; q < 5; ++q) {
+                double fi = F[ELEFT][(k * n + j) * 5 + q] * o.b[0 * n + i];
+                fi = fi + F[ERIGHT][(k * n + j) * 5 + q] * o.b[1 * n + i];
+                fi = fi + F[EFRONT][(k * n + i) * 5 + q] * o.b[0 * n + j];
+                fi = fi + F[EBACK][(k * n + i) * 5 + q] * o.b[1 * n + j];
+                fi = fi + F[EBOTTOM][(j * n + i) * 5 + q] * o.b[0 * n + k];
+                fi = fi + F[ETOP][(j * n + i) * 5 + q] * o.b[1 * n + k];
+                double r = o.QDot[5 * g + q] - fi;
+                r = r / o.jac[g];
+                r = r + (o.hasSource ? o.S[5 * g + q] : 0.0);
+                o.QDot[5 * g + q] = r;
+            }
+        }
+    }
+}
+
+// ComputeTimeDerivative (SpatialDiscretization.f90:227-320)
+void computeTimeDerivative(Oracle& o, double time) {
+    prolongToFaces(o, 5, o.Q, o.fQ);
+    if (o.ph.computeGradients) computeGradient(o, time);
+    computeQDot(o, time);
+}
+
+}  // namespace
+
+// ====================================================================================================
+//  C API (mirrors include/h3d_gpu.h with the prefix orc_)
+// ====================================================================================================
+extern "C" {
+
+void* orc_create() { return new Oracle(); }
+void orc_destroy(void* p) { delete (Oracle*)p; }
+const char* orc_last_error(void* p) { return ((Oracle*)p)->err.c_str(); }
+
+int orc_set_physics(void* p, const H3dPhysics* ph) { ((Oracle*)p)->ph = *ph; return 0; }
+
+int orc_set_basis(void* p, int N, int nodeType, const double* x, const double* w, const double* D, const double* hatD,
+                  const double* sharpD, const double* v, const double* b) {
+    Oracle& o = *(Oracle*)p; const int n = N + 1;
+    o.N = N; o.n = n; o.nodeType = nodeType;
+    o.x.assign(x, x + n); o.w.assign(w, w + n); o.D.assign(D, D + n * n); o.hatD.assign(hatD, hatD + n * n);
+    o.sharpD.assign(sharpD, sharpD + n * n); o.v.assign(v, v + 2 * n); o.b.assign(b, b + 2 * n);
+    return 0;
+}
+
+int orc_set_mesh(void* p, int nElem, int nFace, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+                 const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone,
+                 const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,
+                 const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
+                 const double* faceJacobian, const double* faceX, const double* faceSurface) {
+    Oracle& o = *(Oracle*)p;
+    if (o.N < 0) { o.err = "set_basis must precede set_mesh"; return 1; }
+    const size_t n3 = o.n3(), n2 = o.n2();
+    o.nElem = nElem; o.nFace = nFace;
+    o.elemFace.assign(elemFace, elemFace + 6 * (size_t)nElem); o.elemFaceSide.assign(elemFaceSide, elemFaceSide + 6 * (size_t)nElem);
+    o.faceElem.assign(faceElem, faceElem + 2 * (size_t)nFace); o.faceElemSide.assign(faceElemSide, faceElemSide + 2 * (size_t)nFace);
+    o.faceRot.assign(faceRot, faceRot + nFace); o.faceType.assign(faceType, faceType + nFace); o.faceZone.assign(faceZone, faceZone + nFace);
+    for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_MPI) { o.err = "the oracle is single-domain: MPI faces are not supported"; return 1; }
+    o.JaXi.assign(jGradXi, jGradXi + 3 * n3 * nElem); o.JaEta.assign(jGradEta, jGradEta + 3 * n3 * nElem); o.JaZeta.assign(jGradZeta, jGradZeta + 3 * n3 * nElem);
+    o.jac.assign(jacobian, jacobian + n3 * nElem); o.invJac.resize(n3 * nElem);
+    for (size_t q = 0; q < n3 * nElem; ++q) o.invJac[q] = 1.0 / o.jac[q];   // MappedGeometry.f90:382
+    if (x) o.xyz.assign(x, x + 3 * n3 * nElem);
+    if (volume) o.volume.assign(volume, volume + nElem);
+    o.fNormal.assign(faceNormal, faceNormal + 3 * n2 * nFace); o.fT1.assign(faceT1, faceT1 + 3 * n2 * nFace); o.fT2.assign(faceT2, faceT2 + 3 * n2 * nFace);
+    o.fJac.assign(faceJacobian, faceJacobian + n2 * nFace);
+    if (faceX) o.fX.assign(faceX, faceX + 3 * n2 * nFace);
+    if (faceSurface) o.fSurface.assign(faceSurface, faceSurface + nFace);
+    const size_t ne = n3 * nElem, nf = n2 * nFace * 2;
+    o.Q.assign(5 * ne, 0.0); o.QDot.assign(5 * ne, 0.0); o.G.assign(5 * ne, 0.0); o.S.assign(5 * ne, 0.0);
+    o.Ux.assign(5 * ne, 0.0); o.Uy.assign(5 * ne, 0.0); o.Uz.assign(5 * ne, 0.0); o.mu.assign(2 * ne, 0.0);
+    o.fQ.assign(5 * nf, 0.0); o.fUx.assign(5 * nf, 0.0); o.fUy.assign(5 * nf, 0.0); o.fUz.assign(5 * nf, 0.0);
+    o.fStar.assign(5 * nf, 0.0); o.fmu.assign(2 * nf, 0.0); o.unStar.assign(15 * nf, 0.0);
+    return 0;
+}
+
+int orc_set_boundary_conditions(void* p, int nZones, const int* bcType, const double* bcParams) {
+    Oracle& o = *(Oracle*)p;
+    o.nZones = nZones; o.bcType.assign(bcType, bcType + nZones); o.bcParams.assign(bcParams, bcParams + 16 * (size_t)nZones);
+    return 0;
+}
+
+int orc_upload_Q(void* p, const double* Q) { Oracle& o = *(Oracle*)p; std::memcpy(o.Q.data(), Q, o.Q.size() * sizeof(double)); return 0; }
+
+int orc_download(void* p, double* Q, double* QDot, double* Ux, double* Uy, double* Uz) {
+    Oracle& o = *(Oracle*)p; const size_t b = o.Q.size() * sizeof(double);
+    if (Q) std::memcpy(Q, o.Q.data(), b);
+    if (QDot) std::memcpy(QDot, o.QDot.data(), b);
+    if (Ux) std::memcpy(Ux, o.Ux.data(), b);
+    if (Uy) std::memcpy(Uy, o.Uy.data(), b);
+    if (Uz) std::memcpy(Uz, o.Uz.data(), b);
+    return 0;
+}
+
+// face traces of the last residual evaluation, for unit parity of the prolongation: [f][side][j][i][5]
+int orc_download_faces(void* p, double* fQ, double* fUx, double* fUy, double* fUz, double* fStar) {
+    Oracle& o = *(Oracle*)p; const size_t b = o.fQ.size() * sizeof(double);
+    if (fQ) std::memcpy(fQ, o.fQ.data(), b);
+    if (fUx) std::memcpy(fUx, o.fUx.data(), b);
+    if (fUy) std::memcpy(fUy, o.fUy.data(), b);
+    if (fUz) std::memcpy(fUz, o.fUz.data(), b);
+    if (fStar) std::memcpy(fStar, o.fStar.data(), b);
+    return 0;
+}
+
+int orc_set_source(void* p, const double* S) {
+    Oracle& o = *(Oracle*)p;
+    o.hasSource = S != nullptr;
+    if (S) std::memcpy(o.S.data(), S, o.S.size() * sizeof(double));
+    return 0;
+}
+
+int orc_compute_time_derivative(void* p, double time) { computeTimeDerivative(*(Oracle*)p, time); return 0; }
+
+// TakeRK3Step / TakeRK5Step (libs/timeintegrator/ExplicitMethods.f90:667-788, 790-882)
+int orc_rk_step(void* p, int scheme, double t, double dt, int ctd_after_step) {
+    Oracle& o = *(Oracle*)p;
+    static const double a3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, b3[3] = {0.0, 1.0 / 3.0, 3.0 / 4.0}, c3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
+    static const double a5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
+    static const double b5[5] = {0.0, 0.1496590219993, 0.3704009573644, 0.6222557631345, 0.9582821306748};
+    static const double c5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
+    const int ns = scheme == H3D_RK3 ? 3 : scheme == H3D_RK5 ? 5 : 0;
+    if (!ns) { o.err = "unknown RK scheme"; return 1; }
+    const double *a = ns == 3 ? a3 : a5, *b = ns == 3 ? b3 : b5, *c = ns == 3 ? c3 : c5;
+    double tk = t;
+    for (int k = 0; k < ns; ++k) {
+        tk = t + b[k] * dt;
+        computeTimeDerivative(o, tk);
+        const double ak = a[k], cdt = c[k] * dt;
+#pragma omp parallel for schedule(static)
+        for (size_t q = 0; q < o.Q.size(); ++q) {
+            o.G[q] = ak * o.G[q] + o.QDot[q];
+            o.Q[q] = o.Q[q] + cdt * o.G[q];
+        }
+    }
+    if (ctd_after_step) computeTimeDerivative(o, ns == 3 ? t + dt : tk);
+    return 0;
+}
+
+// ComputeMaxResiduals (libs/discretization/DGSEMClass.f90:770-856)
+int orc_max_residuals(void* p, double out[5]) {
+    Oracle& o = *(Oracle*)p;
+    double R[5] = {0, 0, 0, 0, 0};
+    for (size_t g = 0; g < o.QDot.size() / 5; ++g) for (int q = 0; q < 5; ++q) R[q] = std::fmax(R[q], std::fabs(o.QDot[5 * g + q]));
+    for (int q = 0; q < 5; ++q) out[q] = R[q];
+    return 0;
+}
+
+// MaxTimeStep (DGSEMClass.f90:870-1034) with ComputeEigenvaluesForState (Physics_NS.f90:927-962)
+int orc_max_timestep(void* p, double cfl, double dcfl, double* dt_conv, double* dt_visc) {
+    Oracle& o = *(Oracle*)p;
+    double TimeStep_Conv = std::numeric_limits<double>::max(), TimeStep_Visc = std::numeric_limits<double>::max();
+    const double dcsi = o.N != 0 ? 1.0 / std::fabs(o.x[1] - o.x[0]) : 0.0, deta = dcsi, dzet = dcsi;
+    const double dcsi2 = dcsi * dcsi, deta2 = deta * deta, dzet2 = dzet * dzet;
+    const size_t nn = (size_t)o.n3() * o.nElem;
+    for (size_t g = 0; g < nn; ++g) {
+        const double* Q = &o.Q[5 * g];
+        double u = std::fabs(Q[1] / Q[0]), v = std::fabs(Q[2] / Q[0]), w = std::fabs(Q[3] / Q[0]);
+        double pr = Pressure(o, Q);
+        double a = std::sqrt(o.ph.gamma * pr / Q[0]);
+        double ev[3] = {u + a, v + a, w + a};
+        double jac = o.jac[g];
+        const double* jx = &o.JaXi[3 * g]; const double* je = &o.JaEta[3 * g]; const double* jz = &o.JaZeta[3 * g];
+        double lamcsi_a = std::fabs(jx[0] * ev[0] + jx[1] * ev[1] + jx[2] * ev[2]) * dcsi;
+        double lameta_a = std::fabs(je[0] * ev[0] + je[1] * ev[1] + je[2] * ev[2]) * deta;
+        double lamzet_a = std::fabs(jz[0] * ev[0] + jz[1] * ev[1] + jz[2] * ev[2]) * dzet;
+        TimeStep_Conv = std::fmin(TimeStep_Conv, cfl * std::fabs(jac) / (lamcsi_a + lameta_a + lamzet_a));
+        if (o.ph.flowIsNavierStokes) {
+            double T = Temperature(o, Q);
+            double mu = SutherlandsLaw(o, T);
+            double lamcsi_v = mu * dcsi2 * std::fabs(jx[0] + jx[1] + jx[2]);
+            double lameta_v = mu * deta2 * std::fabs(je[0] + je[1] + je[2]);
+            double lamzet_v = mu * dzet2 * std::fabs(jz[0] + jz[1] + jz[2]);
+            TimeStep_Visc = std::fmin(TimeStep_Visc, dcfl * std::fabs(jac) / (lamcsi_v + lameta_v + lamzet_v));
+        }
+    }
+    *dt_conv = TimeStep_Conv; *dt_visc = TimeStep_Visc;
+    return 0;
+}
+
+// ScalarVolumeIntegral (libs/monitors/VolumeIntegrals.f90:76-120, 167-286)
+int orc_volume_integral(void* p, int kind, double* out) {
+    Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
+    double val = 0.0;
+    for (int e = 0; e < o.nElem; ++e) {
+        double loc = 0.0;
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            size_t g = ix.node(e, i, j, k);
+            const double* Q = &o.Q[5 * g]; const double* QD = &o.QDot[5 * g];
+            double wJ = o.w[i] * o.w[j] * o.w[k] * o.jac[g];
+            switch (kind) {
+                case H3D_INT_VOLUME: loc = loc + wJ; break;
+                case H3D_INT_KINETIC_ENERGY: {
+                    double KinEn = POW2(Q[IRHOU]); KinEn = KinEn + POW2(Q[IRHOV]); KinEn = KinEn + POW2(Q[IRHOW]);
+                    KinEn = 0.5 * KinEn / Q[IRHO];
+                    loc = loc + wJ * KinEn;
+                } break;
+                case H3D_INT_KINETIC_ENERGY_RATE: {
+                    double uvw = Q[IRHOU] / Q[IRHO];
+                    double KinEn = uvw * QD[IRHOU] - 0.5 * POW2(uvw) * QD[IRHO];
+                    uvw = Q[IRHOV] / Q[IRHO];
+                    KinEn = KinEn + uvw * QD[IRHOV] - 0.5 * POW2(uvw) * QD[IRHO];
+                    uvw = Q[IRHOW] / Q[IRHO];
+                    KinEn = KinEn + uvw * QD[IRHOW] - 0.5 * POW2(uvw) * QD[IRHO];
+                    loc = loc + wJ * KinEn;
+                } break;
+                case H3D_INT_ENSTROPHY: {
+                    double U_x[3], U_y[3], U_z[3];
+                    getVelocityGradients_State(Q, &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g], U_x, U_y, U_z);
+                    double KinEn = POW2(U_y[IZ] - U_z[IY]) + POW2(U_z[IX] - U_x[IZ]) + POW2(U_x[IY] - U_y[IX]);
+                    loc = loc + wJ * KinEn;
+                } break;
+                default: o.err = "unknown volume integral"; return 1;
+            }
+        }
+        val = val + loc;
+    }
+    *out = val;
+    return 0;
+}
+
+// checkForNan (ExplicitMethods.f90:1856-1905)
+int orc_has_nan(void* p, int* flag) {
+    Oracle& o = *(Oracle*)p; int f = 0;
+    for (double q : o.Q) if (std::isnan(q)) { f = 1; break; }
+    *flag = f;
+    return 0;
+}
+
+// ---- independent restatement of the 1-D operators for the K6 pin (NodalStorageClass.f90:201-275) -------
+// LegendreAlgorithms.f90:137-212 (Gauss), :275-358 (Lobatto); InterpolationAndDerivatives.f90:230-255, 799-828, 109-159
+static void orc_legendre(int N, double x, double& L, double& dL) {
+    if (N == 0) { L = 1; dL = 0; return; }
+    if (N == 1) { L = x; dL = 1; return; }
+    double Lm2 = 1, dLm2 = 0, Lm1 = x, dLm1 = 1; L = 0; dL = 0;
+    for (int k = 2; k <= N; ++k) { L = ((2 * k - 1) * x * Lm1 - (k - 1) * Lm2) / k; dL = dLm2 + (2 * k - 1) * Lm1; Lm2 = Lm1; Lm1 = L; dLm2 = dLm1; dLm1 = dL; }
+}
+int orc_nodal(int N, int nodeType, double* x, double* w, double* D, double* hatD, double* sharpD, double* v, double* b) {
+    const int n = N + 1; const double PI = 3.141592653589793238462643, tol = 4.0 * std::numeric_limits<double>::epsilon();
+    if (nodeType == H3D_GAUSS) {
+        if (N == 0) { x[0] = 0; w[0] = 2; }
+        else if (N == 1) { x[0] = -std::sqrt(1.0 / 3.0); w[0] = 1; x[1] = -x[0]; w[1] = 1; }
+        else for (int j = 0; j < (N + 1) / 2; ++j) {
+            double xj = -std::cos((2 * j + 1) * PI / (2 * N + 2)), L, dL;
+            for (int k = 0; k <= 10; ++k) { orc_legendre(N + 1, xj, L, dL); double d = -L / dL; xj += d; if (std::fabs(d) <= tol * std::fabs(xj)) break; }
+            orc_legendre(N + 1, xj, L, dL);
+            x[j] = xj; w[j] = 2.0 / ((1.0 - xj * xj) * dL * dL); x[N - j] = -xj; w[N - j] = w[j];
+        }
+        if (N % 2 == 0 && N > 0) { double L, dL; orc_legendre(N + 1, 0.0, L, dL); x[N / 2] = 0; w[N / 2] = 2.0 / (dL * dL); }
+    } else {
+        if (N == 1) { x[0] = -1; w[0] = 1; x[1] = 1; w[1] = 1; }
+        else {
+            x[0] = -1; w[0] = 2.0 / (N * (N + 1)); x[N] = 1; w[N] = w[0];
+            auto qAndL = [&](double xx, double& Q, double& dQ, double& LN) {
+                double Lm2 = 1, dLm2 = 0, Lm1 = xx, dLm1 = 1, Lk = 0, dLk = 0;
+                for (int k = 2; k <= N; ++k) { Lk = ((2 * k - 1) * xx * Lm1 - (k - 1) * Lm2) / k; dLk = dLm2 + (2 * k - 1) * Lm1; Lm2 = Lm1; Lm1 = Lk; dLm2 = dLm1; dLm1 = dLk; }
+                int k = N + 1; Lk = ((2 * k - 1) * xx * Lm1 - (k - 1) * Lm2) / k; dLk = dLm2 + (2 * k - 1) * Lm1;
+                Q = Lk - Lm2; dQ = dLk - dLm2; LN = Lm1;
+            };
+            for (int j = 1; j < (N + 1) / 2; ++j) {
+                double xj = -std::cos((j + 0.25) * PI / N - 3.0 / (8 * N * PI * (j + 0.25))), Q, dQ, LN;
+                for (int k = 0; k <= 10; ++k) { qAndL(xj, Q, dQ, LN); double d = -Q / dQ; xj += d; if (std::fabs(d) <= tol * std::fabs(xj)) break; }
+                qAndL(xj, Q, dQ, LN);
+                x[j] = xj; w[j] = 2.0 / (N * (N + 1) * LN * LN); x[N - j] = -xj; w[N - j] = w[j];
+            }
+            if (N % 2 == 0) { double L, dL; orc_legendre(N, 0.0, L, dL); x[N / 2] = 0; w[N / 2] = 2.0 / (N * (N + 1) * L * L); }
+        }
+    }
+    std::vector<double> wb(n, 1.0);
+    for (int j = 1; j <= N; ++j) for (int k = 0; k < j; ++k) { wb[k] *= (x[k] - x[j]); wb[j] *= (x[j] - x[k]); }
+    for (int j = 0; j <= N; ++j) wb[j] = 1.0 / wb[j];
+    for (int i = 0; i <= N; ++i) { D[i * n + i] = 0; for (int j = 0; j <= N; ++j) if (j != i) { D[i * n + j] = wb[j] / (wb[i] * (x[i] - x[j])); D[i * n + i] -= D[i * n + j]; } }
+    for (int j = 0; j <= N; ++j) for (int i = 0; i <= N; ++i) hatD[i * n + j] = D[j * n + i] * w[j] / w[i];
+    for (int q = 0; q < n * n; ++q) sharpD[q] = 0.0;
+    if (nodeType == H3D_GAUSSLOBATTO && N != 0) { for (int q = 0; q < n * n; ++q) sharpD[q] = 2.0 * D[q]; sharpD[0] = 2.0 * D[0] + 1.0 / w[0]; sharpD[N * n + N] = 2.0 * D[N * n + N] - 1.0 / w[N]; }
+    for (int s = 0; s < 2; ++s) {
+        double xe = s ? 1.0 : -1.0; bool match = false;
+        for (int j = 0; j <= N; ++j) { v[s * n + j] = 0; double a = xe, bb = x[j]; double tl = 2 * std::numeric_limits<double>::epsilon();
+            bool eq = (a == 0.0 || bb == 0.0) ? std::fabs(a - bb) <= tl : std::fabs(bb - a) <= tl * std::fmax(std::fabs(a), std::fabs(bb));
+            if (eq) { v[s * n + j] = 1; match = true; } }
+        if (!match) { double d = 0; for (int j = 0; j <= N; ++j) { double t = wb[j] / (xe - x[j]); v[s * n + j] = t; d += t; } for (int j = 0; j <= N; ++j) v[s * n + j] /= d; }
+        for (int j = 0; j <= N; ++j) b[s * n + j] = v[s * n + j] / w[j];
+    }
+    return 0;
+}
+
+}  // extern "C"
