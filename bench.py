@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- DOF-updates/s (and time per DOF per RK stage) of the explicit RK3 Navier-Stokes step.
+
+Metric (BASELINE.json): Taylor-Green vortex, P=7, compressible NS (Re 1600, M 0.08), Standard DG + BR1 + Roe,
+explicit RK3.  A "step" is one RK3 time step (three residual evaluations + updates).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework on N B200s
+  python bench.py --impl reference --steps K --warmup W    # restated reference algorithm on the host cores
+
+Workload: N=1 -> configs[1]: 32^3 elements, P=7 (16.8 M DOF) on a curvilinear periodic box.
+          N>1 -> weak scaling, 32^3 elements per GPU: (64,32,32), (64,64,32), (64,64,64 = configs[3]) elements,
+                 partitioned element-wise (METIS_PartMeshDual, as the reference) with NCCL face exchange.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_ALG_NS_STAGE = lambda n: 600.0 + 3072.0 / n            # bytes per DOF per RK stage (NS/BR1/StandardDG)
+B_ALG_VOLUME_KERNEL = lambda n: 360.0 + 480.0 / n        # k_volume: Q 40 + gradU 120 + metrics 80 + G 40 read, G 40 + Q 40 written,
+                                                         # + fStar read (6 faces x 5 x n^2) + trace write (same) = 480/n  
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ne", type=int, default=32, help="elements per direction per GPU")
+    ap.add_argument("--order", type=int, default=7)
+    ap.add_argument("--amp", type=float, default=0.1, help="curvature amplitude of the mesh mapping")
+    ap.add_argument("--partition", default="metis", choices=["metis", "block"])
+    ap.add_argument("--dt", type=float, default=1.0e-4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-ne", type=int, default=8, help="elements per direction of the bounded CPU sample")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md, clocks line)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_sample(args, steps, warmup):
+    """The restated reference algorithm (oracle, g++ -O2 -fopenmp, no FMA) on a bounded sample of the same workload."""
+    from horses3d_b200.dgsem import DGSem, taylor_green_ic
+    from horses3d_b200.hostmesh import GAUSS, HostMesh
+    from horses3d_b200.physics import make_physics
+    from oracle.oracle_api import OracleApi
+    mesh = HostMesh.box(args.ref_ne, amp=args.amp, bFaceOrder=2).connect().geometry(args.order, GAUSS)
+    sem = DGSem(OracleApi(), mesh, make_physics(flow="NS", mach=0.08, reynolds=1600.0, riemann="roe"))
+    sem.set_initial_condition(taylor_green_ic)
+    for _ in range(warmup):
+        sem.TakeRK3Step(0.0, args.dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sem.TakeRK3Step(0.0, args.dt)
+    dt = time.perf_counter() - t0
+    value = sem.NDOF * 3 * steps / dt
+    sample = "TGV P=%d, %d^3 curvilinear elements (%d DOF), %d RK3 steps" % (args.order, args.ref_ne, sem.NDOF, steps)
+    return value, dt / steps * 1e3, os.cpu_count(), sample
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, cores, sample = cpu_sample(args, max(args.steps, 1), max(args.warmup, 1))
+    n = args.order + 1
+    line = {
+        "impl": "reference", "metric": "DOF-updates/s (TGV P=%d explicit RK3, NS/BR1/Roe)" % args.order, "value": value, "unit": "DOF-updates/s",
+        "tpdof_s": 1.0 / value, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Taylor-Green vortex Re=1600 M=0.08, P=%d, StandardDG+BR1+Roe, RK3 (bounded CPU sample)" % args.order, "nodes_per_element": n ** 3},
+        "cpu_baseline": {"value": value, "unit": "DOF-updates/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "restated reference algorithm (oracle/h3d_oracle.cpp, g++ -O2 -fopenmp -ffp-contract=off); the Fortran reference cannot be built here"},
+        "e2e": {"value": value, "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def grid_for(ngpus, ne):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(ngpus, (ngpus, 1, 1))
+
+
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    from horses3d_b200.capi import GpuApi, _ptr
+    from horses3d_b200.dgsem import DGSem, taylor_green_ic
+    from horses3d_b200.hostmesh import GAUSS, HostMesh
+    from horses3d_b200.physics import make_physics
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        obj = [GpuApi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        nccl_id = obj[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- mesh: every rank builds the (cheap) global connectivity, partitions it identically, keeps its part
+    N, n = args.order, args.order + 1
+    px, py, pz = grid_for(world, args.ne)
+    gmesh = HostMesh.box(args.ne * px, amp=args.amp, bFaceOrder=2, ney=args.ne * py, nez=args.ne * pz).connect()
+    nElemGlobal = gmesh.nElem
+    if world > 1:
+        if args.partition == "metis":
+            part = gmesh.partition(world, "metis")
+        else:
+            ex, ey, ez = args.ne * px, args.ne * py, args.ne * pz
+            idx = np.arange(nElemGlobal)
+            part = ((idx % ex) // args.ne + px * (((idx // ex) % ey) // args.ne + py * ((idx // (ex * ey)) // args.ne))).astype(np.int32)
+        mesh = gmesh.extract(part, rank)
+        mesh.geometry(N, GAUSS)
+    else:
+        mesh = gmesh.geometry(N, GAUSS)
+    api = GpuApi(rank=rank, nranks=world, device=local, nccl_id=nccl_id)
+    sem = DGSem(api, mesh, make_physics(flow="NS", mach=0.08, reynolds=1600.0, riemann="roe"))
+    Q0 = taylor_green_ic(sem.node_coordinates())
+    sem.set_Q(Q0)
+    ndof_global = nElemGlobal * n ** 3
+    dt = args.dt
+
+    # ---- device-resident timing (value)
+    for _ in range(args.warmup):
+        sem.TakeRK3Step(0.0, dt)
+    api.call("synchronize")
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    l0 = api.kernel_launches()
+    api.call("timer_begin")
+    for _ in range(args.steps):
+        sem.TakeRK3Step(0.0, dt)
+    ms = C.c_double()
+    api.call("timer_end", C.byref(ms))
+    api.call("synchronize")
+    launches = api.kernel_launches() - l0
+    barrier()
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    t_ms = torch.tensor([ms.value], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    value = ndof_global * 3 * args.steps / (total_ms * 1e-3)
+    assert not sem.checkForNan(), "solution diverged during the benchmark"
+
+    # ---- kernel-level timing of the dominant kernel (roofline), a short profiled pass
+    roof = None
+    if rank == 0:
+        try:
+            api.call("set_option", b"profile_kernels=1")
+            for _ in range(3):
+                sem.TakeRK3Step(0.0, dt)
+            prof = (C.c_double * 16)()
+            api.binding.lib.h3d_kernel_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+            api.binding.lib.h3d_kernel_profile(api.handle, prof, 16)
+            api.call("set_option", b"profile_kernels=0")
+            # prof: [ms_gradient, n_gradient, ms_riemann, n_riemann, ms_volume, n_volume, ms_prolong, n_prolong]
+            vol_ms = prof[4] / max(prof[5], 1.0)
+            peaks = {}
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            peak, src = 6650.0, "fallback"
+            if os.path.exists(pk):
+                peaks = json.load(open(pk))
+                peak, src = float(peaks.get("hbm_gbs", 6650.0)), "measured"
+            ndof_local = sem.NDOF
+            achieved = B_ALG_VOLUME_KERNEL(n) * ndof_local / (vol_ms * 1e-3) / 1e9
+            stage_gbs = B_ALG_NS_STAGE(n) * value / world / 1e9
+            roof = {"bound": "hbm", "kernel": "k_volume<%d>" % n, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "avg_launch_ms": vol_ms,
+                    "alg_bytes_per_dof": B_ALG_VOLUME_KERNEL(n),
+                    "per_kernel_ms": {"gradient": prof[0] / max(prof[1], 1), "riemann": prof[2] / max(prof[3], 1), "volume": vol_ms},
+                    "stage": {"alg_bytes_per_dof_stage": B_ALG_NS_STAGE(n), "achieved": stage_gbs, "frac": stage_gbs / peak}}
+        except Exception as ex:  # profile hooks are optional
+            roof = {"bound": "hbm", "error": str(ex)}
+
+    # ---- end-to-end through the C ABI with HOST buffers (strict drop-in: state crosses PCIe every step)
+    e2e = None
+    if not args.no_e2e:
+        hostQ = torch.empty(Q0.shape, dtype=torch.float64, pin_memory=True)
+        hostQ.copy_(torch.from_numpy(sem.Q()))
+        qnp = hostQ.numpy()
+        nsteps = max(3, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            api.call("upload_Q", _ptr(qnp, np.float64))
+            sem.TakeRK3Step(0.0, dt)
+            api.call("download", _ptr(qnp, np.float64), None, None, None, None)
+            sem.ComputeMaxResiduals()
+        barrier()
+        el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e_val = ndof_global * 3 * nsteps / float(el.item())
+        # resident mode: what a time loop of the reference does per step once the state lives on the device
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            sem.TakeRK3Step(0.0, dt)
+            sem.ComputeMaxResiduals()
+            sem.volume_monitors()
+            sem.checkForNan()
+        barrier()
+        el2 = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el2, op=dist.ReduceOp.MAX)
+        e2e = {"value": e2e_val, "unit": "DOF-updates/s", "h2d_bytes_per_step": int(qnp.nbytes), "d2h_bytes_per_step": int(qnp.nbytes + 48),
+               "mode": "strict drop-in: h3d_upload_Q + h3d_rk_step + h3d_download + h3d_max_residuals per step, pinned host buffers",
+               "resident": {"value": ndof_global * 3 * nsteps / float(el2.item()), "unit": "DOF-updates/s", "d2h_bytes_per_step": 8 * (6 + 4 * 4 + 6),
+                            "mode": "state resident on the device; per step h3d_rk_step + residuals + KE/KE-rate/enstrophy monitors + NaN check"}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cms, cores, sample = cpu_sample(args, 2, 1)
+        cpu = {"value": v, "unit": "DOF-updates/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "DOF-updates/s (TGV P=%d explicit RK3, NS/BR1/Roe)" % N, "value": value, "unit": "DOF-updates/s", "tpdof_s": 1.0 / value,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Taylor-Green vortex Re=1600 M=0.08, %dx%dx%d curvilinear hex elements, P=%d Gauss, StandardDG+BR1+Roe, RK3, fixed dt"
+                                   % (args.ne * px, args.ne * py, args.ne * pz, N),
+                       "ndof": ndof_global, "elements_per_gpu": args.ne ** 3, "partition": args.partition if world > 1 else "none",
+                       "l2": "inputs larger than L2 (state + gradients + metrics = %.1f GB per GPU)" % (sem.NDOF * 8 * (30 + 10) / 1e9)},
+            "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

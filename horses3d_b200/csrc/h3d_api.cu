@@ -1,0 +1,832 @@
+// C ABI of libh3dgpu.so (include/h3d_gpu.h): context, device storage, launch orchestration, reductions,
+// NCCL face exchange.  One context = one rank = one B200.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "h3d_gpu.h"
+#include "h3d_kernels.cuh"
+
+using namespace h3d;
+
+namespace {
+thread_local std::string g_create_err;
+}
+
+struct h3d_context {
+    int rank = 0, nranks = 1, device = 0;
+    std::string err;
+    cudaStream_t sCompute = nullptr, sComm = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr, evT0 = nullptr, evT1 = nullptr, evFaces = nullptr, evGrad = nullptr, evSent = nullptr;
+    ncclComm_t comm = nullptr;
+    long long launches = 0;
+    H3dPhysics physics{};
+    Phys ph{};
+    bool havePhysics = false, haveBasis = false, haveMesh = false;
+    int N = -1, n = 0, nodeType = H3D_GAUSS;
+    std::vector<double> hx;   // node positions of the 1-D set (MaxTimeStep)
+    int nElem = 0, nFace = 0, nSeq = 0;          // device order: [0,nSeq) interior elements, [nSeq,nElem) MPI elements
+    int nFaceLocal = 0;                           // device face order: [0,nFaceLocal) interior+boundary, then MPI faces
+    std::vector<int> permE, invPermE, permF, invPermF;   // device index -> host index and inverse
+    DevMesh m{};
+    std::vector<void*> allocs;
+    double* staging = nullptr; size_t stagingBytes = 0;
+    double* dSource = nullptr;
+    double* dPartial = nullptr; double* hScalars = nullptr;  // reduction scratch (device) / pinned host
+    bool facesValid = false;
+    int storeQDotAlways = 0;
+    int profile = 0;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    double profMs[4] = {0, 0, 0, 0}; double profCount[4] = {0, 0, 0, 0};
+    // halo
+    int nNbr = 0; std::vector<int> nbrRank, nbrCount, nbrOffset;   // offsets in faces
+    int nHaloFaces = 0;
+    int *dHaloFace = nullptr, *dHaloSide = nullptr, *dNbrOffset = nullptr, *dNbrOfFace = nullptr;
+    int *dPermE = nullptr, *dPermF = nullptr;
+    double *dSend = nullptr, *dRecv = nullptr;
+};
+
+#define CTX_CHECK(call)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+            return 2;                                                                                     \
+        }                                                                                                 \
+    } while (0)
+#define NCCL_CHECK(call)                                                                                  \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) {                                                                          \
+            h->err = std::string(#call) + ": " + ncclGetErrorString(r_);                                  \
+            return 3;                                                                                     \
+        }                                                                                                 \
+    } while (0)
+
+namespace {
+
+template <typename T>
+int devAlloc(h3d_context* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return 2; }
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+int ensureStaging(h3d_context* h, size_t bytes) {
+    if (h->stagingBytes >= bytes) return 0;
+    if (h->staging) cudaFree(h->staging);
+    h->staging = nullptr; h->stagingBytes = 0;
+    CTX_CHECK(cudaMalloc((void**)&h->staging, bytes));
+    h->stagingBytes = bytes;
+    return 0;
+}
+
+// src[e_host][node][C] (AoS, host element order) -> dst[(cOff + c)][e_dev][node]
+__global__ void k_aos_to_soa(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ perm, int nE, int nn, int C, int cOff) {
+    const size_t total = (size_t)nE * nn;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int ed = (int)(t / nn), node = (int)(t % nn);
+        const int eh = perm ? perm[ed] : ed;
+        for (int c = 0; c < C; ++c) dst[((size_t)(cOff + c) * nE + ed) * nn + node] = src[((size_t)eh * nn + node) * C + c];
+    }
+}
+__global__ void k_soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ perm, int nE, int nn, int C) {
+    const size_t total = (size_t)nE * nn;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int ed = (int)(t / nn), node = (int)(t % nn);
+        const int eh = perm ? perm[ed] : ed;
+        for (int c = 0; c < C; ++c) dst[((size_t)eh * nn + node) * C + c] = src[((size_t)c * nE + ed) * nn + node];
+    }
+}
+
+// ---- reductions ------------------------------------------------------------------------------------------
+template <int K, int OP>   // OP 0 = max, 1 = min, 2 = sum
+__device__ __forceinline__ void blockReduce(double (&v)[K], double* out /*[K] per block*/) {
+    __shared__ double sh[32][K];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+        double x = v[q];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double y = __shfl_down_sync(0xffffffffu, x, o);
+            x = OP == 0 ? fmax(x, y) : (OP == 1 ? fmin(x, y) : x + y);
+        }
+        if (lane == 0) sh[wid][q] = x;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            double x = lane < nw ? sh[lane][q] : (OP == 0 ? -1.7976931348623157e308 : (OP == 1 ? 1.7976931348623157e308 : 0.0));
+            for (int o = 16; o > 0; o >>= 1) {
+                const double y = __shfl_down_sync(0xffffffffu, x, o);
+                x = OP == 0 ? fmax(x, y) : (OP == 1 ? fmin(x, y) : x + y);
+            }
+            if (lane == 0) out[q] = x;
+        }
+    }
+}
+
+constexpr int RED_BLOCKS = 592, RED_THREADS = 256;   // 4 CTAs per SM on 148 SMs
+
+// ComputeMaxResiduals (DGSEMClass.f90:770-856) + checkForNan flag on Q (ExplicitMethods.f90:1879-1886)
+__global__ void __launch_bounds__(RED_THREADS) k_red_residual(DevMesh m, size_t nn, double* partial) {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            v[q] = fmax(v[q], fabs(m.QDot[(size_t)q * nn + t]));
+            if (isnan(m.Q[(size_t)q * nn + t])) v[5] = 1.0;
+        }
+    }
+    blockReduce<6, 0>(v, partial + (size_t)blockIdx.x * 6);
+}
+
+// MaxTimeStep (DGSEMClass.f90:870-1034)
+__global__ void __launch_bounds__(RED_THREADS) k_red_timestep(DevMesh m, Phys ph, size_t nn, double cfl, double dcfl, double dxi, double* partial) {
+    double v[2] = {1.7976931348623157e308, 1.7976931348623157e308};
+    const double dxi2 = dxi * dxi;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (size_t)gridDim.x * blockDim.x) {
+        double Q[5], ja[9];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) Q[q] = m.Q[(size_t)q * nn + t];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) ja[c] = m.Ja[(size_t)c * nn + t];
+        const double u = fabs(Q[1] / Q[0]), vv = fabs(Q[2] / Q[0]), w = fabs(Q[3] / Q[0]);
+        const double p = pressure(ph, Q);
+        const double a = sqrt(ph.gamma * p / Q[0]);
+        const double e0 = u + a, e1 = vv + a, e2 = w + a;
+        const double jac = m.J[t];
+        const double l1 = fabs(ja[0] * e0 + ja[1] * e1 + ja[2] * e2) * dxi;
+        const double l2 = fabs(ja[3] * e0 + ja[4] * e1 + ja[5] * e2) * dxi;
+        const double l3 = fabs(ja[6] * e0 + ja[7] * e1 + ja[8] * e2) * dxi;
+        v[0] = fmin(v[0], cfl * fabs(jac) / (l1 + l2 + l3));
+        if (ph.ns) {
+            const double T = ph.gammaM2 * p / Q[0];
+            const double mu = sutherland(ph, T);
+            const double v1 = mu * dxi2 * fabs(ja[0] + ja[1] + ja[2]);
+            const double v2 = mu * dxi2 * fabs(ja[3] + ja[4] + ja[5]);
+            const double v3 = mu * dxi2 * fabs(ja[6] + ja[7] + ja[8]);
+            v[1] = fmin(v[1], dcfl * fabs(jac) / (v1 + v2 + v3));
+        }
+    }
+    blockReduce<2, 1>(v, partial + (size_t)blockIdx.x * 2);
+}
+
+// ScalarVolumeIntegral_Local (VolumeIntegrals.f90:167-286): all four integrals in one pass
+__global__ void __launch_bounds__(RED_THREADS) k_red_integrals(DevMesh m, size_t nn, int n, double* partial) {
+    double v[4] = {0, 0, 0, 0};
+    const int N2 = n * n, N3 = N2 * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (size_t)gridDim.x * blockDim.x) {
+        const int node = (int)(t % N3);
+        const int i = node % n, j = (node / n) % n, k = node / N2;
+        const double wJ = m.w[i] * m.w[j] * m.w[k] * m.J[t];
+        double Q[5], QD[5], gx[5], gy[5], gz[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { Q[q] = m.Q[(size_t)q * nn + t]; QD[q] = m.QDot[(size_t)q * nn + t]; gx[q] = m.Ux[(size_t)q * nn + t]; gy[q] = m.Uy[(size_t)q * nn + t]; gz[q] = m.Uz[(size_t)q * nn + t]; }
+        v[0] = v[0] + wJ;
+        double ke = pow2(Q[1]); ke = ke + pow2(Q[2]); ke = ke + pow2(Q[3]); ke = 0.5 * ke / Q[0];
+        v[1] = v[1] + wJ * ke;
+        double uvw = Q[1] / Q[0];
+        double kr = uvw * QD[1] - 0.5 * pow2(uvw) * QD[0];
+        uvw = Q[2] / Q[0]; kr = kr + uvw * QD[2] - 0.5 * pow2(uvw) * QD[0];
+        uvw = Q[3] / Q[0]; kr = kr + uvw * QD[3] - 0.5 * pow2(uvw) * QD[0];
+        v[2] = v[2] + wJ * kr;
+        double ux[3], uy[3], uz[3];
+        velocity_gradients(Q, gx, gy, gz, ux, uy, uz);
+        const double ens = pow2(uy[2] - uz[1]) + pow2(uz[0] - ux[2]) + pow2(ux[1] - uy[0]);
+        v[3] = v[3] + wJ * ens;
+    }
+    blockReduce<4, 2>(v, partial + (size_t)blockIdx.x * 4);
+}
+
+template <int K, int OP>
+__global__ void __launch_bounds__(1024) k_red_final(const double* partial, int nBlocks, double* out) {
+    double v[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) v[q] = OP == 0 ? -1.7976931348623157e308 : (OP == 1 ? 1.7976931348623157e308 : 0.0);
+    for (int b = threadIdx.x; b < nBlocks; b += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < K; ++q) { const double y = partial[(size_t)b * K + q]; v[q] = OP == 0 ? fmax(v[q], y) : (OP == 1 ? fmin(v[q], y) : v[q] + y); }
+    }
+    blockReduce<K, OP>(v, out);
+}
+
+// ---- halo pack / unpack ----------------------------------------------------------------------------------
+// send buffer per neighbour: [var][face in exchange order][m]; NV = 5 (Q) or 15 (gradients: dir*5 + eq)
+__global__ void k_halo_pack(DevMesh m, const int* haloFace, const int* haloSide, int nHalo, int n2, int NV, const double* src, double* buf,
+                            const int* nbrOffset, const int* nbrOfFace) {
+    const size_t total = (size_t)nHalo * n2 * NV;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int mm = (int)(t % n2); size_t r = t / n2;
+        const int hf = (int)(r % nHalo); const int vv = (int)(r / nHalo);
+        const int f = haloFace[hf], side = haloSide[hf];
+        const int grp = vv / 5, eq = vv % 5;
+        const int nb = nbrOfFace[hf], off = nbrOffset[nb], cnt = nbrOffset[nb + 1] - off;
+        const double val = src[(((size_t)(grp * 2 + side) * 5 + eq) * m.nFace + f) * n2 + mm];
+        buf[(size_t)off * n2 * NV + ((size_t)vv * cnt + (hf - off)) * n2 + mm] = val;
+    }
+}
+__global__ void k_halo_unpack(DevMesh m, const int* haloFace, const int* haloSide, int nHalo, int n2, int NV, double* dst, const double* buf,
+                              const int* nbrOffset, const int* nbrOfFace) {
+    const size_t total = (size_t)nHalo * n2 * NV;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int mm = (int)(t % n2); size_t r = t / n2;
+        const int hf = (int)(r % nHalo); const int vv = (int)(r / nHalo);
+        const int f = haloFace[hf], side = 1 - haloSide[hf];
+        const int grp = vv / 5, eq = vv % 5;
+        const int nb = nbrOfFace[hf], off = nbrOffset[nb], cnt = nbrOffset[nb + 1] - off;
+        dst[(((size_t)(grp * 2 + side) * 5 + eq) * m.nFace + f) * n2 + mm] = buf[(size_t)off * n2 * NV + ((size_t)vv * cnt + (hf - off)) * n2 + mm];
+    }
+}
+
+// ---- launch helpers --------------------------------------------------------------------------------------
+template <int n> int launchProlong(h3d_context* h, int e0, int e1, cudaStream_t s) {
+    if (e1 <= e0) return 0;
+    const int E = epbFor(n), blocks = (e1 - e0 + E - 1) / E;
+    k_prolong_q<n><<<blocks, E * n * n * n, smemProlong(n), s>>>(h->m, e0, e1);
+    ++h->launches; return 0;
+}
+template <int n> int launchGradient(h3d_context* h, int e0, int e1, cudaStream_t s) {
+    if (e1 <= e0) return 0;
+    const int E = epbFor(n), blocks = (e1 - e0 + E - 1) / E;
+    k_gradient<n><<<blocks, E * n * n * n, smemGradient(n), s>>>(h->m, h->ph, e0, e1);
+    ++h->launches; return 0;
+}
+template <int n> int launchRiemann(h3d_context* h, int f0, int f1, cudaStream_t s) {
+    if (f1 <= f0) return 0;
+    const long long threads = (long long)(f1 - f0) * n * n;
+    k_riemann<n><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(h->m, h->ph, f0, f1);
+    ++h->launches; return 0;
+}
+template <int n> int launchVolume(h3d_context* h, const RkArgs& rk, int e0, int e1, cudaStream_t s) {
+    if (e1 <= e0) return 0;
+    const int E = epbFor(n), blocks = (e1 - e0 + E - 1) / E;
+    if (h->ph.averaging >= 0 && h->physics.inviscid == H3D_SPLIT_DG)
+        k_volume<n, true><<<blocks, E * n * n * n, smemVolume(n, true), s>>>(h->m, h->ph, rk, e0, e1);
+    else
+        k_volume<n, false><<<blocks, E * n * n * n, smemVolume(n, false), s>>>(h->m, h->ph, rk, e0, e1);
+    ++h->launches; return 0;
+}
+template <int n> int setAttrs(h3d_context* h) {
+    CTX_CHECK(cudaFuncSetAttribute(k_prolong_q<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemProlong(n)));
+    CTX_CHECK(cudaFuncSetAttribute(k_gradient<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient(n)));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume(n, false)));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume(n, true)));
+    return 0;
+}
+
+#define DISPATCH_N(h, CALL)                                     \
+    switch ((h)->n) {                                           \
+        case 2: return CALL(2);                                 \
+        case 3: return CALL(3);                                 \
+        case 4: return CALL(4);                                 \
+        case 5: return CALL(5);                                 \
+        case 6: return CALL(6);                                 \
+        case 7: return CALL(7);                                 \
+        case 8: return CALL(8);                                 \
+        case 9: return CALL(9);                                 \
+        case 10: return CALL(10);                               \
+        default: (h)->err = "polynomial order not instantiated (supported N = 1..9)"; return 1; \
+    }
+
+int doProlong(h3d_context* h, int e0, int e1, cudaStream_t s) {
+#define C_(NN) launchProlong<NN>(h, e0, e1, s)
+    DISPATCH_N(h, C_)
+#undef C_
+}
+int doGradient(h3d_context* h, int e0, int e1, cudaStream_t s) {
+#define C_(NN) launchGradient<NN>(h, e0, e1, s)
+    DISPATCH_N(h, C_)
+#undef C_
+}
+int doRiemann(h3d_context* h, int f0, int f1, cudaStream_t s) {
+#define C_(NN) launchRiemann<NN>(h, f0, f1, s)
+    DISPATCH_N(h, C_)
+#undef C_
+}
+int doVolume(h3d_context* h, const RkArgs& rk, int e0, int e1, cudaStream_t s) {
+#define C_(NN) launchVolume<NN>(h, rk, e0, e1, s)
+    DISPATCH_N(h, C_)
+#undef C_
+}
+int doAttrs(h3d_context* h) {
+#define C_(NN) setAttrs<NN>(h)
+    DISPATCH_N(h, C_)
+#undef C_
+}
+
+// halo exchange of NV variables (5: Q traces, 15: gradient traces) on the comm stream
+int haloExchange(h3d_context* h, int NV, const double* srcField, double* dstField, const int* dNbrOffset, const int* dNbrOfFace) {
+    const int n2 = h->n * h->n;
+    const size_t total = (size_t)h->nHaloFaces * n2 * NV;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+    k_halo_pack<<<blocks, 256, 0, h->sComm>>>(h->m, h->dHaloFace, h->dHaloSide, h->nHaloFaces, n2, NV, srcField, h->dSend, dNbrOffset, dNbrOfFace);
+    ++h->launches;
+    NCCL_CHECK(ncclGroupStart());
+    for (int b = 0; b < h->nNbr; ++b) {
+        const size_t off = (size_t)h->nbrOffset[b] * n2 * NV, cnt = (size_t)h->nbrCount[b] * n2 * NV;
+        NCCL_CHECK(ncclSend(h->dSend + off, cnt, ncclDouble, h->nbrRank[b], h->comm, h->sComm));
+        NCCL_CHECK(ncclRecv(h->dRecv + off, cnt, ncclDouble, h->nbrRank[b], h->comm, h->sComm));
+    }
+    NCCL_CHECK(ncclGroupEnd());
+    k_halo_unpack<<<blocks, 256, 0, h->sComm>>>(h->m, h->dHaloFace, h->dHaloSide, h->nHaloFaces, n2, NV, dstField, h->dRecv, dNbrOffset, dNbrOfFace);
+    ++h->launches;
+    return 0;
+}
+
+}  // namespace
+
+namespace {
+// optional per-kernel CUDA-event timing (bench.py roofline): classes 0 gradient, 1 riemann, 2 volume, 3 prolong
+struct ProfScope {
+    h3d_context* h; int cls; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(h3d_context* h_, int cls_, cudaStream_t s_) : h(h_), cls(cls_), s(s_) {
+        if (h->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    }
+    ~ProfScope() { if (h->profile) { cudaEventRecord(b, s); h->prof.push_back({cls, a, b}); } }
+};
+
+// One residual evaluation (ComputeTimeDerivative, SpatialDiscretization.f90:227-320) with the RK update fused
+// into its last kernel.  Stream choreography for nranks > 1 ("Distributed backend"):
+//   comm   : pack Q traces -> send/recv -> unpack            | pack grad traces -> send/recv -> unpack
+//   compute: gradient(interior elems) | wait | gradient(MPI elems) | riemann(local faces) | wait | riemann(MPI faces) | volume(all)
+int residual(h3d_context* h, const RkArgs& rk) {
+    cudaStream_t sc = h->sCompute;
+    const bool multi = h->nNbr > 0;
+    const bool grads = h->physics.computeGradients != 0;
+    int rc;
+    if (!h->facesValid) { ProfScope ps(h, 3, sc); if ((rc = doProlong(h, 0, h->nElem, sc))) return rc; }
+    if (multi) {
+        CTX_CHECK(cudaEventRecord(h->evFaces, sc));
+        CTX_CHECK(cudaStreamWaitEvent(h->sComm, h->evFaces, 0));
+        if ((rc = haloExchange(h, 5, h->m.fQ, h->m.fQ, h->dNbrOffset, h->dNbrOfFace))) return rc;
+        CTX_CHECK(cudaEventRecord(h->evA, h->sComm));
+    }
+    if (grads) {
+        { ProfScope ps(h, 0, sc); if ((rc = doGradient(h, 0, h->nSeq, sc))) return rc; }
+        if (multi) {
+            CTX_CHECK(cudaStreamWaitEvent(sc, h->evA, 0));
+            if ((rc = doGradient(h, h->nSeq, h->nElem, sc))) return rc;
+            if (h->ph.ns) {
+                CTX_CHECK(cudaEventRecord(h->evGrad, sc));
+                CTX_CHECK(cudaStreamWaitEvent(h->sComm, h->evGrad, 0));
+                if ((rc = haloExchange(h, 15, h->m.fU, h->m.fU, h->dNbrOffset, h->dNbrOfFace))) return rc;
+                CTX_CHECK(cudaEventRecord(h->evB, h->sComm));
+            }
+        }
+    } else if (multi) {
+        CTX_CHECK(cudaStreamWaitEvent(sc, h->evA, 0));
+    }
+    { ProfScope ps(h, 1, sc); if ((rc = doRiemann(h, 0, h->nFaceLocal, sc))) return rc; }
+    if (multi) {
+        if (grads && h->ph.ns) CTX_CHECK(cudaStreamWaitEvent(sc, h->evB, 0));
+        if ((rc = doRiemann(h, h->nFaceLocal, h->nFace, sc))) return rc;
+    }
+    { ProfScope ps(h, 2, sc); if ((rc = doVolume(h, rk, 0, h->nElem, sc))) return rc; }
+    h->facesValid = rk.prolong != 0;
+    CTX_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int reduceAcrossRanks(h3d_context* h, double* dvals, int count, ncclRedOp_t op) {
+    if (h->nranks > 1) NCCL_CHECK(ncclAllReduce(dvals, dvals, count, ncclDouble, op, h->comm, h->sCompute));
+    return 0;
+}
+
+}  // namespace
+
+// ==========================================================================================================
+extern "C" {
+
+int h3d_get_nccl_unique_id(void* id128) {
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return 3;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    std::memcpy(id128, &id, 128);
+    return 0;
+}
+
+int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nccl_unique_id) {
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_create_err = std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (there is no CPU fallback)"; return 2; }
+    if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return 1; }
+    h3d_context* h = new h3d_context();
+    h->rank = rank; h->nranks = nranks; h->device = device;
+    auto fail = [&](const std::string& msg) { g_create_err = msg; delete h; return 2; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) return fail(std::string("libh3dgpu is built for sm_100a only; device is ") + prop.name);
+    if (cudaStreamCreateWithFlags(&h->sCompute, cudaStreamNonBlocking) != cudaSuccess) return fail("stream creation failed");
+    cudaStreamCreateWithFlags(&h->sComm, cudaStreamNonBlocking);
+    for (cudaEvent_t* ev : {&h->evA, &h->evB, &h->evFaces, &h->evGrad, &h->evSent}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
+    cudaMalloc((void**)&h->dPartial, sizeof(double) * (RED_BLOCKS * 8 + 64));
+    cudaMallocHost((void**)&h->hScalars, sizeof(double) * 64);
+    if (nranks > 1) {
+        if (!nccl_unique_id) return fail("nranks > 1 needs an ncclUniqueId");
+        ncclUniqueId id; std::memcpy(&id, nccl_unique_id, 128);
+        ncclResult_t r = ncclCommInitRank(&h->comm, nranks, id, rank);
+        if (r != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    }
+    *out = h;
+    return 0;
+}
+
+int h3d_destroy(h3d_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->comm) ncclCommDestroy(h->comm);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->staging) cudaFree(h->staging);
+    if (h->dSource) cudaFree(h->dSource);
+    if (h->dPartial) cudaFree(h->dPartial);
+    if (h->hScalars) cudaFreeHost(h->hScalars);
+    for (cudaEvent_t ev : {h->evA, h->evB, h->evFaces, h->evGrad, h->evSent, h->evT0, h->evT1}) if (ev) cudaEventDestroy(ev);
+    if (h->sCompute) cudaStreamDestroy(h->sCompute);
+    if (h->sComm) cudaStreamDestroy(h->sComm);
+    delete h;
+    return 0;
+}
+
+const char* h3d_last_error(h3d_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int h3d_last_error_copy(h3d_handle h, char* buf, int len) {
+    const char* s = h3d_last_error(h);
+    if (len <= 0) return 1;
+    std::strncpy(buf, s, len - 1); buf[len - 1] = 0;
+    return 0;
+}
+
+int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
+    if (p->riemann != H3D_RIEMANN_ROE && p->riemann != H3D_RIEMANN_LXF && p->riemann != H3D_RIEMANN_CENTRAL) { h->err = "Riemann Solver not recognized."; return 1; }
+    if (p->averaging != H3D_AVG_STANDARD && p->averaging != H3D_AVG_KENNEDYGRUBER && p->averaging != H3D_AVG_PIROZZOLI) { h->err = "Averaging not recognized."; return 1; }
+    if (p->inviscid != H3D_STANDARD_DG && p->inviscid != H3D_SPLIT_DG) { h->err = "Requested inviscid discretization is not implemented."; return 1; }
+    h->physics = *p;
+    Phys& q = h->ph;
+    q.gamma = p->gamma; q.gm1 = p->gammaMinus1; q.gammaM2 = p->gammaM2; q.mu = p->mu; q.mu_to_kappa = p->mu_to_kappa;
+    q.S_div_Tref = p->S_div_Tref; q.T_renorm = p->T_renorm; q.lambdaStab = p->lambdaStab; q.Cs = p->smagorinsky_Cs;
+    q.ns = p->flowIsNavierStokes; q.riemann = p->riemann; q.averaging = p->averaging; q.les = p->les;
+    h->havePhysics = true;
+    return 0;
+}
+
+int h3d_set_basis(h3d_handle h, int N, int nodeType, const double* x, const double* w, const double* D, const double* hatD,
+                  const double* sharpD, const double* v, const double* b) {
+    if (N < 1 || N > 9) { h->err = "polynomial order not instantiated (supported N = 1..9)"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    const int n = N + 1;
+    h->N = N; h->n = n; h->nodeType = nodeType; h->hx.assign(x, x + n);
+    std::vector<double> T(n * n);
+    auto up = [&](const double* src, size_t cnt, const double** dst) -> int {
+        double* d; if (devAlloc(h, &d, cnt)) return 2;
+        if (cudaMemcpy(d, src, cnt * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "basis upload failed"; return 2; }
+        *dst = d; return 0;
+    };
+    auto upT = [&](const double* M, const double** dst) -> int {
+        for (int i = 0; i < n; ++i) for (int l = 0; l < n; ++l) T[l * n + i] = M[i * n + l];
+        return up(T.data(), (size_t)n * n, dst);
+    };
+    if (upT(hatD, &h->m.hatDT) || upT(D, &h->m.DT) || upT(sharpD, &h->m.sharpDT)) return 2;
+    if (up(v, 2 * n, &h->m.v) || up(b, 2 * n, &h->m.b) || up(w, n, &h->m.w)) return 2;
+    // rotation table: element-trace node (ii,jj) -> face node (i,j), MeshTypes.f90:70-108
+    std::vector<int> rot(8 * n * n);
+    for (int r = 0; r < 8; ++r) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+        int ii, jj;
+        switch (r) {
+            case 0: ii = i; jj = j; break;
+            case 1: ii = N - j; jj = i; break;
+            case 2: ii = N - i; jj = N - j; break;
+            case 3: ii = j; jj = N - i; break;
+            case 4: ii = j; jj = i; break;
+            case 5: ii = N - i; jj = j; break;
+            case 6: ii = N - j; jj = N - i; break;
+            default: ii = i; jj = N - j; break;
+        }
+        rot[r * n * n + jj * n + ii] = j * n + i;
+    }
+    int* dr; if (devAlloc(h, &dr, rot.size())) return 2;
+    CTX_CHECK(cudaMemcpy(dr, rot.data(), rot.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->m.rotmap = dr;
+    h->m.n = n;
+    h->haveBasis = true;
+    return doAttrs(h);
+}
+
+int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+                 const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone,
+                 const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,
+                 const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
+                 const double* faceJacobian, const double* faceX, const double* faceSurface) {
+    (void)x; (void)faceX; (void)faceElemSide;
+    if (!h->haveBasis) { h->err = "h3d_set_basis must precede h3d_set_mesh"; return 1; }
+    if (h->haveMesh) { h->err = "h3d_set_mesh may be called once per context"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    const int n = h->n, n2 = n * n, n3 = n2 * n;
+    h->nElem = nElem; h->nFace = nFace;
+    DevMesh& m = h->m;
+    m.nElem = nElem; m.nFace = nFace;
+    // ---- device numbering: interior elements first, elements touching MPI faces last; local faces first
+    std::vector<char> isMpiElem(nElem, 0);
+    for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_MPI) for (int s = 0; s < 2; ++s) if (faceElem[2 * f + s] >= 0) isMpiElem[faceElem[2 * f + s]] = 1;
+    h->permE.clear(); h->invPermE.assign(nElem, -1);
+    for (int pass = 0; pass < 2; ++pass) for (int e = 0; e < nElem; ++e) if ((int)isMpiElem[e] == pass) { h->invPermE[e] = (int)h->permE.size(); h->permE.push_back(e); }
+    h->nSeq = 0; for (int e = 0; e < nElem; ++e) if (!isMpiElem[e]) ++h->nSeq;
+    h->permF.clear(); h->invPermF.assign(nFace, -1);
+    for (int pass = 0; pass < 2; ++pass) for (int f = 0; f < nFace; ++f) if ((faceType[f] == H3D_FACE_MPI) == (pass == 1)) { h->invPermF[f] = (int)h->permF.size(); h->permF.push_back(f); }
+    h->nFaceLocal = 0; for (int f = 0; f < nFace; ++f) if (faceType[f] != H3D_FACE_MPI) ++h->nFaceLocal;
+    // ---- connectivity tables
+    std::vector<int> eFace(6 * (size_t)nElem), eInfo(6 * (size_t)nElem), fInfo(nFace);
+    for (int ed = 0; ed < nElem; ++ed) {
+        const int eh = h->permE[ed];
+        for (int lf = 0; lf < 6; ++lf) {
+            const int f = elemFace[6 * eh + lf], side = elemFaceSide[6 * eh + lf];
+            if (f < 0 || f >= nFace || side < 0 || side > 1) { h->err = "invalid element->face table"; return 1; }
+            const int ridx = side ? faceRot[f] : 0;
+            eFace[6 * (size_t)ed + lf] = h->invPermF[f];
+            eInfo[6 * (size_t)ed + lf] = side | (ridx << 1) | (faceType[f] << 4) | ((faceZone[f] + 1) << 8);
+        }
+    }
+    for (int fd = 0; fd < nFace; ++fd) { const int fh = h->permF[fd]; fInfo[fd] = faceType[fh] | ((faceZone[fh] + 1) << 8); }
+    int *dEF, *dEI, *dFI, *dPermE, *dPermF;
+    if (devAlloc(h, &dEF, eFace.size()) || devAlloc(h, &dEI, eInfo.size()) || devAlloc(h, &dFI, fInfo.size()) || devAlloc(h, &dPermE, nElem) || devAlloc(h, &dPermF, nFace)) return 2;
+    CTX_CHECK(cudaMemcpy(dEF, eFace.data(), eFace.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(dEI, eInfo.data(), eInfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(dFI, fInfo.data(), fInfo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(dPermE, h->permE.data(), nElem * sizeof(int), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(dPermF, h->permF.data(), nFace * sizeof(int), cudaMemcpyHostToDevice));
+    m.elemFace = dEF; m.elemInfo = dEI; m.faceInfo = dFI; h->dPermE = dPermE; h->dPermF = dPermF;
+    // ---- fields
+    const size_t ne = (size_t)nElem * n3, nf = (size_t)nFace * n2;
+    double *Ja, *J, *invJ, *fN, *fT1, *fT2, *fJ;
+    if (devAlloc(h, &m.Q, 5 * ne) || devAlloc(h, &m.G, 5 * ne) || devAlloc(h, &m.QDot, 5 * ne) || devAlloc(h, &m.Ux, 5 * ne) || devAlloc(h, &m.Uy, 5 * ne) ||
+        devAlloc(h, &m.Uz, 5 * ne) || devAlloc(h, &Ja, 9 * ne) || devAlloc(h, &J, ne) || devAlloc(h, &invJ, ne) || devAlloc(h, &m.fQ, 10 * nf) ||
+        devAlloc(h, &m.fU, 30 * nf) || devAlloc(h, &m.fStar, 5 * nf) || devAlloc(h, &fN, 3 * nf) || devAlloc(h, &fT1, 3 * nf) || devAlloc(h, &fT2, 3 * nf) || devAlloc(h, &fJ, nf))
+        return 2;
+    for (double* p : {m.Q, m.G, m.QDot, m.Ux, m.Uy, m.Uz}) CTX_CHECK(cudaMemset(p, 0, 5 * ne * sizeof(double)));
+    CTX_CHECK(cudaMemset(m.fQ, 0, 10 * nf * sizeof(double))); CTX_CHECK(cudaMemset(m.fU, 0, 30 * nf * sizeof(double))); CTX_CHECK(cudaMemset(m.fStar, 0, 5 * nf * sizeof(double)));
+    if (ensureStaging(h, std::max(5 * ne, 3 * nf) * sizeof(double))) return 2;
+    auto upElem = [&](const double* src, int C, double* dst, int cOff) -> int {
+        CTX_CHECK(cudaMemcpy(h->staging, src, (size_t)C * ne * sizeof(double), cudaMemcpyHostToDevice));
+        k_aos_to_soa<<<148 * 8, 256>>>(h->staging, dst, dPermE, nElem, n3, C, cOff);
+        CTX_CHECK(cudaDeviceSynchronize());
+        return 0;
+    };
+    auto upFace = [&](const double* src, int C, double* dst) -> int {
+        CTX_CHECK(cudaMemcpy(h->staging, src, (size_t)C * nf * sizeof(double), cudaMemcpyHostToDevice));
+        k_aos_to_soa<<<148 * 8, 256>>>(h->staging, dst, dPermF, nFace, n2, C, 0);
+        CTX_CHECK(cudaDeviceSynchronize());
+        return 0;
+    };
+    if (upElem(jGradXi, 3, Ja, 0) || upElem(jGradEta, 3, Ja, 3) || upElem(jGradZeta, 3, Ja, 6) || upElem(jacobian, 1, J, 0)) return 2;
+    {   // invJacobian = 1/jacobian computed as the reference does (MappedGeometry.f90:380-382)
+        std::vector<double> inv(ne);
+        for (size_t q = 0; q < ne; ++q) inv[q] = 1.0 / jacobian[q];
+        if (upElem(inv.data(), 1, invJ, 0)) return 2;
+    }
+    if (upFace(faceNormal, 3, fN) || upFace(faceT1, 3, fT1) || upFace(faceT2, 3, fT2) || upFace(faceJacobian, 1, fJ)) return 2;
+    m.Ja = Ja; m.J = J; m.invJ = invJ; m.fN = fN; m.fT1 = fT1; m.fT2 = fT2; m.fJ = fJ;
+    // LES filter widths (SpatialDiscretization.f90:420, :1377), evaluated on the host
+    {
+        std::vector<double> de(nElem, 0.0), df(nFace, 0.0);
+        if (volume) for (int ed = 0; ed < nElem; ++ed) de[ed] = std::pow(volume[h->permE[ed]] / (double)n3, 1.0 / 3.0);
+        if (faceSurface) for (int fd = 0; fd < nFace; ++fd) df[fd] = std::sqrt(faceSurface[h->permF[fd]] / (double)n2);
+        double *dde, *ddf;
+        if (devAlloc(h, &dde, nElem) || devAlloc(h, &ddf, nFace)) return 2;
+        CTX_CHECK(cudaMemcpy(dde, de.data(), nElem * sizeof(double), cudaMemcpyHostToDevice));
+        CTX_CHECK(cudaMemcpy(ddf, df.data(), nFace * sizeof(double), cudaMemcpyHostToDevice));
+        m.lesDelta = dde; m.fDelta = ddf;
+        if (h->physics.les != H3D_LES_NONE && (!volume || !faceSurface)) { h->err = "LES needs element volumes and face surfaces"; return 1; }
+    }
+    m.S = nullptr; m.bcType = nullptr; m.bcParams = nullptr;
+    for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_BOUNDARY && faceZone[f] < 0) { h->err = "boundary face without a zone"; return 1; }
+    h->haveMesh = true; h->facesValid = false;
+    return 0;
+}
+
+int h3d_set_boundary_conditions(h3d_handle h, int nZones, const int* bcType, const double* bcParams) {
+    CTX_CHECK(cudaSetDevice(h->device));
+    int* dt; double* dp;
+    if (devAlloc(h, &dt, nZones) || devAlloc(h, &dp, 16 * (size_t)nZones)) return 2;
+    CTX_CHECK(cudaMemcpy(dt, bcType, nZones * sizeof(int), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(dp, bcParams, 16 * (size_t)nZones * sizeof(double), cudaMemcpyHostToDevice));
+    h->m.bcType = dt; h->m.bcParams = dp;
+    return 0;
+}
+
+int h3d_set_halo(h3d_handle h, int nNeighbors, const int* neighborRank, const int* faceCount, const int* faceIDs, const int* thisSide) {
+    if (!h->haveMesh) { h->err = "h3d_set_mesh must precede h3d_set_halo"; return 1; }
+    if (nNeighbors > 0 && h->nranks < 2) { h->err = "halo given but the context has a single rank"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    h->nNbr = nNeighbors; h->nbrRank.assign(neighborRank, neighborRank + nNeighbors); h->nbrCount.assign(faceCount, faceCount + nNeighbors);
+    h->nbrOffset.assign(nNeighbors + 1, 0);
+    for (int b = 0; b < nNeighbors; ++b) h->nbrOffset[b + 1] = h->nbrOffset[b] + faceCount[b];
+    h->nHaloFaces = h->nbrOffset[nNeighbors];
+    if (h->nHaloFaces != h->nFace - h->nFaceLocal) { h->err = "halo face count does not match the number of MPI faces"; return 1; }
+    std::vector<int> hf(h->nHaloFaces), hs(thisSide, thisSide + h->nHaloFaces), nof(h->nHaloFaces);
+    for (int b = 0; b < nNeighbors; ++b) for (int q = h->nbrOffset[b]; q < h->nbrOffset[b + 1]; ++q) { hf[q] = h->invPermF[faceIDs[q]]; nof[q] = b; }
+    const int n2 = h->n * h->n;
+    if (devAlloc(h, &h->dHaloFace, hf.size()) || devAlloc(h, &h->dHaloSide, hs.size()) || devAlloc(h, &h->dNbrOffset, nNeighbors + 1) || devAlloc(h, &h->dNbrOfFace, nof.size()) ||
+        devAlloc(h, &h->dSend, (size_t)h->nHaloFaces * n2 * 15) || devAlloc(h, &h->dRecv, (size_t)h->nHaloFaces * n2 * 15)) return 2;
+    CTX_CHECK(cudaMemcpy(h->dHaloFace, hf.data(), hf.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(h->dHaloSide, hs.data(), hs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(h->dNbrOffset, h->nbrOffset.data(), (nNeighbors + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(h->dNbrOfFace, nof.data(), nof.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int h3d_upload_Q(h3d_handle h, const double* Q) {
+    if (!h->haveMesh) { h->err = "no mesh"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    const size_t ne = (size_t)h->nElem * h->n * h->n * h->n;
+    if (ensureStaging(h, 5 * ne * sizeof(double))) return 2;
+    CTX_CHECK(cudaMemcpyAsync(h->staging, Q, 5 * ne * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
+    k_aos_to_soa<<<148 * 8, 256, 0, h->sCompute>>>(h->staging, h->m.Q, h->dPermE, h->nElem, h->n * h->n * h->n, 5, 0);
+    ++h->launches;
+    h->facesValid = false;
+    CTX_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int h3d_download(h3d_handle h, double* Q, double* QDot, double* Ux, double* Uy, double* Uz) {
+    if (!h->haveMesh) { h->err = "no mesh"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    const int n3 = h->n * h->n * h->n;
+    const size_t ne = (size_t)h->nElem * n3;
+    if (ensureStaging(h, 5 * ne * sizeof(double))) return 2;
+    double* dst[5] = {Q, QDot, Ux, Uy, Uz};
+    const double* src[5] = {h->m.Q, h->m.QDot, h->m.Ux, h->m.Uy, h->m.Uz};
+    for (int a = 0; a < 5; ++a) {
+        if (!dst[a]) continue;
+        k_soa_to_aos<<<148 * 8, 256, 0, h->sCompute>>>(src[a], h->staging, h->dPermE, h->nElem, n3, 5);
+        ++h->launches;
+        CTX_CHECK(cudaMemcpyAsync(dst[a], h->staging, 5 * ne * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
+        CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+    }
+    return 0;
+}
+
+int h3d_set_source(h3d_handle h, const double* S) {
+    if (!h->haveMesh) { h->err = "no mesh"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    if (!S) { h->m.S = nullptr; return 0; }
+    const int n3 = h->n * h->n * h->n;
+    const size_t ne = (size_t)h->nElem * n3;
+    if (!h->dSource) CTX_CHECK(cudaMalloc((void**)&h->dSource, 5 * ne * sizeof(double)));
+    if (ensureStaging(h, 5 * ne * sizeof(double))) return 2;
+    CTX_CHECK(cudaMemcpyAsync(h->staging, S, 5 * ne * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
+    k_aos_to_soa<<<148 * 8, 256, 0, h->sCompute>>>(h->staging, h->dSource, h->dPermE, h->nElem, n3, 5, 0);
+    ++h->launches;
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute));   // the caller may reuse S
+    h->m.S = h->dSource;
+    return 0;
+}
+
+static int checkReady(h3d_handle h) {
+    if (!h->havePhysics || !h->haveBasis || !h->haveMesh) { h->err = "physics, basis and mesh must be set before the residual is evaluated"; return 1; }
+    if (h->nFace - h->nFaceLocal > 0 && h->nNbr == 0) { h->err = "mesh has MPI faces but h3d_set_halo was not called"; return 1; }
+    if (h->physics.inviscid == H3D_SPLIT_DG && h->nodeType != H3D_GAUSSLOBATTO) { h->err = "split-form discretization needs Gauss-Lobatto nodes"; return 1; }
+    return 0;
+}
+
+int h3d_compute_time_derivative(h3d_handle h, double time) {
+    (void)time;   // no time-dependent boundary condition or source is evaluated on the device
+    if (checkReady(h)) return 1;
+    CTX_CHECK(cudaSetDevice(h->device));
+    RkArgs rk{0, 1, 0, 0.0, 0.0};
+    return residual(h, rk);
+}
+
+int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_step) {
+    (void)t;
+    if (checkReady(h)) return 1;
+    CTX_CHECK(cudaSetDevice(h->device));
+    static const double a3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, c3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
+    static const double a5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
+    static const double c5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
+    const int ns = scheme == H3D_RK3 ? 3 : (scheme == H3D_RK5 ? 5 : 0);
+    if (!ns) { h->err = "unknown Runge-Kutta scheme"; return 1; }
+    const double *a = ns == 3 ? a3 : a5, *c = ns == 3 ? c3 : c5;
+    for (int k = 0; k < ns; ++k) {
+        RkArgs rk{1, (k == ns - 1 || h->storeQDotAlways) ? 1 : 0, 1, a[k], c[k] * dt};
+        int rc = residual(h, rk);
+        if (rc) return rc;
+    }
+    if (ctd_after_step) { RkArgs rk{0, 1, 0, 0.0, 0.0}; int rc = residual(h, rk); if (rc) return rc; }
+    return 0;
+}
+
+int h3d_max_residuals(h3d_handle h, double out[5]) {
+    if (!h->haveMesh) { h->err = "no mesh"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
+    k_red_residual<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, nn, h->dPartial);
+    k_red_final<6, 0><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
+    h->launches += 2;
+    if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 8, 6, ncclMax)) return 3;
+    CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 8, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+    for (int q = 0; q < 5; ++q) out[q] = h->hScalars[q];
+    h->hScalars[32] = h->hScalars[5];   // NaN flag of the same pass
+    return 0;
+}
+
+int h3d_has_nan(h3d_handle h, int* flag) {
+    double r[5];
+    int rc = h3d_max_residuals(h, r);
+    if (rc) return rc;
+    *flag = h->hScalars[32] > 0.5 ? 1 : 0;
+    return 0;
+}
+
+int h3d_max_timestep(h3d_handle h, double cfl, double dcfl, double* dt_conv, double* dt_visc) {
+    if (checkReady(h)) return 1;
+    CTX_CHECK(cudaSetDevice(h->device));
+    const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
+    const double dxi = 1.0 / std::fabs(h->hx[1] - h->hx[0]);
+    k_red_timestep<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, h->ph, nn, cfl, dcfl, dxi, h->dPartial);
+    k_red_final<2, 1><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
+    h->launches += 2;
+    if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 8, 2, ncclMin)) return 3;
+    CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+    *dt_conv = h->hScalars[0]; *dt_visc = h->hScalars[1];
+    return 0;
+}
+
+int h3d_volume_integral(h3d_handle h, int kind, double* val) {
+    if (!h->haveMesh) { h->err = "no mesh"; return 1; }
+    if (kind < 0 || kind > 3) { h->err = "unknown volume integral"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
+    k_red_integrals<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, nn, h->n, h->dPartial);
+    k_red_final<4, 2><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
+    h->launches += 2;
+    if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 8, 4, ncclSum)) return 3;
+    CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+    *val = h->hScalars[kind];
+    return 0;
+}
+
+int h3d_synchronize(h3d_handle h) {
+    CTX_CHECK(cudaSetDevice(h->device));
+    CTX_CHECK(cudaStreamSynchronize(h->sComm));
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+    return 0;
+}
+
+long long h3d_kernel_launches(h3d_handle h) { return h->launches; }
+
+int h3d_kernel_profile(h3d_handle h, double* out, int len) {
+    CTX_CHECK(cudaSetDevice(h->device));
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        h->profMs[r.cls] += ms; h->profCount[r.cls] += 1.0;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    h->prof.clear();
+    for (int c = 0; c < 4 && 2 * c + 1 < len; ++c) { out[2 * c] = h->profMs[c]; out[2 * c + 1] = h->profCount[c]; h->profMs[c] = 0; h->profCount[c] = 0; }
+    return 0;
+}
+
+int h3d_timer_begin(h3d_handle h) { CTX_CHECK(cudaSetDevice(h->device)); CTX_CHECK(cudaEventRecord(h->evT0, h->sCompute)); return 0; }
+int h3d_timer_end(h3d_handle h, double* ms) {
+    CTX_CHECK(cudaSetDevice(h->device));
+    CTX_CHECK(cudaEventRecord(h->evT1, h->sCompute));
+    CTX_CHECK(cudaEventSynchronize(h->evT1));
+    float f = 0.f;
+    CTX_CHECK(cudaEventElapsedTime(&f, h->evT0, h->evT1));
+    *ms = f;
+    return 0;
+}
+
+int h3d_set_option(h3d_handle h, const char* kv) {
+    std::string s(kv);
+    const size_t eq = s.find('=');
+    if (eq == std::string::npos) { h->err = "option must be key=value"; return 1; }
+    const std::string key = s.substr(0, eq); const int val = std::atoi(s.substr(eq + 1).c_str());
+    if (key == "store_qdot_every_stage") { h->storeQDotAlways = val; return 0; }
+    if (key == "profile_kernels") { h->profile = val; return 0; }
+    h->err = "unknown option: " + key;
+    return 1;
+}
+
+}  // extern "C"

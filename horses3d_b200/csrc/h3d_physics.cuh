@@ -1,0 +1,299 @@
+// Per-node device functions of the compressible Navier-Stokes path (FP64).
+//
+// Each function states the reference routine whose arithmetic it reproduces (paths relative to
+// /root/reference/Solver/src/libs/physics/navierstokes unless noted).  The operation order inside an
+// expression follows the reference so that a build with -fmad=false is bit-comparable with the oracle.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "h3d_gpu.h"
+
+namespace h3d {
+
+struct Phys {   // by-value kernel parameter (a trimmed H3dPhysics)
+    double gamma, gm1, gammaM2, mu, mu_to_kappa, S_div_Tref, T_renorm, lambdaStab, Cs;
+    int ns, riemann, averaging, les;
+};
+
+__device__ __forceinline__ double pow2(double x) { return x * x; }
+
+// Physics_NS.f90:51-97 (EulerFlux); F[c][d]
+__device__ __forceinline__ void euler_flux(const Phys& ph, const double Q[5], double F[5][3]) {
+    const double u = Q[1] / Q[0], v = Q[2] / Q[0], w = Q[3] / Q[0];
+    const double p = ph.gm1 * (Q[4] - 0.5 * (Q[1] * u + Q[2] * v + Q[3] * w));
+    F[0][0] = Q[1]; F[1][0] = Q[1] * u + p; F[2][0] = Q[1] * v; F[3][0] = Q[1] * w; F[4][0] = (Q[4] + p) * u;
+    F[0][1] = Q[2]; F[1][1] = F[2][0]; F[2][1] = Q[2] * v + p; F[3][1] = Q[2] * w; F[4][1] = (Q[4] + p) * v;
+    F[0][2] = Q[3]; F[1][2] = F[3][0]; F[2][2] = F[3][1]; F[3][2] = Q[3] * w + p; F[4][2] = (Q[4] + p) * w;
+}
+
+// VariableConversion_NS.f90:50-64,99-115,147-186: mu and kappa from the state (Sutherland)
+__device__ __forceinline__ double pressure(const Phys& ph, const double Q[5]) {
+    return ph.gm1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
+}
+__device__ __forceinline__ double sutherland(const Phys& ph, double T) {
+    const double tT = T * ph.T_renorm;
+    return (1.0 + ph.S_div_Tref) / (tT + ph.S_div_Tref) * tT * sqrt(tT);
+}
+__device__ __forceinline__ void laminar_mu_kappa(const Phys& ph, const double Q[5], double& mu, double& kappa) {
+    const double T = ph.gammaM2 * pressure(ph, Q) / Q[0];
+    mu = ph.mu * sutherland(ph, T);
+    kappa = mu * ph.mu_to_kappa;
+}
+
+// VariableConversion_NS.f90:373-392
+__device__ __forceinline__ void velocity_gradients(const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5],
+                                                   double ux[3], double uy[3], double uz[3]) {
+    const double invRho = 1.0 / Q[0], invRho2 = invRho * invRho;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double uDivRho = Q[1 + c] * invRho2;
+        ux[c] = invRho * Qx[1 + c] - uDivRho * Qx[0];
+        uy[c] = invRho * Qy[1 + c] - uDivRho * Qy[0];
+        uz[c] = invRho * Qz[1 + c] - uDivRho * Qz[0];
+    }
+}
+
+// libs/physics/common/LESModels.f90 Smagorinsky: mu_t = rho (Cs delta)^2 |S|
+__device__ __forceinline__ double smagorinsky(const Phys& ph, double delta, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5]) {
+    double ux[3], uy[3], uz[3];
+    velocity_gradients(Q, Qx, Qy, Qz, ux, uy, uz);
+    double normS = pow2(ux[0]) + pow2(uy[1]) + pow2(uz[2]);
+    normS = 2.0 * normS + pow2(ux[1] + uy[0]) + pow2(ux[2] + uz[0]) + pow2(uy[2] + uz[1]);
+    normS = sqrt(normS);
+    const double LS = ph.Cs * delta;
+    return Q[0] * pow2(LS) * normS;
+}
+
+// Physics_NS.f90:246-304 (ViscousFlux_STATE), beta = 0 kept as in the reference call sites
+__device__ __forceinline__ void viscous_flux(const Phys& ph, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5],
+                                             double mu, double beta, double kappa, double F[5][3]) {
+    const double invRho = 1.0 / Q[0];
+    const double u = Q[1] * invRho, v = Q[2] * invRho, w = Q[3] * invRho;
+    const double uDivRho[3] = {u * invRho, v * invRho, w * invRho};
+    double ux[3], uy[3], uz[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        ux[c] = invRho * Qx[1 + c] - uDivRho[c] * Qx[0];
+        uy[c] = invRho * Qy[1 + c] - uDivRho[c] * Qy[0];
+        uz[c] = invRho * Qz[1 + c] - uDivRho[c] * Qz[0];
+    }
+    const double c0 = ph.gm1 * ph.gammaM2;
+    const double Tx = c0 * (invRho * Qx[4] - Q[4] * invRho * invRho * Qx[0] - u * ux[0] - v * ux[1] - w * ux[2]);
+    const double Ty = c0 * (invRho * Qy[4] - Q[4] * invRho * invRho * Qy[0] - u * uy[0] - v * uy[1] - w * uy[2]);
+    const double Tz = c0 * (invRho * Qz[4] - Q[4] * invRho * invRho * Qz[0] - u * uz[0] - v * uz[1] - w * uz[2]);
+    const double divV = ux[0] + uy[1] + uz[2];
+    F[0][0] = 0.0;
+    F[1][0] = mu * (2.0 * ux[0] - 2.0 / 3.0 * divV) + beta * divV;
+    F[2][0] = mu * (ux[1] + uy[0]);
+    F[3][0] = mu * (ux[2] + uz[0]);
+    F[4][0] = F[1][0] * u + F[2][0] * v + F[3][0] * w + kappa * Tx;
+    F[0][1] = 0.0;
+    F[1][1] = F[2][0];
+    F[2][1] = mu * (2.0 * uy[1] - 2.0 / 3.0 * divV) + beta * divV;
+    F[3][1] = mu * (uy[2] + uz[1]);
+    F[4][1] = F[1][1] * u + F[2][1] * v + F[3][1] * w + kappa * Ty;
+    F[0][2] = 0.0;
+    F[1][2] = F[3][0];
+    F[2][2] = F[3][1];
+    F[3][2] = mu * (2.0 * uz[2] - 2.0 / 3.0 * divV) + beta * divV;
+    F[4][2] = F[1][2] * u + F[2][2] * v + F[3][2] * w + kappa * Tz;
+}
+
+// RiemannSolvers_NS.f90:1784-1962 averaging functions on rotated states
+__device__ __forceinline__ void averaged_states(const Phys& ph, const double QL[5], const double QR[5], double pL, double pR,
+                                                double invRhoL, double invRhoR, double flux[5]) {
+    const double uL = invRhoL * QL[1], uR = invRhoR * QR[1];
+    const double vL = invRhoL * QL[2], vR = invRhoR * QR[2];
+    const double wL = invRhoL * QL[3], wR = invRhoR * QR[3];
+    if (ph.averaging == H3D_AVG_STANDARD) {
+        flux[0] = 0.5 * (QL[1] + QR[1]);
+        flux[1] = 0.5 * (QL[1] * uL + QR[1] * uR + pL + pR);
+        flux[2] = 0.5 * (QL[1] * vL + QR[1] * vR);
+        flux[3] = 0.5 * (QL[1] * wL + QR[1] * wR);
+        flux[4] = 0.5 * (uL * (QL[4] + pL) + uR * (QR[4] + pR));
+    } else {
+        const double rho = 0.5 * (QL[0] + QR[0]), u = 0.5 * (uL + uR), v = 0.5 * (vL + vR), w = 0.5 * (wL + wR), p = 0.5 * (pL + pR);
+        flux[0] = rho * u; flux[1] = rho * u * u + p; flux[2] = rho * u * v; flux[3] = rho * u * w;
+        if (ph.averaging == H3D_AVG_KENNEDYGRUBER) {
+            const double e = 0.5 * (QL[4] * invRhoL + QR[4] * invRhoR);
+            flux[4] = rho * u * e + p * u;
+        } else {   // Pirozzoli
+            const double h = 0.5 * ((QL[4] + pL) * invRhoL + (QR[4] + pR) * invRhoR);
+            flux[4] = rho * u * h;
+        }
+    }
+}
+
+// RiemannSolvers_NS.f90:375-428 (Central) and :1251-1334 (Lax-Friedrichs); central == LxF with lambdaStab = 0
+// up to the reference's own code path (no stabilisation term evaluated).
+__device__ __forceinline__ void rotated_riemann(const Phys& ph, bool lxf, const double QLeft[5], const double QRight[5],
+                                                const double nHat[3], const double t1[3], const double t2[3], double flux[5]) {
+    const double rhoL = QLeft[0], rhoR = QRight[0], invRhoL = 1.0 / rhoL, invRhoR = 1.0 / rhoR;
+    const double rhouL = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    const double rhovL = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    const double rhowL = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    const double rhouR = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    const double rhovR = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    const double rhowR = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    const double rhoeL = QLeft[4], rhoeR = QRight[4];
+    const double rhoV2L = (pow2(rhouL) + pow2(rhovL) + pow2(rhowL)) * invRhoL;
+    const double rhoV2R = (pow2(rhouR) + pow2(rhovR) + pow2(rhowR)) * invRhoR;
+    const double pL = ph.gm1 * (rhoeL - 0.5 * rhoV2L), pR = ph.gm1 * (rhoeR - 0.5 * rhoV2R);
+    const double QLRot[5] = {rhoL, rhouL, rhovL, rhowL, rhoeL}, QRRot[5] = {rhoR, rhouR, rhovR, rhowR, rhoeR};
+    averaged_states(ph, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    if (lxf) {
+        const double aL = sqrt(ph.gamma * pL * invRhoL), aR = sqrt(ph.gamma * pR * invRhoR);
+        const double lambda = fmax(fabs(rhouL * invRhoL) + aL, fabs(rhouR * invRhoR) + aR);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { const double stab = 0.5 * lambda * (QRRot[q] - QLRot[q]); flux[q] = flux[q] - ph.lambdaStab * stab; }
+    }
+    const double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
+// RiemannSolvers_NS.f90:1541-1656 (RoeRiemannSolver): one-wave upwinding with entropy fix, uses nHat only
+__device__ __forceinline__ void roe_riemann(const Phys& ph, const double QLeft[5], const double QRight[5], const double nHat[3], double flux[5]) {
+    const double gamma = ph.gamma;
+    const double rho = QLeft[0], rhou = QLeft[1], rhov = QLeft[2], rhow = QLeft[3], rhoe = QLeft[4];
+    const double rhon = QRight[0], rhoun = QRight[1], rhovn = QRight[2], rhown = QRight[3], rhoen = QRight[4];
+    const double ul = rhou / rho, vl = rhov / rho, wl = rhow / rho;
+    const double pleft = (gamma - 1.0) * (rhoe - 0.5 / rho * (rhou * rhou + rhov * rhov + rhow * rhow));
+    const double ur = rhoun / rhon, vr = rhovn / rhon, wr = rhown / rhon;
+    const double pright = (gamma - 1.0) * (rhoen - 0.5 / rhon * (rhoun * rhoun + rhovn * rhovn + rhown * rhown));
+    const double ql = nHat[0] * ul + nHat[1] * vl + nHat[2] * wl;
+    const double qr = nHat[0] * ur + nHat[1] * vr + nHat[2] * wr;
+    const double hl = 0.5 * (ul * ul + vl * vl + wl * wl) + gamma / (gamma - 1.0) * pleft / rho;
+    const double hr = 0.5 * (ur * ur + vr * vr + wr * wr) + gamma / (gamma - 1.0) * pright / rhon;
+    const double rtd = sqrt(rho * rhon);
+    const double betal = rho / (rho + rtd), betar = 1.0 - betal;
+    const double utd = betal * ul + betar * ur, vtd = betal * vl + betar * vr, wtd = betal * wl + betar * wr, htd = betal * hl + betar * hr;
+    const double atd2 = (gamma - 1.0) * (htd - 0.5 * (utd * utd + vtd * vtd + wtd * wtd));
+    const double atd = sqrt(atd2);
+    const double qtd = utd * nHat[0] + vtd * nHat[1] + wtd * nHat[2];
+    if (qtd >= 0.0) {
+        const double dw1 = 0.5 * ((pright - pleft) / atd2 - (qr - ql) * rtd / atd);
+        const double sp1 = qtd - atd;
+        const double sp1m = fmin(sp1, 0.0);
+        const double hd1m = ((gamma + 1.0) / 4.0 * atd / rtd) * dw1;
+        const double eta1 = fmax(-fabs(sp1) - hd1m, 0.0);
+        const double udw1 = dw1 * (sp1m - 0.5 * eta1);
+        const double rql = rho * ql;
+        flux[0] = rql + udw1;
+        flux[1] = rql * ul + pleft * nHat[0] + udw1 * (utd - atd * nHat[0]);
+        flux[2] = rql * vl + pleft * nHat[1] + udw1 * (vtd - atd * nHat[1]);
+        flux[3] = rql * wl + pleft * nHat[2] + udw1 * (wtd - atd * nHat[2]);
+        flux[4] = rql * hl + udw1 * (htd - qtd * atd);
+    } else {
+        const double dw4 = 0.5 * ((pright - pleft) / atd2 + (qr - ql) * rtd / atd);
+        const double sp4 = qtd + atd;
+        const double sp4p = fmax(sp4, 0.0);
+        const double hd4 = ((gamma + 1.0) / 4.0 * atd / rtd) * dw4;
+        const double eta4 = fmax(-fabs(sp4) + hd4, 0.0);
+        const double udw4 = dw4 * (sp4p + 0.5 * eta4);
+        const double rqr = rhon * qr;
+        flux[0] = rqr - udw4;
+        flux[1] = rqr * ur + pright * nHat[0] - udw4 * (utd + atd * nHat[0]);
+        flux[2] = rqr * vr + pright * nHat[1] - udw4 * (vtd + atd * nHat[1]);
+        flux[3] = rqr * wr + pright * nHat[2] - udw4 * (wtd + atd * nHat[2]);
+        flux[4] = rqr * hr - udw4 * (htd + qtd * atd);
+    }
+}
+
+__device__ __forceinline__ void riemann_solver(const Phys& ph, const double QL[5], const double QR[5], const double nHat[3],
+                                               const double t1[3], const double t2[3], double flux[5]) {
+    if (ph.riemann == H3D_RIEMANN_ROE) roe_riemann(ph, QL, QR, nHat, flux);
+    else rotated_riemann(ph, ph.riemann == H3D_RIEMANN_LXF, QL, QR, nHat, t1, t2, flux);
+}
+
+// RiemannSolvers_NS.f90:2085-2145 (StandardDG), :2296-2367 (Kennedy-Gruber), :2369-2437 (Pirozzoli) two-point fluxes
+__device__ __forceinline__ void two_point_flux(const Phys& ph, const double QL[5], const double QR[5], const double JaL[3], const double JaR[3], double fs[5]) {
+    const double invRhoL = 1.0 / QL[0], invRhoR = 1.0 / QR[0];
+    const double uL = invRhoL * QL[1], uR = invRhoR * QR[1];
+    const double vL = invRhoL * QL[2], vR = invRhoR * QR[2];
+    const double wL = invRhoL * QL[3], wR = invRhoR * QR[3];
+    const double pL = ph.gm1 * (QL[4] - 0.5 * (QL[1] * uL + QL[2] * vL + QL[3] * wL));
+    const double pR = ph.gm1 * (QR[4] - 0.5 * (QR[1] * uR + QR[2] * vR + QR[3] * wR));
+    double f[5], g[5], h[5];
+    if (ph.averaging == H3D_AVG_STANDARD) {
+        const double Ja[3] = {JaL[0] + JaR[0], JaL[1] + JaR[1], JaL[2] + JaR[2]};
+        f[0] = QL[1] + QR[1]; f[1] = QL[1] * uL + QR[1] * uR + pL + pR; f[2] = QL[1] * vL + QR[1] * vR; f[3] = QL[1] * wL + QR[1] * wR;
+        f[4] = uL * (QL[4] + pL) + uR * (QR[4] + pR);
+        g[0] = QL[2] + QR[2]; g[1] = QL[2] * uL + QR[2] * uR; g[2] = QL[2] * vL + QR[2] * vR + pL + pR; g[3] = QL[2] * wL + QR[2] * wR;
+        g[4] = vL * (QL[4] + pL) + vR * (QR[4] + pR);
+        h[0] = QL[3] + QR[3]; h[1] = QL[3] * uL + QR[3] * uR; h[2] = QL[3] * vL + QR[3] * vR; h[3] = QL[3] * wL + QR[3] * wR + pL + pR;
+        h[4] = wL * (QL[4] + pL) + wR * (QR[4] + pR);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) fs[q] = 0.25 * (f[q] * Ja[0] + g[q] * Ja[1] + h[q] * Ja[2]);
+        return;
+    }
+    const double rho = 0.5 * (QL[0] + QR[0]), u = 0.5 * (uL + uR), v = 0.5 * (vL + vR), w = 0.5 * (wL + wR), p = 0.5 * (pL + pR);
+    const double Ja[3] = {0.5 * (JaL[0] + JaR[0]), 0.5 * (JaL[1] + JaR[1]), 0.5 * (JaL[2] + JaR[2])};
+    f[0] = rho * u; f[1] = rho * u * u + p; f[2] = rho * u * v; f[3] = rho * u * w;
+    g[0] = rho * v; g[1] = rho * v * u; g[2] = rho * v * v + p; g[3] = rho * v * w;
+    h[0] = rho * w; h[1] = rho * w * u; h[2] = rho * w * v; h[3] = rho * w * w + p;
+    if (ph.averaging == H3D_AVG_KENNEDYGRUBER) {
+        const double e = 0.5 * (QL[4] * invRhoL + QR[4] * invRhoR);
+        f[4] = rho * u * e + p * u; g[4] = rho * v * e + p * v; h[4] = rho * w * e + p * w;
+    } else {
+        const double hh = 0.5 * ((QL[4] + pL) * invRhoL + (QR[4] + pR) * invRhoR);
+        f[4] = rho * u * hh; g[4] = rho * v * hh; h[4] = rho * w * hh;
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) fs[q] = f[q] * Ja[0] + g[q] * Ja[1] + h[q] * Ja[2];
+}
+
+// ---- boundary conditions (libs/physics/common/{NoSlipWall,FreeSlipWall,Inflow,Outflow}BC.f90) -------------
+// External state for the Riemann solver (FlowState).  P: 16 parameters of the zone.
+__device__ __forceinline__ void bc_flow_state(const Phys& ph, int type, const double* P, const double nHat[3], double Q[5]) {
+    if (type == H3D_BC_NOSLIPWALL) {
+        Q[1] = 2.0 * Q[0] * P[0] - Q[1]; Q[2] = 2.0 * Q[0] * P[1] - Q[2]; Q[3] = 2.0 * Q[0] * P[2] - Q[3];
+    } else if (type == H3D_BC_FREESLIPWALL) {
+        const double vn = Q[1] * nHat[0] + Q[2] * nHat[1] + Q[3] * nHat[2];
+        Q[1] = Q[1] - 2.0 * vn * nHat[0]; Q[2] = Q[2] - 2.0 * vn * nHat[1]; Q[3] = Q[3] - 2.0 * vn * nHat[2];
+    } else if (type == H3D_BC_INFLOW) {
+        const double rho = P[0], u = P[1], v = P[2], w = P[3], p = P[4];
+        Q[0] = rho; Q[1] = rho * u; Q[2] = rho * v; Q[3] = rho * w; Q[4] = p / ph.gm1 + 0.5 * rho * (u * u + v * v + w * w);
+    } else if (type == H3D_BC_OUTFLOW) {
+        const double pExt = P[4];
+        const double rhoInt = Q[0], invRho = 1.0 / rhoInt;
+        const double uInt = Q[1] * invRho, vInt = Q[2] * invRho, wInt = Q[3] * invRho;
+        const double pInt = ph.gm1 * (Q[4] - 0.5 * (Q[1] * uInt + Q[2] * vInt + Q[3] * wInt));
+        const double qnInt = uInt * nHat[0] + vInt * nHat[1] + wInt * nHat[2];
+        const double aInt = sqrt(ph.gamma * pInt * invRho);
+        if (!(qnInt > 0.0 && qnInt / aInt >= 1.0)) {
+            Q[0] = rhoInt; Q[1] = rhoInt * uInt; Q[2] = rhoInt * vInt; Q[3] = rhoInt * wInt;
+            Q[4] = pExt / ph.gm1 + 0.5 * rhoInt * (uInt * uInt + vInt * vInt + wInt * wInt);
+        }
+    }
+}
+
+// Boundary value of the gradient variables (FlowGradVars, STATE variables)
+__device__ __forceinline__ void bc_grad_vars(const Phys& ph, int type, const double* P, const double nHat[3], const double Qi[5], double us[5]) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) us[q] = Qi[q];
+    if (type == H3D_BC_NOSLIPWALL) {
+        const double rho = Qi[0], invRho = 1.0 / rho;
+        const double eInt = Qi[4] - 0.5 * (pow2(Qi[1]) + pow2(Qi[2]) + pow2(Qi[3])) * invRho;
+        us[0] = rho; us[1] = rho * P[0]; us[2] = rho * P[1]; us[3] = rho * P[2];
+        us[4] = eInt + 0.5 * rho * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]);
+    } else if (type == H3D_BC_FREESLIPWALL) {
+        const double vn = Qi[1] * nHat[0] + Qi[2] * nHat[1] + Qi[3] * nHat[2];
+        us[1] = Qi[1] - vn * nHat[0]; us[2] = Qi[2] - vn * nHat[1]; us[3] = Qi[3] - vn * nHat[2];
+    } else if (type == H3D_BC_INFLOW || type == H3D_BC_OUTFLOW) {
+        bc_flow_state(ph, type, P, nHat, us);
+    }
+}
+
+// Neumann fix-up of the boundary viscous flux (FlowNeumann)
+__device__ __forceinline__ void bc_neumann(int type, const double* P, double visc[5]) {
+    if (type == H3D_BC_NOSLIPWALL) {
+        const double work = visc[1] * P[0] + visc[2] * P[1] + visc[3] * P[2];
+        visc[0] = 0.0; visc[4] = work;
+    } else if (type == H3D_BC_FREESLIPWALL || type == H3D_BC_INFLOW || type == H3D_BC_OUTFLOW) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) visc[q] = 0.0;
+    }
+}
+
+}  // namespace h3d

@@ -182,7 +182,10 @@ long long h3d_kernel_launches(h3d_handle h);
 /* CUDA-event timing of work enqueued between begin/end on the compute stream, in milliseconds */
 int h3d_timer_begin(h3d_handle h);
 int h3d_timer_end(h3d_handle h, double* ms);
-/* option string "key=value" (e.g. "store_qdot_every_stage=1"); unknown keys are an error */
+/* accumulated CUDA-event time per kernel class since the last call (option profile_kernels=1):
+ * out = [ms, launches] x {gradient, riemann, volume, prolong} */
+int h3d_kernel_profile(h3d_handle h, double* out, int len);
+/* option string "key=value" ("store_qdot_every_stage=1", "profile_kernels=1"); unknown keys are an error */
 int h3d_set_option(h3d_handle h, const char* key_value);
 
 #ifdef __cplusplus

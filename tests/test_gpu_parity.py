@@ -1,0 +1,144 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical inputs.  Needs a B200.
+
+Tolerance: the north-star bar is 1e-12 relative for the per-DOF time derivative in FP64.  "Relative" is
+measured per equation against the max-norm of that equation's field (a per-DOF ratio is meaningless where the
+field crosses zero).  The production library is compiled with FMA contraction, the oracle without, so the
+two differ by a few ulps of the summed terms.
+"""
+import numpy as np
+import pytest
+
+from horses3d_b200 import physics as P
+from horses3d_b200.dgsem import DGSem, taylor_green_ic
+from horses3d_b200.hostmesh import GAUSS, GAUSSLOBATTO
+from horses3d_b200.physics import make_physics
+from oracle.oracle_api import OracleApi
+from parity import get_mesh, perturbed_tgv, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_QDOT = 1.0e-12
+
+
+def run_pair(gpu_api_cls, mesh, phys, ic=perturbed_tgv):
+    out = []
+    for api in (OracleApi(), gpu_api_cls()):
+        sem = DGSem(api, mesh, phys)
+        sem.set_initial_condition(ic)
+        sem.ComputeTimeDerivative(0.0)
+        out.append((sem, sem.download(Q=True, QDot=True, gradients=True)))
+    return out
+
+
+CASES = [
+    # (ne, N, nodes, amp, shuffle, physics kwargs)
+    (3, 3, GAUSS, 0.0, False, dict(flow="NS", mach=0.08, reynolds=1600.0)),
+    (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.08, reynolds=1600.0)),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.08, reynolds=1600.0)),
+    (3, 2, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=100.0)),
+    (3, 1, GAUSS, 0.0, True, dict(flow="NS", mach=0.3, reynolds=100.0)),
+    (2, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=100.0, riemann="lax-friedrichs")),
+    (2, 5, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=100.0, riemann="central")),
+    (2, 6, GAUSS, 0.1, True, dict(flow="Euler", mach=0.3)),
+    (2, 8, GAUSS, 0.1, True, dict(flow="NS", mach=0.1, reynolds=500.0)),
+    (2, 9, GAUSS, 0.1, True, dict(flow="NS", mach=0.1, reynolds=500.0)),
+    (3, 3, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli")),
+    (2, 7, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli")),
+    (2, 4, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="kennedy-gruber", riemann="lax-friedrichs")),
+    (2, 5, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="standard")),
+    (2, 9, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli")),
+    (2, 3, GAUSSLOBATTO, 0.0, False, dict(flow="NS", mach=0.3, reynolds=200.0)),
+]
+
+
+@pytest.mark.parametrize("ne,N,nodes,amp,shuffle,kw", CASES)
+def test_time_derivative_matches_oracle(gpu_api_cls, ne, N, nodes, amp, shuffle, kw):
+    mesh = get_mesh(ne, N, nodes, amp, shuffle)
+    (so, o), (sg, g) = run_pair(gpu_api_cls, mesh, make_physics(**kw))
+    assert np.array_equal(o["Q"], g["Q"])                       # upload/download round trip is exact
+    if kw.get("flow", "NS") != "Euler":
+        for k in ("U_x", "U_y", "U_z"):
+            assert rel_err(g[k], o[k]) < TOL_QDOT, k
+    assert rel_err(g["QDot"], o["QDot"]) < TOL_QDOT
+    assert sg.api.kernel_launches() > 0
+
+
+@pytest.mark.parametrize("scheme", ["RK3", "RK5"])
+def test_rk_steps_and_monitors_match_oracle(gpu_api_cls, scheme):
+    mesh = get_mesh(4, 3, GAUSS, 0.1, True)
+    phys = make_physics(flow="NS", mach=0.08, reynolds=1600.0)
+    recs = []
+    for api in (OracleApi(), gpu_api_cls()):
+        sem = DGSem(api, mesh, phys)
+        sem.set_initial_condition(taylor_green_ic)
+        recs.append((sem.integrate(10, cfl=0.4, dcfl=0.4, scheme=scheme), sem.Q()))
+    (ro, Qo), (rg, Qg) = recs
+    for a, b in zip(ro, rg):
+        assert abs(a["dt"] - b["dt"]) <= 1e-13 * max(a["dt"], 1e-300)
+        assert np.abs(a["residuals"] - b["residuals"]).max() < 1e-10 * np.abs(a["residuals"]).max()
+        for k in ("kinetic energy", "kinetic energy rate", "enstrophy"):
+            assert abs(a[k] - b[k]) < 1e-10 * max(abs(a[k]), 1e-300), k
+    assert rel_err(Qg, Qo) < 1e-12
+
+
+def test_k1_taylor_green_on_gpu(gpu_api_cls):
+    """The reference's own TaylorGreen regression (K1) run on the device path."""
+    mesh = get_mesh(32, 3, GAUSS)
+    sem = DGSem(gpu_api_cls(), mesh, make_physics(flow="NS", mach=0.08, reynolds=1600.0, riemann="roe"))
+    sem.set_initial_condition(taylor_green_ic)
+    rec = sem.integrate(5, cfl=0.4, dcfl=0.4)[-1]
+    res = np.array([1.6417830052388520E-05, 1.2677577061211545E-01, 1.2677577048633804E-01, 2.4981129585617484E-01, 6.2174425106488129E-01])
+    assert np.abs(rec["residuals"] - res).max() < 1.0e-7
+    assert abs(rec["kinetic energy"] - 1.2499879367819486E-01) < 1.0e-11
+    assert abs(rec["kinetic energy rate"] - (-4.2807806718622574E-04)) < 1.0e-11
+    assert abs(rec["enstrophy"] - 3.7499683882517909E-01) < 1.0e-11
+
+
+def test_free_stream_preservation_full_size_p7(gpu_api_cls):
+    """Size-independent property at the benchmark polynomial order: a uniform state has zero residual on a curved,
+    randomly re-oriented mesh (metric identities + all eight face rotations)."""
+    mesh = get_mesh(6, 7, GAUSS, 0.1, True)
+    sem = DGSem(gpu_api_cls(), mesh, make_physics(flow="NS", mach=0.3, reynolds=100.0))
+    Q = np.zeros((mesh.nElem, 8, 8, 8, 5)); Q[...] = [1.0, 0.3, -0.2, 0.5, 10.0]
+    sem.set_Q(Q)
+    sem.ComputeTimeDerivative(0.0)
+    assert np.abs(sem.QDot()).max() < 2e-9
+    sem.TakeRK3Step(0.0, 1e-3)
+    assert np.abs(sem.Q() - Q).max() < 1e-11
+
+
+def test_residual_is_idempotent_and_source_is_added(gpu_api_cls):
+    mesh = get_mesh(3, 3, GAUSS, 0.1, True)
+    sem = DGSem(gpu_api_cls(), mesh, make_physics(flow="NS", mach=0.08, reynolds=1600.0))
+    sem.set_initial_condition(perturbed_tgv)
+    sem.ComputeTimeDerivative(0.0); a = sem.QDot()
+    sem.ComputeTimeDerivative(0.0); b = sem.QDot()
+    assert np.array_equal(a, b)
+    S = np.random.default_rng(0).standard_normal(a.shape)
+    sem.set_source(S); sem.ComputeTimeDerivative(0.0); c = sem.QDot()
+    assert np.array_equal(c, a + S)
+    sem.set_source(None); sem.ComputeTimeDerivative(0.0)
+    assert np.array_equal(sem.QDot(), a)
+
+
+def test_nan_is_detected(gpu_api_cls):
+    mesh = get_mesh(2, 2, GAUSS)
+    sem = DGSem(gpu_api_cls(), mesh, make_physics())
+    Q = taylor_green_ic(sem.node_coordinates())
+    sem.set_Q(Q)
+    assert not sem.checkForNan()
+    Q[1, 0, 1, 2, 3] = np.nan
+    sem.set_Q(Q)
+    assert sem.checkForNan()
+
+
+def test_errors_follow_the_reference_messages(gpu_api_cls):
+    from horses3d_b200.capi import H3dError
+    mesh = get_mesh(2, 2, GAUSS)
+    bad = make_physics(); bad.riemann = 99
+    with pytest.raises(H3dError, match="Riemann Solver not recognized"):
+        DGSem(gpu_api_cls(), mesh, bad)
+    with pytest.raises(H3dError, match="Gauss-Lobatto"):
+        sem = DGSem(gpu_api_cls(), mesh, make_physics(flow="Euler", inviscid="split-form", averaging="pirozzoli"))
+        sem.set_initial_condition(taylor_green_ic)
+        sem.ComputeTimeDerivative(0.0)

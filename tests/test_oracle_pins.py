@@ -1,0 +1,89 @@
+"""Pins of the CPU oracle against the reference's own known answers.  CPU only."""
+import numpy as np
+import pytest
+
+from horses3d_b200.dgsem import DGSem, taylor_green_ic
+from horses3d_b200.hostmesh import GAUSS, GAUSSLOBATTO, HostMesh, NodalStorage
+from horses3d_b200.physics import make_physics
+from oracle import oracle_api
+
+
+def test_k6_quadrature_and_derivative_exactness():
+    # Solver/test/Components/NodalStorage/src/NodalStorageTests.f90:23-59 (N = 8 Gauss, tol 1e-12)
+    sp = oracle_api.nodal(8, GAUSS)
+    assert abs((sp["w"] * sp["x"] ** 2).sum() - 2.0 / 3.0) < 1e-12
+    assert np.abs(sp["D"] @ sp["x"] ** 2 - 2.0 * sp["x"]).max() < 1e-12
+    spl = oracle_api.nodal(8, GAUSSLOBATTO)
+    assert abs((spl["w"] * spl["x"] ** 2).sum() - 2.0 / 3.0) < 1e-12
+    assert np.abs(spl["D"] @ spl["x"] ** 2 - 2.0 * spl["x"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("nodes", [GAUSS, GAUSSLOBATTO])
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 7, 9])
+def test_oracle_operators_match_host_library(N, nodes):
+    a, b = oracle_api.nodal(N, nodes), NodalStorage(N, nodes)
+    for k in ("x", "w", "D", "hatD", "sharpD", "v", "b"):
+        assert np.array_equal(a[k], getattr(b, k)), k
+    # SBP property of the weak matrices and partition of unity of the trace vectors
+    assert np.allclose(a["v"].sum(axis=1), 1.0, atol=1e-13)
+    W = np.diag(a["w"])
+    Bm = np.outer(a["v"][1], a["v"][1]) - np.outer(a["v"][0], a["v"][0])
+    assert np.allclose(W @ a["D"] + (W @ a["D"]).T, Bm, atol=1e-12)
+
+
+def test_k1_taylor_green_5_steps():
+    """Solver/test/NavierStokes/TaylorGreen: Re 1600, M 0.08, P=3 Gauss, Standard DG, BR1, Roe, RK3,
+    cfl = dcfl = 0.4, 5 steps on the 32^3 periodic box.  Expected values and tolerances from
+    SETUP/ProblemFile.f90:317-366."""
+    m = HostMesh.box(32).connect().geometry(3, GAUSS)
+    sem = DGSem(oracle_api.OracleApi(), m, make_physics(flow="NS", mach=0.08, reynolds=1600.0, riemann="roe"))
+    sem.set_initial_condition(taylor_green_ic)
+    rec = sem.integrate(5, cfl=0.4, dcfl=0.4)[-1]
+    res = np.array([1.6417830052388520E-05, 1.2677577061211545E-01, 1.2677577048633804E-01, 2.4981129585617484E-01, 6.2174425106488129E-01])
+    assert np.abs(rec["residuals"] - res).max() < 1.0e-7
+    assert abs(rec["kinetic energy"] - 1.2499879367819486E-01) < 1.0e-11
+    assert abs(rec["kinetic energy rate"] - (-4.2807806718622574E-04)) < 1.0e-11
+    assert abs(rec["enstrophy"] - 3.7499683882517909E-01) < 1.0e-11
+
+
+@pytest.mark.parametrize("nodes,inviscid,avg", [(GAUSS, "standard", "standard"), (GAUSSLOBATTO, "split-form", "pirozzoli"),
+                                                (GAUSSLOBATTO, "split-form", "kennedy-gruber"), (GAUSSLOBATTO, "split-form", "standard")])
+def test_oracle_free_stream_preservation_on_curved_rotated_mesh(nodes, inviscid, avg):
+    m = HostMesh.box(3, amp=0.15, bFaceOrder=3, shuffle=True).connect().geometry(4, nodes)
+    sem = DGSem(oracle_api.OracleApi(), m, make_physics(flow="NS", mach=0.3, reynolds=100.0, inviscid=inviscid, averaging=avg))
+    Q = np.zeros((m.nElem, 5, 5, 5, 5))
+    Q[...] = [1.0, 0.3, -0.2, 0.5, 10.0]
+    sem.set_Q(Q)
+    sem.ComputeTimeDerivative(0.0)
+    assert np.abs(sem.QDot()).max() < 5e-10
+
+
+def test_oracle_is_invariant_to_element_orientation():
+    """Same physical mesh, elements re-oriented at random (all eight face rotations): same residual at the same points."""
+    out = []
+    for shuffle in (False, True):
+        m = HostMesh.box(3, amp=0.1, bFaceOrder=2, shuffle=shuffle).connect().geometry(3, GAUSS)
+        sem = DGSem(oracle_api.OracleApi(), m, make_physics(flow="NS", mach=0.08, reynolds=50.0))
+        sem.set_initial_condition(taylor_green_ic)
+        sem.ComputeTimeDerivative(0.0)
+        x = sem.node_coordinates().reshape(-1, 3)
+        qd = sem.QDot().reshape(-1, 5)
+        order = np.lexsort(np.round(x * 1e7).astype(np.int64).T[::-1])
+        out.append(qd[order])
+    assert np.abs(out[0] - out[1]).max() < 1e-10 * np.abs(out[0]).max()
+    if True:
+        rots = np.bincount(m.array("faceRot"), minlength=8)
+        assert (rots > 0).all()
+
+
+def test_split_form_standard_average_equals_standard_dg_on_lobatto():
+    """With the 'standard' two-point flux the split form reduces to the standard DG volume term up to round-off on
+    straight-sided elements (the discrete product rule is exact there): a consistency check of a15 against a14."""
+    m = HostMesh.box(2).connect().geometry(3, GAUSSLOBATTO)
+    qd = []
+    for inviscid in ("standard", "split-form"):
+        sem = DGSem(oracle_api.OracleApi(), m, make_physics(flow="Euler", mach=0.3, inviscid=inviscid, averaging="standard"))
+        Q = np.zeros((m.nElem, 4, 4, 4, 5)); Q[...] = [1.0, 0.3, -0.2, 0.5, 10.0]
+        sem.set_Q(Q); sem.ComputeTimeDerivative(0.0)
+        qd.append(sem.QDot())
+    assert np.abs(qd[0]).max() < 1e-11 and np.abs(qd[1]).max() < 1e-11
