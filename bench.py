@@ -34,7 +34,7 @@ B_ALG_VOLUME_KERNEL = lambda n: 360.0 + 480.0 / n        # k_volume: Q 40 + grad
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ne", type=int, default=32, help="elements per direction per GPU")

@@ -20,6 +20,7 @@ INCLUDE_DIR = os.path.join(ROOT, "include")
 
 HOST_LIB = os.path.join(HOST_DIR, "libh3dhost.so")
 GPU_LIB = os.path.join(CSRC_DIR, "libh3dgpu.so")
+GPU_LIB_FMA = os.path.join(CSRC_DIR, "libh3dgpu_fma.so")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libh3doracle.so")
 
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
@@ -63,19 +64,29 @@ def nvcc_path():
     return p
 
 
+# -fmad=false: the reference's gfortran RELEASE build contracts no FMA; without contraction the device results are
+# bit-identical to the oracle (profiles/r1_a_first_correct/parity_strict.txt) at a measured cost of ~2 % (HBM-bound kernels).
 GPU_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-             "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+             "--expt-relaxed-constexpr", "-Xptxas", "-v", "-fmad=false"]
 
 
-def build_gpu(force=False, extra=()):
+def build_gpu(force=False, extra=(), out=None):
+    """libh3dgpu.so.  `extra`/`out` build a variant of the same sources (e.g. extra=("-fmad=false",) for the
+    strict-IEEE parity build, out=GPU_LIB_STRICT)."""
+    out = out or GPU_LIB
     srcs = _sources(CSRC_DIR, (".cu", ".cuh", ".h")) + _sources(INCLUDE_DIR, (".h",))
-    if force or _newer(GPU_LIB, srcs):
+    if force or _newer(out, srcs):
         cus = [s for s in srcs if s.endswith(".cu")]
-        cmd = [nvcc_path()] + GPU_FLAGS + list(extra) + ["-shared", "-I", INCLUDE_DIR, "-I", CSRC_DIR] + cus + ["-o", GPU_LIB, "-lnccl"]
-        out = _run(cmd)
-        with open(os.path.join(CSRC_DIR, "ptxas_info.txt"), "w") as f:
-            f.write(out)
-    return GPU_LIB
+        cmd = [nvcc_path()] + GPU_FLAGS + list(extra) + ["-shared", "-I", INCLUDE_DIR, "-I", CSRC_DIR] + cus + ["-o", out, "-lnccl"]
+        log = _run(cmd)
+        with open(os.path.splitext(out)[0] + ".ptxas.txt", "w") as f:
+            f.write(log)
+    return out
+
+
+def build_gpu_fma(force=False):
+    """Variant WITH FMA contraction (not bit-comparable with the oracle; kept to measure what contraction buys)."""
+    return build_gpu(force, extra=("-fmad=true",), out=GPU_LIB_FMA)
 
 
 def build_oracle(force=False):
@@ -94,5 +105,5 @@ def build_all(force=False):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    {"host": build_host, "gpu": build_gpu, "oracle": build_oracle, "all": build_all}[which](force=True)
+    {"host": build_host, "gpu": build_gpu, "fma": build_gpu_fma, "oracle": build_oracle, "all": build_all}[which](force=True)
     print("built", which)

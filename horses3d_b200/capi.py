@@ -101,7 +101,7 @@ def gpu_library():
     """Loads libh3dgpu.so (built in-tree by build.build_gpu).  Raises if it cannot be built/loaded."""
     global _gpu_lib
     if _gpu_lib is None:
-        path = _build.GPU_LIB
+        path = os.environ.get("H3D_GPU_LIB") or _build.GPU_LIB     # H3D_GPU_LIB: alternative build of the SAME sources (e.g. -fmad=false)
         if not os.path.exists(path):
             path = _build.build_gpu()
         _gpu_lib = C.CDLL(path, mode=C.RTLD_GLOBAL)

@@ -273,17 +273,19 @@ template <int n> int launchRiemann(h3d_context* h, int f0, int f1, cudaStream_t 
 template <int n> int launchVolume(h3d_context* h, const RkArgs& rk, int e0, int e1, cudaStream_t s) {
     if (e1 <= e0) return 0;
     const int E = epbFor(n), blocks = (e1 - e0 + E - 1) / E;
-    if (h->ph.averaging >= 0 && h->physics.inviscid == H3D_SPLIT_DG)
-        k_volume<n, true><<<blocks, E * n * n * n, smemVolume(n, true), s>>>(h->m, h->ph, rk, e0, e1);
+    if (h->physics.inviscid == H3D_SPLIT_DG)
+        k_volume<n, true><<<blocks, E * n * n * n, smemVolume(n, true, h->ph.ns != 0), s>>>(h->m, h->ph, rk, e0, e1);
     else
-        k_volume<n, false><<<blocks, E * n * n * n, smemVolume(n, false), s>>>(h->m, h->ph, rk, e0, e1);
+        k_volume<n, false><<<blocks, E * n * n * n, smemVolume(n, false, true), s>>>(h->m, h->ph, rk, e0, e1);
     ++h->launches; return 0;
 }
 template <int n> int setAttrs(h3d_context* h) {
     CTX_CHECK(cudaFuncSetAttribute(k_prolong_q<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemProlong(n)));
     CTX_CHECK(cudaFuncSetAttribute(k_gradient<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient(n)));
-    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume(n, false)));
-    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume(n, true)));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume(n, false, true)));
+    // SplitDG: the Navier-Stokes variant needs 29 n^3 doubles and does not fit 227 KB at n = 10; the Euler variant (19 n^3) does
+    const size_t splitBytes = std::min<size_t>(smemVolume(n, true, true), 227 * 1024);
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)splitBytes));
     return 0;
 }
 
@@ -701,6 +703,7 @@ static int checkReady(h3d_handle h) {
     if (!h->havePhysics || !h->haveBasis || !h->haveMesh) { h->err = "physics, basis and mesh must be set before the residual is evaluated"; return 1; }
     if (h->nFace - h->nFaceLocal > 0 && h->nNbr == 0) { h->err = "mesh has MPI faces but h3d_set_halo was not called"; return 1; }
     if (h->physics.inviscid == H3D_SPLIT_DG && h->nodeType != H3D_GAUSSLOBATTO) { h->err = "split-form discretization needs Gauss-Lobatto nodes"; return 1; }
+    if (h->physics.inviscid == H3D_SPLIT_DG && smemVolume(h->n, true, h->ph.ns != 0) > 227 * 1024) { h->err = "split-form Navier-Stokes at this polynomial order exceeds the 227 KB shared memory of one CTA"; return 1; }
     return 0;
 }
 

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
             viscous_flux(ph, QL, gx, gy, gz, mu, 0.0, kappa, F);
 #pragma unroll
             for (int q = 0; q < 5; ++q) { visc[q] = F[q][0] * nh[0] + F[q][1] * nh[1] + F[q][2] * nh[2]; }
-            bc_neumann(btype, P, visc);
+            bc_neumann(btype, P, QL, visc);
         }
         riemann_solver(ph, QL, QR, nh, t1, t2, inv);
     } else {
@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(epbFor(n) * n * n * n) k_volume(DevMesh m, Phy
     extern __shared__ double smem[];
     // StandardDG: sF = contravariant total flux [EPB][3][5][N3]
     // SplitDG   : sF = viscous contravariant flux [EPB][3][5][N3]; sQ = state [EPB][5][N3]; sJa = metrics [EPB][9][N3]
-    double* sF = smem;
-    double* sQ = sF + EPB * 15 * N3;
+    double* sF = smem;                                // SplitDG + Euler: only 5 fields are needed here (prolongation buffer)
+    double* sQ = sF + EPB * ((SPLIT && !ph.ns) ? 5 : 15) * N3;
     double* sJa = sQ + (SPLIT ? EPB * 5 * N3 : 0);
     double* sFs = sJa + (SPLIT ? EPB * 9 * N3 : 0);   // [EPB][6][5][N2] fStar at element-trace nodes (signed)
     double* sHatDT = sFs + EPB * 6 * 5 * N2;          // [n][n]
@@ -388,8 +388,10 @@ __global__ void __launch_bounds__(epbFor(n) * n * n * n) k_volume(DevMesh m, Phy
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 sQ[(le * 5 + q) * N3 + node] = Q[q];
+                if (ph.ns) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) sF[((le * 3 + d) * 5 + q) * N3 + node] = Fv[q][d];
+                    for (int d = 0; d < 3; ++d) sF[((le * 3 + d) * 5 + q) * N3 + node] = Fv[q][d];
+                }
             }
 #pragma unroll
             for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * N3 + node] = ja[c];
@@ -487,6 +489,6 @@ __global__ void __launch_bounds__(epbFor(n) * n * n * n) k_volume(DevMesh m, Phy
 // shared-memory footprints (bytes)
 inline size_t smemProlong(int n) { const int n3 = n * n * n, E = epbFor(n); return sizeof(double) * ((size_t)E * 5 * n3 + 2 * n); }
 inline size_t smemGradient(int n) { const int n2 = n * n, n3 = n2 * n, E = epbFor(n); return sizeof(double) * ((size_t)E * 15 * n3 + (size_t)E * 6 * 9 * n2 + n2 + 4 * n); }
-inline size_t smemVolume(int n, bool split) { const int n2 = n * n, n3 = n2 * n, E = epbFor(n); return sizeof(double) * ((size_t)E * 15 * n3 + (split ? (size_t)E * 14 * n3 : 0) + (size_t)E * 30 * n2 + 2 * n2 + 4 * n); }
+inline size_t smemVolume(int n, bool split, bool ns) { const int n2 = n * n, n3 = n2 * n, E = epbFor(n); return sizeof(double) * ((size_t)E * ((split && !ns) ? 5 : 15) * n3 + (split ? (size_t)E * 14 * n3 : 0) + (size_t)E * 30 * n2 + 2 * n2 + 4 * n); }
 
 }  // namespace h3d

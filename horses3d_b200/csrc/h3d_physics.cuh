@@ -53,13 +53,19 @@ __device__ __forceinline__ void velocity_gradients(const double Q[5], const doub
     }
 }
 
-// libs/physics/common/LESModels.f90 Smagorinsky: mu_t = rho (Cs delta)^2 |S|
+// libs/physics/common/LESModels.f90:256-305 Smagorinsky: mu_t = rho (Cs delta)^2 sqrt(2 S:S), S summed column by column
 __device__ __forceinline__ double smagorinsky(const Phys& ph, double delta, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5]) {
     double ux[3], uy[3], uz[3];
     velocity_gradients(Q, Qx, Qy, Qz, ux, uy, uz);
-    double normS = pow2(ux[0]) + pow2(uy[1]) + pow2(uz[2]);
-    normS = 2.0 * normS + pow2(ux[1] + uy[0]) + pow2(ux[2] + uz[0]) + pow2(uy[2] + uz[1]);
-    normS = sqrt(normS);
+    // S(i,j) = 1/2 (column j of grad u + row contribution), built exactly as the reference does
+    const double s00 = 0.5 * (ux[0] + ux[0]), s10 = 0.5 * (ux[1] + uy[0]), s20 = 0.5 * (ux[2] + uz[0]);
+    const double s01 = 0.5 * (uy[0] + ux[1]), s11 = 0.5 * (uy[1] + uy[1]), s21 = 0.5 * (uy[2] + uz[1]);
+    const double s02 = 0.5 * (uz[0] + ux[2]), s12 = 0.5 * (uz[1] + uy[2]), s22 = 0.5 * (uz[2] + uz[2]);
+    double sum = 0.0;
+    sum = sum + s00 * s00; sum = sum + s10 * s10; sum = sum + s20 * s20;
+    sum = sum + s01 * s01; sum = sum + s11 * s11; sum = sum + s21 * s21;
+    sum = sum + s02 * s02; sum = sum + s12 * s12; sum = sum + s22 * s22;
+    const double normS = sqrt(2.0 * sum);
     const double LS = ph.Cs * delta;
     return Q[0] * pow2(LS) * normS;
 }
@@ -244,53 +250,72 @@ __device__ __forceinline__ void two_point_flux(const Phys& ph, const double QL[5
 }
 
 // ---- boundary conditions (libs/physics/common/{NoSlipWall,FreeSlipWall,Inflow,Outflow}BC.f90) -------------
-// External state for the Riemann solver (FlowState).  P: 16 parameters of the zone.
+// Zone parameters P[16]: walls: P[0..2] vWall, P[3] wallType (0 adiabatic / 1 isothermal), P[4] Twall,
+// P[5] T_ref*gammaM2*(gamma-1) (no-slip) or T_ref*gammaM2 (free-slip), P[6] eWall; inflow: rho,u,v,w,p; outflow: P[4] pExt.
+// External state for the Riemann solver (FlowState).
 __device__ __forceinline__ void bc_flow_state(const Phys& ph, int type, const double* P, const double nHat[3], double Q[5]) {
-    if (type == H3D_BC_NOSLIPWALL) {
+    if (type == H3D_BC_NOSLIPWALL) {            // NoSlipWallBC.f90:265-296
         Q[1] = 2.0 * Q[0] * P[0] - Q[1]; Q[2] = 2.0 * Q[0] * P[1] - Q[2]; Q[3] = 2.0 * Q[0] * P[2] - Q[3];
-    } else if (type == H3D_BC_FREESLIPWALL) {
-        const double vn = Q[1] * nHat[0] + Q[2] * nHat[1] + Q[3] * nHat[2];
-        Q[1] = Q[1] - 2.0 * vn * nHat[0]; Q[2] = Q[2] - 2.0 * vn * nHat[1]; Q[3] = Q[3] - 2.0 * vn * nHat[2];
-    } else if (type == H3D_BC_INFLOW) {
-        const double rho = P[0], u = P[1], v = P[2], w = P[3], p = P[4];
-        Q[0] = rho; Q[1] = rho * u; Q[2] = rho * v; Q[3] = rho * w; Q[4] = p / ph.gm1 + 0.5 * rho * (u * u + v * v + w * w);
-    } else if (type == H3D_BC_OUTFLOW) {
+        Q[4] = Q[4] + P[3] * (Q[0] * P[4] / P[5] - Q[4]);
+    } else if (type == H3D_BC_FREESLIPWALL) {   // FreeSlipWallBC.f90:249-283
+        const double qNorm = nHat[0] * Q[1] + nHat[1] * Q[2] + nHat[2] * Q[3];
+        Q[1] = Q[1] - 2.0 * qNorm * nHat[0]; Q[2] = Q[2] - 2.0 * qNorm * nHat[1]; Q[3] = Q[3] - 2.0 * qNorm * nHat[2];
+        const double paux = Q[0] * P[4] / P[5];
+        Q[4] = Q[4] + P[3] * (paux / ph.gm1 + 0.5 * (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) / Q[0] - Q[4]);
+    } else if (type == H3D_BC_INFLOW) {         // InflowBC.f90:363-406 with zero turbulence intensity
+        const double u = P[1], v = P[2], w = P[3];
+        Q[0] = P[0]; Q[1] = Q[0] * u; Q[2] = Q[0] * v; Q[3] = Q[0] * w;
+        Q[4] = P[4] / (ph.gamma - 1.0) + 0.5 * Q[0] * (u * u + v * v + w * w);
+    } else if (type == H3D_BC_OUTFLOW) {        // OutflowBC.f90:226-288
         const double pExt = P[4];
-        const double rhoInt = Q[0], invRho = 1.0 / rhoInt;
-        const double uInt = Q[1] * invRho, vInt = Q[2] * invRho, wInt = Q[3] * invRho;
-        const double pInt = ph.gm1 * (Q[4] - 0.5 * (Q[1] * uInt + Q[2] * vInt + Q[3] * wInt));
-        const double qnInt = uInt * nHat[0] + vInt * nHat[1] + wInt * nHat[2];
-        const double aInt = sqrt(ph.gamma * pInt * invRho);
-        if (!(qnInt > 0.0 && qnInt / aInt >= 1.0)) {
-            Q[0] = rhoInt; Q[1] = rhoInt * uInt; Q[2] = rhoInt * vInt; Q[3] = rhoInt * wInt;
-            Q[4] = pExt / ph.gm1 + 0.5 * rhoInt * (uInt * uInt + vInt * vInt + wInt * wInt);
+        double qDotN = (nHat[0] * Q[1] + nHat[1] * Q[2] + nHat[2] * Q[3]) / Q[0];
+        const double qTanx = Q[1] / Q[0] - qDotN * nHat[0], qTany = Q[2] / Q[0] - qDotN * nHat[1], qTanz = Q[3] / Q[0] - qDotN * nHat[2];
+        const double p = ph.gm1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
+        const double a2 = ph.gamma * p / Q[0];
+        double a = sqrt(a2);
+        if (fabs(qDotN / a) <= 1.0) {
+            const double rPlus = qDotN + 2.0 * a / ph.gm1;
+            const double entropyConstant = p - a2 * Q[0];
+            const double rho = -(entropyConstant - pExt) / a2;
+            a = sqrt(ph.gamma * pExt / rho);
+            qDotN = rPlus - 2.0 * a / ph.gm1;
+            const double u = qTanx + qDotN * nHat[0], v = qTany + qDotN * nHat[1], w = qTanz + qDotN * nHat[2];
+            Q[0] = rho; Q[1] = rho * u; Q[2] = rho * v; Q[3] = rho * w;
+            Q[4] = pExt / ph.gm1 + 0.5 * rho * (u * u + v * v + w * w);
         }
     }
 }
 
-// Boundary value of the gradient variables (FlowGradVars, STATE variables)
+// Boundary value of the gradient variables (FlowGradVars with STATE variables); us enters as the interior state
 __device__ __forceinline__ void bc_grad_vars(const Phys& ph, int type, const double* P, const double nHat[3], const double Qi[5], double us[5]) {
 #pragma unroll
     for (int q = 0; q < 5; ++q) us[q] = Qi[q];
-    if (type == H3D_BC_NOSLIPWALL) {
-        const double rho = Qi[0], invRho = 1.0 / rho;
-        const double eInt = Qi[4] - 0.5 * (pow2(Qi[1]) + pow2(Qi[2]) + pow2(Qi[3])) * invRho;
-        us[0] = rho; us[1] = rho * P[0]; us[2] = rho * P[1]; us[3] = rho * P[2];
-        us[4] = eInt + 0.5 * rho * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]);
-    } else if (type == H3D_BC_FREESLIPWALL) {
-        const double vn = Qi[1] * nHat[0] + Qi[2] * nHat[1] + Qi[3] * nHat[2];
-        us[1] = Qi[1] - vn * nHat[0]; us[2] = Qi[2] - vn * nHat[1]; us[3] = Qi[3] - vn * nHat[2];
-    } else if (type == H3D_BC_INFLOW || type == H3D_BC_OUTFLOW) {
+    if (type == H3D_BC_NOSLIPWALL) {            // NoSlipWallBC.f90:298-337
+        const double invRho = 1.0 / Qi[0];
+        const double e_int = invRho * (Qi[4] - 0.5 * invRho * (pow2(Qi[1]) + pow2(Qi[2]) + pow2(Qi[3])));
+        us[1] = Qi[0] * P[0]; us[2] = Qi[0] * P[1]; us[3] = Qi[0] * P[2];
+        us[4] = Qi[0] * ((1.0 - P[3]) * e_int + P[3] * P[6] + 0.5 * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]));
+    } else if (type == H3D_BC_FREESLIPWALL) {   // FreeSlipWallBC.f90:285-312
+        us[4] = Qi[4] + P[3] * (Qi[0] * P[6] + 0.5 * (pow2(Qi[1]) + pow2(Qi[2]) + pow2(Qi[3])) / Qi[0] - Qi[4]);
+    } else if (type == H3D_BC_INFLOW || type == H3D_BC_OUTFLOW) {   // GenericBoundaryConditionClass.f90:243-278
         bc_flow_state(ph, type, P, nHat, us);
     }
 }
 
-// Neumann fix-up of the boundary viscous flux (FlowNeumann)
-__device__ __forceinline__ void bc_neumann(int type, const double* P, double visc[5]) {
-    if (type == H3D_BC_NOSLIPWALL) {
-        const double work = visc[1] * P[0] + visc[2] * P[1] + visc[3] * P[2];
-        visc[0] = 0.0; visc[4] = work;
-    } else if (type == H3D_BC_FREESLIPWALL || type == H3D_BC_INFLOW || type == H3D_BC_OUTFLOW) {
+// Neumann fix-up of the boundary viscous flux (FlowNeumann); Q is the interior trace
+__device__ __forceinline__ void bc_neumann(int type, const double* P, const double Q[5], double visc[5]) {
+    if (type == H3D_BC_NOSLIPWALL) {            // NoSlipWallBC.f90:339-372
+        const double invRho = 1.0 / Q[0], u = invRho * Q[1], v = invRho * Q[2], w = invRho * Q[3];
+        const double viscWork = u * visc[1] + v * visc[2] + w * visc[3];
+        const double heatFlux = visc[4] - viscWork;
+        visc[0] = 0.0;
+        visc[4] = (P[0] * visc[1] + P[1] * visc[2] + P[2] * visc[3]) + P[3] * heatFlux;
+    } else if (type == H3D_BC_FREESLIPWALL) {   // FreeSlipWallBC.f90:314-351
+        const double viscWork = (visc[1] * Q[1] + visc[2] * Q[2] + visc[3] * Q[3]) / Q[0];
+        const double heatFlux = visc[4] - viscWork;
+        visc[0] = 0.0; visc[1] = 0.0; visc[2] = 0.0; visc[3] = 0.0;
+        visc[4] = P[3] * heatFlux;
+    } else if (type == H3D_BC_INFLOW || type == H3D_BC_OUTFLOW) {
 #pragma unroll
         for (int q = 0; q < 5; ++q) visc[q] = 0.0;
     }

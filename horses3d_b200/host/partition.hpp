@@ -8,15 +8,16 @@
 //                                                 side (1/2) the local element had on the global face
 //   mesh/HexMesh.f90:2663-2664                    per-neighbour face lists define the exchange order
 #pragma once
+#include <cstdint>
 #include <numeric>
 
 #include "mesh.hpp"
 
 extern "C" {
-// METIS 5 (libmetis_static.a shipped with the CUDA toolkit); idx_t = int32, real_t = float in that build
-int METIS_SetDefaultOptions(int* options);
-int METIS_PartMeshDual(int* ne, int* nn, int* eptr, int* eind, int* vwgt, int* vsize, int* ncommon, int* nparts,
-                       float* tpwgts, int* options, int* objval, int* epart, int* npart);
+// METIS 5 (libmetis_static.a shipped with the CUDA toolkit): that build uses idx_t = int64 (probed), real_t = float
+int METIS_SetDefaultOptions(int64_t* options);
+int METIS_PartMeshDual(int64_t* ne, int64_t* nn, int64_t* eptr, int64_t* eind, int64_t* vwgt, int64_t* vsize, int64_t* ncommon, int64_t* nparts,
+                       float* tpwgts, int64_t* options, int64_t* objval, int64_t* epart, int64_t* npart);
 }
 
 namespace h3d {
@@ -35,12 +36,13 @@ inline bool partitionElements(const HostMesh& m, int nparts, int method, int* pa
         return true;
     }
 #ifdef H3D_HAS_METIS
-    int ne = nE, nn = m.nNodes(), ncommon = 4, np = nparts, objval = 0;
-    std::vector<int> eptr(nE + 1), eind(m.elemNodes), npart(nn), options(40);
-    for (int e = 0; e <= nE; ++e) eptr[e] = 8 * e;
+    int64_t ne = nE, nn = m.nNodes(), ncommon = 4, np = nparts, objval = 0;
+    std::vector<int64_t> eptr(nE + 1), eind(m.elemNodes.begin(), m.elemNodes.end()), npart(nn), epart(nE), options(40);
+    for (int e = 0; e <= nE; ++e) eptr[e] = 8 * (int64_t)e;
     METIS_SetDefaultOptions(options.data());
-    int rc = METIS_PartMeshDual(&ne, &nn, eptr.data(), eind.data(), nullptr, nullptr, &ncommon, &np, nullptr, options.data(), &objval, part, npart.data());
+    int rc = METIS_PartMeshDual(&ne, &nn, eptr.data(), eind.data(), nullptr, nullptr, &ncommon, &np, nullptr, options.data(), &objval, epart.data(), npart.data());
     if (rc != 1) { err = "METIS_PartMeshDual failed"; return false; }
+    for (int e = 0; e < nE; ++e) part[e] = (int)epart[e];
     return true;
 #else
     err = "library built without METIS";

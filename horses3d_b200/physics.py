@@ -57,3 +57,40 @@ def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="
     p.les = LES[les.lower()]
     p.smagorinsky_Cs = smagorinsky_cs
     return p
+
+
+def bc_parameters(kind, physics, **kw):
+    """16 parameters of one boundary zone, laid out as include/h3d_gpu.h documents (walls, inflow, outflow).
+
+    Mirrors the BC constructors: NoSlipWallBC.f90:150-210, FreeSlipWallBC.f90:150-200, InflowBC.f90:150-330,
+    OutflowBC.f90:120-200.  Non-dimensional inputs (the reference divides by refValues there)."""
+    import math
+    P = [0.0] * 16
+    kind = kind.lower()
+    Tref = 520.0 * 5.0 / 9.0
+    if kind in ("noslipwall", "freeslipwall"):
+        vw = kw.get("wall_velocity", (0.0, 0.0, 0.0))
+        if kind == "noslipwall":
+            P[0:3] = [float(x) for x in vw]
+        iso = 0.0 if kw.get("adiabatic", True) else 1.0
+        Twall = kw.get("wall_temperature", Tref) if iso else 0.0
+        P[3], P[4] = iso, Twall
+        P[5] = Tref * physics.gammaM2 * physics.gammaMinus1 if kind == "noslipwall" else Tref * physics.gammaM2
+        P[6] = Twall / (Tref * physics.gammaMinus1 * physics.gammaM2) if iso else 0.0
+    elif kind == "inflow":
+        # defaults of InflowBC: rho = 1, |v| = 1, p = 1/(gamma M^2); AoA from the control file
+        rho = kw.get("rho", 1.0)
+        vmag = kw.get("v", 1.0)
+        th, ph = kw.get("aoa_theta", 0.0), kw.get("aoa_phi", 0.0)
+        u = vmag * math.cos(th) * math.cos(ph)
+        v = vmag * math.sin(th) * math.cos(ph)
+        w = vmag * math.sin(ph)
+        P[0], P[1], P[2], P[3] = rho, u, v, w
+        P[4] = kw.get("p", 1.0 / physics.gammaM2)
+    elif kind == "outflow":
+        P[4] = kw.get("p", 1.0 / physics.gammaM2)
+    elif kind == "periodic":
+        pass
+    else:
+        raise ValueError("boundary condition %r is not implemented" % kind)
+    return P

@@ -58,11 +58,11 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_FACE_MPI 3
 
 /* boundary conditions (libs/physics/common, the BC class files); parameters: 16 doubles per zone */
-#define H3D_BC_PERIODIC 0      /* never reaches the device: merged into interior faces at mesh build */
-#define H3D_BC_NOSLIPWALL 1    /* params: [0..2] wall velocity, [3] isAdiabatic (1) or isothermal (0) */
-#define H3D_BC_FREESLIPWALL 2  /* params: [3] isAdiabatic */
-#define H3D_BC_INFLOW 3        /* params: [0] rho, [1..3] u,v,w, [4] p  (non-dimensional) */
-#define H3D_BC_OUTFLOW 4       /* params: [0] rho, [1..3] u,v,w, [4] p  (non-dimensional external state) */
+#define H3D_BC_PERIODIC 0      /* never reaches the device: merged into interior faces at mesh build (HexMesh.f90:519) */
+#define H3D_BC_NOSLIPWALL 1    /* [0..2] vWall, [3] wallType (0 adiabatic, 1 isothermal), [4] Twall, [5] T_ref*gammaM2*gammaMinus1, [6] eWall */
+#define H3D_BC_FREESLIPWALL 2  /* [3] wallType, [4] Twall, [5] T_ref*gammaM2, [6] eWall                                          */
+#define H3D_BC_INFLOW 3        /* [0] rho, [1..3] u,v,w (from |v| and the angles of attack), [4] p; turbulence intensity 0    */
+#define H3D_BC_OUTFLOW 4       /* [4] pExt                                                                                   */
 
 /* volume integrals (libs/monitors/VolumeIntegrals.f90:30-60) */
 #define H3D_INT_VOLUME 0

@@ -139,14 +139,17 @@ inline void getVelocityGradients_State(const double* Q, const double* Q_x, const
     }
 }
 
-// LESModels.f90:256-305 (Smagorinsky, no wall damping: LESModels.f90:162-165 default)
+// LESModels.f90:256-305 (Smagorinsky_ComputeViscosity; no wall model is the default, :162-165)
 inline double SmagorinskyViscosity(const Oracle& o, double delta, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z) {
-    double U_x[3], U_y[3], U_z[3];
+    double U_x[3], U_y[3], U_z[3], S[3][3];
     getVelocityGradients_State(Q, Q_x, Q_y, Q_z, U_x, U_y, U_z);
-    // |S|^2 = 2 Sij Sij
-    double normS = POW2(U_x[0]) + POW2(U_y[1]) + POW2(U_z[2]);
-    normS = 2.0 * normS + POW2(U_x[1] + U_y[0]) + POW2(U_x[2] + U_z[0]) + POW2(U_y[2] + U_z[1]);
-    normS = std::sqrt(normS);
+    for (int i = 0; i < 3; ++i) { S[i][0] = U_x[i]; S[i][1] = U_y[i]; S[i][2] = U_z[i]; }
+    for (int j = 0; j < 3; ++j) S[0][j] = S[0][j] + U_x[j];
+    for (int j = 0; j < 3; ++j) S[1][j] = S[1][j] + U_y[j];
+    for (int j = 0; j < 3; ++j) S[2][j] = S[2][j] + U_z[j];
+    double sum = 0.0;
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) { double sij = 0.5 * S[i][j]; sum = sum + sij * sij; }   // column-major sum(S*S)
+    double normS = std::sqrt(2.0 * sum);
     double LS = o.ph.smagorinsky_Cs * delta;
     return Q[IRHO] * POW2(LS) * normS;
 }
@@ -327,41 +330,95 @@ inline void TwoPointFlux(const Oracle& o, const double* QL, const double* QR, co
 }
 
 // ------------------------------------------------------------------------------------------------
-//  Boundary conditions (libs/physics/common): state, gradient variables, Neumann flux
+//  Boundary conditions (libs/physics/common): FlowState, FlowGradVars, FlowNeumann.
+//  Zone parameters P[16] (prepared by the host from the control file, see include/h3d_gpu.h):
+//    no-slip / free-slip wall: P[0..2] vWall, P[3] wallType (0 adiabatic, 1 isothermal), P[4] Twall,
+//                              P[5] refValues%T*gammaM2*gammaMinus1 (no-slip) or refValues%T*gammaM2 (free-slip), P[6] eWall
+//    inflow: P[0] rho, P[1..3] u,v,w, P[4] p        outflow: P[4] pExt
 // ------------------------------------------------------------------------------------------------
-// NoSlipWallBC.f90:265-296 (FlowState), :298-337 (FlowGradVars, STATE variables), :339-372 (FlowNeumann)
-// FreeSlipWallBC.f90:249-351 ; InflowBC.f90:363-425 ; OutflowBC.f90:226-300
 inline void BC_FlowState(const Oracle& o, int zone, const double* nHat, double* Q) {
     const double* P = &o.bcParams[16 * zone];
     const double gamma = o.ph.gamma, gm1 = o.ph.gammaMinus1;
     switch (o.bcType[zone]) {
-        case H3D_BC_NOSLIPWALL: {
-            // Q(IRHOU:IRHOW) = 2 rho vWall - Q(IRHOU:IRHOW); isothermal not restated (adiabatic only)
+        case H3D_BC_NOSLIPWALL: {   // NoSlipWallBC.f90:265-296
             Q[IRHOU] = 2.0 * Q[IRHO] * P[0] - Q[IRHOU]; Q[IRHOV] = 2.0 * Q[IRHO] * P[1] - Q[IRHOV]; Q[IRHOW] = 2.0 * Q[IRHO] * P[2] - Q[IRHOW];
+            Q[IRHOE] = Q[IRHOE] + P[3] * (Q[IRHO] * P[4] / P[5] - Q[IRHOE]);
         } break;
-        case H3D_BC_FREESLIPWALL: {
-            double vn = Q[IRHOU] * nHat[0] + Q[IRHOV] * nHat[1] + Q[IRHOW] * nHat[2];
-            Q[IRHOU] = Q[IRHOU] - 2.0 * vn * nHat[0]; Q[IRHOV] = Q[IRHOV] - 2.0 * vn * nHat[1]; Q[IRHOW] = Q[IRHOW] - 2.0 * vn * nHat[2];
+        case H3D_BC_FREESLIPWALL: { // FreeSlipWallBC.f90:249-283
+            double qNorm = nHat[IX] * Q[IRHOU] + nHat[IY] * Q[IRHOV] + nHat[IZ] * Q[IRHOW];
+            Q[IRHOU] = Q[IRHOU] - 2.0 * qNorm * nHat[0]; Q[IRHOV] = Q[IRHOV] - 2.0 * qNorm * nHat[1]; Q[IRHOW] = Q[IRHOW] - 2.0 * qNorm * nHat[2];
+            double pressure_aux = Q[IRHO] * P[4] / P[5];
+            Q[IRHOE] = Q[IRHOE] + P[3] * (pressure_aux / gm1 + 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] - Q[IRHOE]);
         } break;
-        case H3D_BC_INFLOW: {
-            double rho = P[0], u = P[1], v = P[2], w = P[3], p = P[4];
-            Q[IRHO] = rho; Q[IRHOU] = rho * u; Q[IRHOV] = rho * v; Q[IRHOW] = rho * w;
-            Q[IRHOE] = p / gm1 + 0.5 * rho * (u * u + v * v + w * w);
+        case H3D_BC_INFLOW: {       // InflowBC.f90:363-406 (TurbIntensity = 0)
+            double u = P[1], v = P[2], w = P[3];
+            Q[0] = P[0]; Q[1] = Q[0] * u; Q[2] = Q[0] * v; Q[3] = Q[0] * w;
+            Q[4] = P[4] / (gamma - 1.0) + 0.5 * Q[0] * (u * u + v * v + w * w);
         } break;
-        case H3D_BC_OUTFLOW: {
-            // OutflowBC.f90:226-288: subsonic outflow keeps interior entropy/Riemann invariant, imposes pExt
-            double rhoExt = P[0], uExt = P[1], vExt = P[2], wExt = P[3], pExt = P[4];
-            double rhoInt = Q[IRHO], invRho = 1.0 / rhoInt;
-            double uInt = Q[IRHOU] * invRho, vInt = Q[IRHOV] * invRho, wInt = Q[IRHOW] * invRho;
-            double pInt = gm1 * (Q[IRHOE] - 0.5 * (Q[IRHOU] * uInt + Q[IRHOV] * vInt + Q[IRHOW] * wInt));
-            double qnInt = uInt * nHat[0] + vInt * nHat[1] + wInt * nHat[2];
-            double aInt = std::sqrt(gamma * pInt * invRho);
-            if (qnInt > 0.0 && qnInt / aInt >= 1.0) break;   // supersonic outflow: interior state
-            (void)rhoExt; (void)uExt; (void)vExt; (void)wExt;
-            double rhoG = rhoInt, uG = uInt, vG = vInt, wG = wInt;
-            Q[IRHO] = rhoG; Q[IRHOU] = rhoG * uG; Q[IRHOV] = rhoG * vG; Q[IRHOW] = rhoG * wG;
-            Q[IRHOE] = pExt / gm1 + 0.5 * rhoG * (uG * uG + vG * vG + wG * wG);
+        case H3D_BC_OUTFLOW: {      // OutflowBC.f90:226-288
+            const double pExt = P[4];
+            double qDotN = (nHat[0] * Q[1] + nHat[1] * Q[2] + nHat[2] * Q[3]) / Q[0];
+            double qTanx = Q[1] / Q[0] - qDotN * nHat[0], qTany = Q[2] / Q[0] - qDotN * nHat[1], qTanz = Q[3] / Q[0] - qDotN * nHat[2];
+            double p = gm1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
+            double a2 = gamma * p / Q[0];
+            double a = std::sqrt(a2);
+            double normalMachNo = std::fabs(qDotN / a);
+            if (normalMachNo <= 1.0) {
+                double rPlus = qDotN + 2.0 * a / gm1;
+                double entropyConstant = p - a2 * Q[0];
+                double rho = -(entropyConstant - pExt) / a2;
+                a = std::sqrt(gamma * pExt / rho);
+                qDotN = rPlus - 2.0 * a / gm1;
+                double u = qTanx + qDotN * nHat[0], v = qTany + qDotN * nHat[1], w = qTanz + qDotN * nHat[2];
+                Q[0] = rho; Q[1] = rho * u; Q[2] = rho * v; Q[3] = rho * w;
+                Q[4] = pExt / gm1 + 0.5 * rho * (u * u + v * v + w * w);
+            }
         } break;
+        default: break;
+    }
+}
+
+// u_star for BR1_ComputeBoundaryFlux (EllipticBR1.f90:686-736): GradVarsForEqn -> FlowGradVars, STATE gradient variables
+inline void BC_FlowGradVars(const Oracle& o, int zone, const double* nHat, const double* Q, double* U) {
+    const double* P = &o.bcParams[16 * zone];
+    switch (o.bcType[zone]) {
+        case H3D_BC_NOSLIPWALL: {   // NoSlipWallBC.f90:298-337 ; U(IRHO) keeps the incoming (interior) value
+            double invRho = 1.0 / Q[IRHO];
+            double e_int = invRho * (Q[IRHOE] - 0.5 * invRho * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])));
+            double U1 = U[IRHO];
+            U[IRHOU] = Q[IRHO] * P[0]; U[IRHOV] = Q[IRHO] * P[1]; U[IRHOW] = Q[IRHO] * P[2];
+            U[IRHOE] = Q[IRHO] * ((1.0 - P[3]) * e_int + P[3] * P[6] + 0.5 * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]));
+            U[IRHO] = U1;
+        } break;
+        case H3D_BC_FREESLIPWALL: { // FreeSlipWallBC.f90:285-312
+            U[IRHO] = Q[IRHO]; U[IRHOU] = Q[IRHOU]; U[IRHOV] = Q[IRHOV]; U[IRHOW] = Q[IRHOW];
+            U[IRHOE] = Q[IRHOE] + P[3] * (Q[IRHO] * P[6] + 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] - Q[IRHOE]);
+        } break;
+        default: {                  // GenericBC_FlowGradVars (GenericBoundaryConditionClass.f90:243-278): gradient variables of the external state
+            for (int q = 0; q < 5; ++q) U[q] = Q[q];
+            BC_FlowState(o, zone, nHat, U);
+        } break;
+    }
+}
+
+// FlowNeumann fix-up of the boundary viscous flux
+inline void BC_FlowNeumann(const Oracle& o, int zone, const double* Q, double* flux) {
+    const double* P = &o.bcParams[16 * zone];
+    switch (o.bcType[zone]) {
+        case H3D_BC_NOSLIPWALL: {   // NoSlipWallBC.f90:339-372
+            double invRho = 1.0 / Q[IRHO], u = invRho * Q[IRHOU], v = invRho * Q[IRHOV], w = invRho * Q[IRHOW];
+            double viscWork = u * flux[IRHOU] + v * flux[IRHOV] + w * flux[IRHOW];
+            double heatFlux = flux[IRHOE] - viscWork;
+            flux[IRHO] = 0.0;
+            flux[IRHOE] = (P[0] * flux[IRHOU] + P[1] * flux[IRHOV] + P[2] * flux[IRHOW]) + P[3] * heatFlux;
+        } break;
+        case H3D_BC_FREESLIPWALL: { // FreeSlipWallBC.f90:314-351
+            double viscWork = (flux[IRHOU] * Q[IRHOU] + flux[IRHOV] * Q[IRHOV] + flux[IRHOW] * Q[IRHOW]) / Q[IRHO];
+            double heatFlux = flux[IRHOE] - viscWork;
+            flux[IRHO] = 0.0; flux[IRHOU] = 0.0; flux[IRHOV] = 0.0; flux[IRHOW] = 0.0;
+            flux[IRHOE] = P[3] * heatFlux;
+        } break;
+        case H3D_BC_INFLOW: case H3D_BC_OUTFLOW: for (int q = 0; q < 5; ++q) flux[q] = 0.0; break;   // InflowBC.f90:408-427, OutflowBC.f90:290-305
         default: break;
     }
 }
@@ -479,24 +536,7 @@ void computeGradient(Oracle& o, double time) {
                 const double Jf = o.fJac[ix.gnode(f, i, j)]; const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
                 double u_int[5], u_star[5];
                 for (int q = 0; q < 5; ++q) { u_int[q] = Qi[q]; u_star[q] = Qi[q]; }
-                // GradVarsForEqn -> FlowGradVars (STATE gradient variables)
-                switch (o.bcType[zone]) {
-                    case H3D_BC_NOSLIPWALL: {   // NoSlipWallBC.f90:298-337: wall velocity, interior internal energy (adiabatic)
-                        const double* P = &o.bcParams[16 * zone];
-                        double rho = Qi[IRHO], invRho = 1.0 / rho;
-                        double eInt = Qi[IRHOE] - 0.5 * (POW2(Qi[IRHOU]) + POW2(Qi[IRHOV]) + POW2(Qi[IRHOW])) * invRho;
-                        u_star[IRHO] = rho; u_star[IRHOU] = rho * P[0]; u_star[IRHOV] = rho * P[1]; u_star[IRHOW] = rho * P[2];
-                        u_star[IRHOE] = eInt + 0.5 * rho * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]);
-                    } break;
-                    case H3D_BC_FREESLIPWALL: {  // FreeSlipWallBC.f90:283-312: remove the normal momentum
-                        double vn = Qi[IRHOU] * nh[0] + Qi[IRHOV] * nh[1] + Qi[IRHOW] * nh[2];
-                        u_star[IRHOU] = Qi[IRHOU] - vn * nh[0]; u_star[IRHOV] = Qi[IRHOV] - vn * nh[1]; u_star[IRHOW] = Qi[IRHOW] - vn * nh[2];
-                    } break;
-                    case H3D_BC_INFLOW: case H3D_BC_OUTFLOW: {   // InflowBC.f90:403-412 / OutflowBC.f90: external state
-                        BC_FlowState(o, zone, nh, u_star);
-                    } break;
-                    default: break;
-                }
+                BC_FlowGradVars(o, zone, nh, Qi, u_star);
                 double* uL = &o.unStar[ix.fnode(f, 0, i, j) * 15];
                 for (int q = 0; q < 5; ++q) for (int d = 0; d < 3; ++d) uL[d * 5 + q] = (u_star[q] - u_int[q]) * nh[d] * Jf;
             }
@@ -684,19 +724,7 @@ void computeQDot(Oracle& o, double time) {
                     double fv[5][3];
                     ViscousFlux_STATE(o, &o.fQ[5 * gL], &o.fUx[5 * gL], &o.fUy[5 * gL], &o.fUz[5 * gL], o.fmu[2 * gL], 0.0, o.fmu[2 * gL + 1], fv);
                     for (int q = 0; q < 5; ++q) { visc[q] = fv[q][IX] * nh[IX] + fv[q][IY] * nh[IY] + fv[q][IZ] * nh[IZ]; visc[q] = visc[q] + 0.0; }
-                    // FlowNeumann
-                    const double* P = &o.bcParams[16 * zone];
-                    switch (o.bcType[zone]) {
-                        case H3D_BC_NOSLIPWALL: {  // NoSlipWallBC.f90:339-372 (adiabatic): no mass flux, energy flux = vWall . tau
-                            double work = visc[IRHOU] * P[0] + visc[IRHOV] * P[1] + visc[IRHOW] * P[2];
-                            visc[IRHO] = 0.0; visc[IRHOE] = work;
-                        } break;
-                        case H3D_BC_FREESLIPWALL: {  // FreeSlipWallBC.f90:314-351: zero viscous flux (adiabatic)
-                            for (int q = 0; q < 5; ++q) visc[q] = 0.0;
-                        } break;
-                        case H3D_BC_INFLOW: case H3D_BC_OUTFLOW: for (int q = 0; q < 5; ++q) visc[q] = 0.0; break;   // InflowBC.f90:425
-                        default: break;
-                    }
+                    BC_FlowNeumann(o, zone, &o.fQ[5 * gL], visc);
                 }
                 RiemannSolver(o, &o.fQ[5 * gL], &o.fQ[5 * gR], nh, &o.fT1[3 * gg], &o.fT2[3 * gg], inv);
                 for (int q = 0; q < 5; ++q) o.fStar[5 * gL + q] = (inv[q] - visc[q]) * o.fJac[gg];

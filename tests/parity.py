@@ -8,11 +8,42 @@ from horses3d_b200.physics import make_physics
 _mesh_cache = {}
 
 
-def get_mesh(ne, N, nodes=GAUSS, amp=0.0, shuffle=False, bFaceOrder=2, seed=1234):
-    key = (ne, N, nodes, amp, shuffle, bFaceOrder, seed)
+def channel_bcs(phys):
+    """Non-periodic box: inflow (left), outflow (right), moving and fixed no-slip walls (bottom/top), free-slip (front/back)."""
+    from horses3d_b200.physics import bc_parameters
+    bcs = [("left", "inflow", None), ("right", "outflow", None), ("bottom", "noslipwall", None), ("top", "noslipwall", None),
+           ("front", "freeslipwall", None), ("back", "freeslipwall", None)]
+    params = [bc_parameters("inflow", phys, aoa_theta=0.05, aoa_phi=0.02), bc_parameters("outflow", phys),
+              bc_parameters("noslipwall", phys, wall_velocity=(0.1, 0.0, 0.0)), bc_parameters("noslipwall", phys),
+              bc_parameters("freeslipwall", phys), bc_parameters("freeslipwall", phys)]
+    return bcs, np.array(params)
+
+
+def get_mesh(ne, N, nodes=GAUSS, amp=0.0, shuffle=False, bFaceOrder=2, seed=1234, bc=None, phys=None):
+    key = (ne, N, nodes, amp, shuffle, bFaceOrder, seed, bc)
     if key not in _mesh_cache:
-        _mesh_cache[key] = HostMesh.box(ne, amp=amp, bFaceOrder=bFaceOrder, shuffle=shuffle, seed=seed).connect().geometry(N, nodes)
+        m = HostMesh.box(ne, amp=amp, bFaceOrder=bFaceOrder, shuffle=shuffle, seed=seed)
+        if bc == "channel":
+            bcs, params = channel_bcs(phys)
+            m.connect(bcs, params)
+        else:
+            m.connect()
+        _mesh_cache[key] = m.geometry(N, nodes)
     return _mesh_cache[key]
+
+
+def channel_state(x, phys):
+    """Smooth non-uniform state around the inflow condition (rho ~ 1, |v| ~ 1, p ~ 1/(gamma M^2))."""
+    X, Y, Z = x[..., 0], x[..., 1], x[..., 2]
+    rho = 1.0 + 0.05 * np.sin(X) * np.cos(Y + 0.1) * np.cos(2 * Z)
+    u = 1.0 + 0.1 * np.sin(Y) * np.cos(Z)
+    v = 0.1 * np.sin(X + 0.3) * np.cos(Z)
+    w = 0.05 * np.cos(X) * np.sin(2 * Y)
+    p = (1.0 / phys.gammaM2) * (1.0 + 0.02 * np.cos(X) * np.sin(Y) * np.cos(Z))
+    Q = np.empty(x.shape[:-1] + (5,))
+    Q[..., 0], Q[..., 1], Q[..., 2], Q[..., 3] = rho, rho * u, rho * v, rho * w
+    Q[..., 4] = p / phys.gammaMinus1 + 0.5 * rho * (u * u + v * v + w * w)
+    return Q
 
 
 def perturbed_tgv(x, mach_scale=1.0):

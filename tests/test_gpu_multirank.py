@@ -1,0 +1,84 @@
+"""Two ranks, two B200s: partitioned mesh + NCCL face exchange must reproduce the single-domain oracle.
+Skipped on boxes with fewer than two GPUs (run with `gpurun --gpus 2`)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, kw, method, N, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from horses3d_b200.capi import GpuApi
+        from horses3d_b200.dgsem import DGSem
+        from horses3d_b200.hostmesh import GAUSS, HostMesh
+        from horses3d_b200.physics import make_physics
+        from parity import perturbed_tgv
+        obj = [GpuApi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        g = HostMesh.box(4, amp=0.1, bFaceOrder=2, shuffle=True, seed=11).connect()
+        part = g.partition(world, method)
+        m = g.extract(part, rank).geometry(N, GAUSS)
+        sem = DGSem(GpuApi(rank=rank, nranks=world, device=rank, nccl_id=obj[0]), m, make_physics(**kw))
+        sem.set_initial_condition(perturbed_tgv)
+        sem.ComputeTimeDerivative(0.0)
+        qd = sem.QDot()
+        for _ in range(3):
+            sem.TakeRK3Step(0.0, 1e-3)
+        Qn = sem.Q()
+        res, mon, dts = sem.ComputeMaxResiduals(), sem.volume_monitors(), sem.MaxTimeStep(0.4, 0.4)
+        q.put((rank, m.array("globalElem").copy(), qd, Qn, res, mon, dts))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kw,method", [(dict(flow="NS", mach=0.08, reynolds=1600.0), "metis"), (dict(flow="Euler", mach=0.3, riemann="lax-friedrichs"), "block")])
+def test_two_ranks_reproduce_the_single_domain_oracle(kw, method):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from horses3d_b200.dgsem import DGSem
+    from horses3d_b200.hostmesh import GAUSS, HostMesh
+    from horses3d_b200.physics import make_physics
+    from oracle.oracle_api import OracleApi
+    from parity import perturbed_tgv, rel_err
+    N, world = 3, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kw, method, N, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g = HostMesh.box(4, amp=0.1, bFaceOrder=2, shuffle=True, seed=11).connect().geometry(N, GAUSS)
+    sem = DGSem(OracleApi(), g, make_physics(**kw))
+    sem.set_initial_condition(perturbed_tgv)
+    sem.ComputeTimeDerivative(0.0)
+    qd = sem.QDot()
+    for _ in range(3):
+        sem.TakeRK3Step(0.0, 1e-3)
+    Qn = sem.Q()
+    res, mon, dts = sem.ComputeMaxResiduals(), sem.volume_monitors(), sem.MaxTimeStep(0.4, 0.4)
+    for rank, ge, qd_r, Qn_r, res_r, mon_r, dts_r in got:
+        assert rel_err(qd_r, qd[ge]) < 1e-13
+        assert rel_err(Qn_r, Qn[ge]) < 1e-13
+        assert np.array_equal(res_r, res)                       # max-reduction over ranks: exact
+        assert np.allclose(dts_r, dts, rtol=0, atol=0)
+        for k in mon:
+            assert abs(mon_r[k] - mon[k]) < 1e-12 * max(abs(mon[k]), 1e-30)

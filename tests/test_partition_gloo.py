@@ -1,0 +1,92 @@
+"""Host-side logic of the multi-rank path, world_size 2 and 3 over gloo (CPU only).
+
+Each rank extracts its partition of a curved, randomly re-oriented periodic box, evaluates a smooth function at
+the nodes of its MPI faces (face frame, from its own element's geometry) and exchanges it with the neighbour in the
+halo order given to h3d_set_halo.  Both ranks must see the same physical points node by node, normals must be
+identical (the face frame belongs to the global face) and the surface Jacobians must agree.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from horses3d_b200.hostmesh import GAUSS, HostMesh  # noqa: E402
+
+
+def _worker(rank, world, port, method, N, result):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = HostMesh.box(4, amp=0.1, bFaceOrder=2, shuffle=True, seed=7).connect()
+        part = g.partition(world, method)
+        m = g.extract(part, rank).geometry(N, GAUSS)
+        n2 = (N + 1) ** 2
+        ranks, counts = m.array("haloRank").copy(), m.array("haloCount").copy()
+        faces, sides = m.array("haloFace").copy(), m.array("haloSide").copy()
+        ftype = m.array("faceType")
+        assert counts.sum() == (ftype == 3).sum() and len(faces) == counts.sum()
+        fx = m.array("faceX").reshape(-1, n2, 3)
+        fn = m.array("faceNormal").reshape(-1, n2, 3)
+        fj = m.array("faceJacobian").reshape(-1, n2)
+        off = 0
+        ok = True
+        for nb, cnt in zip(ranks, counts):
+            ids = faces[off:off + cnt]
+            # positions are compared through sin/cos (periodic faces differ by the box length 2 pi)
+            mine = torch.from_numpy(np.concatenate([fx[ids].reshape(cnt, -1), fn[ids].reshape(cnt, -1), fj[ids]], axis=1).copy())
+            theirs = torch.empty_like(mine)
+            reqs = [dist.isend(mine, int(nb)), dist.irecv(theirs, int(nb))]
+            for r in reqs:
+                r.wait()
+            a, b = mine.numpy(), theirs.numpy()
+            px = max(np.abs(np.sin(a[:, :3 * n2]) - np.sin(b[:, :3 * n2])).max(), np.abs(np.cos(a[:, :3 * n2]) - np.cos(b[:, :3 * n2])).max())  # periodic-safe
+            pn = np.abs(a[:, 3 * n2:6 * n2] - b[:, 3 * n2:6 * n2]).max()
+            pj = np.abs(a[:, 6 * n2:] - b[:, 6 * n2:]).max()
+            ok = ok and px < 1e-11 and pn < 1e-11 and pj < 1e-11
+            # the local side must be the complement of the neighbour's side on every shared face
+            s_mine = torch.from_numpy(sides[off:off + cnt].astype(np.int64).copy()); s_theirs = torch.empty_like(s_mine)
+            reqs = [dist.isend(s_mine, int(nb)), dist.irecv(s_theirs, int(nb))]
+            for r in reqs:
+                r.wait()
+            ok = ok and bool(((s_mine + s_theirs) == 1).all())
+            off += cnt
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        nel = torch.tensor([m.nElem])
+        dist.all_reduce(nel)
+        if rank == 0:
+            result.put((int(flag.item()), int(nel.item()), g.nElem))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,method", [(2, "metis"), (2, "block"), (3, "metis")])
+def test_halo_lists_and_mpi_face_geometry_agree_across_ranks(world, method):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, method, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    ok, nel_sum, nel_global = q.get(timeout=10)
+    assert ok == 1
+    assert nel_sum == nel_global
+
+
+def test_partition_is_balanced_and_complete():
+    g = HostMesh.box(6).connect()
+    for method in ("metis", "block"):
+        part = g.partition(4, method)
+        cnt = np.bincount(part, minlength=4)
+        assert cnt.sum() == g.nElem and cnt.min() > 0.8 * g.nElem / 4
