@@ -9,7 +9,7 @@ from horses3d_b200.physics import make_physics
 from parity import get_mesh, rel_err
 from test_gpu_parity import CASES, run_pair
 
-print("library:", os.environ.get("H3D_GPU_LIB", "libh3dgpu.so (production, FMA contraction on)"))
+print("library:", os.environ.get("H3D_GPU_LIB", "libh3dgpu.so (production build, -fmad=false)"))
 print("%-4s %-3s %-5s %-5s %-7s %-60s %10s %10s %12s" % ("ne", "N", "nodes", "amp", "shuffle", "physics", "err gradU", "err QDot", "bit-equal"))
 for ne, N, nodes, amp, shuffle, kw in CASES:
     mesh = get_mesh(ne, N, nodes, amp, shuffle)
