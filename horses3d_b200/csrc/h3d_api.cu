@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,6 +42,9 @@ struct h3d_context {
     double* dPartial = nullptr; double* hScalars = nullptr;  // reduction scratch (device) / pinned host
     bool facesValid = false;
     int storeQDotAlways = 0;
+    int useTma = 1;      // persistent element kernels with bulk-async prefetch where KCfg<n>::TMA_OK
+    int numSMs = 148;
+    std::vector<std::pair<const void*, int>> occCache;
     int profile = 0;
     struct ProfRec { int cls; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -252,16 +256,28 @@ __global__ void k_halo_unpack(DevMesh m, const int* haloFace, const int* haloSid
 }
 
 // ---- launch helpers --------------------------------------------------------------------------------------
+// persistent kernels: one resident wave, sized by the occupancy the kernel really gets (cached per function)
+int persistentGrid(h3d_context* h, const void* fn, int threads, size_t smemBytes) {
+    for (auto& p : h->occCache) if (p.first == fn) return p.second;
+    int perSM = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, threads, smemBytes) != cudaSuccess || perSM < 1) perSM = 1;
+    h->occCache.push_back({fn, perSM * h->numSMs});
+    return perSM * h->numSMs;
+}
+
 template <int n> int launchProlong(h3d_context* h, int e0, int e1, cudaStream_t s) {
     if (e1 <= e0) return 0;
-    const int E = epbFor(n), blocks = (e1 - e0 + E - 1) / E;
-    k_prolong_q<n><<<blocks, E * n * n * n, smemProlong(n), s>>>(h->m, e0, e1);
+    using C = KCfg<n>;
+    const int blocks = (e1 - e0 + C::EPB - 1) / C::EPB;
+    k_prolong_q<n><<<blocks, C::NT, smemProlong<n>(), s>>>(h->m, e0, e1);
     ++h->launches; return 0;
 }
 template <int n> int launchGradient(h3d_context* h, int e0, int e1, cudaStream_t s) {
     if (e1 <= e0) return 0;
-    const int E = epbFor(n), blocks = (e1 - e0 + E - 1) / E;
-    k_gradient<n><<<blocks, E * n * n * n, smemGradient(n), s>>>(h->m, h->ph, e0, e1);
+    using C = KCfg<n>;
+    const int tiles = (e1 - e0 + C::EPB - 1) / C::EPB;
+    if (C::TMA_OK && h->useTma) k_gradient<n, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient<n, C::TMA_OK>, C::NT, smemGradient<n, C::TMA_OK>())), C::NT, smemGradient<n, C::TMA_OK>(), s>>>(h->m, h->ph, e0, e1);
+    else k_gradient<n, false><<<tiles, C::NT, smemGradient<n, false>(), s>>>(h->m, h->ph, e0, e1);
     ++h->launches; return 0;
 }
 template <int n> int launchRiemann(h3d_context* h, int f0, int f1, cudaStream_t s) {
@@ -272,22 +288,36 @@ template <int n> int launchRiemann(h3d_context* h, int f0, int f1, cudaStream_t 
 }
 template <int n> int launchVolume(h3d_context* h, const RkArgs& rk, int e0, int e1, cudaStream_t s) {
     if (e1 <= e0) return 0;
-    const int E = epbFor(n), blocks = (e1 - e0 + E - 1) / E;
-    if (h->physics.inviscid == H3D_SPLIT_DG)
-        k_volume<n, true><<<blocks, E * n * n * n, smemVolume(n, true, h->ph.ns != 0), s>>>(h->m, h->ph, rk, e0, e1);
-    else
-        k_volume<n, false><<<blocks, E * n * n * n, smemVolume(n, false, true), s>>>(h->m, h->ph, rk, e0, e1);
+    using C = KCfg<n>;
+    const int tiles = (e1 - e0 + C::EPB - 1) / C::EPB;
+    const bool ns = h->ph.ns != 0;
+    const bool tma = C::TMA_OK && h->useTma;
+    if (h->physics.inviscid == H3D_SPLIT_DG) {
+        // the staged-input variant of SplitDG + Navier-Stokes does not fit 227 KB: plain loads there
+        if (tma && !ns) k_volume<n, true, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, true, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(true, false))), C::NT, smemVolume<n, C::TMA_OK>(true, false), s>>>(h->m, h->ph, rk, e0, e1);
+        else k_volume<n, true, false><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, e0, e1);
+    } else {
+        if (tma) k_volume<n, false, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, false, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(false, ns))), C::NT, smemVolume<n, C::TMA_OK>(false, ns), s>>>(h->m, h->ph, rk, e0, e1);
+        else k_volume<n, false, false><<<tiles, C::NT, smemVolume<n, false>(false, true), s>>>(h->m, h->ph, rk, e0, e1);
+    }
     ++h->launches; return 0;
 }
+constexpr size_t SMEM_LIMIT = 227 * 1024;
 template <int n> int setAttrs(h3d_context* h) {
-    CTX_CHECK(cudaFuncSetAttribute(k_prolong_q<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemProlong(n)));
-    CTX_CHECK(cudaFuncSetAttribute(k_gradient<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient(n)));
-    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume(n, false, true)));
-    // SplitDG: the Navier-Stokes variant needs 29 n^3 doubles and does not fit 227 KB at n = 10; the Euler variant (19 n^3) does
-    const size_t splitBytes = std::min<size_t>(smemVolume(n, true, true), 227 * 1024);
-    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)splitBytes));
+    using C = KCfg<n>;
+    CTX_CHECK(cudaFuncSetAttribute(k_prolong_q<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemProlong<n>()));
+    CTX_CHECK(cudaFuncSetAttribute(k_gradient<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient<n, false>()));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, false>(false, true)));
+    // SplitDG: the Navier-Stokes variant (29 padded fields) does not fit 227 KB at n = 10; the Euler variant (14 fields) does
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smemVolume<n, false>(true, true), SMEM_LIMIT)));
+    if (C::TMA_OK) {
+        CTX_CHECK(cudaFuncSetAttribute(k_gradient<n, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient<n, C::TMA_OK>()));
+        CTX_CHECK(cudaFuncSetAttribute(k_volume<n, false, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, C::TMA_OK>(false, true)));
+        CTX_CHECK(cudaFuncSetAttribute(k_volume<n, true, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, C::TMA_OK>(true, false)));
+    }
     return 0;
 }
+template <int n> size_t splitBytes(bool ns) { return smemVolume<n, false>(true, ns); }
 
 #define DISPATCH_N(h, CALL)                                     \
     switch ((h)->n) {                                           \
@@ -327,6 +357,14 @@ int doAttrs(h3d_context* h) {
 #define C_(NN) setAttrs<NN>(h)
     DISPATCH_N(h, C_)
 #undef C_
+}
+size_t splitSmemBytes(h3d_context* h) {
+    const bool ns = h->ph.ns != 0;
+    switch (h->n) {
+        case 2: return splitBytes<2>(ns); case 3: return splitBytes<3>(ns); case 4: return splitBytes<4>(ns); case 5: return splitBytes<5>(ns);
+        case 6: return splitBytes<6>(ns); case 7: return splitBytes<7>(ns); case 8: return splitBytes<8>(ns); case 9: return splitBytes<9>(ns);
+        default: return splitBytes<10>(ns);
+    }
 }
 
 // halo exchange of NV variables (5: Q traces, 15: gradient traces) on the comm stream
@@ -433,6 +471,8 @@ int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nc
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     if (prop.major != 10) return fail(std::string("libh3dgpu is built for sm_100a only; device is ") + prop.name);
+    h->numSMs = prop.multiProcessorCount;
+    if (const char* ev = std::getenv("H3D_USE_TMA")) h->useTma = std::atoi(ev);   // experiments: H3D_USE_TMA=0 selects the plain-load kernels
     if (cudaStreamCreateWithFlags(&h->sCompute, cudaStreamNonBlocking) != cudaSuccess) return fail("stream creation failed");
     cudaStreamCreateWithFlags(&h->sComm, cudaStreamNonBlocking);
     for (cudaEvent_t* ev : {&h->evA, &h->evB, &h->evFaces, &h->evGrad, &h->evSent}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -703,7 +743,7 @@ static int checkReady(h3d_handle h) {
     if (!h->havePhysics || !h->haveBasis || !h->haveMesh) { h->err = "physics, basis and mesh must be set before the residual is evaluated"; return 1; }
     if (h->nFace - h->nFaceLocal > 0 && h->nNbr == 0) { h->err = "mesh has MPI faces but h3d_set_halo was not called"; return 1; }
     if (h->physics.inviscid == H3D_SPLIT_DG && h->nodeType != H3D_GAUSSLOBATTO) { h->err = "split-form discretization needs Gauss-Lobatto nodes"; return 1; }
-    if (h->physics.inviscid == H3D_SPLIT_DG && smemVolume(h->n, true, h->ph.ns != 0) > 227 * 1024) { h->err = "split-form Navier-Stokes at this polynomial order exceeds the 227 KB shared memory of one CTA"; return 1; }
+    if (h->physics.inviscid == H3D_SPLIT_DG && splitSmemBytes(h) > SMEM_LIMIT) { h->err = "split-form Navier-Stokes at this polynomial order exceeds the 227 KB shared memory of one CTA"; return 1; }
     return 0;
 }
 
@@ -828,6 +868,7 @@ int h3d_set_option(h3d_handle h, const char* kv) {
     const std::string key = s.substr(0, eq); const int val = std::atoi(s.substr(eq + 1).c_str());
     if (key == "store_qdot_every_stage") { h->storeQDotAlways = val; return 0; }
     if (key == "profile_kernels") { h->profile = val; return 0; }
+    if (key == "use_tma") { h->useTma = val; return 0; }
     h->err = "unknown option: " + key;
     return 1;
 }

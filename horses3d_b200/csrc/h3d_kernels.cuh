@@ -12,10 +12,15 @@
 //                                   (r = 0 for the left side, the face rotation for the right side)
 // Kernels per RK stage: gradient (element) -> riemann (face) -> volume+lift+RK (+ fused prolongation of the
 // updated state for the next stage).
+//
+// Element kernels: one element per group of TPE threads, NPT nodes per thread (2 at n >= 7 so that two CTAs
+// fit the register file of an SM and their load / contraction / store phases overlap), shared-memory fields
+// padded to an odd row length (conflict-free strided trace reads).  Every sum keeps the reference's order.
 #pragma once
 #include <cuda_runtime.h>
 
 #include "h3d_physics.cuh"
+#include "h3d_tma.cuh"
 
 namespace h3d {
 
@@ -34,10 +39,10 @@ struct DevMesh {
     const double *fN, *fT1, *fT2;          // [3][nFace][n2]
     const double* fJ;                      // [nFace][n2]
     const double* fDelta;                  // [nFace] sqrt(surface/n^2)
-    const int* faceInfo;                   // [nFace] bits0-1 type | bits 8.. zone+1 | bit 2: local side for MPI faces
+    const int* faceInfo;                   // [nFace] bits0-1 type | bits 8.. zone+1
     const int* rotmap;                     // [8][n2]
-    // operators (row-major M(i,l)) and their transposes
-    const double *hatDT, *DT, *sharpDT;    // transposed: MT[l*n + i] = M(i,l)
+    // operators, transposed: MT[l*n + i] = M(i,l)
+    const double *hatDT, *DT, *sharpDT;
     const double *v, *b, *w;               // v,b: [2][n]
     // boundary conditions
     const int* bcType; const double* bcParams;
@@ -50,69 +55,106 @@ struct RkArgs {
     double a, cdt;
 };
 
-__host__ __device__ constexpr int epbFor(int n) { return (n * n * n >= 192) ? 1 : 256 / (n * n * n); }
+#ifndef H3D_NPT_THRESHOLD
+#define H3D_NPT_THRESHOLD 100000   // nodes per element from which a thread takes two nodes (disabled: the 128-register cap spills, profiles/r1_c)
+#endif
 
-#define H3D_EIDX(c, e, node) (((size_t)(c) * m.nElem + (e)) * N3 + (node))
-#define H3D_FIDX(c, f, mm) (((size_t)(c) * m.nFace + (f)) * N2 + (mm))
+template <int n>
+struct KCfg {
+    static constexpr int N2 = n * n, N3 = n * n * n;
+    static constexpr int NP = (n % 2 == 0) ? n + 1 : n;       // padded row length (odd)
+    static constexpr int NS = N2 * NP;                        // padded nodes per shared-memory field
+    static constexpr int NPT = (N3 >= H3D_NPT_THRESHOLD) ? 2 : 1;   // nodes per thread
+    static constexpr int TPE = (N3 + NPT - 1) / NPT;          // threads per element
+    static constexpr int EPB = (TPE >= 128) ? 1 : 256 / TPE;  // elements per CTA
+    static constexpr int NT = TPE * EPB;                      // threads per CTA
+    static constexpr int MINB = (NT <= 256) ? 2 : 1;          // CTAs per SM the register allocation must allow
+    // Persistent variant with bulk-async (TMA) prefetch of the next tile's fields: needs 16-byte aligned, 16-byte
+    // multiple runs per field (EPB*N3 even) and the staged fields to fit beside the work buffers (n <= 8).
+    static constexpr bool TMA_OK = (n % 2 == 0) && (n <= 8) && (NPT == 1);
+    __host__ __device__ static constexpr int pidx(int node) { return (node / n) * NP + node % n; }
+};
 
 // local face helpers: faces 0..5 = FRONT(eta-),BACK(eta+),BOTTOM(zeta-),RIGHT(xi+),TOP(zeta+),LEFT(xi-)
 __device__ __forceinline__ int faceAxis(int lf) { return (lf < 2) ? 1 : ((lf == 2 || lf == 4) ? 2 : 0); }
 __device__ __forceinline__ int faceEnd(int lf) { return (lf == 1 || lf == 3 || lf == 4) ? 1 : 0; }
-// volume node index of trace node (a,b) on local face lf at normal position l
-template <int n>
-__device__ __forceinline__ int traceNode(int lf, int a, int b, int l) {
-    const int ax = faceAxis(lf);
-    if (ax == 0) return (b * n + a) * n + l;          // (eta,zeta) face: i = l, j = a, k = b
-    if (ax == 1) return (b * n + l) * n + a;          // (xi,zeta) face: i = a, j = l, k = b
-    return (l * n + b) * n + a;                       // (xi,eta) face: i = a, j = b, k = l
-}
 
 // ---------------------------------------------------------------------------------------------------------
-// Prolongation of NV element fields held in shared memory (sF[le][v][node]) to the faces.
+// Prolongation of NV element fields held in shared memory (sF[le][v][padded node]) to the faces.
 // HexElement_ProlongSolutionToFaces / ...GradientsToFaces (HexElementClass.f90:233-372): trace = sum_l A(l) v(l,end),
 // accumulated in ascending l from zero; Face_AdaptSolutionToFace: left copies, right is re-indexed.
+// sFace[le][6], sInfo[le][6]: face id / info of the CTA's elements.
 // ---------------------------------------------------------------------------------------------------------
 template <int n, int NV>
-__device__ __forceinline__ void prolong_block(const DevMesh& m, const double* sF, const double* sV, double* dst, int e0, int eEnd) {
-    constexpr int N2 = n * n, N3 = n * n * n, EPB = epbFor(n);
-    const int total = EPB * 6 * NV * N2;
+__device__ __forceinline__ void prolong_block(const DevMesh& m, const double* __restrict__ sF, const double* __restrict__ sV,
+                                              const int* __restrict__ sFace, const int* __restrict__ sInfo, double* __restrict__ dst, int nLocal) {
+    // One work item = (element, axis, field, trace node): the line of n values along the axis is read once from shared
+    // memory and contracted with both end vectors, giving the traces on the two opposite faces of that axis.
+    using C = KCfg<n>;
+    constexpr int N2 = C::N2, NP = C::NP, NS = C::NS;
+    const size_t fstride = (size_t)m.nFace * N2;
+    double v0[n], v1[n];
+#pragma unroll
+    for (int l = 0; l < n; ++l) { v0[l] = sV[l]; v1[l] = sV[n + l]; }
+    const int total = nLocal * 3 * NV * N2;
     for (int o = threadIdx.x; o < total; o += blockDim.x) {
         const int ab = o % N2; int r = o / N2;
         const int vv = r % NV; r /= NV;
-        const int lf = r % 6; const int le = r / 6;
-        const int e = e0 + le;
-        if (e >= eEnd) continue;
+        const int ax = r % 3; const int le = r / 3;
         const int a = ab % n, b = ab / n;
-        const double* src = sF + ((size_t)le * NV + vv) * N3;
-        const double* vv_ = sV + faceEnd(lf) * n;
-        double acc = 0.0;
+        const int base = ax == 0 ? (b * n + a) * NP : (ax == 1 ? (b * n) * NP + a : b * NP + a);
+        const int stride = ax == 0 ? 1 : (ax == 1 ? NP : n * NP);
+        const double* src = sF + ((size_t)le * NV + vv) * NS + base;
+        double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-        for (int l = 0; l < n; ++l) acc = acc + src[traceNode<n>(lf, a, b, l)] * vv_[l];
-        const int f = m.elemFace[e * 6 + lf];
-        const int info = m.elemInfo[e * 6 + lf];
-        const int side = info & 1, ridx = (info >> 1) & 7;
-        const int mm = m.rotmap[ridx * N2 + ab];
+        for (int l = 0; l < n; ++l) { const double sv = src[l * stride]; acc0 = acc0 + sv * v0[l]; acc1 = acc1 + sv * v1[l]; }
+        const int lf0 = ax == 0 ? 5 : (ax == 1 ? 0 : 2), lf1 = ax == 0 ? 3 : (ax == 1 ? 1 : 4);   // (LEFT,RIGHT) (FRONT,BACK) (BOTTOM,TOP)
         const int grp = vv / 5, eq = vv % 5;
-        dst[H3D_FIDX((grp * 2 + side) * 5 + eq, f, mm)] = acc;
+        {
+            const int f = sFace[le * 6 + lf0], info = sInfo[le * 6 + lf0];
+            dst[(size_t)((grp * 2 + (info & 1)) * 5 + eq) * fstride + (size_t)f * N2 + m.rotmap[((info >> 1) & 7) * N2 + ab]] = acc0;
+        }
+        {
+            const int f = sFace[le * 6 + lf1], info = sInfo[le * 6 + lf1];
+            dst[(size_t)((grp * 2 + (info & 1)) * 5 + eq) * fstride + (size_t)f * N2 + m.rotmap[((info >> 1) & 7) * N2 + ab]] = acc1;
+        }
     }
+}
+
+template <int n>
+__device__ __forceinline__ void load_face_tables(const DevMesh& m, int* sFace, int* sInfo, int e0, int nLocal) {
+    for (int t = threadIdx.x; t < nLocal * 6; t += blockDim.x) { sFace[t] = m.elemFace[(size_t)e0 * 6 + t]; sInfo[t] = m.elemInfo[(size_t)e0 * 6 + t]; }
 }
 
 // Stand-alone prolongation of Q (first residual after an upload).
 template <int n>
-__global__ void __launch_bounds__(epbFor(n) * n * n * n) k_prolong_q(DevMesh m, int eBegin, int eEnd) {
-    constexpr int N3 = n * n * n, EPB = epbFor(n);
+__global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, int eBegin, int eEnd) {
+    using C = KCfg<n>;
+    constexpr int N3 = C::N3, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE;
     extern __shared__ double smem[];
-    double* sQ = smem;                  // [EPB][5][N3]
-    double* sV = sQ + EPB * 5 * N3;     // [2][n]
-    const int le = threadIdx.x / N3, node = threadIdx.x % N3;
+    double* sQ = smem;                  // [EPB][5][NS]
+    double* sV = sQ + EPB * 5 * NS;     // [2][n]
+    int* sFace = (int*)(sV + 2 * n);    // [EPB][6]
+    int* sInfo = sFace + EPB * 6;
+    const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const int e0 = eBegin + blockIdx.x * EPB, e = e0 + le;
+    const int nLocal = min(EPB, eEnd - e0);
     if (threadIdx.x < 2 * n) sV[threadIdx.x] = m.v[threadIdx.x];
+    load_face_tables<n>(m, sFace, sInfo, e0, nLocal);
+    const size_t es = (size_t)m.nElem * N3;
     if (e < eEnd) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) sQ[(le * 5 + q) * N3 + node] = m.Q[H3D_EIDX(q, e, node)];
+        for (int r = 0; r < NPT; ++r) {
+            const int node = tn + r * TPE;
+            if (node < N3) {
+                const double* q = m.Q + (size_t)e * N3 + node;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) sQ[(le * 5 + c) * NS + C::pidx(node)] = q[c * es];
+            }
+        }
     }
     __syncthreads();
-    prolong_block<n, 5>(m, sQ, sV, m.fQ, e0, eEnd);
+    prolong_block<n, 5>(m, sQ, sV, sFace, sInfo, m.fQ, nLocal);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -122,124 +164,250 @@ __global__ void __launch_bounds__(epbFor(n) * n * n * n) k_prolong_q(DevMesh m, 
 //   per element side from the two prolonged states: u* n J_f = 1/2 (U_R - U_L) J_f n (same value for both sides)
 //   BR1_GradientFaceLoop -> VectorWeakIntegrals_StdFace (EllipticBR1.f90:531-569, DGIntegrals.f90:365-443)
 //   HexElement_ProlongGradientsToFaces (HexElementClass.f90:304-372)
+// Shared memory: phase 1 {U [5][NS], uStar [6][5][N2], normal+J_f [6][4][N2]}; phase 2 reuses all of it for the
+// 15 gradient fields that are prolonged to the faces.
 // ---------------------------------------------------------------------------------------------------------
+template <int n, bool TMA>
+struct GradSmem {
+    using C = KCfg<n>;
+    // non-TMA: phase 1 {U [5][NS], interface [6][9][N2]} aliased by phase 2 {grad [15][NS]}
+    // TMA    : staged inputs {Q 5, Ja 9, 1/J 1} [15][EPB*N3] + interface [6][9][N2] + grad [15][NS] (no aliasing)
+    static constexpr int phase1 = C::EPB * (5 * C::NS + 6 * 9 * C::N2);
+    static constexpr int phase2 = C::EPB * 15 * C::NS;
+    static constexpr int fields = TMA ? C::EPB * (15 * C::N3 + 6 * 9 * C::N2 + 15 * C::NS) : (phase1 > phase2 ? phase1 : phase2);
+    static constexpr size_t bytes = sizeof(double) * (fields + C::N2 + 4 * n) + sizeof(int) * 12 * C::EPB + 16;
+};
+
+// interface data of one element-trace node: raw loads (issued early) and their reduction to uStar / normal / J_f
+struct GradIface { double QL[5], QR[5], nh[3], Jf; int info; };
+
 template <int n>
-__global__ void __launch_bounds__(epbFor(n) * n * n * n) k_gradient(DevMesh m, Phys ph, int eBegin, int eEnd) {
-    constexpr int N2 = n * n, N3 = n * n * n, EPB = epbFor(n);
-    extern __shared__ double smem[];
-    double* sA = smem;                       // phase 1: U [EPB][5][N3]; phase 3: grad [EPB][15][N3]
-    double* sH = sA + EPB * 15 * N3;         // [EPB][6][5][N2]  uStar*Jf at element-trace nodes
-    double* sNrm = sH + EPB * 6 * 5 * N2;    // [EPB][6][4][N2]  face normal (3) and J_f at element-trace nodes
-    double* sDT = sNrm + EPB * 6 * 4 * N2;   // [n][n] DT[l*n+i] = D(i,l)
-    double* sB = sDT + N2;                   // [2][n]
-    double* sV = sB + 2 * n;                 // [2][n]
-    const int le = threadIdx.x / N3, node = threadIdx.x % N3;
-    const int e0 = eBegin + blockIdx.x * EPB, e = e0 + le;
-    const bool active = e < eEnd;
-    const int i = node % n, j = (node / n) % n, k = node / N2;
+__device__ __forceinline__ void grad_iface_load(const DevMesh& m, int e, int lf, int ab, GradIface& g) {
+    constexpr int N2 = n * n;
+    const size_t fs = (size_t)m.nFace * N2;
+    const int f = m.elemFace[(size_t)e * 6 + lf];
+    g.info = m.elemInfo[(size_t)e * 6 + lf];
+    const int ridx = (g.info >> 1) & 7;
+    const size_t fo = (size_t)f * N2 + m.rotmap[ridx * N2 + ab];
+    g.Jf = m.fJ[fo];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) g.nh[d] = m.fN[d * fs + fo];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { g.QL[q] = m.fQ[(size_t)q * fs + fo]; g.QR[q] = m.fQ[(size_t)(5 + q) * fs + fo]; }
+}
+template <int n>
+__device__ __forceinline__ void grad_iface_store(const DevMesh& m, const Phys& ph, const GradIface& g, double* hh, double* nrm) {
+    constexpr int N2 = n * n;
+    const int side = g.info & 1, ftype = (g.info >> 4) & 3, zone = (g.info >> 8) - 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) nrm[d * N2] = g.nh[d];
+    nrm[3 * N2] = g.Jf;
+    if (ftype == H3D_FACE_BOUNDARY) {
+        // BR1_ComputeBoundaryFlux: unStar = (u* - u_int) n_d J_f ; (u* - u_int) staged, n_d and J_f applied in the lift
+        double Qi[5], us[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) Qi[q] = side ? g.QR[q] : g.QL[q];
+        bc_grad_vars(ph, m.bcType[zone], m.bcParams + 16 * zone, g.nh, Qi, us);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) hh[q * N2] = (us[q] - Qi[q]);
+    } else {
+        // BR1_ComputeElementInterfaceAverage: uStar = 1/2 (U_R - U_L) J_f ; n_d applied in the lift
+#pragma unroll
+        for (int q = 0; q < 5; ++q) hh[q * N2] = 0.5 * (g.QR[q] - g.QL[q]) * g.Jf;
+    }
+}
+
+template <int n, bool TMA>
+__global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh m, Phys ph, int eBegin, int eEnd) {
+    using C = KCfg<n>;
+    constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
+    constexpr int TN3 = EPB * N3;                  // nodes of one tile
+    constexpr int UW = TMA ? N3 : NS;              // per-field stride of the state in shared memory
+    constexpr int ULD = TMA ? n : NP;              // row length of the state in shared memory
+    constexpr int IFI = (EPB * 6 * N2 + NT - 1) / NT;   // interface items per thread
+    extern __shared__ __align__(16) double smem[];
+    double* sIn = smem;                                         // TMA: [15][TN3] = Q 5, Ja 9, 1/J
+    double* sU = TMA ? sIn : smem;                              // state: TMA [5][EPB][N3] (field-major), else [EPB][5][NS]
+    double* sH = smem + (TMA ? 15 * TN3 : EPB * 5 * NS);        // [EPB][6][5][N2]
+    double* sNrm = sH + EPB * 6 * 5 * N2;                       // [EPB][6][4][N2]
+    double* sG = TMA ? sNrm + EPB * 6 * 4 * N2 : smem;          // [EPB][15][NS]
+    double* sDT = smem + GradSmem<n, TMA>::fields;              // [n][n]
+    double* sB = sDT + N2;
+    double* sV = sB + 2 * n;
+    int* sFace = (int*)(sV + 2 * n);
+    int* sInfo = sFace + EPB * 6;
+    uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 6) + 7) & ~(uintptr_t)7);
+    const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
+    const size_t es = (size_t)m.nElem * N3;
+    const int nTiles = (eEnd - eBegin + EPB - 1) / EPB;
     for (int t = threadIdx.x; t < N2; t += blockDim.x) sDT[t] = m.DT[t];
     if (threadIdx.x < 2 * n) { sB[threadIdx.x] = m.b[threadIdx.x]; sV[threadIdx.x] = m.v[threadIdx.x]; }
-    double U[5];
-    if (active) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q) { U[q] = m.Q[H3D_EIDX(q, e, node)]; sA[(le * 5 + q) * N3 + node] = U[q]; }
+    auto issue = [&](int tile) {   // thread 0: bulk copies of the tile's 15 fields
+        const int e0 = eBegin + tile * EPB;
+        const int nLoc = min(EPB, eEnd - e0);
+        const uint32_t bytes = (uint32_t)(nLoc * N3 * sizeof(double));
+        mbar_arrive_expect_tx(bar, 15 * bytes);
+#pragma unroll 1
+        for (int c = 0; c < 5; ++c) bulk_g2s(sIn + c * TN3, m.Q + c * es + (size_t)e0 * N3, bytes, bar);
+#pragma unroll 1
+        for (int c = 0; c < 9; ++c) bulk_g2s(sIn + (5 + c) * TN3, m.Ja + c * es + (size_t)e0 * N3, bytes, bar);
+        bulk_g2s(sIn + 14 * TN3, m.invJ + (size_t)e0 * N3, bytes, bar);
+    };
+    if (TMA) {
+        if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+        __syncthreads();
+        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) issue(blockIdx.x);
     }
-    // interface data of the six faces at element-trace nodes
-    for (int o = threadIdx.x; o < EPB * 6 * N2; o += blockDim.x) {
-        const int ab = o % N2; const int lf = (o / N2) % 6; const int l2 = o / (6 * N2);
-        const int ee = e0 + l2;
-        if (ee >= eEnd) continue;
-        const int f = m.elemFace[ee * 6 + lf];
-        const int info = m.elemInfo[ee * 6 + lf];
-        const int side = info & 1, ridx = (info >> 1) & 7, ftype = (info >> 4) & 3, zone = (info >> 8) - 1;
-        const int mm = m.rotmap[ridx * N2 + ab];
-        const double Jf = m.fJ[(size_t)f * N2 + mm];
-        double nh[3];
+    uint32_t parity = 0;
+    GradIface gi[IFI];
+    bool havePrefetch = false;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int e0 = eBegin + tile * EPB, e = e0 + le;
+        const int nLocal = min(EPB, eEnd - e0);
+        const bool active = e < eEnd;
+        for (int t = threadIdx.x; t < nLocal * 6; t += blockDim.x) { sFace[t] = m.elemFace[(size_t)e0 * 6 + t]; sInfo[t] = m.elemInfo[(size_t)e0 * 6 + t]; }
+        // interface data of the six faces at element-trace nodes (prefetched during the previous tile when possible)
+        if (!havePrefetch) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { nh[d] = m.fN[H3D_FIDX(d, f, mm)]; sNrm[((l2 * 6 + lf) * 4 + d) * N2 + ab] = nh[d]; }
-        sNrm[((l2 * 6 + lf) * 4 + 3) * N2 + ab] = Jf;
-        if (ftype == H3D_FACE_BOUNDARY) {
-            // BR1_ComputeBoundaryFlux: unStar = (u* - u_int) n_d J_f ; (u* - u_int) staged, n_d and J_f applied in the lift
-            double Qi[5], us[5];
+            for (int it = 0; it < IFI; ++it) {
+                const int o = threadIdx.x + it * NT;
+                if (o < nLocal * 6 * N2) grad_iface_load<n>(m, e0 + o / (6 * N2), (o / N2) % 6, o % N2, gi[it]);
+            }
+        }
 #pragma unroll
-            for (int q = 0; q < 5; ++q) Qi[q] = m.fQ[H3D_FIDX(side * 5 + q, f, mm)];
-            bc_grad_vars(ph, m.bcType[zone], m.bcParams + 16 * zone, nh, Qi, us);
+        for (int it = 0; it < IFI; ++it) {
+            const int o = threadIdx.x + it * NT;
+            if (o < nLocal * 6 * N2) {
+                const int ab = o % N2, lf = (o / N2) % 6, l2 = o / (6 * N2);
+                grad_iface_store<n>(m, ph, gi[it], sH + ((l2 * 6 + lf) * 5) * N2 + ab, sNrm + ((l2 * 6 + lf) * 4) * N2 + ab);
+            }
+        }
+        if (!TMA) {
+            if (active) {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) sH[((l2 * 6 + lf) * 5 + q) * N2 + ab] = (us[q] - Qi[q]);
+                for (int r = 0; r < NPT; ++r) {
+                    const int node = tn + r * TPE;
+                    if (node < N3) {
+                        const double* q = m.Q + (size_t)e * N3 + node;
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) sU[(le * 5 + c) * NS + C::pidx(node)] = q[c * es];
+                    }
+                }
+            }
         } else {
-            // BR1_ComputeElementInterfaceAverage: uStar = 1/2 (U_R - U_L) J_f ; n_d applied in the lift
+            mbar_wait(bar, parity); parity ^= 1;
+        }
+        __syncthreads();
+        double g[NPT][15];
+        if (active) {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const double UL = m.fQ[H3D_FIDX(0 * 5 + q, f, mm)], UR = m.fQ[H3D_FIDX(1 * 5 + q, f, mm)];
-                sH[((l2 * 6 + lf) * 5 + q) * N2 + ab] = 0.5 * (UR - UL) * Jf;
+            for (int r = 0; r < NPT; ++r) {
+                const int node = tn + r * TPE;
+                if (node < N3) {
+                    const int i = node % n, j = (node / n) % n, k = node / N2;
+                    double Uxi[5] = {0, 0, 0, 0, 0}, Ueta[5] = {0, 0, 0, 0, 0}, Uzeta[5] = {0, 0, 0, 0, 0};
+                    // state field q of this element: TMA [q][le][node], else [le][q][padded node]
+                    const double* sUe = TMA ? sU + le * N3 : sU + le * 5 * NS;
+                    constexpr int QS = TMA ? TN3 : NS;
+                    const int bx = (k * n + j) * ULD, by = (k * n) * ULD + i, bz = j * ULD + i;
+#pragma unroll
+                    for (int l = 0; l < n; ++l) {
+                        const double dx = sDT[l * n + i], dy = sDT[l * n + j], dz = sDT[l * n + k];
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            Uxi[q] = Uxi[q] + sUe[q * QS + bx + l] * dx;
+                            Ueta[q] = Ueta[q] + sUe[q * QS + by + l * ULD] * dy;
+                            Uzeta[q] = Uzeta[q] + sUe[q * QS + bz + l * n * ULD] * dz;
+                        }
+                    }
+                    double ja[9], iJ;
+                    if (TMA) {
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) ja[c] = sIn[(5 + c) * TN3 + le * N3 + node];
+                        iJ = sIn[14 * TN3 + le * N3 + node];
+                    } else {
+                        const double* jap = m.Ja + (size_t)e * N3 + node;
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) ja[c] = jap[c * es];
+                        iJ = m.invJ[(size_t)e * N3 + node];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        g[r][q] = (Uxi[q] * ja[0] + Ueta[q] * ja[3] + Uzeta[q] * ja[6]) * iJ;
+                        g[r][5 + q] = (Uxi[q] * ja[1] + Ueta[q] * ja[4] + Uzeta[q] * ja[7]) * iJ;
+                        g[r][10 + q] = (Uxi[q] * ja[2] + Ueta[q] * ja[5] + Uzeta[q] * ja[8]) * iJ;
+                    }
+                    // lift: faceInt_d = sum over faces in the order L,R,FRONT,BACK,BOTTOM,TOP of unStar_d * b
+                    const int lfOrder[6] = {5, 3, 0, 1, 2, 4};
+                    const int abOf[6] = {k * n + i, k * n + i, j * n + i, k * n + j, j * n + i, k * n + j};
+                    const int idxOf[6] = {j, j, k, i, k, i};
+                    double fx[5], fy[5], fz[5];
+#pragma unroll
+                    for (int s = 0; s < 6; ++s) {
+                        const int lf = lfOrder[s];
+                        const int ab = abOf[lf];
+                        const double bb = sB[faceEnd(lf) * n + idxOf[lf]];
+                        const double* H = sH + ((le * 6 + lf) * 5) * N2 + ab;
+                        const double* Nn = sNrm + ((le * 6 + lf) * 4) * N2 + ab;
+                        const bool bnd = ((sInfo[le * 6 + lf] >> 4) & 3) == H3D_FACE_BOUNDARY;
+                        const double Jfb = Nn[3 * N2];
+                        const double n0 = Nn[0], n1 = Nn[N2], n2 = Nn[2 * N2];
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            const double h = H[q * N2];
+                            double ux, uy, uz;
+                            if (bnd) { ux = h * n0 * Jfb; uy = h * n1 * Jfb; uz = h * n2 * Jfb; }
+                            else { ux = h * n0; uy = h * n1; uz = h * n2; }
+                            if (s == 0) { fx[q] = ux * bb; fy[q] = uy * bb; fz[q] = uz * bb; }
+                            else { fx[q] = fx[q] + ux * bb; fy[q] = fy[q] + uy * bb; fz[q] = fz[q] + uz * bb; }
+                        }
+                    }
+                    double* ox = m.Ux + (size_t)e * N3 + node; double* oy = m.Uy + (size_t)e * N3 + node; double* oz = m.Uz + (size_t)e * N3 + node;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        g[r][q] = g[r][q] + fx[q] * iJ; g[r][5 + q] = g[r][5 + q] + fy[q] * iJ; g[r][10 + q] = g[r][10 + q] + fz[q] * iJ;
+                        ox[q * es] = g[r][q]; oy[q * es] = g[r][5 + q]; oz[q * es] = g[r][10 + q];
+                    }
+                    if (TMA) {   // the gradient buffer does not alias the inputs: store right away
+                        const int p = C::pidx(node);
+#pragma unroll
+                        for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                    }
+                }
             }
         }
-    }
-    __syncthreads();
-    double gx[5], gy[5], gz[5];
-    if (active) {
-        double Uxi[5] = {0, 0, 0, 0, 0}, Ueta[5] = {0, 0, 0, 0, 0}, Uzeta[5] = {0, 0, 0, 0, 0};
-        const double* sU = sA + le * 5 * N3;
+        __syncthreads();   // U and the interface data are consumed
+        const int next = tile + gridDim.x;
+        if (TMA) {
+            if (threadIdx.x == 0 && next < nTiles) issue(next);
+        } else {
+            if (active) {
 #pragma unroll
-        for (int l = 0; l < n; ++l) {
-            const double dx = sDT[l * n + i], dy = sDT[l * n + j], dz = sDT[l * n + k];
+                for (int r = 0; r < NPT; ++r) {
+                    const int node = tn + r * TPE;
+                    if (node < N3) {
+                        const int p = C::pidx(node);
 #pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                Uxi[q] = Uxi[q] + sU[q * N3 + (k * n + j) * n + l] * dx;
-                Ueta[q] = Ueta[q] + sU[q * N3 + (k * n + l) * n + i] * dy;
-                Uzeta[q] = Uzeta[q] + sU[q * N3 + (l * n + j) * n + i] * dz;
+                        for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                    }
+                }
             }
+            __syncthreads();
         }
-        double ja[9];
+        // start the gather of the next tile's interface data; it completes behind the prolongation below
+        havePrefetch = false;
+        if (next < nTiles) {
+            const int e0n = eBegin + next * EPB, nLocN = min(EPB, eEnd - e0n);
 #pragma unroll
-        for (int c = 0; c < 9; ++c) ja[c] = m.Ja[H3D_EIDX(c, e, node)];
-        const double iJ = m.invJ[(size_t)e * N3 + node];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            gx[q] = (Uxi[q] * ja[0] + Ueta[q] * ja[3] + Uzeta[q] * ja[6]) * iJ;
-            gy[q] = (Uxi[q] * ja[1] + Ueta[q] * ja[4] + Uzeta[q] * ja[7]) * iJ;
-            gz[q] = (Uxi[q] * ja[2] + Ueta[q] * ja[5] + Uzeta[q] * ja[8]) * iJ;
-        }
-        // lift: faceInt_d = sum over faces in the order L,R,FRONT,BACK,BOTTOM,TOP of unStar_d * b
-        const int lfOrder[6] = {5, 3, 0, 1, 2, 4};
-        const int abOf[6] = {k * n + i, k * n + i, j * n + i, k * n + j, j * n + i, k * n + j};
-        const int idxOf[6] = {j, j, k, i, k, i};
-        double fx[5], fy[5], fz[5];
-#pragma unroll
-        for (int s = 0; s < 6; ++s) {
-            const int lf = lfOrder[s];
-            const int ab = abOf[lf];
-            const double bb = sB[faceEnd(lf) * n + idxOf[lf]];
-            const double* H = sH + ((le * 6 + lf) * 5) * N2 + ab;
-            const double* Nn = sNrm + ((le * 6 + lf) * 4) * N2 + ab;
-            const bool bnd = ((m.elemInfo[e * 6 + lf] >> 4) & 3) == H3D_FACE_BOUNDARY;
-            const double Jfb = Nn[3 * N2];
-            const double n0 = Nn[0], n1 = Nn[N2], n2 = Nn[2 * N2];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const double h = H[q * N2];
-                double ux, uy, uz;
-                if (bnd) { ux = h * n0 * Jfb; uy = h * n1 * Jfb; uz = h * n2 * Jfb; }
-                else { ux = h * n0; uy = h * n1; uz = h * n2; }
-                if (s == 0) { fx[q] = ux * bb; fy[q] = uy * bb; fz[q] = uz * bb; }
-                else { fx[q] = fx[q] + ux * bb; fy[q] = fy[q] + uy * bb; fz[q] = fz[q] + uz * bb; }
+            for (int it = 0; it < IFI; ++it) {
+                const int o = threadIdx.x + it * NT;
+                if (o < nLocN * 6 * N2) grad_iface_load<n>(m, e0n + o / (6 * N2), (o / N2) % 6, o % N2, gi[it]);
             }
+            havePrefetch = true;
         }
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            gx[q] = gx[q] + fx[q] * iJ; gy[q] = gy[q] + fy[q] * iJ; gz[q] = gz[q] + fz[q] * iJ;
-            m.Ux[H3D_EIDX(q, e, node)] = gx[q]; m.Uy[H3D_EIDX(q, e, node)] = gy[q]; m.Uz[H3D_EIDX(q, e, node)] = gz[q];
-        }
+        prolong_block<n, 15>(m, sG, sV, sFace, sInfo, m.fU, nLocal);
+        __syncthreads();
     }
-    __syncthreads();   // everyone is done reading U from sA
-    if (active) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            sA[(le * 15 + q) * N3 + node] = gx[q]; sA[(le * 15 + 5 + q) * N3 + node] = gy[q]; sA[(le * 15 + 10 + q) * N3 + node] = gz[q];
-        }
-    }
-    __syncthreads();
-    prolong_block<n, 15>(m, sA, sV, m.fU, e0, eEnd);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -254,26 +422,28 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = fBegin + (int)(t / N2), mm = (int)(t % N2);
     if (f >= fEnd) return;
+    const size_t fs = (size_t)m.nFace * N2, fo = (size_t)f * N2 + mm;
     const int info = m.faceInfo[f];
     const int ftype = info & 3, zone = (info >> 8) - 1;
     double nh[3], t1[3], t2[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) { nh[d] = m.fN[H3D_FIDX(d, f, mm)]; t1[d] = 0.0; t2[d] = 0.0; }
+    for (int d = 0; d < 3; ++d) { nh[d] = m.fN[d * fs + fo]; t1[d] = 0.0; t2[d] = 0.0; }
     if (ph.riemann != H3D_RIEMANN_ROE) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { t1[d] = m.fT1[H3D_FIDX(d, f, mm)]; t2[d] = m.fT2[H3D_FIDX(d, f, mm)]; }
+        for (int d = 0; d < 3; ++d) { t1[d] = m.fT1[d * fs + fo]; t2[d] = m.fT2[d * fs + fo]; }
     }
-    const double Jf = m.fJ[(size_t)f * N2 + mm];
+    const double Jf = m.fJ[fo];
     double QL[5], QR[5], visc[5] = {0, 0, 0, 0, 0}, inv[5];
+    const double* fQ = m.fQ + fo; const double* fU = m.fU + fo;
     if (ftype == H3D_FACE_BOUNDARY) {
         const int btype = m.bcType[zone]; const double* P = m.bcParams + 16 * zone;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) { QL[q] = m.fQ[H3D_FIDX(q, f, mm)]; QR[q] = QL[q]; }
+        for (int q = 0; q < 5; ++q) { QL[q] = fQ[q * fs]; QR[q] = QL[q]; }
         bc_flow_state(ph, btype, P, nh, QR);
         if (ph.ns) {
             double gx[5], gy[5], gz[5], F[5][3], mu, kappa;
 #pragma unroll
-            for (int q = 0; q < 5; ++q) { gx[q] = m.fU[H3D_FIDX((0 * 2 + 0) * 5 + q, f, mm)]; gy[q] = m.fU[H3D_FIDX((1 * 2 + 0) * 5 + q, f, mm)]; gz[q] = m.fU[H3D_FIDX((2 * 2 + 0) * 5 + q, f, mm)]; }
+            for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + q) * fs]; }
             laminar_mu_kappa(ph, QL, mu, kappa);
             if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux(ph, QL, gx, gy, gz, mu, 0.0, kappa, F);
@@ -284,16 +454,16 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
         riemann_solver(ph, QL, QR, nh, t1, t2, inv);
     } else {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) { QL[q] = m.fQ[H3D_FIDX(q, f, mm)]; QR[q] = m.fQ[H3D_FIDX(5 + q, f, mm)]; }
+        for (int q = 0; q < 5; ++q) { QL[q] = fQ[q * fs]; QR[q] = fQ[(size_t)(5 + q) * fs]; }
         if (ph.ns) {
             double gx[5], gy[5], gz[5], FL[5][3], FR[5][3], mu, kappa;
 #pragma unroll
-            for (int q = 0; q < 5; ++q) { gx[q] = m.fU[H3D_FIDX((0 * 2 + 0) * 5 + q, f, mm)]; gy[q] = m.fU[H3D_FIDX((1 * 2 + 0) * 5 + q, f, mm)]; gz[q] = m.fU[H3D_FIDX((2 * 2 + 0) * 5 + q, f, mm)]; }
+            for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + q) * fs]; }
             laminar_mu_kappa(ph, QL, mu, kappa);
             if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux(ph, QL, gx, gy, gz, mu, 0.0, kappa, FL);
 #pragma unroll
-            for (int q = 0; q < 5; ++q) { gx[q] = m.fU[H3D_FIDX((0 * 2 + 1) * 5 + q, f, mm)]; gy[q] = m.fU[H3D_FIDX((1 * 2 + 1) * 5 + q, f, mm)]; gz[q] = m.fU[H3D_FIDX((2 * 2 + 1) * 5 + q, f, mm)]; }
+            for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + 5 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + 5 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + 5 + q) * fs]; }
             laminar_mu_kappa(ph, QR, mu, kappa);
             if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], QR, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux(ph, QR, gx, gy, gz, mu, 0.0, kappa, FR);
@@ -306,7 +476,7 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
         riemann_solver(ph, QL, QR, nh, t1, t2, inv);
     }
 #pragma unroll
-    for (int q = 0; q < 5; ++q) m.fStar[H3D_FIDX(q, f, mm)] = (inv[q] - visc[q]) * Jf;
+    for (int q = 0; q < 5; ++q) m.fStar[(size_t)q * fs + fo] = (inv[q] - visc[q]) * Jf;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -316,179 +486,288 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
 //   ScalarWeakIntegrals_StdVolumeGreen (DGIntegrals.f90:56-87); SplitDG: HyperbolicSplitForm.f90:64-116 + DGIntegrals.f90:92-129
 //   TimeDerivative_FacesContribution -> ScalarWeakIntegrals_StdFace (SpatialDiscretization.f90:1686-1701; DGIntegrals.f90:214-273)
 //   QDot /= jacobian (:489-491); QDot += S_NS (:632-638); TakeRK3Step element loop (ExplicitMethods.f90:766-771)
+// Shared memory: StandardDG: total contravariant flux [3][5][NS].  SplitDG: state [5][NS] + metrics [9][NS]
+// (+ viscous contravariant flux [3][5][NS] for Navier-Stokes).  Plus fStar at element-trace nodes [6][5][N2].
 // ---------------------------------------------------------------------------------------------------------
-template <int n, bool SPLIT>
-__global__ void __launch_bounds__(epbFor(n) * n * n * n) k_volume(DevMesh m, Phys ph, RkArgs rk, int eBegin, int eEnd) {
-    constexpr int N2 = n * n, N3 = n * n * n, EPB = epbFor(n);
-    extern __shared__ double smem[];
-    // StandardDG: sF = contravariant total flux [EPB][3][5][N3]
-    // SplitDG   : sF = viscous contravariant flux [EPB][3][5][N3]; sQ = state [EPB][5][N3]; sJa = metrics [EPB][9][N3]
-    double* sF = smem;                                // SplitDG + Euler: only 5 fields are needed here (prolongation buffer)
-    double* sQ = sF + EPB * ((SPLIT && !ph.ns) ? 5 : 15) * N3;
-    double* sJa = sQ + (SPLIT ? EPB * 5 * N3 : 0);
-    double* sFs = sJa + (SPLIT ? EPB * 9 * N3 : 0);   // [EPB][6][5][N2] fStar at element-trace nodes (signed)
-    double* sHatDT = sFs + EPB * 6 * 5 * N2;          // [n][n]
-    double* sSharpDT = sHatDT + N2;                   // [n][n]
-    double* sB = sSharpDT + N2;                       // [2][n]
-    double* sV = sB + 2 * n;                          // [2][n]
-    const int le = threadIdx.x / N3, node = threadIdx.x % N3;
-    const int e0 = eBegin + blockIdx.x * EPB, e = e0 + le;
-    const bool active = e < eEnd;
-    const int i = node % n, j = (node / n) % n, k = node / N2;
+template <int n, bool TMA>
+struct VolSmem {
+    using C = KCfg<n>;
+    __host__ __device__ static constexpr int fluxFields(bool split, bool ns) { return split ? (ns ? 15 : 0) : 15; }
+    __host__ __device__ static constexpr int stagedFields(bool ns) { return TMA ? (ns ? 29 : 14) : 0; }   // Q 5 [, Ux Uy Uz 15], Ja 9
+    __host__ __device__ static constexpr int fields(bool split, bool ns) {
+        return C::EPB * (stagedFields(ns) * C::N3 + (fluxFields(split, ns) + (split ? 14 : 0)) * C::NS + 30 * C::N2);
+    }
+    static size_t bytes(bool split, bool ns) { return sizeof(double) * (fields(split, ns) + 2 * C::N2 + 4 * n) + sizeof(int) * 12 * C::EPB + 16; }
+};
+
+template <int n, bool SPLIT, bool TMA>
+__global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m, Phys ph, RkArgs rk, int eBegin, int eEnd) {
+    using C = KCfg<n>;
+    constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
+    constexpr int TN3 = EPB * N3;
+    constexpr int FSI = (EPB * 30 * N2 + NT - 1) / NT;   // fStar items per thread
+    extern __shared__ __align__(16) double smem[];
+    const bool ns = ph.ns != 0;
+    const int nStaged = TMA ? (ns ? 29 : 14) : 0;
+    const int nFlux = SPLIT ? (ns ? 15 : 0) : 15;
+    double* sIn = smem;                                  // TMA: [nStaged][TN3]: Q 5, (Ux Uy Uz 15,) Ja 9
+    double* sF = smem + nStaged * TN3;                   // [EPB][nFlux][NS]
+    double* sQ = sF + EPB * nFlux * NS;                  // SPLIT: [EPB][5][NS]
+    double* sJa = sQ + (SPLIT ? EPB * 5 * NS : 0);       // SPLIT: [EPB][9][NS]
+    double* sFs = sJa + (SPLIT ? EPB * 9 * NS : 0);      // [EPB][6][5][N2] fStar at element-trace nodes (signed)
+    double* sHatDT = sFs + EPB * 6 * 5 * N2;             // [n][n]
+    double* sSharpDT = sHatDT + N2;                      // [n][n]
+    double* sB = sSharpDT + N2;                          // [2][n]
+    double* sV = sB + 2 * n;                             // [2][n]
+    int* sFace = (int*)(sV + 2 * n);                     // [EPB][6]
+    int* sInfo = sFace + EPB * 6;
+    uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 6) + 7) & ~(uintptr_t)7);
+    double* sP = SPLIT ? sQ : sF;                        // prolongation buffer for the updated state [EPB][5][NS]
+    const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
+    const size_t es = (size_t)m.nElem * N3, fs = (size_t)m.nFace * N2;
+    const int nTiles = (eEnd - eBegin + EPB - 1) / EPB;
+    const int jaOff = ns ? 20 : 5;                       // first metric field inside sIn
     for (int t = threadIdx.x; t < N2; t += blockDim.x) { sHatDT[t] = m.hatDT[t]; if (SPLIT) sSharpDT[t] = m.sharpDT[t]; }
     if (threadIdx.x < 2 * n) { sB[threadIdx.x] = m.b[threadIdx.x]; sV[threadIdx.x] = m.v[threadIdx.x]; }
-    // interface fluxes of the six faces at element-trace nodes (left: +, right: -, FaceClass.f90:681-690)
-    for (int o = threadIdx.x; o < EPB * 6 * 5 * N2; o += blockDim.x) {
-        const int ab = o % N2; int r = o / N2;
-        const int q = r % 5; r /= 5;
-        const int lf = r % 6; const int l2 = r / 6;
-        const int ee = e0 + l2;
-        if (ee >= eEnd) continue;
-        const int f = m.elemFace[ee * 6 + lf];
-        const int info = m.elemInfo[ee * 6 + lf];
-        const int side = info & 1, ridx = (info >> 1) & 7;
-        const double val = m.fStar[H3D_FIDX(q, f, m.rotmap[ridx * N2 + ab])];
-        sFs[((l2 * 6 + lf) * 5 + q) * N2 + ab] = side ? -val : val;
-    }
-    double Q[5], Finv[5][3];
-    double ja[9];
-    if (active) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q) Q[q] = m.Q[H3D_EIDX(q, e, node)];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) ja[c] = m.Ja[H3D_EIDX(c, e, node)];
-        double F[5][3];
-        euler_flux(ph, Q, F);
-#pragma unroll
-        for (int q = 0; q < 5; ++q)
-#pragma unroll
-            for (int d = 0; d < 3; ++d) Finv[q][d] = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
-        double Fv[5][3];
-        if (ph.ns) {
-            double gx[5], gy[5], gz[5], mu, kappa;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[H3D_EIDX(q, e, node)]; gy[q] = m.Uy[H3D_EIDX(q, e, node)]; gz[q] = m.Uz[H3D_EIDX(q, e, node)]; }
-            laminar_mu_kappa(ph, Q, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.lesDelta[e], Q, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
-            viscous_flux(ph, Q, gx, gy, gz, mu, 0.0, kappa, F);
-#pragma unroll
-            for (int q = 0; q < 5; ++q)
-#pragma unroll
-                for (int d = 0; d < 3; ++d) Fv[q][d] = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
-        } else {
-#pragma unroll
-            for (int q = 0; q < 5; ++q) { Fv[q][0] = 0.0; Fv[q][1] = 0.0; Fv[q][2] = 0.0; }
-        }
-        if (!SPLIT) {
-#pragma unroll
-            for (int q = 0; q < 5; ++q)
-#pragma unroll
-                for (int d = 0; d < 3; ++d) sF[((le * 3 + d) * 5 + q) * N3 + node] = Finv[q][d] - Fv[q][d];
-        } else {
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                sQ[(le * 5 + q) * N3 + node] = Q[q];
-                if (ph.ns) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) sF[((le * 3 + d) * 5 + q) * N3 + node] = Fv[q][d];
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * N3 + node] = ja[c];
-        }
-    }
-    __syncthreads();
-    double Qn[5];
-    if (active) {
-        double vol[5] = {0, 0, 0, 0, 0};
-        if (!SPLIT) {
-            const double* F1 = sF + ((le * 3 + 0) * 5) * N3; const double* F2 = sF + ((le * 3 + 1) * 5) * N3; const double* F3 = sF + ((le * 3 + 2) * 5) * N3;
-#pragma unroll
-            for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + i];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F1[q * N3 + (k * n + j) * n + l]; }
-#pragma unroll
-            for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + j];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F2[q * N3 + (k * n + l) * n + i]; }
-#pragma unroll
-            for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + k];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F3[q * N3 + (l * n + j) * n + i]; }
-        } else {
-            const double* sQe = sQ + le * 5 * N3; const double* sJe = sJa + le * 9 * N3; const double* sFe = sF + le * 15 * N3;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const int me = d == 0 ? i : (d == 1 ? j : k);
-                const double jaMe[3] = {ja[3 * d], ja[3 * d + 1], ja[3 * d + 2]};
-                for (int l = 0; l < n; ++l) {
-                    const int other = d == 0 ? (k * n + j) * n + l : (d == 1 ? (k * n + l) * n + i : (l * n + j) * n + i);
-                    double fs[5];
-                    if (l == me) {
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) fs[q] = Finv[q][d];
-                    } else {
-                        double Qo[5], jo[3];
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) Qo[q] = sQe[q * N3 + other];
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) jo[c] = sJe[(3 * d + c) * N3 + other];
-                        if (l > me) two_point_flux(ph, Q, Qo, jaMe, jo, fs); else two_point_flux(ph, Qo, Q, jo, jaMe, fs);
-                    }
-                    const double sd = sSharpDT[l * n + me], hd = sHatDT[l * n + me];
-                    if (ph.ns) {
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) vol[q] = vol[q] + sd * fs[q] + hd * sFe[(d * 5 + q) * N3 + other];
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) vol[q] = vol[q] + sd * fs[q];
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 5; ++q) vol[q] = -vol[q];
-        }
-        // surface integral in the reference's order L,R,FRONT,BACK,BOTTOM,TOP
-        const double* Fs = sFs + (le * 6) * 5 * N2;
-        const double bL = sB[i], bR = sB[n + i], bF = sB[j], bBk = sB[n + j], bBo = sB[k], bT = sB[n + k];
-        const double Jn = m.J[(size_t)e * N3 + node];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            double fi = Fs[(5 * 5 + q) * N2 + k * n + j] * bL;
-            fi = fi + Fs[(3 * 5 + q) * N2 + k * n + j] * bR;
-            fi = fi + Fs[(0 * 5 + q) * N2 + k * n + i] * bF;
-            fi = fi + Fs[(1 * 5 + q) * N2 + k * n + i] * bBk;
-            fi = fi + Fs[(2 * 5 + q) * N2 + j * n + i] * bBo;
-            fi = fi + Fs[(4 * 5 + q) * N2 + j * n + i] * bT;
-            double r = vol[q] - fi;
-            r = r / Jn;
-            if (m.S) r = r + m.S[H3D_EIDX(q, e, node)];
-            if (rk.mode == 0) {
-                m.QDot[H3D_EIDX(q, e, node)] = r;
-                Qn[q] = Q[q];
-            } else {
-                if (rk.storeQDot) m.QDot[H3D_EIDX(q, e, node)] = r;
-                const double g = rk.a * m.G[H3D_EIDX(q, e, node)] + r;
-                m.G[H3D_EIDX(q, e, node)] = g;
-                Qn[q] = Q[q] + rk.cdt * g;
-                m.Q[H3D_EIDX(q, e, node)] = Qn[q];
+    auto issue = [&](int tile) {   // thread 0: bulk copies of the tile's staged fields
+        const int e0 = eBegin + tile * EPB;
+        const int nLoc = min(EPB, eEnd - e0);
+        const uint32_t bytes = (uint32_t)(nLoc * N3 * sizeof(double));
+        const size_t off = (size_t)e0 * N3;
+        mbar_arrive_expect_tx(bar, (uint32_t)nStaged * bytes);
+#pragma unroll 1
+        for (int c = 0; c < 5; ++c) bulk_g2s(sIn + c * TN3, m.Q + c * es + off, bytes, bar);
+        if (ns) {
+#pragma unroll 1
+            for (int c = 0; c < 5; ++c) {
+                bulk_g2s(sIn + (5 + c) * TN3, m.Ux + c * es + off, bytes, bar);
+                bulk_g2s(sIn + (10 + c) * TN3, m.Uy + c * es + off, bytes, bar);
+                bulk_g2s(sIn + (15 + c) * TN3, m.Uz + c * es + off, bytes, bar);
             }
         }
-    }
-    if (rk.prolong) {
+#pragma unroll 1
+        for (int c = 0; c < 9; ++c) bulk_g2s(sIn + (jaOff + c) * TN3, m.Ja + c * es + off, bytes, bar);
+    };
+    if (TMA) {
+        if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
         __syncthreads();
+        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) issue(blockIdx.x);
+    }
+    uint32_t parity = 0;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int e0 = eBegin + tile * EPB, e = e0 + le;
+        const int nLocal = min(EPB, eEnd - e0);
+        const bool active = e < eEnd;
+        for (int t = threadIdx.x; t < nLocal * 6; t += blockDim.x) { sFace[t] = m.elemFace[(size_t)e0 * 6 + t]; sInfo[t] = m.elemInfo[(size_t)e0 * 6 + t]; }
+        // interface fluxes of the six faces at element-trace nodes (left: +, right: -, FaceClass.f90:681-690):
+        // loads issued now, stored to shared memory after the flux phase
+        double fsv[FSI];
+#pragma unroll
+        for (int it = 0; it < FSI; ++it) {
+            const int o = threadIdx.x + it * NT;
+            fsv[it] = 0.0;
+            if (o < nLocal * 30 * N2) {
+                const int ab = o % N2; int r = o / N2;
+                const int q = r % 5; r /= 5;
+                const int lf = r % 6; const int l2 = r / 6;
+                const int f = m.elemFace[(size_t)(e0 + l2) * 6 + lf];
+                const int info = m.elemInfo[(size_t)(e0 + l2) * 6 + lf];
+                const double val = m.fStar[(size_t)q * fs + (size_t)f * N2 + m.rotmap[((info >> 1) & 7) * N2 + ab]];
+                fsv[it] = (info & 1) ? -val : val;
+            }
+        }
+        if (TMA) { mbar_wait(bar, parity); parity ^= 1; }
+        double Qk[NPT][5];                   // state of the thread's nodes (kept for the update)
+        double FinvD[NPT][SPLIT ? 15 : 1];   // SplitDG: consistent (diagonal) inviscid contravariant fluxes
         if (active) {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) sF[(le * 5 + q) * N3 + node] = Qn[q];
+            for (int r = 0; r < NPT; ++r) {
+                const int node = tn + r * TPE;
+                if (node < N3) {
+                    const int p = C::pidx(node);
+                    const size_t go = (size_t)e * N3 + node;
+                    const int so = le * N3 + node;
+                    double ja[9];
+                    if (TMA) {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) Qk[r][q] = sIn[q * TN3 + so];
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) ja[c] = sIn[(jaOff + c) * TN3 + so];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) Qk[r][q] = m.Q[q * es + go];
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) ja[c] = m.Ja[c * es + go];
+                    }
+                    double F[5][3], Fc[5][3];
+                    euler_flux(ph, Qk[r], F);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) Fc[q][d] = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
+                    if (SPLIT) {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            sQ[(le * 5 + q) * NS + p] = Qk[r][q];
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) FinvD[r][d * 5 + q] = Fc[q][d];
+                        }
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * NS + p] = ja[c];
+                    }
+                    if (ns) {
+                        double gx[5], gy[5], gz[5], mu, kappa;
+                        if (TMA) {
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) { gx[q] = sIn[(5 + q) * TN3 + so]; gy[q] = sIn[(10 + q) * TN3 + so]; gz[q] = sIn[(15 + q) * TN3 + so]; }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[q * es + go]; gy[q] = m.Uy[q * es + go]; gz[q] = m.Uz[q * es + go]; }
+                        }
+                        laminar_mu_kappa(ph, Qk[r], mu, kappa);
+                        if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.lesDelta[e], Qk[r], gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+                        viscous_flux(ph, Qk[r], gx, gy, gz, mu, 0.0, kappa, F);
+#pragma unroll
+                        for (int q = 0; q < 5; ++q)
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                const double fv = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
+                                if (SPLIT) sF[((le * 3 + d) * 5 + q) * NS + p] = fv;
+                                else sF[((le * 3 + d) * 5 + q) * NS + p] = Fc[q][d] - fv;
+                            }
+                    } else if (!SPLIT) {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q)
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) sF[((le * 3 + d) * 5 + q) * NS + p] = Fc[q][d] - 0.0;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < FSI; ++it) {
+            const int o = threadIdx.x + it * NT;
+            if (o < nLocal * 30 * N2) sFs[o] = fsv[it];     // o = ((l2*6 + lf)*5 + q)*N2 + ab
         }
         __syncthreads();
-        prolong_block<n, 5>(m, sF, sV, m.fQ, e0, eEnd);
+        if (TMA && threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issue(tile + gridDim.x);   // the staged inputs are consumed
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < NPT; ++r) {
+                const int node = tn + r * TPE;
+                if (node < N3) {
+                    const int i = node % n, j = (node / n) % n, k = node / N2;
+                    const size_t go = (size_t)e * N3 + node;
+                    const int bx = (k * n + j) * NP, by = (k * n) * NP + i, bz = j * NP + i;
+                    // late inputs, requested before the contraction so that their latency hides behind it
+                    const double Jn = m.J[go];
+                    double Gk[5];
+                    if (rk.mode != 0) {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) Gk[q] = m.G[q * es + go];
+                    }
+                    double vol[5] = {0, 0, 0, 0, 0};
+                    if (!SPLIT) {
+                        const double* F1 = sF + ((le * 3 + 0) * 5) * NS + bx; const double* F2 = sF + ((le * 3 + 1) * 5) * NS + by; const double* F3 = sF + ((le * 3 + 2) * 5) * NS + bz;
+#pragma unroll
+                        for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + i];
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F1[q * NS + l]; }
+#pragma unroll
+                        for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + j];
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F2[q * NS + l * NP]; }
+#pragma unroll
+                        for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + k];
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F3[q * NS + l * n * NP]; }
+                    } else {
+                        const double* sQe = sQ + le * 5 * NS; const double* sJe = sJa + le * 9 * NS; const double* sFe = sF + le * 15 * NS;
+                        const int p = C::pidx(node);
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            const int me = d == 0 ? i : (d == 1 ? j : k);
+                            const int ob = d == 0 ? bx : (d == 1 ? by : bz);
+                            const int ostr = d == 0 ? 1 : (d == 1 ? NP : n * NP);
+                            double jaMe[3];
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) jaMe[c] = sJe[(3 * d + c) * NS + p];
+                            for (int l = 0; l < n; ++l) {
+                                const int other = ob + l * ostr;
+                                double fsvv[5];
+                                if (l == me) {
+#pragma unroll
+                                    for (int q = 0; q < 5; ++q) fsvv[q] = FinvD[r][d * 5 + q];
+                                } else {
+                                    double Qo[5], jo[3];
+#pragma unroll
+                                    for (int q = 0; q < 5; ++q) Qo[q] = sQe[q * NS + other];
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) jo[c] = sJe[(3 * d + c) * NS + other];
+                                    if (l > me) two_point_flux(ph, Qk[r], Qo, jaMe, jo, fsvv); else two_point_flux(ph, Qo, Qk[r], jo, jaMe, fsvv);
+                                }
+                                const double sd = sSharpDT[l * n + me], hd = sHatDT[l * n + me];
+                                if (ns) {
+#pragma unroll
+                                    for (int q = 0; q < 5; ++q) vol[q] = vol[q] + sd * fsvv[q] + hd * sFe[(d * 5 + q) * NS + other];
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 5; ++q) vol[q] = vol[q] + sd * fsvv[q];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) vol[q] = -vol[q];
+                    }
+                    // surface integral in the reference's order L,R,FRONT,BACK,BOTTOM,TOP
+                    const double* Fs = sFs + (le * 6) * 5 * N2;
+                    const double bL = sB[i], bR = sB[n + i], bF = sB[j], bBk = sB[n + j], bBo = sB[k], bT = sB[n + k];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        double fi = Fs[(5 * 5 + q) * N2 + k * n + j] * bL;
+                        fi = fi + Fs[(3 * 5 + q) * N2 + k * n + j] * bR;
+                        fi = fi + Fs[(0 * 5 + q) * N2 + k * n + i] * bF;
+                        fi = fi + Fs[(1 * 5 + q) * N2 + k * n + i] * bBk;
+                        fi = fi + Fs[(2 * 5 + q) * N2 + j * n + i] * bBo;
+                        fi = fi + Fs[(4 * 5 + q) * N2 + j * n + i] * bT;
+                        double res = vol[q] - fi;
+                        res = res / Jn;
+                        if (m.S) res = res + m.S[q * es + go];
+                        if (rk.mode == 0) {
+                            m.QDot[q * es + go] = res;
+                        } else {
+                            if (rk.storeQDot) m.QDot[q * es + go] = res;
+                            const double gg = rk.a * Gk[q] + res;
+                            m.G[q * es + go] = gg;
+                            Qk[r][q] = Qk[r][q] + rk.cdt * gg;
+                            m.Q[q * es + go] = Qk[r][q];
+                        }
+                    }
+                }
+            }
+        }
+        if (rk.prolong) {
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < NPT; ++r) {
+                    const int node = tn + r * TPE;
+                    if (node < N3) {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) sP[(le * 5 + q) * NS + C::pidx(node)] = Qk[r][q];
+                    }
+                }
+            }
+            __syncthreads();
+            prolong_block<n, 5>(m, sP, sV, sFace, sInfo, m.fQ, nLocal);
+        }
+        __syncthreads();
     }
 }
 
 // shared-memory footprints (bytes)
-inline size_t smemProlong(int n) { const int n3 = n * n * n, E = epbFor(n); return sizeof(double) * ((size_t)E * 5 * n3 + 2 * n); }
-inline size_t smemGradient(int n) { const int n2 = n * n, n3 = n2 * n, E = epbFor(n); return sizeof(double) * ((size_t)E * 15 * n3 + (size_t)E * 6 * 9 * n2 + n2 + 4 * n); }
-inline size_t smemVolume(int n, bool split, bool ns) { const int n2 = n * n, n3 = n2 * n, E = epbFor(n); return sizeof(double) * ((size_t)E * ((split && !ns) ? 5 : 15) * n3 + (split ? (size_t)E * 14 * n3 : 0) + (size_t)E * 30 * n2 + 2 * n2 + 4 * n); }
+template <int n> inline size_t smemProlong() { using C = KCfg<n>; return sizeof(double) * ((size_t)C::EPB * 5 * C::NS + 2 * n) + sizeof(int) * 12 * C::EPB; }
+template <int n, bool TMA> inline size_t smemGradient() { return GradSmem<n, TMA>::bytes; }
+template <int n, bool TMA> inline size_t smemVolume(bool split, bool ns) { return VolSmem<n, TMA>::bytes(split, ns); }
 
 }  // namespace h3d

@@ -185,7 +185,7 @@ int h3d_timer_end(h3d_handle h, double* ms);
 /* accumulated CUDA-event time per kernel class since the last call (option profile_kernels=1):
  * out = [ms, launches] x {gradient, riemann, volume, prolong} */
 int h3d_kernel_profile(h3d_handle h, double* out, int len);
-/* option string "key=value" ("store_qdot_every_stage=1", "profile_kernels=1"); unknown keys are an error */
+/* option string "key=value" ("store_qdot_every_stage=1", "profile_kernels=1", "use_tma=0"); unknown keys are an error */
 int h3d_set_option(h3d_handle h, const char* key_value);
 
 #ifdef __cplusplus
