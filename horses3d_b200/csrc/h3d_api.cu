@@ -613,6 +613,31 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
     CTX_CHECK(cudaMemcpy(dPermE, h->permE.data(), nElem * sizeof(int), cudaMemcpyHostToDevice));
     CTX_CHECK(cudaMemcpy(dPermF, h->permF.data(), nFace * sizeof(int), cudaMemcpyHostToDevice));
     m.elemFace = dEF; m.elemInfo = dEI; m.faceInfo = dFI; h->dPermE = dPermE; h->dPermF = dPermF;
+    {   // face-field offset of every element-trace node: f*n2 + (rotated) face node, MeshTypes.f90:70-108
+        const int N = n - 1;
+        std::vector<int> tr((size_t)nElem * 6 * n2);
+        for (int ed = 0; ed < nElem; ++ed) for (int lf = 0; lf < 6; ++lf) {
+            const int fd = eFace[6 * (size_t)ed + lf], ridx = (eInfo[6 * (size_t)ed + lf] >> 1) & 7;
+            for (int jj = 0; jj < n; ++jj) for (int ii = 0; ii < n; ++ii) {
+                int i, j;   // inverse of leftIndexes2Right: element-trace node (ii,jj) -> face node (i,j)
+                switch (ridx) {
+                    case 0: i = ii; j = jj; break;
+                    case 1: i = jj; j = N - ii; break;
+                    case 2: i = N - ii; j = N - jj; break;
+                    case 3: i = N - jj; j = ii; break;
+                    case 4: i = jj; j = ii; break;
+                    case 5: i = N - ii; j = jj; break;
+                    case 6: i = N - jj; j = N - ii; break;
+                    default: i = ii; j = N - jj; break;
+                }
+                tr[((size_t)ed * 6 + lf) * n2 + jj * n + ii] = fd * n2 + j * n + i;
+            }
+        }
+        if ((size_t)nFace * n2 * 30 > 2147483647ull) { h->err = "mesh too large for 32-bit face offsets on one device"; return 1; }
+        int* dTr; if (devAlloc(h, &dTr, tr.size())) return 2;
+        CTX_CHECK(cudaMemcpy(dTr, tr.data(), tr.size() * sizeof(int), cudaMemcpyHostToDevice));
+        m.elemTrace = dTr;
+    }
     // ---- fields
     const size_t ne = (size_t)nElem * n3, nf = (size_t)nFace * n2;
     double *Ja, *J, *invJ, *fN, *fT1, *fT2, *fJ;

@@ -34,6 +34,7 @@ struct DevMesh {
     const double* lesDelta;                // [nElem]  (V/n^3)^(1/3)
     const int* elemFace;                   // [nElem][6] device face id
     const int* elemInfo;                   // [nElem][6] bit0 side | bits1-3 rotation index | bits4-5 face type | bits 8.. zone+1
+    const int* elemTrace;                  // [nElem][6][n2] face-field offset f*n2 + rotmap[r][ab] of every element-trace node
     // face fields
     double *fQ, *fU, *fStar;
     const double *fN, *fT1, *fT2;          // [3][nFace][n2]
@@ -83,47 +84,51 @@ __device__ __forceinline__ int faceEnd(int lf) { return (lf == 1 || lf == 3 || l
 // Prolongation of NV element fields held in shared memory (sF[le][v][padded node]) to the faces.
 // HexElement_ProlongSolutionToFaces / ...GradientsToFaces (HexElementClass.f90:233-372): trace = sum_l A(l) v(l,end),
 // accumulated in ascending l from zero; Face_AdaptSolutionToFace: left copies, right is re-indexed.
-// sFace[le][6], sInfo[le][6]: face id / info of the CTA's elements.
+// sTr[le][6][n2]: face-field offset of every element-trace node; sInfo[le][6]: side / type bits of the element's faces.
 // ---------------------------------------------------------------------------------------------------------
+template <int n, int STRIDE>
+__device__ __forceinline__ void trace_line(const double* __restrict__ src, const double (&v0)[n], const double (&v1)[n], double& acc0, double& acc1) {
+    acc0 = 0.0; acc1 = 0.0;
+#pragma unroll
+    for (int l = 0; l < n; ++l) { const double sv = src[l * STRIDE]; acc0 = acc0 + sv * v0[l]; acc1 = acc1 + sv * v1[l]; }
+}
+
 template <int n, int NV>
 __device__ __forceinline__ void prolong_block(const DevMesh& m, const double* __restrict__ sF, const double* __restrict__ sV,
-                                              const int* __restrict__ sFace, const int* __restrict__ sInfo, double* __restrict__ dst, int nLocal) {
+                                              const int* __restrict__ sTr, const int* __restrict__ sInfo, double* __restrict__ dst, int nLocal) {
     // One work item = (element, axis, field, trace node): the line of n values along the axis is read once from shared
     // memory and contracted with both end vectors, giving the traces on the two opposite faces of that axis.
+    // The trace node ab of a thread is fixed (NT is a multiple of n^2); items advance over (element, axis, field).
     using C = KCfg<n>;
-    constexpr int N2 = C::N2, NP = C::NP, NS = C::NS;
+    constexpr int N2 = C::N2, NP = C::NP, NS = C::NS, NT = C::NT, ROWS = NT / N2;
+    static_assert(NT % N2 == 0, "threads per CTA must be a multiple of n^2");
     const size_t fstride = (size_t)m.nFace * N2;
     double v0[n], v1[n];
 #pragma unroll
     for (int l = 0; l < n; ++l) { v0[l] = sV[l]; v1[l] = sV[n + l]; }
-    const int total = nLocal * 3 * NV * N2;
-    for (int o = threadIdx.x; o < total; o += blockDim.x) {
-        const int ab = o % N2; int r = o / N2;
-        const int vv = r % NV; r /= NV;
-        const int ax = r % 3; const int le = r / 3;
-        const int a = ab % n, b = ab / n;
-        const int base = ax == 0 ? (b * n + a) * NP : (ax == 1 ? (b * n) * NP + a : b * NP + a);
-        const int stride = ax == 0 ? 1 : (ax == 1 ? NP : n * NP);
-        const double* src = sF + ((size_t)le * NV + vv) * NS + base;
-        double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-        for (int l = 0; l < n; ++l) { const double sv = src[l * stride]; acc0 = acc0 + sv * v0[l]; acc1 = acc1 + sv * v1[l]; }
-        const int lf0 = ax == 0 ? 5 : (ax == 1 ? 0 : 2), lf1 = ax == 0 ? 3 : (ax == 1 ? 1 : 4);   // (LEFT,RIGHT) (FRONT,BACK) (BOTTOM,TOP)
-        const int grp = vv / 5, eq = vv % 5;
-        {
-            const int f = sFace[le * 6 + lf0], info = sInfo[le * 6 + lf0];
-            dst[(size_t)((grp * 2 + (info & 1)) * 5 + eq) * fstride + (size_t)f * N2 + m.rotmap[((info >> 1) & 7) * N2 + ab]] = acc0;
-        }
-        {
-            const int f = sFace[le * 6 + lf1], info = sInfo[le * 6 + lf1];
-            dst[(size_t)((grp * 2 + (info & 1)) * 5 + eq) * fstride + (size_t)f * N2 + m.rotmap[((info >> 1) & 7) * N2 + ab]] = acc1;
-        }
+    const int ab = threadIdx.x % N2, a = ab % n, b = ab / n;
+    const int base0 = (b * n + a) * NP, base1 = (b * n) * NP + a, base2 = b * NP + a;
+    const int rows = nLocal * 3 * NV;
+    for (int row = threadIdx.x / N2; row < rows; row += ROWS) {
+        const int vv = row % NV; const int r = row / NV;
+        const int ax = r % 3, le = r / 3;
+        const double* src = sF + ((size_t)le * NV + vv) * NS;
+        double acc0, acc1;
+        int lf0, lf1;
+        if (ax == 0) { trace_line<n, 1>(src + base0, v0, v1, acc0, acc1); lf0 = 5; lf1 = 3; }             // LEFT, RIGHT
+        else if (ax == 1) { trace_line<n, NP>(src + base1, v0, v1, acc0, acc1); lf0 = 0; lf1 = 1; }       // FRONT, BACK
+        else { trace_line<n, n * NP>(src + base2, v0, v1, acc0, acc1); lf0 = 2; lf1 = 4; }                // BOTTOM, TOP
+        const size_t fo = (size_t)((vv / 5) * 10 + vv % 5) * fstride;
+        const int s0 = sInfo[le * 6 + lf0] & 1, s1 = sInfo[le * 6 + lf1] & 1;
+        dst[fo + (size_t)(s0 * 5) * fstride + sTr[(le * 6 + lf0) * N2 + ab]] = acc0;
+        dst[fo + (size_t)(s1 * 5) * fstride + sTr[(le * 6 + lf1) * N2 + ab]] = acc1;
     }
 }
 
 template <int n>
-__device__ __forceinline__ void load_face_tables(const DevMesh& m, int* sFace, int* sInfo, int e0, int nLocal) {
-    for (int t = threadIdx.x; t < nLocal * 6; t += blockDim.x) { sFace[t] = m.elemFace[(size_t)e0 * 6 + t]; sInfo[t] = m.elemInfo[(size_t)e0 * 6 + t]; }
+__device__ __forceinline__ void load_face_tables(const DevMesh& m, int* sTr, int* sInfo, int e0, int nLocal) {
+    for (int t = threadIdx.x; t < nLocal * 6; t += blockDim.x) sInfo[t] = m.elemInfo[(size_t)e0 * 6 + t];
+    for (int t = threadIdx.x; t < nLocal * 6 * n * n; t += blockDim.x) sTr[t] = m.elemTrace[(size_t)e0 * 6 * n * n + t];
 }
 
 // Stand-alone prolongation of Q (first residual after an upload).
@@ -134,13 +139,13 @@ __global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, int eBegin
     extern __shared__ double smem[];
     double* sQ = smem;                  // [EPB][5][NS]
     double* sV = sQ + EPB * 5 * NS;     // [2][n]
-    int* sFace = (int*)(sV + 2 * n);    // [EPB][6]
-    int* sInfo = sFace + EPB * 6;
+    int* sTr = (int*)(sV + 2 * n);      // [EPB][6][N2]
+    int* sInfo = sTr + EPB * 6 * C::N2; // [EPB][6]
     const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const int e0 = eBegin + blockIdx.x * EPB, e = e0 + le;
     const int nLocal = min(EPB, eEnd - e0);
     if (threadIdx.x < 2 * n) sV[threadIdx.x] = m.v[threadIdx.x];
-    load_face_tables<n>(m, sFace, sInfo, e0, nLocal);
+    load_face_tables<n>(m, sTr, sInfo, e0, nLocal);
     const size_t es = (size_t)m.nElem * N3;
     if (e < eEnd) {
 #pragma unroll
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, int eBegin
         }
     }
     __syncthreads();
-    prolong_block<n, 5>(m, sQ, sV, sFace, sInfo, m.fQ, nLocal);
+    prolong_block<n, 5>(m, sQ, sV, sTr, sInfo, m.fQ, nLocal);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -175,7 +180,7 @@ struct GradSmem {
     static constexpr int phase1 = C::EPB * (5 * C::NS + 6 * 9 * C::N2);
     static constexpr int phase2 = C::EPB * 15 * C::NS;
     static constexpr int fields = TMA ? C::EPB * (15 * C::N3 + 6 * 9 * C::N2 + 15 * C::NS) : (phase1 > phase2 ? phase1 : phase2);
-    static constexpr size_t bytes = sizeof(double) * (fields + C::N2 + 4 * n) + sizeof(int) * 12 * C::EPB + 16;
+    static constexpr size_t bytes = sizeof(double) * (fields + C::N2 + 4 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 6) + 16;
 };
 
 // interface data of one element-trace node: raw loads (issued early) and their reduction to uStar / normal / J_f
@@ -185,10 +190,8 @@ template <int n>
 __device__ __forceinline__ void grad_iface_load(const DevMesh& m, int e, int lf, int ab, GradIface& g) {
     constexpr int N2 = n * n;
     const size_t fs = (size_t)m.nFace * N2;
-    const int f = m.elemFace[(size_t)e * 6 + lf];
     g.info = m.elemInfo[(size_t)e * 6 + lf];
-    const int ridx = (g.info >> 1) & 7;
-    const size_t fo = (size_t)f * N2 + m.rotmap[ridx * N2 + ab];
+    const size_t fo = (size_t)m.elemTrace[((size_t)e * 6 + lf) * N2 + ab];
     g.Jf = m.fJ[fo];
 #pragma unroll
     for (int d = 0; d < 3; ++d) g.nh[d] = m.fN[d * fs + fo];
@@ -234,8 +237,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
     double* sDT = smem + GradSmem<n, TMA>::fields;              // [n][n]
     double* sB = sDT + N2;
     double* sV = sB + 2 * n;
-    int* sFace = (int*)(sV + 2 * n);
-    int* sInfo = sFace + EPB * 6;
+    int* sTr = (int*)(sV + 2 * n);                              // [EPB][6][N2]
+    int* sInfo = sTr + EPB * 6 * N2;                            // [EPB][6]
     uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 6) + 7) & ~(uintptr_t)7);
     const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const size_t es = (size_t)m.nElem * N3;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
         const int e0 = eBegin + tile * EPB, e = e0 + le;
         const int nLocal = min(EPB, eEnd - e0);
         const bool active = e < eEnd;
-        for (int t = threadIdx.x; t < nLocal * 6; t += blockDim.x) { sFace[t] = m.elemFace[(size_t)e0 * 6 + t]; sInfo[t] = m.elemInfo[(size_t)e0 * 6 + t]; }
+        load_face_tables<n>(m, sTr, sInfo, e0, nLocal);
         // interface data of the six faces at element-trace nodes (prefetched during the previous tile when possible)
         if (!havePrefetch) {
 #pragma unroll
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
             }
             havePrefetch = true;
         }
-        prolong_block<n, 15>(m, sG, sV, sFace, sInfo, m.fU, nLocal);
+        prolong_block<n, 15>(m, sG, sV, sTr, sInfo, m.fU, nLocal);
         __syncthreads();
     }
 }
@@ -493,11 +496,11 @@ template <int n, bool TMA>
 struct VolSmem {
     using C = KCfg<n>;
     __host__ __device__ static constexpr int fluxFields(bool split, bool ns) { return split ? (ns ? 15 : 0) : 15; }
-    __host__ __device__ static constexpr int stagedFields(bool ns) { return TMA ? (ns ? 29 : 14) : 0; }   // Q 5 [, Ux Uy Uz 15], Ja 9
+    __host__ __device__ static constexpr int stagedFields(bool ns) { return TMA ? (ns ? 29 : 14) + 6 : 0; }   // Q 5 [, Ux Uy Uz 15], Ja 9 | J 1, G 5
     __host__ __device__ static constexpr int fields(bool split, bool ns) {
         return C::EPB * (stagedFields(ns) * C::N3 + (fluxFields(split, ns) + (split ? 14 : 0)) * C::NS + 30 * C::N2);
     }
-    static size_t bytes(bool split, bool ns) { return sizeof(double) * (fields(split, ns) + 2 * C::N2 + 4 * n) + sizeof(int) * 12 * C::EPB + 16; }
+    static size_t bytes(bool split, bool ns) { return sizeof(double) * (fields(split, ns) + 2 * C::N2 + 4 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 6) + 32; }
 };
 
 template <int n, bool SPLIT, bool TMA>
@@ -511,7 +514,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
     const int nStaged = TMA ? (ns ? 29 : 14) : 0;
     const int nFlux = SPLIT ? (ns ? 15 : 0) : 15;
     double* sIn = smem;                                  // TMA: [nStaged][TN3]: Q 5, (Ux Uy Uz 15,) Ja 9
-    double* sF = smem + nStaged * TN3;                   // [EPB][nFlux][NS]
+    double* sJG = smem + nStaged * TN3;                  // TMA: [6][TN3]: J, G 5 (second barrier: consumed after the contraction)
+    double* sF = sJG + (TMA ? 6 * TN3 : 0);              // [EPB][nFlux][NS]
     double* sQ = sF + EPB * nFlux * NS;                  // SPLIT: [EPB][5][NS]
     double* sJa = sQ + (SPLIT ? EPB * 5 * NS : 0);       // SPLIT: [EPB][9][NS]
     double* sFs = sJa + (SPLIT ? EPB * 9 * NS : 0);      // [EPB][6][5][N2] fStar at element-trace nodes (signed)
@@ -519,9 +523,9 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
     double* sSharpDT = sHatDT + N2;                      // [n][n]
     double* sB = sSharpDT + N2;                          // [2][n]
     double* sV = sB + 2 * n;                             // [2][n]
-    int* sFace = (int*)(sV + 2 * n);                     // [EPB][6]
-    int* sInfo = sFace + EPB * 6;
-    uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 6) + 7) & ~(uintptr_t)7);
+    int* sTr = (int*)(sV + 2 * n);                       // [EPB][6][N2]
+    int* sInfo = sTr + EPB * 6 * N2;                     // [EPB][6]
+    uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 6) + 7) & ~(uintptr_t)7);   // bar[0]: flux inputs, bar[1]: J and G
     double* sP = SPLIT ? sQ : sF;                        // prolongation buffer for the updated state [EPB][5][NS]
     const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const size_t es = (size_t)m.nElem * N3, fs = (size_t)m.nFace * N2;
@@ -548,32 +552,39 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 #pragma unroll 1
         for (int c = 0; c < 9; ++c) bulk_g2s(sIn + (jaOff + c) * TN3, m.Ja + c * es + off, bytes, bar);
     };
+    auto issueLate = [&](int tile) {   // thread 0: J and G of the tile (read after the contraction)
+        const int e0 = eBegin + tile * EPB;
+        const int nLoc = min(EPB, eEnd - e0);
+        const uint32_t bytes = (uint32_t)(nLoc * N3 * sizeof(double));
+        const size_t off = (size_t)e0 * N3;
+        mbar_arrive_expect_tx(bar + 1, 6 * bytes);
+        bulk_g2s(sJG, m.J + off, bytes, bar + 1);
+#pragma unroll 1
+        for (int c = 0; c < 5; ++c) bulk_g2s(sJG + (1 + c) * TN3, m.G + c * es + off, bytes, bar + 1);
+    };
     if (TMA) {
-        if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); }
         __syncthreads();
-        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) issue(blockIdx.x);
+        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) { issue(blockIdx.x); issueLate(blockIdx.x); }
     }
     uint32_t parity = 0;
     for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
         const int e0 = eBegin + tile * EPB, e = e0 + le;
         const int nLocal = min(EPB, eEnd - e0);
         const bool active = e < eEnd;
-        for (int t = threadIdx.x; t < nLocal * 6; t += blockDim.x) { sFace[t] = m.elemFace[(size_t)e0 * 6 + t]; sInfo[t] = m.elemInfo[(size_t)e0 * 6 + t]; }
-        // interface fluxes of the six faces at element-trace nodes (left: +, right: -, FaceClass.f90:681-690):
-        // loads issued now, stored to shared memory after the flux phase
-        double fsv[FSI];
+        load_face_tables<n>(m, sTr, sInfo, e0, nLocal);
+        // interface fluxes of the six faces at element-trace nodes: raw loads issued now, signed (left +, right -,
+        // FaceClass.f90:681-690) and stored to shared memory after the flux phase
+        double fsv[FSI]; int fsg[FSI];
 #pragma unroll
         for (int it = 0; it < FSI; ++it) {
             const int o = threadIdx.x + it * NT;
-            fsv[it] = 0.0;
+            fsv[it] = 0.0; fsg[it] = 0;
             if (o < nLocal * 30 * N2) {
                 const int ab = o % N2; int r = o / N2;
-                const int q = r % 5; r /= 5;
-                const int lf = r % 6; const int l2 = r / 6;
-                const int f = m.elemFace[(size_t)(e0 + l2) * 6 + lf];
-                const int info = m.elemInfo[(size_t)(e0 + l2) * 6 + lf];
-                const double val = m.fStar[(size_t)q * fs + (size_t)f * N2 + m.rotmap[((info >> 1) & 7) * N2 + ab]];
-                fsv[it] = (info & 1) ? -val : val;
+                const int q = r % 5; r /= 5;                 // r = l2*6 + lf
+                fsg[it] = m.elemInfo[(size_t)e0 * 6 + r];
+                fsv[it] = m.fStar[(size_t)q * fs + m.elemTrace[((size_t)e0 * 6 + r) * N2 + ab]];
             }
         }
         if (TMA) { mbar_wait(bar, parity); parity ^= 1; }
@@ -647,10 +658,11 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 #pragma unroll
         for (int it = 0; it < FSI; ++it) {
             const int o = threadIdx.x + it * NT;
-            if (o < nLocal * 30 * N2) sFs[o] = fsv[it];     // o = ((l2*6 + lf)*5 + q)*N2 + ab
+            if (o < nLocal * 30 * N2) sFs[o] = (fsg[it] & 1) ? -fsv[it] : fsv[it];     // o = ((l2*6 + lf)*5 + q)*N2 + ab
         }
         __syncthreads();
         if (TMA && threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issue(tile + gridDim.x);   // the staged inputs are consumed
+        if (TMA) mbar_wait(bar + 1, parity ^ 1);   // J and G of this tile (parity was flipped after the first wait)
         if (active) {
 #pragma unroll
             for (int r = 0; r < NPT; ++r) {
@@ -659,13 +671,6 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                     const int i = node % n, j = (node / n) % n, k = node / N2;
                     const size_t go = (size_t)e * N3 + node;
                     const int bx = (k * n + j) * NP, by = (k * n) * NP + i, bz = j * NP + i;
-                    // late inputs, requested before the contraction so that their latency hides behind it
-                    const double Jn = m.J[go];
-                    double Gk[5];
-                    if (rk.mode != 0) {
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) Gk[q] = m.G[q * es + go];
-                    }
                     double vol[5] = {0, 0, 0, 0, 0};
                     if (!SPLIT) {
                         const double* F1 = sF + ((le * 3 + 0) * 5) * NS + bx; const double* F2 = sF + ((le * 3 + 1) * 5) * NS + by; const double* F3 = sF + ((le * 3 + 2) * 5) * NS + bz;
@@ -722,6 +727,16 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                     // surface integral in the reference's order L,R,FRONT,BACK,BOTTOM,TOP
                     const double* Fs = sFs + (le * 6) * 5 * N2;
                     const double bL = sB[i], bR = sB[n + i], bF = sB[j], bBk = sB[n + j], bBo = sB[k], bT = sB[n + k];
+                    double Jn, Gk[5];
+                    if (TMA) {
+                        Jn = sJG[le * N3 + node];
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) Gk[q] = sJG[(1 + q) * TN3 + le * N3 + node];
+                    } else {
+                        Jn = m.J[go];
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) Gk[q] = (rk.mode != 0) ? m.G[q * es + go] : 0.0;
+                    }
 #pragma unroll
                     for (int q = 0; q < 5; ++q) {
                         double fi = Fs[(5 * 5 + q) * N2 + k * n + j] * bL;
@@ -759,14 +774,15 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                 }
             }
             __syncthreads();
-            prolong_block<n, 5>(m, sP, sV, sFace, sInfo, m.fQ, nLocal);
+            prolong_block<n, 5>(m, sP, sV, sTr, sInfo, m.fQ, nLocal);
         }
         __syncthreads();
+        if (TMA && threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issueLate(tile + gridDim.x);   // J/G buffer is free again
     }
 }
 
 // shared-memory footprints (bytes)
-template <int n> inline size_t smemProlong() { using C = KCfg<n>; return sizeof(double) * ((size_t)C::EPB * 5 * C::NS + 2 * n) + sizeof(int) * 12 * C::EPB; }
+template <int n> inline size_t smemProlong() { using C = KCfg<n>; return sizeof(double) * ((size_t)C::EPB * 5 * C::NS + 2 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 6); }
 template <int n, bool TMA> inline size_t smemGradient() { return GradSmem<n, TMA>::bytes; }
 template <int n, bool TMA> inline size_t smemVolume(bool split, bool ns) { return VolSmem<n, TMA>::bytes(split, ns); }
 
