@@ -130,6 +130,8 @@ def main_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # torchrun pins OMP_NUM_THREADS=1; the host-side metric construction is OpenMP code: give each rank its share of the cores
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(world, 1)))
     if world != args.gpus and world > 1:
         raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
     torch.cuda.set_device(local)
@@ -197,15 +199,16 @@ def main_b200(args):
 
     # ---- kernel-level timing of the dominant kernel (roofline), a short profiled pass
     roof = None
+    api.call("set_option", b"profile_kernels=1")        # every rank steps (the halo exchange is collective); rank 0 reports
+    for _ in range(3):
+        sem.TakeRK3Step(0.0, dt)
+    prof = (C.c_double * 16)()
+    api.binding.lib.h3d_kernel_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+    api.binding.lib.h3d_kernel_profile(api.handle, prof, 16)
+    api.call("set_option", b"profile_kernels=0")
+    barrier()
     if rank == 0:
         try:
-            api.call("set_option", b"profile_kernels=1")
-            for _ in range(3):
-                sem.TakeRK3Step(0.0, dt)
-            prof = (C.c_double * 16)()
-            api.binding.lib.h3d_kernel_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-            api.binding.lib.h3d_kernel_profile(api.handle, prof, 16)
-            api.call("set_option", b"profile_kernels=0")
             # prof: [ms_gradient, n_gradient, ms_riemann, n_riemann, ms_volume, n_volume, ms_prolong, n_prolong]
             vol_ms = prof[4] / max(prof[5], 1.0)
             peaks = {}

@@ -101,10 +101,21 @@ def gpu_library():
     """Loads libh3dgpu.so (built in-tree by build.build_gpu).  Raises if it cannot be built/loaded."""
     global _gpu_lib
     if _gpu_lib is None:
-        path = os.environ.get("H3D_GPU_LIB") or _build.GPU_LIB     # H3D_GPU_LIB: alternative build of the SAME sources (e.g. -fmad=false)
+        path = os.environ.get("H3D_GPU_LIB") or _build.GPU_LIB     # H3D_GPU_LIB: alternative build of the SAME sources
         if not os.path.exists(path):
             path = _build.build_gpu()
-        _gpu_lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        # libh3dgpu.so needs libnccl.so.2.  PyTorch bundles a newer NCCL than the system one under the same soname; load
+        # that one first so that this library and a later `import torch` share a single NCCL in the process.
+        import sys
+        for d in sys.path:
+            cand = os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                try:
+                    C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                except OSError:
+                    pass
+                break
+        _gpu_lib = C.CDLL(path)
     return _gpu_lib
 
 

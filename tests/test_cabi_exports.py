@@ -1,0 +1,54 @@
+"""The C-ABI library must load and export every symbol that include/h3d_gpu.h declares (no compute calls here),
+and must refuse to run without a device instead of falling back to anything."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from horses3d_b200 import build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "h3d_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(h3d_[A-Za-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_documented_entry_points():
+    names = declared_functions()
+    for must in ("h3d_create", "h3d_set_physics", "h3d_set_basis", "h3d_set_mesh", "h3d_set_halo", "h3d_upload_Q", "h3d_download",
+                 "h3d_compute_time_derivative", "h3d_rk_step", "h3d_max_residuals", "h3d_max_timestep", "h3d_volume_integral",
+                 "h3d_has_nan", "h3d_destroy", "h3d_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    build.build_gpu()
+    from horses3d_b200.capi import gpu_library
+    lib = gpu_library()
+    missing = [f for f in declared_functions() if not hasattr(lib, f)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from horses3d_b200.capi import GpuApi, H3dError
+    with pytest.raises(H3dError, match="no CUDA device|no CPU fallback"):
+        GpuApi()
+
+
+def test_oracle_is_not_reachable_from_the_product_package():
+    """The product must never import, link or call the oracle."""
+    pkg = os.path.join(ROOT, "horses3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f == "build.py":      # holds the recipe that COMPILES the checker; building it is not using it
+                continue
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle_api" not in text and "h3d_oracle" not in text and "orc_" not in text, os.path.join(dirpath, f)

@@ -78,7 +78,9 @@ def test_two_ranks_reproduce_the_single_domain_oracle(kw, method):
     for rank, ge, qd_r, Qn_r, res_r, mon_r, dts_r in got:
         assert rel_err(qd_r, qd[ge]) < 1e-13
         assert rel_err(Qn_r, Qn[ge]) < 1e-13
-        assert np.array_equal(res_r, res)                       # max-reduction over ranks: exact
-        assert np.allclose(dts_r, dts, rtol=0, atol=0)
+        # MPI-face geometry is built from the local element (right side: rotated), so it differs from the single-domain
+        # face geometry in the last bits: reductions agree to round-off, not bit for bit
+        assert np.allclose(res_r, res, rtol=1e-11, atol=0)
+        assert np.allclose(dts_r, dts, rtol=1e-12, atol=0)
         for k in mon:
             assert abs(mon_r[k] - mon[k]) < 1e-12 * max(abs(mon[k]), 1e-30)
