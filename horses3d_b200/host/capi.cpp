@@ -121,4 +121,30 @@ void* h3dhost_extract_partition(void* hp, const int* part, int rank) {
     return c;
 }
 
+// Copies the parent's element/face geometry into a partition extracted from it (instead of rebuilding it from the local
+// elements).  MPI faces then carry the GLOBAL face geometry on both ranks, which makes results independent of the
+// partition bit for bit (the reference rebuilds MPI-face geometry from the local element, HexMesh.f90:3000-3030).
+int h3dhost_inherit_geometry(void* childp, void* parentp) {
+    Host* c = (Host*)childp; Host* p = (Host*)parentp;
+    if (!p->hasGeom) { g_err = "parent mesh has no geometry"; return 1; }
+    const HostGeometry& G = p->geom; HostGeometry& g = c->geom;
+    g.N = G.N; g.n = G.n; g.nodeType = G.nodeType; g.sp = G.sp;
+    const size_t n3 = (size_t)G.n * G.n * G.n, n2 = (size_t)G.n * G.n;
+    const size_t nE = c->halo.globalElem.size(), nF = c->halo.globalFace.size();
+    auto gatherE = [&](const std::vector<double>& src, std::vector<double>& dst, size_t w) {
+        dst.resize(nE * w);
+        for (size_t l = 0; l < nE; ++l) std::memcpy(&dst[l * w], &src[(size_t)c->halo.globalElem[l] * w], w * sizeof(double));
+    };
+    auto gatherF = [&](const std::vector<double>& src, std::vector<double>& dst, size_t w) {
+        dst.resize(nF * w);
+        for (size_t l = 0; l < nF; ++l) std::memcpy(&dst[l * w], &src[(size_t)c->halo.globalFace[l] * w], w * sizeof(double));
+    };
+    gatherE(G.x, g.x, 3 * n3); gatherE(G.jGradXi, g.jGradXi, 3 * n3); gatherE(G.jGradEta, g.jGradEta, 3 * n3); gatherE(G.jGradZeta, g.jGradZeta, 3 * n3);
+    gatherE(G.jac, g.jac, n3); gatherE(G.invJac, g.invJac, n3); gatherE(G.volume, g.volume, 1);
+    gatherF(G.fx, g.fx, 3 * n2); gatherF(G.fnormal, g.fnormal, 3 * n2); gatherF(G.ft1, g.ft1, 3 * n2); gatherF(G.ft2, g.ft2, 3 * n2);
+    gatherF(G.fjac, g.fjac, n2); gatherF(G.fsurface, g.fsurface, 1);
+    c->hasGeom = true;
+    return 0;
+}
+
 }  // extern "C"

@@ -16,6 +16,7 @@
 #include <array>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <map>
 #include <random>
@@ -99,27 +100,42 @@ inline std::string toLower(std::string s) { for (auto& c : s) c = (char)std::tol
 inline bool readSpecMesh(const std::string& path, HostMesh& m, std::string& err) {
     std::ifstream in(path);
     if (!in) { err = "Error opening file: " + path; return false; }
-    std::string line;
-    auto nextLine = [&](std::istringstream& ss) -> bool {
-        while (std::getline(in, line)) { if (line.find_first_not_of(" \t\r\n") != std::string::npos) { ss.clear(); ss.str(line); return true; } }
-        return false;
+    // Fortran list-directed READ semantics: a READ of `count` items consumes as many records (lines) as it needs and
+    // discards the rest of the last record it touched.
+    auto readTokens = [&](int count, std::vector<std::string>& out) -> bool {
+        out.clear();
+        std::string line;
+        while ((int)out.size() < count) {
+            if (!std::getline(in, line)) return false;
+            std::istringstream ss(line);
+            std::string tok;
+            while ((int)out.size() < count && (ss >> tok)) out.push_back(tok);
+        }
+        return true;
     };
-    std::istringstream ss;
-    int nNodes, nElems, bfo;
-    if (!nextLine(ss) || !(ss >> nNodes >> nElems >> bfo)) { err = "bad SpecMesh header"; return false; }
+    std::vector<std::string> tk;
+    auto toD = [](const std::string& t) { std::string u = t; for (auto& c : u) if (c == 'd' || c == 'D') c = 'e'; return std::strtod(u.c_str(), nullptr); };
+    if (!readTokens(3, tk)) { err = "bad SpecMesh header"; return false; }
+    const int nNodes = std::atoi(tk[0].c_str()), nElems = std::atoi(tk[1].c_str()), bfo = std::atoi(tk[2].c_str());
+    if (nNodes <= 0 || nElems <= 0 || bfo < 1) { err = "bad SpecMesh header"; return false; }
     m.bFaceOrder = bfo;
     const int nb = bfo + 1;
     m.nodes.resize(3 * (size_t)nNodes);
     for (int j = 0; j < nNodes; ++j) {
-        if (!nextLine(ss) || !(ss >> m.nodes[3 * j] >> m.nodes[3 * j + 1] >> m.nodes[3 * j + 2])) { err = "bad node line"; return false; }
+        if (!readTokens(3, tk)) { err = "bad node line"; return false; }
+        for (int c = 0; c < 3; ++c) m.nodes[3 * j + c] = toD(tk[c]);
     }
     m.elemNodes.resize(8 * (size_t)nElems); m.isHex8.assign(nElems, 1); m.patches.resize(nElems); m.bname.resize(6 * (size_t)nElems);
     for (int l = 0; l < nElems; ++l) {
-        if (!nextLine(ss)) { err = "unexpected EOF (element nodes)"; return false; }
-        for (int k = 0; k < 8; ++k) { int id; if (!(ss >> id)) { err = "bad element node ids"; return false; } m.elemNodes[8 * l + k] = id - 1; }
+        if (!readTokens(8, tk)) { err = "unexpected EOF (element nodes)"; return false; }
+        for (int k = 0; k < 8; ++k) {
+            const int id = std::atoi(tk[k].c_str());
+            if (id < 1 || id > nNodes) { err = "bad element node ids"; return false; }
+            m.elemNodes[8 * l + k] = id - 1;
+        }
         int flags[6];
-        if (!nextLine(ss)) { err = "unexpected EOF (face flags)"; return false; }
-        for (int k = 0; k < 6; ++k) if (!(ss >> flags[k])) { err = "bad face flags"; return false; }
+        if (!readTokens(6, tk)) { err = "unexpected EOF (face flags)"; return false; }
+        for (int k = 0; k < 6; ++k) flags[k] = std::atoi(tk[k].c_str());
         int mx = 0; for (int k = 0; k < 6; ++k) mx = std::max(mx, flags[k]);
         if (mx != 0) {
             m.isHex8[l] = 0;
@@ -134,14 +150,14 @@ inline bool readSpecMesh(const std::string& path, HostMesh& m, std::string& err)
                 } else {
                     p.nu = p.nv = nb; p.pts.resize(3 * (size_t)nb * nb);
                     for (int j = 0; j < nb; ++j) for (int i = 0; i < nb; ++i) {
-                        if (!nextLine(ss)) { err = "unexpected EOF (patch)"; return false; }
-                        for (int c = 0; c < 3; ++c) ss >> p.pts[(j * nb + i) * 3 + c];
+                        if (!readTokens(3, tk)) { err = "unexpected EOF (patch)"; return false; }
+                        for (int c = 0; c < 3; ++c) p.pts[(j * nb + i) * 3 + c] = toD(tk[c]);
                     }
                 }
             }
         }
-        if (!nextLine(ss)) { err = "unexpected EOF (boundary names)"; return false; }
-        for (int k = 0; k < 6; ++k) { std::string s; ss >> s; m.bname[6 * l + k] = toLower(s); }
+        if (!readTokens(6, tk)) { err = "unexpected EOF (boundary names)"; return false; }
+        for (int k = 0; k < 6; ++k) m.bname[6 * l + k] = toLower(tk[k]);
     }
     return true;
 }

@@ -38,6 +38,7 @@ def lib():
         L.h3dhost_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.h3dhost_extract_partition.restype = C.c_void_p
         L.h3dhost_extract_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.h3dhost_inherit_geometry.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -146,9 +147,14 @@ class HostMesh:
         _check(lib().h3dhost_partition(self._h, nparts, 0 if method == "metis" else 1, part.ctypes.data))
         return part
 
-    def extract(self, part, rank):
+    def extract(self, part, rank, inherit_geometry=False):
+        """Local mesh of `rank`.  inherit_geometry=True copies this (global) mesh's metric terms instead of rebuilding them
+        from the local elements: MPI faces then carry the global face geometry and results do not depend on the partition."""
         part = np.ascontiguousarray(part, dtype=np.int32)
         child = HostMesh(lib().h3dhost_extract_partition(self._h, part.ctypes.data, rank))
         child.bcs = getattr(self, "bcs", [])
         child.bc_params = getattr(self, "bc_params", None)
+        if inherit_geometry:
+            _check(lib().h3dhost_inherit_geometry(child._h, self._h))
+            child.N, child.nodes = self.N, self.nodes
         return child

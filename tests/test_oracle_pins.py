@@ -46,6 +46,45 @@ def test_k1_taylor_green_5_steps():
     assert abs(rec["enstrophy"] - 3.7499683882517909E-01) < 1.0e-11
 
 
+CYLINDER_MESH = "/root/reference/Solver/test/TestMeshes/CylinderNSpol3.mesh"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(CYLINDER_MESH), reason="reference test mesh not available on this machine")
+def test_k5_cylinder_100_steps():
+    """Solver/test/NavierStokes/Cylinder: Re 200, M 0.3, P=3 Gauss, Roe, BR1, RK3, cfl = dcfl = 0.3, 100 steps on the curved
+    (bFaceOrder 3) cylinder mesh with no-slip wall, free-slip walls, inflow and outflow.  Expected residuals and the
+    1e-11 tolerance from SETUP/ProblemFile.f90:551-575.  Pins the boundary conditions, the curved
+    transfinite geometry and the SpecMesh reader (multi-line records, curved patches)."""
+    import math
+    from horses3d_b200.physics import bc_parameters
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")
+    theta, phi = 0.0, 90.0 * (math.pi / 180.0)
+    zones = [("innercylinder", "noslipwall"), ("bottom", "freeslipwall"), ("top", "freeslipwall"), ("back", "inflow"),
+             ("left", "inflow"), ("front", "inflow"), ("right", "outflow")]
+    p_in, rho_in = 1.0 / phys.gammaM2, 1.0
+    v_in = phys.Mach * math.sqrt(phys.gamma * p_in / rho_in)           # InflowBC.f90:172-186
+    params = []
+    for _, t in zones:
+        if t == "inflow":
+            params.append(bc_parameters("inflow", phys, rho=rho_in, v=v_in, aoa_theta=theta, aoa_phi=phi, p=p_in))
+        elif t == "outflow":
+            params.append(bc_parameters("outflow", phys, p=1.0 / phys.gammaM2))
+        else:
+            params.append(bc_parameters(t, phys))
+    m = HostMesh.read(CYLINDER_MESH).connect([(z, t, None) for z, t in zones], np.array(params)).geometry(3, GAUSS)
+    assert m.sizes()[:2] == (1864, 6182)
+    sem = DGSem(oracle_api.OracleApi(), m, phys)
+    u, v, w = math.cos(theta) * math.cos(phi), math.sin(theta) * math.cos(phi), math.sin(phi)   # ProblemFile.f90:304-322
+    Q = np.zeros(sem.node_coordinates().shape[:-1] + (5,))
+    Q[..., 0], Q[..., 1], Q[..., 2], Q[..., 3] = 1.0, u, v, w
+    Q[..., 4] = (1.0 / phys.gammaM2) / (phys.gamma - 1.0) + 0.5 * (u ** 2 + v ** 2 + w ** 2)
+    sem.set_Q(Q)
+    rec = sem.integrate(100, cfl=0.3, dcfl=0.3, monitors=False)[-1]
+    res = np.array([8.8131248889811715E+00, 1.7608838068776613E+01, 1.9037533106262516E-01, 2.4301352846288605E+01, 2.4063786464536835E+02])
+    assert np.abs(rec["residuals"] - res).max() < 1.0e-11 * 240.0
+    assert np.abs((rec["residuals"] - res) / res).max() < 1.0e-11
+
+
 @pytest.mark.parametrize("nodes,inviscid,avg", [(GAUSS, "standard", "standard"), (GAUSSLOBATTO, "split-form", "pirozzoli"),
                                                 (GAUSSLOBATTO, "split-form", "kennedy-gruber"), (GAUSSLOBATTO, "split-form", "standard")])
 def test_oracle_free_stream_preservation_on_curved_rotated_mesh(nodes, inviscid, avg):
