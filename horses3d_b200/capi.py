@@ -35,6 +35,7 @@ class Binding:
         "set_basis": [C.c_int, C.c_int] + [_D] * 7,
         "set_mesh": [C.c_int, C.c_int] + [_D] * 19,
         "set_boundary_conditions": [C.c_int, _D, _D],
+        "set_wall_distance": [_D, _D],
         "upload_Q": [_D],
         "download": [_D] * 5,
         "set_source": [_D],

@@ -407,6 +407,7 @@ int residual(h3d_context* h, const RkArgs& rk) {
     const bool multi = h->nNbr > 0;
     const bool grads = h->physics.computeGradients != 0;
     int rc;
+    if (h->ph.wallModel && !h->m.dWall) { h->err = "the LES wall model needs h3d_set_wall_distance"; return 1; }
     if (!h->facesValid) { ProfScope ps(h, 3, sc); if ((rc = doProlong(h, 0, h->nElem, sc))) return rc; }
     if (multi) {
         CTX_CHECK(cudaEventRecord(h->evFaces, sc));
@@ -524,6 +525,8 @@ int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
     q.gamma = p->gamma; q.gm1 = p->gammaMinus1; q.gammaM2 = p->gammaM2; q.mu = p->mu; q.mu_to_kappa = p->mu_to_kappa;
     q.S_div_Tref = p->S_div_Tref; q.T_renorm = p->T_renorm; q.lambdaStab = p->lambdaStab; q.Cs = p->smagorinsky_Cs;
     q.ns = p->flowIsNavierStokes; q.riemann = p->riemann; q.averaging = p->averaging; q.les = p->les;
+    q.wallModel = (p->les != H3D_LES_NONE && p->les_wall_model == 1) ? 1 : 0;
+    if (p->les_wall_model != 0 && p->les_wall_model != 1) { h->err = "LES wall model not recognized."; return 1; }
     h->havePhysics = true;
     return 0;
 }
@@ -680,9 +683,26 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
         m.lesDelta = dde; m.fDelta = ddf;
         if (h->physics.les != H3D_LES_NONE && (!volume || !faceSurface)) { h->err = "LES needs element volumes and face surfaces"; return 1; }
     }
-    m.S = nullptr; m.bcType = nullptr; m.bcParams = nullptr;
+    m.S = nullptr; m.bcType = nullptr; m.bcParams = nullptr; m.dWall = nullptr; m.fDWall = nullptr;
     for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_BOUNDARY && faceZone[f] < 0) { h->err = "boundary face without a zone"; return 1; }
     h->haveMesh = true; h->facesValid = false;
+    return 0;
+}
+
+int h3d_set_wall_distance(h3d_handle h, const double* dWallElem, const double* dWallFace) {
+    CTX_CHECK(cudaSetDevice(h->device));
+    if (!h->haveMesh) { h->err = "h3d_set_wall_distance: set the mesh first"; return 1; }
+    if (!dWallElem || !dWallFace) { h->err = "h3d_set_wall_distance: null array"; return 1; }
+    DevMesh& m = h->m;
+    const int n2 = m.n * m.n, n3 = n2 * m.n;
+    std::vector<double> de((size_t)m.nElem * n3), df((size_t)m.nFace * n2);
+    for (int ed = 0; ed < m.nElem; ++ed) std::memcpy(&de[(size_t)ed * n3], dWallElem + (size_t)h->permE[ed] * n3, n3 * sizeof(double));
+    for (int fd = 0; fd < m.nFace; ++fd) std::memcpy(&df[(size_t)fd * n2], dWallFace + (size_t)h->permF[fd] * n2, n2 * sizeof(double));
+    double *dde, *ddf;
+    if (devAlloc(h, &dde, de.size()) || devAlloc(h, &ddf, df.size())) return 2;
+    CTX_CHECK(cudaMemcpy(dde, de.data(), de.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(ddf, df.data(), df.size() * sizeof(double), cudaMemcpyHostToDevice));
+    m.dWall = dde; m.fDWall = ddf;
     return 0;
 }
 

@@ -32,6 +32,7 @@ struct DevMesh {
     const double* Ja;                      // [9][nElem][n3]: (3*d + c) = c-th Cartesian component of J a^d
     const double *J, *invJ;                // [nElem][n3]
     const double* lesDelta;                // [nElem]  (V/n^3)^(1/3)
+    const double *dWall, *fDWall;          // [nElem][n3], [nFace][n2] wall distances (LES wall model) or nullptr
     const int* elemFace;                   // [nElem][6] device face id
     const int* elemInfo;                   // [nElem][6] bit0 side | bits1-3 rotation index | bits4-5 face type | bits 8.. zone+1
     const int* elemTrace;                  // [nElem][6][n2] face-field offset f*n2 + rotmap[r][ab] of every element-trace node
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + q) * fs]; }
             laminar_mu_kappa(ph, QL, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux(ph, QL, gx, gy, gz, mu, 0.0, kappa, F);
 #pragma unroll
             for (int q = 0; q < 5; ++q) { visc[q] = F[q][0] * nh[0] + F[q][1] * nh[1] + F[q][2] * nh[2]; }
@@ -463,12 +464,12 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + q) * fs]; }
             laminar_mu_kappa(ph, QL, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux(ph, QL, gx, gy, gz, mu, 0.0, kappa, FL);
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + 5 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + 5 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + 5 + q) * fs]; }
             laminar_mu_kappa(ph, QR, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], QR, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QR, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux(ph, QR, gx, gy, gz, mu, 0.0, kappa, FR);
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                             for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[q * es + go]; gy[q] = m.Uy[q * es + go]; gz[q] = m.Uz[q * es + go]; }
                         }
                         laminar_mu_kappa(ph, Qk[r], mu, kappa);
-                        if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.lesDelta[e], Qk[r], gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+                        if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.lesDelta[e], ph.wallModel ? m.dWall[go] : 0.0, Qk[r], gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
                         viscous_flux(ph, Qk[r], gx, gy, gz, mu, 0.0, kappa, F);
 #pragma unroll
                         for (int q = 0; q < 5; ++q)

@@ -12,7 +12,7 @@ namespace h3d {
 
 struct Phys {   // by-value kernel parameter (a trimmed H3dPhysics)
     double gamma, gm1, gammaM2, mu, mu_to_kappa, S_div_Tref, T_renorm, lambdaStab, Cs;
-    int ns, riemann, averaging, les;
+    int ns, riemann, averaging, les, wallModel;
 };
 
 __device__ __forceinline__ double pow2(double x) { return x * x; }
@@ -53,8 +53,9 @@ __device__ __forceinline__ void velocity_gradients(const double Q[5], const doub
     }
 }
 
-// libs/physics/common/LESModels.f90:256-305 Smagorinsky: mu_t = rho (Cs delta)^2 sqrt(2 S:S), S summed column by column
-__device__ __forceinline__ double smagorinsky(const Phys& ph, double delta, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5]) {
+// libs/physics/common/LESModels.f90:256-305 Smagorinsky: mu_t = rho LS^2 sqrt(2 S:S), S summed column by column;
+// LS = Cs delta, limited to 0.4 dWall by the linear wall model (LESModel_ComputeWallEffect, :189-203)
+__device__ __forceinline__ double smagorinsky(const Phys& ph, double delta, double dWall, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5]) {
     double ux[3], uy[3], uz[3];
     velocity_gradients(Q, Qx, Qy, Qz, ux, uy, uz);
     // S(i,j) = 1/2 (column j of grad u + row contribution), built exactly as the reference does
@@ -66,7 +67,8 @@ __device__ __forceinline__ double smagorinsky(const Phys& ph, double delta, cons
     sum = sum + s01 * s01; sum = sum + s11 * s11; sum = sum + s21 * s21;
     sum = sum + s02 * s02; sum = sum + s12 * s12; sum = sum + s22 * s22;
     const double normS = sqrt(2.0 * sum);
-    const double LS = ph.Cs * delta;
+    double LS = ph.Cs * delta;
+    if (ph.wallModel) LS = fmin(LS, dWall * 0.4);
     return Q[0] * pow2(LS) * normS;
 }
 

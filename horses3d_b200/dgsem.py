@@ -57,6 +57,11 @@ class DGSem:
             types = [P.BC_TYPES[b[1].lower()] for b in bcs]
             params = mesh.bc_params if mesh.bc_params is not None else np.zeros((len(bcs), 16))
             api.set_boundary_conditions(types, params)
+        if physics.les_wall_model:
+            dw, dwf = np.ascontiguousarray(mesh.array("dWall")), np.ascontiguousarray(mesh.array("faceDWall"))
+            if dw.size == 0:
+                raise ValueError("the LES wall model needs wall distances: call HostMesh.wall_distances() first")
+            api.call("set_wall_distance", _ptr(dw, np.float64), _ptr(dwf, np.float64))
         counts = mesh.array("haloCount")
         if len(counts) and hasattr(api, "set_halo"):
             api.set_halo(mesh.array("haloRank"), counts, mesh.array("haloFace"), mesh.array("haloSide"))

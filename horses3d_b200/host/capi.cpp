@@ -61,6 +61,13 @@ int h3dhost_mesh_geometry(void* hp, int N, int nodeType) {
     return 0;
 }
 
+int h3dhost_wall_distance(void* hp) {
+    Host* h = (Host*)hp;
+    if (!h->hasGeom) { g_err = "geometry has not been built"; return 1; }
+    computeWallDistances(h->mesh, h->geom);
+    return 0;
+}
+
 int h3dhost_mesh_sizes(void* hp, int* nElem, int* nFaces, int* nNodes, int* N) {
     Host* h = (Host*)hp;
     *nElem = h->mesh.nElem(); *nFaces = h->mesh.nFaces; *nNodes = h->mesh.nNodes(); *N = h->hasGeom ? h->geom.N : -1;
@@ -80,7 +87,7 @@ int h3dhost_get_array(void* hp, const char* name, void** ptr, long long* count, 
     DARR("x", h->geom.x) DARR("jGradXi", h->geom.jGradXi) DARR("jGradEta", h->geom.jGradEta) DARR("jGradZeta", h->geom.jGradZeta)
     DARR("jacobian", h->geom.jac) DARR("invJacobian", h->geom.invJac) DARR("volume", h->geom.volume)
     DARR("faceX", h->geom.fx) DARR("faceNormal", h->geom.fnormal) DARR("faceT1", h->geom.ft1) DARR("faceT2", h->geom.ft2)
-    DARR("faceJacobian", h->geom.fjac) DARR("faceSurface", h->geom.fsurface)
+    DARR("faceJacobian", h->geom.fjac) DARR("faceSurface", h->geom.fsurface) DARR("dWall", h->geom.dWall) DARR("faceDWall", h->geom.fdWall)
     IARR("haloRank", h->halo.rank) IARR("haloCount", h->halo.count) IARR("haloFace", h->halo.face) IARR("haloSide", h->halo.side)
     IARR("globalElem", h->halo.globalElem) IARR("globalFace", h->halo.globalFace)
 #undef DARR

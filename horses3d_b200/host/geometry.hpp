@@ -30,6 +30,7 @@ struct HostGeometry {
     std::vector<double> fx, fnormal, ft1, ft2;              // 3*n^2 per face
     std::vector<double> fjac;                               // n^2 per face
     std::vector<double> fsurface;                           // per face
+    std::vector<double> dWall, fdWall;                      // n^3 per element, n^2 per face (optional)
 };
 
 struct ElemMap {
@@ -278,6 +279,31 @@ inline void buildGeometry(const HostMesh& m, int N, int nodeType, HostGeometry& 
             g.fsurface[f] = surf;
         }
     }
+}
+
+// HexMesh_ComputeWallDistances / GatherAllWallCoordinates (HexMesh.f90:5594-5780): nearest no-slip wall node
+inline void computeWallDistances(const HostMesh& m, HostGeometry& g) {
+    const int n = g.n, n2 = n * n, n3 = n2 * n;
+    std::vector<double> Xw;
+    for (int f = 0; f < m.nFaces; ++f) {
+        if (m.faceType[f] != HMESH_BOUNDARY || m.faceZone[f] < 0 || m.bcs[m.faceZone[f]].type != "noslipwall") continue;
+        Xw.insert(Xw.end(), &g.fx[3 * (size_t)f * n2], &g.fx[3 * (size_t)f * n2] + 3 * n2);
+    }
+    const size_t nW = Xw.size() / 3;
+    auto dist = [&](const double* xP) {
+        double mn = 1.7976931348623157e308;
+        for (size_t q = 0; q < nW; ++q) {
+            const double d0 = xP[0] - Xw[3 * q], d1 = xP[1] - Xw[3 * q + 1], d2 = xP[2] - Xw[3 * q + 2];
+            const double cur = d0 * d0 + d1 * d1 + d2 * d2;
+            mn = std::fmin(mn, cur);
+        }
+        return std::sqrt(mn);
+    };
+    g.dWall.resize((size_t)m.nElem() * n3); g.fdWall.resize((size_t)m.nFaces * n2);
+#pragma omp parallel for schedule(static)
+    for (long long q = 0; q < (long long)g.dWall.size(); ++q) g.dWall[q] = dist(&g.x[3 * q]);
+#pragma omp parallel for schedule(static)
+    for (long long q = 0; q < (long long)g.fdWall.size(); ++q) g.fdWall[q] = dist(&g.fx[3 * q]);
 }
 
 }  // namespace h3d

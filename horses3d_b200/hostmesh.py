@@ -39,6 +39,7 @@ def lib():
         L.h3dhost_extract_partition.restype = C.c_void_p
         L.h3dhost_extract_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.h3dhost_inherit_geometry.argtypes = [C.c_void_p, C.c_void_p]
+        L.h3dhost_wall_distance.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -117,6 +118,11 @@ class HostMesh:
     def geometry(self, N, nodes=GAUSS):
         _check(lib().h3dhost_mesh_geometry(self._h, N, nodes))
         self.N, self.nodes = N, nodes
+        return self
+
+    def wall_distances(self):
+        """e % geom % dWall / f % geom % dWall: distance to the nearest no-slip wall node (HexMesh.f90:5594-5692)."""
+        _check(lib().h3dhost_wall_distance(self._h))
         return self
 
     def sizes(self):

@@ -20,11 +20,11 @@ class H3dPhysics(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "gamma", "gammaMinus1", "Mach", "Re", "Pr", "mu", "kappa", "mu_to_kappa", "gammaM2",
         "S_div_Tref", "T_renorm", "lambdaStab", "smagorinsky_Cs", "Prt")] + [(k, C.c_int) for k in (
-        "flowIsNavierStokes", "computeGradients", "inviscid", "riemann", "averaging", "les")] + [("reserved", C.c_int * 2)]
+        "flowIsNavierStokes", "computeGradients", "inviscid", "riemann", "averaging", "les", "les_wall_model", "reserved")]
 
 
 def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="standard", riemann="roe",
-                 averaging="standard", lambda_stab=1.0, compute_gradients=None, les="none", smagorinsky_cs=0.2,
+                 averaging="standard", lambda_stab=1.0, compute_gradients=None, les="none", smagorinsky_cs=0.2, les_wall_model="none",
                  sutherland_temperature=None, reference_temperature=None, sutherland_ref_temperature=None):
     p = H3dPhysics()
     gamma = 1.4
@@ -56,6 +56,7 @@ def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="
     p.lambdaStab = 0.0 if p.riemann == RIEMANN["central"] else lambda_stab    # RiemannSolvers_NS.f90:211-224
     p.les = LES[les.lower()]
     p.smagorinsky_Cs = smagorinsky_cs
+    p.les_wall_model = {"none": 0, "linear": 1}[les_wall_model.lower()]      # LESModels.f90:137-165
     return p
 
 

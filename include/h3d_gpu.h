@@ -98,7 +98,8 @@ typedef struct H3dPhysics {
     int riemann;             /* H3D_RIEMANN_*                                   */
     int averaging;           /* H3D_AVG_*                                       */
     int les;                 /* H3D_LES_*                                       */
-    int reserved[2];
+    int les_wall_model;      /* 0 = none (default), 1 = linear: LS = min(Cs*delta, 0.4*dWall), LESModels.f90:189-203 */
+    int reserved;
 } H3dPhysics;
 
 /* ---- life cycle ------------------------------------------------------------------------------
@@ -137,6 +138,10 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace,
                  const double* faceJacobian, /* [f][j][i]                                                       */
                  const double* faceX,      /* [f][j][i][3]  may be NULL                                        */
                  const double* faceSurface /* [f]           f % geom % surface (LES) - may be NULL             */);
+
+/* e % geom % dWall, f % geom % dWall (HexMesh_ComputeWallDistances, libs/mesh/HexMesh.f90:5594-5692): distance to the
+ * nearest no-slip wall node, [e][k][j][i] and [f][j][i].  Needed only with les_wall_model = 1. */
+int h3d_set_wall_distance(h3d_handle h, const double* dWallElem, const double* dWallFace);
 
 /* BCs(zone) % bc (libs/physics/common/BoundaryConditions.f90): type + 16 parameters per zone */
 int h3d_set_boundary_conditions(h3d_handle h, int nZones, const int* bcType, const double* bcParams);

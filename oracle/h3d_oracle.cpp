@@ -55,6 +55,7 @@ struct Oracle {
     std::vector<int> elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone;
     std::vector<double> JaXi, JaEta, JaZeta, jac, invJac, xyz, volume;
     std::vector<double> fNormal, fT1, fT2, fJac, fX, fSurface;
+    std::vector<double> dWall, fdWall;      // e % geom % dWall(i,j,k), f % geom % dWall(i,j)
     int nZones = 0; std::vector<int> bcType; std::vector<double> bcParams;
     // element storage (reference order [e][k][j][i][eq])
     std::vector<double> Q, QDot, G, S, Ux, Uy, Uz, mu;   // mu: [e][node][2] = (mu, kappa)
@@ -139,8 +140,8 @@ inline void getVelocityGradients_State(const double* Q, const double* Q_x, const
     }
 }
 
-// LESModels.f90:256-305 (Smagorinsky_ComputeViscosity; no wall model is the default, :162-165)
-inline double SmagorinskyViscosity(const Oracle& o, double delta, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z) {
+// LESModels.f90:256-305 (Smagorinsky_ComputeViscosity) with LESModel_ComputeWallEffect (:189-203); no wall model is the default (:162-165)
+inline double SmagorinskyViscosity(const Oracle& o, double delta, double dWall, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z) {
     double U_x[3], U_y[3], U_z[3], S[3][3];
     getVelocityGradients_State(Q, Q_x, Q_y, Q_z, U_x, U_y, U_z);
     for (int i = 0; i < 3; ++i) { S[i][0] = U_x[i]; S[i][1] = U_y[i]; S[i][2] = U_z[i]; }
@@ -151,6 +152,7 @@ inline double SmagorinskyViscosity(const Oracle& o, double delta, const double* 
     for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) { double sij = 0.5 * S[i][j]; sum = sum + sij * sij; }   // column-major sum(S*S)
     double normS = std::sqrt(2.0 * sum);
     double LS = o.ph.smagorinsky_Cs * delta;
+    if (o.ph.les_wall_model == 1) LS = std::fmin(LS, dWall * 0.4);   // K_VONKARMAN = 0.4 (LESModels.f90:31)
     return Q[IRHO] * POW2(LS) * normS;
 }
 
@@ -587,7 +589,7 @@ void computeQDot(Oracle& o, double time) {
                 size_t g = (size_t)e * n3 + q;
                 get_laminar_mu_kappa(o, &o.Q[5 * g], o.mu[2 * g], o.mu[2 * g + 1]);
                 if (o.ph.les == H3D_LES_SMAGORINSKY) {
-                    double mut = SmagorinskyViscosity(o, delta, &o.Q[5 * g], &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g]);
+                    double mut = SmagorinskyViscosity(o, delta, o.dWall.empty() ? 0.0 : o.dWall[g], &o.Q[5 * g], &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g]);
                     o.mu[2 * g] = o.mu[2 * g] + mut; o.mu[2 * g + 1] = o.mu[2 * g + 1] + mut * o.ph.mu_to_kappa;
                 }
             }
@@ -602,7 +604,7 @@ void computeQDot(Oracle& o, double time) {
                 size_t g = ix.fnode(f, s, i, j);
                 get_laminar_mu_kappa(o, &o.fQ[5 * g], o.fmu[2 * g], o.fmu[2 * g + 1]);
                 if (o.ph.les == H3D_LES_SMAGORINSKY) {
-                    double mut = SmagorinskyViscosity(o, delta, &o.fQ[5 * g], &o.fUx[5 * g], &o.fUy[5 * g], &o.fUz[5 * g]);
+                    double mut = SmagorinskyViscosity(o, delta, o.fdWall.empty() ? 0.0 : o.fdWall[(size_t)f * n * n + j * n + i], &o.fQ[5 * g], &o.fUx[5 * g], &o.fUy[5 * g], &o.fUz[5 * g]);
                     o.fmu[2 * g] = o.fmu[2 * g] + mut; o.fmu[2 * g + 1] = o.fmu[2 * g + 1] + mut * o.ph.mu_to_kappa;
                 }
             }
@@ -817,6 +819,12 @@ int orc_set_mesh(void* p, int nElem, int nFace, const int* elemFace, const int* 
 int orc_set_boundary_conditions(void* p, int nZones, const int* bcType, const double* bcParams) {
     Oracle& o = *(Oracle*)p;
     o.nZones = nZones; o.bcType.assign(bcType, bcType + nZones); o.bcParams.assign(bcParams, bcParams + 16 * (size_t)nZones);
+    return 0;
+}
+
+int orc_set_wall_distance(void* p, const double* dWallElem, const double* dWallFace) {
+    Oracle& o = *(Oracle*)p;
+    o.dWall.assign(dWallElem, dWallElem + (size_t)o.nElem * o.n3()); o.fdWall.assign(dWallFace, dWallFace + (size_t)o.nFace * o.n * o.n);
     return 0;
 }
 

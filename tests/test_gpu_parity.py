@@ -70,6 +70,8 @@ BC_CASES = [
     (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, les="smagorinsky")),
     (3, 2, GAUSS, 0.0, False, dict(flow="Euler", mach=0.3, riemann="lax-friedrichs")),
     (3, 3, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="pirozzoli", les="smagorinsky")),
+    (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, les="smagorinsky", les_wall_model="linear")),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, les="smagorinsky", les_wall_model="linear")),
 ]
 
 
@@ -79,6 +81,9 @@ def test_boundary_conditions_and_les_match_oracle(gpu_api_cls, ne, N, nodes, amp
     phys = make_physics(**kw)
     mesh = get_mesh(ne, N, nodes, amp, shuffle, bc="channel", phys=phys)
     assert (mesh.array("faceType") == P.FACE_BOUNDARY).sum() == 6 * ne * ne
+    if phys.les_wall_model:
+        dw = mesh.wall_distances().array("dWall")
+        assert dw.min() >= 0.0 and (0.4 * dw.min() < 0.2 * (mesh.array("volume").max() / (N + 1) ** 3) ** (1 / 3))   # the limiter is active
     (so, o), (sg, g) = run_pair(gpu_api_cls, mesh, phys, ic=lambda x: channel_state(x, phys))
     if kw.get("flow", "NS") != "Euler":
         for k in ("U_x", "U_y", "U_z"):

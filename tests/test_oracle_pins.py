@@ -49,15 +49,12 @@ def test_k1_taylor_green_5_steps():
 CYLINDER_MESH = "/root/reference/Solver/test/TestMeshes/CylinderNSpol3.mesh"
 
 
-@pytest.mark.skipif(not __import__("os").path.exists(CYLINDER_MESH), reason="reference test mesh not available on this machine")
-def test_k5_cylinder_100_steps():
-    """Solver/test/NavierStokes/Cylinder: Re 200, M 0.3, P=3 Gauss, Roe, BR1, RK3, cfl = dcfl = 0.3, 100 steps on the curved
-    (bFaceOrder 3) cylinder mesh with no-slip wall, free-slip walls, inflow and outflow.  Expected residuals and the
-    1e-11 tolerance from SETUP/ProblemFile.f90:551-575.  Pins the boundary conditions, the curved
-    transfinite geometry and the SpecMesh reader (multi-line records, curved patches)."""
+def _cylinder_100_steps(**phys_kw):
+    """Solver/test/NavierStokes/Cylinder*: Re 200, M 0.3, P=3 Gauss, Roe, BR1, RK3, cfl = dcfl = 0.3, 100 steps on the curved
+    (bFaceOrder 3) cylinder mesh with no-slip wall, free-slip walls, inflow and outflow."""
     import math
     from horses3d_b200.physics import bc_parameters
-    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe", **phys_kw)
     theta, phi = 0.0, 90.0 * (math.pi / 180.0)
     zones = [("innercylinder", "noslipwall"), ("bottom", "freeslipwall"), ("top", "freeslipwall"), ("back", "inflow"),
              ("left", "inflow"), ("front", "inflow"), ("right", "outflow")]
@@ -73,16 +70,40 @@ def test_k5_cylinder_100_steps():
             params.append(bc_parameters(t, phys))
     m = HostMesh.read(CYLINDER_MESH).connect([(z, t, None) for z, t in zones], np.array(params)).geometry(3, GAUSS)
     assert m.sizes()[:2] == (1864, 6182)
+    if phys.les_wall_model:
+        m.wall_distances()
     sem = DGSem(oracle_api.OracleApi(), m, phys)
     u, v, w = math.cos(theta) * math.cos(phi), math.sin(theta) * math.cos(phi), math.sin(phi)   # ProblemFile.f90:304-322
     Q = np.zeros(sem.node_coordinates().shape[:-1] + (5,))
     Q[..., 0], Q[..., 1], Q[..., 2], Q[..., 3] = 1.0, u, v, w
     Q[..., 4] = (1.0 / phys.gammaM2) / (phys.gamma - 1.0) + 0.5 * (u ** 2 + v ** 2 + w ** 2)
     sem.set_Q(Q)
-    rec = sem.integrate(100, cfl=0.3, dcfl=0.3, monitors=False)[-1]
+    return sem.integrate(100, cfl=0.3, dcfl=0.3, monitors=False)[-1]["residuals"]
+
+
+needs_cylinder_mesh = pytest.mark.skipif(not __import__("os").path.exists(CYLINDER_MESH), reason="reference test mesh not available on this machine")
+
+
+@needs_cylinder_mesh
+def test_k5_cylinder_100_steps():
+    """Expected residuals and the 1e-11 tolerance from test/NavierStokes/Cylinder/SETUP/ProblemFile.f90:551-575.  Pins the
+    boundary conditions, the curved transfinite geometry and the SpecMesh reader (multi-line records,
+    curved patches)."""
+    got = _cylinder_100_steps()
     res = np.array([8.8131248889811715E+00, 1.7608838068776613E+01, 1.9037533106262516E-01, 2.4301352846288605E+01, 2.4063786464536835E+02])
-    assert np.abs(rec["residuals"] - res).max() < 1.0e-11 * 240.0
-    assert np.abs((rec["residuals"] - res) / res).max() < 1.0e-11
+    assert np.abs(got - res).max() < 1.0e-11 * 240.0
+    assert np.abs((got - res) / res).max() < 1.0e-11
+
+
+@needs_cylinder_mesh
+def test_k5b_cylinder_smagorinsky_100_steps():
+    """test/NavierStokes/CylinderSmagorinsky (LES model = Smagorinsky, wall model = linear): residuals and the 1e-7
+    tolerance from SETUP/ProblemFile.f90:538-569.  Pins the Smagorinsky viscosity at elements and faces, the wall
+    distances (HexMesh.f90:5594-5692) and the linear wall model (LESModels.f90:189-203)."""
+    got = _cylinder_100_steps(les="smagorinsky", les_wall_model="linear")
+    res = np.array([7.58705681758851, 15.5542852761418, 0.231394835496677, 20.0848567943827, 207.594579145771])
+    print("K5b residuals", got, "rel diff", np.abs((got - res) / res).max())
+    assert np.abs(got - res).max() < 1.0e-7
 
 
 @pytest.mark.parametrize("nodes,inviscid,avg", [(GAUSS, "standard", "standard"), (GAUSSLOBATTO, "split-form", "pirozzoli"),
