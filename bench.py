@@ -220,8 +220,15 @@ def main_b200(args):
             ndof_local = sem.NDOF
             achieved = B_ALG_VOLUME_KERNEL(n) * ndof_local / (vol_ms * 1e-3) / 1e9
             stage_gbs = B_ALG_NS_STAGE(n) * value / world / 1e9
+            # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very workload
+            traffic, tsrc = None, None
+            tf = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tf) and world == 1:
+                rec = json.load(open(tf)).get("ne%d_P%d" % (args.ne, args.order))
+                if rec:
+                    traffic, tsrc = rec["k_volume_bytes_per_launch"], rec["source"]
             roof = {"bound": "hbm", "kernel": "k_volume<%d>" % n, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "avg_launch_ms": vol_ms,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc, "avg_launch_ms": vol_ms,
                     "alg_bytes_per_dof": B_ALG_VOLUME_KERNEL(n),
                     "per_kernel_ms": {"gradient": prof[0] / max(prof[1], 1), "riemann": prof[2] / max(prof[3], 1), "volume": vol_ms},
                     "stage": {"alg_bytes_per_dof_stage": B_ALG_NS_STAGE(n), "achieved": stage_gbs, "frac": stage_gbs / peak}}
