@@ -32,6 +32,7 @@ struct h3d_context {
     bool havePhysics = false, haveBasis = false, haveMesh = false;
     int N = -1, n = 0, nodeType = H3D_GAUSS;
     std::vector<double> hx;   // node positions of the 1-D set (MaxTimeStep)
+    std::vector<double> hHatD, hD, hV, hB;   // host copies of the operators (kernel-parameter Ops<n>)
     int nElem = 0, nFace = 0, nSeq = 0;          // device order: [0,nSeq) interior elements, [nSeq,nElem) MPI elements
     int nFaceLocal = 0;                           // device face order: [0,nFaceLocal) interior+boundary, then MPI faces
     std::vector<int> permE, invPermE, permF, invPermF;   // device index -> host index and inverse
@@ -265,19 +266,25 @@ int persistentGrid(h3d_context* h, const void* fn, int threads, size_t smemBytes
     return perSM * h->numSMs;
 }
 
+template <int n> Ops<n> makeOps(const h3d_context* h) {
+    Ops<n> o;
+    std::memcpy(o.hatD, h->hHatD.data(), sizeof(o.hatD)); std::memcpy(o.D, h->hD.data(), sizeof(o.D));
+    std::memcpy(o.v, h->hV.data(), sizeof(o.v)); std::memcpy(o.b, h->hB.data(), sizeof(o.b));
+    return o;
+}
 template <int n> int launchProlong(h3d_context* h, int e0, int e1, cudaStream_t s) {
     if (e1 <= e0) return 0;
     using C = KCfg<n>;
     const int blocks = (e1 - e0 + C::EPB - 1) / C::EPB;
-    k_prolong_q<n><<<blocks, C::NT, smemProlong<n>(), s>>>(h->m, e0, e1);
+    k_prolong_q<n><<<blocks, C::NT, smemProlong<n>(), s>>>(h->m, makeOps<n>(h), e0, e1);
     ++h->launches; return 0;
 }
 template <int n> int launchGradient(h3d_context* h, int e0, int e1, cudaStream_t s) {
     if (e1 <= e0) return 0;
     using C = KCfg<n>;
     const int tiles = (e1 - e0 + C::EPB - 1) / C::EPB;
-    if (C::TMA_OK && h->useTma) k_gradient<n, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient<n, C::TMA_OK>, C::NT, smemGradient<n, C::TMA_OK>())), C::NT, smemGradient<n, C::TMA_OK>(), s>>>(h->m, h->ph, e0, e1);
-    else k_gradient<n, false><<<tiles, C::NT, smemGradient<n, false>(), s>>>(h->m, h->ph, e0, e1);
+    if (C::TMA_OK && h->useTma) k_gradient<n, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient<n, C::TMA_OK>, C::NT, smemGradient<n, C::TMA_OK>())), C::NT, smemGradient<n, C::TMA_OK>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
+    else k_gradient<n, false><<<tiles, C::NT, smemGradient<n, false>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
     ++h->launches; return 0;
 }
 template <int n> int launchRiemann(h3d_context* h, int f0, int f1, cudaStream_t s) {
@@ -294,11 +301,11 @@ template <int n> int launchVolume(h3d_context* h, const RkArgs& rk, int e0, int 
     const bool tma = C::TMA_OK && h->useTma;
     if (h->physics.inviscid == H3D_SPLIT_DG) {
         // the staged-input variant of SplitDG + Navier-Stokes does not fit 227 KB: plain loads there
-        if (tma && !ns) k_volume<n, true, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, true, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(true, false))), C::NT, smemVolume<n, C::TMA_OK>(true, false), s>>>(h->m, h->ph, rk, e0, e1);
-        else k_volume<n, true, false><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, e0, e1);
+        if (tma && !ns) k_volume<n, true, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, true, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(true, false))), C::NT, smemVolume<n, C::TMA_OK>(true, false), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+        else k_volume<n, true, false><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
     } else {
-        if (tma) k_volume<n, false, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, false, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(false, ns))), C::NT, smemVolume<n, C::TMA_OK>(false, ns), s>>>(h->m, h->ph, rk, e0, e1);
-        else k_volume<n, false, false><<<tiles, C::NT, smemVolume<n, false>(false, true), s>>>(h->m, h->ph, rk, e0, e1);
+        if (tma) k_volume<n, false, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, false, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(false, ns))), C::NT, smemVolume<n, C::TMA_OK>(false, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+        else k_volume<n, false, false><<<tiles, C::NT, smemVolume<n, false>(false, true), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
     }
     ++h->launches; return 0;
 }
@@ -537,6 +544,7 @@ int h3d_set_basis(h3d_handle h, int N, int nodeType, const double* x, const doub
     CTX_CHECK(cudaSetDevice(h->device));
     const int n = N + 1;
     h->N = N; h->n = n; h->nodeType = nodeType; h->hx.assign(x, x + n);
+    h->hHatD.assign(hatD, hatD + n * n); h->hD.assign(D, D + n * n); h->hV.assign(v, v + 2 * n); h->hB.assign(b, b + 2 * n);
     std::vector<double> T(n * n);
     auto up = [&](const double* src, size_t cnt, const double** dst) -> int {
         double* d; if (devAlloc(h, &d, cnt)) return 2;

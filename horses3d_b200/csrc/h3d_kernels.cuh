@@ -87,43 +87,61 @@ __device__ __forceinline__ int faceEnd(int lf) { return (lf == 1 || lf == 3 || l
 // accumulated in ascending l from zero; Face_AdaptSolutionToFace: left copies, right is re-indexed.
 // sTr[le][6][n2]: face-field offset of every element-trace node; sInfo[le][6]: side / type bits of the element's faces.
 // ---------------------------------------------------------------------------------------------------------
-template <int n, int STRIDE>
-__device__ __forceinline__ void trace_line(const double* __restrict__ src, const double (&v0)[n], const double (&v1)[n], double& acc0, double& acc1) {
-    acc0 = 0.0; acc1 = 0.0;
+// Operator entries passed as a kernel parameter: after unrolling, every use is a constant-bank operand of the FP64
+// instruction (no shared-memory load, no address arithmetic).  Row-major: M[i*n + l] = M(i,l); v,b: [end*n + l].
+template <int n>
+struct Ops { double hatD[n * n], D[n * n], v[2 * n], b[2 * n]; };
+
+// traces of field line `src` (n values, stride STRIDE) on the two opposite faces of axis AX
+template <int n, int NV, int AX>
+__device__ __forceinline__ void prolong_axis(const DevMesh& m, const Ops<n>& ops, const double* __restrict__ sF, const int* __restrict__ sTr,
+                                             const int* __restrict__ sInfo, double* __restrict__ dst, int nLocal) {
+    using C = KCfg<n>;
+    constexpr int N2 = C::N2, NP = C::NP, NS = C::NS, NT = C::NT, EPB = C::EPB, ROWS = NT / N2;
+    constexpr int STRIDE = AX == 0 ? 1 : (AX == 1 ? NP : n * NP);
+    constexpr int LF0 = AX == 0 ? 5 : (AX == 1 ? 0 : 2), LF1 = AX == 0 ? 3 : (AX == 1 ? 1 : 4);   // LEFT,RIGHT | FRONT,BACK | BOTTOM,TOP
+    const size_t fstride = (size_t)m.nFace * N2;
+    const int ab = threadIdx.x % N2, a = ab % n, b = ab / n;
+    const int base = AX == 0 ? (b * n + a) * NP : (AX == 1 ? (b * n) * NP + a : b * NP + a);
+    auto facePtr = [&](int le, int lf) {
+        const int side = sInfo[le * 6 + lf] & 1;
+        return dst + (size_t)(side * 5) * fstride + sTr[(le * 6 + lf) * N2 + ab];
+    };
+    auto line = [&](const double* __restrict__ src, double& acc0, double& acc1) {
+        acc0 = 0.0; acc1 = 0.0;
 #pragma unroll
-    for (int l = 0; l < n; ++l) { const double sv = src[l * STRIDE]; acc0 = acc0 + sv * v0[l]; acc1 = acc1 + sv * v1[l]; }
+        for (int l = 0; l < n; ++l) { const double sv = src[l * STRIDE]; acc0 = acc0 + sv * ops.v[l]; acc1 = acc1 + sv * ops.v[n + l]; }
+    };
+    if (EPB == 1) {
+        double* p0 = facePtr(0, LF0); double* p1 = facePtr(0, LF1);
+#pragma unroll 2
+        for (int vv = threadIdx.x / N2; vv < NV; vv += ROWS) {
+            double acc0, acc1;
+            line(sF + vv * NS + base, acc0, acc1);
+            const size_t fo = (size_t)((vv / 5) * 10 + vv % 5) * fstride;
+            p0[fo] = acc0; p1[fo] = acc1;
+        }
+    } else {
+        for (int row = threadIdx.x / N2; row < nLocal * NV; row += ROWS) {
+            const int vv = row % NV, le = row / NV;
+            double acc0, acc1;
+            line(sF + (le * NV + vv) * NS + base, acc0, acc1);
+            const size_t fo = (size_t)((vv / 5) * 10 + vv % 5) * fstride;
+            facePtr(le, LF0)[fo] = acc0; facePtr(le, LF1)[fo] = acc1;
+        }
+    }
 }
 
 template <int n, int NV>
-__device__ __forceinline__ void prolong_block(const DevMesh& m, const double* __restrict__ sF, const double* __restrict__ sV,
+__device__ __forceinline__ void prolong_block(const DevMesh& m, const Ops<n>& ops, const double* __restrict__ sF,
                                               const int* __restrict__ sTr, const int* __restrict__ sInfo, double* __restrict__ dst, int nLocal) {
     // One work item = (element, axis, field, trace node): the line of n values along the axis is read once from shared
     // memory and contracted with both end vectors, giving the traces on the two opposite faces of that axis.
-    // The trace node ab of a thread is fixed (NT is a multiple of n^2); items advance over (element, axis, field).
-    using C = KCfg<n>;
-    constexpr int N2 = C::N2, NP = C::NP, NS = C::NS, NT = C::NT, ROWS = NT / N2;
-    static_assert(NT % N2 == 0, "threads per CTA must be a multiple of n^2");
-    const size_t fstride = (size_t)m.nFace * N2;
-    double v0[n], v1[n];
-#pragma unroll
-    for (int l = 0; l < n; ++l) { v0[l] = sV[l]; v1[l] = sV[n + l]; }
-    const int ab = threadIdx.x % N2, a = ab % n, b = ab / n;
-    const int base0 = (b * n + a) * NP, base1 = (b * n) * NP + a, base2 = b * NP + a;
-    const int rows = nLocal * 3 * NV;
-    for (int row = threadIdx.x / N2; row < rows; row += ROWS) {
-        const int vv = row % NV; const int r = row / NV;
-        const int ax = r % 3, le = r / 3;
-        const double* src = sF + ((size_t)le * NV + vv) * NS;
-        double acc0, acc1;
-        int lf0, lf1;
-        if (ax == 0) { trace_line<n, 1>(src + base0, v0, v1, acc0, acc1); lf0 = 5; lf1 = 3; }             // LEFT, RIGHT
-        else if (ax == 1) { trace_line<n, NP>(src + base1, v0, v1, acc0, acc1); lf0 = 0; lf1 = 1; }       // FRONT, BACK
-        else { trace_line<n, n * NP>(src + base2, v0, v1, acc0, acc1); lf0 = 2; lf1 = 4; }                // BOTTOM, TOP
-        const size_t fo = (size_t)((vv / 5) * 10 + vv % 5) * fstride;
-        const int s0 = sInfo[le * 6 + lf0] & 1, s1 = sInfo[le * 6 + lf1] & 1;
-        dst[fo + (size_t)(s0 * 5) * fstride + sTr[(le * 6 + lf0) * N2 + ab]] = acc0;
-        dst[fo + (size_t)(s1 * 5) * fstride + sTr[(le * 6 + lf1) * N2 + ab]] = acc1;
-    }
+    // The trace node ab of a thread is fixed (NT is a multiple of n^2); items advance over (element, field).
+    static_assert(KCfg<n>::NT % KCfg<n>::N2 == 0, "threads per CTA must be a multiple of n^2");
+    prolong_axis<n, NV, 0>(m, ops, sF, sTr, sInfo, dst, nLocal);
+    prolong_axis<n, NV, 1>(m, ops, sF, sTr, sInfo, dst, nLocal);
+    prolong_axis<n, NV, 2>(m, ops, sF, sTr, sInfo, dst, nLocal);
 }
 
 template <int n>
@@ -134,7 +152,7 @@ __device__ __forceinline__ void load_face_tables(const DevMesh& m, int* sTr, int
 
 // Stand-alone prolongation of Q (first residual after an upload).
 template <int n>
-__global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, int eBegin, int eEnd) {
+__global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
     constexpr int N3 = C::N3, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE;
     extern __shared__ double smem[];
@@ -160,7 +178,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, int eBegin
         }
     }
     __syncthreads();
-    prolong_block<n, 5>(m, sQ, sV, sTr, sInfo, m.fQ, nLocal);
+    prolong_block<n, 5>(m, ops, sQ, sTr, sInfo, m.fQ, nLocal);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -222,7 +240,7 @@ __device__ __forceinline__ void grad_iface_store(const DevMesh& m, const Phys& p
 }
 
 template <int n, bool TMA>
-__global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh m, Phys ph, int eBegin, int eEnd) {
+__global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh m, Phys ph, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
     constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;                  // nodes of one tile
@@ -409,7 +427,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
             }
             havePrefetch = true;
         }
-        prolong_block<n, 15>(m, sG, sV, sTr, sInfo, m.fU, nLocal);
+        prolong_block<n, 15>(m, ops, sG, sTr, sInfo, m.fU, nLocal);
         __syncthreads();
     }
 }
@@ -505,7 +523,7 @@ struct VolSmem {
 };
 
 template <int n, bool SPLIT, bool TMA>
-__global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m, Phys ph, RkArgs rk, int eBegin, int eEnd) {
+__global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m, Phys ph, RkArgs rk, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
     constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;
@@ -775,7 +793,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                 }
             }
             __syncthreads();
-            prolong_block<n, 5>(m, sP, sV, sTr, sInfo, m.fQ, nLocal);
+            prolong_block<n, 5>(m, ops, sP, sTr, sInfo, m.fQ, nLocal);
         }
         __syncthreads();
         if (TMA && threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issueLate(tile + gridDim.x);   // J/G buffer is free again
