@@ -604,7 +604,7 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
     for (int pass = 0; pass < 2; ++pass) for (int f = 0; f < nFace; ++f) if ((faceType[f] == H3D_FACE_MPI) == (pass == 1)) { h->invPermF[f] = (int)h->permF.size(); h->permF.push_back(f); }
     h->nFaceLocal = 0; for (int f = 0; f < nFace; ++f) if (faceType[f] != H3D_FACE_MPI) ++h->nFaceLocal;
     // ---- connectivity tables
-    std::vector<int> eFace(6 * (size_t)nElem), eInfo(6 * (size_t)nElem), fInfo(nFace);
+    std::vector<int> eFace(6 * (size_t)nElem), eInfo(8 * (size_t)nElem, 0), fInfo(nFace);
     for (int ed = 0; ed < nElem; ++ed) {
         const int eh = h->permE[ed];
         for (int lf = 0; lf < 6; ++lf) {
@@ -612,7 +612,7 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
             if (f < 0 || f >= nFace || side < 0 || side > 1) { h->err = "invalid element->face table"; return 1; }
             const int ridx = side ? faceRot[f] : 0;
             eFace[6 * (size_t)ed + lf] = h->invPermF[f];
-            eInfo[6 * (size_t)ed + lf] = side | (ridx << 1) | (faceType[f] << 4) | ((faceZone[f] + 1) << 8);
+            eInfo[8 * (size_t)ed + lf] = side | (ridx << 1) | (faceType[f] << 4) | ((faceZone[f] + 1) << 8);
         }
     }
     for (int fd = 0; fd < nFace; ++fd) { const int fh = h->permF[fd]; fInfo[fd] = faceType[fh] | ((faceZone[fh] + 1) << 8); }
@@ -628,7 +628,7 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
         const int N = n - 1;
         std::vector<int> tr((size_t)nElem * 6 * n2);
         for (int ed = 0; ed < nElem; ++ed) for (int lf = 0; lf < 6; ++lf) {
-            const int fd = eFace[6 * (size_t)ed + lf], ridx = (eInfo[6 * (size_t)ed + lf] >> 1) & 7;
+            const int fd = eFace[6 * (size_t)ed + lf], ridx = (eInfo[8 * (size_t)ed + lf] >> 1) & 7;
             for (int jj = 0; jj < n; ++jj) for (int ii = 0; ii < n; ++ii) {
                 int i, j;   // inverse of leftIndexes2Right: element-trace node (ii,jj) -> face node (i,j)
                 switch (ridx) {

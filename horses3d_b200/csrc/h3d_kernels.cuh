@@ -34,7 +34,7 @@ struct DevMesh {
     const double* lesDelta;                // [nElem]  (V/n^3)^(1/3)
     const double *dWall, *fDWall;          // [nElem][n3], [nFace][n2] wall distances (LES wall model) or nullptr
     const int* elemFace;                   // [nElem][6] device face id
-    const int* elemInfo;                   // [nElem][6] bit0 side | bits1-3 rotation index | bits4-5 face type | bits 8.. zone+1
+    const int* elemInfo;                   // [nElem][8] (6 used; 32-byte records for bulk copies) bit0 side | bits1-3 rotation index | bits4-5 face type | bits 8.. zone+1
     const int* elemTrace;                  // [nElem][6][n2] face-field offset f*n2 + rotmap[r][ab] of every element-trace node
     // face fields
     double *fQ, *fU, *fStar;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void prolong_axis(const DevMesh& m, const Ops<n>& ops
     const int ab = threadIdx.x % N2, a = ab % n, b = ab / n;
     const int base = AX == 0 ? (b * n + a) * NP : (AX == 1 ? (b * n) * NP + a : b * NP + a);
     auto facePtr = [&](int le, int lf) {
-        const int side = sInfo[le * 6 + lf] & 1;
+        const int side = sInfo[le * 8 + lf] & 1;
         return dst + (size_t)(side * 5) * fstride + sTr[(le * 6 + lf) * N2 + ab];
     };
     auto line = [&](const double* __restrict__ src, double& acc0, double& acc1) {
@@ -146,7 +146,7 @@ __device__ __forceinline__ void prolong_block(const DevMesh& m, const Ops<n>& op
 
 template <int n>
 __device__ __forceinline__ void load_face_tables(const DevMesh& m, int* sTr, int* sInfo, int e0, int nLocal) {
-    for (int t = threadIdx.x; t < nLocal * 6; t += blockDim.x) sInfo[t] = m.elemInfo[(size_t)e0 * 6 + t];
+    for (int t = threadIdx.x; t < nLocal * 8; t += blockDim.x) sInfo[t] = m.elemInfo[(size_t)e0 * 8 + t];
     for (int t = threadIdx.x; t < nLocal * 6 * n * n; t += blockDim.x) sTr[t] = m.elemTrace[(size_t)e0 * 6 * n * n + t];
 }
 
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, const __gr
     double* sQ = smem;                  // [EPB][5][NS]
     double* sV = sQ + EPB * 5 * NS;     // [2][n]
     int* sTr = (int*)(sV + 2 * n);      // [EPB][6][N2]
-    int* sInfo = sTr + EPB * 6 * C::N2; // [EPB][6]
+    int* sInfo = sTr + EPB * 6 * C::N2; // [EPB][8]
     const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const int e0 = eBegin + blockIdx.x * EPB, e = e0 + le;
     const int nLocal = min(EPB, eEnd - e0);
@@ -199,7 +199,7 @@ struct GradSmem {
     static constexpr int phase1 = C::EPB * (5 * C::NS + 6 * 9 * C::N2);
     static constexpr int phase2 = C::EPB * 15 * C::NS;
     static constexpr int fields = TMA ? C::EPB * (15 * C::N3 + 6 * 9 * C::N2 + 15 * C::NS) : (phase1 > phase2 ? phase1 : phase2);
-    static constexpr size_t bytes = sizeof(double) * (fields + C::N2 + 4 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 6) + 16;
+    static constexpr size_t bytes = sizeof(double) * (fields + C::N2 + 4 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 8) + 16;
 };
 
 // interface data of one element-trace node: raw loads (issued early) and their reduction to uStar / normal / J_f
@@ -209,7 +209,7 @@ template <int n>
 __device__ __forceinline__ void grad_iface_load(const DevMesh& m, int e, int lf, int ab, GradIface& g) {
     constexpr int N2 = n * n;
     const size_t fs = (size_t)m.nFace * N2;
-    g.info = m.elemInfo[(size_t)e * 6 + lf];
+    g.info = m.elemInfo[(size_t)e * 8 + lf];
     const size_t fo = (size_t)m.elemTrace[((size_t)e * 6 + lf) * N2 + ab];
     g.Jf = m.fJ[fo];
 #pragma unroll
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
     double* sB = sDT + N2;
     double* sV = sB + 2 * n;
     int* sTr = (int*)(sV + 2 * n);                              // [EPB][6][N2]
-    int* sInfo = sTr + EPB * 6 * N2;                            // [EPB][6]
-    uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 6) + 7) & ~(uintptr_t)7);
+    int* sInfo = sTr + EPB * 6 * N2;                            // [EPB][8]
+    uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 8) + 7) & ~(uintptr_t)7);
     const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const size_t es = (size_t)m.nElem * N3;
     const int nTiles = (eEnd - eBegin + EPB - 1) / EPB;
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                         const double bb = sB[faceEnd(lf) * n + idxOf[lf]];
                         const double* H = sH + ((le * 6 + lf) * 5) * N2 + ab;
                         const double* Nn = sNrm + ((le * 6 + lf) * 4) * N2 + ab;
-                        const bool bnd = ((sInfo[le * 6 + lf] >> 4) & 3) == H3D_FACE_BOUNDARY;
+                        const bool bnd = ((sInfo[le * 8 + lf] >> 4) & 3) == H3D_FACE_BOUNDARY;
                         const double Jfb = Nn[3 * N2];
                         const double n0 = Nn[0], n1 = Nn[N2], n2 = Nn[2 * N2];
 #pragma unroll
@@ -519,7 +519,8 @@ struct VolSmem {
     __host__ __device__ static constexpr int fields(bool split, bool ns) {
         return C::EPB * (stagedFields(ns) * C::N3 + (fluxFields(split, ns) + (split ? 14 : 0)) * C::NS + 30 * C::N2);
     }
-    static size_t bytes(bool split, bool ns) { return sizeof(double) * (fields(split, ns) + 2 * C::N2 + 4 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 6) + 32; }
+    // face tables: one copy, or two (prefetched by bulk copies) in the staged variant; 4 mbarriers
+    static size_t bytes(bool split, bool ns) { return sizeof(double) * (fields(split, ns) + 2 * C::N2 + 2 * n) + sizeof(int) * (TMA ? 2 : 1) * C::EPB * (6 * C::N2 + 8) + 48; }
 };
 
 template <int n, bool SPLIT, bool TMA>
@@ -541,17 +542,24 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
     double* sHatDT = sFs + EPB * 6 * 5 * N2;             // [n][n]
     double* sSharpDT = sHatDT + N2;                      // [n][n]
     double* sB = sSharpDT + N2;                          // [2][n]
-    double* sV = sB + 2 * n;                             // [2][n]
-    int* sTr = (int*)(sV + 2 * n);                       // [EPB][6][N2]
-    int* sInfo = sTr + EPB * 6 * N2;                     // [EPB][6]
-    uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 6) + 7) & ~(uintptr_t)7);   // bar[0]: flux inputs, bar[1]: J and G
+    constexpr int TABI = EPB * (6 * N2 + 8);             // ints of one face-table set: trace offsets [EPB][6][N2] + info [EPB][8]
+    int* sTab = (int*)(sB + 2 * n);                      // TMA: two sets, the next tile's is prefetched by bulk copies
+    uint64_t* bar = (uint64_t*)(((uintptr_t)(sTab + (TMA ? 2 : 1) * TABI) + 7) & ~(uintptr_t)7);   // bar[0]: flux inputs, bar[1]: J and G, bar[2..3]: face tables
     double* sP = SPLIT ? sQ : sF;                        // prolongation buffer for the updated state [EPB][5][NS]
     const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const size_t es = (size_t)m.nElem * N3, fs = (size_t)m.nFace * N2;
     const int nTiles = (eEnd - eBegin + EPB - 1) / EPB;
     const int jaOff = ns ? 20 : 5;                       // first metric field inside sIn
     for (int t = threadIdx.x; t < N2; t += blockDim.x) { sHatDT[t] = m.hatDT[t]; if (SPLIT) sSharpDT[t] = m.sharpDT[t]; }
-    if (threadIdx.x < 2 * n) { sB[threadIdx.x] = m.b[threadIdx.x]; sV[threadIdx.x] = m.v[threadIdx.x]; }
+    if (threadIdx.x < 2 * n) sB[threadIdx.x] = m.b[threadIdx.x];
+    auto issueTab = [&](int tile, int buf) {   // thread 0: face tables of the tile
+        const int e0 = eBegin + tile * EPB;
+        const int nLoc = min(EPB, eEnd - e0);
+        int* dst = sTab + buf * TABI;
+        mbar_arrive_expect_tx(bar + 2 + buf, (uint32_t)(nLoc * (6 * N2 + 8) * sizeof(int)));
+        bulk_g2s(dst, m.elemTrace + (size_t)e0 * 6 * N2, (uint32_t)(nLoc * 6 * N2 * sizeof(int)), bar + 2 + buf);
+        bulk_g2s(dst + EPB * 6 * N2, m.elemInfo + (size_t)e0 * 8, (uint32_t)(nLoc * 8 * sizeof(int)), bar + 2 + buf);
+    };
     auto issue = [&](int tile) {   // thread 0: bulk copies of the tile's staged fields
         const int e0 = eBegin + tile * EPB;
         const int nLoc = min(EPB, eEnd - e0);
@@ -582,16 +590,28 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
         for (int c = 0; c < 5; ++c) bulk_g2s(sJG + (1 + c) * TN3, m.G + c * es + off, bytes, bar + 1);
     };
     if (TMA) {
-        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); }
+        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); fence_barrier_init(); }
         __syncthreads();
-        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) { issue(blockIdx.x); issueLate(blockIdx.x); }
+        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) { issueTab(blockIdx.x, 0); issue(blockIdx.x); issueLate(blockIdx.x); }
     }
     uint32_t parity = 0;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++iter) {
         const int e0 = eBegin + tile * EPB, e = e0 + le;
         const int nLocal = min(EPB, eEnd - e0);
         const bool active = e < eEnd;
-        load_face_tables<n>(m, sTr, sInfo, e0, nLocal);
+        const int tbuf = TMA ? (iter & 1) : 0;
+        int* sTr = sTab + tbuf * TABI;                   // [EPB][6][N2]
+        int* sInfo = sTr + EPB * 6 * N2;                 // [EPB][8]
+        if (TMA) {
+            // this tile's tables were copied during the previous tile; the other set was last read by the previous
+            // tile's prolongation, which the barrier at the end of the tile has closed
+            if (threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issueTab(tile + gridDim.x, tbuf ^ 1);
+            mbar_wait(bar + 2 + tbuf, (uint32_t)((iter >> 1) & 1));
+        } else {
+            load_face_tables<n>(m, sTr, sInfo, e0, nLocal);
+            __syncthreads();
+        }
         // interface fluxes of the six faces at element-trace nodes: raw loads issued now, signed (left +, right -,
         // FaceClass.f90:681-690) and stored to shared memory after the flux phase
         double fsv[FSI]; int fsg[FSI];
@@ -602,8 +622,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
             if (o < nLocal * 30 * N2) {
                 const int ab = o % N2; int r = o / N2;
                 const int q = r % 5; r /= 5;                 // r = l2*6 + lf
-                fsg[it] = m.elemInfo[(size_t)e0 * 6 + r];
-                fsv[it] = m.fStar[(size_t)q * fs + m.elemTrace[((size_t)e0 * 6 + r) * N2 + ab]];
+                fsg[it] = sInfo[(r / 6) * 8 + r % 6];
+                fsv[it] = m.fStar[(size_t)q * fs + sTr[r * N2 + ab]];
             }
         }
         if (TMA) { mbar_wait(bar, parity); parity ^= 1; }
@@ -801,7 +821,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 }
 
 // shared-memory footprints (bytes)
-template <int n> inline size_t smemProlong() { using C = KCfg<n>; return sizeof(double) * ((size_t)C::EPB * 5 * C::NS + 2 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 6); }
+template <int n> inline size_t smemProlong() { using C = KCfg<n>; return sizeof(double) * ((size_t)C::EPB * 5 * C::NS + 2 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 8); }
 template <int n, bool TMA> inline size_t smemGradient() { return GradSmem<n, TMA>::bytes; }
 template <int n, bool TMA> inline size_t smemVolume(bool split, bool ns) { return VolSmem<n, TMA>::bytes(split, ns); }
 
