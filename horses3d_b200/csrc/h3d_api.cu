@@ -32,6 +32,7 @@ struct h3d_context {
     bool havePhysics = false, haveBasis = false, haveMesh = false;
     int N = -1, n = 0, nodeType = H3D_GAUSS;
     std::vector<double> hx;   // node positions of the 1-D set (MaxTimeStep)
+    bool extPhysics = false;   // a Riemann solver / average outside the base set: kernels instantiated with EXT
     std::vector<double> hHatD, hD, hV, hB;   // host copies of the operators (kernel-parameter Ops<n>)
     int nElem = 0, nFace = 0, nSeq = 0;          // device order: [0,nSeq) interior elements, [nSeq,nElem) MPI elements
     int nFaceLocal = 0;                           // device face order: [0,nFaceLocal) interior+boundary, then MPI faces
@@ -290,7 +291,8 @@ template <int n> int launchGradient(h3d_context* h, int e0, int e1, cudaStream_t
 template <int n> int launchRiemann(h3d_context* h, int f0, int f1, cudaStream_t s) {
     if (f1 <= f0) return 0;
     const long long threads = (long long)(f1 - f0) * n * n;
-    k_riemann<n><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(h->m, h->ph, f0, f1);
+    if (h->extPhysics) k_riemann<n, true><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(h->m, h->ph, f0, f1);
+    else k_riemann<n, false><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(h->m, h->ph, f0, f1);
     ++h->launches; return 0;
 }
 template <int n> int launchVolume(h3d_context* h, const RkArgs& rk, int e0, int e1, cudaStream_t s) {
@@ -299,13 +301,15 @@ template <int n> int launchVolume(h3d_context* h, const RkArgs& rk, int e0, int 
     const int tiles = (e1 - e0 + C::EPB - 1) / C::EPB;
     const bool ns = h->ph.ns != 0;
     const bool tma = C::TMA_OK && h->useTma;
-    if (h->physics.inviscid == H3D_SPLIT_DG) {
+    if (h->physics.inviscid == H3D_SPLIT_DG && h->extPhysics) {
+        k_volume<n, 2, false><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+    } else if (h->physics.inviscid == H3D_SPLIT_DG) {
         // the staged-input variant of SplitDG + Navier-Stokes does not fit 227 KB: plain loads there
-        if (tma && !ns) k_volume<n, true, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, true, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(true, false))), C::NT, smemVolume<n, C::TMA_OK>(true, false), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
-        else k_volume<n, true, false><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+        if (tma && !ns) k_volume<n, 1, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, 1, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(true, false))), C::NT, smemVolume<n, C::TMA_OK>(true, false), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+        else k_volume<n, 1, false><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
     } else {
-        if (tma) k_volume<n, false, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, false, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(false, ns))), C::NT, smemVolume<n, C::TMA_OK>(false, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
-        else k_volume<n, false, false><<<tiles, C::NT, smemVolume<n, false>(false, true), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+        if (tma) k_volume<n, 0, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, 0, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(false, ns))), C::NT, smemVolume<n, C::TMA_OK>(false, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+        else k_volume<n, 0, false><<<tiles, C::NT, smemVolume<n, false>(false, true), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
     }
     ++h->launches; return 0;
 }
@@ -314,13 +318,14 @@ template <int n> int setAttrs(h3d_context* h) {
     using C = KCfg<n>;
     CTX_CHECK(cudaFuncSetAttribute(k_prolong_q<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemProlong<n>()));
     CTX_CHECK(cudaFuncSetAttribute(k_gradient<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient<n, false>()));
-    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, false>(false, true)));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, false>(false, true)));
     // SplitDG: the Navier-Stokes variant (29 padded fields) does not fit 227 KB at n = 10; the Euler variant (14 fields) does
-    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smemVolume<n, false>(true, true), SMEM_LIMIT)));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smemVolume<n, false>(true, true), SMEM_LIMIT)));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smemVolume<n, false>(true, true), SMEM_LIMIT)));
     if (C::TMA_OK) {
         CTX_CHECK(cudaFuncSetAttribute(k_gradient<n, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient<n, C::TMA_OK>()));
-        CTX_CHECK(cudaFuncSetAttribute(k_volume<n, false, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, C::TMA_OK>(false, true)));
-        CTX_CHECK(cudaFuncSetAttribute(k_volume<n, true, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, C::TMA_OK>(true, false)));
+        CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 0, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, C::TMA_OK>(false, true)));
+        CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 1, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, C::TMA_OK>(true, false)));
     }
     return 0;
 }
@@ -524,14 +529,15 @@ int h3d_last_error_copy(h3d_handle h, char* buf, int len) {
 }
 
 int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
-    if (p->riemann != H3D_RIEMANN_ROE && p->riemann != H3D_RIEMANN_LXF && p->riemann != H3D_RIEMANN_CENTRAL) { h->err = "Riemann Solver not recognized."; return 1; }
-    if (p->averaging != H3D_AVG_STANDARD && p->averaging != H3D_AVG_KENNEDYGRUBER && p->averaging != H3D_AVG_PIROZZOLI) { h->err = "Averaging not recognized."; return 1; }
+    if (p->riemann < H3D_RIEMANN_ROE || p->riemann > H3D_RIEMANN_UDISS) { h->err = "Riemann Solver not recognized."; return 1; }
+    if (p->averaging < H3D_AVG_STANDARD || p->averaging > H3D_AVG_CHANDRASEKAR) { h->err = "Averaging not recognized."; return 1; }
     if (p->inviscid != H3D_STANDARD_DG && p->inviscid != H3D_SPLIT_DG) { h->err = "Requested inviscid discretization is not implemented."; return 1; }
     h->physics = *p;
     Phys& q = h->ph;
     q.gamma = p->gamma; q.gm1 = p->gammaMinus1; q.gammaM2 = p->gammaM2; q.mu = p->mu; q.mu_to_kappa = p->mu_to_kappa;
     q.S_div_Tref = p->S_div_Tref; q.T_renorm = p->T_renorm; q.lambdaStab = p->lambdaStab; q.Cs = p->smagorinsky_Cs;
     q.ns = p->flowIsNavierStokes; q.riemann = p->riemann; q.averaging = p->averaging; q.les = p->les;
+    h->extPhysics = p->riemann > H3D_RIEMANN_CENTRAL || p->averaging > H3D_AVG_PIROZZOLI;
     q.wallModel = (p->les != H3D_LES_NONE && p->les_wall_model == 1) ? 1 : 0;
     if (p->les_wall_model != 0 && p->les_wall_model != 1) { h->err = "LES wall model not recognized."; return 1; }
     h->havePhysics = true;

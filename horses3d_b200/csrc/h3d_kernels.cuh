@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                     double* ox = m.Ux + (size_t)e * N3 + node; double* oy = m.Uy + (size_t)e * N3 + node; double* oz = m.Uz + (size_t)e * N3 + node;
 #pragma unroll
                     for (int q = 0; q < 5; ++q) {
-                        g[r][q] = g[r][q] + fx[q] * iJ; g[r][5 + q] = g[r][5 + q] + fy[q] * iJ; g[r][10 + q] = g[r][10 + q] + fz[q] * iJ;
+                        // Euler with "compute gradients": local gradient only (base-class ComputeGradient, EllipticDiscretizationClass.f90:122-187)
+                        if (ph.ns) { g[r][q] = g[r][q] + fx[q] * iJ; g[r][5 + q] = g[r][5 + q] + fy[q] * iJ; g[r][10 + q] = g[r][10 + q] + fz[q] * iJ; }
                         ox[q * es] = g[r][q]; oy[q * es] = g[r][5 + q]; oz[q * es] = g[r][10 + q];
                     }
                     if (TMA) {   // the gradient buffer does not alias the inputs: store right away
@@ -438,8 +439,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
 //   BR1_RiemannSolver (EllipticBR1.f90:816-868), RiemannSolver pointer (RiemannSolvers_NS.f90)
 //   compute_viscosity_at_faces (SpatialDiscretization.f90:1345-1398): mu,kappa from the prolonged states
 // ---------------------------------------------------------------------------------------------------------
-template <int n>
-__global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin, int fEnd) {
+template <int n, bool EXT>
+__global__ void __launch_bounds__(128, EXT ? 1 : 4) k_riemann(DevMesh m, Phys ph, int fBegin, int fEnd) {
     constexpr int N2 = n * n;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = fBegin + (int)(t / N2), mm = (int)(t % N2);
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
             for (int q = 0; q < 5; ++q) { visc[q] = F[q][0] * nh[0] + F[q][1] * nh[1] + F[q][2] * nh[2]; }
             bc_neumann(btype, P, QL, visc);
         }
-        riemann_solver(ph, QL, QR, nh, t1, t2, inv);
+        riemann_solver<EXT>(ph, QL, QR, nh, t1, t2, inv);
     } else {
 #pragma unroll
         for (int q = 0; q < 5; ++q) { QL[q] = fQ[q * fs]; QR[q] = fQ[(size_t)(5 + q) * fs]; }
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(128) k_riemann(DevMesh m, Phys ph, int fBegin,
                 visc[q] = fx * nh[0] + fy * nh[1] + fz * nh[2];
             }
         }
-        riemann_solver(ph, QL, QR, nh, t1, t2, inv);
+        riemann_solver<EXT>(ph, QL, QR, nh, t1, t2, inv);
     }
 #pragma unroll
     for (int q = 0; q < 5; ++q) m.fStar[(size_t)q * fs + fo] = (inv[q] - visc[q]) * Jf;
@@ -523,9 +524,11 @@ struct VolSmem {
     static size_t bytes(bool split, bool ns) { return sizeof(double) * (fields(split, ns) + 2 * C::N2 + 2 * n) + sizeof(int) * (TMA ? 2 : 1) * C::EPB * (6 * C::N2 + 8) + 48; }
 };
 
-template <int n, bool SPLIT, bool TMA>
+// MODE 0: StandardDG; 1: SplitDG with the standard / Kennedy-Gruber / Pirozzoli two-point fluxes; 2: SplitDG with all averages
+template <int n, int MODE, bool TMA>
 __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m, Phys ph, RkArgs rk, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
+    constexpr bool SPLIT = MODE != 0, EXT = MODE == 2;
     constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;
     constexpr int FSI = (EPB * 30 * N2 + NT - 1) / NT;   // fStar items per thread
@@ -748,7 +751,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                                     for (int q = 0; q < 5; ++q) Qo[q] = sQe[q * NS + other];
 #pragma unroll
                                     for (int c = 0; c < 3; ++c) jo[c] = sJe[(3 * d + c) * NS + other];
-                                    if (l > me) two_point_flux(ph, Qk[r], Qo, jaMe, jo, fsvv); else two_point_flux(ph, Qo, Qk[r], jo, jaMe, fsvv);
+                                    if (l > me) two_point_flux<EXT>(ph, Qk[r], Qo, jaMe, jo, fsvv); else two_point_flux<EXT>(ph, Qo, Qk[r], jo, jaMe, fsvv);
                                 }
                                 const double sd = sSharpDT[l * n + me], hd = sHatDT[l * n + me];
                                 if (ns) {

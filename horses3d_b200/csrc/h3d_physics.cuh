@@ -107,12 +107,97 @@ __device__ __forceinline__ void viscous_flux(const Phys& ph, const double Q[5], 
     F[4][2] = F[1][2] * u + F[2][2] * v + F[3][2] * w + kappa * Tz;
 }
 
+// libs/foundation/Utilities.f90:269-300 (logarithmicMean, Ismail & Roe)
+__device__ __forceinline__ double log_mean(double aL, double aR) {
+    const double xi = aL / aR;
+    const double f = (xi - 1.0) / (xi + 1.0);
+    const double u = f * f;
+    double FF;
+    if (u < 0.01) FF = 1.0 + (1.0 / 3.0) * u + (1.0 / 5.0) * pow2(u) + (1.0 / 7.0) * (u * u * u);
+    else FF = log(xi) / (2.0 * f);
+    return 0.5 * (aL + aR) / FF;
+}
+
+// Ismail-Roe (entropy conserving) and Chandrasekar mean states shared by the averages and the two-point fluxes
+// (RiemannSolvers_NS.f90:1964-2077 and :2439-2641; the two families differ in 1/2 (zL+zR) versus (zL+zR) only)
+__device__ __forceinline__ void ec_mean_state(const Phys& ph, bool twoPoint, double rhoL, double rhoR, double uL, double uR, double vL, double vR,
+                                              double wL, double wR, double pL, double pR, double& rho, double& u, double& v, double& w, double& p, double& h) {
+    const double gamma = ph.gamma, gm1 = ph.gm1;
+    const double gammaPlus1Div2 = (gamma + 1.0) / 2.0, gammaMinus1Div2 = gm1 / 2.0, gammaDivGammaMinus1 = gamma / gm1, invGamma = 1.0 / gamma;
+    double zL[5], zR[5], z[5];
+    zL[4] = sqrt(rhoL * pL); zR[4] = sqrt(rhoR * pR);
+    zL[0] = rhoL / zL[4]; zR[0] = rhoR / zR[4];
+    zL[1] = zL[0] * uL; zR[1] = zR[0] * uR;
+    zL[2] = zL[0] * vL; zR[2] = zR[0] * vR;
+    zL[3] = zL[0] * wL; zR[3] = zR[0] * wR;
+    const double z1Log = log_mean(zL[0], zR[0]), z5Log = log_mean(zL[4], zR[4]);
+    if (twoPoint) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) z[q] = 0.5 * (zL[q] + zR[q]);
+        rho = z[0] * z5Log;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) z[q] = zL[q] + zR[q];
+        rho = 0.5 * z[0] * z5Log;
+    }
+    const double invZ1 = 1.0 / z[0];
+    u = z[1] * invZ1; v = z[2] * invZ1; w = z[3] * invZ1; p = z[4] * invZ1;
+    const double p2 = (gammaPlus1Div2 * z5Log / z1Log + gammaMinus1Div2 * p) * invGamma;
+    h = gammaDivGammaMinus1 * p2 / rho + 0.5 * (pow2(u) + pow2(v) + pow2(w));
+}
+__device__ __forceinline__ void chandrasekar_mean_state(const Phys& ph, double rhoL, double rhoR, double uL, double uR, double vL, double vR,
+                                                        double wL, double wR, double pL, double pR, double& rho, double& u, double& v, double& w, double& p, double& h) {
+    const double betaL = 0.5 * rhoL / pL, betaR = 0.5 * rhoR / pR;
+    const double betaLog = log_mean(betaL, betaR);
+    rho = log_mean(rhoL, rhoR);
+    u = 0.5 * (uL + uR); v = 0.5 * (vL + vR); w = 0.5 * (wL + wR);
+    p = 0.5 * (rhoL + rhoR) / (betaL + betaR);
+    h = 0.5 / (betaLog * ph.gm1) - 0.5 * (0.5 * ((pow2(uL) + pow2(vL) + pow2(wL)) + (pow2(uR) + pow2(vR) + pow2(wR))))
+        + p / rho + pow2(u) + pow2(v) + pow2(w);
+}
+
+// Ducros, Morinishi, entropy-conserving and Chandrasekar averages (RiemannSolvers_NS.f90:1821-1886, 1964-2077).
+// Out of line: these are not on the headline path and must not weigh on its register allocation.
+__device__ __noinline__ void averaged_states_ext(const Phys& ph, const double QL[5], const double QR[5], double pL, double pR,
+                                                 double invRhoL, double invRhoR, double flux[5]) {
+    const double uL = invRhoL * QL[1], uR = invRhoR * QR[1];
+    const double vL = invRhoL * QL[2], vR = invRhoR * QR[2];
+    const double wL = invRhoL * QL[3], wR = invRhoR * QR[3];
+    if (ph.averaging == H3D_AVG_DUCROS) {
+        flux[0] = 0.25 * (QL[0] + QR[0]) * (uL + uR);
+        flux[1] = 0.25 * (QL[1] + QR[1]) * (uL + uR) + 0.5 * (pL + pR);
+        flux[2] = 0.25 * (QL[2] + QR[2]) * (uL + uR);
+        flux[3] = 0.25 * (QL[3] + QR[3]) * (uL + uR);
+        flux[4] = 0.25 * (QL[4] + pL + QR[4] + pR) * (uL + uR);
+    } else if (ph.averaging == H3D_AVG_MORINISHI) {
+        const double cp = ph.gamma * (1.0 / ph.gm1);
+        const double hL = cp * pL, hR = cp * pR;
+        flux[0] = 0.5 * (QL[1] + QR[1]);
+        flux[1] = 0.25 * (QL[1] + QR[1]) * (uL + uR) + 0.5 * (pL + pR);
+        flux[2] = 0.25 * (QL[1] + QR[1]) * (vL + vR);
+        flux[3] = 0.25 * (QL[1] + QR[1]) * (wL + wR);
+        flux[4] = 0.5 * (uL * hL + uR * hR) + 0.25 * (QL[1] * uL + QR[1] * uR) * (uL + uR)
+                  + 0.25 * (QL[1] * vL + QR[1] * vR) * (vL + vR)
+                  + 0.25 * (QL[1] * wL + QR[1] * wR) * (wL + wR)
+                  - 0.25 * (QL[1] * pow2(uL) + QR[1] * pow2(uR))
+                  - 0.25 * (QL[1] * pow2(vL) + QR[1] * pow2(vR))
+                  - 0.25 * (QL[1] * pow2(wL) + QR[1] * pow2(wR));
+    } else {
+        double rho, u, v, w, p, h;
+        if (ph.averaging == H3D_AVG_ENTROPYCONS) ec_mean_state(ph, false, QL[0], QR[0], uL, uR, vL, vR, wL, wR, pL, pR, rho, u, v, w, p, h);
+        else chandrasekar_mean_state(ph, QL[0], QR[0], uL, uR, vL, vR, wL, wR, pL, pR, rho, u, v, w, p, h);
+        flux[0] = rho * u; flux[1] = rho * u * u + p; flux[2] = rho * u * v; flux[3] = rho * u * w; flux[4] = rho * u * h;
+    }
+}
+
 // RiemannSolvers_NS.f90:1784-1962 averaging functions on rotated states
+template <bool EXT>
 __device__ __forceinline__ void averaged_states(const Phys& ph, const double QL[5], const double QR[5], double pL, double pR,
                                                 double invRhoL, double invRhoR, double flux[5]) {
     const double uL = invRhoL * QL[1], uR = invRhoR * QR[1];
     const double vL = invRhoL * QL[2], vR = invRhoR * QR[2];
     const double wL = invRhoL * QL[3], wR = invRhoR * QR[3];
+    if constexpr (EXT) { if (ph.averaging > H3D_AVG_PIROZZOLI) { averaged_states_ext(ph, QL, QR, pL, pR, invRhoL, invRhoR, flux); return; } }
     if (ph.averaging == H3D_AVG_STANDARD) {
         flux[0] = 0.5 * (QL[1] + QR[1]);
         flux[1] = 0.5 * (QL[1] * uL + QR[1] * uR + pL + pR);
@@ -134,7 +219,8 @@ __device__ __forceinline__ void averaged_states(const Phys& ph, const double QL[
 
 // RiemannSolvers_NS.f90:375-428 (Central) and :1251-1334 (Lax-Friedrichs); central == LxF with lambdaStab = 0
 // up to the reference's own code path (no stabilisation term evaluated).
-__device__ __forceinline__ void rotated_riemann(const Phys& ph, bool lxf, const double QLeft[5], const double QRight[5],
+template <bool EXT>
+__device__ __forceinline__ void rotated_riemann(const Phys& ph, int mode, const double QLeft[5], const double QRight[5],
                                                 const double nHat[3], const double t1[3], const double t2[3], double flux[5]) {
     const double rhoL = QLeft[0], rhoR = QRight[0], invRhoL = 1.0 / rhoL, invRhoR = 1.0 / rhoR;
     const double rhouL = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
@@ -148,10 +234,15 @@ __device__ __forceinline__ void rotated_riemann(const Phys& ph, bool lxf, const 
     const double rhoV2R = (pow2(rhouR) + pow2(rhovR) + pow2(rhowR)) * invRhoR;
     const double pL = ph.gm1 * (rhoeL - 0.5 * rhoV2L), pR = ph.gm1 * (rhoeR - 0.5 * rhoV2R);
     const double QLRot[5] = {rhoL, rhouL, rhovL, rhowL, rhoeL}, QRRot[5] = {rhoR, rhouR, rhovR, rhowR, rhoeR};
-    averaged_states(ph, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
-    if (lxf) {
-        const double aL = sqrt(ph.gamma * pL * invRhoL), aR = sqrt(ph.gamma * pR * invRhoR);
-        const double lambda = fmax(fabs(rhouL * invRhoL) + aL, fabs(rhouR * invRhoR) + aR);
+    averaged_states<EXT>(ph, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    if (mode != H3D_RIEMANN_CENTRAL) {   // Lax-Friedrichs: lambda = max(|u| + a); u-diss (:1336-1417): lambda = max(|u|)
+        double lambda;
+        if (mode == H3D_RIEMANN_LXF) {
+            const double aL = sqrt(ph.gamma * pL * invRhoL), aR = sqrt(ph.gamma * pR * invRhoR);
+            lambda = fmax(fabs(rhouL * invRhoL) + aL, fabs(rhouR * invRhoR) + aR);
+        } else {
+            lambda = fmax(fabs(rhouL * invRhoL), fabs(rhouR * invRhoR));
+        }
 #pragma unroll
         for (int q = 0; q < 5; ++q) { const double stab = 0.5 * lambda * (QRRot[q] - QLRot[q]); flux[q] = flux[q] - ph.lambdaStab * stab; }
     }
@@ -208,13 +299,157 @@ __device__ __forceinline__ void roe_riemann(const Phys& ph, const double QLeft[5
     }
 }
 
+// RiemannSolvers_NS.f90:1661-1762 (RusanovRiemannSolver): unrotated, smax = max(a + |q|)
+__device__ __noinline__ void rusanov_riemann(const Phys& ph, const double QLeft[5], const double QRight[5], const double nHat[3], double flux[5]) {
+    const double gamma = ph.gamma;
+    const double rho = QLeft[0], rhou = QLeft[1], rhov = QLeft[2], rhow = QLeft[3], rhoe = QLeft[4];
+    const double rhon = QRight[0], rhoun = QRight[1], rhovn = QRight[2], rhown = QRight[3], rhoen = QRight[4];
+    const double ul = rhou / rho, vl = rhov / rho, wl = rhow / rho;
+    const double pleft = (gamma - 1.0) * (rhoe - 0.5 / rho * (rhou * rhou + rhov * rhov + rhow * rhow));
+    const double ur = rhoun / rhon, vr = rhovn / rhon, wr = rhown / rhon;
+    const double pright = (gamma - 1.0) * (rhoen - 0.5 / rhon * (rhoun * rhoun + rhovn * rhovn + rhown * rhown));
+    const double ql = nHat[0] * ul + nHat[1] * vl + nHat[2] * wl;
+    const double qr = nHat[0] * ur + nHat[1] * vr + nHat[2] * wr;
+    const double hl = 0.5 * (ul * ul + vl * vl + wl * wl) + gamma / (gamma - 1.0) * pleft / rho;
+    const double hr = 0.5 * (ur * ur + vr * vr + wr * wr) + gamma / (gamma - 1.0) * pright / rhon;
+    const double ar2 = (gamma - 1.0) * (hr - 0.5 * (ur * ur + vr * vr + wr * wr));
+    const double al2 = (gamma - 1.0) * (hl - 0.5 * (ul * ul + vl * vl + wl * wl));
+    const double ar = sqrt(ar2), al = sqrt(al2);
+    const double rql = rho * ql, rqr = rhon * qr;
+    flux[0] = rql + rqr;
+    flux[1] = rql * ul + pleft * nHat[0] + rqr * ur + pright * nHat[0];
+    flux[2] = rql * vl + pleft * nHat[1] + rqr * vr + pright * nHat[1];
+    flux[3] = rql * wl + pleft * nHat[2] + rqr * wr + pright * nHat[2];
+    flux[4] = rql * hl + rqr * hr;
+    const double smax = fmax(ar + fabs(qr), al + fabs(ql));
+#pragma unroll
+    for (int q = 0; q < 5; ++q) flux[q] = (flux[q] - smax * (QRight[q] - QLeft[q])) / 2.0;
+}
+
+// RiemannSolvers_NS.f90:430-576 (StdRoeRiemannSolver): rotated, full wave decomposition, Harten / van Leer entropy fix;
+// getPrimitiveVariables / getRoeVariables: VariableConversion_NS.f90:266-294, 323-365
+__device__ __noinline__ void stdroe_riemann(const Phys& ph, const double QLeft[5], const double QRight[5], const double nHat[3],
+                                            const double t1[3], const double t2[3], double flux[5]) {
+    const double gamma = ph.gamma, gm1 = ph.gm1;
+    double QLRot[5], QRRot[5];
+    QLRot[0] = QLeft[0]; QRRot[0] = QRight[0];
+    QLRot[1] = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    QRRot[1] = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    QLRot[2] = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    QRRot[2] = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    QLRot[3] = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    QRRot[3] = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    QLRot[4] = QLeft[4]; QRRot[4] = QRight[4];
+    const double iRL = 1.0 / QLRot[0], iRR = 1.0 / QRRot[0];
+    const double VLu = QLRot[1] * iRL, VLv = QLRot[2] * iRL, VLw = QLRot[3] * iRL;
+    const double VRu = QRRot[1] * iRR, VRv = QRRot[2] * iRR, VRw = QRRot[3] * iRR;
+    const double VLp = gm1 * (QLRot[4] - 0.5 * (VLu * QLRot[1] + VLv * QLRot[2] + VLw * QLRot[3]));
+    const double VRp = gm1 * (QRRot[4] - 0.5 * (VRu * QRRot[1] + VRv * QRRot[2] + VRw * QRRot[3]));
+    const double aL = sqrt(gamma * VLp * iRL), aR = sqrt(gamma * VRp * iRR);
+    const double sqrtRhoL = sqrt(QLRot[0]), sqrtRhoR = sqrt(QRRot[0]);
+    const double invSum = 1.0 / (sqrtRhoL + sqrtRhoR);
+    const double HL = (VLp + QLRot[4]) * iRL, HR = (VRp + QRRot[4]) * iRR;
+    const double u = (sqrtRhoL * VLu + sqrtRhoR * VRu) * invSum;
+    const double v = (sqrtRhoL * VLv + sqrtRhoR * VRv) * invSum;
+    const double w = (sqrtRhoL * VLw + sqrtRhoR * VRw) * invSum;
+    const double H = (sqrtRhoL * HL + sqrtRhoR * HR) * invSum;
+    const double V2 = pow2(u) + pow2(v) + pow2(w);
+    const double a = sqrt(gm1 * (H - 0.5 * V2));
+    double lambda[5] = {u - a, u, u, u, u + a};
+    const double K[5][5] = {{1.0, u - a, v, w, H - u * a}, {1.0, u, v, w, 0.5 * V2}, {0.0, 0.0, 1.0, 0.0, v}, {0.0, 0.0, 0.0, 1.0, w}, {1.0, u + a, v, w, H + u * a}};
+    double dQ[5], alpha[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) dQ[q] = QRRot[q] - QLRot[q];
+    alpha[2] = dQ[2] - v * dQ[0]; alpha[3] = dQ[3] - w * dQ[0];
+    dQ[4] = dQ[4] - alpha[2] * v - alpha[3] * w;
+    alpha[1] = gm1 * (dQ[0] * (H - u * u) + u * dQ[1] - dQ[4]) / (pow2(a));
+    alpha[0] = 0.5 * (dQ[0] * lambda[4] - dQ[1] - a * alpha[1]) / a;
+    alpha[4] = dQ[0] - alpha[0] - alpha[1];
+    double dLambda = fmax((VRu - aR) - (VLu - aL), 0.0);
+    if (fabs(lambda[0]) >= 2.0 * dLambda) lambda[0] = fabs(lambda[0]);
+    else lambda[0] = pow2(lambda[0]) / (4.0 * dLambda) + dLambda;
+    dLambda = fmax((VRu + aR) - (VLu + aL), 0.0);
+    if (fabs(lambda[4]) >= 2.0 * dLambda) lambda[4] = fabs(lambda[4]);
+    else lambda[4] = pow2(lambda[4]) / (4.0 * dLambda) + dLambda;
+    averaged_states<true>(ph, QLRot, QRRot, VLp, VRp, iRL, iRR, flux);
+    if (ph.averaging == H3D_AVG_PIROZZOLI || ph.averaging == H3D_AVG_KENNEDYGRUBER) lambda[0] = lambda[4];
+    double stab[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) stab[q] = stab[q] + 0.5 * alpha[i] * fabs(lambda[i]) * K[i][q];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) flux[q] = flux[q] - ph.lambdaStab * stab[q];
+    const double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
+// EXT = false: Roe, Lax-Friedrichs, central with the standard / Kennedy-Gruber / Pirozzoli averages (the instantiation on
+// the headline path); EXT = true adds the out-of-line solvers and averages
+template <bool EXT>
 __device__ __forceinline__ void riemann_solver(const Phys& ph, const double QL[5], const double QR[5], const double nHat[3],
                                                const double t1[3], const double t2[3], double flux[5]) {
-    if (ph.riemann == H3D_RIEMANN_ROE) roe_riemann(ph, QL, QR, nHat, flux);
-    else rotated_riemann(ph, ph.riemann == H3D_RIEMANN_LXF, QL, QR, nHat, t1, t2, flux);
+    if (ph.riemann == H3D_RIEMANN_ROE) { roe_riemann(ph, QL, QR, nHat, flux); return; }
+    if constexpr (EXT) {
+        if (ph.riemann == H3D_RIEMANN_RUSANOV) { rusanov_riemann(ph, QL, QR, nHat, flux); return; }
+        if (ph.riemann == H3D_RIEMANN_STDROE) { stdroe_riemann(ph, QL, QR, nHat, t1, t2, flux); return; }
+    }
+    rotated_riemann<EXT>(ph, ph.riemann, QL, QR, nHat, t1, t2, flux);
+}
+
+// Morinishi, Ducros, entropy-conserving and Chandrasekar two-point fluxes (RiemannSolvers_NS.f90:2147-2294, 2439-2641)
+__device__ __noinline__ void two_point_flux_ext(const Phys& ph, const double QL[5], const double QR[5], const double JaL[3], const double JaR[3], double fs[5]) {
+    const double invRhoL = 1.0 / QL[0], invRhoR = 1.0 / QR[0];
+    const double uL = invRhoL * QL[1], uR = invRhoR * QR[1];
+    const double vL = invRhoL * QL[2], vR = invRhoR * QR[2];
+    const double wL = invRhoL * QL[3], wR = invRhoR * QR[3];
+    const double pL = ph.gm1 * (QL[4] - 0.5 * (QL[1] * uL + QL[2] * vL + QL[3] * wL));
+    const double pR = ph.gm1 * (QR[4] - 0.5 * (QR[1] * uR + QR[2] * vR + QR[3] * wR));
+    const double Ja[3] = {0.5 * (JaL[0] + JaR[0]), 0.5 * (JaL[1] + JaR[1]), 0.5 * (JaL[2] + JaR[2])};
+    double F[3][5];
+    if (ph.averaging == H3D_AVG_DUCROS) {
+        const double velSum[3] = {uL + uR, vL + vR, wL + wR};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            F[d][0] = 0.25 * (QL[0] + QR[0]) * velSum[d];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) F[d][1 + c] = 0.25 * (QL[1 + c] + QR[1 + c]) * velSum[d];
+            F[d][1 + d] = 0.25 * (QL[1 + d] + QR[1 + d]) * velSum[d] + 0.5 * (pL + pR);
+            F[d][4] = 0.25 * (QL[4] + pL + QR[4] + pR) * velSum[d];
+        }
+    } else if (ph.averaging == H3D_AVG_MORINISHI) {
+        const double cp = ph.gamma * (1.0 / ph.gm1);
+        const double hL = cp * pL, hR = cp * pR;
+        const double velL[3] = {uL, vL, wL}, velR[3] = {uR, vR, wR};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double mL = QL[1 + d], mR = QR[1 + d];
+            F[d][0] = 0.5 * (mL + mR);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) F[d][1 + c] = 0.25 * (mL + mR) * (velL[c] + velR[c]);
+            F[d][1 + d] = 0.25 * (mL + mR) * (velL[d] + velR[d]) + 0.5 * (pL + pR);
+            F[d][4] = 0.5 * (velL[d] * hL + velR[d] * hR) + 0.25 * (mL * uL + mR * uR) * (uL + uR)
+                      + 0.25 * (mL * vL + mR * vR) * (vL + vR)
+                      + 0.25 * (mL * wL + mR * wR) * (wL + wR)
+                      - 0.25 * (mL * pow2(uL) + mR * pow2(uR))
+                      - 0.25 * (mL * pow2(vL) + mR * pow2(vR))
+                      - 0.25 * (mL * pow2(wL) + mR * pow2(wR));
+        }
+    } else {
+        double rho, u, v, w, p, h;
+        if (ph.averaging == H3D_AVG_ENTROPYCONS) ec_mean_state(ph, true, QL[0], QR[0], uL, uR, vL, vR, wL, wR, pL, pR, rho, u, v, w, p, h);
+        else chandrasekar_mean_state(ph, QL[0], QR[0], uL, uR, vL, vR, wL, wR, pL, pR, rho, u, v, w, p, h);
+        F[0][0] = rho * u; F[0][1] = rho * u * u + p; F[0][2] = rho * u * v; F[0][3] = rho * u * w; F[0][4] = rho * u * h;
+        F[1][0] = rho * v; F[1][1] = rho * v * u; F[1][2] = rho * v * v + p; F[1][3] = rho * v * w; F[1][4] = rho * v * h;
+        F[2][0] = rho * w; F[2][1] = rho * w * u; F[2][2] = rho * w * v; F[2][3] = rho * w * w + p; F[2][4] = rho * w * h;
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) fs[q] = F[0][q] * Ja[0] + F[1][q] * Ja[1] + F[2][q] * Ja[2];
 }
 
 // RiemannSolvers_NS.f90:2085-2145 (StandardDG), :2296-2367 (Kennedy-Gruber), :2369-2437 (Pirozzoli) two-point fluxes
+template <bool EXT>
 __device__ __forceinline__ void two_point_flux(const Phys& ph, const double QL[5], const double QR[5], const double JaL[3], const double JaR[3], double fs[5]) {
     const double invRhoL = 1.0 / QL[0], invRhoR = 1.0 / QR[0];
     const double uL = invRhoL * QL[1], uR = invRhoR * QR[1];
@@ -223,6 +458,7 @@ __device__ __forceinline__ void two_point_flux(const Phys& ph, const double QL[5
     const double pL = ph.gm1 * (QL[4] - 0.5 * (QL[1] * uL + QL[2] * vL + QL[3] * wL));
     const double pR = ph.gm1 * (QR[4] - 0.5 * (QR[1] * uR + QR[2] * vR + QR[3] * wR));
     double f[5], g[5], h[5];
+    if constexpr (EXT) { if (ph.averaging > H3D_AVG_PIROZZOLI) { two_point_flux_ext(ph, QL, QR, JaL, JaR, fs); return; } }
     if (ph.averaging == H3D_AVG_STANDARD) {
         const double Ja[3] = {JaL[0] + JaR[0], JaL[1] + JaR[1], JaL[2] + JaR[2]};
         f[0] = QL[1] + QR[1]; f[1] = QL[1] * uL + QR[1] * uR + pL + pR; f[2] = QL[1] * vL + QR[1] * vR; f[3] = QL[1] * wL + QR[1] * wR;

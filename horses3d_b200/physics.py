@@ -6,8 +6,9 @@ SetRiemannSolver (RiemannSolvers_NS.f90:120-286): same defaults, same arithmetic
 import ctypes as C
 
 STANDARD_DG, SPLIT_DG = 0, 1
-RIEMANN = {"roe": 0, "lax-friedrichs": 1, "central": 2, "rusanov": 3, "standard roe": 4}
-AVERAGING = {"standard": 0, "kennedy-gruber": 1, "pirozzoli": 2, "ducros": 3, "morinishi": 4}
+RIEMANN = {"roe": 0, "lax-friedrichs": 1, "central": 2, "rusanov": 3, "standard roe": 4, "u-diss": 5}
+AVERAGING = {"standard": 0, "kennedy-gruber": 1, "pirozzoli": 2, "ducros": 3, "morinishi": 4, "entropy conserving": 5,
+             "chandrasekar": 6}
 LES = {"none": 0, "smagorinsky": 1}
 
 INT_VOLUME, INT_KINETIC_ENERGY, INT_KINETIC_ENERGY_RATE, INT_ENSTROPHY = 0, 1, 2, 3

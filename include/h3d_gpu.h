@@ -40,6 +40,7 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_RIEMANN_CENTRAL 2
 #define H3D_RIEMANN_RUSANOV 3
 #define H3D_RIEMANN_STDROE 4
+#define H3D_RIEMANN_UDISS 5
 
 /* averaging / two-point flux (RiemannSolvers_NS.f90:233-285) */
 #define H3D_AVG_STANDARD 0
@@ -47,6 +48,8 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_AVG_PIROZZOLI 2
 #define H3D_AVG_DUCROS 3
 #define H3D_AVG_MORINISHI 4
+#define H3D_AVG_ENTROPYCONS 5
+#define H3D_AVG_CHANDRASEKAR 6
 
 /* LES (libs/physics/common/LESModels.f90) */
 #define H3D_LES_NONE 0

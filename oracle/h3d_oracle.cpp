@@ -156,7 +156,19 @@ inline double SmagorinskyViscosity(const Oracle& o, double delta, double dWall, 
     return Q[IRHO] * POW2(LS) * normS;
 }
 
-// ---- averaging functions on rotated states (RiemannSolvers_NS.f90:1784-1962)
+// libs/foundation/Utilities.f90:269-300 (logarithmicMean, Ismail & Roe)
+inline double logarithmicMean(double aL, double aR) {
+    const double eps = 0.01;
+    double xi = aL / aR;
+    double f = (xi - 1.0) / (xi + 1.0);
+    double u = f * f;
+    double FF;
+    if (u < eps) FF = 1.0 + (1.0 / 3.0) * u + (1.0 / 5.0) * POW2(u) + (1.0 / 7.0) * (u * u * u);
+    else FF = std::log(xi) / (2.0 * f);
+    return 0.5 * (aL + aR) / FF;
+}
+
+// ---- averaging functions on rotated states (RiemannSolvers_NS.f90:1784-2077)
 inline void AveragedStates(const Oracle& o, const double* QL, const double* QR, double pL, double pR, double invRhoL, double invRhoR, double* flux) {
     double uL = invRhoL * QL[IRHOU], uR = invRhoR * QR[IRHOU];
     double vL = invRhoL * QL[IRHOV], vR = invRhoR * QR[IRHOV];
@@ -177,6 +189,57 @@ inline void AveragedStates(const Oracle& o, const double* QL, const double* QR, 
         case H3D_AVG_PIROZZOLI: {
             double rho = 0.5 * (QL[IRHO] + QR[IRHO]), u = 0.5 * (uL + uR), v = 0.5 * (vL + vR), w = 0.5 * (wL + wR), p = 0.5 * (pL + pR);
             double h = 0.5 * ((QL[IRHOE] + pL) * invRhoL + (QR[IRHOE] + pR) * invRhoR);
+            flux[IRHO] = rho * u; flux[IRHOU] = rho * u * u + p; flux[IRHOV] = rho * u * v; flux[IRHOW] = rho * u * w; flux[IRHOE] = rho * u * h;
+        } break;
+        case H3D_AVG_DUCROS:   // :1821-1848
+            flux[IRHO] = 0.25 * (QL[IRHO] + QR[IRHO]) * (uL + uR);
+            flux[IRHOU] = 0.25 * (QL[IRHOU] + QR[IRHOU]) * (uL + uR) + 0.5 * (pL + pR);
+            flux[IRHOV] = 0.25 * (QL[IRHOV] + QR[IRHOV]) * (uL + uR);
+            flux[IRHOW] = 0.25 * (QL[IRHOW] + QR[IRHOW]) * (uL + uR);
+            flux[IRHOE] = 0.25 * (QL[IRHOE] + pL + QR[IRHOE] + pR) * (uL + uR);
+            break;
+        case H3D_AVG_MORINISHI: {   // :1850-1886; the enthalpy does not contain the kinetic energy
+            const double cp = o.ph.gamma * (1.0 / o.ph.gammaMinus1);   // dimensionless % cp, PhysicsStorage_NS.f90:190
+            double hL = cp * pL, hR = cp * pR;
+            flux[IRHO] = 0.5 * (QL[IRHOU] + QR[IRHOU]);
+            flux[IRHOU] = 0.25 * (QL[IRHOU] + QR[IRHOU]) * (uL + uR) + 0.5 * (pL + pR);
+            flux[IRHOV] = 0.25 * (QL[IRHOU] + QR[IRHOU]) * (vL + vR);
+            flux[IRHOW] = 0.25 * (QL[IRHOU] + QR[IRHOU]) * (wL + wR);
+            flux[IRHOE] = 0.5 * (uL * hL + uR * hR) + 0.25 * (QL[IRHOU] * uL + QR[IRHOU] * uR) * (uL + uR)
+                          + 0.25 * (QL[IRHOU] * vL + QR[IRHOU] * vR) * (vL + vR)
+                          + 0.25 * (QL[IRHOU] * wL + QR[IRHOU] * wR) * (wL + wR)
+                          - 0.25 * (QL[IRHOU] * POW2(uL) + QR[IRHOU] * POW2(uR))
+                          - 0.25 * (QL[IRHOU] * POW2(vL) + QR[IRHOU] * POW2(vR))
+                          - 0.25 * (QL[IRHOU] * POW2(wL) + QR[IRHOU] * POW2(wR));
+        } break;
+        case H3D_AVG_ENTROPYCONS: {   // :1964-2026 (Ismail & Roe parameter vector)
+            const double gamma = o.ph.gamma, gm1 = o.ph.gammaMinus1;
+            const double gammaPlus1Div2 = (gamma + 1.0) / 2.0, gammaMinus1Div2 = gm1 / 2.0, gammaDivGammaMinus1 = gamma / gm1, invGamma = 1.0 / gamma;
+            double rhoL = QL[IRHO], rhoR = QR[IRHO];
+            double zL[5], zR[5], zSum[5];
+            zL[4] = std::sqrt(rhoL * pL); zR[4] = std::sqrt(rhoR * pR);
+            zL[0] = rhoL / zL[4]; zR[0] = rhoR / zR[4];
+            zL[1] = zL[0] * uL; zR[1] = zR[0] * uR;
+            zL[2] = zL[0] * vL; zR[2] = zR[0] * vR;
+            zL[3] = zL[0] * wL; zR[3] = zR[0] * wR;
+            for (int q = 0; q < 5; ++q) zSum[q] = zL[q] + zR[q];
+            double invZ1Sum = 1.0 / zSum[0];
+            double z1Log = logarithmicMean(zL[0], zR[0]), z5Log = logarithmicMean(zL[4], zR[4]);
+            double rho = 0.5 * zSum[0] * z5Log;
+            double u = zSum[1] * invZ1Sum, v = zSum[2] * invZ1Sum, w = zSum[3] * invZ1Sum, p = zSum[4] * invZ1Sum;
+            double p2 = (gammaPlus1Div2 * z5Log / z1Log + gammaMinus1Div2 * p) * invGamma;
+            double h = gammaDivGammaMinus1 * p2 / rho + 0.5 * (POW2(u) + POW2(v) + POW2(w));
+            flux[IRHO] = rho * u; flux[IRHOU] = rho * u * u + p; flux[IRHOV] = rho * u * v; flux[IRHOW] = rho * u * w; flux[IRHOE] = rho * u * h;
+        } break;
+        case H3D_AVG_CHANDRASEKAR: {   // :2028-2077
+            double rhoL = QL[IRHO], rhoR = QR[IRHO];
+            double betaL = 0.5 * rhoL / pL, betaR = 0.5 * rhoR / pR;
+            double betaLog = logarithmicMean(betaL, betaR);
+            double rho = logarithmicMean(rhoL, rhoR);
+            double u = 0.5 * (uL + uR), v = 0.5 * (vL + vR), w = 0.5 * (wL + wR);
+            double p = 0.5 * (rhoL + rhoR) / (betaL + betaR);
+            double h = 0.5 / (betaLog * o.ph.gammaMinus1) - 0.5 * (0.5 * ((POW2(uL) + POW2(vL) + POW2(wL)) + (POW2(uR) + POW2(vR) + POW2(wR))))
+                       + p / rho + POW2(u) + POW2(v) + POW2(w);
             flux[IRHO] = rho * u; flux[IRHOU] = rho * u * u + p; flux[IRHOV] = rho * u * v; flux[IRHOW] = rho * u * w; flux[IRHOE] = rho * u * h;
         } break;
         default: for (int q = 0; q < 5; ++q) flux[q] = std::numeric_limits<double>::quiet_NaN();
@@ -274,8 +337,116 @@ inline void RoeRiemannSolver(const Oracle& o, const double* QLeft, const double*
     }
 }
 
+// RiemannSolvers_NS.f90:1661-1762 (RusanovRiemannSolver): unrotated, smax = max(a + |q|)
+inline void RusanovRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, double* flux) {
+    const double gamma = o.ph.gamma, ds = 1.0;
+    double rho = QLeft[0], rhou = QLeft[1], rhov = QLeft[2], rhow = QLeft[3], rhoe = QLeft[4];
+    double rhon = QRight[0], rhoun = QRight[1], rhovn = QRight[2], rhown = QRight[3], rhoen = QRight[4];
+    double ul = rhou / rho, vl = rhov / rho, wl = rhow / rho;
+    double pleft = (gamma - 1.0) * (rhoe - 0.5 / rho * (rhou * rhou + rhov * rhov + rhow * rhow));
+    double ur = rhoun / rhon, vr = rhovn / rhon, wr = rhown / rhon;
+    double pright = (gamma - 1.0) * (rhoen - 0.5 / rhon * (rhoun * rhoun + rhovn * rhovn + rhown * rhown));
+    double ql = nHat[0] * ul + nHat[1] * vl + nHat[2] * wl;
+    double qr = nHat[0] * ur + nHat[1] * vr + nHat[2] * wr;
+    double hl = 0.5 * (ul * ul + vl * vl + wl * wl) + gamma / (gamma - 1.0) * pleft / rho;
+    double hr = 0.5 * (ur * ur + vr * vr + wr * wr) + gamma / (gamma - 1.0) * pright / rhon;
+    double ar2 = (gamma - 1.0) * (hr - 0.5 * (ur * ur + vr * vr + wr * wr));
+    double al2 = (gamma - 1.0) * (hl - 0.5 * (ul * ul + vl * vl + wl * wl));
+    double ar = std::sqrt(ar2), al = std::sqrt(al2);
+    double rql = rho * ql, rqr = rhon * qr;
+    flux[0] = ds * (rql + rqr);
+    flux[1] = ds * (rql * ul + pleft * nHat[0] + rqr * ur + pright * nHat[0]);
+    flux[2] = ds * (rql * vl + pleft * nHat[1] + rqr * vr + pright * nHat[1]);
+    flux[3] = ds * (rql * wl + pleft * nHat[2] + rqr * wr + pright * nHat[2]);
+    flux[4] = ds * (rql * hl + rqr * hr);
+    double smax = std::fmax(ar + std::fabs(qr), al + std::fabs(ql));
+    for (int q = 0; q < 5; ++q) flux[q] = (flux[q] - ds * smax * (QRight[q] - QLeft[q])) / 2.0;
+}
+
+// RiemannSolvers_NS.f90:430-576 (StdRoeRiemannSolver): rotated, full wave decomposition, Harten / van Leer entropy fix
+inline void StdRoeRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, const double* t1, const double* t2, double* flux) {
+    const double gamma = o.ph.gamma, gm1 = o.ph.gammaMinus1;
+    double QLRot[5], QRRot[5];
+    QLRot[0] = QLeft[0]; QRRot[0] = QRight[0];
+    QLRot[1] = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    QRRot[1] = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    QLRot[2] = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    QRRot[2] = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    QLRot[3] = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    QRRot[3] = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    QLRot[4] = QLeft[4]; QRRot[4] = QRight[4];
+    // getPrimitiveVariables (VariableConversion_NS.f90:266-294): [invRho, u, v, w, p, T, a^2]
+    auto prim = [&](const double* U, double* V) {
+        double invRho = 1.0 / U[0];
+        V[0] = invRho; V[1] = U[1] * invRho; V[2] = U[2] * invRho; V[3] = U[3] * invRho;
+        V[4] = gm1 * (U[4] - 0.5 * (V[1] * U[1] + V[2] * U[2] + V[3] * U[3]));
+        V[5] = V[4] * o.ph.gammaM2 * invRho;
+        V[6] = gamma * V[4] * invRho;
+    };
+    double VL[7], VR[7];
+    prim(QLRot, VL); prim(QRRot, VR);
+    double aL = std::sqrt(VL[6]), aR = std::sqrt(VR[6]);
+    // getRoeVariables (VariableConversion_NS.f90:323-365)
+    double sqrtRhoL = std::sqrt(QLRot[0]), sqrtRhoR = std::sqrt(QRRot[0]);
+    double invSumSqrtRhoLR = 1.0 / (sqrtRhoL + sqrtRhoR);
+    double HL = (VL[4] + QLRot[4]) * VL[0], HR = (VR[4] + QRRot[4]) * VR[0];
+    double u = (sqrtRhoL * VL[1] + sqrtRhoR * VR[1]) * invSumSqrtRhoLR;
+    double v = (sqrtRhoL * VL[2] + sqrtRhoR * VR[2]) * invSumSqrtRhoLR;
+    double w = (sqrtRhoL * VL[3] + sqrtRhoR * VR[3]) * invSumSqrtRhoLR;
+    double H = (sqrtRhoL * HL + sqrtRhoR * HR) * invSumSqrtRhoLR;
+    double V2 = POW2(u) + POW2(v) + POW2(w);
+    double a = std::sqrt(gm1 * (H - 0.5 * V2));
+    double lambda[5] = {u - a, u, u, u, u + a};
+    double K[5][5] = {{1.0, u - a, v, w, H - u * a}, {1.0, u, v, w, 0.5 * V2}, {0.0, 0.0, 1.0, 0.0, v}, {0.0, 0.0, 0.0, 1.0, w}, {1.0, u + a, v, w, H + u * a}};   // K[wave][component]
+    double dQ[5], alpha[5];
+    for (int q = 0; q < 5; ++q) dQ[q] = QRRot[q] - QLRot[q];
+    alpha[2] = dQ[2] - v * dQ[0]; alpha[3] = dQ[3] - w * dQ[0];
+    dQ[4] = dQ[4] - alpha[2] * v - alpha[3] * w;
+    alpha[1] = gm1 * (dQ[0] * (H - u * u) + u * dQ[1] - dQ[4]) / (POW2(a));
+    alpha[0] = 0.5 * (dQ[0] * lambda[4] - dQ[1] - a * alpha[1]) / a;
+    alpha[4] = dQ[0] - alpha[0] - alpha[1];
+    double dLambda = std::fmax((VR[1] - aR) - (VL[1] - aL), 0.0);
+    if (std::fabs(lambda[0]) >= 2.0 * dLambda) lambda[0] = std::fabs(lambda[0]);
+    else lambda[0] = POW2(lambda[0]) / (4.0 * dLambda) + dLambda;
+    dLambda = std::fmax((VR[1] + aR) - (VL[1] + aL), 0.0);
+    if (std::fabs(lambda[4]) >= 2.0 * dLambda) lambda[4] = std::fabs(lambda[4]);
+    else lambda[4] = POW2(lambda[4]) / (4.0 * dLambda) + dLambda;
+    AveragedStates(o, QLRot, QRRot, VL[4], VR[4], VL[0], VR[0], flux);
+    if (o.ph.averaging == H3D_AVG_PIROZZOLI || o.ph.averaging == H3D_AVG_KENNEDYGRUBER) lambda[0] = lambda[4];   // Winters et al. correction (:548-558)
+    double stab[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; ++i) for (int q = 0; q < 5; ++q) stab[q] = stab[q] + 0.5 * alpha[i] * std::fabs(lambda[i]) * K[i][q];
+    for (int q = 0; q < 5; ++q) flux[q] = flux[q] - o.ph.lambdaStab * stab[q];
+    double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
+// RiemannSolvers_NS.f90:1336-1417 (u_dissRiemannSolver): as Lax-Friedrichs with lambda = max(|uL|, |uR|)
+inline void UDissRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, const double* t1, const double* t2, double* flux) {
+    const double gm1 = o.ph.gammaMinus1;
+    double rhoL = QLeft[0], rhoR = QRight[0], invRhoL = 1.0 / rhoL, invRhoR = 1.0 / rhoR;
+    double rhouL = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    double rhouR = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    double rhovL = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    double rhovR = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    double rhowL = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    double rhowR = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    double rhoV2L = (POW2(rhouL) + POW2(rhovL) + POW2(rhowL)) * invRhoL;
+    double rhoV2R = (POW2(rhouR) + POW2(rhovR) + POW2(rhowR)) * invRhoR;
+    double rhoeL = QLeft[4], rhoeR = QRight[4];
+    double pL = gm1 * (rhoeL - 0.5 * rhoV2L), pR = gm1 * (rhoeR - 0.5 * rhoV2R);
+    double lambda = std::fmax(std::fabs(rhouL * invRhoL), std::fabs(rhouR * invRhoR));
+    double QLRot[5] = {rhoL, rhouL, rhovL, rhowL, rhoeL}, QRRot[5] = {rhoR, rhouR, rhovR, rhowR, rhoeR};
+    AveragedStates(o, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    for (int q = 0; q < 5; ++q) { double stab = 0.5 * lambda * (QRRot[q] - QLRot[q]); flux[q] = flux[q] - o.ph.lambdaStab * stab; }
+    double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
 inline void RiemannSolver(const Oracle& o, const double* QL, const double* QR, const double* nHat, const double* t1, const double* t2, double* flux) {
     switch (o.ph.riemann) {
+        case H3D_RIEMANN_RUSANOV: RusanovRiemannSolver(o, QL, QR, nHat, flux); break;
+        case H3D_RIEMANN_STDROE: StdRoeRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
+        case H3D_RIEMANN_UDISS: UDissRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
         case H3D_RIEMANN_ROE: RoeRiemannSolver(o, QL, QR, nHat, flux); break;
         case H3D_RIEMANN_LXF: LxFRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
         case H3D_RIEMANN_CENTRAL: CentralRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
@@ -325,6 +496,63 @@ inline void TwoPointFlux(const Oracle& o, const double* QL, const double* QR, co
         f[IRHO] = rho * u; f[IRHOU] = rho * u * u + p; f[IRHOV] = rho * u * v; f[IRHOW] = rho * u * w; f[IRHOE] = rho * u * hh;
         g[IRHO] = rho * v; g[IRHOU] = rho * v * u; g[IRHOV] = rho * v * v + p; g[IRHOW] = rho * v * w; g[IRHOE] = rho * v * hh;
         h[IRHO] = rho * w; h[IRHOU] = rho * w * u; h[IRHOV] = rho * w * v; h[IRHOW] = rho * w * w + p; h[IRHOE] = rho * w * hh;
+    } else if (o.ph.averaging == H3D_AVG_DUCROS) {   // :2231-2294
+        const double QLm[3] = {QL[IRHOU], QL[IRHOV], QL[IRHOW]}, QRm[3] = {QR[IRHOU], QR[IRHOV], QR[IRHOW]};
+        const double velSum[3] = {uL + uR, vL + vR, wL + wR};
+        double* F[3] = {f, g, h};
+        for (int d = 0; d < 3; ++d) {
+            F[d][IRHO] = 0.25 * (QL[IRHO] + QR[IRHO]) * velSum[d];
+            for (int c = 0; c < 3; ++c) F[d][IRHOU + c] = 0.25 * (QLm[c] + QRm[c]) * velSum[d];
+            F[d][IRHOU + d] = 0.25 * (QLm[d] + QRm[d]) * velSum[d] + 0.5 * (pL + pR);
+            F[d][IRHOE] = 0.25 * (QL[IRHOE] + pL + QR[IRHOE] + pR) * velSum[d];
+        }
+    } else if (o.ph.averaging == H3D_AVG_MORINISHI) {   // :2147-2229
+        const double cp = o.ph.gamma * (1.0 / o.ph.gammaMinus1);
+        const double hL = cp * pL, hR = cp * pR;
+        const double QLm[3] = {QL[IRHOU], QL[IRHOV], QL[IRHOW]}, QRm[3] = {QR[IRHOU], QR[IRHOV], QR[IRHOW]};
+        const double velL[3] = {uL, vL, wL}, velR[3] = {uR, vR, wR};
+        double* F[3] = {f, g, h};
+        for (int d = 0; d < 3; ++d) {
+            F[d][IRHO] = 0.5 * (QLm[d] + QRm[d]);
+            for (int c = 0; c < 3; ++c) F[d][IRHOU + c] = 0.25 * (QLm[d] + QRm[d]) * (velL[c] + velR[c]);
+            F[d][IRHOU + d] = 0.25 * (QLm[d] + QRm[d]) * (velL[d] + velR[d]) + 0.5 * (pL + pR);
+            F[d][IRHOE] = 0.5 * (velL[d] * hL + velR[d] * hR) + 0.25 * (QLm[d] * uL + QRm[d] * uR) * (uL + uR)
+                          + 0.25 * (QLm[d] * vL + QRm[d] * vR) * (vL + vR)
+                          + 0.25 * (QLm[d] * wL + QRm[d] * wR) * (wL + wR)
+                          - 0.25 * (QLm[d] * POW2(uL) + QRm[d] * POW2(uR))
+                          - 0.25 * (QLm[d] * POW2(vL) + QRm[d] * POW2(vR))
+                          - 0.25 * (QLm[d] * POW2(wL) + QRm[d] * POW2(wR));
+        }
+    } else if (o.ph.averaging == H3D_AVG_ENTROPYCONS || o.ph.averaging == H3D_AVG_CHANDRASEKAR) {   // :2439-2558, :2560-2641
+        double rhoL = QL[IRHO], rhoR = QR[IRHO], rhoM, uM, vM, wM, pM, hM;
+        if (o.ph.averaging == H3D_AVG_ENTROPYCONS) {
+            const double gamma = o.ph.gamma;
+            const double gammaPlus1Div2 = (gamma + 1.0) / 2.0, gammaMinus1Div2 = gm1 / 2.0, gammaDivGammaMinus1 = gamma / gm1, invGamma = 1.0 / gamma;
+            double zL[5], zR[5], zAv[5];
+            zL[4] = std::sqrt(rhoL * pL); zR[4] = std::sqrt(rhoR * pR);
+            zL[0] = rhoL / zL[4]; zR[0] = rhoR / zR[4];
+            zL[1] = zL[0] * uL; zR[1] = zR[0] * uR;
+            zL[2] = zL[0] * vL; zR[2] = zR[0] * vR;
+            zL[3] = zL[0] * wL; zR[3] = zR[0] * wR;
+            for (int q = 0; q < 5; ++q) zAv[q] = 0.5 * (zL[q] + zR[q]);
+            double invZ1Av = 1.0 / zAv[0];
+            double z1Log = logarithmicMean(zL[0], zR[0]), z5Log = logarithmicMean(zL[4], zR[4]);
+            rhoM = zAv[0] * z5Log;
+            uM = zAv[1] * invZ1Av; vM = zAv[2] * invZ1Av; wM = zAv[3] * invZ1Av; pM = zAv[4] * invZ1Av;
+            double p2 = (gammaPlus1Div2 * z5Log / z1Log + gammaMinus1Div2 * pM) * invGamma;
+            hM = gammaDivGammaMinus1 * p2 / rhoM + 0.5 * (POW2(uM) + POW2(vM) + POW2(wM));
+        } else {
+            double betaL = 0.5 * rhoL / pL, betaR = 0.5 * rhoR / pR;
+            double betaLog = logarithmicMean(betaL, betaR);
+            rhoM = logarithmicMean(rhoL, rhoR);
+            uM = 0.5 * (uL + uR); vM = 0.5 * (vL + vR); wM = 0.5 * (wL + wR);
+            pM = 0.5 * (rhoL + rhoR) / (betaL + betaR);
+            hM = 0.5 / (betaLog * gm1) - 0.5 * (0.5 * ((POW2(uL) + POW2(vL) + POW2(wL)) + (POW2(uR) + POW2(vR) + POW2(wR))))
+                 + pM / rhoM + POW2(uM) + POW2(vM) + POW2(wM);
+        }
+        f[IRHO] = rhoM * uM; f[IRHOU] = rhoM * uM * uM + pM; f[IRHOV] = rhoM * uM * vM; f[IRHOW] = rhoM * uM * wM; f[IRHOE] = rhoM * uM * hM;
+        g[IRHO] = rhoM * vM; g[IRHOU] = rhoM * vM * uM; g[IRHOV] = rhoM * vM * vM + pM; g[IRHOW] = rhoM * vM * wM; g[IRHOE] = rhoM * vM * hM;
+        h[IRHO] = rhoM * wM; h[IRHOU] = rhoM * wM * uM; h[IRHOV] = rhoM * wM * vM; h[IRHOW] = rhoM * wM * wM + pM; h[IRHOE] = rhoM * wM * hM;
     } else {
         for (int q = 0; q < 5; ++q) f[q] = g[q] = h[q] = std::numeric_limits<double>::quiet_NaN();
     }
@@ -514,6 +742,12 @@ void computeGradient(Oracle& o, double time) {
                 }
             }
         }
+    }
+    // Euler with "compute gradients": the viscous discretization is the base class, whose ComputeGradient is the local
+    // gradient alone (SpatialDiscretization.f90:185-195, EllipticDiscretizationClass.f90:122-187): no interface terms
+    if (!o.ph.flowIsNavierStokes) {
+        prolongToFaces(o, 5, o.Ux, o.fUx); prolongToFaces(o, 5, o.Uy, o.fUy); prolongToFaces(o, 5, o.Uz, o.fUz);
+        return;
     }
     // BR1_ComputeElementInterfaceAverage (:571-627) + Face_ProjectGradientFluxToElements (FaceClass.f90:865-961, factor = 1)
     // BR1_ComputeBoundaryFlux (:686-736)

@@ -49,6 +49,15 @@ CASES = [
     (2, 5, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="standard")),
     (2, 9, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli")),
     (2, 3, GAUSSLOBATTO, 0.0, False, dict(flow="NS", mach=0.3, reynolds=200.0)),
+    # the remaining Riemann solvers and averages (SURVEY 8f "next"): K2 / K4 ingredients
+    (3, 3, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.08, inviscid="split-form", averaging="chandrasekar", riemann="central", compute_gradients=True)),
+    (2, 7, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="chandrasekar", riemann="central")),
+    (3, 3, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli", riemann="standard roe")),
+    (2, 4, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="entropy conserving", riemann="standard roe")),
+    (2, 5, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="ducros", riemann="u-diss")),
+    (2, 3, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="morinishi", riemann="lax-friedrichs")),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, riemann="rusanov")),
+    (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, riemann="standard roe", averaging="kennedy-gruber")),
 ]
 
 
@@ -57,7 +66,7 @@ def test_time_derivative_matches_oracle(gpu_api_cls, ne, N, nodes, amp, shuffle,
     mesh = get_mesh(ne, N, nodes, amp, shuffle)
     (so, o), (sg, g) = run_pair(gpu_api_cls, mesh, make_physics(**kw))
     assert np.array_equal(o["Q"], g["Q"])                       # upload/download round trip is exact
-    if kw.get("flow", "NS") != "Euler":
+    if kw.get("flow", "NS") != "Euler" or kw.get("compute_gradients"):
         for k in ("U_x", "U_y", "U_z"):
             assert rel_err(g[k], o[k]) < TOL_QDOT, k
     assert rel_err(g["QDot"], o["QDot"]) < TOL_QDOT

@@ -46,6 +46,25 @@ def test_k1_taylor_green_5_steps():
     assert abs(rec["enstrophy"] - 3.7499683882517909E-01) < 1.0e-11
 
 
+def test_k2_euler_taylor_green_kepec_10_steps():
+    """Solver/test/Euler/TaylorGreenKEPEC: Euler, M 0.08, P=3 (Gauss-Lobatto: split-form), Chandrasekar two-point flux,
+    central Riemann solver, compute gradients, RK3, cfl 0.4, 10 steps on the 32^3 periodic box.  Expected values and
+    tolerances from SETUP/ProblemFile.f90:337-395.  Pins the SplitDG volume term, the logarithmic mean,
+    the Chandrasekar average and the central solver."""
+    m = HostMesh.box(32).connect().geometry(3, GAUSSLOBATTO)
+    phys = make_physics(flow="Euler", mach=0.08, inviscid="split-form", averaging="chandrasekar", riemann="central", compute_gradients=True)
+    sem = DGSem(oracle_api.OracleApi(), m, phys)
+    sem.set_initial_condition(taylor_green_ic)
+    rec = sem.integrate(10, cfl=0.4, dcfl=0.4)[-1]
+    res = np.array([1.1131779208842484E-04, 0.12741606758485369, 0.12741606776695064, 0.24998271835184718, 0.62461894702221510])
+    print("K2", rec["residuals"] - res, rec["kinetic energy"] - 0.12500000000766839, rec["kinetic energy rate"] - 2.3284871259485850E-06,
+          rec["enstrophy"] - 0.37500245097897006)
+    assert np.abs(rec["residuals"] - res).max() < 1.0e-7
+    assert abs(rec["kinetic energy"] - 0.12500000000766839) < 1.0e-11
+    assert abs(rec["kinetic energy rate"] - 2.3284871259485850E-06) < 1.0e-11
+    assert abs(rec["enstrophy"] - 0.37500245097897006) < 1.0e-11
+
+
 CYLINDER_MESH = "/root/reference/Solver/test/TestMeshes/CylinderNSpol3.mesh"
 
 
@@ -104,6 +123,37 @@ def test_k5b_cylinder_smagorinsky_100_steps():
     res = np.array([7.58705681758851, 15.5542852761418, 0.231394835496677, 20.0848567943827, 207.594579145771])
     print("K5b residuals", got, "rel diff", np.abs((got - res) / res).max())
     assert np.abs(got - res).max() < 1.0e-7
+
+
+BOX_CIRCLE_MESH = "/root/reference/Solver/test/TestMeshes/BoxAroundCircle3D_extended_pol3.mesh"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(BOX_CIRCLE_MESH), reason="reference test mesh not available on this machine")
+def test_k4_box_around_circle_pirozzoli_1000_steps():
+    """Solver/test/Euler/BoxAroundCirclePirozzoli: Euler, M 0.3, P=3 Gauss-Lobatto, split-form with the Pirozzoli two-point
+    flux, standard Roe solver, RK3, cfl 0.7, 1000 steps on the curved mesh around a cylinder (free-slip walls, inflow).
+    Final time (the sum of the CFL steps) and residuals with the 1e-11 tolerance of SETUP/ProblemFile.f90:322-363."""
+    import math
+    from horses3d_b200.physics import bc_parameters
+    phys = make_physics(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli", riemann="standard roe")
+    zones = [("innercylinder", "freeslipwall"), ("front", "inflow"), ("bottom", "freeslipwall"), ("top", "freeslipwall"),
+             ("back", "inflow"), ("left", "inflow"), ("right", "inflow")]
+    p_in, rho_in = 1.0 / phys.gammaM2, 1.0
+    v_in = phys.Mach * math.sqrt(phys.gamma * p_in / rho_in)
+    params = [bc_parameters("inflow", phys, rho=rho_in, v=v_in, aoa_theta=0.0, aoa_phi=0.0, p=p_in) if t == "inflow" else bc_parameters(t, phys)
+              for _, t in zones]
+    m = HostMesh.read(BOX_CIRCLE_MESH).connect([(z, t, None) for z, t in zones], np.array(params)).geometry(3, GAUSSLOBATTO)
+    assert m.sizes()[0] == 400
+    sem = DGSem(oracle_api.OracleApi(), m, phys)
+    Q = np.zeros(sem.node_coordinates().shape[:-1] + (5,))
+    Q[..., 0], Q[..., 1] = 1.0, 1.0
+    Q[..., 4] = (1.0 / phys.gammaM2) / (phys.gamma - 1.0) + 0.5
+    sem.set_Q(Q)
+    rec = sem.integrate(1000, cfl=0.7, dcfl=0.7, monitors=False)[-1]
+    res = np.array([3.2245412233756249E-03, 7.2948338786761158E-02, 7.8482433396760149E-12, 6.3956090995916370E-02, 9.8435366345196243E-02])
+    print("K4 t", rec["t"] - 8.4020848657635838, "res", rec["residuals"] - res)
+    assert abs(rec["t"] - 8.4020848657635838) < 1.0e-11
+    assert np.abs(rec["residuals"] - res).max() < 1.0e-11
 
 
 @pytest.mark.parametrize("nodes,inviscid,avg", [(GAUSS, "standard", "standard"), (GAUSSLOBATTO, "split-form", "pirozzoli"),
