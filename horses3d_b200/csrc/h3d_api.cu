@@ -814,23 +814,37 @@ int h3d_compute_time_derivative(h3d_handle h, double time) {
     return residual(h, rk);
 }
 
+namespace {
+// Williamson RK3 (ExplicitMethods.f90:690-692) and Carpenter-Kennedy RK5 (:812-816) coefficients
+const double RK_A3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, RK_C3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
+const double RK_A5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
+const double RK_C5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
+int rkStage(h3d_context* h, int ns, int k, double dt) {
+    const double *a = ns == 3 ? RK_A3 : RK_A5, *c = ns == 3 ? RK_C3 : RK_C5;
+    RkArgs rk{1, (k == ns - 1 || h->storeQDotAlways) ? 1 : 0, 1, a[k], c[k] * dt};
+    return residual(h, rk);
+}
+}  // namespace
+
 int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_step) {
     (void)t;
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
-    static const double a3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, c3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
-    static const double a5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
-    static const double c5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
     const int ns = scheme == H3D_RK3 ? 3 : (scheme == H3D_RK5 ? 5 : 0);
     if (!ns) { h->err = "unknown Runge-Kutta scheme"; return 1; }
-    const double *a = ns == 3 ? a3 : a5, *c = ns == 3 ? c3 : c5;
-    for (int k = 0; k < ns; ++k) {
-        RkArgs rk{1, (k == ns - 1 || h->storeQDotAlways) ? 1 : 0, 1, a[k], c[k] * dt};
-        int rc = residual(h, rk);
-        if (rc) return rc;
-    }
+    for (int k = 0; k < ns; ++k) { int rc = rkStage(h, ns, k, dt); if (rc) return rc; }
     if (ctd_after_step) { RkArgs rk{0, 1, 0, 0.0, 0.0}; int rc = residual(h, rk); if (rc) return rc; }
     return 0;
+}
+
+int h3d_rk_stage(h3d_handle h, int scheme, int stage, double t, double dt) {
+    (void)t;
+    if (checkReady(h)) return 1;
+    CTX_CHECK(cudaSetDevice(h->device));
+    const int ns = scheme == H3D_RK3 ? 3 : (scheme == H3D_RK5 ? 5 : 0);
+    if (!ns) { h->err = "unknown Runge-Kutta scheme"; return 1; }
+    if (stage < 0 || stage >= ns) { h->err = "Runge-Kutta stage out of range"; return 1; }
+    return rkStage(h, ns, stage, dt);
 }
 
 int h3d_max_residuals(h3d_handle h, double out[5]) {

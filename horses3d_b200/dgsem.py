@@ -107,11 +107,27 @@ class DGSem:
     def ComputeTimeDerivative(self, time=0.0):
         self.api.call("compute_time_derivative", float(time))
 
-    def TakeRK3Step(self, t, dt, ctd_after_step=False):
-        self.api.call("rk_step", P.RK3, float(t), float(dt), int(ctd_after_step))
+    _RK_B = {P.RK3: (0.0, 1.0 / 3.0, 3.0 / 4.0),                                               # ExplicitMethods.f90:690-692
+             P.RK5: (0.0, 0.1496590219993, 0.3704009573644, 0.6222557631345, 0.9582821306748)}   # :812-816
 
-    def TakeRK5Step(self, t, dt, ctd_after_step=False):
-        self.api.call("rk_step", P.RK5, float(t), float(dt), int(ctd_after_step))
+    def _rk_step(self, scheme, t, dt, ctd_after_step, source):
+        """source: None (the source set by set_source, constant over the step) or a callable time -> S array: the
+        UserDefinedSourceTermNS of the reference, evaluated at every stage time (SpatialDiscretization.f90:569-577)."""
+        if source is None:
+            self.api.call("rk_step", scheme, float(t), float(dt), int(ctd_after_step))
+            return
+        for k, b in enumerate(self._RK_B[scheme]):
+            self.set_source(source(t + b * dt))
+            self.api.call("rk_stage", scheme, k, float(t), float(dt))
+        if ctd_after_step:
+            self.set_source(source(t + dt))
+            self.ComputeTimeDerivative(t + dt)
+
+    def TakeRK3Step(self, t, dt, ctd_after_step=False, source=None):
+        self._rk_step(P.RK3, t, dt, ctd_after_step, source)
+
+    def TakeRK5Step(self, t, dt, ctd_after_step=False, source=None):
+        self._rk_step(P.RK5, t, dt, ctd_after_step, source)
 
     def MaxTimeStep(self, cfl, dcfl):
         a, b = C.c_double(), C.c_double()
@@ -142,23 +158,36 @@ class DGSem:
             "enstrophy": 0.5 * self.ScalarVolumeIntegral(P.INT_ENSTROPHY) / vol,
         }
 
-    def integrate(self, nsteps, cfl=None, dcfl=None, dt=None, t0=0.0, scheme="RK3", monitors=True):
+    def integrate(self, nsteps, cfl=None, dcfl=None, dt=None, t0=0.0, scheme="RK3", monitors=True, t_final=None, source=None,
+                  ctd_after_step=False, keep="all"):
         """Explicit branch of TimeIntegrator_t%integrate: initial residual, then per step
-        MaxTimeStep -> RKStep -> ComputeMaxResiduals -> monitors (TimeIntegrator.f90:667-673, 737-959).
-        Returns a list of per-step records (the reference's monitor buffer lines)."""
+        MaxTimeStep -> CorrectDt -> RKStep -> ComputeMaxResiduals -> monitors (TimeIntegrator.f90:667-673, 737-959).
+        t_final selects the time-accurate mode: the step is clipped to land on t_final (CorrectDt, :1130-1135) and the
+        loop ends there (:882-887).  Returns the per-step records (the reference's monitor buffer lines), or only the
+        last one with keep="last"."""
         step = self.TakeRK3Step if scheme.upper() == "RK3" else self.TakeRK5Step
         t = t0
+        if source is not None:
+            self.set_source(source(t))
         self.ComputeTimeDerivative(t)
         rec = [dict(iter=0, t=t, dt=0.0, residuals=self.ComputeMaxResiduals(), **(self.volume_monitors() if monitors else {}))]
+        eps = np.finfo(np.float64).eps
         for k in range(nsteps):
             if dt is None:
                 dtc, dtv = self.MaxTimeStep(cfl, dcfl if dcfl is not None else cfl)
                 step_dt = dtc if dtc < dtv else dtv       # DGSEMClass.f90:1025-1031
             else:
                 step_dt = dt
-            step(t, step_dt)
+            if t_final is not None and t + step_dt > t_final:
+                step_dt = t_final - t
+            step(t, step_dt, ctd_after_step=ctd_after_step, source=source)
             t = t + step_dt
-            if self.checkForNan():
-                raise FloatingPointError("Numerical divergence obtained in solver.")
-            rec.append(dict(iter=k + 1, t=t, dt=step_dt, residuals=self.ComputeMaxResiduals(), **(self.volume_monitors() if monitors else {})))
+            last = (t_final is not None and (t >= t_final or abs(t - t_final) <= 100.0 * eps)) or k == nsteps - 1
+            if keep == "all" or last:
+                if self.checkForNan():
+                    raise FloatingPointError("Numerical divergence obtained in solver.")
+                r = dict(iter=k + 1, t=t, dt=step_dt, residuals=self.ComputeMaxResiduals(), **(self.volume_monitors() if monitors else {}))
+                rec = rec + [r] if keep == "all" else [r]
+            if last:
+                break
         return rec

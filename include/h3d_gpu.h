@@ -173,6 +173,13 @@ int h3d_compute_time_derivative(h3d_handle h, double time);
  * TimeStep_FCN, TimeIntegratorDefinitions.f90:10-35).  ctd_after_step = CTD_AFTER_STEPS (:784). */
 int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_step);
 
+/* One stage (0-based) of the same schemes: residual at t + b_stage dt with the current source, then
+ * G = a_stage G + QDot, Q = Q + c_stage dt G (the loop body of ExplicitMethods.f90:746-760, 857-872).  For
+ * time-dependent user source terms (UserDefinedSourceTermNS is evaluated at the stage time,
+ * SpatialDiscretization.f90:569-577): the adapter calls h3d_set_source between stages.  h3d_rk_step equals the
+ * stages 0..ns-1 in a row. */
+int h3d_rk_stage(h3d_handle h, int scheme, int stage, double t, double dt);
+
 /* ---- per-step reductions (all globally reduced over ranks) ----------------------------------- */
 /* ComputeMaxResiduals (libs/discretization/DGSEMClass.f90:770-856) */
 int h3d_max_residuals(h3d_handle h, double out[5]);

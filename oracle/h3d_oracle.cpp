@@ -1095,27 +1095,41 @@ int orc_set_source(void* p, const double* S) {
 int orc_compute_time_derivative(void* p, double time) { computeTimeDerivative(*(Oracle*)p, time); return 0; }
 
 // TakeRK3Step / TakeRK5Step (libs/timeintegrator/ExplicitMethods.f90:667-788, 790-882)
+namespace {
+const double RK_A3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, RK_B3[3] = {0.0, 1.0 / 3.0, 3.0 / 4.0}, RK_C3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
+const double RK_A5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
+const double RK_B5[5] = {0.0, 0.1496590219993, 0.3704009573644, 0.6222557631345, 0.9582821306748};
+const double RK_C5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
+double rkStage(Oracle& o, int ns, int k, double t, double dt) {   // loop body of ExplicitMethods.f90:746-760, 857-872
+    const double *a = ns == 3 ? RK_A3 : RK_A5, *b = ns == 3 ? RK_B3 : RK_B5, *c = ns == 3 ? RK_C3 : RK_C5;
+    const double tk = t + b[k] * dt;
+    computeTimeDerivative(o, tk);
+    const double ak = a[k], cdt = c[k] * dt;
+#pragma omp parallel for schedule(static)
+    for (size_t q = 0; q < o.Q.size(); ++q) {
+        o.G[q] = ak * o.G[q] + o.QDot[q];
+        o.Q[q] = o.Q[q] + cdt * o.G[q];
+    }
+    return tk;
+}
+}  // namespace
+
 int orc_rk_step(void* p, int scheme, double t, double dt, int ctd_after_step) {
     Oracle& o = *(Oracle*)p;
-    static const double a3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, b3[3] = {0.0, 1.0 / 3.0, 3.0 / 4.0}, c3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
-    static const double a5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
-    static const double b5[5] = {0.0, 0.1496590219993, 0.3704009573644, 0.6222557631345, 0.9582821306748};
-    static const double c5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
     const int ns = scheme == H3D_RK3 ? 3 : scheme == H3D_RK5 ? 5 : 0;
     if (!ns) { o.err = "unknown RK scheme"; return 1; }
-    const double *a = ns == 3 ? a3 : a5, *b = ns == 3 ? b3 : b5, *c = ns == 3 ? c3 : c5;
     double tk = t;
-    for (int k = 0; k < ns; ++k) {
-        tk = t + b[k] * dt;
-        computeTimeDerivative(o, tk);
-        const double ak = a[k], cdt = c[k] * dt;
-#pragma omp parallel for schedule(static)
-        for (size_t q = 0; q < o.Q.size(); ++q) {
-            o.G[q] = ak * o.G[q] + o.QDot[q];
-            o.Q[q] = o.Q[q] + cdt * o.G[q];
-        }
-    }
+    for (int k = 0; k < ns; ++k) tk = rkStage(o, ns, k, t, dt);
     if (ctd_after_step) computeTimeDerivative(o, ns == 3 ? t + dt : tk);
+    return 0;
+}
+
+int orc_rk_stage(void* p, int scheme, int stage, double t, double dt) {
+    Oracle& o = *(Oracle*)p;
+    const int ns = scheme == H3D_RK3 ? 3 : scheme == H3D_RK5 ? 5 : 0;
+    if (!ns) { o.err = "unknown RK scheme"; return 1; }
+    if (stage < 0 || stage >= ns) { o.err = "Runge-Kutta stage out of range"; return 1; }
+    rkStage(o, ns, stage, t, dt);
     return 0;
 }
 

@@ -122,6 +122,39 @@ def test_rk_steps_and_monitors_match_oracle(gpu_api_cls, scheme):
     assert rel_err(Qg, Qo) < 1e-12
 
 
+@pytest.mark.parametrize("scheme", ["RK3", "RK5"])
+def test_stagewise_step_with_time_dependent_source_matches_oracle(gpu_api_cls, scheme):
+    """h3d_rk_stage with the source updated at every stage time (the K3 manufactured source of the reference's
+    NavierStokes/Convergence case), P=7; and rk_step == its stages in a row, bit for bit."""
+    from convergence_case import state_source_in_point
+    mesh = get_mesh(2, 7, GAUSS, 0.1, True)
+    phys = make_physics(flow="NS", mach=0.3, reynolds=10.0)
+    args = (phys.gammaMinus1, phys.gammaM2, phys.mu, phys.kappa)
+    out = []
+    for api in (OracleApi(), gpu_api_cls()):
+        sem = DGSem(api, mesh, phys)
+        X = sem.node_coordinates() / np.pi            # the manufactured state stays positive on [0, 2]^3
+        exact = lambda t: state_source_in_point(X[..., 0], X[..., 1], X[..., 2], t, *args)
+        sem.set_Q(exact(0.0)[0])
+        rec = sem.integrate(3, dt=1.0e-3, scheme=scheme, source=lambda t: exact(t)[1], ctd_after_step=True, monitors=False)
+        out.append((rec, sem.download(Q=True, QDot=True)))
+    (ro, o), (rg, g) = out
+    assert np.abs(o["QDot"]).max() > 1.0
+    assert rel_err(g["Q"], o["Q"]) < TOL_QDOT and rel_err(g["QDot"], o["QDot"]) < TOL_QDOT
+    assert np.abs(ro[-1]["residuals"] - rg[-1]["residuals"]).max() < 1e-12 * np.abs(ro[-1]["residuals"]).max()
+    # constant source: one call per step equals the stages one by one
+    S = exact(0.0)[1]
+    res = []
+    for staged in (False, True):
+        sem = DGSem(gpu_api_cls(), mesh, phys)
+        sem.set_Q(exact(0.0)[0])
+        sem.set_source(S)
+        step = sem.TakeRK3Step if scheme == "RK3" else sem.TakeRK5Step
+        step(0.0, 1.0e-3, source=(lambda t: S) if staged else None)
+        res.append(sem.Q())
+    assert np.array_equal(res[0], res[1])
+
+
 def test_k1_taylor_green_on_gpu(gpu_api_cls):
     """The reference's own TaylorGreen regression (K1) run on the device path."""
     mesh = get_mesh(32, 3, GAUSS)

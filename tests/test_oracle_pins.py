@@ -125,6 +125,59 @@ def test_k5b_cylinder_smagorinsky_100_steps():
     assert np.abs(got - res).max() < 1.0e-7
 
 
+UNIT_CUBE_MESH = "/root/reference/Solver/test/TestMeshes/UnitCube4x4.mesh"
+
+
+def convergence_case(api, t_final=1.0):
+    """Solver/test/NavierStokes/Convergence: manufactured solution, NS, Re 10, M 0.3, P=7 Gauss, Roe, BR1, RK3, cfl 0.5,
+    dcfl 1e5, time-accurate to t_final with the residual recomputed after every step, on the periodic 4x4x4 unit cube."""
+    from convergence_case import W_LGL7, state_source_in_point
+    zones = [("front", "periodic", "back"), ("bottom", "periodic", "top"), ("top", "periodic", "bottom"), ("back", "periodic", "front"),
+             ("left", "periodic", "right"), ("right", "periodic", "left")]
+    m = HostMesh.read(UNIT_CUBE_MESH).connect(zones).geometry(7, GAUSS)
+    phys = make_physics(flow="NS", mach=0.3, reynolds=10.0, riemann="roe")
+    sem = DGSem(api, m, phys)
+    X = sem.node_coordinates()
+    args = (phys.gammaMinus1, phys.gammaM2, phys.mu, phys.kappa)
+    exact = lambda t: state_source_in_point(X[..., 0], X[..., 1], X[..., 2], t, *args)
+    sem.set_Q(exact(0.0)[0])
+    rec = sem.integrate(10 ** 7, cfl=0.5, dcfl=1.0e5, t_final=t_final, source=lambda t: exact(t)[1], ctd_after_step=True, monitors=False, keep="last")[-1]
+    Qe, _, QDe = exact(rec["t"])
+    JW = m.array("jacobian").reshape(X.shape[:-1]) * (W_LGL7[None, :, None, None] * W_LGL7[None, None, :, None] * W_LGL7[None, None, None, :])
+    err = np.sqrt((JW[..., None] * (sem.Q() - Qe) ** 2).sum(axis=(0, 1, 2, 3)))         # FinalCheck, ProblemFile.f90:666-690
+    qerr = np.sqrt((JW[..., None] * (sem.QDot() - QDe) ** 2).sum(axis=(0, 1, 2, 3)))
+    return rec, err, qerr, sem
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(UNIT_CUBE_MESH), reason="reference test mesh not available on this machine")
+def test_k3_navier_stokes_convergence_p7():
+    """Expected values and the 1e-11 tolerance from SETUP/ProblemFile.f90:619-635, 714-790.  Pins the headline polynomial
+    order (P=7), the time-dependent user source term evaluated at the stage times, the time-accurate step clipping and
+    the residual after the step; the state and QDot errors are measured against the exact solution."""
+    rec, err, qerr, _ = convergence_case(oracle_api.OracleApi())
+    assert abs(rec["t"] - 1.0) < 1e-13
+    res = np.array([6.2801762330611588E-01, 1.8889640334957627E+00, 2.5256897695536247E+00, 4.4142472296503827E+00, 2.5163928650671146E+00])
+    e0 = np.array([1.0983475326313417E-06, 1.4788256133056976E-06, 4.5499827613507929E-07, 9.0819927730318800E-07, 2.5402026557722347E-06])
+    q0 = np.array([1.1342700947907287E-05, 1.1638989807665964E-05, 3.5549224957856481E-06, 1.0769093706709006E-05, 2.0658954210939997E-05])
+    print("K3 steps", rec["iter"], "res", np.abs(rec["residuals"] - res).max(), "err", np.abs(err - e0).max(), "qdot err", np.abs(qerr - q0).max())
+    assert np.abs(rec["residuals"] - res).max() < 1.0e-11
+    assert np.abs(err - e0).max() < 1.0e-11
+    assert np.abs(qerr - q0).max() < 1.0e-11
+
+
+def test_rk_step_equals_its_stages():
+    m = HostMesh.box(2, amp=0.1, shuffle=True).connect().geometry(3, GAUSS)
+    phys = make_physics(flow="NS", mach=0.08, reynolds=1600.0)
+    res = []
+    for staged in (False, True):
+        sem = DGSem(oracle_api.OracleApi(), m, phys)
+        sem.set_initial_condition(taylor_green_ic)
+        sem.TakeRK5Step(0.0, 1.0e-3, source=(lambda t: None) if staged else None)
+        sem.TakeRK3Step(1.0e-3, 1.0e-3, source=(lambda t: None) if staged else None)
+        res.append(sem.Q())
+    assert np.array_equal(res[0], res[1])
+
+
 BOX_CIRCLE_MESH = "/root/reference/Solver/test/TestMeshes/BoxAroundCircle3D_extended_pol3.mesh"
 
 
