@@ -46,6 +46,7 @@ class Binding:
         "max_timestep": [C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "volume_integral": [C.c_int, C.POINTER(C.c_double)],
         "has_nan": [C.POINTER(C.c_int)],
+        "surface_integral": [C.c_int, C.c_int, _D],
     }
 
     def __init__(self, lib, prefix, extra=None):

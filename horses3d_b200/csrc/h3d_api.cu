@@ -217,6 +217,47 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_integrals(DevMesh m, size_t
     blockReduce<4, 2>(v, partial + (size_t)blockIdx.x * 4);
 }
 
+// ScalarSurfaceIntegral_Face / VectorSurfaceIntegral_Face (SurfaceIntegrals.f90:124-240, 347-445): every kind in one pass
+// over the face nodes of the zone.  v: 0 surface, 1 mass flow, 2 flow rate, 3 int p, 4-6 int n, 7-9 int p n, 10-12 -int tau n
+__global__ void __launch_bounds__(RED_THREADS) k_red_surface(DevMesh m, Phys ph, int zone, int n, int withGradients, double* partial) {
+    double v[13];
+#pragma unroll
+    for (int q = 0; q < 13; ++q) v[q] = 0.0;
+    const int N2 = n * n;
+    const size_t fs = (size_t)m.nFace * N2;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < fs; t += (size_t)gridDim.x * blockDim.x) {
+        const int f = (int)(t / N2), mm = (int)(t % N2);
+        const int info = m.faceInfo[f];
+        if ((info & 3) != H3D_FACE_BOUNDARY || (info >> 8) - 1 != zone) continue;
+        const double wJ = m.w[mm % n] * m.w[mm / n] * m.fJ[t];
+        double Q[5], nh[3];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) Q[q] = m.fQ[(size_t)q * fs + t];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) nh[d] = m.fN[d * fs + t];
+        const double qn = Q[1] * nh[0] + Q[2] * nh[1] + Q[3] * nh[2];
+        const double pr = pressure(ph, Q);
+        v[0] = v[0] + wJ; v[1] = v[1] + qn * wJ; v[2] = v[2] + (1.0 / Q[0]) * qn * wJ; v[3] = v[3] + pr * wJ;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { v[4 + d] = v[4 + d] + wJ * nh[d]; v[7 + d] = v[7 + d] + (pr * nh[d]) * wJ; }
+        if (withGradients) {
+            double gx[5], gy[5], gz[5], ux[3], uy[3], uz[3], mu, kappa;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(size_t)(0 * 10 + q) * fs + t]; gy[q] = m.fU[(size_t)(1 * 10 + q) * fs + t]; gz[q] = m.fU[(size_t)(2 * 10 + q) * fs + t]; }
+            velocity_gradients(Q, gx, gy, gz, ux, uy, uz);
+            laminar_mu_kappa(ph, Q, mu, kappa);
+            const double divV = ux[0] + uy[1] + uz[2];
+            double tau[3][3];
+            tau[0][0] = mu * (2.0 * ux[0] - 2.0 / 3.0 * divV); tau[1][0] = mu * (ux[1] + uy[0]); tau[2][0] = mu * (ux[2] + uz[0]);
+            tau[0][1] = tau[1][0]; tau[1][1] = mu * (2.0 * uy[1] - 2.0 / 3.0 * divV); tau[2][1] = mu * (uy[2] + uz[1]);
+            tau[0][2] = tau[2][0]; tau[1][2] = tau[2][1]; tau[2][2] = mu * (2.0 * uz[2] - 2.0 / 3.0 * divV);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) v[10 + d] = v[10 + d] - (tau[d][0] * nh[0] + tau[d][1] * nh[1] + tau[d][2] * nh[2]) * wJ;
+        }
+    }
+    blockReduce<13, 2>(v, partial + (size_t)blockIdx.x * 13);
+}
+
 template <int K, int OP>
 __global__ void __launch_bounds__(1024) k_red_final(const double* partial, int nBlocks, double* out) {
     double v[K];
@@ -490,7 +531,7 @@ int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nc
     cudaStreamCreateWithFlags(&h->sComm, cudaStreamNonBlocking);
     for (cudaEvent_t* ev : {&h->evA, &h->evB, &h->evFaces, &h->evGrad, &h->evSent}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
-    cudaMalloc((void**)&h->dPartial, sizeof(double) * (RED_BLOCKS * 8 + 64));
+    cudaMalloc((void**)&h->dPartial, sizeof(double) * (RED_BLOCKS * 16 + 64));
     cudaMallocHost((void**)&h->hScalars, sizeof(double) * 64);
     if (nranks > 1) {
         if (!nccl_unique_id) return fail("nranks > 1 needs an ncclUniqueId");
@@ -897,6 +938,34 @@ int h3d_volume_integral(h3d_handle h, int kind, double* val) {
     CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
     CTX_CHECK(cudaStreamSynchronize(h->sCompute));
     *val = h->hScalars[kind];
+    return 0;
+}
+
+int h3d_surface_integral(h3d_handle h, int zone, int kind, double out[3]) {
+    if (checkReady(h)) return 1;
+    if (kind < H3D_SURF_SURFACE || kind > H3D_SURF_VISCOUS_FORCE) { h->err = "unknown surface integral"; return 1; }
+    const bool viscous = kind == H3D_SURF_TOTAL_FORCE || kind == H3D_SURF_VISCOUS_FORCE;
+    if (viscous && !h->physics.computeGradients) { h->err = "surface integral needs gradients"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    if (!h->facesValid) { int rc = doProlong(h, 0, h->nElem, h->sCompute); if (rc) return rc; h->facesValid = true; }
+    k_red_surface<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, h->ph, zone, h->n, h->physics.computeGradients ? 1 : 0, h->dPartial);
+    k_red_final<13, 2><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 13);
+    h->launches += 2;
+    if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 13, 13, ncclSum)) return 3;
+    CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 13, 13 * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+    const double* s = h->hScalars;
+    out[0] = out[1] = out[2] = 0.0;
+    switch (kind) {
+        case H3D_SURF_SURFACE: out[0] = s[0]; break;
+        case H3D_SURF_MASS_FLOW: out[0] = s[1]; break;
+        case H3D_SURF_FLOW_RATE: out[0] = s[2]; break;
+        case H3D_SURF_PRESSURE: out[0] = s[3]; break;
+        case H3D_SURF_VEC_SURFACE: for (int d = 0; d < 3; ++d) out[d] = s[4 + d]; break;
+        case H3D_SURF_PRESSURE_FORCE: for (int d = 0; d < 3; ++d) out[d] = s[7 + d]; break;
+        case H3D_SURF_VISCOUS_FORCE: for (int d = 0; d < 3; ++d) out[d] = s[10 + d]; break;
+        default: for (int d = 0; d < 3; ++d) out[d] = s[7 + d] + s[10 + d];
+    }
     return 0;
 }
 

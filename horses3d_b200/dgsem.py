@@ -144,6 +144,38 @@ class DGSem:
         self.api.call("volume_integral", int(kind), C.byref(v))
         return v.value
 
+    def SurfaceIntegral(self, zone, kind):
+        """ScalarSurfaceIntegral / VectorSurfaceIntegral (libs/monitors/SurfaceIntegrals.f90:40, 248); zone = name or index."""
+        if isinstance(zone, str):
+            zone = [b[0].lower() for b in self.mesh.bcs].index(zone.lower())
+        out = np.zeros(3)
+        self.api.call("surface_integral", int(zone), int(kind), _ptr(out, np.float64))
+        return out[0] if kind <= P.SURF_PRESSURE else out
+
+    def surface_monitor(self, zone, variable, direction=None, reference_surface=None, Lref=1.0):
+        """SurfaceMonitor_Update (libs/monitors/SurfaceMonitor.f90:337-446) with the reference values of
+        PhysicsStorage_NS.f90:290-306 (T_ref = 520 R, p_ref = 101325 Pa, R = 287.15)."""
+        ph, variable = self.physics, variable.lower()
+        T_ref = 520.0 * 5.0 / 9.0
+        rho_ref = 101325.0 / (287.15 * T_ref)
+        V_ref = ph.Mach * np.sqrt(ph.gamma * 287.15 * T_ref)
+        d = None if direction is None else np.asarray(direction, dtype=np.float64)
+        if variable == "mass-flow":
+            return self.SurfaceIntegral(zone, P.SURF_MASS_FLOW)
+        if variable == "flow":
+            return self.SurfaceIntegral(zone, P.SURF_FLOW_RATE)
+        if variable == "pressure-average":
+            return self.SurfaceIntegral(zone, P.SURF_PRESSURE) / self.SurfaceIntegral(zone, P.SURF_SURFACE)
+        if variable in ("pressure-force", "viscous-force", "force"):
+            kind = {"pressure-force": P.SURF_PRESSURE_FORCE, "viscous-force": P.SURF_VISCOUS_FORCE, "force": P.SURF_TOTAL_FORCE}[variable]
+            F = rho_ref * V_ref ** 2 * Lref ** 2 * self.SurfaceIntegral(zone, kind)
+            return float(np.dot(F, d))
+        if variable in ("lift", "drag"):
+            kind = P.SURF_TOTAL_FORCE if ph.flowIsNavierStokes else P.SURF_PRESSURE_FORCE
+            F = 2.0 * Lref ** 2 * self.SurfaceIntegral(zone, kind) / reference_surface
+            return float(np.dot(F, d))
+        raise ValueError("surface monitor variable not recognized: " + variable)
+
     def checkForNan(self):
         f = C.c_int()
         self.api.call("has_nan", C.byref(f))

@@ -187,6 +187,20 @@ int h3d_max_residuals(h3d_handle h, double out[5]);
 int h3d_max_timestep(h3d_handle h, double cfl, double dcfl, double* dt_conv, double* dt_visc);
 /* ScalarVolumeIntegral (libs/monitors/VolumeIntegrals.f90:76-120,167-286): raw integral, H3D_INT_* */
 int h3d_volume_integral(h3d_handle h, int kind, double* val);
+/* ScalarSurfaceIntegral / VectorSurfaceIntegral over the faces of boundary zone `zone` (libs/monitors/SurfaceIntegrals.f90:
+ * 40-240, 248-445), from the prolonged state of the owning element and, for the viscous kinds, the prolonged gradients of
+ * the last residual evaluation (getStressTensor, Physics_NS.f90:822-886).  Raw integrals: the monitors' scalings
+ * (SurfaceMonitor.f90:356-446: rho_ref V_ref^2 Lref^2, 2 Lref^2 / reference surface, direction) stay with the caller.
+ * out[3]: scalar kinds fill out[0]. */
+#define H3D_SURF_SURFACE 0         /* int dS                                   */
+#define H3D_SURF_MASS_FLOW 1       /* int rho u.n dS                            */
+#define H3D_SURF_FLOW_RATE 2       /* int u.n dS                                */
+#define H3D_SURF_PRESSURE 3        /* int p dS (scalar PRESSURE_FORCE: pressure-average numerator) */
+#define H3D_SURF_VEC_SURFACE 4     /* int n dS                                  */
+#define H3D_SURF_TOTAL_FORCE 5     /* int (p n - tau n) dS                      */
+#define H3D_SURF_PRESSURE_FORCE 6  /* int p n dS                                */
+#define H3D_SURF_VISCOUS_FORCE 7   /* - int tau n dS                            */
+int h3d_surface_integral(h3d_handle h, int zone, int kind, double out[3]);
 /* checkForNan (ExplicitMethods.f90:1856-1905): flag = 1 if any NaN in Q on any rank */
 int h3d_has_nan(h3d_handle h, int* flag);
 

@@ -1175,6 +1175,59 @@ int orc_max_timestep(void* p, double cfl, double dcfl, double* dt_conv, double* 
 }
 
 // ScalarVolumeIntegral (libs/monitors/VolumeIntegrals.f90:76-120, 167-286)
+// ScalarSurfaceIntegral / VectorSurfaceIntegral (libs/monitors/SurfaceIntegrals.f90:40-445) with getStressTensor
+// (Physics_NS.f90:822-886); the state (and gradients) are prolonged anew as the reference does (:57-77)
+int orc_surface_integral(void* p, int zone, int kind, double* out) {
+    Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
+    if (kind < H3D_SURF_SURFACE || kind > H3D_SURF_VISCOUS_FORCE) { o.err = "unknown surface integral"; return 1; }
+    const bool viscous = kind == H3D_SURF_TOTAL_FORCE || kind == H3D_SURF_VISCOUS_FORCE;
+    if (viscous && !o.ph.computeGradients) { o.err = "surface integral needs gradients"; return 1; }
+    prolongToFaces(o, 5, o.Q, o.fQ);
+    if (o.ph.computeGradients) { prolongToFaces(o, 5, o.Ux, o.fUx); prolongToFaces(o, 5, o.Uy, o.fUy); prolongToFaces(o, 5, o.Uz, o.fUz); }
+    double val[3] = {0, 0, 0};
+    for (int f = 0; f < o.nFace; ++f) {
+        if (o.faceType[f] != H3D_FACE_BOUNDARY || o.faceZone[f] != zone) continue;
+        double fv[3] = {0, 0, 0};
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            const double* Q = &o.fQ[ix.fnode(f, 0, i, j) * 5];
+            const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
+            const double Jf = o.fJac[ix.gnode(f, i, j)];
+            switch (kind) {
+                case H3D_SURF_SURFACE: fv[0] = fv[0] + o.w[i] * o.w[j] * Jf; break;
+                case H3D_SURF_MASS_FLOW: fv[0] = fv[0] + (Q[IRHOU] * nh[0] + Q[IRHOV] * nh[1] + Q[IRHOW] * nh[2]) * o.w[i] * o.w[j] * Jf; break;
+                case H3D_SURF_FLOW_RATE: fv[0] = fv[0] + (1.0 / Q[IRHO]) * (Q[IRHOU] * nh[0] + Q[IRHOV] * nh[1] + Q[IRHOW] * nh[2]) * o.w[i] * o.w[j] * Jf; break;
+                case H3D_SURF_PRESSURE: { double pr = Pressure(o, Q); fv[0] = fv[0] + pr * o.w[i] * o.w[j] * Jf; } break;
+                case H3D_SURF_VEC_SURFACE: for (int d = 0; d < 3; ++d) fv[d] = fv[d] + o.w[i] * o.w[j] * Jf * nh[d]; break;
+                case H3D_SURF_PRESSURE_FORCE: { double pr = Pressure(o, Q); for (int d = 0; d < 3; ++d) fv[d] = fv[d] + (pr * nh[d]) * Jf * o.w[i] * o.w[j]; } break;
+                default: {
+                    double U_x[3], U_y[3], U_z[3], tau[3][3], mu, kappa;
+                    getVelocityGradients_State(Q, &o.fUx[ix.fnode(f, 0, i, j) * 5], &o.fUy[ix.fnode(f, 0, i, j) * 5], &o.fUz[ix.fnode(f, 0, i, j) * 5], U_x, U_y, U_z);
+                    get_laminar_mu_kappa(o, Q, mu, kappa);      // mu = mu0 * SutherlandsLaw(T)
+                    double divV = U_x[IX] + U_y[IY] + U_z[IZ];
+                    tau[IX][IX] = mu * (2.0 * U_x[IX] - 2.0 / 3.0 * divV);
+                    tau[IY][IX] = mu * (U_x[IY] + U_y[IX]);
+                    tau[IZ][IX] = mu * (U_x[IZ] + U_z[IX]);
+                    tau[IX][IY] = tau[IY][IX];
+                    tau[IY][IY] = mu * (2.0 * U_y[IY] - 2.0 / 3.0 * divV);
+                    tau[IZ][IY] = mu * (U_y[IZ] + U_z[IY]);
+                    tau[IX][IZ] = tau[IZ][IX];
+                    tau[IY][IZ] = tau[IZ][IY];
+                    tau[IZ][IZ] = mu * (2.0 * U_z[IZ] - 2.0 / 3.0 * divV);
+                    double pr = Pressure(o, Q);
+                    for (int d = 0; d < 3; ++d) {
+                        double tn = tau[d][0] * nh[0] + tau[d][1] * nh[1] + tau[d][2] * nh[2];   // matmul(tau, n)
+                        if (kind == H3D_SURF_TOTAL_FORCE) fv[d] = fv[d] + (pr * nh[d] - tn) * Jf * o.w[i] * o.w[j];
+                        else fv[d] = fv[d] - tn * Jf * o.w[i] * o.w[j];
+                    }
+                }
+            }
+        }
+        for (int d = 0; d < 3; ++d) val[d] = val[d] + fv[d];
+    }
+    for (int d = 0; d < 3; ++d) out[d] = val[d];
+    return 0;
+}
+
 int orc_volume_integral(void* p, int kind, double* out) {
     Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
     double val = 0.0;

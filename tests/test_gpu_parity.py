@@ -104,6 +104,31 @@ def test_boundary_conditions_and_les_match_oracle(gpu_api_cls, ne, N, nodes, amp
     assert rel_err(sg.Q(), so.Q()) < TOL_QDOT
 
 
+def test_surface_integrals_match_oracle(gpu_api_cls):
+    """ScalarSurfaceIntegral / VectorSurfaceIntegral of every kind on every zone of the channel mesh, after an RK step
+    (prolonged updated state, gradients of the last stage as the reference has them)."""
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0)
+    mesh = get_mesh(3, 4, GAUSS, 0.1, True, bc="channel", phys=phys)
+    sems = []
+    for api in (OracleApi(), gpu_api_cls()):
+        sem = DGSem(api, mesh, phys)
+        sem.set_initial_condition(lambda x: channel_state(x, phys))
+        sem.TakeRK3Step(0.0, 1.0e-3)
+        sems.append(sem)
+    so, sg = sems
+    nonzero = 0
+    for zone in range(len(mesh.bcs)):
+        for kind in range(8):
+            a, b = np.atleast_1d(so.SurfaceIntegral(zone, kind)), np.atleast_1d(sg.SurfaceIntegral(zone, kind))
+            assert np.abs(a - b).max() <= 1e-12 * max(np.abs(a).max(), 1.0), (zone, kind, a, b)
+            nonzero += int(np.abs(a).max() > 1e-3)
+    assert nonzero > 20
+    assert abs(so.surface_monitor(0, "drag", [1.0, 0.0, 0.0], reference_surface=1.0) - sg.surface_monitor(0, "drag", [1.0, 0.0, 0.0], reference_surface=1.0)) < 1e-11
+    e = gpu_api_cls()
+    with pytest.raises(RuntimeError):
+        DGSem(e, get_mesh(2, 2, GAUSS), make_physics(flow="Euler")).SurfaceIntegral(0, P.SURF_TOTAL_FORCE)
+
+
 @pytest.mark.parametrize("scheme", ["RK3", "RK5"])
 def test_rk_steps_and_monitors_match_oracle(gpu_api_cls, scheme):
     mesh = get_mesh(4, 3, GAUSS, 0.1, True)
