@@ -199,7 +199,7 @@ struct GradSmem {
     static constexpr int phase1 = C::EPB * (5 * C::NS + 6 * 9 * C::N2);
     static constexpr int phase2 = C::EPB * 15 * C::NS;
     static constexpr int fields = TMA ? C::EPB * (15 * C::N3 + 6 * 9 * C::N2 + 15 * C::NS) : (phase1 > phase2 ? phase1 : phase2);
-    static constexpr size_t bytes = sizeof(double) * (fields + C::N2 + 4 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 8) + 16;
+    static constexpr size_t bytes = sizeof(double) * (fields + C::N2 + 4 * n) + sizeof(int) * (TMA ? 2 : 1) * C::EPB * (6 * C::N2 + 8) + 32;
 };
 
 // interface data of one element-trace node: raw loads (issued early) and their reduction to uStar / normal / J_f
@@ -256,14 +256,22 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
     double* sDT = smem + GradSmem<n, TMA>::fields;              // [n][n]
     double* sB = sDT + N2;
     double* sV = sB + 2 * n;
-    int* sTr = (int*)(sV + 2 * n);                              // [EPB][6][N2]
-    int* sInfo = sTr + EPB * 6 * N2;                            // [EPB][8]
-    uint64_t* bar = (uint64_t*)(((uintptr_t)(sInfo + EPB * 8) + 7) & ~(uintptr_t)7);
+    constexpr int TABI = EPB * (6 * N2 + 8);                    // ints of one face-table set: trace offsets [EPB][6][N2] + info [EPB][8]
+    int* sTab = (int*)(sV + 2 * n);                             // TMA: two sets, the next tile's is prefetched by bulk copies
+    uint64_t* bar = (uint64_t*)(((uintptr_t)(sTab + (TMA ? 2 : 1) * TABI) + 7) & ~(uintptr_t)7);   // bar[0]: fields, bar[1..2]: face tables
     const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const size_t es = (size_t)m.nElem * N3;
     const int nTiles = (eEnd - eBegin + EPB - 1) / EPB;
     for (int t = threadIdx.x; t < N2; t += blockDim.x) sDT[t] = m.DT[t];
     if (threadIdx.x < 2 * n) { sB[threadIdx.x] = m.b[threadIdx.x]; sV[threadIdx.x] = m.v[threadIdx.x]; }
+    auto issueTab = [&](int tile, int buf) {   // thread 0: face tables of the tile
+        const int e0 = eBegin + tile * EPB;
+        const int nLoc = min(EPB, eEnd - e0);
+        int* dst = sTab + buf * TABI;
+        mbar_arrive_expect_tx(bar + 1 + buf, (uint32_t)(nLoc * (6 * N2 + 8) * sizeof(int)));
+        bulk_g2s(dst, m.elemTrace + (size_t)e0 * 6 * N2, (uint32_t)(nLoc * 6 * N2 * sizeof(int)), bar + 1 + buf);
+        bulk_g2s(dst + EPB * 6 * N2, m.elemInfo + (size_t)e0 * 8, (uint32_t)(nLoc * 8 * sizeof(int)), bar + 1 + buf);
+    };
     auto issue = [&](int tile) {   // thread 0: bulk copies of the tile's 15 fields
         const int e0 = eBegin + tile * EPB;
         const int nLoc = min(EPB, eEnd - e0);
@@ -276,18 +284,26 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
         bulk_g2s(sIn + 14 * TN3, m.invJ + (size_t)e0 * N3, bytes, bar);
     };
     if (TMA) {
-        if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+        if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); fence_barrier_init(); }
         __syncthreads();
-        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) issue(blockIdx.x);
+        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) { issueTab(blockIdx.x, 0); issue(blockIdx.x); }
     }
     uint32_t parity = 0;
     GradIface gi[IFI];
     bool havePrefetch = false;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++iter) {
         const int e0 = eBegin + tile * EPB, e = e0 + le;
         const int nLocal = min(EPB, eEnd - e0);
         const bool active = e < eEnd;
-        load_face_tables<n>(m, sTr, sInfo, e0, nLocal);
+        const int tbuf = TMA ? (iter & 1) : 0;
+        int* sTr = sTab + tbuf * TABI;                          // [EPB][6][N2]
+        int* sInfo = sTr + EPB * 6 * N2;                        // [EPB][8]
+        if (TMA) {   // as in k_volume: the other table set was last read by the previous tile's prolongation
+            if (threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issueTab(tile + gridDim.x, tbuf ^ 1);
+        } else {
+            load_face_tables<n>(m, sTr, sInfo, e0, nLocal);
+        }
         // interface data of the six faces at element-trace nodes (prefetched during the previous tile when possible)
         if (!havePrefetch) {
 #pragma unroll
@@ -317,6 +333,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                 }
             }
         } else {
+            mbar_wait(bar + 1 + tbuf, (uint32_t)((iter >> 1) & 1));
             mbar_wait(bar, parity); parity ^= 1;
         }
         __syncthreads();
