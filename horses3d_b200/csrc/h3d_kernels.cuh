@@ -272,21 +272,23 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
         bulk_g2s(dst, m.elemTrace + (size_t)e0 * 6 * N2, (uint32_t)(nLoc * 6 * N2 * sizeof(int)), bar + 1 + buf);
         bulk_g2s(dst + EPB * 6 * N2, m.elemInfo + (size_t)e0 * 8, (uint32_t)(nLoc * 8 * sizeof(int)), bar + 1 + buf);
     };
-    auto issue = [&](int tile) {   // thread 0: bulk copies of the tile's 15 fields
+    // bulk copies of the tile's 15 fields: lane 0 of warp w issues copy w (one thread issuing all of them would keep its
+    // warp behind the others at the next barrier); the transaction count is posted by thread 0 alone
+    auto issue = [&](int tile) {
+        if (threadIdx.x & 31) return;
         const int e0 = eBegin + tile * EPB;
         const int nLoc = min(EPB, eEnd - e0);
         const uint32_t bytes = (uint32_t)(nLoc * N3 * sizeof(double));
-        mbar_arrive_expect_tx(bar, 15 * bytes);
-#pragma unroll 1
-        for (int c = 0; c < 5; ++c) bulk_g2s(sIn + c * TN3, m.Q + c * es + (size_t)e0 * N3, bytes, bar);
-#pragma unroll 1
-        for (int c = 0; c < 9; ++c) bulk_g2s(sIn + (5 + c) * TN3, m.Ja + c * es + (size_t)e0 * N3, bytes, bar);
-        bulk_g2s(sIn + 14 * TN3, m.invJ + (size_t)e0 * N3, bytes, bar);
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, 15 * bytes);
+        for (int c = threadIdx.x >> 5; c < 15; c += (NT + 31) / 32) {
+            const double* src = c < 5 ? m.Q + c * es : (c < 14 ? m.Ja + (c - 5) * es : m.invJ);
+            bulk_g2s(sIn + c * TN3, src + (size_t)e0 * N3, bytes, bar);
+        }
     };
     if (TMA) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); fence_barrier_init(); }
         __syncthreads();
-        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) { issueTab(blockIdx.x, 0); issue(blockIdx.x); }
+        if ((int)blockIdx.x < nTiles) { if (threadIdx.x == 0) issueTab(blockIdx.x, 0); issue(blockIdx.x); }
     }
     uint32_t parity = 0;
     GradIface gi[IFI];
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
         __syncthreads();   // U and the interface data are consumed
         const int next = tile + gridDim.x;
         if (TMA) {
-            if (threadIdx.x == 0 && next < nTiles) issue(next);
+            if (next < nTiles) issue(next);
         } else {
             if (active) {
 #pragma unroll
@@ -580,6 +582,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
         bulk_g2s(dst, m.elemTrace + (size_t)e0 * 6 * N2, (uint32_t)(nLoc * 6 * N2 * sizeof(int)), bar + 2 + buf);
         bulk_g2s(dst + EPB * 6 * N2, m.elemInfo + (size_t)e0 * 8, (uint32_t)(nLoc * 8 * sizeof(int)), bar + 2 + buf);
     };
+    // (spreading these copies over the warps as k_gradient does costs this kernel 4 %: no warp waits for warp 0 here)
     auto issue = [&](int tile) {   // thread 0: bulk copies of the tile's staged fields
         const int e0 = eBegin + tile * EPB;
         const int nLoc = min(EPB, eEnd - e0);
