@@ -45,6 +45,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-ne", type=int, default=8, help="elements per direction of the bounded CPU sample")
+    # the other configurations of SURVEY 8d (C1 P=3, C3 Euler split-form sweeps); the defaults are the headline C2 / C4
+    ap.add_argument("--flow", default="NS", choices=["NS", "Euler"])
+    ap.add_argument("--inviscid", default="standard", choices=["standard", "split-form"])
+    ap.add_argument("--averaging", default="standard")
+    ap.add_argument("--riemann", default="roe")
+    ap.add_argument("--nodes", default="gauss", choices=["gauss", "gauss-lobatto"])
     return ap.parse_args()
 
 
@@ -123,9 +129,14 @@ def main_b200(args):
     import torch.distributed as dist
     from horses3d_b200.capi import GpuApi, _ptr
     from horses3d_b200.dgsem import DGSem, taylor_green_ic
-    from horses3d_b200.hostmesh import GAUSS, HostMesh
+    from horses3d_b200.hostmesh import GAUSS, GAUSSLOBATTO, HostMesh
     from horses3d_b200.physics import make_physics
     import ctypes as C
+    nodes = GAUSS if args.nodes == "gauss" else GAUSSLOBATTO
+    euler = args.flow == "Euler"
+    phys_kw = dict(flow=args.flow, mach=0.08, reynolds=1600.0, riemann=args.riemann, inviscid=args.inviscid, averaging=args.averaging)
+    headline = (not euler) and args.inviscid == "standard" and args.riemann == "roe" and args.nodes == "gauss"
+    scheme = "%s, %s%s+%s" % (args.flow, "StandardDG" if args.inviscid == "standard" else "SplitDG-" + args.averaging, "" if euler else "+BR1", args.riemann)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -160,11 +171,11 @@ def main_b200(args):
             idx = np.arange(nElemGlobal)
             part = ((idx % ex) // args.ne + px * (((idx // ex) % ey) // args.ne + py * ((idx // (ex * ey)) // args.ne))).astype(np.int32)
         mesh = gmesh.extract(part, rank)
-        mesh.geometry(N, GAUSS)
+        mesh.geometry(N, nodes)
     else:
-        mesh = gmesh.geometry(N, GAUSS)
+        mesh = gmesh.geometry(N, nodes)
     api = GpuApi(rank=rank, nranks=world, device=local, nccl_id=nccl_id)
-    sem = DGSem(api, mesh, make_physics(flow="NS", mach=0.08, reynolds=1600.0, riemann="roe"))
+    sem = DGSem(api, mesh, make_physics(**phys_kw))
     Q0 = taylor_green_ic(sem.node_coordinates())
     sem.set_Q(Q0)
     ndof_global = nElemGlobal * n ** 3
@@ -218,20 +229,23 @@ def main_b200(args):
                 peaks = json.load(open(pk))
                 peak, src = float(peaks.get("hbm_gbs", 6650.0)), "measured"
             ndof_local = sem.NDOF
-            achieved = B_ALG_VOLUME_KERNEL(n) * ndof_local / (vol_ms * 1e-3) / 1e9
-            stage_gbs = B_ALG_NS_STAGE(n) * value / world / 1e9
+            # Euler without gradients: stage 240 + 936/n, volume kernel Q 40 + metrics 80 + G 40 read, G 40 + Q 40 written
+            b_vol = (240.0 + 480.0 / n) if euler else B_ALG_VOLUME_KERNEL(n)
+            b_stage = (240.0 + 936.0 / n) if euler else B_ALG_NS_STAGE(n)
+            achieved = b_vol * ndof_local / (vol_ms * 1e-3) / 1e9
+            stage_gbs = b_stage * value / world / 1e9
             # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very workload
             traffic, tsrc = None, None
             tf = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-            if os.path.exists(tf) and world == 1:
+            if os.path.exists(tf) and world == 1 and headline:
                 rec = json.load(open(tf)).get("ne%d_P%d" % (args.ne, args.order))
                 if rec:
                     traffic, tsrc = rec["k_volume_bytes_per_launch"], rec["source"]
             roof = {"bound": "hbm", "kernel": "k_volume<%d>" % n, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc, "avg_launch_ms": vol_ms,
-                    "alg_bytes_per_dof": B_ALG_VOLUME_KERNEL(n),
+                    "alg_bytes_per_dof": b_vol,
                     "per_kernel_ms": {"gradient": prof[0] / max(prof[1], 1), "riemann": prof[2] / max(prof[3], 1), "volume": vol_ms},
-                    "stage": {"alg_bytes_per_dof_stage": B_ALG_NS_STAGE(n), "achieved": stage_gbs, "frac": stage_gbs / peak}}
+                    "stage": {"alg_bytes_per_dof_stage": b_stage, "achieved": stage_gbs, "frac": stage_gbs / peak}}
         except Exception as ex:  # profile hooks are optional
             roof = {"bound": "hbm", "error": str(ex)}
 
@@ -278,11 +292,12 @@ def main_b200(args):
 
     if rank == 0:
         line = {
-            "metric": "DOF-updates/s (TGV P=%d explicit RK3, NS/BR1/Roe)" % N, "value": value, "unit": "DOF-updates/s", "tpdof_s": 1.0 / value,
+            "metric": "DOF-updates/s (TGV P=%d explicit RK3, %s)" % (N, "NS/BR1/Roe" if headline else scheme), "value": value, "unit": "DOF-updates/s", "tpdof_s": 1.0 / value,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "Taylor-Green vortex Re=1600 M=0.08, %dx%dx%d curvilinear hex elements, P=%d Gauss, StandardDG+BR1+Roe, RK3, fixed dt"
-                                   % (args.ne * px, args.ne * py, args.ne * pz, N),
+            "config": {"workload": "Taylor-Green vortex Re=1600 M=0.08, %dx%dx%d curvilinear hex elements, P=%d %s, %s, RK3, fixed dt"
+                                   % (args.ne * px, args.ne * py, args.ne * pz, N, "Gauss" if args.nodes == "gauss" else "Gauss-Lobatto",
+                                      "StandardDG+BR1+Roe" if headline else scheme),
                        "ndof": ndof_global, "elements_per_gpu": args.ne ** 3, "partition": args.partition if world > 1 else "none",
                        "l2": "inputs larger than L2 (state + gradients + metrics = %.1f GB per GPU)" % (sem.NDOF * 8 * (30 + 10) / 1e9)},
             "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
