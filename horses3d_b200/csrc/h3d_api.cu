@@ -570,7 +570,7 @@ int h3d_last_error_copy(h3d_handle h, char* buf, int len) {
 }
 
 int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
-    if (p->riemann < H3D_RIEMANN_ROE || p->riemann > H3D_RIEMANN_UDISS) { h->err = "Riemann Solver not recognized."; return 1; }
+    if (p->riemann < H3D_RIEMANN_ROE || p->riemann > H3D_RIEMANN_MATRIXDISS) { h->err = "Riemann Solver not recognized."; return 1; }
     if (p->averaging < H3D_AVG_STANDARD || p->averaging > H3D_AVG_CHANDRASEKAR) { h->err = "Averaging not recognized."; return 1; }
     if (p->inviscid != H3D_STANDARD_DG && p->inviscid != H3D_SPLIT_DG) { h->err = "Requested inviscid discretization is not implemented."; return 1; }
     h->physics = *p;

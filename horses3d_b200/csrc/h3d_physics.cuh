@@ -385,6 +385,157 @@ __device__ __noinline__ void stdroe_riemann(const Phys& ph, const double QLeft[5
     for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
 }
 
+// shared tail of the Roe-type solvers (RiemannSolvers_NS.f90:520-572 and the identical blocks of the variants)
+__device__ __forceinline__ void roe_type_tail(const Phys& ph, const double QLRot[5], const double QRRot[5], double pL, double pR, double invRhoL, double invRhoR,
+                                              double uL, double uR, double aL, double aR, double u, double v, double w, double H, double a, double V2,
+                                              const double alpha[5], const double nHat[3], const double t1[3], const double t2[3], double flux[5]) {
+    double lambda[5] = {u - a, u, u, u, u + a};
+    const double K[5][5] = {{1.0, u - a, v, w, H - u * a}, {1.0, u, v, w, 0.5 * V2}, {0.0, 0.0, 1.0, 0.0, v}, {0.0, 0.0, 0.0, 1.0, w}, {1.0, u + a, v, w, H + u * a}};
+    double dLambda = fmax((uR - aR) - (uL - aL), 0.0);
+    if (fabs(lambda[0]) >= 2.0 * dLambda) lambda[0] = fabs(lambda[0]);
+    else lambda[0] = pow2(lambda[0]) / (4.0 * dLambda) + dLambda;
+    dLambda = fmax((uR + aR) - (uL + aL), 0.0);
+    if (fabs(lambda[4]) >= 2.0 * dLambda) lambda[4] = fabs(lambda[4]);
+    else lambda[4] = pow2(lambda[4]) / (4.0 * dLambda) + dLambda;
+    averaged_states<true>(ph, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    if (ph.averaging == H3D_AVG_PIROZZOLI || ph.averaging == H3D_AVG_KENNEDYGRUBER) lambda[0] = lambda[4];
+    double stab[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) stab[q] = stab[q] + 0.5 * alpha[i] * fabs(lambda[i]) * K[i][q];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) flux[q] = flux[q] - ph.lambdaStab * stab[q];
+    const double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
+__device__ __forceinline__ void rotate_state(const double Q[5], const double nHat[3], const double t1[3], const double t2[3], double R[5]) {
+    R[0] = Q[0];
+    R[1] = Q[1] * nHat[0] + Q[2] * nHat[1] + Q[3] * nHat[2];
+    R[2] = Q[1] * t1[0] + Q[2] * t1[1] + Q[3] * t1[2];
+    R[3] = Q[1] * t2[0] + Q[2] * t2[1] + Q[3] * t2[2];
+    R[4] = Q[4];
+}
+
+// RiemannSolvers_NS.f90:721-861 (RoePikeRiemannSolver)
+__device__ __noinline__ void roepike_riemann(const Phys& ph, const double QLeft[5], const double QRight[5], const double nHat[3],
+                                             const double t1[3], const double t2[3], double flux[5]) {
+    const double gamma = ph.gamma, gm1 = ph.gm1;
+    double QLRot[5], QRRot[5];
+    rotate_state(QLeft, nHat, t1, t2, QLRot); rotate_state(QRight, nHat, t1, t2, QRRot);
+    const double iRL = 1.0 / QLRot[0], iRR = 1.0 / QRRot[0];
+    const double VLu = QLRot[1] * iRL, VLv = QLRot[2] * iRL, VLw = QLRot[3] * iRL;
+    const double VRu = QRRot[1] * iRR, VRv = QRRot[2] * iRR, VRw = QRRot[3] * iRR;
+    const double VLp = gm1 * (QLRot[4] - 0.5 * (VLu * QLRot[1] + VLv * QLRot[2] + VLw * QLRot[3]));
+    const double VRp = gm1 * (QRRot[4] - 0.5 * (VRu * QRRot[1] + VRv * QRRot[2] + VRw * QRRot[3]));
+    const double aL = sqrt(gamma * VLp * iRL), aR = sqrt(gamma * VRp * iRR);
+    const double sqrtRhoL = sqrt(QLRot[0]), sqrtRhoR = sqrt(QRRot[0]);
+    const double invSum = 1.0 / (sqrtRhoL + sqrtRhoR);
+    const double HL = (VLp + QLRot[4]) * iRL, HR = (VRp + QRRot[4]) * iRR;
+    const double rho = sqrtRhoL * sqrtRhoR;
+    const double u = (sqrtRhoL * VLu + sqrtRhoR * VRu) * invSum;
+    const double v = (sqrtRhoL * VLv + sqrtRhoR * VRv) * invSum;
+    const double w = (sqrtRhoL * VLw + sqrtRhoR * VRw) * invSum;
+    const double H = (sqrtRhoL * HL + sqrtRhoR * HR) * invSum;
+    const double V2 = pow2(u) + pow2(v) + pow2(w);
+    const double a = sqrt(gm1 * (H - 0.5 * V2));
+    double alpha[5];
+    alpha[0] = ((VRp - VLp) - rho * a * (VRu - VLu)) / (2.0 * a * a);
+    alpha[1] = (QRight[0] - QLeft[0]) - (VRp - VLp) / (a * a);
+    alpha[2] = rho * (VRv - VLv);
+    alpha[3] = rho * (VRw - VLw);
+    alpha[4] = ((VRp - VLp) + rho * a * (VRu - VLu)) / (2.0 * a * a);
+    roe_type_tail(ph, QLRot, QRRot, VLp, VRp, iRL, iRR, VLu, VRu, aL, aR, u, v, w, H, a, V2, alpha, nHat, t1, t2, flux);
+}
+
+// RiemannSolvers_NS.f90:863-1058 (LowDissipationRoeRiemannSolver)
+__device__ __noinline__ void lowdiss_riemann(const Phys& ph, const double QLeft[5], const double QRight[5], const double nHat[3],
+                                             const double t1[3], const double t2[3], double flux[5]) {
+    const double gamma = ph.gamma, gm1 = ph.gm1;
+    double QLRot[5], QRRot[5];
+    rotate_state(QLeft, nHat, t1, t2, QLRot); rotate_state(QRight, nHat, t1, t2, QRRot);
+    const double rhoL = QLRot[0], rhoR = QRRot[0], invRhoL = 1.0 / rhoL, invRhoR = 1.0 / rhoR;
+    const double sqrtRhoL = sqrt(rhoL), sqrtRhoR = sqrt(rhoR);
+    const double invSqrtRhoL = 1.0 / sqrtRhoL, invSqrtRhoR = 1.0 / sqrtRhoR;
+    const double invSum = 1.0 / (sqrtRhoL + sqrtRhoR);
+    const double uL = QLRot[1] * invRhoL, uR = QRRot[1] * invRhoR, vL = QLRot[2] * invRhoL, vR = QRRot[2] * invRhoR, wL = QLRot[3] * invRhoL, wR = QRRot[3] * invRhoR;
+    const double rhoV2L = (pow2(uL) + pow2(vL) + pow2(wL)) * rhoL, rhoV2R = (pow2(uR) + pow2(vR) + pow2(wR)) * rhoR;
+    const double rhoHL = gamma * QLRot[4] - 0.5 * gm1 * rhoV2L, rhoHR = gamma * QRRot[4] - 0.5 * gm1 * rhoV2R;
+    const double pL = gm1 * (QLRot[4] - 0.5 * rhoV2L), pR = gm1 * (QRRot[4] - 0.5 * rhoV2R);
+    const double aL = sqrt(gamma * pL * invRhoL), aR = sqrt(gamma * pR * invRhoR);
+    const double rho = sqrtRhoL * sqrtRhoR;
+    const double u = (invSqrtRhoL * QLRot[1] + invSqrtRhoR * QRRot[1]) * invSum;
+    const double v = (invSqrtRhoL * QLRot[2] + invSqrtRhoR * QRRot[2]) * invSum;
+    const double w = (invSqrtRhoL * QLRot[3] + invSqrtRhoR * QRRot[3]) * invSum;
+    const double H = (invSqrtRhoL * rhoHL + invSqrtRhoR * rhoHR) * invSum;
+    const double V2abs = pow2(u) + pow2(v) + pow2(w);
+    const double a = sqrt(gm1 * (H - 0.5 * V2abs));
+    const double ML = fabs(uL) / aL, MR = fabs(uR) / aR;
+    const double z = fmin(1.0, fmax(ML, MR));
+    const double du = z * (uR - uL), dv = z * (vR - vL), dw = z * (wR - wL), dp = pR - pL;
+    double alpha[5];
+    alpha[0] = (dp - rho * a * du) / (2.0 * a * a);
+    alpha[1] = (rhoR - rhoL) - dp / (a * a);
+    alpha[2] = rho * dv;
+    alpha[3] = rho * dw;
+    alpha[4] = (dp + rho * a * du) / (2.0 * a * a);
+    roe_type_tail(ph, QLRot, QRRot, pL, pR, invRhoL, invRhoR, uL, uR, aL, aR, u, v, w, H, a, V2abs, alpha, nHat, t1, t2, flux);
+}
+
+// RiemannSolvers_NS.f90:578-719 (MatrixDissipationRiemannSolver); entropy variables: VariableConversion_NS.f90:211-237
+__device__ __noinline__ void matrixdiss_riemann(const Phys& ph, const double QLeft[5], const double QRight[5], const double nHat[3],
+                                                const double t1[3], const double t2[3], double flux[5]) {
+    const double gamma = ph.gamma, gm1 = ph.gm1;
+    const double invGamma = 1.0 / gamma, cp = gamma / gm1, gammaMinus1Div2g = gm1 / (2.0 * gamma), invGammaMinus1 = 1.0 / gm1;
+    double QLRot[5], QRRot[5], EVL[5], EVR[5];
+    rotate_state(QLeft, nHat, t1, t2, QLRot); rotate_state(QRight, nHat, t1, t2, QRRot);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const double* Q = side ? QRRot : QLRot; double* U = side ? EVR : EVL;
+        const double invRho = 1.0 / Q[0];
+        const double rhoV2 = (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) * invRho;
+        const double p = gm1 * (Q[4] - 0.5 * rhoV2);
+        const double invP = 1.0 / p;
+        U[0] = (gamma - (log(p) - gamma * log(Q[0]))) * invGammaMinus1 - 0.5 * rhoV2 * invP;
+        U[1] = Q[1] * invP; U[2] = Q[2] * invP; U[3] = Q[3] * invP; U[4] = -Q[0] * invP;
+    }
+    const double invRhoL = 1.0 / QLRot[0], invRhoR = 1.0 / QRRot[0];
+    const double uL = QLRot[1] * invRhoL, uR = QRRot[1] * invRhoR, vL = QLRot[2] * invRhoL, vR = QRRot[2] * invRhoR, wL = QLRot[3] * invRhoL, wR = QRRot[3] * invRhoR;
+    const double vtotL = uL * uL + vL * vL + wL * wL, vtotR = uR * uR + vR * vR + wR * wR;
+    const double pL = gm1 * (QLRot[4] - 0.5 * QLRot[0] * vtotL), pR = gm1 * (QRRot[4] - 0.5 * QRRot[0] * vtotR);
+    const double betaL = -0.5 * EVL[4], betaR = -0.5 * EVR[4];
+    const double betaLogMean = log_mean(betaL, betaR), rhoLogMean = log_mean(QLRot[0], QRRot[0]);
+    const double pMean = 0.5 * (QLRot[0] + QRRot[0]) / (betaL + betaR);
+    const double a_bar = sqrt(gamma * pMean / rhoLogMean);
+    const double uMean = 0.5 * (uL + uR), vMean = 0.5 * (vL + vR), wMean = 0.5 * (wL + wR);
+    const double V2abs = 2.0 * (pow2(uMean) + pow2(vMean) + pow2(wMean)) - 0.5 * (vtotL + vtotR);
+    const double h_bar = 0.5 * (cp / betaLogMean + V2abs);
+    double lambda[5] = {fabs(uMean - a_bar), fabs(uMean), fabs(uMean), fabs(uMean), fabs(uMean + a_bar)};
+    const double R1[5][5] = {{1.0, 1.0, 0.0, 0.0, 1.0},
+                             {uMean - a_bar, uMean, 0.0, 0.0, uMean + a_bar},
+                             {vMean, vMean, 1.0, 0.0, vMean},
+                             {wMean, wMean, 0.0, 1.0, wMean},
+                             {h_bar - uMean * a_bar, 0.5 * V2abs, vMean, wMean, h_bar + uMean * a_bar}};
+    double T[5];
+    T[0] = 0.5 * rhoLogMean * invGamma; T[1] = 2.0 * gammaMinus1Div2g * rhoLogMean; T[2] = pMean; T[3] = pMean; T[4] = T[0];
+    averaged_states<true>(ph, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    if (ph.averaging == H3D_AVG_PIROZZOLI || ph.averaging == H3D_AVG_KENNEDYGRUBER) lambda[0] = lambda[4];
+    double stab[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) stab[i] = stab[i] + 0.5 * R1[i][j] * lambda[j] * T[j] * R1[k][j] * (EVR[k] - EVL[k]);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) flux[q] = flux[q] - ph.lambdaStab * stab[q];
+    const double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
 // EXT = false: Roe, Lax-Friedrichs, central with the standard / Kennedy-Gruber / Pirozzoli averages (the instantiation on
 // the headline path); EXT = true adds the out-of-line solvers and averages
 template <bool EXT>
@@ -394,6 +545,9 @@ __device__ __forceinline__ void riemann_solver(const Phys& ph, const double QL[5
     if constexpr (EXT) {
         if (ph.riemann == H3D_RIEMANN_RUSANOV) { rusanov_riemann(ph, QL, QR, nHat, flux); return; }
         if (ph.riemann == H3D_RIEMANN_STDROE) { stdroe_riemann(ph, QL, QR, nHat, t1, t2, flux); return; }
+        if (ph.riemann == H3D_RIEMANN_ROEPIKE) { roepike_riemann(ph, QL, QR, nHat, t1, t2, flux); return; }
+        if (ph.riemann == H3D_RIEMANN_LOWDISSROE) { lowdiss_riemann(ph, QL, QR, nHat, t1, t2, flux); return; }
+        if (ph.riemann == H3D_RIEMANN_MATRIXDISS) { matrixdiss_riemann(ph, QL, QR, nHat, t1, t2, flux); return; }
     }
     rotated_riemann<EXT>(ph, ph.riemann, QL, QR, nHat, t1, t2, flux);
 }

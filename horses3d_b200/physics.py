@@ -6,7 +6,8 @@ SetRiemannSolver (RiemannSolvers_NS.f90:120-286): same defaults, same arithmetic
 import ctypes as C
 
 STANDARD_DG, SPLIT_DG = 0, 1
-RIEMANN = {"roe": 0, "lax-friedrichs": 1, "central": 2, "rusanov": 3, "standard roe": 4, "u-diss": 5}
+RIEMANN = {"roe": 0, "lax-friedrichs": 1, "central": 2, "rusanov": 3, "standard roe": 4, "u-diss": 5, "roe-pike": 6,
+           "low dissipation roe": 7, "matrix dissipation": 8}
 AVERAGING = {"standard": 0, "kennedy-gruber": 1, "pirozzoli": 2, "ducros": 3, "morinishi": 4, "entropy conserving": 5,
              "chandrasekar": 6}
 LES = {"none": 0, "smagorinsky": 1}

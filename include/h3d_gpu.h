@@ -41,6 +41,9 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_RIEMANN_RUSANOV 3
 #define H3D_RIEMANN_STDROE 4
 #define H3D_RIEMANN_UDISS 5
+#define H3D_RIEMANN_ROEPIKE 6
+#define H3D_RIEMANN_LOWDISSROE 7
+#define H3D_RIEMANN_MATRIXDISS 8
 
 /* averaging / two-point flux (RiemannSolvers_NS.f90:233-285) */
 #define H3D_AVG_STANDARD 0

@@ -442,8 +442,165 @@ inline void UDissRiemannSolver(const Oracle& o, const double* QLeft, const doubl
     for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
 }
 
+// shared tail of the Roe-type solvers (RiemannSolvers_NS.f90:520-572 and the identical blocks of the variants): Harten / van
+// Leer entropy fix of waves 1 and 5, averaged flux, Winters correction, stab = sum_i 1/2 alpha_i |lambda_i| K(:,i)
+inline void roeTypeTail(const Oracle& o, const double* QLRot, const double* QRRot, double pL, double pR, double invRhoL, double invRhoR,
+                        double uL, double uR, double aL, double aR, double u, double v, double w, double H, double a, double V2,
+                        const double* alpha, const double* nHat, const double* t1, const double* t2, double* flux) {
+    double lambda[5] = {u - a, u, u, u, u + a};
+    double K[5][5] = {{1.0, u - a, v, w, H - u * a}, {1.0, u, v, w, 0.5 * V2}, {0.0, 0.0, 1.0, 0.0, v}, {0.0, 0.0, 0.0, 1.0, w}, {1.0, u + a, v, w, H + u * a}};
+    double dLambda = std::fmax((uR - aR) - (uL - aL), 0.0);
+    if (std::fabs(lambda[0]) >= 2.0 * dLambda) lambda[0] = std::fabs(lambda[0]);
+    else lambda[0] = POW2(lambda[0]) / (4.0 * dLambda) + dLambda;
+    dLambda = std::fmax((uR + aR) - (uL + aL), 0.0);
+    if (std::fabs(lambda[4]) >= 2.0 * dLambda) lambda[4] = std::fabs(lambda[4]);
+    else lambda[4] = POW2(lambda[4]) / (4.0 * dLambda) + dLambda;
+    AveragedStates(o, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    if (o.ph.averaging == H3D_AVG_PIROZZOLI || o.ph.averaging == H3D_AVG_KENNEDYGRUBER) lambda[0] = lambda[4];
+    double stab[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; ++i) for (int q = 0; q < 5; ++q) stab[q] = stab[q] + 0.5 * alpha[i] * std::fabs(lambda[i]) * K[i][q];
+    for (int q = 0; q < 5; ++q) flux[q] = flux[q] - o.ph.lambdaStab * stab[q];
+    double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
+// RiemannSolvers_NS.f90:721-861 (RoePikeRiemannSolver): as the standard Roe solver with the wave strengths from primitive jumps
+inline void RoePikeRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, const double* t1, const double* t2, double* flux) {
+    const double gamma = o.ph.gamma, gm1 = o.ph.gammaMinus1;
+    double QLRot[5], QRRot[5];
+    QLRot[0] = QLeft[0]; QRRot[0] = QRight[0];
+    QLRot[1] = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    QRRot[1] = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    QLRot[2] = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    QRRot[2] = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    QLRot[3] = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    QRRot[3] = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    QLRot[4] = QLeft[4]; QRRot[4] = QRight[4];
+    auto prim = [&](const double* U, double* V) {
+        double invRho = 1.0 / U[0];
+        V[0] = invRho; V[1] = U[1] * invRho; V[2] = U[2] * invRho; V[3] = U[3] * invRho;
+        V[4] = gm1 * (U[4] - 0.5 * (V[1] * U[1] + V[2] * U[2] + V[3] * U[3]));
+        V[6] = gamma * V[4] * invRho;
+    };
+    double VL[7], VR[7];
+    prim(QLRot, VL); prim(QRRot, VR);
+    double aL = std::sqrt(VL[6]), aR = std::sqrt(VR[6]);
+    double sqrtRhoL = std::sqrt(QLRot[0]), sqrtRhoR = std::sqrt(QRRot[0]);
+    double invSumSqrtRhoLR = 1.0 / (sqrtRhoL + sqrtRhoR);
+    double HL = (VL[4] + QLRot[4]) * VL[0], HR = (VR[4] + QRRot[4]) * VR[0];
+    double rho = sqrtRhoL * sqrtRhoR;
+    double u = (sqrtRhoL * VL[1] + sqrtRhoR * VR[1]) * invSumSqrtRhoLR;
+    double v = (sqrtRhoL * VL[2] + sqrtRhoR * VR[2]) * invSumSqrtRhoLR;
+    double w = (sqrtRhoL * VL[3] + sqrtRhoR * VR[3]) * invSumSqrtRhoLR;
+    double H = (sqrtRhoL * HL + sqrtRhoR * HR) * invSumSqrtRhoLR;
+    double V2 = POW2(u) + POW2(v) + POW2(w);
+    double a = std::sqrt(gm1 * (H - 0.5 * V2));
+    double alpha[5];
+    alpha[0] = ((VR[4] - VL[4]) - rho * a * (VR[1] - VL[1])) / (2.0 * a * a);
+    alpha[1] = (QRight[0] - QLeft[0]) - (VR[4] - VL[4]) / (a * a);
+    alpha[2] = rho * (VR[2] - VL[2]);
+    alpha[3] = rho * (VR[3] - VL[3]);
+    alpha[4] = ((VR[4] - VL[4]) + rho * a * (VR[1] - VL[1])) / (2.0 * a * a);
+    roeTypeTail(o, QLRot, QRRot, VL[4], VR[4], VL[0], VR[0], VL[1], VR[1], aL, aR, u, v, w, H, a, V2, alpha, nHat, t1, t2, flux);
+}
+
+// RiemannSolvers_NS.f90:863-1058 (LowDissipationRoeRiemannSolver): velocity jumps scaled by z = min(1, max(M_L, M_R))
+inline void LowDissipationRoeRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, const double* t1, const double* t2, double* flux) {
+    const double gamma = o.ph.gamma, gm1 = o.ph.gammaMinus1;
+    double rhoL = QLeft[0], rhoR = QRight[0], invRhoL = 1.0 / rhoL, invRhoR = 1.0 / rhoR;
+    double sqrtRhoL = std::sqrt(rhoL), sqrtRhoR = std::sqrt(rhoR);
+    double invSqrtRhoL = 1.0 / sqrtRhoL, invSqrtRhoR = 1.0 / sqrtRhoR;
+    double invSumSqrtRhoLR = 1.0 / (sqrtRhoL + sqrtRhoR);
+    double rhouL = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    double rhouR = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    double rhovL = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    double rhovR = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    double rhowL = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    double rhowR = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    double rhoeL = QLeft[4], rhoeR = QRight[4];
+    double uL = rhouL * invRhoL, uR = rhouR * invRhoR, vL = rhovL * invRhoL, vR = rhovR * invRhoR, wL = rhowL * invRhoL, wR = rhowR * invRhoR;
+    double rhoV2L = (POW2(uL) + POW2(vL) + POW2(wL)) * rhoL, rhoV2R = (POW2(uR) + POW2(vR) + POW2(wR)) * rhoR;
+    double rhoHL = gamma * rhoeL - 0.5 * gm1 * rhoV2L, rhoHR = gamma * rhoeR - 0.5 * gm1 * rhoV2R;
+    double pL = gm1 * (rhoeL - 0.5 * rhoV2L), pR = gm1 * (rhoeR - 0.5 * rhoV2R);
+    double aL = std::sqrt(gamma * pL * invRhoL), aR = std::sqrt(gamma * pR * invRhoR);
+    double rho = sqrtRhoL * sqrtRhoR;
+    double u = (invSqrtRhoL * rhouL + invSqrtRhoR * rhouR) * invSumSqrtRhoLR;
+    double v = (invSqrtRhoL * rhovL + invSqrtRhoR * rhovR) * invSumSqrtRhoLR;
+    double w = (invSqrtRhoL * rhowL + invSqrtRhoR * rhowR) * invSumSqrtRhoLR;
+    double H = (invSqrtRhoL * rhoHL + invSqrtRhoR * rhoHR) * invSumSqrtRhoLR;
+    double V2abs = POW2(u) + POW2(v) + POW2(w);
+    double a = std::sqrt(gm1 * (H - 0.5 * V2abs));
+    double ML = std::fabs(uL) / aL, MR = std::fabs(uR) / aR;
+    double z = std::fmin(1.0, std::fmax(ML, MR));
+    double du = z * (uR - uL), dv = z * (vR - vL), dw = z * (wR - wL), dp = pR - pL;
+    double alpha[5];
+    alpha[0] = (dp - rho * a * du) / (2.0 * a * a);
+    alpha[1] = (rhoR - rhoL) - dp / (a * a);
+    alpha[2] = rho * dv;
+    alpha[3] = rho * dw;
+    alpha[4] = (dp + rho * a * du) / (2.0 * a * a);
+    double QLRot[5] = {rhoL, rhouL, rhovL, rhowL, rhoeL}, QRRot[5] = {rhoR, rhouR, rhovR, rhowR, rhoeR};
+    roeTypeTail(o, QLRot, QRRot, pL, pR, invRhoL, invRhoR, uL, uR, aL, aR, u, v, w, H, a, V2abs, alpha, nHat, t1, t2, flux);
+}
+
+// RiemannSolvers_NS.f90:578-719 (MatrixDissipationRiemannSolver): entropy-variable jump, Chandrasekar mean state
+inline void MatrixDissipationRiemannSolver(const Oracle& o, const double* QLeft, const double* QRight, const double* nHat, const double* t1, const double* t2, double* flux) {
+    const double gamma = o.ph.gamma, gm1 = o.ph.gammaMinus1;
+    const double invGamma = 1.0 / gamma, cp = gamma / gm1, gammaMinus1Div2g = gm1 / (2.0 * gamma), invGammaMinus1 = 1.0 / gm1;
+    double QLRot[5], QRRot[5];
+    QLRot[0] = QLeft[0]; QRRot[0] = QRight[0];
+    QLRot[1] = QLeft[1] * nHat[0] + QLeft[2] * nHat[1] + QLeft[3] * nHat[2];
+    QRRot[1] = QRight[1] * nHat[0] + QRight[2] * nHat[1] + QRight[3] * nHat[2];
+    QLRot[2] = QLeft[1] * t1[0] + QLeft[2] * t1[1] + QLeft[3] * t1[2];
+    QRRot[2] = QRight[1] * t1[0] + QRight[2] * t1[1] + QRight[3] * t1[2];
+    QLRot[3] = QLeft[1] * t2[0] + QLeft[2] * t2[1] + QLeft[3] * t2[2];
+    QRRot[3] = QRight[1] * t2[0] + QRight[2] * t2[1] + QRight[3] * t2[2];
+    QLRot[4] = QLeft[4]; QRRot[4] = QRight[4];
+    auto entropyVars = [&](const double* Q, double* U) {   // NSGradientVariables_ENTROPY, VariableConversion_NS.f90:211-237
+        double invRho = 1.0 / Q[0];
+        double rhoV2 = (POW2(Q[1]) + POW2(Q[2]) + POW2(Q[3])) * invRho;
+        double p = gm1 * (Q[4] - 0.5 * rhoV2);
+        double invP = 1.0 / p;
+        U[0] = (gamma - (std::log(p) - gamma * std::log(Q[0]))) * invGammaMinus1 - 0.5 * rhoV2 * invP;
+        U[1] = Q[1] * invP; U[2] = Q[2] * invP; U[3] = Q[3] * invP; U[4] = -Q[0] * invP;
+    };
+    double EVL[5], EVR[5];
+    entropyVars(QLRot, EVL); entropyVars(QRRot, EVR);
+    double invRhoL = 1.0 / QLRot[0], invRhoR = 1.0 / QRRot[0];
+    double uL = QLRot[1] * invRhoL, uR = QRRot[1] * invRhoR, vL = QLRot[2] * invRhoL, vR = QRRot[2] * invRhoR, wL = QLRot[3] * invRhoL, wR = QRRot[3] * invRhoR;
+    double vtotL = uL * uL + vL * vL + wL * wL, vtotR = uR * uR + vR * vR + wR * wR;
+    double pL = gm1 * (QLRot[4] - 0.5 * QLRot[0] * vtotL), pR = gm1 * (QRRot[4] - 0.5 * QRRot[0] * vtotR);
+    double betaL = -0.5 * EVL[4], betaR = -0.5 * EVR[4];
+    double betaLogMean = logarithmicMean(betaL, betaR), rhoLogMean = logarithmicMean(QLRot[0], QRRot[0]);
+    double pMean = 0.5 * (QLRot[0] + QRRot[0]) / (betaL + betaR);
+    double a_bar = std::sqrt(gamma * pMean / rhoLogMean);
+    double uMean = 0.5 * (uL + uR), vMean = 0.5 * (vL + vR), wMean = 0.5 * (wL + wR);
+    double V2abs = 2.0 * (POW2(uMean) + POW2(vMean) + POW2(wMean)) - 0.5 * (vtotL + vtotR);
+    double h_bar = 0.5 * (cp / betaLogMean + V2abs);
+    double lambda[5] = {std::fabs(uMean - a_bar), std::fabs(uMean), std::fabs(uMean), std::fabs(uMean), std::fabs(uMean + a_bar)};
+    // R1(component, wave)
+    double R1[5][5] = {{1.0, 1.0, 0.0, 0.0, 1.0},
+                       {uMean - a_bar, uMean, 0.0, 0.0, uMean + a_bar},
+                       {vMean, vMean, 1.0, 0.0, vMean},
+                       {wMean, wMean, 0.0, 1.0, wMean},
+                       {h_bar - uMean * a_bar, 0.5 * V2abs, vMean, wMean, h_bar + uMean * a_bar}};
+    double T[5];
+    T[0] = 0.5 * rhoLogMean * invGamma; T[1] = 2.0 * gammaMinus1Div2g * rhoLogMean; T[2] = pMean; T[3] = pMean; T[4] = T[0];
+    AveragedStates(o, QLRot, QRRot, pL, pR, invRhoL, invRhoR, flux);
+    if (o.ph.averaging == H3D_AVG_PIROZZOLI || o.ph.averaging == H3D_AVG_KENNEDYGRUBER) lambda[0] = lambda[4];
+    double stab[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) for (int k = 0; k < 5; ++k)
+        stab[i] = stab[i] + 0.5 * R1[i][j] * lambda[j] * T[j] * R1[k][j] * (EVR[k] - EVL[k]);
+    for (int q = 0; q < 5; ++q) flux[q] = flux[q] - o.ph.lambdaStab * stab[q];
+    double f2 = flux[1], f3 = flux[2], f4 = flux[3];
+    for (int c = 0; c < 3; ++c) flux[1 + c] = nHat[c] * f2 + t1[c] * f3 + t2[c] * f4;
+}
+
 inline void RiemannSolver(const Oracle& o, const double* QL, const double* QR, const double* nHat, const double* t1, const double* t2, double* flux) {
     switch (o.ph.riemann) {
+        case H3D_RIEMANN_ROEPIKE: RoePikeRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
+        case H3D_RIEMANN_LOWDISSROE: LowDissipationRoeRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
+        case H3D_RIEMANN_MATRIXDISS: MatrixDissipationRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
         case H3D_RIEMANN_RUSANOV: RusanovRiemannSolver(o, QL, QR, nHat, flux); break;
         case H3D_RIEMANN_STDROE: StdRoeRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;
         case H3D_RIEMANN_UDISS: UDissRiemannSolver(o, QL, QR, nHat, t1, t2, flux); break;

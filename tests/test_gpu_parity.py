@@ -58,6 +58,9 @@ CASES = [
     (2, 3, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="morinishi", riemann="lax-friedrichs")),
     (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, riemann="rusanov")),
     (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, riemann="standard roe", averaging="kennedy-gruber")),
+    (2, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, riemann="roe-pike")),
+    (2, 3, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli", riemann="low dissipation roe")),
+    (2, 5, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="chandrasekar", riemann="matrix dissipation")),
 ]
 
 
