@@ -47,6 +47,7 @@ class Binding:
         "volume_integral": [C.c_int, C.POINTER(C.c_double)],
         "has_nan": [C.POINTER(C.c_int)],
         "surface_integral": [C.c_int, C.c_int, _D],
+        "probe": [C.c_int, _D, _D, _D, _D, _D, _D],
     }
 
     def __init__(self, lib, prefix, extra=None):

@@ -258,6 +258,35 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_surface(DevMesh m, Phys ph,
     blockReduce<13, 2>(v, partial + (size_t)blockIdx.x * 13);
 }
 
+// Probe_Update (Probe.f90:330-420): one CTA per probe
+__global__ void __launch_bounds__(256) k_probe(DevMesh m, Phys ph, int n, const int* elem, const int* variable, const double* lxi, const double* leta,
+                                               const double* lzeta, double* values) {
+    const int pr = blockIdx.x, N2 = n * n, N3 = N2 * n;
+    const size_t es = (size_t)m.nElem * N3;
+    double v[1] = {0.0};
+    for (int node = threadIdx.x; node < N3; node += blockDim.x) {
+        const int i = node % n, j = (node / n) % n, k = node / N2;
+        double Q[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) Q[q] = m.Q[q * es + (size_t)elem[pr] * N3 + node];
+        double var;
+        switch (variable[pr]) {
+            case H3D_PROBE_PRESSURE: var = pressure(ph, Q); break;
+            case H3D_PROBE_VELOCITY: var = sqrt(pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) / Q[0]; break;
+            case H3D_PROBE_U: var = Q[1] / Q[0]; break;
+            case H3D_PROBE_V: var = Q[2] / Q[0]; break;
+            case H3D_PROBE_W: var = Q[3] / Q[0]; break;
+            case H3D_PROBE_MACH:
+                var = pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3]) / pow2(Q[0]);
+                var = sqrt(var / (ph.gamma * (ph.gamma - 1.0) * (Q[4] / Q[0] - 0.5 * var)));
+                break;
+            default: var = 0.5 * (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) / Q[0];
+        }
+        v[0] = v[0] + var * lxi[pr * n + i] * leta[pr * n + j] * lzeta[pr * n + k];
+    }
+    blockReduce<1, 2>(v, values + pr);
+}
+
 template <int K, int OP>
 __global__ void __launch_bounds__(1024) k_red_final(const double* partial, int nBlocks, double* out) {
     double v[K];
@@ -966,6 +995,34 @@ int h3d_surface_integral(h3d_handle h, int zone, int kind, double out[3]) {
         case H3D_SURF_VISCOUS_FORCE: for (int d = 0; d < 3; ++d) out[d] = s[10 + d]; break;
         default: for (int d = 0; d < 3; ++d) out[d] = s[7 + d] + s[10 + d];
     }
+    return 0;
+}
+
+int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, const double* lxi, const double* leta, const double* lzeta, double* values) {
+    if (checkReady(h)) return 1;
+    if (nProbes <= 0) return 0;
+    CTX_CHECK(cudaSetDevice(h->device));
+    const int n = h->n;
+    std::vector<int> ev(2 * (size_t)nProbes);
+    for (int p = 0; p < nProbes; ++p) {
+        if (elem[p] < 0 || elem[p] >= h->nElem) { h->err = "probe element out of range"; return 1; }
+        if (variable[p] < H3D_PROBE_PRESSURE || variable[p] > H3D_PROBE_K) { h->err = "unknown probe variable"; return 1; }
+        ev[p] = h->invPermE[elem[p]]; ev[nProbes + p] = variable[p];
+    }
+    int* dEV = nullptr; double* dL = nullptr;
+    const size_t nl = (size_t)nProbes * n;
+    CTX_CHECK(cudaMalloc((void**)&dEV, ev.size() * sizeof(int)));
+    CTX_CHECK(cudaMalloc((void**)&dL, (3 * nl + nProbes) * sizeof(double)));
+    CTX_CHECK(cudaMemcpyAsync(dEV, ev.data(), ev.size() * sizeof(int), cudaMemcpyHostToDevice, h->sCompute));
+    CTX_CHECK(cudaMemcpyAsync(dL, lxi, nl * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
+    CTX_CHECK(cudaMemcpyAsync(dL + nl, leta, nl * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
+    CTX_CHECK(cudaMemcpyAsync(dL + 2 * nl, lzeta, nl * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
+    k_probe<<<nProbes, 256, 0, h->sCompute>>>(h->m, h->ph, n, dEV, dEV + nProbes, dL, dL + nl, dL + 2 * nl, dL + 3 * nl);
+    ++h->launches;
+    cudaError_t e1 = cudaMemcpyAsync(values, dL + 3 * nl, nProbes * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute);
+    cudaError_t e2 = cudaStreamSynchronize(h->sCompute);
+    cudaFree(dEV); cudaFree(dL);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { h->err = "probe evaluation failed"; return 2; }
     return 0;
 }
 

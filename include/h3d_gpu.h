@@ -204,6 +204,17 @@ int h3d_volume_integral(h3d_handle h, int kind, double* val);
 #define H3D_SURF_PRESSURE_FORCE 6  /* int p n dS                                */
 #define H3D_SURF_VISCOUS_FORCE 7   /* - int tau n dS                            */
 int h3d_surface_integral(h3d_handle h, int zone, int kind, double out[3]);
+/* Probe_Update (libs/monitors/Probe.f90:330-420): value = sum_ijk var(i,j,k) lxi(i) leta(j) lzeta(k) in element elem[p] (local
+ * 0-based id on this rank), var evaluated at the nodes from Q.  The Lagrange vectors [p][n] come from the host-side
+ * point location (HexMesh_FindPointWithCoords, HexMesh.f90:5483; horses3d_b200/probes.py).  Rank-local: no reduction. */
+#define H3D_PROBE_PRESSURE 0
+#define H3D_PROBE_VELOCITY 1
+#define H3D_PROBE_U 2
+#define H3D_PROBE_V 3
+#define H3D_PROBE_W 4
+#define H3D_PROBE_MACH 5
+#define H3D_PROBE_K 6
+int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, const double* lxi, const double* leta, const double* lzeta, double* values);
 /* checkForNan (ExplicitMethods.f90:1856-1905): flag = 1 if any NaN in Q on any rank */
 int h3d_has_nan(h3d_handle h, int* flag);
 

@@ -1385,6 +1385,36 @@ int orc_surface_integral(void* p, int zone, int kind, double* out) {
     return 0;
 }
 
+// Probe_Update (libs/monitors/Probe.f90:330-420)
+int orc_probe(void* p, int nProbes, const int* elem, const int* variable, const double* lxi, const double* leta, const double* lzeta, double* values) {
+    Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
+    const double gamma = o.ph.gamma;
+    for (int pr = 0; pr < nProbes; ++pr) {
+        if (elem[pr] < 0 || elem[pr] >= o.nElem) { o.err = "probe element out of range"; return 1; }
+        double value = 0.0;
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            const double* Q = &o.Q[5 * ix.node(elem[pr], i, j, k)];
+            double var;
+            switch (variable[pr]) {
+                case H3D_PROBE_PRESSURE: var = Pressure(o, Q); break;
+                case H3D_PROBE_VELOCITY: var = std::sqrt(POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO]; break;
+                case H3D_PROBE_U: var = Q[IRHOU] / Q[IRHO]; break;
+                case H3D_PROBE_V: var = Q[IRHOV] / Q[IRHO]; break;
+                case H3D_PROBE_W: var = Q[IRHOW] / Q[IRHO]; break;
+                case H3D_PROBE_MACH: {   // as written in the reference (:359-362), including its operator precedence
+                    var = POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW]) / POW2(Q[IRHO]);
+                    var = std::sqrt(var / (gamma * (gamma - 1.0) * (Q[IRHOE] / Q[IRHO] - 0.5 * var)));
+                } break;
+                case H3D_PROBE_K: var = 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO]; break;
+                default: o.err = "unknown probe variable"; return 1;
+            }
+            value = value + var * lxi[pr * n + i] * leta[pr * n + j] * lzeta[pr * n + k];
+        }
+        values[pr] = value;
+    }
+    return 0;
+}
+
 int orc_volume_integral(void* p, int kind, double* out) {
     Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
     double val = 0.0;

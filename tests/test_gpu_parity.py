@@ -132,6 +132,28 @@ def test_surface_integrals_match_oracle(gpu_api_cls):
         DGSem(e, get_mesh(2, 2, GAUSS), make_physics(flow="Euler")).SurfaceIntegral(0, P.SURF_TOTAL_FORCE)
 
 
+def test_probes_match_oracle(gpu_api_cls):
+    """Probe_Update: every variable at points inside, on a face of and at a corner of curved, re-oriented elements."""
+    from horses3d_b200 import probes
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0)
+    mesh = get_mesh(3, 4, GAUSS, 0.1, True)
+    vals = []
+    for api in (OracleApi(), gpu_api_cls()):
+        sem = DGSem(api, mesh, phys)
+        sem.set_initial_condition(perturbed_tgv)
+        sem.TakeRK3Step(0.0, 1.0e-3)
+        pts = [[1.0, 2.0, 3.0], [2.0 * np.pi / 3.0, 1.0, 1.0], [0.3, 5.9, 4.4], [3.1, 3.2, 0.05]]
+        pr = [probes.Probe(sem, x, v) for x in pts for v in probes.VARIABLES]
+        assert all(p.active for p in pr)
+        # the located point maps back onto the requested position
+        X = sem.node_coordinates()
+        for p, x in zip(pr[::len(probes.VARIABLES)], pts):
+            assert np.abs(np.einsum("kjic,i,j,k->c", X[p.eID], p.l[0], p.l[1], p.l[2]) - np.array(x)).max() < 1e-11
+        vals.append(probes.evaluate(sem, pr))
+    assert np.abs(vals[0]).max() > 0.1
+    assert np.abs(vals[0] - vals[1]).max() <= 1e-13 * np.abs(vals[0]).max()
+
+
 @pytest.mark.parametrize("scheme", ["RK3", "RK5"])
 def test_rk_steps_and_monitors_match_oracle(gpu_api_cls, scheme):
     mesh = get_mesh(4, 3, GAUSS, 0.1, True)

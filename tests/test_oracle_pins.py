@@ -101,7 +101,9 @@ def _cylinder_100_steps(**phys_kw):
     # surface monitors of the control file: drag along z, lift along x on the cylinder, reference surface 1
     cd = sem.surface_monitor("innercylinder", "drag", [0.0, 0.0, 1.0], reference_surface=1.0)
     cl = sem.surface_monitor("innercylinder", "lift", [1.0, 0.0, 0.0], reference_surface=1.0)
-    return res, cd, cl
+    from horses3d_b200 import probes
+    wake_u = probes.evaluate(sem, [probes.Probe(sem, [0.0, 2.0, 4.0], "u")])[0]       # probe 1 of the control file
+    return res, cd, cl, wake_u
 
 
 needs_cylinder_mesh = pytest.mark.skipif(not __import__("os").path.exists(CYLINDER_MESH), reason="reference test mesh not available on this machine")
@@ -112,13 +114,15 @@ def test_k5_cylinder_100_steps():
     """Expected residuals and the 1e-11 tolerance from test/NavierStokes/Cylinder/SETUP/ProblemFile.f90:551-575.  Pins the
     boundary conditions, the curved transfinite geometry and the SpecMesh reader (multi-line records,
     curved patches)."""
-    got, cd, cl = _cylinder_100_steps()
+    got, cd, cl, wake_u = _cylinder_100_steps()
     res = np.array([8.8131248889811715E+00, 1.7608838068776613E+01, 1.9037533106262516E-01, 2.4301352846288605E+01, 2.4063786464536835E+02])
     assert np.abs(got - res).max() < 1.0e-11 * 240.0
     assert np.abs((got - res) / res).max() < 1.0e-11
     print("K5 cd", cd - 3.4573345486345943E+01, "cl", cl - (-4.6800322917661674E-04))
     assert abs(cd - 3.4573345486345943E+01) < 1.0e-11 * 35.0     # drag and lift monitors, ProblemFile.f90:563-564, 607-615
     assert abs(cl - (-4.6800322917661674E-04)) < 1.0e-11
+    print("K5 wake_u", wake_u - 1.0965307794823676E-08)
+    assert abs(wake_u - 1.0965307794823676E-08) < 1.0e-11        # probe, ProblemFile.f90:562, 602-605
 
 
 @needs_cylinder_mesh
@@ -126,12 +130,14 @@ def test_k5b_cylinder_smagorinsky_100_steps():
     """test/NavierStokes/CylinderSmagorinsky (LES model = Smagorinsky, wall model = linear): residuals and the 1e-7
     tolerance from SETUP/ProblemFile.f90:538-569.  Pins the Smagorinsky viscosity at elements and faces, the wall
     distances (HexMesh.f90:5594-5692) and the linear wall model (LESModels.f90:189-203)."""
-    got, cd, cl = _cylinder_100_steps(les="smagorinsky", les_wall_model="linear")
+    got, cd, cl, wake_u = _cylinder_100_steps(les="smagorinsky", les_wall_model="linear")
     res = np.array([7.58705681758851, 15.5542852761418, 0.231394835496677, 20.0848567943827, 207.594579145771])
     print("K5b residuals", got, "rel diff", np.abs((got - res) / res).max(), "cd", cd - 34.9438869828619, "cl", cl - (-1.582092121135137E-004))
     assert np.abs(got - res).max() < 1.0e-7
     assert abs(cd - 34.9438869828619) < 1.0e-11 * 35.0           # ProblemFile.f90:535-536
     assert abs(cl - (-1.582092121135137E-004)) < 1.0e-11
+    print("K5b wake_u", wake_u - 9.867445291005896E-009)
+    assert abs(wake_u - 9.867445291005896E-009) < 1.0e-11
 
 
 UNIT_CUBE_MESH = "/root/reference/Solver/test/TestMeshes/UnitCube4x4.mesh"
@@ -215,6 +221,10 @@ def test_k4_box_around_circle_pirozzoli_1000_steps():
     res = np.array([3.2245412233756249E-03, 7.2948338786761158E-02, 7.8482433396760149E-12, 6.3956090995916370E-02, 9.8435366345196243E-02])
     cd = sem.surface_monitor("innercylinder", "pressure-force", [1.0, 0.0, 0.0])      # "drag" monitor of the control file
     p_aver = sem.surface_monitor("innercylinder", "pressure-average")
+    from horses3d_b200 import probes
+    wake_w = probes.evaluate(sem, [probes.Probe(sem, [0.0, 2.0, 4.0], "w")])[0]       # probe "wake_w" of the control file
+    print("K4 wake_w", wake_w - (-3.2221536957553205E-002))
+    assert abs(wake_w - (-3.2221536957553205E-002)) < 1.0e-11
     print("K4 t", rec["t"] - 8.4020848657635838, "res", rec["residuals"] - res, "cd", cd - 147.57687869771942, "p_aver", p_aver - 7.3652850621645536)
     assert abs(rec["t"] - 8.4020848657635838) < 1.0e-11
     assert np.abs(rec["residuals"] - res).max() < 1.0e-11
