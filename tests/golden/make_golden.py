@@ -1,0 +1,48 @@
+"""Regenerates tests/golden/*.npz: residuals of the CPU oracle (oracle/h3d_oracle.cpp, itself pinned to the reference's
+regression values by tests/test_oracle_pins.py) on small generated meshes.  The Fortran reference cannot run in this
+container, so these are oracle outputs, frozen so that neither the oracle nor the device path can drift unnoticed.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from horses3d_b200.dgsem import DGSem  # noqa: E402
+from horses3d_b200.hostmesh import GAUSS, GAUSSLOBATTO  # noqa: E402
+from horses3d_b200.physics import make_physics  # noqa: E402
+from oracle.oracle_api import OracleApi  # noqa: E402
+from parity import channel_state, get_mesh, perturbed_tgv  # noqa: E402
+
+CASES = {
+    "tgv_ns_p3": dict(ne=2, N=3, nodes=GAUSS, bc=None, kw=dict(flow="NS", mach=0.08, reynolds=1600.0)),
+    "tgv_ns_p7": dict(ne=2, N=7, nodes=GAUSS, bc=None, kw=dict(flow="NS", mach=0.08, reynolds=1600.0)),
+    "tgv_euler_split_pirozzoli_p4": dict(ne=2, N=4, nodes=GAUSSLOBATTO, bc=None, kw=dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli")),
+    "channel_ns_smagorinsky_p3": dict(ne=3, N=3, nodes=GAUSS, bc="channel", kw=dict(flow="NS", mach=0.3, reynolds=200.0, les="smagorinsky")),
+}
+
+
+def run(api, name):
+    c = CASES[name]
+    phys = make_physics(**c["kw"])
+    mesh = get_mesh(c["ne"], c["N"], c["nodes"], 0.1, True, bc=c["bc"], phys=phys)
+    sem = DGSem(api, mesh, phys)
+    sem.set_initial_condition((lambda x: channel_state(x, phys)) if c["bc"] else perturbed_tgv)
+    sem.ComputeTimeDerivative(0.0)
+    out = sem.download(Q=True, QDot=True, gradients=True)
+    sem.TakeRK3Step(0.0, 1.0e-3)
+    out["Q_after_rk3"] = sem.Q()
+    return out
+
+
+if __name__ == "__main__":
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in CASES:
+        out = run(OracleApi(), name)
+        np.savez_compressed(os.path.join(here, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items()})

@@ -1,0 +1,34 @@
+"""Frozen oracle outputs (tests/golden/*.npz, made by tests/golden/make_golden.py): the oracle must still reproduce them
+bit for bit (CPU), and so must the device path (GPU)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_golden import CASES, run  # noqa: E402
+from oracle.oracle_api import OracleApi  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def check(api, name, exact):
+    ref = np.load(os.path.join(GOLDEN, name + ".npz"))
+    got = run(api, name)
+    for k in ref.files:
+        if exact:
+            assert np.array_equal(got[k], ref[k]), (name, k)
+        else:
+            assert np.abs(got[k] - ref[k]).max() <= 1e-13 * max(np.abs(ref[k]).max(), 1e-300), (name, k)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_golden(name):
+    check(OracleApi(), name, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_device_reproduces_golden(gpu_api_cls, name):
+    check(gpu_api_cls(), name, exact=False)
