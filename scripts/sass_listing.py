@@ -6,8 +6,8 @@ n = sys.argv[3] if len(sys.argv) > 3 else "8"
 os.makedirs(out, exist_ok=True)
 txt = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
-want = {"k_gradientILi%sELb1" % n: "k_gradient_tma", "k_volumeILi%sELb0ELb1" % n: "k_volume_tma", "k_volumeILi%sELb1ELb1" % n: "k_volume_split_tma",
-        "k_riemannILi%s" % n: "k_riemann", "k_prolong_qILi%s" % n: "k_prolong_q", "k_red_residual": "k_red_residual",
+want = {"k_gradientILi%sELb1" % n: "k_gradient_tma", "k_volumeILi%sELi0ELb1" % n: "k_volume_tma", "k_volumeILi%sELi1ELb1" % n: "k_volume_split_tma",
+        "k_riemannILi%sELb0" % n: "k_riemann", "k_riemannILi%sELb1" % n: "k_riemann_ext", "k_prolong_qILi%s" % n: "k_prolong_q", "k_red_residual": "k_red_residual",
         "k_red_timestep": "k_red_timestep", "k_red_integrals": "k_red_integrals", "k_halo_pack": "k_halo_pack", "k_halo_unpack": "k_halo_unpack"}
 summary = []
 for f in funcs:
