@@ -880,18 +880,41 @@ int h3d_compute_time_derivative(h3d_handle h, double time) {
     (void)time;   // no time-dependent boundary condition or source is evaluated on the device
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
-    RkArgs rk{0, 1, 0, 0.0, 0.0};
+    RkArgs rk{0, 1, 0, 0.0, 0.0, 0.0, 0};
     return residual(h, rk);
 }
 
 namespace {
-// Williamson RK3 (ExplicitMethods.f90:690-692) and Carpenter-Kennedy RK5 (:812-816) coefficients
+// Coefficient tables of libs/timeintegrator/ExplicitMethods.f90: explicit Euler (:1232-1284), Williamson RK3 (:690-692),
+// Carpenter-Kennedy RK5 (:812-816), LSERK14-4 (:903-905) in the low-storage form G = a G + QDot, Q += c dt G;
+// SSPRK33 (:999-1002) and SSPRK43 (:1125-1128) in the form Q = a G + b Q + c dt QDot with G = Q(t_n)
+const double RK_A1[1] = {0.0}, RK_C1[1] = {1.0};
 const double RK_A3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, RK_C3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
 const double RK_A5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
 const double RK_C5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
-int rkStage(h3d_context* h, int ns, int k, double dt) {
-    const double *a = ns == 3 ? RK_A3 : RK_A5, *c = ns == 3 ? RK_C3 : RK_C5;
-    RkArgs rk{1, (k == ns - 1 || h->storeQDotAlways) ? 1 : 0, 1, a[k], c[k] * dt};
+const double RK_A14[14] = {0.0000000000000000, -0.7188012108672410, -0.7785331173421570, -0.0053282796654044, -0.8552979934029281, -3.9564138245774565, -1.5780575380587385,
+                           -2.0837094552574054, -0.7483334182761610, -0.7032861106563359, +0.0013917096117681, -0.0932075369637460, -0.9514200470875948, -7.1151571693922548};
+const double RK_C14[14] = {0.0367762454319673, 0.3136296607553959, 0.1531848691869027, 0.0030097086818182, 0.3326293790646110, 0.2440251405350864, 0.3718879239592277,
+                           0.6204126221582444, 0.1524043173028741, 0.0760894927419266, 0.0077604214040978, 0.0024647284755382, 0.0780348340049386, 5.5059777270269628};
+const double SSP33_A[3] = {1.0, 3.0 / 4.0, 1.0 / 3.0}, SSP33_B[3] = {0.0, 1.0 / 4.0, 2.0 / 3.0}, SSP33_C[3] = {1.0, 1.0 / 4.0, 2.0 / 3.0};
+const double SSP43_A[4] = {1.0, 0.0, 2.0 / 3.0, 0.0}, SSP43_B[4] = {0.0, 1.0, 1.0 / 3.0, 1.0}, SSP43_C[4] = {0.5, 0.5, 1.0 / 6.0, 0.5};
+int rkStages(int scheme) {
+    switch (scheme) {
+        case H3D_EULER: return 1; case H3D_RK3: return 3; case H3D_RK5: return 5; case H3D_LSERK14_4: return 14;
+        case H3D_SSPRK33: return 3; case H3D_SSPRK43: return 4; default: return 0;
+    }
+}
+int rkStage(h3d_context* h, int scheme, int k, double dt) {
+    const int ns = rkStages(scheme);
+    const int store = (k == ns - 1 || h->storeQDotAlways) ? 1 : 0;
+    if (scheme == H3D_SSPRK33 || scheme == H3D_SSPRK43) {
+        const double *a = scheme == H3D_SSPRK33 ? SSP33_A : SSP43_A, *b = scheme == H3D_SSPRK33 ? SSP33_B : SSP43_B, *c = scheme == H3D_SSPRK33 ? SSP33_C : SSP43_C;
+        RkArgs rk{2, store, 1, a[k], c[k] * dt, b[k], k == 0 ? 1 : 0};
+        return residual(h, rk);
+    }
+    const double *a = scheme == H3D_EULER ? RK_A1 : (scheme == H3D_RK3 ? RK_A3 : (scheme == H3D_RK5 ? RK_A5 : RK_A14));
+    const double *c = scheme == H3D_EULER ? RK_C1 : (scheme == H3D_RK3 ? RK_C3 : (scheme == H3D_RK5 ? RK_C5 : RK_C14));
+    RkArgs rk{1, store, 1, a[k], c[k] * dt, 0.0, 0};
     return residual(h, rk);
 }
 }  // namespace
@@ -900,10 +923,10 @@ int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_ste
     (void)t;
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
-    const int ns = scheme == H3D_RK3 ? 3 : (scheme == H3D_RK5 ? 5 : 0);
+    const int ns = rkStages(scheme);
     if (!ns) { h->err = "unknown Runge-Kutta scheme"; return 1; }
-    for (int k = 0; k < ns; ++k) { int rc = rkStage(h, ns, k, dt); if (rc) return rc; }
-    if (ctd_after_step) { RkArgs rk{0, 1, 0, 0.0, 0.0}; int rc = residual(h, rk); if (rc) return rc; }
+    for (int k = 0; k < ns; ++k) { int rc = rkStage(h, scheme, k, dt); if (rc) return rc; }
+    if (ctd_after_step) { RkArgs rk{0, 1, 0, 0.0, 0.0, 0.0, 0}; int rc = residual(h, rk); if (rc) return rc; }
     return 0;
 }
 
@@ -911,10 +934,10 @@ int h3d_rk_stage(h3d_handle h, int scheme, int stage, double t, double dt) {
     (void)t;
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
-    const int ns = scheme == H3D_RK3 ? 3 : (scheme == H3D_RK5 ? 5 : 0);
+    const int ns = rkStages(scheme);
     if (!ns) { h->err = "unknown Runge-Kutta scheme"; return 1; }
     if (stage < 0 || stage >= ns) { h->err = "Runge-Kutta stage out of range"; return 1; }
-    return rkStage(h, ns, stage, dt);
+    return rkStage(h, scheme, stage, dt);
 }
 
 int h3d_max_residuals(h3d_handle h, double out[5]) {

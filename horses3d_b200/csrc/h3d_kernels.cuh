@@ -51,10 +51,13 @@ struct DevMesh {
 };
 
 struct RkArgs {
-    int mode;        // 0: residual only (QDot stored), 1: RK update G = a G + QDot, Q += cdt G
-    int storeQDot;   // also store QDot in mode 1 (last stage: monitors read it)
+    int mode;        // 0: residual only (QDot stored), 1: low-storage update G = a G + QDot, Q += cdt G (Euler, RK3, RK5, LSERK14-4),
+                     // 2: SSP form Q = a G + b Q + cdt QDot with G = Q at the start of the step (SSPRK33, SSPRK43)
+    int storeQDot;   // also store QDot in modes 1, 2 (last stage: monitors read it)
     int prolong;     // prolong the (updated) Q to the faces at the end
     double a, cdt;
+    double b;        // mode 2
+    int copyG;       // mode 2, first stage: G = Q before the update
 };
 
 #ifndef H3D_NPT_THRESHOLD
@@ -812,11 +815,17 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                         if (m.S) res = res + m.S[q * es + go];
                         if (rk.mode == 0) {
                             m.QDot[q * es + go] = res;
-                        } else {
+                        } else if (rk.mode == 1) {
                             if (rk.storeQDot) m.QDot[q * es + go] = res;
                             const double gg = rk.a * Gk[q] + res;
                             m.G[q * es + go] = gg;
                             Qk[r][q] = Qk[r][q] + rk.cdt * gg;
+                            m.Q[q * es + go] = Qk[r][q];
+                        } else {   // TakeSSPRK33Step / TakeSSPRK43Step (ExplicitMethods.f90:983-1230)
+                            if (rk.storeQDot) m.QDot[q * es + go] = res;
+                            const double g0 = rk.copyG ? Qk[r][q] : Gk[q];
+                            if (rk.copyG) m.G[q * es + go] = g0;
+                            Qk[r][q] = rk.a * g0 + rk.b * Qk[r][q] + rk.cdt * res;
                             m.Q[q * es + go] = Qk[r][q];
                         }
                     }

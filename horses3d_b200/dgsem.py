@@ -107,8 +107,14 @@ class DGSem:
     def ComputeTimeDerivative(self, time=0.0):
         self.api.call("compute_time_derivative", float(time))
 
-    _RK_B = {P.RK3: (0.0, 1.0 / 3.0, 3.0 / 4.0),                                               # ExplicitMethods.f90:690-692
-             P.RK5: (0.0, 0.1496590219993, 0.3704009573644, 0.6222557631345, 0.9582821306748)}   # :812-816
+    # stage times t + b dt (ExplicitMethods.f90:690-692, 812-816, 903-905; d(k) of the SSP schemes :1002, :1128)
+    _RK_B = {P.EULER: (0.0,), P.RK3: (0.0, 1.0 / 3.0, 3.0 / 4.0),
+             P.RK5: (0.0, 0.1496590219993, 0.3704009573644, 0.6222557631345, 0.9582821306748),
+             P.LSERK14_4: (0.0000000000000000, 0.0367762454319673, 0.1249685262725025, 0.2446177702277698, 0.2476149531070420, 0.2969311120382472,
+                           0.3978149645802642, 0.5270854589440328, 0.6981269994175695, 0.8190890835352128, 0.8527059887098624, 0.8604711817462826,
+                           0.8627060376969976, 0.8734213127600976),
+             P.SSPRK33: (0.0, 1.0, 0.5), P.SSPRK43: (0.0, 0.5, 1.0, 0.5)}
+    SCHEMES = {"euler": P.EULER, "rk3": P.RK3, "rk5": P.RK5, "lserk14-4": P.LSERK14_4, "ssprk33": P.SSPRK33, "ssprk43": P.SSPRK43}
 
     def _rk_step(self, scheme, t, dt, ctd_after_step, source):
         """source: None (the source set by set_source, constant over the step) or a callable time -> S array: the
@@ -128,6 +134,18 @@ class DGSem:
 
     def TakeRK5Step(self, t, dt, ctd_after_step=False, source=None):
         self._rk_step(P.RK5, t, dt, ctd_after_step, source)
+
+    def TakeExplicitEulerStep(self, t, dt, ctd_after_step=False, source=None):
+        self._rk_step(P.EULER, t, dt, ctd_after_step, source)
+
+    def TakeLSERK14_4Step(self, t, dt, ctd_after_step=False, source=None):
+        self._rk_step(P.LSERK14_4, t, dt, ctd_after_step, source)
+
+    def TakeSSPRK33Step(self, t, dt, ctd_after_step=False, source=None):
+        self._rk_step(P.SSPRK33, t, dt, ctd_after_step, source)
+
+    def TakeSSPRK43Step(self, t, dt, ctd_after_step=False, source=None):
+        self._rk_step(P.SSPRK43, t, dt, ctd_after_step, source)
 
     def MaxTimeStep(self, cfl, dcfl):
         a, b = C.c_double(), C.c_double()
@@ -197,7 +215,8 @@ class DGSem:
         t_final selects the time-accurate mode: the step is clipped to land on t_final (CorrectDt, :1130-1135) and the
         loop ends there (:882-887).  Returns the per-step records (the reference's monitor buffer lines), or only the
         last one with keep="last"."""
-        step = self.TakeRK3Step if scheme.upper() == "RK3" else self.TakeRK5Step
+        code = self.SCHEMES[scheme.lower()]
+        step = lambda t, dt, **kw: self._rk_step(code, t, dt, kw.get("ctd_after_step", False), kw.get("source"))
         t = t0
         if source is not None:
             self.set_source(source(t))

@@ -14,6 +14,7 @@ LES = {"none": 0, "smagorinsky": 1}
 
 INT_VOLUME, INT_KINETIC_ENERGY, INT_KINETIC_ENERGY_RATE, INT_ENSTROPHY = 0, 1, 2, 3
 RK3, RK5 = 3, 5
+EULER, LSERK14_4, SSPRK33, SSPRK43 = 1, 14, 33, 43
 SURF_SURFACE, SURF_MASS_FLOW, SURF_FLOW_RATE, SURF_PRESSURE, SURF_VEC_SURFACE, SURF_TOTAL_FORCE, SURF_PRESSURE_FORCE, SURF_VISCOUS_FORCE = range(8)
 FACE_INTERIOR, FACE_BOUNDARY, FACE_MPI = 1, 2, 3
 BC_TYPES = {"periodic": 0, "noslipwall": 1, "freeslipwall": 2, "inflow": 3, "outflow": 4}

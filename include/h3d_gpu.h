@@ -77,8 +77,12 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_INT_ENSTROPHY 3
 
 /* RK schemes (libs/timeintegrator/ExplicitMethods.f90:667,790) */
+#define H3D_EULER 1       /* TakeExplicitEulerStep, ExplicitMethods.f90:1232 */
 #define H3D_RK3 3
 #define H3D_RK5 5
+#define H3D_LSERK14_4 14  /* TakeLSERK14_4Step, :884 */
+#define H3D_SSPRK33 33     /* TakeSSPRK33Step, :983 (without the optional stage limiter) */
+#define H3D_SSPRK43 43     /* TakeSSPRK43Step, :1109 */
 
 /* Run-time physics: the protected module variables the reference's kernels read
  * (libs/physics/navierstokes/PhysicsStorage_NS.f90:81-131,190-250,285,416-429;

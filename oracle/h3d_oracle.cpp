@@ -1253,14 +1253,48 @@ int orc_compute_time_derivative(void* p, double time) { computeTimeDerivative(*(
 
 // TakeRK3Step / TakeRK5Step (libs/timeintegrator/ExplicitMethods.f90:667-788, 790-882)
 namespace {
+// libs/timeintegrator/ExplicitMethods.f90: Euler :1232-1284, RK3 :690-692, RK5 :812-816, LSERK14-4 :903-905, SSPRK33 :999-1002, SSPRK43 :1125-1128
+const double RK_A1[1] = {0.0}, RK_B1[1] = {0.0}, RK_C1[1] = {1.0};
 const double RK_A3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, RK_B3[3] = {0.0, 1.0 / 3.0, 3.0 / 4.0}, RK_C3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
 const double RK_A5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
 const double RK_B5[5] = {0.0, 0.1496590219993, 0.3704009573644, 0.6222557631345, 0.9582821306748};
 const double RK_C5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
-double rkStage(Oracle& o, int ns, int k, double t, double dt) {   // loop body of ExplicitMethods.f90:746-760, 857-872
-    const double *a = ns == 3 ? RK_A3 : RK_A5, *b = ns == 3 ? RK_B3 : RK_B5, *c = ns == 3 ? RK_C3 : RK_C5;
+const double RK_A14[14] = {0.0000000000000000, -0.7188012108672410, -0.7785331173421570, -0.0053282796654044, -0.8552979934029281, -3.9564138245774565, -1.5780575380587385,
+                           -2.0837094552574054, -0.7483334182761610, -0.7032861106563359, +0.0013917096117681, -0.0932075369637460, -0.9514200470875948, -7.1151571693922548};
+const double RK_B14[14] = {0.0000000000000000, 0.0367762454319673, 0.1249685262725025, 0.2446177702277698, 0.2476149531070420, 0.2969311120382472, 0.3978149645802642,
+                           0.5270854589440328, 0.6981269994175695, 0.8190890835352128, 0.8527059887098624, 0.8604711817462826, 0.8627060376969976, 0.8734213127600976};
+const double RK_C14[14] = {0.0367762454319673, 0.3136296607553959, 0.1531848691869027, 0.0030097086818182, 0.3326293790646110, 0.2440251405350864, 0.3718879239592277,
+                           0.6204126221582444, 0.1524043173028741, 0.0760894927419266, 0.0077604214040978, 0.0024647284755382, 0.0780348340049386, 5.5059777270269628};
+const double SSP33_A[3] = {1.0, 3.0 / 4.0, 1.0 / 3.0}, SSP33_B[3] = {0.0, 1.0 / 4.0, 2.0 / 3.0}, SSP33_C[3] = {1.0, 1.0 / 4.0, 2.0 / 3.0}, SSP33_D[3] = {0.0, 1.0, 0.5};
+const double SSP43_A[4] = {1.0, 0.0, 2.0 / 3.0, 0.0}, SSP43_B[4] = {0.0, 1.0, 1.0 / 3.0, 1.0}, SSP43_C[4] = {0.5, 0.5, 1.0 / 6.0, 0.5}, SSP43_D[4] = {0.0, 0.5, 1.0, 0.5};
+int rkStages(int scheme) {
+    switch (scheme) {
+        case H3D_EULER: return 1; case H3D_RK3: return 3; case H3D_RK5: return 5; case H3D_LSERK14_4: return 14;
+        case H3D_SSPRK33: return 3; case H3D_SSPRK43: return 4; default: return 0;
+    }
+}
+double rkStage(Oracle& o, int scheme, int k, double t, double dt) {   // loop bodies of the steppers
+    if (scheme == H3D_SSPRK33 || scheme == H3D_SSPRK43) {
+        const bool s3 = scheme == H3D_SSPRK33;
+        const double *a = s3 ? SSP33_A : SSP43_A, *b = s3 ? SSP33_B : SSP43_B, *c = s3 ? SSP33_C : SSP43_C, *d = s3 ? SSP33_D : SSP43_D;
+        if (k == 0) o.G = o.Q;
+        const double tk = t + d[k] * dt;
+        computeTimeDerivative(o, tk);
+        const double ak = a[k], bk = b[k], ck = c[k];
+#pragma omp parallel for schedule(static)
+        for (size_t q = 0; q < o.Q.size(); ++q) o.Q[q] = ak * o.G[q] + bk * o.Q[q] + ck * dt * o.QDot[q];
+        return tk;
+    }
+    const double *a = scheme == H3D_EULER ? RK_A1 : scheme == H3D_RK3 ? RK_A3 : scheme == H3D_RK5 ? RK_A5 : RK_A14;
+    const double *b = scheme == H3D_EULER ? RK_B1 : scheme == H3D_RK3 ? RK_B3 : scheme == H3D_RK5 ? RK_B5 : RK_B14;
+    const double *c = scheme == H3D_EULER ? RK_C1 : scheme == H3D_RK3 ? RK_C3 : scheme == H3D_RK5 ? RK_C5 : RK_C14;
     const double tk = t + b[k] * dt;
     computeTimeDerivative(o, tk);
+    if (scheme == H3D_EULER) {   // Q = Q + deltaT QDot (:1262-1271)
+#pragma omp parallel for schedule(static)
+        for (size_t q = 0; q < o.Q.size(); ++q) o.Q[q] = o.Q[q] + dt * o.QDot[q];
+        return tk;
+    }
     const double ak = a[k], cdt = c[k] * dt;
 #pragma omp parallel for schedule(static)
     for (size_t q = 0; q < o.Q.size(); ++q) {
@@ -1273,20 +1307,20 @@ double rkStage(Oracle& o, int ns, int k, double t, double dt) {   // loop body o
 
 int orc_rk_step(void* p, int scheme, double t, double dt, int ctd_after_step) {
     Oracle& o = *(Oracle*)p;
-    const int ns = scheme == H3D_RK3 ? 3 : scheme == H3D_RK5 ? 5 : 0;
+    const int ns = rkStages(scheme);
     if (!ns) { o.err = "unknown RK scheme"; return 1; }
     double tk = t;
-    for (int k = 0; k < ns; ++k) tk = rkStage(o, ns, k, t, dt);
-    if (ctd_after_step) computeTimeDerivative(o, ns == 3 ? t + dt : tk);
+    for (int k = 0; k < ns; ++k) tk = rkStage(o, scheme, k, t, dt);
+    if (ctd_after_step) computeTimeDerivative(o, (scheme == H3D_RK3 || scheme == H3D_SSPRK33 || scheme == H3D_SSPRK43) ? t + dt : tk);
     return 0;
 }
 
 int orc_rk_stage(void* p, int scheme, int stage, double t, double dt) {
     Oracle& o = *(Oracle*)p;
-    const int ns = scheme == H3D_RK3 ? 3 : scheme == H3D_RK5 ? 5 : 0;
+    const int ns = rkStages(scheme);
     if (!ns) { o.err = "unknown RK scheme"; return 1; }
     if (stage < 0 || stage >= ns) { o.err = "Runge-Kutta stage out of range"; return 1; }
-    rkStage(o, ns, stage, t, dt);
+    rkStage(o, scheme, stage, t, dt);
     return 0;
 }
 

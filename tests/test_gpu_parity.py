@@ -154,7 +154,7 @@ def test_probes_match_oracle(gpu_api_cls):
     assert np.abs(vals[0] - vals[1]).max() <= 1e-13 * np.abs(vals[0]).max()
 
 
-@pytest.mark.parametrize("scheme", ["RK3", "RK5"])
+@pytest.mark.parametrize("scheme", ["RK3", "RK5", "Euler", "LSERK14-4", "SSPRK33", "SSPRK43"])
 def test_rk_steps_and_monitors_match_oracle(gpu_api_cls, scheme):
     mesh = get_mesh(4, 3, GAUSS, 0.1, True)
     phys = make_physics(flow="NS", mach=0.08, reynolds=1600.0)

@@ -180,6 +180,25 @@ def test_k3_navier_stokes_convergence_p7():
     assert np.abs(qerr - q0).max() < 1.0e-11
 
 
+def test_time_steppers_converge_to_the_same_solution():
+    """Euler, RK3, RK5, LSERK14-4, SSPRK33, SSPRK43 (ExplicitMethods.f90) over the same interval: the differences to a fine RK5
+    reference shrink with the order of each scheme when dt is halved (1, 3, 4, 4, 3, 3)."""
+    m = HostMesh.box(2, amp=0.1, shuffle=True).connect().geometry(3, GAUSS)
+    phys = make_physics(flow="NS", mach=0.3, reynolds=100.0)
+
+    def run(scheme, nsteps, T=0.02):
+        sem = DGSem(oracle_api.OracleApi(), m, phys)
+        sem.set_initial_condition(taylor_green_ic)
+        sem.integrate(nsteps, dt=T / nsteps, scheme=scheme, monitors=False, keep="last")
+        return sem.Q()
+
+    ref = run("rk5", 64)
+    for scheme, order in [("euler", 1), ("rk3", 3), ("rk5", 4), ("lserk14-4", 4), ("ssprk33", 3), ("ssprk43", 3)]:
+        e1, e2 = np.abs(run(scheme, 2) - ref).max(), np.abs(run(scheme, 4) - ref).max()
+        rate = np.log2(e1 / e2)
+        assert e2 < e1 and rate > order - 0.6, (scheme, e1, e2, rate)
+
+
 def test_rk_step_equals_its_stages():
     m = HostMesh.box(2, amp=0.1, shuffle=True).connect().geometry(3, GAUSS)
     phys = make_physics(flow="NS", mach=0.08, reynolds=1600.0)
