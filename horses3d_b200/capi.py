@@ -47,6 +47,10 @@ class Binding:
         "volume_integral": [C.c_int, C.POINTER(C.c_double)],
         "has_nan": [C.POINTER(C.c_int)],
         "surface_integral": [C.c_int, C.c_int, _D],
+        "statistics_update": [C.c_int],
+        "snapshot_begin": [],
+        "snapshot_end": [_D],
+        "statistics_download": [_D, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "probe": [C.c_int, _D, _D, _D, _D, _D, _D],
     }
 

@@ -32,6 +32,9 @@ struct h3d_context {
     bool havePhysics = false, haveBasis = false, haveMesh = false;
     int N = -1, n = 0, nodeType = H3D_GAUSS;
     std::vector<double> hx;   // node positions of the 1-D set (MaxTimeStep)
+    double* dSnap = nullptr; double* hSnap = nullptr; size_t snapDoubles = 0; bool snapPending = false;   // asynchronous autosave
+    cudaStream_t sCopy = nullptr; cudaEvent_t evSnap = nullptr, evSnapDone = nullptr;
+    double* dStats = nullptr; int statVars = 0, statSamples = 0;   // running averages [var][e][node] (StatisticsMonitor)
     bool extPhysics = false;   // a Riemann solver / average outside the base set: kernels instantiated with EXT
     std::vector<double> hHatD, hD, hV, hB;   // host copies of the operators (kernel-parameter Ops<n>)
     int nElem = 0, nFace = 0, nSeq = 0;          // device order: [0,nSeq) interior elements, [nSeq,nElem) MPI elements
@@ -256,6 +259,36 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_surface(DevMesh m, Phys ph,
         }
     }
     blockReduce<13, 2>(v, partial + (size_t)blockIdx.x * 13);
+}
+
+// StatisticsMonitor_UpdateValues (StatisticsMonitor.f90:279-540); data [var][e][node]
+__global__ void k_statistics(DevMesh m, size_t nn, int nv, double ratio, double inv, double* __restrict__ data) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (size_t)gridDim.x * blockDim.x) {
+        double Q[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) Q[q] = m.Q[(size_t)q * nn + t];
+        const double r1 = inv / Q[0], r2 = inv / pow2(Q[0]);
+        double* d = data + t;
+        d[0 * nn] = d[0 * nn] * ratio + Q[1] * r1;
+        d[1 * nn] = d[1 * nn] * ratio + Q[2] * r1;
+        d[2 * nn] = d[2 * nn] * ratio + Q[3] * r1;
+        d[3 * nn] = d[3 * nn] * ratio + pow2(Q[1]) * r2;
+        d[4 * nn] = d[4 * nn] * ratio + pow2(Q[2]) * r2;
+        d[5 * nn] = d[5 * nn] * ratio + pow2(Q[3]) * r2;
+        d[6 * nn] = d[6 * nn] * ratio + Q[1] * Q[2] * r2;
+        d[7 * nn] = d[7 * nn] * ratio + Q[1] * Q[3] * r2;
+        d[8 * nn] = d[8 * nn] * ratio + Q[2] * Q[3] * r2;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) d[(size_t)(9 + q) * nn] = d[(size_t)(9 + q) * nn] * ratio + Q[q] * inv;
+        if (nv == 29) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                d[(size_t)(14 + q) * nn] = d[(size_t)(14 + q) * nn] * ratio + m.Ux[(size_t)q * nn + t] * inv;
+                d[(size_t)(19 + q) * nn] = d[(size_t)(19 + q) * nn] * ratio + m.Uy[(size_t)q * nn + t] * inv;
+                d[(size_t)(24 + q) * nn] = d[(size_t)(24 + q) * nn] * ratio + m.Uz[(size_t)q * nn + t] * inv;
+            }
+        }
+    }
 }
 
 // Probe_Update (Probe.f90:330-420): one CTA per probe
@@ -582,6 +615,9 @@ int h3d_destroy(h3d_handle h) {
     if (h->dSource) cudaFree(h->dSource);
     if (h->dPartial) cudaFree(h->dPartial);
     if (h->hScalars) cudaFreeHost(h->hScalars);
+    if (h->dSnap) cudaFree(h->dSnap);
+    if (h->hSnap) cudaFreeHost(h->hSnap);
+    if (h->sCopy) { cudaStreamDestroy(h->sCopy); cudaEventDestroy(h->evSnap); cudaEventDestroy(h->evSnapDone); }
     for (cudaEvent_t ev : {h->evA, h->evB, h->evFaces, h->evGrad, h->evSent, h->evT0, h->evT1}) if (ev) cudaEventDestroy(ev);
     if (h->sCompute) cudaStreamDestroy(h->sCompute);
     if (h->sComm) cudaStreamDestroy(h->sComm);
@@ -852,6 +888,44 @@ int h3d_download(h3d_handle h, double* Q, double* QDot, double* Ux, double* Uy, 
     return 0;
 }
 
+int h3d_snapshot_begin(h3d_handle h) {
+    if (!h->haveMesh) { h->err = "no mesh"; return 1; }
+    if (h->snapPending) { h->err = "a snapshot is already in flight: call h3d_snapshot_end first"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    const int n3 = h->n * h->n * h->n;
+    const size_t nd = 5 * (size_t)h->nElem * n3;
+    if (!h->sCopy) {
+        CTX_CHECK(cudaStreamCreateWithFlags(&h->sCopy, cudaStreamNonBlocking));
+        CTX_CHECK(cudaEventCreateWithFlags(&h->evSnap, cudaEventDisableTiming));
+        CTX_CHECK(cudaEventCreateWithFlags(&h->evSnapDone, cudaEventDisableTiming));
+    }
+    if (h->snapDoubles < nd) {
+        if (h->dSnap) cudaFree(h->dSnap);
+        if (h->hSnap) cudaFreeHost(h->hSnap);
+        CTX_CHECK(cudaMalloc((void**)&h->dSnap, nd * sizeof(double)));
+        CTX_CHECK(cudaMallocHost((void**)&h->hSnap, nd * sizeof(double)));
+        h->snapDoubles = nd;
+    }
+    // the snapshot is taken in stream order with the time loop; only the PCIe transfer runs beside it
+    k_soa_to_aos<<<148 * 8, 256, 0, h->sCompute>>>(h->m.Q, h->dSnap, h->dPermE, h->nElem, n3, 5);
+    ++h->launches;
+    CTX_CHECK(cudaEventRecord(h->evSnap, h->sCompute));
+    CTX_CHECK(cudaStreamWaitEvent(h->sCopy, h->evSnap, 0));
+    CTX_CHECK(cudaMemcpyAsync(h->hSnap, h->dSnap, nd * sizeof(double), cudaMemcpyDeviceToHost, h->sCopy));
+    CTX_CHECK(cudaEventRecord(h->evSnapDone, h->sCopy));
+    h->snapPending = true;
+    return 0;
+}
+
+int h3d_snapshot_end(h3d_handle h, double* Q) {
+    if (!h->snapPending) { h->err = "no snapshot in flight"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    CTX_CHECK(cudaEventSynchronize(h->evSnapDone));
+    h->snapPending = false;
+    if (Q) std::memcpy(Q, h->hSnap, 5 * (size_t)h->nElem * h->n * h->n * h->n * sizeof(double));
+    return 0;
+}
+
 int h3d_set_source(h3d_handle h, const double* S) {
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1046,6 +1120,40 @@ int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, c
     cudaError_t e2 = cudaStreamSynchronize(h->sCompute);
     cudaFree(dEV); cudaFree(dL);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { h->err = "probe evaluation failed"; return 2; }
+    return 0;
+}
+
+int h3d_statistics_update(h3d_handle h, int reset) {
+    if (checkReady(h)) return 1;
+    CTX_CHECK(cudaSetDevice(h->device));
+    const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
+    const int nv = h->physics.computeGradients ? 29 : 14;
+    if (!h->dStats || h->statVars != nv) {
+        if (devAlloc(h, &h->dStats, nn * nv)) return 2;
+        h->statVars = nv; reset = 1;
+    }
+    if (reset) { CTX_CHECK(cudaMemsetAsync(h->dStats, 0, nn * nv * sizeof(double), h->sCompute)); h->statSamples = 0; }
+    const double inv = 1.0 / (h->statSamples + 1), ratio = h->statSamples * inv;
+    k_statistics<<<RED_BLOCKS * 4, RED_THREADS, 0, h->sCompute>>>(h->m, nn, nv, ratio, inv, h->dStats);
+    ++h->launches; ++h->statSamples;
+    CTX_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int h3d_statistics_download(h3d_handle h, double* data, int* nVars, int* nSamples) {
+    if (!h->dStats) { h->err = "no statistics have been accumulated"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    *nVars = h->statVars; *nSamples = h->statSamples;
+    if (!data) return 0;
+    const int n3 = h->n * h->n * h->n, nv = h->statVars;
+    const size_t nn = (size_t)h->nElem * n3;
+    std::vector<double> tmp(nn * nv);
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+    CTX_CHECK(cudaMemcpy(tmp.data(), h->dStats, nn * nv * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int ed = 0; ed < h->nElem; ++ed) {   // device element order -> host order, SoA -> the reference's data(var,i,j,k)
+        const size_t eh = (size_t)h->permE[ed];
+        for (int node = 0; node < n3; ++node) for (int v = 0; v < nv; ++v) data[(eh * n3 + node) * nv + v] = tmp[(size_t)v * nn + (size_t)ed * n3 + node];
+    }
     return 0;
 }
 

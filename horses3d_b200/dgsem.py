@@ -194,6 +194,27 @@ class DGSem:
             return float(np.dot(F, d))
         raise ValueError("surface monitor variable not recognized: " + variable)
 
+    def snapshot_begin(self):
+        """Start an asynchronous copy of the current Q to the host (autosave beside the time loop)."""
+        self.api.call("snapshot_begin")
+
+    def snapshot_end(self):
+        out = np.empty(self._shape)
+        self.api.call("snapshot_end", _ptr(out, np.float64))
+        return out
+
+    def UpdateStatistics(self, reset=False):
+        """StatisticsMonitor_UpdateValues (libs/monitors/StatisticsMonitor.f90:279)."""
+        self.api.call("statistics_update", int(reset))
+
+    def Statistics(self):
+        """(data[e][k][j][i][var], samples): u v w uu vv ww uv uw vw, Q(5) [, U_x, U_y, U_z]."""
+        nv, ns = C.c_int(), C.c_int()
+        self.api.call("statistics_download", None, C.byref(nv), C.byref(ns))
+        data = np.empty(self._shape[:-1] + (nv.value,))
+        self.api.call("statistics_download", _ptr(data, np.float64), C.byref(nv), C.byref(ns))
+        return data, ns.value
+
     def checkForNan(self):
         f = C.c_int()
         self.api.call("has_nan", C.byref(f))

@@ -167,6 +167,13 @@ int h3d_set_halo(h3d_handle h, int nNeighbors, const int* neighborRank, const in
 int h3d_upload_Q(h3d_handle h, const double* Q);
 /* any pointer may be NULL.  Ux,Uy,Uz are e % storage % U_x,U_y,U_z of the last residual evaluation. */
 int h3d_download(h3d_handle h, double* Q, double* QDot, double* Ux, double* Uy, double* Uz);
+
+/* Autosave without stalling the time loop (TimeIntegrator.f90:924 SaveSolution): _begin takes a
+ * device-side snapshot of Q (in the reference's packed layout) at the current point of the time loop and starts its
+ * transfer into pinned host memory on a separate stream; the caller keeps stepping; _end waits for the transfer and
+ * copies the snapshot into Q.  One snapshot in flight at a time. */
+int h3d_snapshot_begin(h3d_handle h);
+int h3d_snapshot_end(h3d_handle h, double* Q);
 /* e % storage % S_NS evaluated by the host (UserDefinedSourceTermNS, SpatialDiscretization.f90:569-577);
  * NULL clears it.  Kept until replaced. */
 int h3d_set_source(h3d_handle h, const double* S);
@@ -219,6 +226,12 @@ int h3d_surface_integral(h3d_handle h, int zone, int kind, double out[3]);
 #define H3D_PROBE_MACH 5
 #define H3D_PROBE_K 6
 int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, const double* lxi, const double* leta, const double* lzeta, double* values);
+/* StatisticsMonitor_UpdateValues (libs/monitors/StatisticsMonitor.f90:279-540): running averages, kept on the device.
+ * Variables per node, in the reference's order: u v w uu vv ww uv uw vw | Q(1:5) | U_x(1:5) U_y(1:5) U_z(1:5) (the gradients
+ * only with computeGradients, as "save gradients with solution").  reset != 0 zeroes the averages and the sample count
+ * first ("@reset").  download: data[e][k][j][i][nVars] (nVars = 14 or 29), nSamples = samples accumulated so far. */
+int h3d_statistics_update(h3d_handle h, int reset);
+int h3d_statistics_download(h3d_handle h, double* data, int* nVars, int* nSamples);
 /* checkForNan (ExplicitMethods.f90:1856-1905): flag = 1 if any NaN in Q on any rank */
 int h3d_has_nan(h3d_handle h, int* flag);
 

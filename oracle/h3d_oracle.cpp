@@ -56,6 +56,8 @@ struct Oracle {
     std::vector<double> JaXi, JaEta, JaZeta, jac, invJac, xyz, volume;
     std::vector<double> fNormal, fT1, fT2, fJac, fX, fSurface;
     std::vector<double> dWall, fdWall;      // e % geom % dWall(i,j,k), f % geom % dWall(i,j)
+    std::vector<double> stats; int statSamples = 0;
+    std::vector<double> snapshot;   // e % storage % stats % data(var,i,j,k)
     int nZones = 0; std::vector<int> bcType; std::vector<double> bcParams;
     // element storage (reference order [e][k][j][i][eq])
     std::vector<double> Q, QDot, G, S, Ux, Uy, Uz, mu;   // mu: [e][node][2] = (mu, kappa)
@@ -1446,6 +1448,52 @@ int orc_probe(void* p, int nProbes, const int* elem, const int* variable, const 
         }
         values[pr] = value;
     }
+    return 0;
+}
+
+// StatisticsMonitor_UpdateValues (libs/monitors/StatisticsMonitor.f90:279-540), velocities, Reynolds stresses, state [, gradients]
+int orc_snapshot_begin(void* p) { Oracle& o = *(Oracle*)p; o.snapshot = o.Q; return 0; }
+int orc_snapshot_end(void* p, double* Q) {
+    Oracle& o = *(Oracle*)p;
+    if (o.snapshot.empty()) { o.err = "no snapshot in flight"; return 1; }
+    if (Q) std::memcpy(Q, o.snapshot.data(), o.snapshot.size() * sizeof(double));
+    o.snapshot.clear();
+    return 0;
+}
+int orc_statistics_update(void* p, int reset) {
+    Oracle& o = *(Oracle*)p;
+    const int nv = o.ph.computeGradients ? 29 : 14;
+    const size_t nn = (size_t)o.nElem * o.n3();
+    if (reset || o.stats.size() != nn * nv) { o.stats.assign(nn * nv, 0.0); o.statSamples = 0; }
+    const double inv_nsamples_plus_1 = 1.0 / (o.statSamples + 1);
+    const double ratio = o.statSamples * inv_nsamples_plus_1;
+    for (size_t g = 0; g < nn; ++g) {
+        double* data = &o.stats[g * nv]; const double* Q = &o.Q[5 * g];
+        const double rfactor1 = inv_nsamples_plus_1 / Q[IRHO], rfactor2 = inv_nsamples_plus_1 / POW2(Q[IRHO]);
+        data[0] = data[0] * ratio + Q[IRHOU] * rfactor1;
+        data[1] = data[1] * ratio + Q[IRHOV] * rfactor1;
+        data[2] = data[2] * ratio + Q[IRHOW] * rfactor1;
+        data[3] = data[3] * ratio + POW2(Q[IRHOU]) * rfactor2;
+        data[4] = data[4] * ratio + POW2(Q[IRHOV]) * rfactor2;
+        data[5] = data[5] * ratio + POW2(Q[IRHOW]) * rfactor2;
+        data[6] = data[6] * ratio + Q[IRHOU] * Q[IRHOV] * rfactor2;
+        data[7] = data[7] * ratio + Q[IRHOU] * Q[IRHOW] * rfactor2;
+        data[8] = data[8] * ratio + Q[IRHOV] * Q[IRHOW] * rfactor2;
+        for (int q = 0; q < 5; ++q) data[9 + q] = data[9 + q] * ratio + Q[q] * inv_nsamples_plus_1;
+        if (nv == 29) for (int q = 0; q < 5; ++q) {
+            data[14 + q] = data[14 + q] * ratio + o.Ux[5 * g + q] * inv_nsamples_plus_1;
+            data[19 + q] = data[19 + q] * ratio + o.Uy[5 * g + q] * inv_nsamples_plus_1;
+            data[24 + q] = data[24 + q] * ratio + o.Uz[5 * g + q] * inv_nsamples_plus_1;
+        }
+    }
+    ++o.statSamples;
+    return 0;
+}
+int orc_statistics_download(void* p, double* data, int* nVars, int* nSamples) {
+    Oracle& o = *(Oracle*)p;
+    if (o.stats.empty()) { o.err = "no statistics have been accumulated"; return 1; }
+    *nVars = (int)(o.stats.size() / ((size_t)o.nElem * o.n3())); *nSamples = o.statSamples;
+    if (data) std::memcpy(data, o.stats.data(), o.stats.size() * sizeof(double));
     return 0;
 }
 

@@ -132,6 +132,48 @@ def test_surface_integrals_match_oracle(gpu_api_cls):
         DGSem(e, get_mesh(2, 2, GAUSS), make_physics(flow="Euler")).SurfaceIntegral(0, P.SURF_TOTAL_FORCE)
 
 
+def test_asynchronous_snapshot(gpu_api_cls):
+    """h3d_snapshot_begin / _end: the snapshot holds the state at the point of the call although the loop kept stepping."""
+    phys = make_physics(flow="NS", mach=0.08, reynolds=1600.0)
+    mesh = get_mesh(4, 3, GAUSS, 0.1, True)
+    sem = DGSem(gpu_api_cls(), mesh, phys)
+    sem.set_initial_condition(taylor_green_ic)
+    sem.TakeRK3Step(0.0, 1e-3)
+    Q1 = sem.Q()
+    sem.snapshot_begin()
+    with pytest.raises(RuntimeError):
+        sem.snapshot_begin()
+    for _ in range(3):
+        sem.TakeRK3Step(0.0, 1e-3)
+    snap = sem.snapshot_end()
+    assert np.array_equal(snap, Q1) and not np.array_equal(sem.Q(), Q1)
+    with pytest.raises(RuntimeError):
+        sem.snapshot_end()
+
+
+def test_statistics_match_oracle(gpu_api_cls):
+    """StatisticsMonitor_UpdateValues: running averages over five steps, with a reset in between."""
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0)
+    mesh = get_mesh(3, 3, GAUSS, 0.1, True)
+    out = []
+    for api in (OracleApi(), gpu_api_cls()):
+        sem = DGSem(api, mesh, phys)
+        sem.set_initial_condition(perturbed_tgv)
+        sem.TakeRK3Step(0.0, 1.0e-2); sem.UpdateStatistics()
+        sem.TakeRK3Step(0.0, 1.0e-2); sem.UpdateStatistics(reset=True)
+        samples = []
+        for _ in range(4):
+            sem.TakeRK3Step(0.0, 1.0e-2); sem.UpdateStatistics()
+            Q = sem.Q(); samples.append(Q[..., 1] / Q[..., 0])
+        data, ns = sem.Statistics()
+        assert ns == 5 and data.shape[-1] == 29
+        out.append((data, np.mean(samples[-4:], axis=0)))
+    (do, _), (dg, _) = out
+    assert np.abs(do - dg).max() <= 1e-13 * np.abs(do).max()
+    for v in range(29):
+        assert np.abs(do[..., v]).max() > 0 or v in ()
+
+
 def test_probes_match_oracle(gpu_api_cls):
     """Probe_Update: every variable at points inside, on a face of and at a corner of curved, re-oriented elements."""
     from horses3d_b200 import probes

@@ -180,6 +180,23 @@ def test_k3_navier_stokes_convergence_p7():
     assert np.abs(qerr - q0).max() < 1.0e-11
 
 
+def test_oracle_statistics_are_running_means():
+    m = HostMesh.box(2, amp=0.1, shuffle=True).connect().geometry(3, GAUSS)
+    sem = DGSem(oracle_api.OracleApi(), m, make_physics(flow="NS", mach=0.3, reynolds=100.0))
+    sem.set_initial_condition(taylor_green_ic)
+    us, uvs, rhos = [], [], []
+    for k in range(4):
+        sem.TakeRK3Step(0.0, 5.0e-3)
+        sem.UpdateStatistics(reset=(k == 0))
+        Q = sem.Q()
+        us.append(Q[..., 1] / Q[..., 0]); uvs.append(Q[..., 1] * Q[..., 2] / Q[..., 0] ** 2); rhos.append(Q[..., 0])
+    data, ns = sem.Statistics()
+    assert ns == 4 and data.shape[-1] == 29
+    assert np.abs(data[..., 0] - np.mean(us, axis=0)).max() < 1e-13
+    assert np.abs(data[..., 6] - np.mean(uvs, axis=0)).max() < 1e-13
+    assert np.abs(data[..., 9] - np.mean(rhos, axis=0)).max() < 1e-13
+
+
 def test_time_steppers_converge_to_the_same_solution():
     """Euler, RK3, RK5, LSERK14-4, SSPRK33, SSPRK43 (ExplicitMethods.f90) over the same interval: the differences to a fine RK5
     reference shrink with the order of each scheme when dt is halved (1, 3, 4, 4, 3, 3)."""
