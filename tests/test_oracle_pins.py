@@ -68,12 +68,13 @@ def test_k2_euler_taylor_green_kepec_10_steps():
 CYLINDER_MESH = "/root/reference/Solver/test/TestMeshes/CylinderNSpol3.mesh"
 
 
-def _cylinder_100_steps(**phys_kw):
+def _cylinder_100_steps(nodes=GAUSS, **phys_kw):
     """Solver/test/NavierStokes/Cylinder*: Re 200, M 0.3, P=3 Gauss, Roe, BR1, RK3, cfl = dcfl = 0.3, 100 steps on the curved
     (bFaceOrder 3) cylinder mesh with no-slip wall, free-slip walls, inflow and outflow."""
     import math
     from horses3d_b200.physics import bc_parameters
-    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe", **phys_kw)
+    phys_kw.setdefault("riemann", "roe")
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, **phys_kw)
     theta, phi = 0.0, 90.0 * (math.pi / 180.0)
     zones = [("innercylinder", "noslipwall"), ("bottom", "freeslipwall"), ("top", "freeslipwall"), ("back", "inflow"),
              ("left", "inflow"), ("front", "inflow"), ("right", "outflow")]
@@ -87,7 +88,7 @@ def _cylinder_100_steps(**phys_kw):
             params.append(bc_parameters("outflow", phys, p=1.0 / phys.gammaM2))
         else:
             params.append(bc_parameters(t, phys))
-    m = HostMesh.read(CYLINDER_MESH).connect([(z, t, None) for z, t in zones], np.array(params)).geometry(3, GAUSS)
+    m = HostMesh.read(CYLINDER_MESH).connect([(z, t, None) for z, t in zones], np.array(params)).geometry(3, nodes)
     assert m.sizes()[:2] == (1864, 6182)
     if phys.les_wall_model:
         m.wall_distances()
@@ -138,6 +139,33 @@ def test_k5b_cylinder_smagorinsky_100_steps():
     assert abs(cl - (-1.582092121135137E-004)) < 1.0e-11
     print("K5b wake_u", wake_u - 9.867445291005896E-009)
     assert abs(wake_u - 9.867445291005896E-009) < 1.0e-11
+
+
+@needs_cylinder_mesh
+def test_k5c_cylinder_ducros_standard_roe_100_steps():
+    """test/NavierStokes/CylinderDucros (split-form + Ducros average, Standard Roe with lambda stabilization 0.9, BR1;
+    split-form forces Gauss-Lobatto nodes): residuals, cd, cl, wake_u and the 1e-11 tolerance from
+    SETUP/ProblemFile.f90:555-615."""
+    got, cd, cl, wake_u = _cylinder_100_steps(nodes=GAUSSLOBATTO, inviscid="split-form", averaging="ducros", riemann="standard roe", lambda_stab=0.9)
+    res = np.array([9.49419906221126, 24.2427358262976, 0.231929845707823, 27.3961550687737, 259.972329181719])
+    print("K5c rel diff", np.abs((got - res) / res).max(), "cd", cd - 35.1193923795559, "cl", cl - (-2.273386753208761E-004), "wake_u", wake_u - 2.218200364909068E-015)
+    assert np.abs((got - res) / (1.0 + res)).max() < 1.0e-11
+    assert abs(cd - 35.1193923795559) < 1.0e-11 * 36.0
+    assert abs(cl - (-2.273386753208761E-004)) < 1.0e-11
+    assert abs(wake_u - 2.218200364909068E-015) < 1.0e-11
+
+
+@needs_cylinder_mesh
+def test_k5d_cylinder_chandrasekar_roe_100_steps():
+    """test/NavierStokes/CylinderChandrasekarRoe (Gauss-Lobatto, split-form + Chandrasekar average, Roe, BR1): residuals
+    (tolerance 1e-7), cd, cl, wake_u (1e-11) from SETUP/ProblemFile.f90:535-590."""
+    got, cd, cl, wake_u = _cylinder_100_steps(nodes=GAUSSLOBATTO, inviscid="split-form", averaging="chandrasekar", riemann="roe")
+    res = np.array([9.292005572719354, 24.258016397589838, 0.2388511827572224, 28.435107391243378, 253.03319158649319])
+    print("K5d rel diff", np.abs((got - res) / res).max(), "cd", cd - 35.517808389300342, "cl", cl - (-0.0001597956781), "wake_u", wake_u - 2.44E-14)
+    assert np.abs(got - res).max() < 1.0e-7
+    assert abs(cd - 35.517808389300342) < 1.0e-11 * 36.0
+    assert abs(cl - (-0.0001597956781)) < 1.0e-11
+    assert abs(wake_u - 2.44E-14) < 1.0e-11
 
 
 UNIT_CUBE_MESH = "/root/reference/Solver/test/TestMeshes/UnitCube4x4.mesh"
