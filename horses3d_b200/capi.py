@@ -36,6 +36,7 @@ class Binding:
         "set_mesh": [C.c_int, C.c_int] + [_D] * 19,
         "set_boundary_conditions": [C.c_int, _D, _D],
         "set_wall_distance": [_D, _D],
+        "set_face_h": [_D],
         "upload_Q": [_D],
         "download": [_D] * 5,
         "set_source": [_D],

@@ -62,6 +62,8 @@ class DGSem:
             if dw.size == 0:
                 raise ValueError("the LES wall model needs wall distances: call HostMesh.wall_distances() first")
             api.call("set_wall_distance", _ptr(dw, np.float64), _ptr(dwf, np.float64))
+        if physics.viscous == P.VISCOUS["ip"]:
+            api.call("set_face_h", _ptr(np.ascontiguousarray(mesh.array("faceH")), np.float64))
         counts = mesh.array("haloCount")
         if len(counts) and hasattr(api, "set_halo"):
             api.set_halo(mesh.array("haloRank"), counts, mesh.array("haloFace"), mesh.array("haloSide"))

@@ -87,7 +87,7 @@ int h3dhost_get_array(void* hp, const char* name, void** ptr, long long* count, 
     DARR("x", h->geom.x) DARR("jGradXi", h->geom.jGradXi) DARR("jGradEta", h->geom.jGradEta) DARR("jGradZeta", h->geom.jGradZeta)
     DARR("jacobian", h->geom.jac) DARR("invJacobian", h->geom.invJac) DARR("volume", h->geom.volume)
     DARR("faceX", h->geom.fx) DARR("faceNormal", h->geom.fnormal) DARR("faceT1", h->geom.ft1) DARR("faceT2", h->geom.ft2)
-    DARR("faceJacobian", h->geom.fjac) DARR("faceSurface", h->geom.fsurface) DARR("dWall", h->geom.dWall) DARR("faceDWall", h->geom.fdWall)
+    DARR("faceJacobian", h->geom.fjac) DARR("faceSurface", h->geom.fsurface) DARR("faceH", h->geom.fh) DARR("dWall", h->geom.dWall) DARR("faceDWall", h->geom.fdWall)
     IARR("haloRank", h->halo.rank) IARR("haloCount", h->halo.count) IARR("haloFace", h->halo.face) IARR("haloSide", h->halo.side)
     IARR("globalElem", h->halo.globalElem) IARR("globalFace", h->halo.globalFace)
 #undef DARR
@@ -149,7 +149,7 @@ int h3dhost_inherit_geometry(void* childp, void* parentp) {
     gatherE(G.x, g.x, 3 * n3); gatherE(G.jGradXi, g.jGradXi, 3 * n3); gatherE(G.jGradEta, g.jGradEta, 3 * n3); gatherE(G.jGradZeta, g.jGradZeta, 3 * n3);
     gatherE(G.jac, g.jac, n3); gatherE(G.invJac, g.invJac, n3); gatherE(G.volume, g.volume, 1);
     gatherF(G.fx, g.fx, 3 * n2); gatherF(G.fnormal, g.fnormal, 3 * n2); gatherF(G.ft1, g.ft1, 3 * n2); gatherF(G.ft2, g.ft2, 3 * n2);
-    gatherF(G.fjac, g.fjac, n2); gatherF(G.fsurface, g.fsurface, 1);
+    gatherF(G.fjac, g.fjac, n2); gatherF(G.fsurface, g.fsurface, 1); gatherF(G.fh, g.fh, 1);
     c->hasGeom = true;
     return 0;
 }

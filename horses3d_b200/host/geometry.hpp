@@ -13,6 +13,7 @@
 // reference enforces by projecting patches down, HexMesh.f90:2830-2840) instead of the analytic blend
 // derivative, and the CGL->node interpolation is sum-factorised.
 #pragma once
+#include <algorithm>
 #include <cstring>
 
 #include "mesh.hpp"
@@ -30,8 +31,11 @@ struct HostGeometry {
     std::vector<double> fx, fnormal, ft1, ft2;              // 3*n^2 per face
     std::vector<double> fjac;                               // n^2 per face
     std::vector<double> fsurface;                           // per face
+    std::vector<double> fh;                                 // per face: f % geom % h (HexMesh.f90:3020-3040)
     std::vector<double> dWall, fdWall;                      // n^3 per element, n^2 per face (optional)
 };
+
+inline void computeFaceMinimumDistance(const HostMesh& m, HostGeometry& g);
 
 struct ElemMap {
     const HostMesh* m; int e; double corners[8][3];
@@ -278,6 +282,24 @@ inline void buildGeometry(const HostMesh& m, int N, int nodeType, HostGeometry& 
             }
             g.fsurface[f] = surf;
         }
+    }
+    computeFaceMinimumDistance(m, g);
+}
+
+// Faces' minimum orthogonal distance estimate (HexMesh.f90:3016-3041): h = min over the adjacent elements of min(J) / max(J_f).
+// A face on a partition cut sees its local element only; the reference then takes the minimum with the neighbour's value
+// (CommunicateMPIFaceMinimumDistance, HexMesh.f90:3059-3145) -- partitions made with inherit_geometry copy the global value.
+inline void computeFaceMinimumDistance(const HostMesh& m, HostGeometry& g) {
+    const size_t n2 = (size_t)g.n * g.n, n3 = n2 * g.n;
+    std::vector<double> minJ(m.nElem());
+    for (int e = 0; e < m.nElem(); ++e) minJ[e] = *std::min_element(g.jac.begin() + e * n3, g.jac.begin() + (e + 1) * n3);
+    g.fh.assign(m.nFaces, 0.0);
+    for (int f = 0; f < m.nFaces; ++f) {
+        const int e1 = m.faceElem[2 * f], e2 = m.faceElem[2 * f + 1];
+        double num;
+        if (e1 >= 0 && e2 >= 0) num = std::min(minJ[e1], minJ[e2]);
+        else num = minJ[std::max(e1, e2)];
+        g.fh[f] = num / *std::max_element(g.fjac.begin() + f * n2, g.fjac.begin() + (f + 1) * n2);
     }
 }
 

@@ -11,6 +11,8 @@ RIEMANN = {"roe": 0, "lax-friedrichs": 1, "central": 2, "rusanov": 3, "standard 
 AVERAGING = {"standard": 0, "kennedy-gruber": 1, "pirozzoli": 2, "ducros": 3, "morinishi": 4, "entropy conserving": 5,
              "chandrasekar": 6}
 LES = {"none": 0, "smagorinsky": 1}
+VISCOUS = {"br1": 0, "br2": 1, "ip": 2}
+IP_VARIANT = {"sipg": -1, "iipg": 0, "nipg": 1}
 
 INT_VOLUME, INT_KINETIC_ENERGY, INT_KINETIC_ENERGY_RATE, INT_ENSTROPHY = 0, 1, 2, 3
 RK3, RK5 = 3, 5
@@ -23,13 +25,14 @@ BC_TYPES = {"periodic": 0, "noslipwall": 1, "freeslipwall": 2, "inflow": 3, "out
 class H3dPhysics(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "gamma", "gammaMinus1", "Mach", "Re", "Pr", "mu", "kappa", "mu_to_kappa", "gammaM2",
-        "S_div_Tref", "T_renorm", "lambdaStab", "smagorinsky_Cs", "Prt")] + [(k, C.c_int) for k in (
-        "flowIsNavierStokes", "computeGradients", "inviscid", "riemann", "averaging", "les", "les_wall_model", "reserved")]
+        "S_div_Tref", "T_renorm", "lambdaStab", "smagorinsky_Cs", "Prt", "penaltyParameter")] + [(k, C.c_int) for k in (
+        "flowIsNavierStokes", "computeGradients", "inviscid", "riemann", "averaging", "les", "les_wall_model", "viscous", "ipVariant", "reserved")]
 
 
 def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="standard", riemann="roe",
                  averaging="standard", lambda_stab=1.0, compute_gradients=None, les="none", smagorinsky_cs=0.2, les_wall_model="none",
-                 sutherland_temperature=None, reference_temperature=None, sutherland_ref_temperature=None):
+                 sutherland_temperature=None, reference_temperature=None, sutherland_ref_temperature=None,
+                 viscous="BR1", penalty_parameter=None, ip_variant="SIPG"):
     p = H3dPhysics()
     gamma = 1.4
     gm1 = 1.4 - 1.0                                   # PhysicsStorage_NS.f90:120 (not 0.4)
@@ -58,6 +61,10 @@ def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="
     p.riemann = RIEMANN[riemann.lower()]
     p.averaging = AVERAGING[averaging.lower()]
     p.lambdaStab = 0.0 if p.riemann == RIEMANN["central"] else lambda_stab    # RiemannSolvers_NS.f90:211-224
+    p.viscous = VISCOUS[viscous.lower()]
+    # "penalty parameter": BR2 eta defaults to 2 (EllipticBR2.f90:80-91), IP sigma to 1 (EllipticIP.f90:110-121)
+    p.penaltyParameter = penalty_parameter if penalty_parameter is not None else {0: 0.0, 1: 2.0, 2: 1.0}[p.viscous]
+    p.ipVariant = IP_VARIANT[ip_variant.lower()]
     p.les = LES[les.lower()]
     p.smagorinsky_Cs = smagorinsky_cs
     p.les_wall_model = {"none": 0, "linear": 1}[les_wall_model.lower()]      # LESModels.f90:137-165

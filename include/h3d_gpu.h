@@ -58,6 +58,11 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_LES_NONE 0
 #define H3D_LES_SMAGORINSKY 1
 
+/* viscous discretization (libs/discretization/EllipticDiscretizations.f90; EllipticBR1.f90, EllipticBR2.f90, EllipticIP.f90) */
+#define H3D_VISCOUS_BR1 0
+#define H3D_VISCOUS_BR2 1      /* penaltyParameter = eta (default 2, EllipticBR2.f90:80-91)                          */
+#define H3D_VISCOUS_IP 2       /* penaltyParameter = sigma (default 1), ipVariant = SIPG -1 | IIPG 0 | NIPG 1 (EllipticIP.f90:26-28,110-150) */
+
 /* face types (libs/mesh/MeshTypes.f90:21-25) */
 #define H3D_FACE_INTERIOR 1
 #define H3D_FACE_BOUNDARY 2
@@ -102,6 +107,7 @@ typedef struct H3dPhysics {
     double lambdaStab;       /* RiemannSolvers_NS lambdaStab (0 for central)    */
     double smagorinsky_Cs;   /* LESModels.f90 Smagorinsky CS                    */
     double Prt;              /* dimensionless % Prt                             */
+    double penaltyParameter; /* BR2 eta / IP sigma ("penalty parameter" key)    */
     int flowIsNavierStokes;  /* 0 = Euler                                       */
     int computeGradients;    /* PhysicsStorage_NS computeGradients              */
     int inviscid;            /* H3D_STANDARD_DG | H3D_SPLIT_DG                  */
@@ -109,6 +115,8 @@ typedef struct H3dPhysics {
     int averaging;           /* H3D_AVG_*                                       */
     int les;                 /* H3D_LES_*                                       */
     int les_wall_model;      /* 0 = none (default), 1 = linear: LS = min(Cs*delta, 0.4*dWall), LESModels.f90:189-203 */
+    int viscous;             /* H3D_VISCOUS_*                                   */
+    int ipVariant;           /* IP: -1 SIPG (default), 0 IIPG, 1 NIPG           */
     int reserved;
 } H3dPhysics;
 
@@ -152,6 +160,10 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace,
 /* e % geom % dWall, f % geom % dWall (HexMesh_ComputeWallDistances, libs/mesh/HexMesh.f90:5594-5692): distance to the
  * nearest no-slip wall node, [e][k][j][i] and [f][j][i].  Needed only with les_wall_model = 1. */
 int h3d_set_wall_distance(h3d_handle h, const double* dWallElem, const double* dWallFace);
+
+/* f % geom % h (HexMesh.f90:3016-3041, for MPI faces after CommunicateMPIFaceMinimumDistance :3059-3145): the faces'
+ * minimum orthogonal distance estimate, [f].  Needed only with viscous = H3D_VISCOUS_IP (penalty, EllipticIP.f90:678-687). */
+int h3d_set_face_h(h3d_handle h, const double* faceH);
 
 /* BCs(zone) % bc (libs/physics/common/BoundaryConditions.f90): type + 16 parameters per zone */
 int h3d_set_boundary_conditions(h3d_handle h, int nZones, const int* bcType, const double* bcParams);

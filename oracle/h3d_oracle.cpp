@@ -56,6 +56,7 @@ struct Oracle {
     std::vector<double> JaXi, JaEta, JaZeta, jac, invJac, xyz, volume;
     std::vector<double> fNormal, fT1, fT2, fJac, fX, fSurface;
     std::vector<double> dWall, fdWall;      // e % geom % dWall(i,j,k), f % geom % dWall(i,j)
+    std::vector<double> fH;                 // f % geom % h
     std::vector<double> stats; int statSamples = 0;
     std::vector<double> snapshot;   // e % storage % stats % data(var,i,j,k)
     int nZones = 0; std::vector<int> bcType; std::vector<double> bcParams;
@@ -869,6 +870,87 @@ void prolongToFaces(Oracle& o, int nv, const std::vector<double>& field, std::ve
 }
 
 // ------------------------------------------------------------------------------------------------
+//  BR2_ComputeGradient (libs/discretization/EllipticBR2.f90:122-297) and IP_ComputeGradient (EllipticIP.f90:189-362),
+//  entered with the local gradients in Ux,Uy,Uz: both prolong the LOCAL gradients first, then lift the interface jumps.
+// ------------------------------------------------------------------------------------------------
+void computeGradientBR2IP(Oracle& o) {
+    const int n = o.n, N = o.N; Idx ix{n};
+    const bool br2 = o.ph.viscous == H3D_VISCOUS_BR2;
+    prolongToFaces(o, 5, o.Ux, o.fUx); prolongToFaces(o, 5, o.Uy, o.fUy); prolongToFaces(o, 5, o.Uz, o.fUz);
+    // BR2_GradientInterfaceSolution / ...Boundary (EllipticBR2.f90:458-592) = IP_GradientInterfaceSolution / ...Boundary
+    // (EllipticIP.f90:410-585): Uhat = 1/2 (UL - UR) J_f, unStar_d = Uhat n_d; the boundary state comes from StateForEqn
+    // (= FlowState for NCONS equations), not from the gradient-variable BC
+#pragma omp parallel for schedule(static)
+    for (int f = 0; f < o.nFace; ++f) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            const double Jf = o.fJac[ix.gnode(f, i, j)]; const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
+            const double* UL = &o.fQ[ix.fnode(f, 0, i, j) * 5];
+            double* uL = &o.unStar[ix.fnode(f, 0, i, j) * 15];
+            if (o.faceType[f] == H3D_FACE_INTERIOR) {
+                const double* UR = &o.fQ[ix.fnode(f, 1, i, j) * 5];
+                int ii, jj; leftIndexes2Right(i, j, N, N, o.faceRot[f], ii, jj);
+                double* uR = &o.unStar[ix.fnode(f, 1, ii, jj) * 15];
+                for (int q = 0; q < 5; ++q) {
+                    double Uhat = 0.5 * (UL[q] - UR[q]) * Jf;
+                    for (int d = 0; d < 3; ++d) { double val = Uhat * nh[d]; uL[d * 5 + q] = val; uR[d * 5 + q] = 1 * val; }
+                }
+            } else if (o.faceType[f] == H3D_FACE_BOUNDARY) {
+                double bvExt[5];
+                for (int q = 0; q < 5; ++q) bvExt[q] = UL[q];
+                BC_FlowState(o, o.faceZone[f], nh, bvExt);
+                for (int q = 0; q < 5; ++q) {
+                    double Uhat = 0.5 * (UL[q] - bvExt[q]) * Jf;
+                    for (int d = 0; d < 3; ++d) uL[d * 5 + q] = Uhat * nh[d];
+                }
+            }
+        }
+    }
+    // BR2_ComputeGradientFaceIntegrals (EllipticBR2.f90:301-454) / IP_ComputeGradientFaceIntegrals (EllipticIP.f90:366-406)
+    const double eta = o.ph.penaltyParameter;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nElem; ++e) {
+        const double* H[6]; double* FU[6][3];
+        for (int lf = 0; lf < 6; ++lf) {
+            const size_t fb = ix.fnode(o.elemFace[6 * e + lf], o.elemFaceSide[6 * e + lf], 0, 0);
+            H[lf] = &o.unStar[fb * 15];
+            FU[lf][0] = &o.fUx[fb * 5]; FU[lf][1] = &o.fUy[fb * 5]; FU[lf][2] = &o.fUz[fb * 5];
+        }
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            size_t g = ix.node(e, i, j, k);
+            // BR2: invjac = 1/jacobian, U -= faceInt * invjac ; IP: invjac = IPmethod * invJacobian, U += faceInt * invjac
+            const double iJ = br2 ? 1.0 / o.jac[g] : o.ph.ipVariant * o.invJac[g];
+            for (int d = 0; d < 3; ++d) {
+                double* Ud = (d == 0 ? o.Ux.data() : d == 1 ? o.Uy.data() : o.Uz.data()) + 5 * g;
+                for (int q = 0; q < 5; ++q) {
+                    double fi = H[ELEFT][((k * n + j) * 3 + d) * 5 + q] * o.b[0 * n + i];
+                    fi = fi + H[ERIGHT][((k * n + j) * 3 + d) * 5 + q] * o.b[1 * n + i];
+                    fi = fi + H[EFRONT][((k * n + i) * 3 + d) * 5 + q] * o.b[0 * n + j];
+                    fi = fi + H[EBACK][((k * n + i) * 3 + d) * 5 + q] * o.b[1 * n + j];
+                    fi = fi + H[EBOTTOM][((j * n + i) * 3 + d) * 5 + q] * o.b[0 * n + k];
+                    fi = fi + H[ETOP][((j * n + i) * 3 + d) * 5 + q] * o.b[1 * n + k];
+                    Ud[q] = br2 ? Ud[q] - fi * iJ : Ud[q] + fi * iJ;
+                }
+            }
+        }
+        if (!br2) continue;
+        // interface gradients correction: the element's own face storage, indexed with the ELEMENT's (j,k) / (i,k) / (i,j)
+        // as the reference does (:362-451), whatever the rotation of the face
+        const int lfs[6] = {ELEFT, ERIGHT, EFRONT, EBACK, EBOTTOM, ETOP};
+        for (int s = 0; s < 6; ++s) {
+            const int lf = lfs[s], side = s & 1, ax = s / 2;
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                const int ab = ax == 0 ? k * n + j : (ax == 1 ? k * n + i : j * n + i);
+                const int l = ax == 0 ? i : (ax == 1 ? j : k);
+                const double bv = o.b[side * n + l] * o.v[side * n + l];
+                const double invjac = 1.0 / o.jac[ix.node(e, i, j, k)];
+                for (int d = 0; d < 3; ++d) for (int q = 0; q < 5; ++q)
+                    FU[lf][d][ab * 5 + q] = FU[lf][d][ab * 5 + q] - eta * H[lf][(ab * 3 + d) * 5 + q] * bv * invjac;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 //  BR1_ComputeGradient (libs/discretization/EllipticBR1.f90:71-160, 168-393)
 // ------------------------------------------------------------------------------------------------
 void computeGradient(Oracle& o, double time) {
@@ -908,6 +990,7 @@ void computeGradient(Oracle& o, double time) {
         prolongToFaces(o, 5, o.Ux, o.fUx); prolongToFaces(o, 5, o.Uy, o.fUy); prolongToFaces(o, 5, o.Uz, o.fUz);
         return;
     }
+    if (o.ph.viscous != H3D_VISCOUS_BR1) { computeGradientBR2IP(o); return; }
     // BR1_ComputeElementInterfaceAverage (:571-627) + Face_ProjectGradientFluxToElements (FaceClass.f90:865-961, factor = 1)
     // BR1_ComputeBoundaryFlux (:686-736)
 #pragma omp parallel for schedule(static)
@@ -1096,6 +1179,11 @@ void computeQDot(Oracle& o, double time) {
                     for (int q = 0; q < 5; ++q) {
                         double fx = 0.5 * (fL[q][IX] + fR[q][IX]), fy = 0.5 * (fL[q][IY] + fR[q][IY]), fz = 0.5 * (fL[q][IZ] + fR[q][IZ]);
                         visc[q] = fx * nh[IX] + fy * nh[IY] + fz * nh[IZ];
+                        // IP_RiemannSolver (EllipticIP.f90:704-761) with PenaltyParameterNS (:678-687)
+                        if (o.ph.viscous == H3D_VISCOUS_IP) {
+                            const double penalty = 0.5 * o.ph.penaltyParameter * (N + 1) * (N + 2) / o.fH[f];
+                            visc[q] = visc[q] - penalty * o.ph.mu * (o.fQ[5 * gL + q] - o.fQ[5 * gR + q]);
+                        }
                     }
                 }
                 RiemannSolver(o, &o.fQ[5 * gL], &o.fQ[5 * gR], nh, &o.fT1[3 * gg], &o.fT2[3 * gg], inv);
@@ -1220,6 +1308,8 @@ int orc_set_wall_distance(void* p, const double* dWallElem, const double* dWallF
     o.dWall.assign(dWallElem, dWallElem + (size_t)o.nElem * o.n3()); o.fdWall.assign(dWallFace, dWallFace + (size_t)o.nFace * o.n * o.n);
     return 0;
 }
+
+int orc_set_face_h(void* p, const double* faceH) { Oracle& o = *(Oracle*)p; o.fH.assign(faceH, faceH + o.nFace); return 0; }
 
 int orc_upload_Q(void* p, const double* Q) { Oracle& o = *(Oracle*)p; std::memcpy(o.Q.data(), Q, o.Q.size() * sizeof(double)); return 0; }
 

@@ -168,6 +168,55 @@ def test_k5d_cylinder_chandrasekar_roe_100_steps():
     assert abs(wake_u - 2.44E-14) < 1.0e-11
 
 
+@needs_cylinder_mesh
+def test_k7_cylinder_br2_100_steps():
+    """test/NavierStokes/CylinderBR2 (viscous discretization = BR2, eta = 2): residuals, cd, cl, wake_u and the 1e-11
+    tolerance from SETUP/ProblemFile.f90:555-615.  Pins BR2_ComputeGradient and its interface-gradient correction."""
+    got, cd, cl, wake_u = _cylinder_100_steps(viscous="BR2")
+    res = np.array([8.9494751074667516, 18.052481444063439, 0.1887988263729878, 24.233109718227368, 244.03459342403502])
+    print("K7 rel diff", np.abs((got - res) / res).max(), "cd", cd - 34.303121634815788, "cl", cl - (-5.536315782160184E-003), "wake_u", wake_u - 8.381270411983929E-009)
+    assert np.abs((got - res) / (1.0 + res)).max() < 1.0e-11
+    assert abs(cd - 34.303121634815788) < 1.0e-11 * 35.0
+    assert abs(cl - (-5.536315782160184E-003)) < 1.0e-11
+    assert abs(wake_u - 8.381270411983929E-009) < 1.0e-11
+
+
+@needs_cylinder_mesh
+def test_k8_cylinder_ip_100_steps():
+    """test/NavierStokes/CylinderIP (viscous discretization = IP, SIPG, sigma = 1): residuals, cd, cl, wake_u and the 1e-11
+    tolerance from SETUP/ProblemFile.f90:555-612.  Pins IP_ComputeGradient, the penalty flux and the faces' h."""
+    got, cd, cl, wake_u = _cylinder_100_steps(viscous="IP")
+    res = np.array([8.2374879363448539E+00, 3.7936823935546542E+01, 1.5394486878254571E-01, 2.4481366234488725E+01, 2.2515000434272847E+02])
+    print("K8 rel diff", np.abs((got - res) / res).max(), "cd", cd - 3.9873101495434206E+01, "cl", cl - (-5.9974378623905977E-04), "wake_u", wake_u - 8.0400149338013901E-09)
+    assert np.abs((got - res) / (1.0 + res)).max() < 1.0e-11
+    assert abs(cd - 3.9873101495434206E+01) < 1.0e-11 * 41.0
+    assert abs(cl - (-5.9974378623905977E-04)) < 1.0e-11
+    assert abs(wake_u - 8.0400149338013901E-09) < 1.0e-11
+
+
+@pytest.mark.parametrize("case", ["KEP_BR2", "KEPEC_IP"])
+def test_k9_taylor_green_split_form_br2_ip_5_steps(case):
+    """test/NavierStokes/TaylorGreenKEP_BR2 (split-form Kennedy-Gruber, Standard Roe, BR2) and TaylorGreenKEPEC_IP
+    (split-form Chandrasekar, Roe-Pike, IP/SIPG): Re 1600, M 0.08, P=3 Gauss-Lobatto, RK3, cfl = dcfl = 0.4, 5 steps on the
+    32^3 periodic box.  Expected values and tolerances from SETUP/ProblemFile.f90:316-367."""
+    kw, res, ke, ker, ens = {
+        "KEP_BR2": (dict(averaging="kennedy-gruber", riemann="standard roe", viscous="BR2"),
+                    [3.7044022120992646E-05, 1.2726954756803863E-01, 1.2726954706398708E-01, 2.5000199683269914E-01, 6.2890286300662734E-01],
+                    1.2499872046477557E-01, -4.2794492040058033E-04, 3.7499666432797546E-01),
+        "KEPEC_IP": (dict(averaging="chandrasekar", riemann="roe-pike", viscous="IP"),
+                     [3.6469242819987200E-05, 1.2726228936783626E-01, 1.2726229047731236E-01, 2.5000215229641615E-01, 6.2895574553694467E-01],
+                     1.2499872046477421E-01, -4.2794492107371625E-04, 3.7499666432797263E-01)}[case]
+    m = HostMesh.box(32).connect().geometry(3, GAUSSLOBATTO)
+    sem = DGSem(oracle_api.OracleApi(), m, make_physics(flow="NS", mach=0.08, reynolds=1600.0, inviscid="split-form", **kw))
+    sem.set_initial_condition(taylor_green_ic)
+    rec = sem.integrate(5, cfl=0.4, dcfl=0.4)[-1]
+    print("K9", case, rec["residuals"] - np.array(res), rec["kinetic energy"] - ke, rec["kinetic energy rate"] - ker, rec["enstrophy"] - ens)
+    assert np.abs(rec["residuals"] - np.array(res)).max() < 1.0e-7
+    assert abs(rec["kinetic energy"] - ke) < 1.0e-11
+    assert abs(rec["kinetic energy rate"] - ker) < 1.0e-11
+    assert abs(rec["enstrophy"] - ens) < 1.0e-11
+
+
 UNIT_CUBE_MESH = "/root/reference/Solver/test/TestMeshes/UnitCube4x4.mesh"
 
 
