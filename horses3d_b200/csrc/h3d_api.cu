@@ -387,7 +387,8 @@ template <int n> int launchGradient(h3d_context* h, int e0, int e1, cudaStream_t
     if (e1 <= e0) return 0;
     using C = KCfg<n>;
     const int tiles = (e1 - e0 + C::EPB - 1) / C::EPB;
-    if (C::TMA_OK && h->useTma) k_gradient<n, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient<n, C::TMA_OK>, C::NT, smemGradient<n, C::TMA_OK>())), C::NT, smemGradient<n, C::TMA_OK>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
+    if (h->ph.viscous != H3D_VISCOUS_BR1) k_gradient<n, false, true><<<tiles, C::NT, smemGradient<n, false, true>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
+    else if (C::TMA_OK && h->useTma) k_gradient<n, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient<n, C::TMA_OK>, C::NT, smemGradient<n, C::TMA_OK>())), C::NT, smemGradient<n, C::TMA_OK>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
     else k_gradient<n, false><<<tiles, C::NT, smemGradient<n, false>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
     ++h->launches; return 0;
 }
@@ -421,6 +422,7 @@ template <int n> int setAttrs(h3d_context* h) {
     using C = KCfg<n>;
     CTX_CHECK(cudaFuncSetAttribute(k_prolong_q<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemProlong<n>()));
     CTX_CHECK(cudaFuncSetAttribute(k_gradient<n, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient<n, false>()));
+    CTX_CHECK(cudaFuncSetAttribute(k_gradient<n, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient<n, false, true>()));
     CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, false>(false, true)));
     // SplitDG: the Navier-Stokes variant (29 padded fields) does not fit 227 KB at n = 10; the Euler variant (14 fields) does
     CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smemVolume<n, false>(true, true), SMEM_LIMIT)));
@@ -523,6 +525,10 @@ int residual(h3d_context* h, const RkArgs& rk) {
     const bool grads = h->physics.computeGradients != 0;
     int rc;
     if (h->ph.wallModel && !h->m.dWall) { h->err = "the LES wall model needs h3d_set_wall_distance"; return 1; }
+    if (h->ph.viscous == H3D_VISCOUS_IP) {
+        if (!h->m.fH) { h->err = "the interior-penalty discretization needs h3d_set_face_h"; return 1; }
+        h->ph.penaltyNum = 0.5 * h->physics.penaltyParameter * (h->N + 1) * (h->N + 2);   // PenaltyParameterNS, EllipticIP.f90:678-687
+    }
     if (!h->facesValid) { ProfScope ps(h, 3, sc); if ((rc = doProlong(h, 0, h->nElem, sc))) return rc; }
     if (multi) {
         CTX_CHECK(cudaEventRecord(h->evFaces, sc));
@@ -643,6 +649,9 @@ int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
     q.gamma = p->gamma; q.gm1 = p->gammaMinus1; q.gammaM2 = p->gammaM2; q.mu = p->mu; q.mu_to_kappa = p->mu_to_kappa;
     q.S_div_Tref = p->S_div_Tref; q.T_renorm = p->T_renorm; q.lambdaStab = p->lambdaStab; q.Cs = p->smagorinsky_Cs;
     q.ns = p->flowIsNavierStokes; q.riemann = p->riemann; q.averaging = p->averaging; q.les = p->les;
+    if (p->viscous < H3D_VISCOUS_BR1 || p->viscous > H3D_VISCOUS_IP) { h->err = "Requested viscous discretization is not implemented."; return 1; }
+    if (p->ipVariant < -1 || p->ipVariant > 1) { h->err = "Unknown selected IP variant."; return 1; }
+    q.viscous = p->flowIsNavierStokes ? p->viscous : H3D_VISCOUS_BR1; q.ipVariant = p->ipVariant; q.eta = p->penaltyParameter;
     h->extPhysics = p->riemann > H3D_RIEMANN_CENTRAL || p->averaging > H3D_AVG_PIROZZOLI;
     q.wallModel = (p->les != H3D_LES_NONE && p->les_wall_model == 1) ? 1 : 0;
     if (p->les_wall_model != 0 && p->les_wall_model != 1) { h->err = "LES wall model not recognized."; return 1; }
@@ -803,7 +812,7 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
         m.lesDelta = dde; m.fDelta = ddf;
         if (h->physics.les != H3D_LES_NONE && (!volume || !faceSurface)) { h->err = "LES needs element volumes and face surfaces"; return 1; }
     }
-    m.S = nullptr; m.bcType = nullptr; m.bcParams = nullptr; m.dWall = nullptr; m.fDWall = nullptr;
+    m.S = nullptr; m.bcType = nullptr; m.bcParams = nullptr; m.dWall = nullptr; m.fDWall = nullptr; m.fH = nullptr;
     for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_BOUNDARY && faceZone[f] < 0) { h->err = "boundary face without a zone"; return 1; }
     h->haveMesh = true; h->facesValid = false;
     return 0;
@@ -823,6 +832,20 @@ int h3d_set_wall_distance(h3d_handle h, const double* dWallElem, const double* d
     CTX_CHECK(cudaMemcpy(dde, de.data(), de.size() * sizeof(double), cudaMemcpyHostToDevice));
     CTX_CHECK(cudaMemcpy(ddf, df.data(), df.size() * sizeof(double), cudaMemcpyHostToDevice));
     m.dWall = dde; m.fDWall = ddf;
+    return 0;
+}
+
+int h3d_set_face_h(h3d_handle h, const double* faceH) {
+    CTX_CHECK(cudaSetDevice(h->device));
+    if (!h->haveMesh) { h->err = "h3d_set_face_h: set the mesh first"; return 1; }
+    if (!faceH) { h->err = "h3d_set_face_h: null array"; return 1; }
+    DevMesh& m = h->m;
+    std::vector<double> df(m.nFace);
+    for (int fd = 0; fd < m.nFace; ++fd) df[fd] = faceH[h->permF[fd]];
+    double* ddf;
+    if (devAlloc(h, &ddf, df.size())) return 2;
+    CTX_CHECK(cudaMemcpy(ddf, df.data(), df.size() * sizeof(double), cudaMemcpyHostToDevice));
+    m.fH = ddf;
     return 0;
 }
 

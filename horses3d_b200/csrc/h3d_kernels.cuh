@@ -41,6 +41,7 @@ struct DevMesh {
     const double *fN, *fT1, *fT2;          // [3][nFace][n2]
     const double* fJ;                      // [nFace][n2]
     const double* fDelta;                  // [nFace] sqrt(surface/n^2)
+    const double* fH;                      // [nFace] f % geom % h (interior penalty) or nullptr
     const int* faceInfo;                   // [nFace] bits0-1 type | bits 8.. zone+1
     const int* rotmap;                     // [8][n2]
     // operators, transposed: MT[l*n + i] = M(i,l)
@@ -147,6 +148,46 @@ __device__ __forceinline__ void prolong_block(const DevMesh& m, const Ops<n>& op
     prolong_axis<n, NV, 2>(m, ops, sF, sTr, sInfo, dst, nLocal);
 }
 
+// BR2: prolongation of the 15 LOCAL gradient fields followed by the interface-gradient correction of the element's own
+// side (BR2_ComputeGradientFaceIntegrals, EllipticBR2.f90:356-451): trace -= eta * unStar_d * (b v)(l) / J(l), l ascending.
+// The reference indexes the face storage with the ELEMENT's trace indices, so the face-frame node m receives the correction
+// evaluated at the element-trace node of the same index m (identical for unrotated faces); restated as is.
+// sH [le][6][5][N2] = Uhat, sNrm [le][6][4][N2] = normal, J_f at element-trace nodes.
+template <int n, int AX>
+__device__ __forceinline__ void prolong_axis_br2(const DevMesh& m, const Phys& ph, const Ops<n>& ops, const double* __restrict__ sF, const int* __restrict__ sTr,
+                                                 const int* __restrict__ sInfo, const double* __restrict__ sH, const double* __restrict__ sNrm,
+                                                 double* __restrict__ dst, int e0, int nLocal) {
+    using C = KCfg<n>;
+    constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, NT = C::NT, ROWS = NT / N2, NV = 15;
+    constexpr int STRIDE = AX == 0 ? 1 : (AX == 1 ? NP : n * NP);
+    constexpr int GSTRIDE = AX == 0 ? 1 : (AX == 1 ? n : N2);
+    constexpr int LF0 = AX == 0 ? 5 : (AX == 1 ? 0 : 2), LF1 = AX == 0 ? 3 : (AX == 1 ? 1 : 4);
+    const size_t fstride = (size_t)m.nFace * N2;
+    const int ab = threadIdx.x % N2, a = ab % n, b = ab / n;
+    const int base = AX == 0 ? (b * n + a) * NP : (AX == 1 ? (b * n) * NP + a : b * NP + a);
+    for (int row = threadIdx.x / N2; row < nLocal * NV; row += ROWS) {
+        const int vv = row % NV, le = row / NV, d = vv / 5, q = vv % 5;
+        const double* src = sF + (le * NV + vv) * NS + base;
+        double acc[2] = {0.0, 0.0};
+#pragma unroll
+        for (int l = 0; l < n; ++l) { const double sv = src[l * STRIDE]; acc[0] = acc[0] + sv * ops.v[l]; acc[1] = acc[1] + sv * ops.v[n + l]; }
+#pragma unroll
+        for (int end = 0; end < 2; ++end) {
+            const int lf = end ? LF1 : LF0;
+            const int off = sTr[(le * 6 + lf) * N2 + ab];
+            const int mm = off % N2, am = mm % n, bm = mm / n;
+            const double un = sH[((le * 6 + lf) * 5 + q) * N2 + mm] * sNrm[((le * 6 + lf) * 4 + d) * N2 + mm];
+            const double* iJ = m.invJ + (size_t)(e0 + le) * N3 + (AX == 0 ? (bm * n + am) * n : (AX == 1 ? (bm * n) * n + am : bm * n + am));
+            const double eu = ph.eta * un;
+            double t = acc[end];
+#pragma unroll
+            for (int l = 0; l < n; ++l) t = t - eu * (ops.b[end * n + l] * ops.v[end * n + l]) * iJ[l * GSTRIDE];
+            const int side = sInfo[le * 8 + lf] & 1;
+            dst[(size_t)(side * 5) * fstride + off + (size_t)((vv / 5) * 10 + vv % 5) * fstride] = t;
+        }
+    }
+}
+
 template <int n>
 __device__ __forceinline__ void load_face_tables(const DevMesh& m, int* sTr, int* sInfo, int e0, int nLocal) {
     for (int t = threadIdx.x; t < nLocal * 8; t += blockDim.x) sInfo[t] = m.elemInfo[(size_t)e0 * 8 + t];
@@ -194,14 +235,16 @@ __global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, const __gr
 // Shared memory: phase 1 {U [5][NS], uStar [6][5][N2], normal+J_f [6][4][N2]}; phase 2 reuses all of it for the
 // 15 gradient fields that are prolonged to the faces.
 // ---------------------------------------------------------------------------------------------------------
-template <int n, bool TMA>
+template <int n, bool TMA, bool VISC = false>
 struct GradSmem {
     using C = KCfg<n>;
+    static_assert(!(TMA && VISC), "the BR2 / IP variant uses plain loads");
     // non-TMA: phase 1 {U [5][NS], interface [6][9][N2]} aliased by phase 2 {grad [15][NS]}
     // TMA    : staged inputs {Q 5, Ja 9, 1/J 1} [15][EPB*N3] + interface [6][9][N2] + grad [15][NS] (no aliasing)
     static constexpr int phase1 = C::EPB * (5 * C::NS + 6 * 9 * C::N2);
     static constexpr int phase2 = C::EPB * 15 * C::NS;
-    static constexpr int fields = TMA ? C::EPB * (15 * C::N3 + 6 * 9 * C::N2 + 15 * C::NS) : (phase1 > phase2 ? phase1 : phase2);
+    // BR2 / IP: the interface data stays live until the prolongation, no aliasing
+    static constexpr int fields = TMA ? C::EPB * (15 * C::N3 + 6 * 9 * C::N2 + 15 * C::NS) : (VISC ? phase1 + phase2 : (phase1 > phase2 ? phase1 : phase2));
     static constexpr size_t bytes = sizeof(double) * (fields + C::N2 + 4 * n) + sizeof(int) * (TMA ? 2 : 1) * C::EPB * (6 * C::N2 + 8) + 32;
 };
 
@@ -220,13 +263,28 @@ __device__ __forceinline__ void grad_iface_load(const DevMesh& m, int e, int lf,
 #pragma unroll
     for (int q = 0; q < 5; ++q) { g.QL[q] = m.fQ[(size_t)q * fs + fo]; g.QR[q] = m.fQ[(size_t)(5 + q) * fs + fo]; }
 }
-template <int n>
+template <int n, bool VISC = false>
 __device__ __forceinline__ void grad_iface_store(const DevMesh& m, const Phys& ph, const GradIface& g, double* hh, double* nrm) {
     constexpr int N2 = n * n;
     const int side = g.info & 1, ftype = (g.info >> 4) & 3, zone = (g.info >> 8) - 1;
 #pragma unroll
     for (int d = 0; d < 3; ++d) nrm[d * N2] = g.nh[d];
     nrm[3 * N2] = g.Jf;
+    if (VISC) {
+        // BR2_/IP_GradientInterfaceSolution[Boundary] (EllipticBR2.f90:458-592, EllipticIP.f90:410-585):
+        // Uhat = 1/2 (UL - UR) J_f, the boundary state from StateForEqn (FlowState); n_d applied in the lift
+        double UL[5], UR[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { UL[q] = g.QL[q]; UR[q] = g.QR[q]; }
+        if (ftype == H3D_FACE_BOUNDARY) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { UL[q] = side ? g.QR[q] : g.QL[q]; UR[q] = UL[q]; }
+            bc_flow_state(ph, m.bcType[zone], m.bcParams + 16 * zone, g.nh, UR);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) hh[q * N2] = 0.5 * (UL[q] - UR[q]) * g.Jf;
+        return;
+    }
     if (ftype == H3D_FACE_BOUNDARY) {
         // BR1_ComputeBoundaryFlux: unStar = (u* - u_int) n_d J_f ; (u* - u_int) staged, n_d and J_f applied in the lift
         double Qi[5], us[5];
@@ -242,7 +300,7 @@ __device__ __forceinline__ void grad_iface_store(const DevMesh& m, const Phys& p
     }
 }
 
-template <int n, bool TMA>
+template <int n, bool TMA, bool VISC = false>
 __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh m, Phys ph, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
     constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
@@ -255,8 +313,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
     double* sU = TMA ? sIn : smem;                              // state: TMA [5][EPB][N3] (field-major), else [EPB][5][NS]
     double* sH = smem + (TMA ? 15 * TN3 : EPB * 5 * NS);        // [EPB][6][5][N2]
     double* sNrm = sH + EPB * 6 * 5 * N2;                       // [EPB][6][4][N2]
-    double* sG = TMA ? sNrm + EPB * 6 * 4 * N2 : smem;          // [EPB][15][NS]
-    double* sDT = smem + GradSmem<n, TMA>::fields;              // [n][n]
+    double* sG = (TMA || VISC) ? sNrm + EPB * 6 * 4 * N2 : smem;   // [EPB][15][NS]
+    double* sDT = smem + GradSmem<n, TMA, VISC>::fields;        // [n][n]
     double* sB = sDT + N2;
     double* sV = sB + 2 * n;
     constexpr int TABI = EPB * (6 * N2 + 8);                    // ints of one face-table set: trace offsets [EPB][6][N2] + info [EPB][8]
@@ -322,7 +380,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
             const int o = threadIdx.x + it * NT;
             if (o < nLocal * 6 * N2) {
                 const int ab = o % N2, lf = (o / N2) % 6, l2 = o / (6 * N2);
-                grad_iface_store<n>(m, ph, gi[it], sH + ((l2 * 6 + lf) * 5) * N2 + ab, sNrm + ((l2 * 6 + lf) * 4) * N2 + ab);
+                grad_iface_store<n, VISC>(m, ph, gi[it], sH + ((l2 * 6 + lf) * 5) * N2 + ab, sNrm + ((l2 * 6 + lf) * 4) * N2 + ab);
             }
         }
         if (!TMA) {
@@ -393,7 +451,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                         const double bb = sB[faceEnd(lf) * n + idxOf[lf]];
                         const double* H = sH + ((le * 6 + lf) * 5) * N2 + ab;
                         const double* Nn = sNrm + ((le * 6 + lf) * 4) * N2 + ab;
-                        const bool bnd = ((sInfo[le * 8 + lf] >> 4) & 3) == H3D_FACE_BOUNDARY;
+                        const bool bnd = !VISC && ((sInfo[le * 8 + lf] >> 4) & 3) == H3D_FACE_BOUNDARY;
                         const double Jfb = Nn[3 * N2];
                         const double n0 = Nn[0], n1 = Nn[N2], n2 = Nn[2 * N2];
 #pragma unroll
@@ -407,11 +465,26 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                         }
                     }
                     double* ox = m.Ux + (size_t)e * N3 + node; double* oy = m.Uy + (size_t)e * N3 + node; double* oz = m.Uz + (size_t)e * N3 + node;
+                    if (VISC) {
+                        // BR2 / IP prolong the LOCAL gradients (EllipticBR2.f90:160-190, EllipticIP.f90:215-262); the elements get
+                        // U -= faceInt * (1/J) (BR2, :332-338) or U += faceInt * (IPmethod * invJacobian) (IP, :396-402)
+                        const int p = C::pidx(node);
 #pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        // Euler with "compute gradients": local gradient only (base-class ComputeGradient, EllipticDiscretizationClass.f90:122-187)
-                        if (ph.ns) { g[r][q] = g[r][q] + fx[q] * iJ; g[r][5 + q] = g[r][5 + q] + fy[q] * iJ; g[r][10 + q] = g[r][10 + q] + fz[q] * iJ; }
-                        ox[q * es] = g[r][q]; oy[q * es] = g[r][5 + q]; oz[q * es] = g[r][10 + q];
+                        for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                        const double iJs = ph.ipVariant * iJ;
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            if (ph.viscous == H3D_VISCOUS_BR2) { g[r][q] = g[r][q] - fx[q] * iJ; g[r][5 + q] = g[r][5 + q] - fy[q] * iJ; g[r][10 + q] = g[r][10 + q] - fz[q] * iJ; }
+                            else { g[r][q] = g[r][q] + fx[q] * iJs; g[r][5 + q] = g[r][5 + q] + fy[q] * iJs; g[r][10 + q] = g[r][10 + q] + fz[q] * iJs; }
+                            ox[q * es] = g[r][q]; oy[q * es] = g[r][5 + q]; oz[q * es] = g[r][10 + q];
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            // Euler with "compute gradients": local gradient only (base-class ComputeGradient, EllipticDiscretizationClass.f90:122-187)
+                            if (ph.ns) { g[r][q] = g[r][q] + fx[q] * iJ; g[r][5 + q] = g[r][5 + q] + fy[q] * iJ; g[r][10 + q] = g[r][10 + q] + fz[q] * iJ; }
+                            ox[q * es] = g[r][q]; oy[q * es] = g[r][5 + q]; oz[q * es] = g[r][10 + q];
+                        }
                     }
                     if (TMA) {   // the gradient buffer does not alias the inputs: store right away
                         const int p = C::pidx(node);
@@ -425,7 +498,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
         const int next = tile + gridDim.x;
         if (TMA) {
             if (next < nTiles) issue(next);
-        } else {
+        } else if (!VISC) {
             if (active) {
 #pragma unroll
                 for (int r = 0; r < NPT; ++r) {
@@ -450,7 +523,13 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
             }
             havePrefetch = true;
         }
-        prolong_block<n, 15>(m, ops, sG, sTr, sInfo, m.fU, nLocal);
+        if (VISC && ph.viscous == H3D_VISCOUS_BR2) {
+            prolong_axis_br2<n, 0>(m, ph, ops, sG, sTr, sInfo, sH, sNrm, m.fU, e0, nLocal);
+            prolong_axis_br2<n, 1>(m, ph, ops, sG, sTr, sInfo, sH, sNrm, m.fU, e0, nLocal);
+            prolong_axis_br2<n, 2>(m, ph, ops, sG, sTr, sInfo, sH, sNrm, m.fU, e0, nLocal);
+        } else {
+            prolong_block<n, 15>(m, ops, sG, sTr, sInfo, m.fU, nLocal);
+        }
         __syncthreads();
     }
 }
@@ -516,6 +595,11 @@ __global__ void __launch_bounds__(128, EXT ? 1 : 4) k_riemann(DevMesh m, Phys ph
             for (int q = 0; q < 5; ++q) {
                 const double fx = 0.5 * (FL[q][0] + FR[q][0]), fy = 0.5 * (FL[q][1] + FR[q][1]), fz = 0.5 * (FL[q][2] + FR[q][2]);
                 visc[q] = fx * nh[0] + fy * nh[1] + fz * nh[2];
+            }
+            if (ph.viscous == H3D_VISCOUS_IP) {   // IP_RiemannSolver (EllipticIP.f90:704-761)
+                const double penalty = ph.penaltyNum / m.fH[f];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) visc[q] = visc[q] - penalty * ph.mu * (QL[q] - QR[q]);
             }
         }
         riemann_solver<EXT>(ph, QL, QR, nh, t1, t2, inv);
@@ -854,7 +938,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 
 // shared-memory footprints (bytes)
 template <int n> inline size_t smemProlong() { using C = KCfg<n>; return sizeof(double) * ((size_t)C::EPB * 5 * C::NS + 2 * n) + sizeof(int) * C::EPB * (6 * C::N2 + 8); }
-template <int n, bool TMA> inline size_t smemGradient() { return GradSmem<n, TMA>::bytes; }
+template <int n, bool TMA, bool VISC = false> inline size_t smemGradient() { return GradSmem<n, TMA, VISC>::bytes; }
 template <int n, bool TMA> inline size_t smemVolume(bool split, bool ns) { return VolSmem<n, TMA>::bytes(split, ns); }
 
 }  // namespace h3d

@@ -12,7 +12,10 @@ namespace h3d {
 
 struct Phys {   // by-value kernel parameter (a trimmed H3dPhysics)
     double gamma, gm1, gammaM2, mu, mu_to_kappa, S_div_Tref, T_renorm, lambdaStab, Cs;
+    double eta;          // BR2 eta (EllipticBR2.f90:80-91)
+    double penaltyNum;   // IP: 0.5 * sigma * (N+1) * (N+2), divided by the face's h in the kernel (EllipticIP.f90:678-687)
     int ns, riemann, averaging, les, wallModel;
+    int viscous, ipVariant;   // H3D_VISCOUS_*, IP variant -1 / 0 / 1
 };
 
 __device__ __forceinline__ double pow2(double x) { return x * x; }

@@ -50,7 +50,9 @@ def _worker(rank, world, port, kw, method, N, inherit, q):
 
 @pytest.mark.parametrize("kw,method,inherit", [(dict(flow="NS", mach=0.08, reynolds=1600.0), "metis", True),
                                                (dict(flow="Euler", mach=0.3, riemann="lax-friedrichs"), "block", True),
-                                               (dict(flow="NS", mach=0.08, reynolds=1600.0), "metis", False)])
+                                               (dict(flow="NS", mach=0.08, reynolds=1600.0), "metis", False),
+                                               (dict(flow="NS", mach=0.3, reynolds=200.0, viscous="BR2"), "metis", True),
+                                               (dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP"), "block", True)])
 def test_two_ranks_reproduce_the_single_domain_oracle(kw, method, inherit):
     import torch
     import torch.multiprocessing as mp

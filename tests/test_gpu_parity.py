@@ -61,6 +61,17 @@ CASES = [
     (2, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, riemann="roe-pike")),
     (2, 3, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli", riemann="low dissipation roe")),
     (2, 5, GAUSSLOBATTO, 0.1, True, dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="chandrasekar", riemann="matrix dissipation")),
+    # BR2 and interior-penalty viscous discretizations: K7 / K8 / K9 ingredients
+    (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="BR2")),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.08, reynolds=1600.0, viscous="BR2")),
+    (3, 1, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=100.0, viscous="BR2", penalty_parameter=3.0)),
+    (2, 9, GAUSS, 0.1, True, dict(flow="NS", mach=0.1, reynolds=500.0, viscous="BR2")),
+    (2, 4, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.08, reynolds=1600.0, inviscid="split-form", averaging="kennedy-gruber", riemann="standard roe", viscous="BR2")),
+    (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP")),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.08, reynolds=1600.0, viscous="IP")),
+    (2, 5, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=100.0, viscous="IP", ip_variant="NIPG", penalty_parameter=2.0)),
+    (2, 2, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=100.0, viscous="IP", ip_variant="IIPG")),
+    (3, 3, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.08, reynolds=1600.0, inviscid="split-form", averaging="chandrasekar", riemann="roe-pike", viscous="IP")),
 ]
 
 
@@ -84,6 +95,10 @@ BC_CASES = [
     (3, 3, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="pirozzoli", les="smagorinsky")),
     (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, les="smagorinsky", les_wall_model="linear")),
     (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, les="smagorinsky", les_wall_model="linear")),
+    (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="BR2")),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="BR2")),
+    (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP", les="smagorinsky")),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP")),
 ]
 
 
