@@ -35,6 +35,7 @@ struct h3d_context {
     double* dSnap = nullptr; double* hSnap = nullptr; size_t snapDoubles = 0; bool snapPending = false;   // asynchronous autosave
     cudaStream_t sCopy = nullptr; cudaEvent_t evSnap = nullptr, evSnapDone = nullptr;
     double* dStats = nullptr; int statVars = 0, statSamples = 0;   // running averages [var][e][node] (StatisticsMonitor)
+    bool genGrad = false;      // gradient variables other than State: general gradient / volume instantiations
     bool extPhysics = false;   // a Riemann solver / average outside the base set: kernels instantiated with EXT
     std::vector<double> hHatD, hD, hV, hB;   // host copies of the operators (kernel-parameter Ops<n>)
     int nElem = 0, nFace = 0, nSeq = 0;          // device order: [0,nSeq) interior elements, [nSeq,nElem) MPI elements
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_timestep(DevMesh m, Phys ph
 }
 
 // ScalarVolumeIntegral_Local (VolumeIntegrals.f90:167-286): all four integrals in one pass
-__global__ void __launch_bounds__(RED_THREADS) k_red_integrals(DevMesh m, size_t nn, int n, double* partial) {
+__global__ void __launch_bounds__(RED_THREADS) k_red_integrals(DevMesh m, Phys ph, size_t nn, int n, double* partial) {
     double v[4] = {0, 0, 0, 0};
     const int N2 = n * n, N3 = N2 * n;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (size_t)gridDim.x * blockDim.x) {
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_integrals(DevMesh m, size_t
         uvw = Q[3] / Q[0]; kr = kr + uvw * QD[3] - 0.5 * pow2(uvw) * QD[0];
         v[2] = v[2] + wJ * kr;
         double ux[3], uy[3], uz[3];
-        velocity_gradients(Q, gx, gy, gz, ux, uy, uz);
+        velocity_gradients_gv<true>(ph, Q, gx, gy, gz, ux, uy, uz);
         const double ens = pow2(uy[2] - uz[1]) + pow2(uz[0] - ux[2]) + pow2(ux[1] - uy[0]);
         v[3] = v[3] + wJ * ens;
     }
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_surface(DevMesh m, Phys ph,
             double gx[5], gy[5], gz[5], ux[3], uy[3], uz[3], mu, kappa;
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(size_t)(0 * 10 + q) * fs + t]; gy[q] = m.fU[(size_t)(1 * 10 + q) * fs + t]; gz[q] = m.fU[(size_t)(2 * 10 + q) * fs + t]; }
-            velocity_gradients(Q, gx, gy, gz, ux, uy, uz);
+            stress_velocity_gradients(ph, Q, gx, gy, gz, ux, uy, uz);
             laminar_mu_kappa(ph, Q, mu, kappa);
             const double divV = ux[0] + uy[1] + uz[2];
             double tau[3][3];
@@ -387,7 +388,7 @@ template <int n> int launchGradient(h3d_context* h, int e0, int e1, cudaStream_t
     if (e1 <= e0) return 0;
     using C = KCfg<n>;
     const int tiles = (e1 - e0 + C::EPB - 1) / C::EPB;
-    if (h->ph.viscous != H3D_VISCOUS_BR1) k_gradient<n, false, true><<<tiles, C::NT, smemGradient<n, false, true>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
+    if (h->ph.viscous != H3D_VISCOUS_BR1 || h->genGrad) k_gradient<n, false, true><<<tiles, C::NT, smemGradient<n, false, true>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
     else if (C::TMA_OK && h->useTma) k_gradient<n, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient<n, C::TMA_OK>, C::NT, smemGradient<n, C::TMA_OK>())), C::NT, smemGradient<n, C::TMA_OK>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
     else k_gradient<n, false><<<tiles, C::NT, smemGradient<n, false>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
     ++h->launches; return 0;
@@ -405,7 +406,10 @@ template <int n> int launchVolume(h3d_context* h, const RkArgs& rk, int e0, int 
     const int tiles = (e1 - e0 + C::EPB - 1) / C::EPB;
     const bool ns = h->ph.ns != 0;
     const bool tma = C::TMA_OK && h->useTma;
-    if (h->physics.inviscid == H3D_SPLIT_DG && h->extPhysics) {
+    if (h->genGrad) {
+        if (h->physics.inviscid == H3D_SPLIT_DG) k_volume<n, 2, false, true><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+        else k_volume<n, 0, false, true><<<tiles, C::NT, smemVolume<n, false>(false, true), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
+    } else if (h->physics.inviscid == H3D_SPLIT_DG && h->extPhysics) {
         k_volume<n, 2, false><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
     } else if (h->physics.inviscid == H3D_SPLIT_DG) {
         // the staged-input variant of SplitDG + Navier-Stokes does not fit 227 KB: plain loads there
@@ -427,6 +431,8 @@ template <int n> int setAttrs(h3d_context* h) {
     // SplitDG: the Navier-Stokes variant (29 padded fields) does not fit 227 KB at n = 10; the Euler variant (14 fields) does
     CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smemVolume<n, false>(true, true), SMEM_LIMIT)));
     CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smemVolume<n, false>(true, true), SMEM_LIMIT)));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, false>(false, true)));
+    CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smemVolume<n, false>(true, true), SMEM_LIMIT)));
     if (C::TMA_OK) {
         CTX_CHECK(cudaFuncSetAttribute(k_gradient<n, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient<n, C::TMA_OK>()));
         CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 0, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, C::TMA_OK>(false, true)));
@@ -651,8 +657,12 @@ int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
     q.ns = p->flowIsNavierStokes; q.riemann = p->riemann; q.averaging = p->averaging; q.les = p->les;
     if (p->viscous < H3D_VISCOUS_BR1 || p->viscous > H3D_VISCOUS_IP) { h->err = "Requested viscous discretization is not implemented."; return 1; }
     if (p->ipVariant < -1 || p->ipVariant > 1) { h->err = "Unknown selected IP variant."; return 1; }
+    if (p->gradientVariables < H3D_GRADVARS_STATE || p->gradientVariables > H3D_GRADVARS_ENERGY) { h->err = "Gradient variables are not currently implemented."; return 1; }
     q.viscous = p->flowIsNavierStokes ? p->viscous : H3D_VISCOUS_BR1; q.ipVariant = p->ipVariant; q.eta = p->penaltyParameter;
-    h->extPhysics = p->riemann > H3D_RIEMANN_CENTRAL || p->averaging > H3D_AVG_PIROZZOLI;
+    q.gradVars = p->flowIsNavierStokes ? p->gradientVariables : H3D_GRADVARS_STATE;
+    h->genGrad = q.gradVars != H3D_GRADVARS_STATE;
+    // anything outside the base set runs in the general instantiations so that it costs the headline kernels nothing
+    h->extPhysics = p->riemann > H3D_RIEMANN_CENTRAL || p->averaging > H3D_AVG_PIROZZOLI || h->genGrad;
     q.wallModel = (p->les != H3D_LES_NONE && p->les_wall_model == 1) ? 1 : 0;
     if (p->les_wall_model != 0 && p->les_wall_model != 1) { h->err = "LES wall model not recognized."; return 1; }
     h->havePhysics = true;
@@ -1080,7 +1090,7 @@ int h3d_volume_integral(h3d_handle h, int kind, double* val) {
     if (kind < 0 || kind > 3) { h->err = "unknown volume integral"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
-    k_red_integrals<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, nn, h->n, h->dPartial);
+    k_red_integrals<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, h->ph, nn, h->n, h->dPartial);
     k_red_final<4, 2><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
     h->launches += 2;
     if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 8, 4, ncclSum)) return 3;

@@ -270,26 +270,42 @@ __device__ __forceinline__ void grad_iface_store(const DevMesh& m, const Phys& p
 #pragma unroll
     for (int d = 0; d < 3; ++d) nrm[d * N2] = g.nh[d];
     nrm[3 * N2] = g.Jf;
-    if (VISC) {
-        // BR2_/IP_GradientInterfaceSolution[Boundary] (EllipticBR2.f90:458-592, EllipticIP.f90:410-585):
-        // Uhat = 1/2 (UL - UR) J_f, the boundary state from StateForEqn (FlowState); n_d applied in the lift
-        double UL[5], UR[5];
+    if (VISC) {   // the general variant: BR1 / BR2 / IP with any gradient variables
+        double Qi[5], Qe[5], UL[5], UR[5];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) { UL[q] = g.QL[q]; UR[q] = g.QR[q]; }
+        for (int q = 0; q < 5; ++q) { Qi[q] = g.QL[q]; Qe[q] = g.QR[q]; }
         if (ftype == H3D_FACE_BOUNDARY) {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) { UL[q] = side ? g.QR[q] : g.QL[q]; UR[q] = UL[q]; }
-            bc_flow_state(ph, m.bcType[zone], m.bcParams + 16 * zone, g.nh, UR);
+            for (int q = 0; q < 5; ++q) { Qi[q] = side ? g.QR[q] : g.QL[q]; Qe[q] = Qi[q]; }
         }
+        get_gradients(ph, Qi, UL);
+        if (ph.viscous == H3D_VISCOUS_BR1) {
+            if (ftype == H3D_FACE_BOUNDARY) {   // BR1_ComputeBoundaryFlux (EllipticBR1.f90:686-736)
 #pragma unroll
-        for (int q = 0; q < 5; ++q) hh[q * N2] = 0.5 * (UL[q] - UR[q]) * g.Jf;
+                for (int q = 0; q < 5; ++q) UR[q] = UL[q];
+                bc_grad_vars<true>(ph, m.bcType[zone], m.bcParams + 16 * zone, g.nh, Qi, UR);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) hh[q * N2] = (UR[q] - UL[q]);
+            } else {                            // BR1_ComputeElementInterfaceAverage (:571-627)
+                get_gradients(ph, Qe, UR);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) hh[q * N2] = 0.5 * (UR[q] - UL[q]) * g.Jf;
+            }
+        } else {
+            // BR2_/IP_GradientInterfaceSolution[Boundary] (EllipticBR2.f90:458-592, EllipticIP.f90:410-585):
+            // Uhat = 1/2 (UL - UR) J_f, the boundary state from StateForEqn (FlowState); n_d applied in the lift
+            if (ftype == H3D_FACE_BOUNDARY) bc_flow_state(ph, m.bcType[zone], m.bcParams + 16 * zone, g.nh, Qe);
+            get_gradients(ph, Qe, UR);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) hh[q * N2] = 0.5 * (UL[q] - UR[q]) * g.Jf;
+        }
         return;
     }
     if (ftype == H3D_FACE_BOUNDARY) {
         // BR1_ComputeBoundaryFlux: unStar = (u* - u_int) n_d J_f ; (u* - u_int) staged, n_d and J_f applied in the lift
         double Qi[5], us[5];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) Qi[q] = side ? g.QR[q] : g.QL[q];
+        for (int q = 0; q < 5; ++q) { Qi[q] = side ? g.QR[q] : g.QL[q]; us[q] = Qi[q]; }
         bc_grad_vars(ph, m.bcType[zone], m.bcParams + 16 * zone, g.nh, Qi, us);
 #pragma unroll
         for (int q = 0; q < 5; ++q) hh[q * N2] = (us[q] - Qi[q]);
@@ -390,8 +406,17 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                     const int node = tn + r * TPE;
                     if (node < N3) {
                         const double* q = m.Q + (size_t)e * N3 + node;
+                        if (VISC) {   // GetGradientValues at every node (HexElementClass.f90:466-470)
+                            double Qn[5], Un[5];
 #pragma unroll
-                        for (int c = 0; c < 5; ++c) sU[(le * 5 + c) * NS + C::pidx(node)] = q[c * es];
+                            for (int c = 0; c < 5; ++c) Qn[c] = q[c * es];
+                            get_gradients(ph, Qn, Un);
+#pragma unroll
+                            for (int c = 0; c < 5; ++c) sU[(le * 5 + c) * NS + C::pidx(node)] = Un[c];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 5; ++c) sU[(le * 5 + c) * NS + C::pidx(node)] = q[c * es];
+                        }
                     }
                 }
             }
@@ -451,7 +476,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                         const double bb = sB[faceEnd(lf) * n + idxOf[lf]];
                         const double* H = sH + ((le * 6 + lf) * 5) * N2 + ab;
                         const double* Nn = sNrm + ((le * 6 + lf) * 4) * N2 + ab;
-                        const bool bnd = !VISC && ((sInfo[le * 8 + lf] >> 4) & 3) == H3D_FACE_BOUNDARY;
+                        const bool bnd = (!VISC || ph.viscous == H3D_VISCOUS_BR1) && ((sInfo[le * 8 + lf] >> 4) & 3) == H3D_FACE_BOUNDARY;
                         const double Jfb = Nn[3 * N2];
                         const double n0 = Nn[0], n1 = Nn[N2], n2 = Nn[2 * N2];
 #pragma unroll
@@ -469,14 +494,21 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                         // BR2 / IP prolong the LOCAL gradients (EllipticBR2.f90:160-190, EllipticIP.f90:215-262); the elements get
                         // U -= faceInt * (1/J) (BR2, :332-338) or U += faceInt * (IPmethod * invJacobian) (IP, :396-402)
                         const int p = C::pidx(node);
+                        if (ph.viscous != H3D_VISCOUS_BR1) {
 #pragma unroll
-                        for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                            for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                        }
                         const double iJs = ph.ipVariant * iJ;
 #pragma unroll
                         for (int q = 0; q < 5; ++q) {
-                            if (ph.viscous == H3D_VISCOUS_BR2) { g[r][q] = g[r][q] - fx[q] * iJ; g[r][5 + q] = g[r][5 + q] - fy[q] * iJ; g[r][10 + q] = g[r][10 + q] - fz[q] * iJ; }
+                            if (ph.viscous == H3D_VISCOUS_BR1) { g[r][q] = g[r][q] + fx[q] * iJ; g[r][5 + q] = g[r][5 + q] + fy[q] * iJ; g[r][10 + q] = g[r][10 + q] + fz[q] * iJ; }
+                            else if (ph.viscous == H3D_VISCOUS_BR2) { g[r][q] = g[r][q] - fx[q] * iJ; g[r][5 + q] = g[r][5 + q] - fy[q] * iJ; g[r][10 + q] = g[r][10 + q] - fz[q] * iJ; }
                             else { g[r][q] = g[r][q] + fx[q] * iJs; g[r][5 + q] = g[r][5 + q] + fy[q] * iJs; g[r][10 + q] = g[r][10 + q] + fz[q] * iJs; }
                             ox[q * es] = g[r][q]; oy[q * es] = g[r][5 + q]; oz[q * es] = g[r][10 + q];
+                        }
+                        if (ph.viscous == H3D_VISCOUS_BR1) {   // BR1 prolongs the lifted gradients
+#pragma unroll
+                            for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
                         }
                     } else {
 #pragma unroll
@@ -569,8 +601,8 @@ __global__ void __launch_bounds__(128, EXT ? 1 : 4) k_riemann(DevMesh m, Phys ph
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + q) * fs]; }
             laminar_mu_kappa(ph, QL, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
-            viscous_flux(ph, QL, gx, gy, gz, mu, 0.0, kappa, F);
+            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            viscous_flux<EXT>(ph, QL, gx, gy, gz, mu, 0.0, kappa, F);
 #pragma unroll
             for (int q = 0; q < 5; ++q) { visc[q] = F[q][0] * nh[0] + F[q][1] * nh[1] + F[q][2] * nh[2]; }
             bc_neumann(btype, P, QL, visc);
@@ -584,13 +616,13 @@ __global__ void __launch_bounds__(128, EXT ? 1 : 4) k_riemann(DevMesh m, Phys ph
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + q) * fs]; }
             laminar_mu_kappa(ph, QL, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
-            viscous_flux(ph, QL, gx, gy, gz, mu, 0.0, kappa, FL);
+            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            viscous_flux<EXT>(ph, QL, gx, gy, gz, mu, 0.0, kappa, FL);
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + 5 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + 5 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + 5 + q) * fs]; }
             laminar_mu_kappa(ph, QR, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QR, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
-            viscous_flux(ph, QR, gx, gy, gz, mu, 0.0, kappa, FR);
+            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QR, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            viscous_flux<EXT>(ph, QR, gx, gy, gz, mu, 0.0, kappa, FR);
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 const double fx = 0.5 * (FL[q][0] + FR[q][0]), fy = 0.5 * (FL[q][1] + FR[q][1]), fz = 0.5 * (FL[q][2] + FR[q][2]);
@@ -631,7 +663,7 @@ struct VolSmem {
 };
 
 // MODE 0: StandardDG; 1: SplitDG with the standard / Kennedy-Gruber / Pirozzoli two-point fluxes; 2: SplitDG with all averages
-template <int n, int MODE, bool TMA>
+template <int n, int MODE, bool TMA, bool GV = false>
 __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m, Phys ph, RkArgs rk, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
     constexpr bool SPLIT = MODE != 0, EXT = MODE == 2;
@@ -785,8 +817,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                             for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[q * es + go]; gy[q] = m.Uy[q * es + go]; gz[q] = m.Uz[q * es + go]; }
                         }
                         laminar_mu_kappa(ph, Qk[r], mu, kappa);
-                        if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky(ph, m.lesDelta[e], ph.wallModel ? m.dWall[go] : 0.0, Qk[r], gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
-                        viscous_flux(ph, Qk[r], gx, gy, gz, mu, 0.0, kappa, F);
+                        if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky<GV>(ph, m.lesDelta[e], ph.wallModel ? m.dWall[go] : 0.0, Qk[r], gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+                        viscous_flux<GV>(ph, Qk[r], gx, gy, gz, mu, 0.0, kappa, F);
 #pragma unroll
                         for (int q = 0; q < 5; ++q)
 #pragma unroll

@@ -16,6 +16,7 @@ struct Phys {   // by-value kernel parameter (a trimmed H3dPhysics)
     double penaltyNum;   // IP: 0.5 * sigma * (N+1) * (N+2), divided by the face's h in the kernel (EllipticIP.f90:678-687)
     int ns, riemann, averaging, les, wallModel;
     int viscous, ipVariant;   // H3D_VISCOUS_*, IP variant -1 / 0 / 1
+    int gradVars;             // H3D_GRADVARS_*
 };
 
 __device__ __forceinline__ double pow2(double x) { return x * x; }
@@ -56,11 +57,72 @@ __device__ __forceinline__ void velocity_gradients(const double Q[5], const doub
     }
 }
 
+// GetGradients procedure pointer: NSGradientVariables_STATE / _ENTROPY / _ENERGY (VariableConversion_NS.f90:196-262)
+__device__ __forceinline__ void get_gradients(const Phys& ph, const double Q[5], double U[5]) {
+    if (ph.gradVars == H3D_GRADVARS_ENTROPY) {
+        const double invRho = 1.0 / Q[0];
+        const double rhoV2 = (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) * invRho;
+        const double p = ph.gm1 * (Q[4] - 0.5 * rhoV2);
+        const double invP = 1.0 / p;
+        const double invGm1 = 1.0 / ph.gm1;
+        const double U0 = (ph.gamma - (log(p) - ph.gamma * log(Q[0]))) * invGm1 - 0.5 * rhoV2 * invP;
+        const double U4 = -Q[0] * invP;
+        U[1] = Q[1] * invP; U[2] = Q[2] * invP; U[3] = Q[3] * invP; U[0] = U0; U[4] = U4;
+    } else if (ph.gradVars == H3D_GRADVARS_ENERGY) {
+        const double invRho = 1.0 / Q[0];
+        const double rhoV2 = (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) * invRho;
+        const double p = ph.gm1 * (Q[4] - 0.5 * rhoV2);
+        const double U4 = ph.gammaM2 * p * invRho, U0 = Q[0];
+        U[1] = Q[1] * invRho; U[2] = Q[2] * invRho; U[3] = Q[3] * invRho; U[0] = U0; U[4] = U4;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) U[q] = Q[q];
+    }
+}
+
+// getVelocityGradients procedure pointer (VariableConversion_NS.f90:373-428, set at :602-617); GV = false: State only
+template <bool GV>
+__device__ __forceinline__ void velocity_gradients_gv(const Phys& ph, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5],
+                                                      double ux[3], double uy[3], double uz[3]) {
+    if (GV && ph.gradVars == H3D_GRADVARS_ENERGY) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { ux[c] = Qx[1 + c]; uy[c] = Qy[1 + c]; uz[c] = Qz[1 + c]; }
+    } else if (GV && ph.gradVars == H3D_GRADVARS_ENTROPY) {   // as written in the reference (:421-426)
+        const double pDivRho = pressure(ph, Q) / Q[0];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double U = Q[1 + c] / Q[0];
+            ux[c] = pDivRho * Qx[1 + c] + U / pDivRho * Qx[4];
+            uy[c] = pDivRho * Qy[1 + c] + U / pDivRho * Qy[4];
+            uz[c] = pDivRho * Qz[1 + c] + U / pDivRho * Qz[4];
+        }
+    } else {
+        velocity_gradients(Q, Qx, Qy, Qz, ux, uy, uz);
+    }
+}
+
+// velocity gradients of getStressTensor (Physics_NS.f90:840-866): its entropy branch differs from the pointer's
+__device__ __forceinline__ void stress_velocity_gradients(const Phys& ph, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5],
+                                                          double ux[3], double uy[3], double uz[3]) {
+    if (ph.gradVars == H3D_GRADVARS_ENTROPY) {
+        const double invRho = 1.0 / Q[0];
+        const double pdr = ph.gm1 * invRho * (Q[4] - 0.5 * (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) * invRho);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double u = Q[1 + c] * invRho;
+            ux[c] = pdr * (Qx[1 + c] + u * Qx[4]); uy[c] = pdr * (Qy[1 + c] + u * Qy[4]); uz[c] = pdr * (Qz[1 + c] + u * Qz[4]);
+        }
+    } else {
+        velocity_gradients_gv<true>(ph, Q, Qx, Qy, Qz, ux, uy, uz);
+    }
+}
+
 // libs/physics/common/LESModels.f90:256-305 Smagorinsky: mu_t = rho LS^2 sqrt(2 S:S), S summed column by column;
 // LS = Cs delta, limited to 0.4 dWall by the linear wall model (LESModel_ComputeWallEffect, :189-203)
+template <bool GV = false>
 __device__ __forceinline__ double smagorinsky(const Phys& ph, double delta, double dWall, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5]) {
     double ux[3], uy[3], uz[3];
-    velocity_gradients(Q, Qx, Qy, Qz, ux, uy, uz);
+    velocity_gradients_gv<GV>(ph, Q, Qx, Qy, Qz, ux, uy, uz);
     // S(i,j) = 1/2 (column j of grad u + row contribution), built exactly as the reference does
     const double s00 = 0.5 * (ux[0] + ux[0]), s10 = 0.5 * (ux[1] + uy[0]), s20 = 0.5 * (ux[2] + uz[0]);
     const double s01 = 0.5 * (uy[0] + ux[1]), s11 = 0.5 * (uy[1] + uy[1]), s21 = 0.5 * (uy[2] + uz[1]);
@@ -75,23 +137,39 @@ __device__ __forceinline__ double smagorinsky(const Phys& ph, double delta, doub
     return Q[0] * pow2(LS) * normS;
 }
 
-// Physics_NS.f90:246-304 (ViscousFlux_STATE), beta = 0 kept as in the reference call sites
+// Physics_NS.f90:246-304 (ViscousFlux_STATE), :306-359 (_ENTROPY), :361-414 (_ENERGY); beta = 0 kept as in the reference
+// call sites.  GV = false: State gradient variables only (the headline instantiations); GV = true: run-time choice.
+template <bool GV = false>
 __device__ __forceinline__ void viscous_flux(const Phys& ph, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5],
                                              double mu, double beta, double kappa, double F[5][3]) {
     const double invRho = 1.0 / Q[0];
     const double u = Q[1] * invRho, v = Q[2] * invRho, w = Q[3] * invRho;
-    const double uDivRho[3] = {u * invRho, v * invRho, w * invRho};
-    double ux[3], uy[3], uz[3];
+    double ux[3], uy[3], uz[3], Tx, Ty, Tz;
+    if (GV && ph.gradVars == H3D_GRADVARS_ENTROPY) {
+        const double pdr = ph.gm1 * invRho * (Q[4] - 0.5 * (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) * invRho);
+        const double uu[3] = {u, v, w};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        ux[c] = invRho * Qx[1 + c] - uDivRho[c] * Qx[0];
-        uy[c] = invRho * Qy[1 + c] - uDivRho[c] * Qy[0];
-        uz[c] = invRho * Qz[1 + c] - uDivRho[c] * Qz[0];
+        for (int c = 0; c < 3; ++c) {
+            ux[c] = pdr * (Qx[1 + c] + uu[c] * Qx[4]); uy[c] = pdr * (Qy[1 + c] + uu[c] * Qy[4]); uz[c] = pdr * (Qz[1 + c] + uu[c] * Qz[4]);
+        }
+        Tx = ph.gammaM2 * pow2(pdr) * Qx[4]; Ty = ph.gammaM2 * pow2(pdr) * Qy[4]; Tz = ph.gammaM2 * pow2(pdr) * Qz[4];
+    } else if (GV && ph.gradVars == H3D_GRADVARS_ENERGY) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { ux[c] = Qx[1 + c]; uy[c] = Qy[1 + c]; uz[c] = Qz[1 + c]; }
+        Tx = Qx[4]; Ty = Qy[4]; Tz = Qz[4];
+    } else {
+        const double uDivRho[3] = {u * invRho, v * invRho, w * invRho};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            ux[c] = invRho * Qx[1 + c] - uDivRho[c] * Qx[0];
+            uy[c] = invRho * Qy[1 + c] - uDivRho[c] * Qy[0];
+            uz[c] = invRho * Qz[1 + c] - uDivRho[c] * Qz[0];
+        }
+        const double c0 = ph.gm1 * ph.gammaM2;
+        Tx = c0 * (invRho * Qx[4] - Q[4] * invRho * invRho * Qx[0] - u * ux[0] - v * ux[1] - w * ux[2]);
+        Ty = c0 * (invRho * Qy[4] - Q[4] * invRho * invRho * Qy[0] - u * uy[0] - v * uy[1] - w * uy[2]);
+        Tz = c0 * (invRho * Qz[4] - Q[4] * invRho * invRho * Qz[0] - u * uz[0] - v * uz[1] - w * uz[2]);
     }
-    const double c0 = ph.gm1 * ph.gammaM2;
-    const double Tx = c0 * (invRho * Qx[4] - Q[4] * invRho * invRho * Qx[0] - u * ux[0] - v * ux[1] - w * ux[2]);
-    const double Ty = c0 * (invRho * Qy[4] - Q[4] * invRho * invRho * Qy[0] - u * uy[0] - v * uy[1] - w * uy[2]);
-    const double Tz = c0 * (invRho * Qz[4] - Q[4] * invRho * invRho * Qz[0] - u * uz[0] - v * uz[1] - w * uz[2]);
     const double divV = ux[0] + uy[1] + uz[2];
     F[0][0] = 0.0;
     F[1][0] = mu * (2.0 * ux[0] - 2.0 / 3.0 * divV) + beta * divV;
@@ -682,18 +760,41 @@ __device__ __forceinline__ void bc_flow_state(const Phys& ph, int type, const do
 }
 
 // Boundary value of the gradient variables (FlowGradVars with STATE variables); us enters as the interior state
+// u_int = GetGradients(Q_int) on entry in us (BR1_ComputeBoundaryFlux, EllipticBR1.f90:703-722); GV = false: State variables
+template <bool GV = false>
 __device__ __forceinline__ void bc_grad_vars(const Phys& ph, int type, const double* P, const double nHat[3], const double Qi[5], double us[5]) {
+    double Qa[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) us[q] = Qi[q];
-    if (type == H3D_BC_NOSLIPWALL) {            // NoSlipWallBC.f90:298-337
+    for (int q = 0; q < 5; ++q) Qa[q] = Qi[q];
+    if (type == H3D_BC_NOSLIPWALL) {            // NoSlipWallBC.f90:298-337: U(IRHO) keeps the interior value
         const double invRho = 1.0 / Qi[0];
         const double e_int = invRho * (Qi[4] - 0.5 * invRho * (pow2(Qi[1]) + pow2(Qi[2]) + pow2(Qi[3])));
-        us[1] = Qi[0] * P[0]; us[2] = Qi[0] * P[1]; us[3] = Qi[0] * P[2];
-        us[4] = Qi[0] * ((1.0 - P[3]) * e_int + P[3] * P[6] + 0.5 * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]));
+        const double U1 = us[0];
+        Qa[1] = Qi[0] * P[0]; Qa[2] = Qi[0] * P[1]; Qa[3] = Qi[0] * P[2];
+        Qa[4] = Qi[0] * ((1.0 - P[3]) * e_int + P[3] * P[6] + 0.5 * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]));
+        if (GV) get_gradients(ph, Qa, us);
+        else {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) us[q] = Qa[q];
+        }
+        us[0] = U1;
     } else if (type == H3D_BC_FREESLIPWALL) {   // FreeSlipWallBC.f90:285-312
-        us[4] = Qi[4] + P[3] * (Qi[0] * P[6] + 0.5 * (pow2(Qi[1]) + pow2(Qi[2]) + pow2(Qi[3])) / Qi[0] - Qi[4]);
-    } else if (type == H3D_BC_INFLOW || type == H3D_BC_OUTFLOW) {   // GenericBoundaryConditionClass.f90:243-278
-        bc_flow_state(ph, type, P, nHat, us);
+        Qa[4] = Qi[4] + P[3] * (Qi[0] * P[6] + 0.5 * (pow2(Qi[1]) + pow2(Qi[2]) + pow2(Qi[3])) / Qi[0] - Qi[4]);
+        if (GV) get_gradients(ph, Qa, us);
+        else {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) us[q] = Qa[q];
+        }
+    } else if (type == H3D_BC_INFLOW || type == H3D_BC_OUTFLOW) {   // GenericBC_FlowGradVars (GenericBoundaryConditionClass.f90:243-278)
+        double Ua[5];
+        bc_flow_state(ph, type, P, nHat, Qa);
+        if (GV) get_gradients(ph, Qa, Ua);
+        else {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) Ua[q] = Qa[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) us[q] = 0.5 * (Ua[q] + us[q]);
     }
 }
 

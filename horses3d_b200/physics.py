@@ -13,6 +13,7 @@ AVERAGING = {"standard": 0, "kennedy-gruber": 1, "pirozzoli": 2, "ducros": 3, "m
 LES = {"none": 0, "smagorinsky": 1}
 VISCOUS = {"br1": 0, "br2": 1, "ip": 2}
 IP_VARIANT = {"sipg": -1, "iipg": 0, "nipg": 1}
+GRADVARS = {"state": 0, "entropy": 1, "energy": 2}
 
 INT_VOLUME, INT_KINETIC_ENERGY, INT_KINETIC_ENERGY_RATE, INT_ENSTROPHY = 0, 1, 2, 3
 RK3, RK5 = 3, 5
@@ -26,13 +27,13 @@ class H3dPhysics(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "gamma", "gammaMinus1", "Mach", "Re", "Pr", "mu", "kappa", "mu_to_kappa", "gammaM2",
         "S_div_Tref", "T_renorm", "lambdaStab", "smagorinsky_Cs", "Prt", "penaltyParameter")] + [(k, C.c_int) for k in (
-        "flowIsNavierStokes", "computeGradients", "inviscid", "riemann", "averaging", "les", "les_wall_model", "viscous", "ipVariant", "reserved")]
+        "flowIsNavierStokes", "computeGradients", "inviscid", "riemann", "averaging", "les", "les_wall_model", "viscous", "ipVariant", "gradientVariables")]
 
 
 def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="standard", riemann="roe",
                  averaging="standard", lambda_stab=1.0, compute_gradients=None, les="none", smagorinsky_cs=0.2, les_wall_model="none",
                  sutherland_temperature=None, reference_temperature=None, sutherland_ref_temperature=None,
-                 viscous="BR1", penalty_parameter=None, ip_variant="SIPG"):
+                 viscous="BR1", penalty_parameter=None, ip_variant="SIPG", gradient_variables="State"):
     p = H3dPhysics()
     gamma = 1.4
     gm1 = 1.4 - 1.0                                   # PhysicsStorage_NS.f90:120 (not 0.4)
@@ -65,6 +66,7 @@ def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="
     # "penalty parameter": BR2 eta defaults to 2 (EllipticBR2.f90:80-91), IP sigma to 1 (EllipticIP.f90:110-121)
     p.penaltyParameter = penalty_parameter if penalty_parameter is not None else {0: 0.0, 1: 2.0, 2: 1.0}[p.viscous]
     p.ipVariant = IP_VARIANT[ip_variant.lower()]
+    p.gradientVariables = GRADVARS[gradient_variables.lower()] if ns else 0       # SpatialDiscretization.f90:106-148, 190-193
     p.les = LES[les.lower()]
     p.smagorinsky_Cs = smagorinsky_cs
     p.les_wall_model = {"none": 0, "linear": 1}[les_wall_model.lower()]      # LESModels.f90:137-165

@@ -63,6 +63,11 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_VISCOUS_BR2 1      /* penaltyParameter = eta (default 2, EllipticBR2.f90:80-91)                          */
 #define H3D_VISCOUS_IP 2       /* penaltyParameter = sigma (default 1), ipVariant = SIPG -1 | IIPG 0 | NIPG 1 (EllipticIP.f90:26-28,110-150) */
 
+/* gradient variables (PhysicsStorage_NS.f90:105-108; SpatialDiscretization.f90:106-148; VariableConversion_NS.f90:196-262) */
+#define H3D_GRADVARS_STATE 0
+#define H3D_GRADVARS_ENTROPY 1
+#define H3D_GRADVARS_ENERGY 2
+
 /* face types (libs/mesh/MeshTypes.f90:21-25) */
 #define H3D_FACE_INTERIOR 1
 #define H3D_FACE_BOUNDARY 2
@@ -117,7 +122,7 @@ typedef struct H3dPhysics {
     int les_wall_model;      /* 0 = none (default), 1 = linear: LS = min(Cs*delta, 0.4*dWall), LESModels.f90:189-203 */
     int viscous;             /* H3D_VISCOUS_*                                   */
     int ipVariant;           /* IP: -1 SIPG (default), 0 IIPG, 1 NIPG           */
-    int reserved;
+    int gradientVariables;   /* H3D_GRADVARS_* ("gradient variables" key)       */
 } H3dPhysics;
 
 /* ---- life cycle ------------------------------------------------------------------------------

@@ -116,6 +116,93 @@ inline void ViscousFlux_STATE(const Oracle& o, const double* Q, const double* Q_
     F[IRHOE][IZ] = F[IRHOU][IZ] * u + F[IRHOV][IZ] * v + F[IRHOW][IZ] * w + kappa * nablaT[IZ];
 }
 
+// shared tail of the three ViscousFlux_* routines (Physics_NS.f90:283-303, 338-358, 393-413)
+inline void viscousFluxTail(const double* u, const double* u_x, const double* u_y, const double* u_z, const double* nablaT,
+                            double mu, double beta, double kappa, double F[NCONS][NDIM]) {
+    double divV = u_x[IX] + u_y[IY] + u_z[IZ];
+    F[IRHO][IX] = 0.0;
+    F[IRHOU][IX] = mu * (2.0 * u_x[IX] - 2.0 / 3.0 * divV) + beta * divV;
+    F[IRHOV][IX] = mu * (u_x[IY] + u_y[IX]);
+    F[IRHOW][IX] = mu * (u_x[IZ] + u_z[IX]);
+    F[IRHOE][IX] = F[IRHOU][IX] * u[IX] + F[IRHOV][IX] * u[IY] + F[IRHOW][IX] * u[IZ] + kappa * nablaT[IX];
+    F[IRHO][IY] = 0.0;
+    F[IRHOU][IY] = F[IRHOV][IX];
+    F[IRHOV][IY] = mu * (2.0 * u_y[IY] - 2.0 / 3.0 * divV) + beta * divV;
+    F[IRHOW][IY] = mu * (u_y[IZ] + u_z[IY]);
+    F[IRHOE][IY] = F[IRHOU][IY] * u[IX] + F[IRHOV][IY] * u[IY] + F[IRHOW][IY] * u[IZ] + kappa * nablaT[IY];
+    F[IRHO][IZ] = 0.0;
+    F[IRHOU][IZ] = F[IRHOW][IX];
+    F[IRHOV][IZ] = F[IRHOW][IY];
+    F[IRHOW][IZ] = mu * (2.0 * u_z[IZ] - 2.0 / 3.0 * divV) + beta * divV;
+    F[IRHOE][IZ] = F[IRHOU][IZ] * u[IX] + F[IRHOV][IZ] * u[IY] + F[IRHOW][IZ] * u[IZ] + kappa * nablaT[IZ];
+}
+
+// Physics_NS.f90:306-359 (gradients of the entropy variables)
+inline void ViscousFlux_ENTROPY(const Oracle& o, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z,
+                                double mu, double beta, double kappa, double F[NCONS][NDIM]) {
+    double invRho = 1.0 / Q[IRHO];
+    double p_div_rho = o.ph.gammaMinus1 * invRho * (Q[IRHOE] - 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) * invRho);
+    double u[3] = {Q[IRHOU] * invRho, Q[IRHOV] * invRho, Q[IRHOW] * invRho};
+    double u_x[3], u_y[3], u_z[3], nablaT[3];
+    for (int c = 0; c < 3; ++c) {
+        u_x[c] = p_div_rho * (Q_x[IRHOU + c] + u[c] * Q_x[IRHOE]);
+        u_y[c] = p_div_rho * (Q_y[IRHOU + c] + u[c] * Q_y[IRHOE]);
+        u_z[c] = p_div_rho * (Q_z[IRHOU + c] + u[c] * Q_z[IRHOE]);
+    }
+    nablaT[IX] = o.ph.gammaM2 * POW2(p_div_rho) * Q_x[IRHOE];
+    nablaT[IY] = o.ph.gammaM2 * POW2(p_div_rho) * Q_y[IRHOE];
+    nablaT[IZ] = o.ph.gammaM2 * POW2(p_div_rho) * Q_z[IRHOE];
+    viscousFluxTail(u, u_x, u_y, u_z, nablaT, mu, beta, kappa, F);
+}
+
+// Physics_NS.f90:361-414 (gradients of [rho, u, v, w, T])
+inline void ViscousFlux_ENERGY(const Oracle& o, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z,
+                               double mu, double beta, double kappa, double F[NCONS][NDIM]) {
+    (void)o;
+    double invRho = 1.0 / Q[IRHO];
+    double u[3] = {Q[IRHOU] * invRho, Q[IRHOV] * invRho, Q[IRHOW] * invRho};
+    double u_x[3] = {Q_x[IRHOU], Q_x[IRHOV], Q_x[IRHOW]}, u_y[3] = {Q_y[IRHOU], Q_y[IRHOV], Q_y[IRHOW]}, u_z[3] = {Q_z[IRHOU], Q_z[IRHOV], Q_z[IRHOW]};
+    double nablaT[3] = {Q_x[IRHOE], Q_y[IRHOE], Q_z[IRHOE]};
+    viscousFluxTail(u, u_x, u_y, u_z, nablaT, mu, beta, kappa, F);
+}
+
+// ViscousFlux procedure pointer (SpatialDiscretization.f90:106-148)
+inline void ViscousFlux(const Oracle& o, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z,
+                        double mu, double beta, double kappa, double F[NCONS][NDIM]) {
+    switch (o.ph.gradientVariables) {
+        case H3D_GRADVARS_ENTROPY: ViscousFlux_ENTROPY(o, Q, Q_x, Q_y, Q_z, mu, beta, kappa, F); break;
+        case H3D_GRADVARS_ENERGY: ViscousFlux_ENERGY(o, Q, Q_x, Q_y, Q_z, mu, beta, kappa, F); break;
+        default: ViscousFlux_STATE(o, Q, Q_x, Q_y, Q_z, mu, beta, kappa, F); break;
+    }
+}
+
+// GetGradients procedure pointer: NSGradientVariables_STATE / _ENTROPY / _ENERGY (VariableConversion_NS.f90:196-262)
+inline void GetGradients(const Oracle& o, const double* Q, double* U) {
+    switch (o.ph.gradientVariables) {
+        case H3D_GRADVARS_ENTROPY: {
+            double invRho = 1.0 / Q[IRHO];
+            double rhoV2 = (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) * invRho;
+            double p = o.ph.gammaMinus1 * (Q[IRHOE] - 0.5 * rhoV2);
+            double invP = 1.0 / p;
+            double invGammaMinus1 = 1.0 / o.ph.gammaMinus1;      // thermodynamics % invGammaMinus1 (FluidData_NS.f90)
+            double U0 = (o.ph.gamma - (std::log(p) - o.ph.gamma * std::log(Q[IRHO]))) * invGammaMinus1 - 0.5 * rhoV2 * invP;
+            double U4 = -Q[IRHO] * invP;
+            U[IRHOU] = Q[IRHOU] * invP; U[IRHOV] = Q[IRHOV] * invP; U[IRHOW] = Q[IRHOW] * invP;
+            U[IRHO] = U0; U[IRHOE] = U4;
+        } break;
+        case H3D_GRADVARS_ENERGY: {
+            double invRho = 1.0 / Q[IRHO];
+            double rhoV2 = (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) * invRho;
+            double p = o.ph.gammaMinus1 * (Q[IRHOE] - 0.5 * rhoV2);
+            double U4 = o.ph.gammaM2 * p * invRho;
+            double U0 = Q[IRHO];
+            U[IRHOU] = Q[IRHOU] * invRho; U[IRHOV] = Q[IRHOV] * invRho; U[IRHOW] = Q[IRHOW] * invRho;
+            U[IRHO] = U0; U[IRHOE] = U4;
+        } break;
+        default: for (int q = 0; q < 5; ++q) U[q] = Q[q]; break;
+    }
+}
+
 // VariableConversion_NS.f90:50-64, 99-115, 166-186, 147-164
 inline double Pressure(const Oracle& o, const double* Q) {
     return o.ph.gammaMinus1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
@@ -143,10 +230,29 @@ inline void getVelocityGradients_State(const double* Q, const double* Q_x, const
     }
 }
 
+// getVelocityGradients procedure pointer (VariableConversion_NS.f90:373-428, set at :602-617)
+inline void getVelocityGradients(const Oracle& o, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z, double* U_x, double* U_y, double* U_z) {
+    switch (o.ph.gradientVariables) {
+        case H3D_GRADVARS_ENERGY:
+            for (int c = 0; c < 3; ++c) { U_x[c] = Q_x[IRHOU + c]; U_y[c] = Q_y[IRHOU + c]; U_z[c] = Q_z[IRHOU + c]; }
+            break;
+        case H3D_GRADVARS_ENTROPY: {   // as written in the reference (:421-426): U / pDivRho multiplies the energy-variable gradient
+            double pDivRho = Pressure(o, Q) / Q[IRHO];
+            double U[3] = {Q[IRHOU] / Q[IRHO], Q[IRHOV] / Q[IRHO], Q[IRHOW] / Q[IRHO]};
+            for (int c = 0; c < 3; ++c) {
+                U_x[c] = pDivRho * Q_x[IRHOU + c] + U[c] / pDivRho * Q_x[IRHOE];
+                U_y[c] = pDivRho * Q_y[IRHOU + c] + U[c] / pDivRho * Q_y[IRHOE];
+                U_z[c] = pDivRho * Q_z[IRHOU + c] + U[c] / pDivRho * Q_z[IRHOE];
+            }
+        } break;
+        default: getVelocityGradients_State(Q, Q_x, Q_y, Q_z, U_x, U_y, U_z); break;
+    }
+}
+
 // LESModels.f90:256-305 (Smagorinsky_ComputeViscosity) with LESModel_ComputeWallEffect (:189-203); no wall model is the default (:162-165)
 inline double SmagorinskyViscosity(const Oracle& o, double delta, double dWall, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z) {
     double U_x[3], U_y[3], U_z[3], S[3][3];
-    getVelocityGradients_State(Q, Q_x, Q_y, Q_z, U_x, U_y, U_z);
+    getVelocityGradients(o, Q, Q_x, Q_y, Q_z, U_x, U_y, U_z);
     for (int i = 0; i < 3; ++i) { S[i][0] = U_x[i]; S[i][1] = U_y[i]; S[i][2] = U_z[i]; }
     for (int j = 0; j < 3; ++j) S[0][j] = S[0][j] + U_x[j];
     for (int j = 0; j < 3; ++j) S[1][j] = S[1][j] + U_y[j];
@@ -775,18 +881,25 @@ inline void BC_FlowGradVars(const Oracle& o, int zone, const double* nHat, const
         case H3D_BC_NOSLIPWALL: {   // NoSlipWallBC.f90:298-337 ; U(IRHO) keeps the incoming (interior) value
             double invRho = 1.0 / Q[IRHO];
             double e_int = invRho * (Q[IRHOE] - 0.5 * invRho * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])));
-            double U1 = U[IRHO];
-            U[IRHOU] = Q[IRHO] * P[0]; U[IRHOV] = Q[IRHO] * P[1]; U[IRHOW] = Q[IRHO] * P[2];
-            U[IRHOE] = Q[IRHO] * ((1.0 - P[3]) * e_int + P[3] * P[6] + 0.5 * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]));
+            double U1 = U[IRHO], Q_aux[5];
+            Q_aux[IRHO] = Q[IRHO];
+            Q_aux[IRHOU] = Q[IRHO] * P[0]; Q_aux[IRHOV] = Q[IRHO] * P[1]; Q_aux[IRHOW] = Q[IRHO] * P[2];
+            Q_aux[IRHOE] = Q[IRHO] * ((1.0 - P[3]) * e_int + P[3] * P[6] + 0.5 * (P[0] * P[0] + P[1] * P[1] + P[2] * P[2]));
+            GetGradients(o, Q_aux, U);
             U[IRHO] = U1;
         } break;
         case H3D_BC_FREESLIPWALL: { // FreeSlipWallBC.f90:285-312
-            U[IRHO] = Q[IRHO]; U[IRHOU] = Q[IRHOU]; U[IRHOV] = Q[IRHOV]; U[IRHOW] = Q[IRHOW];
-            U[IRHOE] = Q[IRHOE] + P[3] * (Q[IRHO] * P[6] + 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] - Q[IRHOE]);
+            double Q_aux[5];
+            Q_aux[IRHO] = Q[IRHO]; Q_aux[IRHOU] = Q[IRHOU]; Q_aux[IRHOV] = Q[IRHOV]; Q_aux[IRHOW] = Q[IRHOW];
+            Q_aux[IRHOE] = Q[IRHOE] + P[3] * (Q[IRHO] * P[6] + 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] - Q[IRHOE]);
+            GetGradients(o, Q_aux, U);
         } break;
         default: {                  // GenericBC_FlowGradVars (GenericBoundaryConditionClass.f90:243-278): gradient variables of the external state
-            for (int q = 0; q < 5; ++q) U[q] = Q[q];
-            BC_FlowState(o, zone, nHat, U);
+            double Q_aux[5], U_aux[5];
+            for (int q = 0; q < 5; ++q) Q_aux[q] = Q[q];
+            BC_FlowState(o, zone, nHat, Q_aux);
+            GetGradients(o, Q_aux, U_aux);
+            for (int q = 0; q < 5; ++q) U[q] = 0.5 * (U_aux[q] + U[q]);
         } break;
     }
 }
@@ -884,10 +997,13 @@ void computeGradientBR2IP(Oracle& o) {
     for (int f = 0; f < o.nFace; ++f) {
         for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
             const double Jf = o.fJac[ix.gnode(f, i, j)]; const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
-            const double* UL = &o.fQ[ix.fnode(f, 0, i, j) * 5];
+            const double* QL = &o.fQ[ix.fnode(f, 0, i, j) * 5];
+            double UL[5];
+            GetGradients(o, QL, UL);
             double* uL = &o.unStar[ix.fnode(f, 0, i, j) * 15];
             if (o.faceType[f] == H3D_FACE_INTERIOR) {
-                const double* UR = &o.fQ[ix.fnode(f, 1, i, j) * 5];
+                double UR[5];
+                GetGradients(o, &o.fQ[ix.fnode(f, 1, i, j) * 5], UR);
                 int ii, jj; leftIndexes2Right(i, j, N, N, o.faceRot[f], ii, jj);
                 double* uR = &o.unStar[ix.fnode(f, 1, ii, jj) * 15];
                 for (int q = 0; q < 5; ++q) {
@@ -895,11 +1011,12 @@ void computeGradientBR2IP(Oracle& o) {
                     for (int d = 0; d < 3; ++d) { double val = Uhat * nh[d]; uL[d * 5 + q] = val; uR[d * 5 + q] = 1 * val; }
                 }
             } else if (o.faceType[f] == H3D_FACE_BOUNDARY) {
-                double bvExt[5];
-                for (int q = 0; q < 5; ++q) bvExt[q] = UL[q];
+                double bvExt[5], UR[5];
+                for (int q = 0; q < 5; ++q) bvExt[q] = QL[q];
                 BC_FlowState(o, o.faceZone[f], nh, bvExt);
+                GetGradients(o, bvExt, UR);
                 for (int q = 0; q < 5; ++q) {
-                    double Uhat = 0.5 * (UL[q] - bvExt[q]) * Jf;
+                    double Uhat = 0.5 * (UL[q] - UR[q]) * Jf;
                     for (int d = 0; d < 3; ++d) uL[d * 5 + q] = Uhat * nh[d];
                 }
             }
@@ -959,11 +1076,15 @@ void computeGradient(Oracle& o, double time) {
     // HexElement_ComputeLocalGradient (HexElementClass.f90:427-531); U = Q (NSGradientVariables_STATE)
 #pragma omp parallel
     {
-        std::vector<double> Uxi((size_t)n3 * 5), Ueta((size_t)n3 * 5), Uzeta((size_t)n3 * 5);
+        std::vector<double> Uxi((size_t)n3 * 5), Ueta((size_t)n3 * 5), Uzeta((size_t)n3 * 5), Ugv((size_t)n3 * 5);
 #pragma omp for schedule(static)
         for (int e = 0; e < o.nElem; ++e) {
             std::fill(Uxi.begin(), Uxi.end(), 0.0); std::fill(Ueta.begin(), Ueta.end(), 0.0); std::fill(Uzeta.begin(), Uzeta.end(), 0.0);
             const double* U = &o.Q[ix.node(e, 0, 0, 0) * 5];
+            if (o.ph.gradientVariables != H3D_GRADVARS_STATE) {   // GetGradientValues at every node (:466-470)
+                for (int t = 0; t < n3; ++t) GetGradients(o, U + (size_t)t * 5, &Ugv[(size_t)t * 5]);
+                U = Ugv.data();
+            }
             auto L = [&](int i, int j, int k) { return (size_t)((k * n + j) * n + i) * 5; };
             for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int l = 0; l < n; ++l) for (int i = 0; i < n; ++i)
                 for (int q = 0; q < 5; ++q) Uxi[L(i, j, k) + q] = Uxi[L(i, j, k) + q] + U[L(l, j, k) + q] * o.D[i * n + l];
@@ -998,7 +1119,8 @@ void computeGradient(Oracle& o, double time) {
         const int N = o.N;
         if (o.faceType[f] == H3D_FACE_INTERIOR) {
             for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
-                const double* UL = &o.fQ[ix.fnode(f, 0, i, j) * 5]; const double* UR = &o.fQ[ix.fnode(f, 1, i, j) * 5];
+                double UL[5], UR[5];
+                GetGradients(o, &o.fQ[ix.fnode(f, 0, i, j) * 5], UL); GetGradients(o, &o.fQ[ix.fnode(f, 1, i, j) * 5], UR);
                 const double Jf = o.fJac[ix.gnode(f, i, j)]; const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
                 int ii, jj; leftIndexes2Right(i, j, N, N, o.faceRot[f], ii, jj);
                 double* uL = &o.unStar[ix.fnode(f, 0, i, j) * 15]; double* uR = &o.unStar[ix.fnode(f, 1, ii, jj) * 15];
@@ -1013,7 +1135,8 @@ void computeGradient(Oracle& o, double time) {
                 const double* Qi = &o.fQ[ix.fnode(f, 0, i, j) * 5];
                 const double Jf = o.fJac[ix.gnode(f, i, j)]; const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
                 double u_int[5], u_star[5];
-                for (int q = 0; q < 5; ++q) { u_int[q] = Qi[q]; u_star[q] = Qi[q]; }
+                GetGradients(o, Qi, u_int);
+                for (int q = 0; q < 5; ++q) u_star[q] = u_int[q];
                 BC_FlowGradVars(o, zone, nh, Qi, u_star);
                 double* uL = &o.unStar[ix.fnode(f, 0, i, j) * 15];
                 for (int q = 0; q < 5; ++q) for (int d = 0; d < 3; ++d) uL[d * 5 + q] = (u_star[q] - u_int[q]) * nh[d] * Jf;
@@ -1107,7 +1230,7 @@ void computeQDot(Oracle& o, double time) {
                     Finv[(l * 3 + 2) * 5 + q] = F[q][IX] * jz[IX] + F[q][IY] * jz[IY] + F[q][IZ] * jz[IZ];
                 }
                 if (NS) {
-                    ViscousFlux_STATE(o, &o.Q[5 * g], &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g], o.mu[2 * g], 0.0, o.mu[2 * g + 1], F);
+                    ViscousFlux(o, &o.Q[5 * g], &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g], o.mu[2 * g], 0.0, o.mu[2 * g + 1], F);
                     for (int q = 0; q < 5; ++q) {
                         Fvis[(l * 3 + 0) * 5 + q] = F[q][IX] * jx[IX] + F[q][IY] * jx[IY] + F[q][IZ] * jx[IZ];
                         Fvis[(l * 3 + 1) * 5 + q] = F[q][IX] * je[IX] + F[q][IY] * je[IY] + F[q][IZ] * je[IZ];
@@ -1174,8 +1297,8 @@ void computeQDot(Oracle& o, double time) {
                 double visc[5] = {0, 0, 0, 0, 0}, inv[5];
                 if (NS) {   // BR1_RiemannSolver (EllipticBR1.f90:816-868)
                     double fL[5][3], fR[5][3];
-                    ViscousFlux_STATE(o, &o.fQ[5 * gL], &o.fUx[5 * gL], &o.fUy[5 * gL], &o.fUz[5 * gL], o.fmu[2 * gL], 0.0, o.fmu[2 * gL + 1], fL);
-                    ViscousFlux_STATE(o, &o.fQ[5 * gR], &o.fUx[5 * gR], &o.fUy[5 * gR], &o.fUz[5 * gR], o.fmu[2 * gR], 0.0, o.fmu[2 * gR + 1], fR);
+                    ViscousFlux(o, &o.fQ[5 * gL], &o.fUx[5 * gL], &o.fUy[5 * gL], &o.fUz[5 * gL], o.fmu[2 * gL], 0.0, o.fmu[2 * gL + 1], fL);
+                    ViscousFlux(o, &o.fQ[5 * gR], &o.fUx[5 * gR], &o.fUy[5 * gR], &o.fUz[5 * gR], o.fmu[2 * gR], 0.0, o.fmu[2 * gR + 1], fR);
                     for (int q = 0; q < 5; ++q) {
                         double fx = 0.5 * (fL[q][IX] + fR[q][IX]), fy = 0.5 * (fL[q][IY] + fR[q][IY]), fz = 0.5 * (fL[q][IZ] + fR[q][IZ]);
                         visc[q] = fx * nh[IX] + fy * nh[IY] + fz * nh[IZ];
@@ -1205,7 +1328,7 @@ void computeQDot(Oracle& o, double time) {
                 double visc[5] = {0, 0, 0, 0, 0}, inv[5];
                 if (NS) {
                     double fv[5][3];
-                    ViscousFlux_STATE(o, &o.fQ[5 * gL], &o.fUx[5 * gL], &o.fUy[5 * gL], &o.fUz[5 * gL], o.fmu[2 * gL], 0.0, o.fmu[2 * gL + 1], fv);
+                    ViscousFlux(o, &o.fQ[5 * gL], &o.fUx[5 * gL], &o.fUy[5 * gL], &o.fUz[5 * gL], o.fmu[2 * gL], 0.0, o.fmu[2 * gL + 1], fv);
                     for (int q = 0; q < 5; ++q) { visc[q] = fv[q][IX] * nh[IX] + fv[q][IY] * nh[IY] + fv[q][IZ] * nh[IZ]; visc[q] = visc[q] + 0.0; }
                     BC_FlowNeumann(o, zone, &o.fQ[5 * gL], visc);
                 }
@@ -1484,7 +1607,17 @@ int orc_surface_integral(void* p, int zone, int kind, double* out) {
                 case H3D_SURF_PRESSURE_FORCE: { double pr = Pressure(o, Q); for (int d = 0; d < 3; ++d) fv[d] = fv[d] + (pr * nh[d]) * Jf * o.w[i] * o.w[j]; } break;
                 default: {
                     double U_x[3], U_y[3], U_z[3], tau[3][3], mu, kappa;
-                    getVelocityGradients_State(Q, &o.fUx[ix.fnode(f, 0, i, j) * 5], &o.fUy[ix.fnode(f, 0, i, j) * 5], &o.fUz[ix.fnode(f, 0, i, j) * 5], U_x, U_y, U_z);
+                    const double* gx = &o.fUx[ix.fnode(f, 0, i, j) * 5]; const double* gy = &o.fUy[ix.fnode(f, 0, i, j) * 5]; const double* gz = &o.fUz[ix.fnode(f, 0, i, j) * 5];
+                    if (o.ph.gradientVariables == H3D_GRADVARS_ENTROPY) {   // getStressTensor's own entropy branch (Physics_NS.f90:858-866)
+                        double invRho = 1.0 / Q[IRHO];
+                        double p_div_rho = o.ph.gammaMinus1 * invRho * (Q[IRHOE] - 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) * invRho);
+                        for (int c = 0; c < 3; ++c) {
+                            double u = Q[IRHOU + c] * invRho;
+                            U_x[c] = p_div_rho * (gx[IRHOU + c] + u * gx[IRHOE]); U_y[c] = p_div_rho * (gy[IRHOU + c] + u * gy[IRHOE]); U_z[c] = p_div_rho * (gz[IRHOU + c] + u * gz[IRHOE]);
+                        }
+                    } else {
+                        getVelocityGradients(o, Q, gx, gy, gz, U_x, U_y, U_z);   // STATE and ENERGY branches (:841-856) coincide with the pointer's
+                    }
                     get_laminar_mu_kappa(o, Q, mu, kappa);      // mu = mu0 * SutherlandsLaw(T)
                     double divV = U_x[IX] + U_y[IY] + U_z[IZ];
                     tau[IX][IX] = mu * (2.0 * U_x[IX] - 2.0 / 3.0 * divV);
@@ -1614,7 +1747,7 @@ int orc_volume_integral(void* p, int kind, double* out) {
                 } break;
                 case H3D_INT_ENSTROPHY: {
                     double U_x[3], U_y[3], U_z[3];
-                    getVelocityGradients_State(Q, &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g], U_x, U_y, U_z);
+                    getVelocityGradients(o, Q, &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g], U_x, U_y, U_z);
                     double KinEn = POW2(U_y[IZ] - U_z[IY]) + POW2(U_z[IX] - U_x[IZ]) + POW2(U_x[IY] - U_y[IX]);
                     loc = loc + wJ * KinEn;
                 } break;

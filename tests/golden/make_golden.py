@@ -24,6 +24,10 @@ CASES = {
     "tgv_ns_p7": dict(ne=2, N=7, nodes=GAUSS, bc=None, kw=dict(flow="NS", mach=0.08, reynolds=1600.0)),
     "tgv_euler_split_pirozzoli_p4": dict(ne=2, N=4, nodes=GAUSSLOBATTO, bc=None, kw=dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli")),
     "channel_ns_smagorinsky_p3": dict(ne=3, N=3, nodes=GAUSS, bc="channel", kw=dict(flow="NS", mach=0.3, reynolds=200.0, les="smagorinsky")),
+    "channel_ns_br2_p2": dict(ne=2, N=2, nodes=GAUSS, bc="channel", kw=dict(flow="NS", mach=0.3, reynolds=200.0, viscous="BR2")),
+    "channel_ns_ip_p2": dict(ne=2, N=2, nodes=GAUSS, bc="channel", kw=dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP")),
+    "channel_ns_entropy_split_p3": dict(ne=2, N=3, nodes=GAUSSLOBATTO, bc="channel", kw=dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="chandrasekar", riemann="central", gradient_variables="Entropy")),
+    "tgv_ns_energy_p4": dict(ne=2, N=4, nodes=GAUSS, bc=None, kw=dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Energy")),
 }
 
 

@@ -20,7 +20,8 @@ def check(api, name, exact):
         if exact:
             assert np.array_equal(got[k], ref[k]), (name, k)
         else:
-            assert np.abs(got[k] - ref[k]).max() <= 1e-13 * max(np.abs(ref[k]).max(), 1e-300), (name, k)
+            tol = 1e-12 if "entropy" in name else 1e-13     # log() differs in the last bit between CUDA and glibc
+            assert np.abs(got[k] - ref[k]).max() <= tol * max(np.abs(ref[k]).max(), 1e-300), (name, k)
 
 
 @pytest.mark.parametrize("name", list(CASES))

@@ -19,6 +19,14 @@ from parity import channel_state, get_mesh, perturbed_tgv, rel_err
 pytestmark = pytest.mark.gpu
 
 TOL_QDOT = 1.0e-13
+# Entropy gradient variables take log(p) and log(rho) at every node (VariableConversion_NS.f90:233): CUDA's log and glibc's
+# differ in the last bit for some arguments, and the derivative matrix amplifies that by O(N^2).  Those cases are held to the
+# north-star bound itself.
+TOL_ENTROPY = 1.0e-12
+
+
+def tol_of(kw):
+    return TOL_ENTROPY if kw.get("gradient_variables", "State").lower() == "entropy" else TOL_QDOT
 
 
 def run_pair(gpu_api_cls, mesh, phys, ic=perturbed_tgv):
@@ -72,6 +80,14 @@ CASES = [
     (2, 5, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=100.0, viscous="IP", ip_variant="NIPG", penalty_parameter=2.0)),
     (2, 2, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=100.0, viscous="IP", ip_variant="IIPG")),
     (3, 3, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.08, reynolds=1600.0, inviscid="split-form", averaging="chandrasekar", riemann="roe-pike", viscous="IP")),
+    # entropy / energy gradient variables: K10 / K11 ingredients
+    (2, 7, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=10.0, inviscid="split-form", averaging="pirozzoli", gradient_variables="Energy")),
+    (2, 7, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=10.0, inviscid="split-form", averaging="chandrasekar", riemann="matrix dissipation", gradient_variables="Entropy")),
+    (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Energy")),
+    (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Entropy")),
+    (2, 9, GAUSS, 0.1, True, dict(flow="NS", mach=0.1, reynolds=500.0, gradient_variables="Entropy")),
+    (2, 5, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="chandrasekar", riemann="central", gradient_variables="Entropy", viscous="BR2")),
+    (2, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Energy", viscous="IP")),
 ]
 
 
@@ -82,8 +98,8 @@ def test_time_derivative_matches_oracle(gpu_api_cls, ne, N, nodes, amp, shuffle,
     assert np.array_equal(o["Q"], g["Q"])                       # upload/download round trip is exact
     if kw.get("flow", "NS") != "Euler" or kw.get("compute_gradients"):
         for k in ("U_x", "U_y", "U_z"):
-            assert rel_err(g[k], o[k]) < TOL_QDOT, k
-    assert rel_err(g["QDot"], o["QDot"]) < TOL_QDOT
+            assert rel_err(g[k], o[k]) < tol_of(kw), k
+    assert rel_err(g["QDot"], o["QDot"]) < tol_of(kw)
     assert sg.api.kernel_launches() > 0
 
 
@@ -99,6 +115,10 @@ BC_CASES = [
     (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="BR2")),
     (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP", les="smagorinsky")),
     (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP")),
+    (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Energy")),
+    (3, 5, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="chandrasekar", riemann="central", gradient_variables="Entropy")),
+    (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Entropy", les="smagorinsky")),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Energy", les="smagorinsky", les_wall_model="linear")),
 ]
 
 
@@ -114,12 +134,12 @@ def test_boundary_conditions_and_les_match_oracle(gpu_api_cls, ne, N, nodes, amp
     (so, o), (sg, g) = run_pair(gpu_api_cls, mesh, phys, ic=lambda x: channel_state(x, phys))
     if kw.get("flow", "NS") != "Euler":
         for k in ("U_x", "U_y", "U_z"):
-            assert rel_err(g[k], o[k]) < TOL_QDOT, k
+            assert rel_err(g[k], o[k]) < tol_of(kw), k
     assert np.abs(o["QDot"]).max() > 1e-3
-    assert rel_err(g["QDot"], o["QDot"]) < TOL_QDOT
+    assert rel_err(g["QDot"], o["QDot"]) < tol_of(kw)
     for api in (so, sg):
         api.TakeRK3Step(0.0, 1e-3)
-    assert rel_err(sg.Q(), so.Q()) < TOL_QDOT
+    assert rel_err(sg.Q(), so.Q()) < tol_of(kw)
 
 
 def test_surface_integrals_match_oracle(gpu_api_cls):
