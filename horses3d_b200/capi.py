@@ -43,6 +43,7 @@ class Binding:
         "compute_time_derivative": [C.c_double],
         "rk_step": [C.c_int, C.c_double, C.c_double, C.c_int],
         "rk_stage": [C.c_int, C.c_int, C.c_double, C.c_double],
+        "enable_limiter": [C.c_int, C.c_double],
         "max_residuals": [_D],
         "max_timestep": [C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "volume_integral": [C.c_int, C.POINTER(C.c_double)],

@@ -35,6 +35,8 @@ struct h3d_context {
     double* dSnap = nullptr; double* hSnap = nullptr; size_t snapDoubles = 0; bool snapPending = false;   // asynchronous autosave
     cudaStream_t sCopy = nullptr; cudaEvent_t evSnap = nullptr, evSnapDone = nullptr;
     double* dStats = nullptr; int statVars = 0, statSamples = 0;   // running averages [var][e][node] (StatisticsMonitor)
+    bool limited = false; double limiterMin = 1e-13;   // LIMITED, LIMITER_MIN (ExplicitMethods.f90:28-29)
+    std::vector<double> hVolume; double* dVolume = nullptr;   // e % geom % volume in device order (stage limiter)
     bool genGrad = false;      // gradient variables other than State: general gradient / volume instantiations
     bool extPhysics = false;   // a Riemann solver / average outside the base set: kernels instantiated with EXT
     std::vector<double> hHatD, hD, hV, hB;   // host copies of the operators (kernel-parameter Ops<n>)
@@ -194,6 +196,75 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_timestep(DevMesh m, Phys ph
     blockReduce<2, 1>(v, partial + (size_t)blockIdx.x * 2);
 }
 
+// stage_limiter (ExplicitMethods.f90:1755-1847): one warp per element.  The element averages are sums in the reference's
+// node order (one lane per equation adds sequentially, which keeps them bit-identical); minima and the rescaling of the
+// nodes run over all lanes.
+__global__ void __launch_bounds__(256) k_stage_limiter(DevMesh m, Phys ph, int n, const double* __restrict__ volume, double limiterMin) {
+    const int e = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (e >= m.nElem) return;
+    const int N2 = n * n, N3 = N2 * n;
+    const size_t es = (size_t)m.nElem * N3, base = (size_t)e * N3;
+    const unsigned full = 0xffffffffu;
+    // averages
+    double acc = 0.0;
+    if (lane < 5) {
+        const double* q = m.Q + lane * es + base;
+        for (int node = 0; node < N3; ++node) {
+            const int i = node % n, j = (node / n) % n, k = node / N2;
+            acc = acc + q[node] * m.w[i] * m.w[j] * m.w[k] * m.J[base + node];
+        }
+        acc = acc / volume[e];
+    }
+    double Qavg[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) Qavg[q] = __shfl_sync(full, acc, q);
+    // density
+    double mn = 1.7976931348623157e308;
+    for (int node = lane; node < N3; node += 32) mn = fmin(mn, m.Q[base + node]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(full, mn, o));
+    if (Qavg[0] != mn) {
+        const double mm = fmin(limiterMin, Qavg[0]);
+        const double theta = fabs((Qavg[0] - mm) / (Qavg[0] - mn));
+        if (theta <= 1.0)
+            for (int node = lane; node < N3; node += 32) m.Q[base + node] = theta * (m.Q[base + node] - Qavg[0]) + Qavg[0];
+    }
+    __syncwarp();
+    // pressure: average in node order (lane 0), minimum over all lanes
+    double pavg = 0.0;
+    mn = 1.7976931348623157e308;
+    for (int node = lane; node < N3; node += 32) {
+        double Q[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) Q[q] = m.Q[q * es + base + node];
+        const double p = ph.gm1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
+        mn = fmin(mn, p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(full, mn, o));
+    if (lane == 0) {
+        for (int node = 0; node < N3; ++node) {
+            const int i = node % n, j = (node / n) % n, k = node / N2;
+            double Q[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) Q[q] = m.Q[q * es + base + node];
+            const double p = ph.gm1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
+            pavg = pavg + p * m.w[i] * m.w[j] * m.w[k] * m.J[base + node];
+        }
+        pavg = pavg / volume[e];
+    }
+    pavg = __shfl_sync(full, pavg, 0);
+    if (pavg != mn) {
+        const double mm = fmin(limiterMin, pavg);
+        const double theta = fabs((pavg - mm) / (pavg - mn));
+        if (theta <= 1.0)
+            for (int node = lane; node < N3; node += 32) {
+#pragma unroll
+                for (int q = 0; q < 5; ++q) m.Q[q * es + base + node] = theta * (m.Q[q * es + base + node] - Qavg[q]) + Qavg[q];
+            }
+    }
+}
+
 // ScalarVolumeIntegral_Local (VolumeIntegrals.f90:167-286): all four integrals in one pass
 __global__ void __launch_bounds__(RED_THREADS) k_red_integrals(DevMesh m, Phys ph, size_t nn, int n, double* partial) {
     double v[4] = {0, 0, 0, 0};
@@ -219,6 +290,53 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_integrals(DevMesh m, Phys p
         v[3] = v[3] + wJ * ens;
     }
     blockReduce<4, 2>(v, partial + (size_t)blockIdx.x * 4);
+}
+
+// The entropy-related and remaining scalar integrals (VolumeIntegrals.f90:288-386) in one pass:
+// v: 0 velocity, 1 entropy, 2 entropy rate, 3 internal energy, 4 entropy balance, 5 math entropy
+__global__ void __launch_bounds__(RED_THREADS) k_red_integrals2(DevMesh m, Phys ph, size_t nn, int n, int withGradients, double* partial) {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    const int N2 = n * n, N3 = N2 * n;
+    Phys phE = ph; phE.gradVars = H3D_GRADVARS_ENTROPY;      // NSGradientVariables_ENTROPY whatever the run's gradient variables
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (size_t)gridDim.x * blockDim.x) {
+        const int node = (int)(t % N3);
+        const int i = node % n, j = (node / n) % n, k = node / N2;
+        const double Jn = m.J[t];
+        const double wJ = m.w[i] * m.w[j] * m.w[k] * Jn;
+        double Q[5], QD[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { Q[q] = m.Q[(size_t)q * nn + t]; QD[q] = m.QDot[(size_t)q * nn + t]; }
+        v[0] = v[0] + m.w[i] * m.w[j] * m.w[k] * sqrt(pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) / Q[0] * Jn;
+        const double pr = pressure(ph, Q);
+        const double sp = log(pr) - ph.gamma * log(Q[0]);
+        v[1] = v[1] + wJ * sp;
+        const double ms = -Q[0] * sp / ph.gm1;
+        v[5] = v[5] + wJ * ms;
+        v[3] = v[3] + wJ * Q[4];
+        double EV[5];
+        get_gradients(phE, Q, EV);
+        double dot = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) dot = dot + QD[q] * EV[q];
+        v[2] = v[2] + wJ * dot;
+        if (withGradients) {
+            double gx[5], gy[5], gz[5], F[5][3], mu, kappa;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[(size_t)q * nn + t]; gy[q] = m.Uy[(size_t)q * nn + t]; gz[q] = m.Uz[(size_t)q * nn + t]; }
+            laminar_mu_kappa(ph, Q, mu, kappa);
+            if (ph.les == H3D_LES_SMAGORINSKY) {
+                const double mut = smagorinsky<true>(ph, m.lesDelta[t / N3], ph.wallModel ? m.dWall[t] : 0.0, Q, gx, gy, gz);
+                mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa;
+            }
+            viscous_flux<true>(ph, Q, gx, gy, gz, mu, 0.0, kappa, F);
+            double work = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) work = work + (F[q][0] * gx[q] + F[q][1] * gy[q] + F[q][2] * gz[q]);
+            dot = dot + work;
+        }
+        v[4] = v[4] + wJ * dot;
+    }
+    blockReduce<6, 2>(v, partial + (size_t)blockIdx.x * 6);
 }
 
 // ScalarSurfaceIntegral_Face / VectorSurfaceIntegral_Face (SurfaceIntegrals.f90:124-240, 347-445): every kind in one pass
@@ -814,6 +932,8 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
     {
         std::vector<double> de(nElem, 0.0), df(nFace, 0.0);
         if (volume) for (int ed = 0; ed < nElem; ++ed) de[ed] = std::pow(volume[h->permE[ed]] / (double)n3, 1.0 / 3.0);
+        h->hVolume.clear(); h->dVolume = nullptr; h->limited = false;
+        if (volume) { h->hVolume.resize(nElem); for (int ed = 0; ed < nElem; ++ed) h->hVolume[ed] = volume[h->permE[ed]]; }
         if (faceSurface) for (int fd = 0; fd < nFace; ++fd) df[fd] = std::sqrt(faceSurface[h->permF[fd]] / (double)n2);
         double *dde, *ddf;
         if (devAlloc(h, &dde, nElem) || devAlloc(h, &ddf, nFace)) return 2;
@@ -1016,8 +1136,13 @@ int rkStage(h3d_context* h, int scheme, int k, double dt) {
     const int store = (k == ns - 1 || h->storeQDotAlways) ? 1 : 0;
     if (scheme == H3D_SSPRK33 || scheme == H3D_SSPRK43) {
         const double *a = scheme == H3D_SSPRK33 ? SSP33_A : SSP43_A, *b = scheme == H3D_SSPRK33 ? SSP33_B : SSP43_B, *c = scheme == H3D_SSPRK33 ? SSP33_C : SSP43_C;
-        RkArgs rk{2, store, 1, a[k], c[k] * dt, b[k], k == 0 ? 1 : 0};
-        return residual(h, rk);
+        RkArgs rk{2, store, h->limited ? 0 : 1, a[k], c[k] * dt, b[k], k == 0 ? 1 : 0};
+        int rc = residual(h, rk);
+        if (rc || !h->limited) return rc;
+        // stage_limiter (ExplicitMethods.f90:1050-1052, 1177-1179); the traces are prolonged anew by the next residual
+        k_stage_limiter<<<(unsigned)(((size_t)h->nElem * 32 + 255) / 256), 256, 0, h->sCompute>>>(h->m, h->ph, h->n, h->dVolume, h->limiterMin);
+        ++h->launches; h->facesValid = false;
+        return 0;
     }
     const double *a = scheme == H3D_EULER ? RK_A1 : (scheme == H3D_RK3 ? RK_A3 : (scheme == H3D_RK5 ? RK_A5 : RK_A14));
     const double *c = scheme == H3D_EULER ? RK_C1 : (scheme == H3D_RK3 ? RK_C3 : (scheme == H3D_RK5 ? RK_C5 : RK_C14));
@@ -1034,6 +1159,19 @@ int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_ste
     if (!ns) { h->err = "unknown Runge-Kutta scheme"; return 1; }
     for (int k = 0; k < ns; ++k) { int rc = rkStage(h, scheme, k, dt); if (rc) return rc; }
     if (ctd_after_step) { RkArgs rk{0, 1, 0, 0.0, 0.0, 0.0, 0}; int rc = residual(h, rk); if (rc) return rc; }
+    return 0;
+}
+
+int h3d_enable_limiter(h3d_handle h, int enabled, double minimum) {
+    if (!h->haveMesh) { h->err = "h3d_enable_limiter: set the mesh first"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    if (enabled && !h->dVolume) {
+        if (h->hVolume.empty()) { h->err = "the limiter needs the element volumes (h3d_set_mesh: volume)"; return 1; }
+        if (devAlloc(h, &h->dVolume, h->hVolume.size())) return 2;
+        CTX_CHECK(cudaMemcpy(h->dVolume, h->hVolume.data(), h->hVolume.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->limited = enabled != 0;
+    if (minimum > 0.0) h->limiterMin = minimum;
     return 0;
 }
 
@@ -1087,9 +1225,21 @@ int h3d_max_timestep(h3d_handle h, double cfl, double dcfl, double* dt_conv, dou
 
 int h3d_volume_integral(h3d_handle h, int kind, double* val) {
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
-    if (kind < 0 || kind > 3) { h->err = "unknown volume integral"; return 1; }
+    if (kind < 0 || kind > H3D_INT_MATH_ENTROPY) { h->err = "unknown volume integral"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
+    if (kind > H3D_INT_ENSTROPHY) {
+        if (kind == H3D_INT_ENTROPY_BALANCE && !h->physics.flowIsNavierStokes) { h->err = "the entropy balance needs the viscous fluxes"; return 1; }
+        k_red_integrals2<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, h->ph, nn, h->n, h->physics.flowIsNavierStokes ? 1 : 0, h->dPartial);
+        k_red_final<6, 2><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
+        h->launches += 2;
+        if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 8, 6, ncclSum)) return 3;
+        CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 8, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
+        CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+        static const int slot[6] = {0, 1, 2, 3, 4, 5};   // VELOCITY, ENTROPY, ENTROPY_RATE, INTERNAL_ENERGY, ENTROPY_BALANCE, MATH_ENTROPY
+        *val = h->hScalars[slot[kind - H3D_INT_VELOCITY]];
+        return 0;
+    }
     k_red_integrals<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, h->ph, nn, h->n, h->dPartial);
     k_red_final<4, 2><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
     h->launches += 2;

@@ -231,6 +231,20 @@ class DGSem:
             "enstrophy": 0.5 * self.ScalarVolumeIntegral(P.INT_ENSTROPHY) / vol,
         }
 
+    def enable_limiter(self, enabled=True, minimum=0.0):
+        """Enable_limiter (ExplicitMethods.f90:1737-1752): positivity limiter after every SSPRK33 / SSPRK43 stage."""
+        self.api.call("enable_limiter", int(bool(enabled)), float(minimum))
+
+    VOLUME_MONITORS = {"kinetic energy": (P.INT_KINETIC_ENERGY, 1.0), "kinetic energy rate": (P.INT_KINETIC_ENERGY_RATE, 1.0),
+                       "enstrophy": (P.INT_ENSTROPHY, 0.5), "entropy": (P.INT_ENTROPY, 1.0), "entropy rate": (P.INT_ENTROPY_RATE, 1.0),
+                       "entropy balance": (P.INT_ENTROPY_BALANCE, 1.0), "math entropy": (P.INT_MATH_ENTROPY, 1.0),
+                       "internal energy": (P.INT_INTERNAL_ENERGY, 1.0), "mean velocity": (P.INT_VELOCITY, 1.0)}
+
+    def volume_monitor(self, variable):
+        """One volume monitor by its control-file name (VolumeMonitor_Update, VolumeMonitor.f90:297-330)."""
+        kind, factor = self.VOLUME_MONITORS[variable.lower()]
+        return factor * self.ScalarVolumeIntegral(kind) / self.ScalarVolumeIntegral(P.INT_VOLUME)
+
     def integrate(self, nsteps, cfl=None, dcfl=None, dt=None, t0=0.0, scheme="RK3", monitors=True, t_final=None, source=None,
                   ctd_after_step=False, keep="all"):
         """Explicit branch of TimeIntegrator_t%integrate: initial residual, then per step

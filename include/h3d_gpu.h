@@ -85,6 +85,12 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_INT_KINETIC_ENERGY 1
 #define H3D_INT_KINETIC_ENERGY_RATE 2
 #define H3D_INT_ENSTROPHY 3
+#define H3D_INT_VELOCITY 4          /* "mean velocity",  VolumeIntegrals.f90:288-296 */
+#define H3D_INT_ENTROPY 5           /* "entropy",        :298-309                    */
+#define H3D_INT_ENTROPY_RATE 6      /* "entropy rate",   :322-332                    */
+#define H3D_INT_INTERNAL_ENERGY 7   /* "internal energy",:374-386                    */
+#define H3D_INT_ENTROPY_BALANCE 8   /* "entropy balance",:335-370 (entropy rate minus viscous work, per gradient variables) */
+#define H3D_INT_MATH_ENTROPY 9      /* "math entropy",   :311-320                    */
 
 /* RK schemes (libs/timeintegrator/ExplicitMethods.f90:667,790) */
 #define H3D_EULER 1       /* TakeExplicitEulerStep, ExplicitMethods.f90:1232 */
@@ -210,6 +216,11 @@ int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_ste
  * SpatialDiscretization.f90:569-577): the adapter calls h3d_set_source between stages.  h3d_rk_step equals the
  * stages 0..ns-1 in a row. */
 int h3d_rk_stage(h3d_handle h, int scheme, int stage, double t, double dt);
+
+/* Enable_limiter + stage_limiter (ExplicitMethods.f90:1737-1847; keys "limit timestep" / "limiter minimum",
+ * TimeIntegrator.f90:303-311): after every SSPRK33 / SSPRK43 stage, density and then pressure of each element are scaled
+ * towards the element average so that they stay above min(minimum, average).  minimum <= 0 keeps the default 1e-13. */
+int h3d_enable_limiter(h3d_handle h, int enabled, double minimum);
 
 /* ---- per-step reductions (all globally reduced over ranks) ----------------------------------- */
 /* ComputeMaxResiduals (libs/discretization/DGSEMClass.f90:770-856) */

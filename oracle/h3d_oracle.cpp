@@ -57,6 +57,7 @@ struct Oracle {
     std::vector<double> fNormal, fT1, fT2, fJac, fX, fSurface;
     std::vector<double> dWall, fdWall;      // e % geom % dWall(i,j,k), f % geom % dWall(i,j)
     std::vector<double> fH;                 // f % geom % h
+    bool limited = false; double limiterMin = 1e-13;   // LIMITED, LIMITER_MIN (ExplicitMethods.f90:28-29)
     std::vector<double> stats; int statSamples = 0;
     std::vector<double> snapshot;   // e % storage % stats % data(var,i,j,k)
     int nZones = 0; std::vector<int> bcType; std::vector<double> bcParams;
@@ -177,8 +178,11 @@ inline void ViscousFlux(const Oracle& o, const double* Q, const double* Q_x, con
 }
 
 // GetGradients procedure pointer: NSGradientVariables_STATE / _ENTROPY / _ENERGY (VariableConversion_NS.f90:196-262)
-inline void GetGradients(const Oracle& o, const double* Q, double* U) {
-    switch (o.ph.gradientVariables) {
+inline void GetGradientsAs(const H3dPhysics& ph, int gradVars, const double* Q, double* U);
+inline void GetGradients(const Oracle& o, const double* Q, double* U) { GetGradientsAs(o.ph, o.ph.gradientVariables, Q, U); }
+inline void GetGradientsAs(const H3dPhysics& ph, int gradVars, const double* Q, double* U) {
+    struct { const H3dPhysics& ph; } o{ph};
+    switch (gradVars) {
         case H3D_GRADVARS_ENTROPY: {
             double invRho = 1.0 / Q[IRHO];
             double rhoV2 = (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) * invRho;
@@ -1488,6 +1492,44 @@ int rkStages(int scheme) {
         case H3D_SSPRK33: return 3; case H3D_SSPRK43: return 4; default: return 0;
     }
 }
+// stage_limiter (ExplicitMethods.f90:1755-1847)
+void stageLimiter(Oracle& o) {
+    const int n = o.n; Idx ix{n};
+    const double gm1 = o.ph.gammaMinus1, LIMITER_MIN = o.limiterMin;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o.nElem; ++e) {
+        double Qavg[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            size_t g = ix.node(e, i, j, k);
+            for (int q = 0; q < 5; ++q) Qavg[q] = Qavg[q] + o.Q[5 * g + q] * o.w[i] * o.w[j] * o.w[k] * o.jac[g];
+        }
+        for (int q = 0; q < 5; ++q) Qavg[q] = Qavg[q] / o.volume[e];
+        double minrho = std::numeric_limits<double>::max();
+        for (int t = 0; t < n * n * n; ++t) { double rho = o.Q[5 * (ix.node(e, 0, 0, 0) + t)]; if (rho < minrho) minrho = rho; }
+        if (Qavg[0] != minrho) {
+            double m = std::fmin(LIMITER_MIN, Qavg[0]);
+            double theta = std::fabs((Qavg[0] - m) / (Qavg[0] - minrho));
+            if (theta <= 1.0)
+                for (int t = 0; t < n * n * n; ++t) { double& r = o.Q[5 * (ix.node(e, 0, 0, 0) + t)]; r = theta * (r - Qavg[0]) + Qavg[0]; }
+        }
+        double minp = std::numeric_limits<double>::max(), pavg = 0.0;
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            size_t g = ix.node(e, i, j, k);
+            const double* Q = &o.Q[5 * g];
+            double p = gm1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
+            pavg = pavg + p * o.w[i] * o.w[j] * o.w[k] * o.jac[g];
+            if (p < minp) minp = p;
+        }
+        pavg = pavg / o.volume[e];
+        if (pavg != minp) {
+            double m = std::fmin(LIMITER_MIN, pavg);
+            double theta = std::fabs((pavg - m) / (pavg - minp));
+            if (theta <= 1.0)
+                for (int t = 0; t < n * n * n; ++t) { double* Q = &o.Q[5 * (ix.node(e, 0, 0, 0) + t)]; for (int q = 0; q < 5; ++q) Q[q] = theta * (Q[q] - Qavg[q]) + Qavg[q]; }
+        }
+    }
+}
+
 double rkStage(Oracle& o, int scheme, int k, double t, double dt) {   // loop bodies of the steppers
     if (scheme == H3D_SSPRK33 || scheme == H3D_SSPRK43) {
         const bool s3 = scheme == H3D_SSPRK33;
@@ -1498,6 +1540,7 @@ double rkStage(Oracle& o, int scheme, int k, double t, double dt) {   // loop bo
         const double ak = a[k], bk = b[k], ck = c[k];
 #pragma omp parallel for schedule(static)
         for (size_t q = 0; q < o.Q.size(); ++q) o.Q[q] = ak * o.G[q] + bk * o.Q[q] + ck * dt * o.QDot[q];
+        if (o.limited) stageLimiter(o);     // :1050-1052, :1177-1179
         return tk;
     }
     const double *a = scheme == H3D_EULER ? RK_A1 : scheme == H3D_RK3 ? RK_A3 : scheme == H3D_RK5 ? RK_A5 : RK_A14;
@@ -1519,6 +1562,13 @@ double rkStage(Oracle& o, int scheme, int k, double t, double dt) {   // loop bo
     return tk;
 }
 }  // namespace
+
+int orc_enable_limiter(void* p, int enabled, double minimum) {
+    Oracle& o = *(Oracle*)p;
+    if (enabled && o.volume.empty()) { o.err = "the limiter needs the element volumes"; return 1; }
+    o.limited = enabled != 0; if (minimum > 0.0) o.limiterMin = minimum;
+    return 0;
+}
 
 int orc_rk_step(void* p, int scheme, double t, double dt, int ctd_after_step) {
     Oracle& o = *(Oracle*)p;
@@ -1750,6 +1800,36 @@ int orc_volume_integral(void* p, int kind, double* out) {
                     getVelocityGradients(o, Q, &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g], U_x, U_y, U_z);
                     double KinEn = POW2(U_y[IZ] - U_z[IY]) + POW2(U_z[IX] - U_x[IZ]) + POW2(U_x[IY] - U_y[IX]);
                     loc = loc + wJ * KinEn;
+                } break;
+                case H3D_INT_VELOCITY:
+                    loc = loc + o.w[i] * o.w[j] * o.w[k] * std::sqrt(POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] * o.jac[g];
+                    break;
+                case H3D_INT_ENTROPY: {
+                    double pr = Pressure(o, Q);
+                    double sp = std::log(pr) - o.ph.gamma * std::log(Q[IRHO]);
+                    loc = loc + wJ * sp;
+                } break;
+                case H3D_INT_MATH_ENTROPY: {
+                    double pr = Pressure(o, Q);
+                    double sp = std::log(pr) - o.ph.gamma * std::log(Q[IRHO]);
+                    double ms = -Q[IRHO] * sp / o.ph.gammaMinus1;
+                    loc = loc + wJ * ms;
+                } break;
+                case H3D_INT_INTERNAL_ENERGY: loc = loc + wJ * Q[IRHOE]; break;
+                case H3D_INT_ENTROPY_RATE: case H3D_INT_ENTROPY_BALANCE: {
+                    // NSGradientVariables_ENTROPY whatever the gradient variables of the run (:326, :343, :353, :363)
+                    double EV[5];
+                    GetGradientsAs(o.ph, H3D_GRADVARS_ENTROPY, Q, EV);
+                    double dot = 0.0;
+                    for (int q = 0; q < 5; ++q) dot = dot + QD[q] * EV[q];
+                    if (kind == H3D_INT_ENTROPY_BALANCE) {
+                        double F[NCONS][NDIM], work = 0.0;
+                        const double* gx = &o.Ux[5 * g]; const double* gy = &o.Uy[5 * g]; const double* gz = &o.Uz[5 * g];
+                        ViscousFlux(o, Q, gx, gy, gz, o.mu[2 * g], 0.0, o.mu[2 * g + 1], F);
+                        for (int q = 0; q < 5; ++q) work = work + (F[q][IX] * gx[q] + F[q][IY] * gy[q] + F[q][IZ] * gz[q]);
+                        dot = dot + work;
+                    }
+                    loc = loc + wJ * dot;
                 } break;
                 default: o.err = "unknown volume integral"; return 1;
             }

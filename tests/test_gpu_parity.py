@@ -249,6 +249,40 @@ def test_rk_steps_and_monitors_match_oracle(gpu_api_cls, scheme):
     assert rel_err(Qg, Qo) < 1e-12
 
 
+@pytest.mark.parametrize("scheme", ["SSPRK33", "SSPRK43"])
+def test_stage_limiter_matches_oracle(gpu_api_cls, scheme):
+    """stage_limiter (ExplicitMethods.f90:1755-1847) after every SSPRK stage: same limited elements, same values."""
+    from test_oracle_pins import limiter_case
+    (so, Q1o), (sg, Q1g) = limiter_case(OracleApi(), scheme), limiter_case(gpu_api_cls(), scheme)
+    (_, Q1n) = limiter_case(gpu_api_cls(), scheme, limited=False)
+    assert np.abs(Q1g - Q1n).max() > 1e-3                          # the limiter acted on the device
+    assert rel_err(Q1g, Q1o) < TOL_QDOT
+    assert rel_err(sg.Q(), so.Q()) < TOL_QDOT
+
+
+@pytest.mark.parametrize("kw", [dict(flow="NS", mach=0.3, reynolds=200.0),
+                                dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Energy", les="smagorinsky"),
+                                dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Entropy", inviscid="split-form", averaging="chandrasekar", riemann="central"),
+                                dict(flow="Euler", mach=0.3)])
+def test_volume_monitors_match_oracle(gpu_api_cls, kw):
+    """Every ScalarVolumeIntegral kind behind the volume monitors (VolumeMonitor.f90:297-330), after an RK3 step on a curved
+    mesh with boundaries: volumes, kinetic energy (rate), enstrophy, entropy (rate, balance), math entropy, internal energy,
+    mean velocity."""
+    phys = make_physics(**kw)
+    nodes = GAUSSLOBATTO if kw.get("inviscid") == "split-form" else GAUSS
+    mesh = get_mesh(3, 4, nodes, 0.1, True, bc="channel", phys=phys)
+    vals = []
+    for api in (OracleApi(), gpu_api_cls()):
+        sem = DGSem(api, mesh, phys)
+        sem.set_initial_condition(lambda x: channel_state(x, phys))
+        sem.TakeRK3Step(0.0, 1.0e-3)
+        sem.ComputeTimeDerivative(1.0e-3)
+        names = [k for k in sem.VOLUME_MONITORS if phys.flowIsNavierStokes or k not in ("enstrophy", "entropy balance")]
+        vals.append(np.array([sem.volume_monitor(k) for k in names]))
+    assert np.abs(vals[0]).min() > 0.0
+    assert (np.abs(vals[1] - vals[0]) <= 1e-11 * np.abs(vals[0])).all(), (names, vals[0], vals[1] - vals[0])
+
+
 @pytest.mark.parametrize("scheme", ["RK3", "RK5"])
 def test_stagewise_step_with_time_dependent_source_matches_oracle(gpu_api_cls, scheme):
     """h3d_rk_stage with the source updated at every stage time (the K3 manufactured source of the reference's
