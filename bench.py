@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--averaging", default="standard")
     ap.add_argument("--riemann", default="roe")
     ap.add_argument("--nodes", default="gauss", choices=["gauss", "gauss-lobatto"])
+    ap.add_argument("--viscous", default="BR1", choices=["BR1", "BR2", "IP"])
+    ap.add_argument("--gradient-variables", default="State", choices=["State", "Entropy", "Energy"])
     return ap.parse_args()
 
 
@@ -134,9 +136,12 @@ def main_b200(args):
     import ctypes as C
     nodes = GAUSS if args.nodes == "gauss" else GAUSSLOBATTO
     euler = args.flow == "Euler"
-    phys_kw = dict(flow=args.flow, mach=0.08, reynolds=1600.0, riemann=args.riemann, inviscid=args.inviscid, averaging=args.averaging)
-    headline = (not euler) and args.inviscid == "standard" and args.riemann == "roe" and args.nodes == "gauss"
-    scheme = "%s, %s%s+%s" % (args.flow, "StandardDG" if args.inviscid == "standard" else "SplitDG-" + args.averaging, "" if euler else "+BR1", args.riemann)
+    phys_kw = dict(flow=args.flow, mach=0.08, reynolds=1600.0, riemann=args.riemann, inviscid=args.inviscid, averaging=args.averaging,
+                   viscous=args.viscous, gradient_variables=args.gradient_variables)
+    headline = (not euler) and args.inviscid == "standard" and args.riemann == "roe" and args.nodes == "gauss" and args.viscous == "BR1" \
+        and args.gradient_variables == "State"
+    scheme = "%s, %s%s+%s" % (args.flow, "StandardDG" if args.inviscid == "standard" else "SplitDG-" + args.averaging,
+                              "" if euler else "+" + args.viscous + ("" if args.gradient_variables == "State" else "(" + args.gradient_variables + " variables)"), args.riemann)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -329,6 +329,29 @@ def test_k1_taylor_green_on_gpu(gpu_api_cls):
     assert abs(rec["enstrophy"] - 3.7499683882517909E-01) < 1.0e-11
 
 
+def test_1000_rk3_steps_traces_match_oracle(gpu_api_cls):
+    """North-star acceptance: the L2 solution and kinetic-energy monitor traces after 1000 RK3 steps agree within 1e-10
+    relative (here between the device and the restated reference; curved periodic mesh, P=3, CFL-limited steps)."""
+    mesh = get_mesh(4, 3, GAUSS, 0.1, True)
+    phys = make_physics(flow="NS", mach=0.08, reynolds=1600.0)
+    recs = []
+    for api in (OracleApi(), gpu_api_cls()):
+        sem = DGSem(api, mesh, phys)
+        sem.set_initial_condition(taylor_green_ic)
+        recs.append((sem.integrate(1000, cfl=0.4, dcfl=0.4), sem.Q()))
+    (ro, Qo), (rg, Qg) = recs
+    assert len(ro) == len(rg) == 1001
+    t = np.array([[a["t"], b["t"]] for a, b in zip(ro, rg)])
+    ke = np.array([[a["kinetic energy"], b["kinetic energy"]] for a, b in zip(ro, rg)])
+    ens = np.array([[a["enstrophy"], b["enstrophy"]] for a, b in zip(ro, rg)])
+    assert np.abs(t[:, 0] - t[:, 1]).max() <= 1e-10 * t[-1, 0]
+    assert np.abs(ke[:, 0] - ke[:, 1]).max() <= 1e-10 * np.abs(ke[:, 0]).max()
+    assert np.abs(ens[:, 0] - ens[:, 1]).max() <= 1e-10 * np.abs(ens[:, 0]).max()
+    l2 = np.sqrt(((Qg - Qo) ** 2).sum() / (Qo ** 2).sum())
+    assert l2 <= 1e-10
+    assert abs(ke[-1, 0] - ke[0, 0]) > 1e-6 * ke[0, 0]              # the flow evolved
+
+
 def test_free_stream_preservation_full_size_p7(gpu_api_cls):
     """Size-independent property at the benchmark polynomial order: a uniform state has zero residual on a curved,
     randomly re-oriented mesh (metric identities + all eight face rotations)."""
