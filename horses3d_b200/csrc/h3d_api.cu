@@ -49,6 +49,9 @@ struct h3d_context {
     double* dSource = nullptr;
     double* dPartial = nullptr; double* hScalars = nullptr;  // reduction scratch (device) / pinned host
     bool facesValid = false;
+    // every change of Q / QDot / gradients bumps the version; the two volume-integral passes cache their results per version,
+    // so the monitors of one step (kinetic energy, its rate, enstrophy, ...) cost one pass over the fields, not one each
+    unsigned long long stateVersion = 1, intVersion[2] = {0, 0}; double intCache[2][6];
     int storeQDotAlways = 0;
     int useTma = 1;      // persistent element kernels with bulk-async prefetch where KCfg<n>::TMA_OK
     int numSMs = 148;
@@ -682,6 +685,7 @@ int residual(h3d_context* h, const RkArgs& rk) {
     }
     { ProfScope ps(h, 2, sc); if ((rc = doVolume(h, rk, 0, h->nElem, sc))) return rc; }
     h->facesValid = rk.prolong != 0;
+    ++h->stateVersion;
     CTX_CHECK(cudaGetLastError());
     return 0;
 }
@@ -944,7 +948,7 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
     }
     m.S = nullptr; m.bcType = nullptr; m.bcParams = nullptr; m.dWall = nullptr; m.fDWall = nullptr; m.fH = nullptr;
     for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_BOUNDARY && faceZone[f] < 0) { h->err = "boundary face without a zone"; return 1; }
-    h->haveMesh = true; h->facesValid = false;
+    h->haveMesh = true; h->facesValid = false; ++h->stateVersion;
     return 0;
 }
 
@@ -1018,7 +1022,7 @@ int h3d_upload_Q(h3d_handle h, const double* Q) {
     CTX_CHECK(cudaMemcpyAsync(h->staging, Q, 5 * ne * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
     k_aos_to_soa<<<148 * 8, 256, 0, h->sCompute>>>(h->staging, h->m.Q, h->dPermE, h->nElem, h->n * h->n * h->n, 5, 0);
     ++h->launches;
-    h->facesValid = false;
+    h->facesValid = false; ++h->stateVersion;
     CTX_CHECK(cudaGetLastError());
     return 0;
 }
@@ -1141,7 +1145,7 @@ int rkStage(h3d_context* h, int scheme, int k, double dt) {
         if (rc || !h->limited) return rc;
         // stage_limiter (ExplicitMethods.f90:1050-1052, 1177-1179); the traces are prolonged anew by the next residual
         k_stage_limiter<<<(unsigned)(((size_t)h->nElem * 32 + 255) / 256), 256, 0, h->sCompute>>>(h->m, h->ph, h->n, h->dVolume, h->limiterMin);
-        ++h->launches; h->facesValid = false;
+        ++h->launches; h->facesValid = false; ++h->stateVersion;
         return 0;
     }
     const double *a = scheme == H3D_EULER ? RK_A1 : (scheme == H3D_RK3 ? RK_A3 : (scheme == H3D_RK5 ? RK_A5 : RK_A14));
@@ -1230,23 +1234,28 @@ int h3d_volume_integral(h3d_handle h, int kind, double* val) {
     const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
     if (kind > H3D_INT_ENSTROPHY) {
         if (kind == H3D_INT_ENTROPY_BALANCE && !h->physics.flowIsNavierStokes) { h->err = "the entropy balance needs the viscous fluxes"; return 1; }
+        if (h->intVersion[1] == h->stateVersion) { *val = h->intCache[1][kind - H3D_INT_VELOCITY]; return 0; }
         k_red_integrals2<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, h->ph, nn, h->n, h->physics.flowIsNavierStokes ? 1 : 0, h->dPartial);
         k_red_final<6, 2><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
         h->launches += 2;
         if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 8, 6, ncclSum)) return 3;
         CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 8, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
         CTX_CHECK(cudaStreamSynchronize(h->sCompute));
-        static const int slot[6] = {0, 1, 2, 3, 4, 5};   // VELOCITY, ENTROPY, ENTROPY_RATE, INTERNAL_ENERGY, ENTROPY_BALANCE, MATH_ENTROPY
-        *val = h->hScalars[slot[kind - H3D_INT_VELOCITY]];
+        for (int q = 0; q < 6; ++q) h->intCache[1][q] = h->hScalars[q];   // VELOCITY, ENTROPY, ENTROPY_RATE, INTERNAL_ENERGY, ENTROPY_BALANCE, MATH_ENTROPY
+        h->intVersion[1] = h->stateVersion;
+        *val = h->intCache[1][kind - H3D_INT_VELOCITY];
         return 0;
     }
+    if (h->intVersion[0] == h->stateVersion) { *val = h->intCache[0][kind]; return 0; }
     k_red_integrals<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, h->ph, nn, h->n, h->dPartial);
     k_red_final<4, 2><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
     h->launches += 2;
     if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 8, 4, ncclSum)) return 3;
     CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
     CTX_CHECK(cudaStreamSynchronize(h->sCompute));
-    *val = h->hScalars[kind];
+    for (int q = 0; q < 4; ++q) h->intCache[0][q] = h->hScalars[q];
+    h->intVersion[0] = h->stateVersion;
+    *val = h->intCache[0][kind];
     return 0;
 }
 
