@@ -784,7 +784,8 @@ int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
     q.gradVars = p->flowIsNavierStokes ? p->gradientVariables : H3D_GRADVARS_STATE;
     h->genGrad = q.gradVars != H3D_GRADVARS_STATE;
     // anything outside the base set runs in the general instantiations so that it costs the headline kernels nothing
-    h->extPhysics = p->riemann > H3D_RIEMANN_CENTRAL || p->averaging > H3D_AVG_PIROZZOLI || h->genGrad;
+    h->extPhysics = p->riemann > H3D_RIEMANN_CENTRAL || p->averaging > H3D_AVG_PIROZZOLI || h->genGrad ||
+                    (p->inviscid == H3D_SPLIT_DG && p->averaging == H3D_AVG_STANDARD);   // k_volume<n,1> stages primitives: KG / Pirozzoli only
     q.wallModel = (p->les != H3D_LES_NONE && p->les_wall_model == 1) ? 1 : 0;
     if (p->les_wall_model != 0 && p->les_wall_model != 1) { h->err = "LES wall model not recognized."; return 1; }
     h->havePhysics = true;

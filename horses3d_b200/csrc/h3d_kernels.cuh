@@ -656,13 +656,13 @@ struct VolSmem {
     __host__ __device__ static constexpr int fluxFields(bool split, bool ns) { return split ? (ns ? 15 : 0) : 15; }
     __host__ __device__ static constexpr int stagedFields(bool ns) { return TMA ? (ns ? 29 : 14) + 6 : 0; }   // Q 5 [, Ux Uy Uz 15], Ja 9 | J 1, G 5
     __host__ __device__ static constexpr int fields(bool split, bool ns) {
-        return C::EPB * (stagedFields(ns) * C::N3 + (fluxFields(split, ns) + (split ? 14 : 0)) * C::NS + 30 * C::N2);
+        return C::EPB * (stagedFields(ns) * C::N3 + (fluxFields(split, ns) + (split ? 15 : 0)) * C::NS + 30 * C::N2);   // split: Q 5, Ja 9, X 1
     }
     // face tables: one copy, or two (prefetched by bulk copies) in the staged variant; 4 mbarriers
     static size_t bytes(bool split, bool ns) { return sizeof(double) * (fields(split, ns) + 2 * C::N2 + 2 * n) + sizeof(int) * (TMA ? 2 : 1) * C::EPB * (6 * C::N2 + 8) + 48; }
 };
 
-// MODE 0: StandardDG; 1: SplitDG with the standard / Kennedy-Gruber / Pirozzoli two-point fluxes; 2: SplitDG with all averages
+// MODE 0: StandardDG; 1: SplitDG with the Kennedy-Gruber / Pirozzoli two-point fluxes; 2: SplitDG with all averages
 template <int n, int MODE, bool TMA, bool GV = false>
 __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m, Phys ph, RkArgs rk, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
@@ -679,7 +679,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
     double* sF = sJG + (TMA ? 6 * TN3 : 0);              // [EPB][nFlux][NS]
     double* sQ = sF + EPB * nFlux * NS;                  // SPLIT: [EPB][5][NS]
     double* sJa = sQ + (SPLIT ? EPB * 5 * NS : 0);       // SPLIT: [EPB][9][NS]
-    double* sFs = sJa + (SPLIT ? EPB * 9 * NS : 0);      // [EPB][6][5][N2] fStar at element-trace nodes (signed)
+    double* sX = sJa + (SPLIT ? EPB * 9 * NS : 0);       // SPLIT: [EPB][NS] sixth per-node primitive (see two_point_flux_prim)
+    double* sFs = sX + (SPLIT ? EPB * NS : 0);           // [EPB][6][5][N2] fStar at element-trace nodes (signed)
     double* sHatDT = sFs + EPB * 6 * 5 * N2;             // [n][n]
     double* sSharpDT = sHatDT + N2;                      // [n][n]
     double* sB = sSharpDT + N2;                          // [2][n]
@@ -769,7 +770,11 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
             }
         }
         if (TMA) { mbar_wait(bar, parity); parity ^= 1; }
+        // SplitDG: per-node primitives are staged instead of the conserved state where the two-point flux allows it
+        // (MODE 1 serves Kennedy-Gruber and Pirozzoli only and always does; MODE 2 decides at run time)
+        const bool prim = (MODE == 1) || (EXT && prim_two_point_ok(ph.averaging));
         double Qk[NPT][5];                   // state of the thread's nodes (kept for the update)
+        double Pk[NPT][SPLIT ? 6 : 1];       // SplitDG: primitives of the thread's nodes
         double FinvD[NPT][SPLIT ? 15 : 1];   // SplitDG: consistent (diagonal) inviscid contravariant fluxes
         if (active) {
 #pragma unroll
@@ -798,9 +803,13 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 #pragma unroll
                         for (int d = 0; d < 3; ++d) Fc[q][d] = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
                     if (SPLIT) {
+                        if (prim) {
+                            node_primitives(ph, Qk[r], Pk[r]);
+                            sX[le * NS + p] = Pk[r][5];
+                        }
 #pragma unroll
                         for (int q = 0; q < 5; ++q) {
-                            sQ[(le * 5 + q) * NS + p] = Qk[r][q];
+                            sQ[(le * 5 + q) * NS + p] = prim ? Pk[r][q] : Qk[r][q];
 #pragma unroll
                             for (int d = 0; d < 3; ++d) FinvD[r][d * 5 + q] = Fc[q][d];
                         }
@@ -885,12 +894,17 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 #pragma unroll
                                     for (int q = 0; q < 5; ++q) fsvv[q] = FinvD[r][d * 5 + q];
                                 } else {
-                                    double Qo[5], jo[3];
+                                    double Qo[6], jo[3];
 #pragma unroll
                                     for (int q = 0; q < 5; ++q) Qo[q] = sQe[q * NS + other];
 #pragma unroll
                                     for (int c = 0; c < 3; ++c) jo[c] = sJe[(3 * d + c) * NS + other];
-                                    if (l > me) two_point_flux<EXT>(ph, Qk[r], Qo, jaMe, jo, fsvv); else two_point_flux<EXT>(ph, Qo, Qk[r], jo, jaMe, fsvv);
+                                    if (prim) {
+                                        Qo[5] = sX[le * NS + other];
+                                        if (l > me) two_point_flux_prim<EXT>(ph, Pk[r], Qo, jaMe, jo, fsvv); else two_point_flux_prim<EXT>(ph, Qo, Pk[r], jo, jaMe, fsvv);
+                                    } else {
+                                        if (l > me) two_point_flux<EXT>(ph, Qk[r], Qo, jaMe, jo, fsvv); else two_point_flux<EXT>(ph, Qo, Qk[r], jo, jaMe, fsvv);
+                                    }
                                 }
                                 const double sd = sSharpDT[l * n + me], hd = sHatDT[l * n + me];
                                 if (ns) {

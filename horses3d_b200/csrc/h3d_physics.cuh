@@ -722,6 +722,49 @@ __device__ __forceinline__ void two_point_flux(const Phys& ph, const double QL[5
     for (int q = 0; q < 5; ++q) fs[q] = f[q] * Ja[0] + g[q] * Ja[1] + h[q] * Ja[2];
 }
 
+// The same two-point fluxes from per-node primitives P = [rho, u, v, w, p, X] evaluated ONCE per node instead of once per
+// pair (the split-form volume term evaluates 3 N pairs per node): X = rho e / rho for Kennedy-Gruber, (rho e + p) / rho for
+// Pirozzoli, unused by the entropy-conserving and Chandrasekar fluxes.  Every per-node expression is the one the pairwise
+// routines above evaluate (invRho = 1 / rho; u = invRho * rho u; p = (gamma-1)(rho e - (rho u u + rho v v + rho w w)/2)), so the
+// result is bit-identical.  prim_two_point_ok() tells which averages take this path.
+__device__ __forceinline__ bool prim_two_point_ok(int averaging) {
+    return averaging == H3D_AVG_KENNEDYGRUBER || averaging == H3D_AVG_PIROZZOLI || averaging == H3D_AVG_ENTROPYCONS || averaging == H3D_AVG_CHANDRASEKAR;
+}
+__device__ __forceinline__ void node_primitives(const Phys& ph, const double Q[5], double P[6]) {
+    const double invRho = 1.0 / Q[0];
+    const double u = invRho * Q[1], v = invRho * Q[2], w = invRho * Q[3];
+    const double p = ph.gm1 * (Q[4] - 0.5 * (Q[1] * u + Q[2] * v + Q[3] * w));
+    P[0] = Q[0]; P[1] = u; P[2] = v; P[3] = w; P[4] = p;
+    P[5] = ph.averaging == H3D_AVG_KENNEDYGRUBER ? Q[4] * invRho : (Q[4] + p) * invRho;
+}
+template <bool EXT>
+__device__ __forceinline__ void two_point_flux_prim(const Phys& ph, const double PL[6], const double PR[6], const double JaL[3], const double JaR[3], double fs[5]) {
+    const double Ja[3] = {0.5 * (JaL[0] + JaR[0]), 0.5 * (JaL[1] + JaR[1]), 0.5 * (JaL[2] + JaR[2])};
+    double f[5], g[5], h[5];
+    if constexpr (EXT) {
+        if (ph.averaging > H3D_AVG_PIROZZOLI) {
+            double rho, u, v, w, p, hh;
+            if (ph.averaging == H3D_AVG_ENTROPYCONS) ec_mean_state(ph, true, PL[0], PR[0], PL[1], PR[1], PL[2], PR[2], PL[3], PR[3], PL[4], PR[4], rho, u, v, w, p, hh);
+            else chandrasekar_mean_state(ph, PL[0], PR[0], PL[1], PR[1], PL[2], PR[2], PL[3], PR[3], PL[4], PR[4], rho, u, v, w, p, hh);
+            f[0] = rho * u; f[1] = rho * u * u + p; f[2] = rho * u * v; f[3] = rho * u * w; f[4] = rho * u * hh;
+            g[0] = rho * v; g[1] = rho * v * u; g[2] = rho * v * v + p; g[3] = rho * v * w; g[4] = rho * v * hh;
+            h[0] = rho * w; h[1] = rho * w * u; h[2] = rho * w * v; h[3] = rho * w * w + p; h[4] = rho * w * hh;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) fs[q] = f[q] * Ja[0] + g[q] * Ja[1] + h[q] * Ja[2];
+            return;
+        }
+    }
+    const double rho = 0.5 * (PL[0] + PR[0]), u = 0.5 * (PL[1] + PR[1]), v = 0.5 * (PL[2] + PR[2]), w = 0.5 * (PL[3] + PR[3]), p = 0.5 * (PL[4] + PR[4]);
+    f[0] = rho * u; f[1] = rho * u * u + p; f[2] = rho * u * v; f[3] = rho * u * w;
+    g[0] = rho * v; g[1] = rho * v * u; g[2] = rho * v * v + p; g[3] = rho * v * w;
+    h[0] = rho * w; h[1] = rho * w * u; h[2] = rho * w * v; h[3] = rho * w * w + p;
+    const double X = 0.5 * (PL[5] + PR[5]);
+    if (ph.averaging == H3D_AVG_KENNEDYGRUBER) { f[4] = rho * u * X + p * u; g[4] = rho * v * X + p * v; h[4] = rho * w * X + p * w; }
+    else { f[4] = rho * u * X; g[4] = rho * v * X; h[4] = rho * w * X; }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) fs[q] = f[q] * Ja[0] + g[q] * Ja[1] + h[q] * Ja[2];
+}
+
 // ---- boundary conditions (libs/physics/common/{NoSlipWall,FreeSlipWall,Inflow,Outflow}BC.f90) -------------
 // Zone parameters P[16]: walls: P[0..2] vWall, P[3] wallType (0 adiabatic / 1 isothermal), P[4] Twall,
 // P[5] T_ref*gammaM2*(gamma-1) (no-slip) or T_ref*gammaM2 (free-slip), P[6] eWall; inflow: rho,u,v,w,p; outflow: P[4] pExt.

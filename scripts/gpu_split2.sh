@@ -1,0 +1,20 @@
+#!/bin/bash
+# parity tests + bench lines of the split-form configurations (BASELINE config 3) and the headline
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+run() { tag=$1; shift; timeout 300 python bench.py --steps 30 --warmup 3 --no-e2e --no-cpu-baseline "$@" > gpurun_out/sweep_$tag.json 2> gpurun_out/sweep_$tag.err; python - $tag <<'PY'
+import json,sys
+t=sys.argv[1]
+try:
+    d=json.loads(open('gpurun_out/sweep_%s.json'%t).read().strip().splitlines()[-1]); r=d['roofline']
+    print("%-22s %7.3f GDOF/s %7.2f ms/step  grad %.3f riem %.3f vol %.3f  stage-frac %.3f  ndof %d"%(t,d['value']/1e9,d['ms_per_step'],r['per_kernel_ms']['gradient'],r['per_kernel_ms']['riemann'],r['per_kernel_ms']['volume'],r['stage']['frac'],d['config']['ndof']))
+except Exception as ex: print(t,"FAILED",ex, open('gpurun_out/sweep_%s.err'%t).read()[-800:])
+PY
+}
+run c3_split_p3 --order 3 --ne 64 --flow Euler --inviscid split-form --averaging pirozzoli --nodes gauss-lobatto
+run c3_split_p5 --order 5 --ne 40 --flow Euler --inviscid split-form --averaging pirozzoli --nodes gauss-lobatto
+run c3_split_p7 --order 7 --ne 32 --flow Euler --inviscid split-form --averaging pirozzoli --nodes gauss-lobatto
+run c3_split_p9 --order 9 --ne 26 --flow Euler --inviscid split-form --averaging pirozzoli --nodes gauss-lobatto
+run ns_split_p7 --order 7 --ne 32 --inviscid split-form --averaging pirozzoli --nodes gauss-lobatto
+run euler_chandrasekar_p7 --order 7 --ne 32 --flow Euler --inviscid split-form --averaging chandrasekar --riemann central --nodes gauss-lobatto
+run headline "$@"
