@@ -670,6 +670,9 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
     constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;
     constexpr int FSI = (EPB * 30 * N2 + NT - 1) / NT;   // fStar items per thread
+    // MODE 1 stages HALVED primitives and metrics (two_point_flux_half).  Measured on B200, Euler Pirozzoli, volume kernel:
+    // n=4 3.17 -> 3.11 ms, n=8 3.54 -> 3.35 ms, n=10 5.90 -> 5.66 ms, but n=6 3.23 -> 3.47 ms (three runs each): not at n=6.
+    constexpr bool HALF = (MODE == 1) && (n != 6);
     extern __shared__ __align__(16) double smem[];
     const bool ns = ph.ns != 0;
     const int nStaged = TMA ? (ns ? 29 : 14) : 0;
@@ -805,6 +808,10 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                     if (SPLIT) {
                         if (prim) {
                             node_primitives(ph, Qk[r], Pk[r]);
+                            if (HALF) {   // halved primitives and metrics (two_point_flux_half)
+#pragma unroll
+                                for (int q = 0; q < 6; ++q) Pk[r][q] = 0.5 * Pk[r][q];
+                            }
                             sX[le * NS + p] = Pk[r][5];
                         }
 #pragma unroll
@@ -814,7 +821,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                             for (int d = 0; d < 3; ++d) FinvD[r][d * 5 + q] = Fc[q][d];
                         }
 #pragma unroll
-                        for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * NS + p] = ja[c];
+                        for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * NS + p] = HALF ? 0.5 * ja[c] : ja[c];
                     }
                     if (ns) {
                         double gx[5], gy[5], gz[5], mu, kappa;
@@ -901,7 +908,8 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                                     for (int c = 0; c < 3; ++c) jo[c] = sJe[(3 * d + c) * NS + other];
                                     if (prim) {
                                         Qo[5] = sX[le * NS + other];
-                                        if (l > me) two_point_flux_prim<EXT>(ph, Pk[r], Qo, jaMe, jo, fsvv); else two_point_flux_prim<EXT>(ph, Qo, Pk[r], jo, jaMe, fsvv);
+                                        if (HALF) { if (l > me) two_point_flux_half(ph, Pk[r], Qo, jaMe, jo, fsvv); else two_point_flux_half(ph, Qo, Pk[r], jo, jaMe, fsvv); }
+                                        else if (l > me) two_point_flux_prim<EXT>(ph, Pk[r], Qo, jaMe, jo, fsvv); else two_point_flux_prim<EXT>(ph, Qo, Pk[r], jo, jaMe, fsvv);
                                     } else {
                                         if (l > me) two_point_flux<EXT>(ph, Qk[r], Qo, jaMe, jo, fsvv); else two_point_flux<EXT>(ph, Qo, Qk[r], jo, jaMe, fsvv);
                                     }

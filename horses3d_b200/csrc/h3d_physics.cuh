@@ -765,6 +765,21 @@ __device__ __forceinline__ void two_point_flux_prim(const Phys& ph, const double
     for (int q = 0; q < 5; ++q) fs[q] = f[q] * Ja[0] + g[q] * Ja[1] + h[q] * Ja[2];
 }
 
+// Kennedy-Gruber / Pirozzoli from HALVED per-node primitives and metrics: 1/2 (a + b) = a/2 + b/2 exactly in binary floating
+// point (scaling by a power of two commutes with rounding), so the nine multiplications by 1/2 of every pair are done once per node.
+__device__ __forceinline__ void two_point_flux_half(const Phys& ph, const double hL[6], const double hR[6], const double hJaL[3], const double hJaR[3], double fs[5]) {
+    const double Ja[3] = {hJaL[0] + hJaR[0], hJaL[1] + hJaR[1], hJaL[2] + hJaR[2]};
+    const double rho = hL[0] + hR[0], u = hL[1] + hR[1], v = hL[2] + hR[2], w = hL[3] + hR[3], p = hL[4] + hR[4], X = hL[5] + hR[5];
+    double f[5], g[5], h[5];
+    f[0] = rho * u; f[1] = rho * u * u + p; f[2] = rho * u * v; f[3] = rho * u * w;
+    g[0] = rho * v; g[1] = rho * v * u; g[2] = rho * v * v + p; g[3] = rho * v * w;
+    h[0] = rho * w; h[1] = rho * w * u; h[2] = rho * w * v; h[3] = rho * w * w + p;
+    if (ph.averaging == H3D_AVG_KENNEDYGRUBER) { f[4] = rho * u * X + p * u; g[4] = rho * v * X + p * v; h[4] = rho * w * X + p * w; }
+    else { f[4] = rho * u * X; g[4] = rho * v * X; h[4] = rho * w * X; }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) fs[q] = f[q] * Ja[0] + g[q] * Ja[1] + h[q] * Ja[2];
+}
+
 // ---- boundary conditions (libs/physics/common/{NoSlipWall,FreeSlipWall,Inflow,Outflow}BC.f90) -------------
 // Zone parameters P[16]: walls: P[0..2] vWall, P[3] wallType (0 adiabatic / 1 isothermal), P[4] Twall,
 // P[5] T_ref*gammaM2*(gamma-1) (no-slip) or T_ref*gammaM2 (free-slip), P[6] eWall; inflow: rho,u,v,w,p; outflow: P[4] pExt.
