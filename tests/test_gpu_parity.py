@@ -329,6 +329,36 @@ def test_k1_taylor_green_on_gpu(gpu_api_cls):
     assert abs(rec["enstrophy"] - 3.7499683882517909E-01) < 1.0e-11
 
 
+@pytest.mark.parametrize("case", ["state", "energy", "entropy"])
+def test_k3_k10_convergence_p7_on_gpu(gpu_api_cls, case):
+    """The reference's Convergence, Convergence_energy and Convergence_entropy regressions (K3, K10: P=7, manufactured solution
+    with a time-dependent source, t = 1) run on the device path, on the generated equivalent of UnitCube4x4.mesh: residuals,
+    L2 state errors, L2 QDot errors and the entropy-rate monitor against the reference's values at its 1e-11 tolerance."""
+    from test_oracle_pins import convergence_case
+    kw, nodes, cfl, res, e0, q0, er = {
+        "state": (dict(), GAUSS, 0.5,
+                  [6.2801762330611588E-01, 1.8889640334957627E+00, 2.5256897695536247E+00, 4.4142472296503827E+00, 2.5163928650671146E+00],
+                  [1.0983475326313417E-06, 1.4788256133056976E-06, 4.5499827613507929E-07, 9.0819927730318800E-07, 2.5402026557722347E-06],
+                  [1.1342700947907287E-05, 1.1638989807665964E-05, 3.5549224957856481E-06, 1.0769093706709006E-05, 2.0658954210939997E-05],
+                  8.7517056213126665E-08),
+        "energy": (dict(inviscid="split-form", averaging="pirozzoli", riemann="roe", gradient_variables="Energy"), GAUSSLOBATTO, 1.0,
+                   [6.2838924111412731E-01, 1.8880402299553984E+00, 2.5257816906017094E+00, 4.4137338696617938E+00, 2.5153751482782658E+00],
+                   [6.7174769052792914E-06, 7.8936751849804373E-06, 2.8203611177044557E-06, 6.6884144365250127E-06, 1.4116624697295942E-05],
+                   [1.2370219075207763E-04, 1.1813999720732922E-04, 4.0653170754839378E-05, 1.2358578587070169E-04, 2.1723315094097264E-04],
+                   3.4973252274750376E-07),
+        "entropy": (dict(inviscid="split-form", averaging="chandrasekar", riemann="matrix dissipation", gradient_variables="Entropy"), GAUSSLOBATTO, 1.0,
+                    [6.2929844029491377E-01, 1.8894710750845625E+00, 2.5264755519384234E+00, 4.4146672499485859E+00, 2.5157533917446182E+00],
+                    [3.3102799903292017E-05, 3.6405407003671022E-05, 1.5957629488942332E-05, 3.4132613560424396E-05, 6.6811198249671421E-05],
+                    [9.2273153574772720E-04, 9.6259031804949867E-04, 3.8474183309141608E-04, 8.7717012428247660E-04, 1.6750805236722724E-03],
+                    3.6207469616966779E-07)}[case]
+    rec, err, qerr, sem = convergence_case(gpu_api_cls(), nodes=nodes, cfl=cfl, generated=True, **kw)
+    assert abs(rec["t"] - 1.0) < 1e-13
+    assert np.abs(rec["residuals"] - np.array(res)).max() < 1.0e-11
+    assert np.abs(err - np.array(e0)).max() < 1.0e-11
+    assert np.abs(qerr - np.array(q0)).max() < 1.0e-11
+    assert abs(sem.volume_monitor("entropy rate") - er) < 1.0e-11
+
+
 def test_1000_rk3_steps_traces_match_oracle(gpu_api_cls):
     """North-star acceptance: the L2 solution and kinetic-energy monitor traces after 1000 RK3 steps agree within 1e-10
     relative (here between the device and the restated reference; curved periodic mesh, P=3, CFL-limited steps)."""
