@@ -51,7 +51,7 @@ struct h3d_context {
     bool facesValid = false;
     // every change of Q / QDot / gradients bumps the version; the two volume-integral passes cache their results per version,
     // so the monitors of one step (kinetic energy, its rate, enstrophy, ...) cost one pass over the fields, not one each
-    unsigned long long stateVersion = 1, intVersion[2] = {0, 0}; double intCache[2][6];
+    unsigned long long stateVersion = 1, intVersion[3] = {0, 0, 0}; double intCache[3][6];
     int storeQDotAlways = 0;
     int useTma = 1;      // persistent element kernels with bulk-async prefetch where KCfg<n>::TMA_OK
     int numSMs = 148;
@@ -340,6 +340,61 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_integrals2(DevMesh m, Phys 
         v[4] = v[4] + wJ * dot;
     }
     blockReduce<6, 2>(v, partial + (size_t)blockIdx.x * 6);
+}
+
+// KINETIC_ENERGY_BALANCE (VolumeIntegrals.f90:220-265): kinetic energy rate + viscous work - pressure work + the de-aliasing
+// correction 1/2 u . (M grad p - grad(M p)) of GetPressureLocalGradient (:724-764); energy gradient variables.  The pressure
+// of the line nodes is recomputed from the state (a monitor, not a hot path).
+__global__ void __launch_bounds__(RED_THREADS) k_red_ke_balance(DevMesh m, Phys ph, size_t nn, int n, double* partial) {
+    double v[1] = {0};
+    const int N2 = n * n, N3 = N2 * n;
+    Phys phE = ph; phE.gradVars = H3D_GRADVARS_ENERGY;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (size_t)gridDim.x * blockDim.x) {
+        const int node = (int)(t % N3);
+        const size_t eb = t - node;
+        const int i = node % n, j = (node / n) % n, k = node / N2;
+        double Q[5], QD[5], gx[5], gy[5], gz[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { Q[q] = m.Q[(size_t)q * nn + t]; QD[q] = m.QDot[(size_t)q * nn + t]; gx[q] = m.Ux[(size_t)q * nn + t]; gy[q] = m.Uy[(size_t)q * nn + t]; gz[q] = m.Uz[(size_t)q * nn + t]; }
+        double gMp[3] = {0, 0, 0}, Mgp[3] = {0, 0, 0};
+        for (int ax = 0; ax < 3; ++ax) {
+            const int me = ax == 0 ? i : (ax == 1 ? j : k);
+            const int stride = ax == 0 ? 1 : (ax == 1 ? n : N2);
+            const size_t line0 = eb + node - (size_t)me * stride;
+            for (int l = 0; l < n; ++l) {
+                const size_t tl = line0 + (size_t)l * stride;
+                double Ql[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) Ql[q] = m.Q[(size_t)q * nn + tl];
+                const double pl = pressure(ph, Ql);
+                const double d = m.DT[l * n + me];       // D(me, l)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    gMp[c] = gMp[c] + pl * m.Ja[(size_t)(3 * ax + c) * nn + tl] * d;
+                    Mgp[c] = Mgp[c] + pl * m.Ja[(size_t)(3 * ax + c) * nn + t] * d;
+                }
+            }
+        }
+        const double inv_rho = 1.0 / Q[0];
+        double uvw = Q[1] * inv_rho;
+        double ke = uvw * QD[1] - 0.5 * pow2(uvw) * QD[0];
+        uvw = Q[2] * inv_rho; ke = ke + uvw * QD[2] - 0.5 * pow2(uvw) * QD[0];
+        uvw = Q[3] * inv_rho; ke = ke + uvw * QD[3] - 0.5 * pow2(uvw) * QD[0];
+        const double p3 = ph.gm1 * (Q[4] - 0.5 * (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) * inv_rho);
+        const double corr = 0.5 * (Q[1] * (Mgp[0] - gMp[0]) + Q[2] * (Mgp[1] - gMp[1]) + Q[3] * (Mgp[2] - gMp[2])) * inv_rho;
+        double F[5][3], mu, kappa;
+        laminar_mu_kappa(ph, Q, mu, kappa);
+        if (ph.les == H3D_LES_SMAGORINSKY) {
+            const double mut = smagorinsky<true>(ph, m.lesDelta[t / N3], ph.wallModel ? m.dWall[t] : 0.0, Q, gx, gy, gz);
+            mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa;
+        }
+        viscous_flux<true>(phE, Q, gx, gy, gz, mu, 0.0, kappa, F);
+        double work = 0.0;
+#pragma unroll
+        for (int q = 1; q < 4; ++q) work = work + (F[q][0] * gx[q] + F[q][1] * gy[q] + F[q][2] * gz[q]);
+        v[0] = v[0] + m.w[i] * m.w[j] * m.w[k] * (m.J[t] * (ke + work - p3 * (gx[1] + gy[2] + gz[3])) + corr);
+    }
+    blockReduce<1, 2>(v, partial + (size_t)blockIdx.x);
 }
 
 // ScalarSurfaceIntegral_Face / VectorSurfaceIntegral_Face (SurfaceIntegrals.f90:124-240, 347-445): every kind in one pass
@@ -1230,9 +1285,22 @@ int h3d_max_timestep(h3d_handle h, double cfl, double dcfl, double* dt_conv, dou
 
 int h3d_volume_integral(h3d_handle h, int kind, double* val) {
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
-    if (kind < 0 || kind > H3D_INT_MATH_ENTROPY) { h->err = "unknown volume integral"; return 1; }
+    if (kind < 0 || kind > H3D_INT_KINETIC_ENERGY_BALANCE) { h->err = "unknown volume integral"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
+    if (kind == H3D_INT_KINETIC_ENERGY_BALANCE) {
+        if (!h->physics.flowIsNavierStokes) { h->err = "the kinetic energy balance needs the viscous fluxes"; return 1; }
+        if (h->intVersion[2] == h->stateVersion) { *val = h->intCache[2][0]; return 0; }
+        k_red_ke_balance<<<RED_BLOCKS, RED_THREADS, 0, h->sCompute>>>(h->m, h->ph, nn, h->n, h->dPartial);
+        k_red_final<1, 2><<<1, 1024, 0, h->sCompute>>>(h->dPartial, RED_BLOCKS, h->dPartial + RED_BLOCKS * 8);
+        h->launches += 2;
+        if (reduceAcrossRanks(h, h->dPartial + RED_BLOCKS * 8, 1, ncclSum)) return 3;
+        CTX_CHECK(cudaMemcpyAsync(h->hScalars, h->dPartial + RED_BLOCKS * 8, sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
+        CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+        h->intCache[2][0] = h->hScalars[0]; h->intVersion[2] = h->stateVersion;
+        *val = h->intCache[2][0];
+        return 0;
+    }
     if (kind > H3D_INT_ENSTROPHY) {
         if (kind == H3D_INT_ENTROPY_BALANCE && !h->physics.flowIsNavierStokes) { h->err = "the entropy balance needs the viscous fluxes"; return 1; }
         if (h->intVersion[1] == h->stateVersion) { *val = h->intCache[1][kind - H3D_INT_VELOCITY]; return 0; }

@@ -238,7 +238,8 @@ class DGSem:
     VOLUME_MONITORS = {"kinetic energy": (P.INT_KINETIC_ENERGY, 1.0), "kinetic energy rate": (P.INT_KINETIC_ENERGY_RATE, 1.0),
                        "enstrophy": (P.INT_ENSTROPHY, 0.5), "entropy": (P.INT_ENTROPY, 1.0), "entropy rate": (P.INT_ENTROPY_RATE, 1.0),
                        "entropy balance": (P.INT_ENTROPY_BALANCE, 1.0), "math entropy": (P.INT_MATH_ENTROPY, 1.0),
-                       "internal energy": (P.INT_INTERNAL_ENERGY, 1.0), "mean velocity": (P.INT_VELOCITY, 1.0)}
+                       "internal energy": (P.INT_INTERNAL_ENERGY, 1.0), "mean velocity": (P.INT_VELOCITY, 1.0),
+                       "kinetic energy balance": (P.INT_KINETIC_ENERGY_BALANCE, 1.0)}
 
     def volume_monitor(self, variable):
         """One volume monitor by its control-file name (VolumeMonitor_Update, VolumeMonitor.f90:297-330)."""

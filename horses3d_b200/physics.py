@@ -17,6 +17,7 @@ GRADVARS = {"state": 0, "entropy": 1, "energy": 2}
 
 INT_VOLUME, INT_KINETIC_ENERGY, INT_KINETIC_ENERGY_RATE, INT_ENSTROPHY = 0, 1, 2, 3
 INT_VELOCITY, INT_ENTROPY, INT_ENTROPY_RATE, INT_INTERNAL_ENERGY, INT_ENTROPY_BALANCE, INT_MATH_ENTROPY = 4, 5, 6, 7, 8, 9
+INT_KINETIC_ENERGY_BALANCE = 10
 RK3, RK5 = 3, 5
 EULER, LSERK14_4, SSPRK33, SSPRK43 = 1, 14, 33, 43
 SURF_SURFACE, SURF_MASS_FLOW, SURF_FLOW_RATE, SURF_PRESSURE, SURF_VEC_SURFACE, SURF_TOTAL_FORCE, SURF_PRESSURE_FORCE, SURF_VISCOUS_FORCE = range(8)

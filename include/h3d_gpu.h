@@ -91,6 +91,7 @@ typedef struct h3d_context* h3d_handle;
 #define H3D_INT_INTERNAL_ENERGY 7   /* "internal energy",:374-386                    */
 #define H3D_INT_ENTROPY_BALANCE 8   /* "entropy balance",:335-370 (entropy rate minus viscous work, per gradient variables) */
 #define H3D_INT_MATH_ENTROPY 9      /* "math entropy",   :311-320                    */
+#define H3D_INT_KINETIC_ENERGY_BALANCE 10 /* "kinetic energy balance", :220-265 with GetPressureLocalGradient :724-764 (energy gradient variables) */
 
 /* RK schemes (libs/timeintegrator/ExplicitMethods.f90:667,790) */
 #define H3D_EULER 1       /* TakeExplicitEulerStep, ExplicitMethods.f90:1232 */

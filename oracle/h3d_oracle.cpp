@@ -1801,6 +1801,30 @@ int orc_volume_integral(void* p, int kind, double* out) {
                     double KinEn = POW2(U_y[IZ] - U_z[IY]) + POW2(U_z[IX] - U_x[IZ]) + POW2(U_x[IY] - U_y[IX]);
                     loc = loc + wJ * KinEn;
                 } break;
+                case H3D_INT_KINETIC_ENERGY_BALANCE: {
+                    // kinetic energy rate + viscous work - pressure work + de-aliasing correction (:220-265)
+                    auto pressureAt = [&](int a, int b, int c) { return Pressure(o, &o.Q[5 * ix.node(e, a, b, c)]); };
+                    double grad_Mp[3] = {0, 0, 0}, M_grad_p[3] = {0, 0, 0};     // GetPressureLocalGradient (:724-764)
+                    for (int l = 0; l < n; ++l) { double pl = pressureAt(l, j, k); size_t gl = ix.node(e, l, j, k);
+                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaXi[3 * gl + d] * o.D[i * n + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaXi[3 * g + d] * o.D[i * n + l]; } }
+                    for (int l = 0; l < n; ++l) { double pl = pressureAt(i, l, k); size_t gl = ix.node(e, i, l, k);
+                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaEta[3 * gl + d] * o.D[j * n + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaEta[3 * g + d] * o.D[j * n + l]; } }
+                    for (int l = 0; l < n; ++l) { double pl = pressureAt(i, j, l); size_t gl = ix.node(e, i, j, l);
+                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaZeta[3 * gl + d] * o.D[k * n + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaZeta[3 * g + d] * o.D[k * n + l]; } }
+                    double inv_rho = 1.0 / Q[IRHO];
+                    double uvw = Q[IRHOU] * inv_rho;
+                    double KinEn = uvw * QD[IRHOU] - 0.5 * POW2(uvw) * QD[IRHO];
+                    uvw = Q[IRHOV] * inv_rho; KinEn = KinEn + uvw * QD[IRHOV] - 0.5 * POW2(uvw) * QD[IRHO];
+                    uvw = Q[IRHOW] * inv_rho; KinEn = KinEn + uvw * QD[IRHOW] - 0.5 * POW2(uvw) * QD[IRHO];
+                    double p3 = o.ph.gammaMinus1 * (Q[IRHOE] - 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) * inv_rho);
+                    double corr = 0.5 * (Q[IRHOU] * (M_grad_p[IX] - grad_Mp[IX]) + Q[IRHOV] * (M_grad_p[IY] - grad_Mp[IY]) + Q[IRHOW] * (M_grad_p[IZ] - grad_Mp[IZ])) * inv_rho;
+                    double F[NCONS][NDIM];
+                    const double* gx = &o.Ux[5 * g]; const double* gy = &o.Uy[5 * g]; const double* gz = &o.Uz[5 * g];
+                    ViscousFlux_ENERGY(o, Q, gx, gy, gz, o.mu[2 * g], 0.0, o.mu[2 * g + 1], F);
+                    double work = 0.0;
+                    for (int q = IRHOU; q <= IRHOW; ++q) work = work + (F[q][IX] * gx[q] + F[q][IY] * gy[q] + F[q][IZ] * gz[q]);
+                    loc = loc + o.w[i] * o.w[j] * o.w[k] * (o.jac[g] * (KinEn + work - p3 * (gx[IRHOU] + gy[IRHOV] + gz[IRHOW])) + corr);
+                } break;
                 case H3D_INT_VELOCITY:
                     loc = loc + o.w[i] * o.w[j] * o.w[k] * std::sqrt(POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] * o.jac[g];
                     break;

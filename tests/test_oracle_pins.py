@@ -255,9 +255,10 @@ def test_k11_energy_and_entropy_conserving_tests_10_steps(case):
         print("K11 entropy balance", bal - 2.1107188664393733E-15, "rate", rate - (-5.3666005706312387E-04))
         assert abs(bal - 2.1107188664393733E-15) < 1.0e-11
         assert abs(rate - (-5.3666005706312387E-04)) < 1.0e-11
-    else:                      # "kinetic energy rate" (the balance monitor of this case is not implemented)
-        rate = sem.volume_monitor("kinetic energy rate")
-        print("K11 kinetic energy rate", rate - (-2.5103194887975733E-02))
+    else:                      # "kinetic energy balance" and "kinetic energy rate", ProblemFile.f90:565-566, 630-638
+        bal, rate = sem.volume_monitor("kinetic energy balance"), sem.volume_monitor("kinetic energy rate")
+        print("K11 kinetic energy balance", bal - (-1.5010521152042858E-15), "rate", rate - (-2.5103194887975733E-02))
+        assert abs(bal - (-1.5010521152042858E-15)) < 1.0e-11
         assert abs(rate - (-2.5103194887975733E-02)) < 1.0e-11
     # the y-momentum residual vanishes by symmetry: its value (6e-11 in the reference, 4e-10 here) is accumulated round-off of
     # terms of magnitude 1e3, so the reference's 1e-10 bound on it is not reproducible across summation orders; it is checked
