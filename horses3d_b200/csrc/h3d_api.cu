@@ -34,6 +34,9 @@ struct h3d_context {
     std::vector<double> hx;   // node positions of the 1-D set (MaxTimeStep)
     double* dSnap = nullptr; double* hSnap = nullptr; size_t snapDoubles = 0; bool snapPending = false;   // asynchronous autosave
     cudaStream_t sCopy = nullptr; cudaEvent_t evSnap = nullptr, evSnapDone = nullptr;
+    // h3d_upload_Q / h3d_download move the state in XFER_CHUNKS pieces: the PCIe copy of one piece runs beside the AoS <-> SoA
+    // transposition of its neighbours (transfer stream + one event per piece)
+    cudaStream_t sXfer = nullptr; cudaEvent_t evX[8] = {nullptr}, evXfree = nullptr; int* dInvPermE = nullptr;
     double* dStats = nullptr; int statVars = 0, statSamples = 0;   // running averages [var][e][node] (StatisticsMonitor)
     bool limited = false; double limiterMin = 1e-13;   // LIMITED, LIMITER_MIN (ExplicitMethods.f90:28-29)
     std::vector<double> hVolume; double* dVolume = nullptr;   // e % geom % volume in device order (stage limiter)
@@ -97,6 +100,19 @@ int devAlloc(h3d_context* h, T** p, size_t count) {
     return 0;
 }
 
+constexpr int XFER_CHUNKS = 8;
+int ensureXfer(h3d_context* h) {
+    if (!h->sXfer) {
+        CTX_CHECK(cudaStreamCreateWithFlags(&h->sXfer, cudaStreamNonBlocking));
+        for (int c = 0; c < XFER_CHUNKS; ++c) CTX_CHECK(cudaEventCreateWithFlags(&h->evX[c], cudaEventDisableTiming));
+        CTX_CHECK(cudaEventCreateWithFlags(&h->evXfree, cudaEventDisableTiming));
+    }
+    if (!h->dInvPermE) {
+        if (devAlloc(h, &h->dInvPermE, h->invPermE.size())) return 2;
+        CTX_CHECK(cudaMemcpy(h->dInvPermE, h->invPermE.data(), h->invPermE.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
 int ensureStaging(h3d_context* h, size_t bytes) {
     if (h->stagingBytes >= bytes) return 0;
     if (h->staging) cudaFree(h->staging);
@@ -113,6 +129,23 @@ __global__ void k_aos_to_soa(const double* __restrict__ src, double* __restrict_
         const int ed = (int)(t / nn), node = (int)(t % nn);
         const int eh = perm ? perm[ed] : ed;
         for (int c = 0; c < C; ++c) dst[((size_t)(cOff + c) * nE + ed) * nn + node] = src[((size_t)eh * nn + node) * C + c];
+    }
+}
+// the same two transpositions over a range [e0, e1) of HOST elements (invPerm: host index -> device index)
+__global__ void k_aos_to_soa_range(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ invPerm, int nE, int nn, int C, int e0, int e1) {
+    const size_t total = (size_t)(e1 - e0) * nn;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int eh = e0 + (int)(t / nn), node = (int)(t % nn);
+        const int ed = invPerm[eh];
+        for (int c = 0; c < C; ++c) dst[((size_t)c * nE + ed) * nn + node] = src[((size_t)eh * nn + node) * C + c];
+    }
+}
+__global__ void k_soa_to_aos_range(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ invPerm, int nE, int nn, int C, int e0, int e1) {
+    const size_t total = (size_t)(e1 - e0) * nn;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int eh = e0 + (int)(t / nn), node = (int)(t % nn);
+        const int ed = invPerm[eh];
+        for (int c = 0; c < C; ++c) dst[((size_t)eh * nn + node) * C + c] = src[((size_t)c * nE + ed) * nn + node];
     }
 }
 __global__ void k_soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, const int* __restrict__ perm, int nE, int nn, int C) {
@@ -807,6 +840,7 @@ int h3d_destroy(h3d_handle h) {
     if (h->dSnap) cudaFree(h->dSnap);
     if (h->hSnap) cudaFreeHost(h->hSnap);
     if (h->sCopy) { cudaStreamDestroy(h->sCopy); cudaEventDestroy(h->evSnap); cudaEventDestroy(h->evSnapDone); }
+    if (h->sXfer) { cudaStreamDestroy(h->sXfer); for (int c = 0; c < XFER_CHUNKS; ++c) cudaEventDestroy(h->evX[c]); cudaEventDestroy(h->evXfree); }
     for (cudaEvent_t ev : {h->evA, h->evB, h->evFaces, h->evGrad, h->evSent, h->evT0, h->evT1}) if (ev) cudaEventDestroy(ev);
     if (h->sCompute) cudaStreamDestroy(h->sCompute);
     if (h->sComm) cudaStreamDestroy(h->sComm);
@@ -906,7 +940,7 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
     // ---- device numbering: interior elements first, elements touching MPI faces last; local faces first
     std::vector<char> isMpiElem(nElem, 0);
     for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_MPI) for (int s = 0; s < 2; ++s) if (faceElem[2 * f + s] >= 0) isMpiElem[faceElem[2 * f + s]] = 1;
-    h->permE.clear(); h->invPermE.assign(nElem, -1);
+    h->permE.clear(); h->invPermE.assign(nElem, -1); h->dInvPermE = nullptr;
     for (int pass = 0; pass < 2; ++pass) for (int e = 0; e < nElem; ++e) if ((int)isMpiElem[e] == pass) { h->invPermE[e] = (int)h->permE.size(); h->permE.push_back(e); }
     h->nSeq = 0; for (int e = 0; e < nElem; ++e) if (!isMpiElem[e]) ++h->nSeq;
     h->permF.clear(); h->invPermF.assign(nFace, -1);
@@ -1075,9 +1109,21 @@ int h3d_upload_Q(h3d_handle h, const double* Q) {
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t ne = (size_t)h->nElem * h->n * h->n * h->n;
     if (ensureStaging(h, 5 * ne * sizeof(double))) return 2;
-    CTX_CHECK(cudaMemcpyAsync(h->staging, Q, 5 * ne * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
-    k_aos_to_soa<<<148 * 8, 256, 0, h->sCompute>>>(h->staging, h->m.Q, h->dPermE, h->nElem, h->n * h->n * h->n, 5, 0);
-    ++h->launches;
+    if (ensureXfer(h)) return 2;
+    // piece c: copy on the transfer stream, transposition on the compute stream as soon as the piece has landed
+    const int n3 = h->n * h->n * h->n;
+    CTX_CHECK(cudaEventRecord(h->evXfree, h->sCompute));           // earlier users of the staging buffer
+    CTX_CHECK(cudaStreamWaitEvent(h->sXfer, h->evXfree, 0));
+    for (int c = 0; c < XFER_CHUNKS; ++c) {
+        const int e0 = (int)((long long)h->nElem * c / XFER_CHUNKS), e1 = (int)((long long)h->nElem * (c + 1) / XFER_CHUNKS);
+        if (e1 <= e0) continue;
+        const size_t off = (size_t)e0 * n3 * 5, cnt = (size_t)(e1 - e0) * n3 * 5;
+        CTX_CHECK(cudaMemcpyAsync(h->staging + off, Q + off, cnt * sizeof(double), cudaMemcpyHostToDevice, h->sXfer));
+        CTX_CHECK(cudaEventRecord(h->evX[c], h->sXfer));
+        CTX_CHECK(cudaStreamWaitEvent(h->sCompute, h->evX[c], 0));
+        k_aos_to_soa_range<<<148 * 2, 256, 0, h->sCompute>>>(h->staging, h->m.Q, h->dInvPermE, h->nElem, n3, 5, e0, e1);
+        ++h->launches;
+    }
     h->facesValid = false; ++h->stateVersion;
     CTX_CHECK(cudaGetLastError());
     return 0;
@@ -1091,12 +1137,21 @@ int h3d_download(h3d_handle h, double* Q, double* QDot, double* Ux, double* Uy, 
     if (ensureStaging(h, 5 * ne * sizeof(double))) return 2;
     double* dst[5] = {Q, QDot, Ux, Uy, Uz};
     const double* src[5] = {h->m.Q, h->m.QDot, h->m.Ux, h->m.Uy, h->m.Uz};
+    if (ensureXfer(h)) return 2;
     for (int a = 0; a < 5; ++a) {
         if (!dst[a]) continue;
-        k_soa_to_aos<<<148 * 8, 256, 0, h->sCompute>>>(src[a], h->staging, h->dPermE, h->nElem, n3, 5);
-        ++h->launches;
-        CTX_CHECK(cudaMemcpyAsync(dst[a], h->staging, 5 * ne * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute));
-        CTX_CHECK(cudaStreamSynchronize(h->sCompute));
+        // piece c: transposition on the compute stream, copy on the transfer stream beside the next transposition
+        for (int c = 0; c < XFER_CHUNKS; ++c) {
+            const int e0 = (int)((long long)h->nElem * c / XFER_CHUNKS), e1 = (int)((long long)h->nElem * (c + 1) / XFER_CHUNKS);
+            if (e1 <= e0) continue;
+            const size_t off = (size_t)e0 * n3 * 5, cnt = (size_t)(e1 - e0) * n3 * 5;
+            k_soa_to_aos_range<<<148 * 2, 256, 0, h->sCompute>>>(src[a], h->staging, h->dInvPermE, h->nElem, n3, 5, e0, e1);
+            ++h->launches;
+            CTX_CHECK(cudaEventRecord(h->evX[c], h->sCompute));
+            CTX_CHECK(cudaStreamWaitEvent(h->sXfer, h->evX[c], 0));
+            CTX_CHECK(cudaMemcpyAsync(dst[a] + off, h->staging + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->sXfer));
+        }
+        CTX_CHECK(cudaStreamSynchronize(h->sXfer));    // the staging buffer is free again and the host array is complete
     }
     return 0;
 }
