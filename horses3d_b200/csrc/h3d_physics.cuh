@@ -226,9 +226,16 @@ __device__ __forceinline__ void ec_mean_state(const Phys& ph, bool twoPoint, dou
     const double p2 = (gammaPlus1Div2 * z5Log / z1Log + gammaMinus1Div2 * p) * invGamma;
     h = gammaDivGammaMinus1 * p2 / rho + 0.5 * (pow2(u) + pow2(v) + pow2(w));
 }
+// betaL, betaR = 1/2 rho / p of the two states (evaluated per pair by chandrasekar_mean_state, once per node by the volume kernel)
+__device__ __forceinline__ void chandrasekar_mean_state_beta(const Phys& ph, double rhoL, double rhoR, double uL, double uR, double vL, double vR,
+                                                             double wL, double wR, double betaL, double betaR, double& rho, double& u, double& v, double& w, double& p, double& h);
 __device__ __forceinline__ void chandrasekar_mean_state(const Phys& ph, double rhoL, double rhoR, double uL, double uR, double vL, double vR,
                                                         double wL, double wR, double pL, double pR, double& rho, double& u, double& v, double& w, double& p, double& h) {
     const double betaL = 0.5 * rhoL / pL, betaR = 0.5 * rhoR / pR;
+    chandrasekar_mean_state_beta(ph, rhoL, rhoR, uL, uR, vL, vR, wL, wR, betaL, betaR, rho, u, v, w, p, h);
+}
+__device__ __forceinline__ void chandrasekar_mean_state_beta(const Phys& ph, double rhoL, double rhoR, double uL, double uR, double vL, double vR,
+                                                             double wL, double wR, double betaL, double betaR, double& rho, double& u, double& v, double& w, double& p, double& h) {
     const double betaLog = log_mean(betaL, betaR);
     rho = log_mean(rhoL, rhoR);
     u = 0.5 * (uL + uR); v = 0.5 * (vL + vR); w = 0.5 * (wL + wR);
@@ -724,7 +731,7 @@ __device__ __forceinline__ void two_point_flux(const Phys& ph, const double QL[5
 
 // The same two-point fluxes from per-node primitives P = [rho, u, v, w, p, X] evaluated ONCE per node instead of once per
 // pair (the split-form volume term evaluates 3 N pairs per node): X = rho e / rho for Kennedy-Gruber, (rho e + p) / rho for
-// Pirozzoli, unused by the entropy-conserving and Chandrasekar fluxes.  Every per-node expression is the one the pairwise
+// Pirozzoli, beta = 1/2 rho / p for Chandrasekar, unused by the entropy-conserving flux.  Every per-node expression is the one the pairwise
 // routines above evaluate (invRho = 1 / rho; u = invRho * rho u; p = (gamma-1)(rho e - (rho u u + rho v v + rho w w)/2)), so the
 // result is bit-identical.  prim_two_point_ok() tells which averages take this path.
 __device__ __forceinline__ bool prim_two_point_ok(int averaging) {
@@ -735,7 +742,7 @@ __device__ __forceinline__ void node_primitives(const Phys& ph, const double Q[5
     const double u = invRho * Q[1], v = invRho * Q[2], w = invRho * Q[3];
     const double p = ph.gm1 * (Q[4] - 0.5 * (Q[1] * u + Q[2] * v + Q[3] * w));
     P[0] = Q[0]; P[1] = u; P[2] = v; P[3] = w; P[4] = p;
-    P[5] = ph.averaging == H3D_AVG_KENNEDYGRUBER ? Q[4] * invRho : (Q[4] + p) * invRho;
+    P[5] = ph.averaging == H3D_AVG_KENNEDYGRUBER ? Q[4] * invRho : (ph.averaging == H3D_AVG_CHANDRASEKAR ? 0.5 * Q[0] / p : (Q[4] + p) * invRho);
 }
 template <bool EXT>
 __device__ __forceinline__ void two_point_flux_prim(const Phys& ph, const double PL[6], const double PR[6], const double JaL[3], const double JaR[3], double fs[5]) {
@@ -745,7 +752,7 @@ __device__ __forceinline__ void two_point_flux_prim(const Phys& ph, const double
         if (ph.averaging > H3D_AVG_PIROZZOLI) {
             double rho, u, v, w, p, hh;
             if (ph.averaging == H3D_AVG_ENTROPYCONS) ec_mean_state(ph, true, PL[0], PR[0], PL[1], PR[1], PL[2], PR[2], PL[3], PR[3], PL[4], PR[4], rho, u, v, w, p, hh);
-            else chandrasekar_mean_state(ph, PL[0], PR[0], PL[1], PR[1], PL[2], PR[2], PL[3], PR[3], PL[4], PR[4], rho, u, v, w, p, hh);
+            else chandrasekar_mean_state_beta(ph, PL[0], PR[0], PL[1], PR[1], PL[2], PR[2], PL[3], PR[3], PL[5], PR[5], rho, u, v, w, p, hh);
             f[0] = rho * u; f[1] = rho * u * u + p; f[2] = rho * u * v; f[3] = rho * u * w; f[4] = rho * u * hh;
             g[0] = rho * v; g[1] = rho * v * u; g[2] = rho * v * v + p; g[3] = rho * v * w; g[4] = rho * v * hh;
             h[0] = rho * w; h[1] = rho * w * u; h[2] = rho * w * v; h[3] = rho * w * w + p; h[4] = rho * w * hh;
