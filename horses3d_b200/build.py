@@ -19,6 +19,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 INCLUDE_DIR = os.path.join(ROOT, "include")
 
 HOST_LIB = os.path.join(HOST_DIR, "libh3dhost.so")
+DRIVER_BIN = os.path.join(HOST_DIR, "h3d_driver")
 GPU_LIB = os.path.join(CSRC_DIR, "libh3dgpu.so")
 GPU_LIB_FMA = os.path.join(CSRC_DIR, "libh3dgpu_fma.so")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libh3doracle.so")
@@ -55,6 +56,14 @@ def build_host(force=False):
             cmd.append(METIS_A)
         _run(cmd)
     return HOST_LIB
+
+
+def build_driver(force=False):
+    """h3d_driver: the native (C++) host-side driver above the C ABI (horses3d_b200/host/h3d_driver.cpp, dgsem.hpp)."""
+    srcs = _sources(HOST_DIR, (".cpp", ".hpp")) + _sources(INCLUDE_DIR, (".h",))
+    if force or _newer(DRIVER_BIN, srcs):
+        _run(["g++", "-O2", "-std=c++17", "-fopenmp", os.path.join(HOST_DIR, "h3d_driver.cpp"), "-o", DRIVER_BIN, "-ldl"])
+    return DRIVER_BIN
 
 
 def nvcc_path():
@@ -100,10 +109,10 @@ def build_oracle(force=False):
 
 
 def build_all(force=False):
-    return build_host(force), build_gpu(force), build_oracle(force)
+    return build_host(force), build_gpu(force), build_oracle(force), build_driver(force)
 
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    {"host": build_host, "gpu": build_gpu, "fma": build_gpu_fma, "oracle": build_oracle, "all": build_all}[which](force=True)
+    {"host": build_host, "gpu": build_gpu, "fma": build_gpu_fma, "oracle": build_oracle, "driver": build_driver, "all": build_all}[which](force=True)
     print("built", which)

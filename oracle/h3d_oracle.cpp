@@ -1380,6 +1380,7 @@ void computeTimeDerivative(Oracle& o, double time) {
 extern "C" {
 
 void* orc_create() { return new Oracle(); }
+int orc_create_handle(void** out, int, int, int, const void*) { *out = new Oracle(); return 0; }   // the signature of h3d_create
 void orc_destroy(void* p) { delete (Oracle*)p; }
 const char* orc_last_error(void* p) { return ((Oracle*)p)->err.c_str(); }
 
