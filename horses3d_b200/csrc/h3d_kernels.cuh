@@ -799,30 +799,10 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 #pragma unroll
                         for (int c = 0; c < 9; ++c) ja[c] = m.Ja[c * es + go];
                     }
-                    double F[5][3], Fc[5][3];
-                    euler_flux(ph, Qk[r], F);
-#pragma unroll
-                    for (int q = 0; q < 5; ++q)
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) Fc[q][d] = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
-                    if (SPLIT) {
-                        if (prim) {
-                            node_primitives(ph, Qk[r], Pk[r]);
-                            if (HALF) {   // halved primitives and metrics (two_point_flux_half)
-#pragma unroll
-                                for (int q = 0; q < 6; ++q) Pk[r][q] = 0.5 * Pk[r][q];
-                            }
-                            sX[le * NS + p] = Pk[r][5];
-                        }
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            sQ[(le * 5 + q) * NS + p] = prim ? Pk[r][q] : Qk[r][q];
-#pragma unroll
-                            for (int d = 0; d < 3; ++d) FinvD[r][d * 5 + q] = Fc[q][d];
-                        }
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * NS + p] = HALF ? 0.5 * ja[c] : ja[c];
-                    }
+                    // The viscous contravariant flux comes first: its inputs (15 gradient values) are dead before the inviscid
+                    // flux is formed, which keeps the live set of this phase at ~45 doubles instead of ~60 (the kernel is bound
+                    // by its 128 registers: a build with 16 more bytes of spills measured 20 % slower).
+                    double F[5][3], fv[5][3];
                     if (ns) {
                         double gx[5], gy[5], gz[5], mu, kappa;
                         if (TMA) {
@@ -839,15 +819,32 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                         for (int q = 0; q < 5; ++q)
 #pragma unroll
                             for (int d = 0; d < 3; ++d) {
-                                const double fv = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
-                                if (SPLIT) sF[((le * 3 + d) * 5 + q) * NS + p] = fv;
-                                else sF[((le * 3 + d) * 5 + q) * NS + p] = Fc[q][d] - fv;
+                                fv[q][d] = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
+                                if (SPLIT) sF[((le * 3 + d) * 5 + q) * NS + p] = fv[q][d];
                             }
-                    } else if (!SPLIT) {
+                    }
+                    euler_flux(ph, Qk[r], F);
 #pragma unroll
-                        for (int q = 0; q < 5; ++q)
+                    for (int q = 0; q < 5; ++q)
 #pragma unroll
-                            for (int d = 0; d < 3; ++d) sF[((le * 3 + d) * 5 + q) * NS + p] = Fc[q][d] - 0.0;
+                        for (int d = 0; d < 3; ++d) {
+                            const double fc = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
+                            if (SPLIT) FinvD[r][d * 5 + q] = fc;
+                            else sF[((le * 3 + d) * 5 + q) * NS + p] = fc - (ns ? fv[q][d] : 0.0);
+                        }
+                    if (SPLIT) {
+                        if (prim) {
+                            node_primitives(ph, Qk[r], Pk[r]);
+                            if (HALF) {   // halved primitives and metrics (two_point_flux_half)
+#pragma unroll
+                                for (int q = 0; q < 6; ++q) Pk[r][q] = 0.5 * Pk[r][q];
+                            }
+                            sX[le * NS + p] = Pk[r][5];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) sQ[(le * 5 + q) * NS + p] = prim ? Pk[r][q] : Qk[r][q];
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * NS + p] = HALF ? 0.5 * ja[c] : ja[c];
                     }
                 }
             }
