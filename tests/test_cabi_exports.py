@@ -52,3 +52,18 @@ def test_oracle_is_not_reachable_from_the_product_package():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_api" not in text and "h3d_oracle" not in text and "orc_" not in text, os.path.join(dirpath, f)
+
+
+def test_fortran_interfaces_are_in_step_with_the_header():
+    """integration/h3d_gpu_interfaces.f90 (the ISO_C_BINDING interface block a maintainer of the reference compiles into the
+    adapter) is generated from include/h3d_gpu.h: it must be current and cover every entry point and every field of H3dPhysics."""
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_fortran_interfaces.py"), "--check"]).returncode == 0
+    text = open(os.path.join(ROOT, "integration", "h3d_gpu_interfaces.f90")).read()
+    for f in declared_functions():
+        assert 'bind(C, name="%s")' % f in text or 'name="%s")' % f in text, f
+    from horses3d_b200.physics import H3dPhysics
+    for name, _ in H3dPhysics._fields_:
+        assert re.search(r":: %s\b" % name, text), name
+    assert max(len(l) for l in text.splitlines()) <= 132
