@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--riemann", default="roe")
     ap.add_argument("--nodes", default="gauss", choices=["gauss", "gauss-lobatto"])
     ap.add_argument("--viscous", default="BR1", choices=["BR1", "BR2", "IP"])
+    ap.add_argument("--les", default="none", choices=["none", "smagorinsky"])
     ap.add_argument("--gradient-variables", default="State", choices=["State", "Entropy", "Energy"])
     return ap.parse_args()
 
@@ -137,11 +138,12 @@ def main_b200(args):
     nodes = GAUSS if args.nodes == "gauss" else GAUSSLOBATTO
     euler = args.flow == "Euler"
     phys_kw = dict(flow=args.flow, mach=0.08, reynolds=1600.0, riemann=args.riemann, inviscid=args.inviscid, averaging=args.averaging,
-                   viscous=args.viscous, gradient_variables=args.gradient_variables)
+                   viscous=args.viscous, gradient_variables=args.gradient_variables, les=args.les)
     headline = (not euler) and args.inviscid == "standard" and args.riemann == "roe" and args.nodes == "gauss" and args.viscous == "BR1" \
-        and args.gradient_variables == "State"
+        and args.gradient_variables == "State" and args.les == "none"
     scheme = "%s, %s%s+%s" % (args.flow, "StandardDG" if args.inviscid == "standard" else "SplitDG-" + args.averaging,
-                              "" if euler else "+" + args.viscous + ("" if args.gradient_variables == "State" else "(" + args.gradient_variables + " variables)"), args.riemann)
+                              "" if euler else "+" + args.viscous + ("" if args.gradient_variables == "State" else "(" + args.gradient_variables + " variables)")
+                              + ("" if args.les == "none" else "+Smagorinsky"), args.riemann)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

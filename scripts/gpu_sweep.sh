@@ -20,3 +20,5 @@ run c3_split_p7 --order 7 --ne 32 --flow Euler --inviscid split-form --averaging
 run c3_split_p9 --order 9 --ne 26 --flow Euler --inviscid split-form --averaging pirozzoli --nodes gauss-lobatto
 run euler_std_p7 --order 7 --ne 32 --flow Euler
 run ns_split_p7 --order 7 --ne 32 --inviscid split-form --averaging pirozzoli --nodes gauss-lobatto
+run c5_les_p3_ne64 --order 3 --ne 64 --les smagorinsky
+run les_p7_ne32 --order 7 --ne 32 --les smagorinsky
