@@ -102,7 +102,7 @@ def build_oracle(force=False):
     srcs = _sources(ORACLE_DIR, (".cpp", ".hpp"))
     if force or _newer(ORACLE_LIB, srcs):
         # -ffp-contract=off: the reference's gfortran RELEASE build (-O3, no -march, no -ffast-math) emits no FMA
-        cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared",
+        cmd = ["g++", "-O3", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared",
                os.path.join(ORACLE_DIR, "h3d_oracle.cpp"), "-o", ORACLE_LIB]
         _run(cmd)
     return ORACLE_LIB
