@@ -8,7 +8,10 @@ txt = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=T
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
 want = {"k_gradientILi%sELb1" % n: "k_gradient_tma", "k_volumeILi%sELi0ELb1" % n: "k_volume_tma", "k_volumeILi%sELi1ELb1" % n: "k_volume_split_tma",
         "k_riemannILi%sELb0" % n: "k_riemann", "k_riemannILi%sELb1" % n: "k_riemann_ext", "k_prolong_qILi%s" % n: "k_prolong_q", "k_red_residual": "k_red_residual",
-        "k_red_timestep": "k_red_timestep", "k_red_integrals": "k_red_integrals", "k_halo_pack": "k_halo_pack", "k_halo_unpack": "k_halo_unpack"}
+        "k_red_timestep": "k_red_timestep", "k_red_integralsE": "k_red_integrals", "k_red_integrals2": "k_red_integrals2", "k_red_ke_balance": "k_red_ke_balance",
+        "k_stage_limiter": "k_stage_limiter", "k_halo_pack": "k_halo_pack", "k_halo_unpack": "k_halo_unpack",
+        "k_gradientILi%sELb0ELb1" % n: "k_gradient_general", "k_volumeILi%sELi2ELb0ELb0" % n: "k_volume_split_ext", "k_volumeILi%sELi0ELb0ELb1" % n: "k_volume_gradvars",
+        "k_aos_to_soa_range": "k_aos_to_soa_range", "k_soa_to_aos_range": "k_soa_to_aos_range"}
 summary = []
 for f in funcs:
     name = f.split("\n", 1)[0].strip()
