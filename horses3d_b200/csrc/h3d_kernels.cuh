@@ -673,6 +673,10 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
     // MODE 1 stages HALVED primitives and metrics (two_point_flux_half).  Measured on B200, Euler Pirozzoli, volume kernel:
     // n=4 3.17 -> 3.11 ms, n=8 3.54 -> 3.35 ms, n=10 5.90 -> 5.66 ms, but n=6 3.23 -> 3.47 ms (three runs each): not at n=6.
     constexpr bool HALF = (MODE == 1) && (n != 6);
+    // pair loop of the split form unrolled by LU: several pairs in flight give the FP64 pipe independent work.  Measured (Euler
+    // Pirozzoli volume kernel, LU = 1 / 2 / 4): n=4 2.99 / 2.86 / 3.01 ms, n=6 3.03 / 3.02 / 3.35, n=8 3.37 / 3.20 / 3.14, n=10 5.66 /
+    // 5.52 / 5.56; the general instantiation (MODE 2, logarithmic means) is slower unrolled (11.7 -> 12.5 ms) and stays rolled
+    constexpr int LU = (MODE != 1) ? 1 : (n == 8 ? 4 : 2);
     extern __shared__ __align__(16) double smem[];
     const bool ns = ph.ns != 0;
     const int nStaged = TMA ? (ns ? 29 : 14) : 0;
@@ -891,6 +895,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                             double jaMe[3];
 #pragma unroll
                             for (int c = 0; c < 3; ++c) jaMe[c] = sJe[(3 * d + c) * NS + p];
+#pragma unroll LU
                             for (int l = 0; l < n; ++l) {
                                 const int other = ob + l * ostr;
                                 double fsvv[5];
