@@ -17,7 +17,7 @@ for f in funcs:
     name = f.split("\n", 1)[0].strip()
     for key, short in want.items():
         if key in name:
-            ins = re.findall(r"/\*[0-9a-f]{4}\*/\s+(.*?);", f)
+            ins = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+(.*?);", f)
             ops = collections.Counter((i.split()[1] if i.startswith("@") else i.split()[0]).split(".")[0] for i in ins if i.strip())
             with open(os.path.join(out, "sass_%s_n%s.txt" % (short, n)), "w") as fh:
                 fh.write("// %s\n// %d instructions; opcode histogram: %s\n" % (name, len(ins), dict(ops.most_common(25))))
