@@ -142,6 +142,21 @@ def test_boundary_conditions_and_les_match_oracle(gpu_api_cls, ne, N, nodes, amp
     assert rel_err(sg.Q(), so.Q()) < tol_of(kw)
 
 
+@pytest.mark.parametrize("dims,N", [((3, 1, 2), 3), ((1, 1, 1), 7), ((2, 2, 1), 2), ((1, 2, 1), 4)])
+def test_elements_that_are_their_own_periodic_neighbours_match_oracle(gpu_api_cls, dims, N):
+    """Smallest meshes: with one element along a periodic direction a face has the SAME element on both sides (the
+    reference's CylinderNSpol3_1elem_y.mesh situation); down to a single element that is its own neighbour six times."""
+    from horses3d_b200.hostmesh import HostMesh
+    mesh = HostMesh.box(dims[0], ney=dims[1], nez=dims[2], amp=0.05, bFaceOrder=2).connect().geometry(N, GAUSS)
+    assert mesh.nElem == dims[0] * dims[1] * dims[2] and mesh.nFaces == 3 * mesh.nElem
+    (so, o), (sg, g) = run_pair(gpu_api_cls, mesh, make_physics(flow="NS", mach=0.3, reynolds=100.0))
+    for k in ("U_x", "U_y", "U_z", "QDot"):
+        assert rel_err(g[k], o[k]) < TOL_QDOT, k
+    for api in (so, sg):
+        api.TakeRK3Step(0.0, 1e-3)
+    assert rel_err(sg.Q(), so.Q()) < TOL_QDOT
+
+
 def test_surface_integrals_match_oracle(gpu_api_cls):
     """ScalarSurfaceIntegral / VectorSurfaceIntegral of every kind on every zone of the channel mesh, after an RK step
     (prolonged updated state, gradients of the last stage as the reference has them)."""
