@@ -436,6 +436,41 @@ BOX_CIRCLE_MESH = "/root/reference/Solver/test/TestMeshes/BoxAroundCircle3D_exte
 
 
 @pytest.mark.skipif(not __import__("os").path.exists(BOX_CIRCLE_MESH), reason="reference test mesh not available on this machine")
+def test_k4b_box_around_circle_standard_dg_1000_steps():
+    """Solver/test/Euler/BoxAroundCircle: the same case with the standard DG discretization on Gauss nodes (standard Roe solver,
+    RK3, cfl 0.7, 1000 steps).  Final time, residuals, wake probe and pressure average with the 1e-11 tolerance of
+    SETUP/ProblemFile.f90:340-400, the drag monitor (453.58) with its 1e-10."""
+    import math
+    from horses3d_b200 import probes
+    from horses3d_b200.physics import bc_parameters
+    phys = make_physics(flow="Euler", mach=0.3, riemann="standard roe")
+    zones = [("innercylinder", "freeslipwall"), ("front", "inflow"), ("bottom", "freeslipwall"), ("top", "freeslipwall"),
+             ("back", "inflow"), ("left", "inflow"), ("right", "inflow")]
+    p_in, rho_in = 1.0 / phys.gammaM2, 1.0
+    v_in = phys.Mach * math.sqrt(phys.gamma * p_in / rho_in)
+    params = [bc_parameters("inflow", phys, rho=rho_in, v=v_in, aoa_theta=0.0, aoa_phi=0.0, p=p_in) if t == "inflow" else bc_parameters(t, phys)
+              for _, t in zones]
+    m = HostMesh.read(BOX_CIRCLE_MESH).connect([(z, t, None) for z, t in zones], np.array(params)).geometry(3, GAUSS)
+    sem = DGSem(oracle_api.OracleApi(), m, phys)
+    Q = np.zeros(sem.node_coordinates().shape[:-1] + (5,))
+    Q[..., 0], Q[..., 1] = 1.0, 1.0
+    Q[..., 4] = (1.0 / phys.gammaM2) / (phys.gamma - 1.0) + 0.5
+    sem.set_Q(Q)
+    rec = sem.integrate(1000, cfl=0.7, dcfl=0.7, monitors=False)[-1]
+    res = np.array([3.9167069726447580E-003, 7.0027671589173224E-002, 3.6068228611380296E-013, 8.2231956082004870E-002, 0.10659815868258372])
+    cd = sem.surface_monitor("innercylinder", "pressure-force", [1.0, 0.0, 0.0])
+    p_aver = sem.surface_monitor("innercylinder", "pressure-average")
+    wake = probes.evaluate(sem, [probes.Probe(sem, [0.0, 2.0, 4.0], "w")])[0]
+    print("K4b t", rec["t"] - 8.1360293112980031, "res", rec["residuals"] - res, "cd", cd - 453.57879703318662, "p_aver", p_aver - 7.3644805258897463,
+          "wake", wake - (-2.1611054398635306E-002))
+    assert abs(rec["t"] - 8.1360293112980031) < 1.0e-11
+    assert np.abs(rec["residuals"] - res).max() < 1.0e-11
+    assert abs(p_aver - 7.3644805258897463) < 1.0e-11
+    assert abs(wake - (-2.1611054398635306E-002)) < 1.0e-11
+    assert abs(cd - 453.57879703318662) < 1.0e-10      # the reference's own tolerance
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(BOX_CIRCLE_MESH), reason="reference test mesh not available on this machine")
 def test_k4_box_around_circle_pirozzoli_1000_steps():
     """Solver/test/Euler/BoxAroundCirclePirozzoli: Euler, M 0.3, P=3 Gauss-Lobatto, split-form with the Pirozzoli two-point
     flux, standard Roe solver, RK3, cfl 0.7, 1000 steps on the curved mesh around a cylinder (free-slip walls, inflow).
