@@ -432,6 +432,44 @@ def test_rk_step_equals_its_stages():
     assert np.array_equal(res[0], res[1])
 
 
+BOX27_MESH = "/root/reference/Solver/test/TestMeshes/Box27.mesh"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(BOX27_MESH), reason="reference test mesh not available on this machine")
+def test_k12_euler_uniform_flow_rusanov_iterations_to_tolerance():
+    """Solver/test/Euler/UniformFlow: Euler, M 0.5, P=5 Gauss, Rusanov solver, inflow on all six sides of the 27-element box, a 5 %
+    density bump at node (3,3,3) of every element that relaxes back to the uniform flow; RK3 at cfl 0.4 until the maximum residual
+    falls below the convergence tolerance 1e-10.  The reference pins the NUMBER OF ITERATIONS (4164), the final residual
+    (9.7454147241309180E-011, 1e-3 relative) and the maximum deviation from the uniform state (1e-10), SETUP/ProblemFile.f90:316-372."""
+    import math
+    from horses3d_b200.physics import bc_parameters
+    phys = make_physics(flow="Euler", mach=0.5, riemann="rusanov")
+    zones = ["left", "right", "front", "back", "bottom", "top"]
+    p_in = 1.0 / phys.gammaM2
+    v_in = phys.Mach * math.sqrt(phys.gamma * p_in / 1.0)
+    params = np.array([bc_parameters("inflow", phys, rho=1.0, v=v_in, aoa_theta=0.0, aoa_phi=0.0, p=p_in) for _ in zones])
+    m = HostMesh.read(BOX27_MESH).connect([(z, "inflow", None) for z in zones], params).geometry(5, GAUSS)
+    assert m.nElem == 27
+    sem = DGSem(oracle_api.OracleApi(), m, phys)
+    Q0 = np.zeros(sem.node_coordinates().shape[:-1] + (5,))
+    Q0[..., 0], Q0[..., 1] = 1.0, 1.0
+    Q0[..., 4] = p_in / (phys.gamma - 1.0) + 0.5
+    Q = Q0.copy()
+    Q[:, 3, 3, 3, 0] = 1.05 * Q[:, 3, 3, 3, 0]            # storage % Q(1,3,3,3), ProblemFile.f90:139
+    sem.set_Q(Q)
+    sem.ComputeTimeDerivative(0.0)
+    t, it, res = 0.0, 0, sem.ComputeMaxResiduals().max()
+    while res > 1.0e-10 and it < 5000:                      # TimeIntegrator.f90:860-870 (convergence test after every step)
+        dt = min(sem.MaxTimeStep(0.4, 0.4))
+        sem.TakeRK3Step(t, dt)
+        t, it = t + dt, it + 1
+        res = sem.ComputeMaxResiduals().max()
+    print("K12 iterations", it, "residual", res, "max error", np.abs(sem.Q() - Q0).max())
+    assert it == 4164
+    assert abs(res - 9.7454147241309180E-011) <= 1.0e-3 * 9.7454147241309180E-011
+    assert np.abs(sem.Q() - Q0).max() < 1.0e-10
+
+
 BOX_CIRCLE_MESH = "/root/reference/Solver/test/TestMeshes/BoxAroundCircle3D_extended_pol3.mesh"
 
 
