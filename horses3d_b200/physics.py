@@ -10,7 +10,7 @@ RIEMANN = {"roe": 0, "lax-friedrichs": 1, "central": 2, "rusanov": 3, "standard 
            "low dissipation roe": 7, "matrix dissipation": 8}
 AVERAGING = {"standard": 0, "kennedy-gruber": 1, "pirozzoli": 2, "ducros": 3, "morinishi": 4, "entropy conserving": 5,
              "chandrasekar": 6}
-LES = {"none": 0, "smagorinsky": 1}
+LES = {"none": 0, "smagorinsky": 1, "wale": 2, "vreman": 3}
 VISCOUS = {"br1": 0, "br2": 1, "ip": 2}
 IP_VARIANT = {"sipg": -1, "iipg": 0, "nipg": 1}
 GRADVARS = {"state": 0, "entropy": 1, "energy": 2}
@@ -33,7 +33,7 @@ class H3dPhysics(C.Structure):
 
 
 def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="standard", riemann="roe",
-                 averaging="standard", lambda_stab=1.0, compute_gradients=None, les="none", smagorinsky_cs=0.2, les_wall_model="none",
+                 averaging="standard", lambda_stab=1.0, compute_gradients=None, les="none", smagorinsky_cs=None, les_wall_model="none",
                  sutherland_temperature=None, reference_temperature=None, sutherland_ref_temperature=None,
                  viscous="BR1", penalty_parameter=None, ip_variant="SIPG", gradient_variables="State"):
     p = H3dPhysics()
@@ -70,7 +70,8 @@ def make_physics(flow="NS", mach=0.08, reynolds=1600.0, prandtl=0.72, inviscid="
     p.ipVariant = IP_VARIANT[ip_variant.lower()]
     p.gradientVariables = GRADVARS[gradient_variables.lower()] if ns else 0       # SpatialDiscretization.f90:106-148, 190-193
     p.les = LES[les.lower()]
-    p.smagorinsky_Cs = smagorinsky_cs
+    # "LES model intensity" defaults: Smagorinsky 0.2, WALE 0.325, Vreman 0.07 (LESModels.f90:233-254, 337-356, 466-485)
+    p.smagorinsky_Cs = smagorinsky_cs if smagorinsky_cs is not None else {0: 0.2, 1: 0.2, 2: 0.325, 3: 0.07}[p.les]
     p.les_wall_model = {"none": 0, "linear": 1}[les_wall_model.lower()]      # LESModels.f90:137-165
     return p
 

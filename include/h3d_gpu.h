@@ -57,6 +57,8 @@ typedef struct h3d_context* h3d_handle;
 /* LES (libs/physics/common/LESModels.f90) */
 #define H3D_LES_NONE 0
 #define H3D_LES_SMAGORINSKY 1
+#define H3D_LES_WALE 2            /* WALE_ComputeViscosity, LESModels.f90:358-435; intensity Cw (default 0.325)   */
+#define H3D_LES_VREMAN 3          /* Vreman_ComputeViscosity, LESModels.f90:487-546; intensity C (default 0.07)    */
 
 /* viscous discretization (libs/discretization/EllipticDiscretizations.f90; EllipticBR1.f90, EllipticBR2.f90, EllipticIP.f90) */
 #define H3D_VISCOUS_BR1 0
@@ -117,7 +119,7 @@ typedef struct H3dPhysics {
     double S_div_Tref;       /* S_div_TRef_Sutherland                           */
     double T_renorm;         /* TemperatureReNormalization_Sutherland           */
     double lambdaStab;       /* RiemannSolvers_NS lambdaStab (0 for central)    */
-    double smagorinsky_Cs;   /* LESModels.f90 Smagorinsky CS                    */
+    double smagorinsky_Cs;   /* "LES model intensity": Smagorinsky CS / WALE Cw / Vreman C */
     double Prt;              /* dimensionless % Prt                             */
     double penaltyParameter; /* BR2 eta / IP sigma ("penalty parameter" key)    */
     int flowIsNavierStokes;  /* 0 = Euler                                       */

@@ -256,8 +256,48 @@ inline void getVelocityGradients(const Oracle& o, const double* Q, const double*
     }
 }
 
+// WALE_ComputeViscosity (LESModels.f90:358-435) and Vreman_ComputeViscosity (:487-546)
+inline void getVelocityGradients(const Oracle& o, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z, double* U_x, double* U_y, double* U_z);
+inline double WaleViscosity(const Oracle& o, double delta, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z) {
+    double U_x[3], U_y[3], U_z[3], gradV[3][3], S[3][3], gradV2[3][3], Sd[3][3];
+    getVelocityGradients(o, Q, Q_x, Q_y, Q_z, U_x, U_y, U_z);
+    for (int c = 0; c < 3; ++c) { gradV[0][c] = U_x[c]; gradV[1][c] = U_y[c]; gradV[2][c] = U_z[c]; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        S[i][j] = 0.5 * (gradV[i][j] + gradV[j][i]);
+        gradV2[i][j] = 0;
+        for (int k = 0; k < 3; ++k) gradV2[i][j] = gradV2[i][j] + gradV[i][k] * gradV[k][j];
+    }
+    double divV2 = gradV2[0][0] + gradV2[1][1] + gradV2[2][2];
+    double normS = 0.0;
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) normS = normS + S[i][j] * S[i][j];      // sum(S*S), column-major
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Sd[i][j] = 0.5 * (gradV2[i][j] + gradV2[j][i]);
+    Sd[0][0] = Sd[0][0] - 1.0 / 3.0 * divV2; Sd[1][1] = Sd[1][1] - 1.0 / 3.0 * divV2; Sd[2][2] = Sd[2][2] - 1.0 / 3.0 * divV2;
+    double normSd = 0.0;
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) normSd = normSd + Sd[i][j] * Sd[i][j];
+    double LS = o.ph.smagorinsky_Cs * delta;
+    double mu = Q[IRHO] * POW2(LS) * (std::pow(normSd, 3.0 / 2.0) / (std::pow(normS, 5.0 / 2.0) + std::pow(normSd, 5.0 / 4.0)));
+    if (normS < 1.0e-8 && normSd < 1.0e-8) mu = 0.0;
+    return mu;
+}
+inline double VremanViscosity(const Oracle& o, double delta, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z) {
+    double U_x[3], U_y[3], U_z[3], gradV[3][3], G[3][3];
+    getVelocityGradients(o, Q, Q_x, Q_y, Q_z, U_x, U_y, U_z);
+    const double delta2 = delta * delta;
+    for (int c = 0; c < 3; ++c) { gradV[0][c] = U_x[c]; gradV[1][c] = U_y[c]; gradV[2][c] = U_z[c]; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        G[i][j] = 0.0;
+        for (int k = 0; k < 3; ++k) G[i][j] = G[i][j] + (gradV[i][k] * gradV[j][k] * delta2);
+    }
+    double alpha = 0.0;
+    for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) alpha = alpha + gradV[i][j] * gradV[i][j];
+    double Bbeta = G[0][0] * G[1][1] + G[1][1] * G[2][2] + G[2][2] * G[0][0] - G[0][1] * G[0][1] - G[1][2] * G[1][2] - G[0][2] * G[0][2];
+    return alpha > 1.0e-10 ? Q[IRHO] * o.ph.smagorinsky_Cs * std::sqrt(std::fabs(Bbeta) / alpha) : 0.0;
+}
+
 // LESModels.f90:256-305 (Smagorinsky_ComputeViscosity) with LESModel_ComputeWallEffect (:189-203); no wall model is the default (:162-165)
 inline double SmagorinskyViscosity(const Oracle& o, double delta, double dWall, const double* Q, const double* Q_x, const double* Q_y, const double* Q_z) {
+    if (o.ph.les == H3D_LES_WALE) return WaleViscosity(o, delta, Q, Q_x, Q_y, Q_z);        // LESModel % ComputeViscosity is polymorphic
+    if (o.ph.les == H3D_LES_VREMAN) return VremanViscosity(o, delta, Q, Q_x, Q_y, Q_z);
     double U_x[3], U_y[3], U_z[3], S[3][3];
     getVelocityGradients(o, Q, Q_x, Q_y, Q_z, U_x, U_y, U_z);
     for (int i = 0; i < 3; ++i) { S[i][0] = U_x[i]; S[i][1] = U_y[i]; S[i][2] = U_z[i]; }
@@ -1190,11 +1230,11 @@ void computeQDot(Oracle& o, double time) {
 #pragma omp parallel for schedule(static)
         for (int e = 0; e < o.nElem; ++e) {
             double delta = 0.0;
-            if (o.ph.les == H3D_LES_SMAGORINSKY) delta = std::pow(o.volume[e] / (double)(n * n * n), 1.0 / 3.0);
+            if (o.ph.les != H3D_LES_NONE) delta = std::pow(o.volume[e] / (double)(n * n * n), 1.0 / 3.0);
             for (int q = 0; q < n3; ++q) {
                 size_t g = (size_t)e * n3 + q;
                 get_laminar_mu_kappa(o, &o.Q[5 * g], o.mu[2 * g], o.mu[2 * g + 1]);
-                if (o.ph.les == H3D_LES_SMAGORINSKY) {
+                if (o.ph.les != H3D_LES_NONE) {
                     double mut = SmagorinskyViscosity(o, delta, o.dWall.empty() ? 0.0 : o.dWall[g], &o.Q[5 * g], &o.Ux[5 * g], &o.Uy[5 * g], &o.Uz[5 * g]);
                     o.mu[2 * g] = o.mu[2 * g] + mut; o.mu[2 * g + 1] = o.mu[2 * g + 1] + mut * o.ph.mu_to_kappa;
                 }
@@ -1205,11 +1245,11 @@ void computeQDot(Oracle& o, double time) {
         for (int f = 0; f < o.nFace; ++f) {
             const int sides = o.faceType[f] == H3D_FACE_INTERIOR ? 2 : 1;
             double delta = 0.0;
-            if (o.ph.les == H3D_LES_SMAGORINSKY) delta = std::sqrt(o.fSurface[f] / (double)(n * n));
+            if (o.ph.les != H3D_LES_NONE) delta = std::sqrt(o.fSurface[f] / (double)(n * n));
             for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int s = 0; s < sides; ++s) {
                 size_t g = ix.fnode(f, s, i, j);
                 get_laminar_mu_kappa(o, &o.fQ[5 * g], o.fmu[2 * g], o.fmu[2 * g + 1]);
-                if (o.ph.les == H3D_LES_SMAGORINSKY) {
+                if (o.ph.les != H3D_LES_NONE) {
                     double mut = SmagorinskyViscosity(o, delta, o.fdWall.empty() ? 0.0 : o.fdWall[(size_t)f * n * n + j * n + i], &o.fQ[5 * g], &o.fUx[5 * g], &o.fUy[5 * g], &o.fUz[5 * g]);
                     o.fmu[2 * g] = o.fmu[2 * g] + mut; o.fmu[2 * g + 1] = o.fmu[2 * g + 1] + mut * o.ph.mu_to_kappa;
                 }

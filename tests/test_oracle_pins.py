@@ -143,6 +143,25 @@ def test_k5b_cylinder_smagorinsky_100_steps():
 
 
 @needs_cylinder_mesh
+@pytest.mark.parametrize("model", ["WALE", "Vreman"])
+def test_k5e_cylinder_wale_and_vreman_100_steps(model):
+    """test/NavierStokes/CylinderWALE and CylinderVreman (the Cylinder case with LES model = Wale / Vreman, default intensities
+    0.325 / 0.07): residuals (tolerance 1e-7), cd, cl, wake_u (1e-11) from SETUP/ProblemFile.f90:535-590.  Pins
+    WALE_ComputeViscosity and Vreman_ComputeViscosity (LESModels.f90:358-546) at elements and faces."""
+    res, cd0, cl0, wu0 = {
+        "WALE": ([7.9687618041712476, 16.312135941662717, 0.2211855539938163, 21.313216389082029, 218.00956664214917],
+                 3.4701284621010650E+01, -3.5491030364454E-04, 9.375821230506176E-09),
+        "Vreman": ([8.74266124458872, 17.4701104368444, 0.18963568534174, 24.0324616446032, 238.729734578169],
+                   34.5428177831554, -4.7999091236761160E-04, 1.0883014687531778E-08)}[model]
+    got, cd, cl, wake_u = _cylinder_100_steps(les=model)
+    print("K5e", model, "rel diff", np.abs((got - np.array(res)) / np.array(res)).max(), "cd", cd - cd0, "cl", cl - cl0, "wake_u", wake_u - wu0)
+    assert np.abs(got - np.array(res)).max() < 1.0e-7
+    assert abs(cd - cd0) < 1.0e-11 * 35.0
+    assert abs(cl - cl0) < 1.0e-11
+    assert abs(wake_u - wu0) < 1.0e-11
+
+
+@needs_cylinder_mesh
 def test_k5c_cylinder_ducros_standard_roe_100_steps():
     """test/NavierStokes/CylinderDucros (split-form + Ducros average, Standard Roe with lambda stabilization 0.9, BR1;
     split-form forces Gauss-Lobatto nodes): residuals, cd, cl, wake_u and the 1e-11 tolerance from
