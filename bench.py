@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--riemann", default="roe")
     ap.add_argument("--nodes", default="gauss", choices=["gauss", "gauss-lobatto"])
     ap.add_argument("--viscous", default="BR1", choices=["BR1", "BR2", "IP"])
-    ap.add_argument("--les", default="none", choices=["none", "smagorinsky"])
+    ap.add_argument("--les", default="none", choices=["none", "smagorinsky", "wale", "vreman"])
     ap.add_argument("--gradient-variables", default="State", choices=["State", "Entropy", "Energy"])
     return ap.parse_args()
 
@@ -143,7 +143,7 @@ def main_b200(args):
         and args.gradient_variables == "State" and args.les == "none"
     scheme = "%s, %s%s+%s" % (args.flow, "StandardDG" if args.inviscid == "standard" else "SplitDG-" + args.averaging,
                               "" if euler else "+" + args.viscous + ("" if args.gradient_variables == "State" else "(" + args.gradient_variables + " variables)")
-                              + ("" if args.les == "none" else "+Smagorinsky"), args.riemann)
+                              + ("" if args.les == "none" else "+LES-" + args.les), args.riemann)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

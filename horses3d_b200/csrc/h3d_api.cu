@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_integrals2(DevMesh m, Phys 
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[(size_t)q * nn + t]; gy[q] = m.Uy[(size_t)q * nn + t]; gz[q] = m.Uz[(size_t)q * nn + t]; }
             laminar_mu_kappa(ph, Q, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) {
+            if (ph.les != H3D_LES_NONE) {
                 const double mut = smagorinsky<true>(ph, m.lesDelta[t / N3], ph.wallModel ? m.dWall[t] : 0.0, Q, gx, gy, gz);
                 mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa;
             }
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_red_ke_balance(DevMesh m, Phys 
         const double corr = 0.5 * (Q[1] * (Mgp[0] - gMp[0]) + Q[2] * (Mgp[1] - gMp[1]) + Q[3] * (Mgp[2] - gMp[2])) * inv_rho;
         double F[5][3], mu, kappa;
         laminar_mu_kappa(ph, Q, mu, kappa);
-        if (ph.les == H3D_LES_SMAGORINSKY) {
+        if (ph.les != H3D_LES_NONE) {
             const double mut = smagorinsky<true>(ph, m.lesDelta[t / N3], ph.wallModel ? m.dWall[t] : 0.0, Q, gx, gy, gz);
             mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa;
         }
@@ -871,7 +871,8 @@ int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
     if (p->gradientVariables < H3D_GRADVARS_STATE || p->gradientVariables > H3D_GRADVARS_ENERGY) { h->err = "Gradient variables are not currently implemented."; return 1; }
     q.viscous = p->flowIsNavierStokes ? p->viscous : H3D_VISCOUS_BR1; q.ipVariant = p->ipVariant; q.eta = p->penaltyParameter;
     q.gradVars = p->flowIsNavierStokes ? p->gradientVariables : H3D_GRADVARS_STATE;
-    h->genGrad = q.gradVars != H3D_GRADVARS_STATE;
+    if (p->les < H3D_LES_NONE || p->les > H3D_LES_VREMAN) { h->err = "LES model not recognized."; return 1; }
+    h->genGrad = q.gradVars != H3D_GRADVARS_STATE || p->les > H3D_LES_SMAGORINSKY;   // WALE / Vreman live in the general instantiations
     // anything outside the base set runs in the general instantiations so that it costs the headline kernels nothing
     h->extPhysics = p->riemann > H3D_RIEMANN_CENTRAL || p->averaging > H3D_AVG_PIROZZOLI || h->genGrad ||
                     (p->inviscid == H3D_SPLIT_DG && p->averaging == H3D_AVG_STANDARD);   // k_volume<n,1> stages primitives: KG / Pirozzoli only

@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(128, EXT ? 1 : 4) k_riemann(DevMesh m, Phys ph
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + q) * fs]; }
             laminar_mu_kappa(ph, QL, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            if (ph.les != H3D_LES_NONE) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux<EXT>(ph, QL, gx, gy, gz, mu, 0.0, kappa, F);
 #pragma unroll
             for (int q = 0; q < 5; ++q) { visc[q] = F[q][0] * nh[0] + F[q][1] * nh[1] + F[q][2] * nh[2]; }
@@ -616,12 +616,12 @@ __global__ void __launch_bounds__(128, EXT ? 1 : 4) k_riemann(DevMesh m, Phys ph
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + q) * fs]; }
             laminar_mu_kappa(ph, QL, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            if (ph.les != H3D_LES_NONE) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux<EXT>(ph, QL, gx, gy, gz, mu, 0.0, kappa, FL);
 #pragma unroll
             for (int q = 0; q < 5; ++q) { gx[q] = fU[(size_t)(0 * 10 + 5 + q) * fs]; gy[q] = fU[(size_t)(1 * 10 + 5 + q) * fs]; gz[q] = fU[(size_t)(2 * 10 + 5 + q) * fs]; }
             laminar_mu_kappa(ph, QR, mu, kappa);
-            if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QR, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+            if (ph.les != H3D_LES_NONE) { const double mut = smagorinsky<EXT>(ph, m.fDelta[f], ph.wallModel ? m.fDWall[fo] : 0.0, QR, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
             viscous_flux<EXT>(ph, QR, gx, gy, gz, mu, 0.0, kappa, FR);
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                             for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[q * es + go]; gy[q] = m.Uy[q * es + go]; gz[q] = m.Uz[q * es + go]; }
                         }
                         laminar_mu_kappa(ph, Qk[r], mu, kappa);
-                        if (ph.les == H3D_LES_SMAGORINSKY) { const double mut = smagorinsky<GV>(ph, m.lesDelta[e], ph.wallModel ? m.dWall[go] : 0.0, Qk[r], gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+                        if (ph.les != H3D_LES_NONE) { const double mut = smagorinsky<GV>(ph, m.lesDelta[e], ph.wallModel ? m.dWall[go] : 0.0, Qk[r], gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
                         viscous_flux<GV>(ph, Qk[r], gx, gy, gz, mu, 0.0, kappa, F);
 #pragma unroll
                         for (int q = 0; q < 5; ++q)

@@ -119,10 +119,65 @@ __device__ __forceinline__ void stress_velocity_gradients(const Phys& ph, const 
 
 // libs/physics/common/LESModels.f90:256-305 Smagorinsky: mu_t = rho LS^2 sqrt(2 S:S), S summed column by column;
 // LS = Cs delta, limited to 0.4 dWall by the linear wall model (LESModel_ComputeWallEffect, :189-203)
+// WALE_ComputeViscosity (LESModels.f90:358-435) and Vreman_ComputeViscosity (:487-546); only in the general instantiations
+__device__ __noinline__ double wale_vreman(const Phys& ph, double delta, const double Q[5], const double ux[3], const double uy[3], const double uz[3]) {
+    const double gradV[3][3] = {{ux[0], ux[1], ux[2]}, {uy[0], uy[1], uy[2]}, {uz[0], uz[1], uz[2]}};
+    if (ph.les == H3D_LES_WALE) {
+        double S[3][3], g2[3][3], Sd[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                S[i][j] = 0.5 * (gradV[i][j] + gradV[j][i]);
+                g2[i][j] = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g2[i][j] = g2[i][j] + gradV[i][k] * gradV[k][j];
+            }
+        const double divV2 = g2[0][0] + g2[1][1] + g2[2][2];
+        double normS = 0.0, normSd = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) normS = normS + S[i][j] * S[i][j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Sd[i][j] = 0.5 * (g2[i][j] + g2[j][i]);
+        Sd[0][0] = Sd[0][0] - 1.0 / 3.0 * divV2; Sd[1][1] = Sd[1][1] - 1.0 / 3.0 * divV2; Sd[2][2] = Sd[2][2] - 1.0 / 3.0 * divV2;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) normSd = normSd + Sd[i][j] * Sd[i][j];
+        const double LS = ph.Cs * delta;
+        double mu = Q[0] * pow2(LS) * (pow(normSd, 3.0 / 2.0) / (pow(normS, 5.0 / 2.0) + pow(normSd, 5.0 / 4.0)));
+        if (normS < 1.0e-8 && normSd < 1.0e-8) mu = 0.0;
+        return mu;
+    }
+    const double delta2 = delta * delta;
+    double G[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            G[i][j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) G[i][j] = G[i][j] + (gradV[i][k] * gradV[j][k] * delta2);
+        }
+    double alpha = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) alpha = alpha + gradV[i][j] * gradV[i][j];
+    const double Bbeta = G[0][0] * G[1][1] + G[1][1] * G[2][2] + G[2][2] * G[0][0] - G[0][1] * G[0][1] - G[1][2] * G[1][2] - G[0][2] * G[0][2];
+    return alpha > 1.0e-10 ? Q[0] * ph.Cs * sqrt(fabs(Bbeta) / alpha) : 0.0;
+}
+
+// LESModel % ComputeViscosity: Smagorinsky everywhere, WALE and Vreman in the general (GV) instantiations
 template <bool GV = false>
 __device__ __forceinline__ double smagorinsky(const Phys& ph, double delta, double dWall, const double Q[5], const double Qx[5], const double Qy[5], const double Qz[5]) {
     double ux[3], uy[3], uz[3];
     velocity_gradients_gv<GV>(ph, Q, Qx, Qy, Qz, ux, uy, uz);
+    if (GV && ph.les != H3D_LES_SMAGORINSKY) return wale_vreman(ph, delta, Q, ux, uy, uz);
     // S(i,j) = 1/2 (column j of grad u + row contribution), built exactly as the reference does
     const double s00 = 0.5 * (ux[0] + ux[0]), s10 = 0.5 * (ux[1] + uy[0]), s20 = 0.5 * (ux[2] + uz[0]);
     const double s01 = 0.5 * (uy[0] + ux[1]), s11 = 0.5 * (uy[1] + uy[1]), s21 = 0.5 * (uy[2] + uz[1]);

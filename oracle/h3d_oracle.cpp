@@ -9,8 +9,8 @@
 //
 //  Parity pins (tests/test_oracle_pins.py): this restatement reproduces, at the reference's own
 //  tolerances, the regression values of its test cases Components/NodalStorage (K6), NavierStokes/TaylorGreen (K1),
-//  Euler/TaylorGreenKEPEC (K2), NavierStokes/Convergence (K3, P=7), Euler/BoxAroundCirclePirozzoli (K4, 1000 steps; the force
-//  monitor to 5e-10 where the reference asserts 1e-10), NavierStokes/Cylinder and CylinderSmagorinsky (K5, K5b),
+//  Euler/TaylorGreenKEPEC (K2), NavierStokes/Convergence (K3, P=7), Euler/BoxAroundCircle and BoxAroundCirclePirozzoli (K4b, K4, 1000 steps; the
+//  force monitor of the latter to 5e-10 where the reference asserts 1e-10), Euler/UniformFlow (K12, iterations to tolerance), NavierStokes/Cylinder, CylinderSmagorinsky, CylinderWALE and CylinderVreman (K5, K5b, K5e),
 //  CylinderDucros and CylinderChandrasekarRoe (K5c, K5d), CylinderBR2 and CylinderIP (K7, K8), TaylorGreenKEP_BR2 and
 //  TaylorGreenKEPEC_IP (K9), Convergence_energy and Convergence_entropy (K10, P=7), EnergyConservingTest and
 //  EntropyConservingTest (K11).  The reference itself cannot be built in this container (no Fortran compiler), so there is

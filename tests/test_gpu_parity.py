@@ -26,7 +26,9 @@ TOL_ENTROPY = 1.0e-12
 
 
 def tol_of(kw):
-    return TOL_ENTROPY if kw.get("gradient_variables", "State").lower() == "entropy" else TOL_QDOT
+    # the same holds for WALE, which takes three real powers per node (pow differs in the last bits between CUDA and glibc)
+    loose = kw.get("gradient_variables", "State").lower() == "entropy" or kw.get("les", "none").lower() == "wale"
+    return TOL_ENTROPY if loose else TOL_QDOT
 
 
 def run_pair(gpu_api_cls, mesh, phys, ic=perturbed_tgv):
@@ -115,6 +117,9 @@ BC_CASES = [
     (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="BR2")),
     (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP", les="smagorinsky")),
     (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP")),
+    (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, les="wale")),
+    (2, 7, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, les="vreman")),
+    (3, 4, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="pirozzoli", les="vreman", gradient_variables="Energy")),
     (3, 3, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Energy")),
     (3, 5, GAUSSLOBATTO, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="chandrasekar", riemann="central", gradient_variables="Entropy")),
     (3, 4, GAUSS, 0.1, True, dict(flow="NS", mach=0.3, reynolds=200.0, gradient_variables="Entropy", les="smagorinsky")),
