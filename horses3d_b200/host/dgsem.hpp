@@ -70,7 +70,7 @@ struct Backend {
 
 struct PhysicsOptions {
     std::string flow = "NS", inviscid = "standard", riemann = "roe", averaging = "standard", viscous = "BR1", gradientVariables = "state", les = "none";
-    double mach = 0.08, reynolds = 1600.0, prandtl = 0.72, lambdaStab = 1.0, penalty = -1.0, smagorinskyCs = 0.2;
+    double mach = 0.08, reynolds = 1600.0, prandtl = 0.72, lambdaStab = 1.0, penalty = -1.0, smagorinskyCs = -1.0;
     int ipVariant = -1, lesWallModel = 0;
 };
 
@@ -90,7 +90,7 @@ inline H3dPhysics makePhysics(const PhysicsOptions& o) {
         if (o.reynolds != 0.0) { p.mu = 1.0 / o.reynolds; p.kappa = 1.0 / (gm1 * (o.mach * o.mach) * o.reynolds * o.prandtl); }   // :240-243
         p.mu_to_kappa = 1.0 / (gm1 * (o.mach * o.mach) * o.prandtl);                                                           // :250
     }
-    p.les = lookup("LES model", o.les, {{"none", H3D_LES_NONE}, {"smagorinsky", H3D_LES_SMAGORINSKY}});
+    p.les = lookup("LES model", o.les, {{"none", H3D_LES_NONE}, {"smagorinsky", H3D_LES_SMAGORINSKY}, {"wale", H3D_LES_WALE}, {"vreman", H3D_LES_VREMAN}});
     if (p.les != H3D_LES_NONE) ns = true;                             // :405-414
     p.flowIsNavierStokes = ns ? 1 : 0; p.computeGradients = ns ? 1 : 0;
     p.gammaM2 = gamma * (o.mach * o.mach);                            // :285
@@ -108,7 +108,9 @@ inline H3dPhysics makePhysics(const PhysicsOptions& o) {
     p.ipVariant = o.ipVariant;
     p.gradientVariables = ns ? lookup("gradient variables", o.gradientVariables, {{"state", H3D_GRADVARS_STATE}, {"entropy", H3D_GRADVARS_ENTROPY},
                                       {"energy", H3D_GRADVARS_ENERGY}}) : H3D_GRADVARS_STATE;
-    p.smagorinsky_Cs = o.smagorinskyCs; p.les_wall_model = o.lesWallModel;
+    // "LES model intensity" defaults: Smagorinsky 0.2, WALE 0.325, Vreman 0.07 (LESModels.f90:233-254, 337-356, 466-485)
+    p.smagorinsky_Cs = o.smagorinskyCs >= 0.0 ? o.smagorinskyCs : (p.les == H3D_LES_WALE ? 0.325 : (p.les == H3D_LES_VREMAN ? 0.07 : 0.2));
+    p.les_wall_model = o.lesWallModel;
     return p;
 }
 

@@ -58,6 +58,16 @@ def test_cpp_driver_reproduces_the_cylinder_regression_with_the_oracle_backend()
     assert f["iter"] == 100 and np.abs((f["residuals"] - res) / res).max() < 1.0e-11
 
 
+@pytest.mark.skipif(not os.path.exists(CYLINDER_MESH), reason="reference test mesh not available on this machine")
+def test_cpp_driver_reproduces_the_cylinder_wale_regression_with_the_oracle_backend():
+    """test/NavierStokes/CylinderWALE through the C++ driver (LES model and its default intensity chosen in makePhysics)."""
+    r = run_driver("--lib", build.build_oracle(), "--prefix", "orc_", "--mesh", CYLINDER_MESH, "--order", 3, "--steps", 100, "--cfl", 0.3, "--dcfl", 0.3,
+                   "--mach", 0.3, "--reynolds", 200, "--aoa-phi", 90, "--ic", "uniform", "--les", "wale", "--bc", "innercylinder:noslipwall",
+                   "--bc", "bottom:freeslipwall", "--bc", "top:freeslipwall", "--bc", "back:inflow", "--bc", "left:inflow", "--bc", "front:inflow", "--bc", "right:outflow")
+    res = np.array([7.9687618041712476, 16.312135941662717, 0.2211855539938163, 21.313216389082029, 218.00956664214917])
+    assert np.abs(final_line(r)["residuals"] - res).max() < 1.0e-7
+
+
 def test_cpp_driver_fails_loudly_without_a_device_or_with_bad_options():
     import torch
     r = run_driver("--lib", "/nonexistent/libh3dgpu.so", check=False)
