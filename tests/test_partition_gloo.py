@@ -90,3 +90,53 @@ def test_partition_is_balanced_and_complete():
         part = g.partition(4, method)
         cnt = np.bincount(part, minlength=4)
         assert cnt.sum() == g.nElem and cnt.min() > 0.8 * g.nElem / 4
+
+
+def _worker_face_h(rank, world, port, result):
+    """CommunicateMPIFaceMinimumDistance (HexMesh.f90:3059-3145) over gloo: each rank sends the h of its MPI faces (its own
+    element only), takes the minimum with the neighbour's and must land on the single-domain value of that face."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = HostMesh.box(4, amp=0.1, bFaceOrder=2, shuffle=True, seed=3).connect()
+        part = g.partition(world, "metis")
+        g.geometry(3, GAUSS)
+        h_global = g.array("faceH").copy()
+        m = g.extract(part, rank).geometry(3, GAUSS)                  # geometry rebuilt from the local elements
+        inh = g.extract(part, rank, inherit_geometry=True)            # geometry copied from the global mesh
+        gf = m.array("globalFace").copy()
+        h_loc = m.array("faceH").copy()
+        ranks, counts, faces = m.array("haloRank").copy(), m.array("haloCount").copy(), m.array("haloFace").copy()
+        ok = np.allclose(inh.array("faceH"), h_global[inh.array("globalFace")], rtol=0, atol=0)
+        interior = m.array("faceType") != 3
+        ok = ok and np.allclose(h_loc[interior], h_global[gf[interior]], rtol=1e-12)
+        off = 0
+        for nb, cnt in zip(ranks, counts):
+            ids = faces[off:off + cnt]
+            mine = torch.from_numpy(h_loc[ids].copy()); theirs = torch.empty_like(mine)
+            for r in [dist.isend(mine, int(nb)), dist.irecv(theirs, int(nb))]:
+                r.wait()
+            h_min = np.minimum(mine.numpy(), theirs.numpy())
+            ok = ok and bool((h_loc[ids] >= h_global[gf[ids]] * (1 - 1e-12)).all())          # one element only: never smaller
+            ok = ok and np.allclose(h_min, h_global[gf[ids]], rtol=1e-11)
+            off += cnt
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            result.put(int(flag.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mpi_face_minimum_distance_matches_the_single_domain_value():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 17
+    procs = [ctx.Process(target=_worker_face_h, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1
