@@ -21,6 +21,7 @@
 
 #include "h3d_physics.cuh"
 #include "h3d_tma.cuh"
+#include "h3d_mma.cuh"
 
 namespace h3d {
 
@@ -316,9 +317,10 @@ __device__ __forceinline__ void grad_iface_store(const DevMesh& m, const Phys& p
     }
 }
 
-template <int n, bool TMA, bool VISC = false>
+template <int n, bool TMA, bool VISC = false, bool MMA = false>
 __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh m, Phys ph, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
+    static_assert(!MMA || (n == 8 && TMA && !VISC && C::EPB == 1 && C::NPT == 1), "the DMMA contraction is written for the staged n = 8 BR1 kernel");
     constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;                  // nodes of one tile
     constexpr int UW = TMA ? N3 : NS;              // per-field stride of the state in shared memory
@@ -425,6 +427,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
             mbar_wait(bar, parity); parity ^= 1;
         }
         __syncthreads();
+        if constexpr (MMA) mma_gradient_contract<NT / 32, TN3, NS>(sU, sG, sDT);   // U_xi, U_eta, U_zeta of the 5 variables -> sG
         double g[NPT][15];
         if (active) {
 #pragma unroll
@@ -437,14 +440,20 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                     const double* sUe = TMA ? sU + le * N3 : sU + le * 5 * NS;
                     constexpr int QS = TMA ? TN3 : NS;
                     const int bx = (k * n + j) * ULD, by = (k * n) * ULD + i, bz = j * ULD + i;
+                    if (MMA) {
+                        const int p = C::pidx(node);
 #pragma unroll
-                    for (int l = 0; l < n; ++l) {
-                        const double dx = sDT[l * n + i], dy = sDT[l * n + j], dz = sDT[l * n + k];
+                        for (int q = 0; q < 5; ++q) { Uxi[q] = sG[q * NS + p]; Ueta[q] = sG[(5 + q) * NS + p]; Uzeta[q] = sG[(10 + q) * NS + p]; }
+                    } else {
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            Uxi[q] = Uxi[q] + sUe[q * QS + bx + l] * dx;
-                            Ueta[q] = Ueta[q] + sUe[q * QS + by + l * ULD] * dy;
-                            Uzeta[q] = Uzeta[q] + sUe[q * QS + bz + l * n * ULD] * dz;
+                        for (int l = 0; l < n; ++l) {
+                            const double dx = sDT[l * n + i], dy = sDT[l * n + j], dz = sDT[l * n + k];
+#pragma unroll
+                            for (int q = 0; q < 5; ++q) {
+                                Uxi[q] = Uxi[q] + sUe[q * QS + bx + l] * dx;
+                                Ueta[q] = Ueta[q] + sUe[q * QS + by + l * ULD] * dy;
+                                Uzeta[q] = Uzeta[q] + sUe[q * QS + bz + l * n * ULD] * dz;
+                            }
                         }
                     }
                     double ja[9], iJ;
@@ -663,10 +672,13 @@ struct VolSmem {
 };
 
 // MODE 0: StandardDG; 1: SplitDG with the Kennedy-Gruber / Pirozzoli two-point fluxes; 2: SplitDG with all averages
-template <int n, int MODE, bool TMA, bool GV = false>
+// MMA (n = 8, StandardDG, staged): the three contractions run on the FP64 tensor cores (h3d_mma.cuh); the flux fields are then
+// stored unpadded and swizzled, and the node-per-thread phase reads the contracted sums back from shared memory.
+template <int n, int MODE, bool TMA, bool GV = false, bool MMA = false>
 __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m, Phys ph, RkArgs rk, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
     constexpr bool SPLIT = MODE != 0, EXT = MODE == 2;
+    static_assert(!MMA || (n == 8 && MODE == 0 && TMA && C::EPB == 1 && C::NPT == 1), "the DMMA contraction is written for the staged n = 8 StandardDG kernel");
     constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;
     constexpr int FSI = (EPB * 30 * N2 + NT - 1) / NT;   // fStar items per thread
@@ -788,7 +800,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
             for (int r = 0; r < NPT; ++r) {
                 const int node = tn + r * TPE;
                 if (node < N3) {
-                    const int p = C::pidx(node);
+                    const int p = MMA ? swzF(node) : C::pidx(node);
                     const size_t go = (size_t)e * N3 + node;
                     const int so = le * N3 + node;
                     double ja[9];
@@ -834,7 +846,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                         for (int d = 0; d < 3; ++d) {
                             const double fc = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
                             if (SPLIT) FinvD[r][d * 5 + q] = fc;
-                            else sF[((le * 3 + d) * 5 + q) * NS + p] = fc - (ns ? fv[q][d] : 0.0);
+                            else sF[((le * 3 + d) * 5 + q) * (MMA ? N3 : NS) + p] = fc - (ns ? fv[q][d] : 0.0);
                         }
                     if (SPLIT) {
                         if (prim) {
@@ -860,6 +872,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
         }
         __syncthreads();
         if (TMA && threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issue(tile + gridDim.x);   // the staged inputs are consumed
+        if constexpr (MMA) mma_volume_contract<NT / 32>(sF, sHatDT);
         if (TMA) mbar_wait(bar + 1, parity ^ 1);   // J and G of this tile (parity was flipped after the first wait)
         if (active) {
 #pragma unroll
@@ -870,7 +883,10 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                     const size_t go = (size_t)e * N3 + node;
                     const int bx = (k * n + j) * NP, by = (k * n) * NP + i, bz = j * NP + i;
                     double vol[5] = {0, 0, 0, 0, 0};
-                    if (!SPLIT) {
+                    if (MMA) {
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) vol[q] = sF[q * N3 + swzR(node)];
+                    } else if (!SPLIT) {
                         const double* F1 = sF + ((le * 3 + 0) * 5) * NS + bx; const double* F2 = sF + ((le * 3 + 1) * 5) * NS + by; const double* F3 = sF + ((le * 3 + 2) * 5) * NS + bz;
 #pragma unroll
                         for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + i];

@@ -22,6 +22,9 @@
 #include <limits>
 #include <string>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/h3d_gpu.h"
 
@@ -1421,6 +1424,29 @@ void computeTimeDerivative(Oracle& o, double time) {
 //  C API (mirrors include/h3d_gpu.h with the prefix orc_)
 // ====================================================================================================
 extern "C" {
+
+// threads the OpenMP loops of the oracle really use (bench.py reports this as cpu_baseline.cores), and a setter for launchers
+// that pin OMP_NUM_THREADS=1 before the process starts (torchrun)
+int orc_num_threads() {
+#ifdef _OPENMP
+    int nt = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        nt = omp_get_num_threads();
+    }
+    return nt;
+#else
+    return 1;
+#endif
+}
+void orc_set_num_threads(int nt) {
+#ifdef _OPENMP
+    if (nt > 0) omp_set_num_threads(nt);
+#else
+    (void)nt;
+#endif
+}
 
 void* orc_create() { return new Oracle(); }
 int orc_create_handle(void** out, int, int, int, const void*) { *out = new Oracle(); return 0; }   // the signature of h3d_create
