@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "h3d_gpu.h"
-#include "h3d_kernels.cuh"
+#include "h3d_kernels2.cuh"
 
 using namespace h3d;
 
@@ -57,6 +57,7 @@ struct h3d_context {
     unsigned long long stateVersion = 1, intVersion[3] = {0, 0, 0}; double intCache[3][6];
     int storeQDotAlways = 0;
     int useTma = 1;      // persistent element kernels with bulk-async prefetch where KCfg<n>::TMA_OK
+    int useGen2 = 0;     // n = 8 StandardDG / BR1: second-generation kernels (256 threads, two CTAs per SM), h3d_kernels2.cuh
     int useMma = 0;      // n = 8 staged StandardDG / BR1 kernels: contractions on the FP64 tensor cores (DMMA); not bit-identical to the oracle
     int numSMs = 148;
     std::vector<std::pair<const void*, int>> occCache;
@@ -599,6 +600,12 @@ template <int n> int launchGradient(h3d_context* h, int e0, int e1, cudaStream_t
     using C = KCfg<n>;
     const int tiles = (e1 - e0 + C::EPB - 1) / C::EPB;
     if (h->ph.viscous != H3D_VISCOUS_BR1 || h->genGrad) k_gradient<n, false, true><<<tiles, C::NT, smemGradient<n, false, true>(), s>>>(h->m, h->ph, makeOps<n>(h), e0, e1);
+    else if (C::TMA_OK && h->useTma && h->useGen2 && n == 8) {
+        if constexpr (n == 8) {
+            if (h->useMma) k_gradient2<true><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient2<true>, 256, Grad2Smem::bytes)), 256, Grad2Smem::bytes, s>>>(h->m, h->ph, makeOps<8>(h), e0, e1);
+            else k_gradient2<false><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient2<false>, 256, Grad2Smem::bytes)), 256, Grad2Smem::bytes, s>>>(h->m, h->ph, makeOps<8>(h), e0, e1);
+        }
+    }
     else if (C::TMA_OK && h->useTma && h->useMma && n == 8) {
         if constexpr (n == 8) k_gradient<8, true, false, true><<<std::min(tiles, persistentGrid(h, (const void*)k_gradient<8, true, false, true>, C::NT, smemGradient<8, true>())), C::NT, smemGradient<8, true>(), s>>>(h->m, h->ph, makeOps<8>(h), e0, e1);
     }
@@ -629,7 +636,14 @@ template <int n> int launchVolume(h3d_context* h, const RkArgs& rk, int e0, int 
         if (tma && !ns) k_volume<n, 1, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, 1, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(true, false))), C::NT, smemVolume<n, C::TMA_OK>(true, false), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
         else k_volume<n, 1, false><<<tiles, C::NT, smemVolume<n, false>(true, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
     } else {
-        if (tma && h->useMma && n == 8) {
+        if (tma && h->useGen2 && n == 8) {
+            const int grid = std::min(tiles, h->useMma ? persistentGrid(h, (const void*)k_volume2<true>, 256, Vol2Smem::bytes) : persistentGrid(h, (const void*)k_volume2<false>, 256, Vol2Smem::bytes));
+            if constexpr (n == 8) {
+                if (h->useMma) k_volume2<true><<<grid, 256, Vol2Smem::bytes, s>>>(h->m, h->ph, rk, makeOps<8>(h), e0, e1);
+                else k_volume2<false><<<grid, 256, Vol2Smem::bytes, s>>>(h->m, h->ph, rk, makeOps<8>(h), e0, e1);
+            }
+        }
+        else if (tma && h->useMma && n == 8) {
             if constexpr (n == 8) k_volume<8, 0, true, false, true><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<8, 0, true, false, true>, C::NT, smemVolume<8, true>(false, ns))), C::NT, smemVolume<8, true>(false, ns), s>>>(h->m, h->ph, rk, makeOps<8>(h), e0, e1);
         }
         else if (tma) k_volume<n, 0, C::TMA_OK><<<std::min(tiles, persistentGrid(h, (const void*)k_volume<n, 0, C::TMA_OK>, C::NT, smemVolume<n, C::TMA_OK>(false, ns))), C::NT, smemVolume<n, C::TMA_OK>(false, ns), s>>>(h->m, h->ph, rk, makeOps<n>(h), e0, e1);
@@ -655,6 +669,10 @@ template <int n> int setAttrs(h3d_context* h) {
         CTX_CHECK(cudaFuncSetAttribute(k_volume<n, 1, C::TMA_OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<n, C::TMA_OK>(true, false)));
     }
     if constexpr (n == 8) {
+        CTX_CHECK(cudaFuncSetAttribute(k_gradient2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Grad2Smem::bytes));
+        CTX_CHECK(cudaFuncSetAttribute(k_gradient2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Grad2Smem::bytes));
+        CTX_CHECK(cudaFuncSetAttribute(k_volume2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Vol2Smem::bytes));
+        CTX_CHECK(cudaFuncSetAttribute(k_volume2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Vol2Smem::bytes));
         CTX_CHECK(cudaFuncSetAttribute(k_gradient<8, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemGradient<8, true>()));
         CTX_CHECK(cudaFuncSetAttribute(k_volume<8, 0, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemVolume<8, true>(false, true)));
     }
@@ -822,6 +840,7 @@ int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nc
     if (prop.major != 10) return fail(std::string("libh3dgpu is built for sm_100a only; device is ") + prop.name);
     h->numSMs = prop.multiProcessorCount;
     if (const char* ev = std::getenv("H3D_USE_MMA")) h->useMma = std::atoi(ev);
+    if (const char* ev = std::getenv("H3D_GEN2")) h->useGen2 = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_USE_TMA")) h->useTma = std::atoi(ev);   // experiments: H3D_USE_TMA=0 selects the plain-load kernels
     if (cudaStreamCreateWithFlags(&h->sCompute, cudaStreamNonBlocking) != cudaSuccess) return fail("stream creation failed");
     cudaStreamCreateWithFlags(&h->sComm, cudaStreamNonBlocking);
@@ -1529,6 +1548,7 @@ int h3d_set_option(h3d_handle h, const char* kv) {
     if (key == "profile_kernels") { h->profile = val; return 0; }
     if (key == "use_tma") { h->useTma = val; return 0; }
     if (key == "mma") { h->useMma = val; return 0; }
+    if (key == "gen2") { h->useGen2 = val; return 0; }
     h->err = "unknown option: " + key;
     return 1;
 }

@@ -681,6 +681,11 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
     static_assert(!MMA || (n == 8 && MODE == 0 && TMA && C::EPB == 1 && C::NPT == 1), "the DMMA contraction is written for the staged n = 8 StandardDG kernel");
     constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;
+    // Work fields (fluxes; SplitDG: state, metrics, sixth primitive) are stored UNPADDED, node = (k n + j) n + i: the lines the
+    // contraction reads are then broadcasts (xi, eta) or consecutive words (zeta), free of bank conflicts; rows padded to an
+    // odd length (round 1) cost the zeta lines a 3-way conflict and the whole phase twice the wavefronts
+    // (profiles/r2_d_gen2/regions_gen2_core.txt: 94 M wavefronts against 200 M).  Only the prolongation buffer sP is padded.
+    constexpr int WS = N3;
     constexpr int FSI = (EPB * 30 * N2 + NT - 1) / NT;   // fStar items per thread
     // MODE 1 stages HALVED primitives and metrics (two_point_flux_half).  Measured on B200, Euler Pirozzoli, volume kernel:
     // n=4 3.17 -> 3.11 ms, n=8 3.54 -> 3.35 ms, n=10 5.90 -> 5.66 ms, but n=6 3.23 -> 3.47 ms (three runs each): not at n=6.
@@ -695,18 +700,18 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
     const int nFlux = SPLIT ? (ns ? 15 : 0) : 15;
     double* sIn = smem;                                  // TMA: [nStaged][TN3]: Q 5, (Ux Uy Uz 15,) Ja 9
     double* sJG = smem + nStaged * TN3;                  // TMA: [6][TN3]: J, G 5 (second barrier: consumed after the contraction)
-    double* sF = sJG + (TMA ? 6 * TN3 : 0);              // [EPB][nFlux][NS]
-    double* sQ = sF + EPB * nFlux * NS;                  // SPLIT: [EPB][5][NS]
-    double* sJa = sQ + (SPLIT ? EPB * 5 * NS : 0);       // SPLIT: [EPB][9][NS]
-    double* sX = sJa + (SPLIT ? EPB * 9 * NS : 0);       // SPLIT: [EPB][NS] sixth per-node primitive (see two_point_flux_prim)
-    double* sFs = sX + (SPLIT ? EPB * NS : 0);           // [EPB][6][5][N2] fStar at element-trace nodes (signed)
+    double* sF = sJG + (TMA ? 6 * TN3 : 0);              // [EPB][nFlux][WS]
+    double* sQ = sF + EPB * nFlux * WS;                  // SPLIT: [EPB][5][WS]
+    double* sJa = sQ + (SPLIT ? EPB * 5 * WS : 0);       // SPLIT: [EPB][9][WS]
+    double* sX = sJa + (SPLIT ? EPB * 9 * WS : 0);       // SPLIT: [EPB][WS] sixth per-node primitive (see two_point_flux_prim)
+    double* sFs = sF + EPB * (nFlux + (SPLIT ? 15 : 0)) * NS;   // [EPB][6][5][N2] fStar at element-trace nodes (signed); behind the padded extent
     double* sHatDT = sFs + EPB * 6 * 5 * N2;             // [n][n]
     double* sSharpDT = sHatDT + N2;                      // [n][n]
     double* sB = sSharpDT + N2;                          // [2][n]
     constexpr int TABI = EPB * (6 * N2 + 8);             // ints of one face-table set: trace offsets [EPB][6][N2] + info [EPB][8]
     int* sTab = (int*)(sB + 2 * n);                      // TMA: two sets, the next tile's is prefetched by bulk copies
     uint64_t* bar = (uint64_t*)(((uintptr_t)(sTab + (TMA ? 2 : 1) * TABI) + 7) & ~(uintptr_t)7);   // bar[0]: flux inputs, bar[1]: J and G, bar[2..3]: face tables
-    double* sP = SPLIT ? sQ : sF;                        // prolongation buffer for the updated state [EPB][5][NS]
+    double* sP = SPLIT ? sQ : sF;                        // prolongation buffer for the updated state [EPB][5][NS] (padded rows; SplitDG: runs into sJa)
     const int le = threadIdx.x / TPE, tn = threadIdx.x % TPE;
     const size_t es = (size_t)m.nElem * N3, fs = (size_t)m.nFace * N2;
     const int nTiles = (eEnd - eBegin + EPB - 1) / EPB;
@@ -722,39 +727,38 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
         bulk_g2s(dst + EPB * 6 * N2, m.elemInfo + (size_t)e0 * 8, (uint32_t)(nLoc * 8 * sizeof(int)), bar + 2 + buf);
     };
     // (spreading these copies over the warps as k_gradient does costs this kernel 4 %: no warp waits for warp 0 here)
-    auto issue = [&](int tile) {   // thread 0: bulk copies of the tile's staged fields
+    // Warp 0 issues the bulk copies of a tile, lane c the copy of staged field c: one warp instruction instead of a loop of 29
+    // in thread 0 (which kept warp 0 ~1.8 k cycles behind the others at the next barrier, profiles/r2_d_gen2/regions_gen1_mma.txt)
+    auto issue = [&](int tile) {   // lanes of warp 0: bulk copies of the tile's staged fields
         const int e0 = eBegin + tile * EPB;
         const int nLoc = min(EPB, eEnd - e0);
         const uint32_t bytes = (uint32_t)(nLoc * N3 * sizeof(double));
         const size_t off = (size_t)e0 * N3;
-        mbar_arrive_expect_tx(bar, (uint32_t)nStaged * bytes);
-#pragma unroll 1
-        for (int c = 0; c < 5; ++c) bulk_g2s(sIn + c * TN3, m.Q + c * es + off, bytes, bar);
-        if (ns) {
-#pragma unroll 1
-            for (int c = 0; c < 5; ++c) {
-                bulk_g2s(sIn + (5 + c) * TN3, m.Ux + c * es + off, bytes, bar);
-                bulk_g2s(sIn + (10 + c) * TN3, m.Uy + c * es + off, bytes, bar);
-                bulk_g2s(sIn + (15 + c) * TN3, m.Uz + c * es + off, bytes, bar);
-            }
+        const int c = threadIdx.x;
+        if (c == 0) mbar_arrive_expect_tx(bar, (uint32_t)nStaged * bytes);
+        __syncwarp();
+        if (c < nStaged) {
+            const double* src;
+            if (c < 5) src = m.Q + c * es;
+            else if (c >= jaOff) src = m.Ja + (c - jaOff) * es;
+            else { const int g = c - 5; src = (g < 5 ? m.Ux : (g < 10 ? m.Uy : m.Uz)) + (g % 5) * es; }
+            bulk_g2s(sIn + c * TN3, src + off, bytes, bar);
         }
-#pragma unroll 1
-        for (int c = 0; c < 9; ++c) bulk_g2s(sIn + (jaOff + c) * TN3, m.Ja + c * es + off, bytes, bar);
     };
-    auto issueLate = [&](int tile) {   // thread 0: J and G of the tile (read after the contraction)
+    auto issueLate = [&](int tile) {   // lanes of warp 0: J and G of the tile (read after the contraction)
         const int e0 = eBegin + tile * EPB;
         const int nLoc = min(EPB, eEnd - e0);
         const uint32_t bytes = (uint32_t)(nLoc * N3 * sizeof(double));
         const size_t off = (size_t)e0 * N3;
-        mbar_arrive_expect_tx(bar + 1, 6 * bytes);
-        bulk_g2s(sJG, m.J + off, bytes, bar + 1);
-#pragma unroll 1
-        for (int c = 0; c < 5; ++c) bulk_g2s(sJG + (1 + c) * TN3, m.G + c * es + off, bytes, bar + 1);
+        const int c = threadIdx.x;
+        if (c == 0) mbar_arrive_expect_tx(bar + 1, 6 * bytes);
+        __syncwarp();
+        if (c < 6) bulk_g2s(sJG + c * TN3, (c == 0 ? m.J : m.G + (c - 1) * es) + off, bytes, bar + 1);
     };
     if (TMA) {
         if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); mbar_init(bar + 3, 1); fence_barrier_init(); }
         __syncthreads();
-        if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) { issueTab(blockIdx.x, 0); issue(blockIdx.x); issueLate(blockIdx.x); }
+        if (threadIdx.x < 32 && (int)blockIdx.x < nTiles) { if (threadIdx.x == 0) issueTab(blockIdx.x, 0); issue(blockIdx.x); issueLate(blockIdx.x); }
     }
     uint32_t parity = 0;
     int iter = 0;
@@ -800,7 +804,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
             for (int r = 0; r < NPT; ++r) {
                 const int node = tn + r * TPE;
                 if (node < N3) {
-                    const int p = MMA ? swzF(node) : C::pidx(node);
+                    const int p = MMA ? swzF(node) : node;
                     const size_t go = (size_t)e * N3 + node;
                     const int so = le * N3 + node;
                     double ja[9];
@@ -836,7 +840,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 #pragma unroll
                             for (int d = 0; d < 3; ++d) {
                                 fv[q][d] = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
-                                if (SPLIT) sF[((le * 3 + d) * 5 + q) * NS + p] = fv[q][d];
+                                if (SPLIT) sF[((le * 3 + d) * 5 + q) * WS + p] = fv[q][d];
                             }
                     }
                     euler_flux(ph, Qk[r], F);
@@ -846,7 +850,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                         for (int d = 0; d < 3; ++d) {
                             const double fc = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
                             if (SPLIT) FinvD[r][d * 5 + q] = fc;
-                            else sF[((le * 3 + d) * 5 + q) * (MMA ? N3 : NS) + p] = fc - (ns ? fv[q][d] : 0.0);
+                            else sF[((le * 3 + d) * 5 + q) * WS + p] = fc - (ns ? fv[q][d] : 0.0);
                         }
                     if (SPLIT) {
                         if (prim) {
@@ -855,12 +859,12 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 #pragma unroll
                                 for (int q = 0; q < 6; ++q) Pk[r][q] = 0.5 * Pk[r][q];
                             }
-                            sX[le * NS + p] = Pk[r][5];
+                            sX[le * WS + p] = Pk[r][5];
                         }
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) sQ[(le * 5 + q) * NS + p] = prim ? Pk[r][q] : Qk[r][q];
+                        for (int q = 0; q < 5; ++q) sQ[(le * 5 + q) * WS + p] = prim ? Pk[r][q] : Qk[r][q];
 #pragma unroll
-                        for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * NS + p] = HALF ? 0.5 * ja[c] : ja[c];
+                        for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * WS + p] = HALF ? 0.5 * ja[c] : ja[c];
                     }
                 }
             }
@@ -871,7 +875,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
             if (o < nLocal * 30 * N2) sFs[o] = (fsg[it] & 1) ? -fsv[it] : fsv[it];     // o = ((l2*6 + lf)*5 + q)*N2 + ab
         }
         __syncthreads();
-        if (TMA && threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issue(tile + gridDim.x);   // the staged inputs are consumed
+        if (TMA && threadIdx.x < 32 && tile + (int)gridDim.x < nTiles) issue(tile + gridDim.x);   // the staged inputs are consumed
         if constexpr (MMA) mma_volume_contract<NT / 32>(sF, sHatDT);
         if (TMA) mbar_wait(bar + 1, parity ^ 1);   // J and G of this tile (parity was flipped after the first wait)
         if (active) {
@@ -881,36 +885,36 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                 if (node < N3) {
                     const int i = node % n, j = (node / n) % n, k = node / N2;
                     const size_t go = (size_t)e * N3 + node;
-                    const int bx = (k * n + j) * NP, by = (k * n) * NP + i, bz = j * NP + i;
+                    const int bx = (k * n + j) * n, by = (k * n) * n + i, bz = j * n + i;
                     double vol[5] = {0, 0, 0, 0, 0};
                     if (MMA) {
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) vol[q] = sF[q * N3 + swzR(node)];
+                        for (int q = 0; q < 5; ++q) vol[q] = sF[q * WS + swzR(node)];
                     } else if (!SPLIT) {
-                        const double* F1 = sF + ((le * 3 + 0) * 5) * NS + bx; const double* F2 = sF + ((le * 3 + 1) * 5) * NS + by; const double* F3 = sF + ((le * 3 + 2) * 5) * NS + bz;
+                        const double* F1 = sF + ((le * 3 + 0) * 5) * WS + bx; const double* F2 = sF + ((le * 3 + 1) * 5) * WS + by; const double* F3 = sF + ((le * 3 + 2) * 5) * WS + bz;
 #pragma unroll
                         for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + i];
 #pragma unroll
-                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F1[q * NS + l]; }
+                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F1[q * WS + l]; }
 #pragma unroll
                         for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + j];
 #pragma unroll
-                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F2[q * NS + l * NP]; }
+                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F2[q * WS + l * n]; }
 #pragma unroll
                         for (int l = 0; l < n; ++l) { const double d = sHatDT[l * n + k];
 #pragma unroll
-                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F3[q * NS + l * n * NP]; }
+                            for (int q = 0; q < 5; ++q) vol[q] = vol[q] + d * F3[q * WS + l * N2]; }
                     } else {
-                        const double* sQe = sQ + le * 5 * NS; const double* sJe = sJa + le * 9 * NS; const double* sFe = sF + le * 15 * NS;
-                        const int p = C::pidx(node);
+                        const double* sQe = sQ + le * 5 * WS; const double* sJe = sJa + le * 9 * WS; const double* sFe = sF + le * 15 * WS;
+                        const int p = node;
 #pragma unroll
                         for (int d = 0; d < 3; ++d) {
                             const int me = d == 0 ? i : (d == 1 ? j : k);
                             const int ob = d == 0 ? bx : (d == 1 ? by : bz);
-                            const int ostr = d == 0 ? 1 : (d == 1 ? NP : n * NP);
+                            const int ostr = d == 0 ? 1 : (d == 1 ? n : N2);
                             double jaMe[3];
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) jaMe[c] = sJe[(3 * d + c) * NS + p];
+                            for (int c = 0; c < 3; ++c) jaMe[c] = sJe[(3 * d + c) * WS + p];
 #pragma unroll LU
                             for (int l = 0; l < n; ++l) {
                                 const int other = ob + l * ostr;
@@ -921,11 +925,11 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                                 } else {
                                     double Qo[6], jo[3];
 #pragma unroll
-                                    for (int q = 0; q < 5; ++q) Qo[q] = sQe[q * NS + other];
+                                    for (int q = 0; q < 5; ++q) Qo[q] = sQe[q * WS + other];
 #pragma unroll
-                                    for (int c = 0; c < 3; ++c) jo[c] = sJe[(3 * d + c) * NS + other];
+                                    for (int c = 0; c < 3; ++c) jo[c] = sJe[(3 * d + c) * WS + other];
                                     if (prim) {
-                                        Qo[5] = sX[le * NS + other];
+                                        Qo[5] = sX[le * WS + other];
                                         if (HALF) { if (l > me) two_point_flux_half(ph, Pk[r], Qo, jaMe, jo, fsvv); else two_point_flux_half(ph, Qo, Pk[r], jo, jaMe, fsvv); }
                                         else if (l > me) two_point_flux_prim<EXT>(ph, Pk[r], Qo, jaMe, jo, fsvv); else two_point_flux_prim<EXT>(ph, Qo, Pk[r], jo, jaMe, fsvv);
                                     } else {
@@ -935,7 +939,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                                 const double sd = sSharpDT[l * n + me], hd = sHatDT[l * n + me];
                                 if (ns) {
 #pragma unroll
-                                    for (int q = 0; q < 5; ++q) vol[q] = vol[q] + sd * fsvv[q] + hd * sFe[(d * 5 + q) * NS + other];
+                                    for (int q = 0; q < 5; ++q) vol[q] = vol[q] + sd * fsvv[q] + hd * sFe[(d * 5 + q) * WS + other];
                                 } else {
 #pragma unroll
                                     for (int q = 0; q < 5; ++q) vol[q] = vol[q] + sd * fsvv[q];
@@ -1004,7 +1008,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
             prolong_block<n, 5>(m, ops, sP, sTr, sInfo, m.fQ, nLocal);
         }
         __syncthreads();
-        if (TMA && threadIdx.x == 0 && tile + (int)gridDim.x < nTiles) issueLate(tile + gridDim.x);   // J/G buffer is free again
+        if (TMA && threadIdx.x < 32 && tile + (int)gridDim.x < nTiles) issueLate(tile + gridDim.x);   // J/G buffer is free again
     }
 }
 

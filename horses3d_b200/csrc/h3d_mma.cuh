@@ -72,8 +72,9 @@ __device__ __forceinline__ void mma_volume_contract(double* __restrict__ sF, con
 
 // Local gradient: G[(d*5 + q)][pidx(node)] = sum_l D(node_d, l) U_q(.. l ..) for d = xi, eta, zeta
 // (HexElement_ComputeLocalGradient, HexElementClass.f90:484-500).  sU: [5] fields of stride US, unpadded and unswizzled (staged by
-// bulk copies); sG: [15] fields of stride GS with rows padded to 9 doubles.  sDT[l*8 + i] = D(i,l).
-template <int NWARPS, int US, int GS>
+// bulk copies); sG: [15] fields of stride GS, rows padded to 9 doubles (PSWZ false) or in the pswz layout of h3d_kernels2.cuh.
+// sDT[l*8 + i] = D(i,l).
+template <int NWARPS, int US, int GS, bool PSWZ = false>
 __device__ __forceinline__ void mma_gradient_contract(const double* __restrict__ sU, double* __restrict__ sG, const double* __restrict__ sDT) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, a = lane & 3;
     const double bx0 = sDT[(2 * a) * 8 + g], bx1 = sDT[(2 * a + 1) * 8 + g];
@@ -98,8 +99,14 @@ __device__ __forceinline__ void mma_gradient_contract(const double* __restrict__
             dmma884(c0, c1, ay0, U[a * 64 + pl * 8 + g]);
             dmma884(c0, c1, ay1, U[(a + 4) * 64 + pl * 8 + g]);
         }
-        double* o = sG + (d * 5 + q) * GS + (node >> 3) * 9 + (node & 7);
-        o[0] = c0; o[1] = c1;
+        if (PSWZ) {   // node and node + 1 differ in bit 0 of i only: the swizzled positions are the two halves of one 16-byte pair
+            const int p = (node & ~63) | (((((node >> 3) & 7) ^ ((node >> 6) & 1))) << 3) | ((node & 7) ^ ((node >> 3) & 7));
+            double* o = sG + (d * 5 + q) * GS;
+            o[p] = c0; o[p ^ 1] = c1;
+        } else {
+            double* o = sG + (d * 5 + q) * GS + (node >> 3) * 9 + (node & 7);
+            o[0] = c0; o[1] = c1;
+        }
     }
     __syncthreads();
 }

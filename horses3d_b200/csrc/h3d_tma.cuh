@@ -35,4 +35,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "r"(smem_u32(bar)) : "memory");
 }
 
+// bulk prefetch of a contiguous, 16-byte aligned run into L2 (no shared-memory destination, no completion tracking): the plain
+// loads that follow find their lines in L2 instead of HBM
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 }  // namespace h3d
