@@ -7,9 +7,12 @@ explicit RK3.  A "step" is one RK3 time step (three residual evaluations + updat
   python bench.py --gpus N --steps K --warmup W            # this framework on N B200s
   python bench.py --impl reference --steps K --warmup W    # restated reference algorithm on the host cores
 
-Workload: N=1 -> configs[1]: 32^3 elements, P=7 (16.8 M DOF) on a curvilinear periodic box.
-          N>1 -> weak scaling, 32^3 elements per GPU: (64,32,32), (64,64,32), (64,64,64 = configs[3]) elements,
-                 partitioned element-wise (METIS_PartMeshDual, as the reference) with NCCL face exchange.
+Workload (default): STRONG scaling of BASELINE configs[3], the north star's target: the 64^3-element P=7 curvilinear periodic
+          box (134 M DOF, fits one B200) on N = 1, 2, 4, 8 GPUs, partitioned element-wise (METIS_PartMeshDual, as the
+          reference) with NCCL face exchange.  The per-GPU rate of the N=1 run is that of configs[1] (32^3, 16.8 M DOF)
+          within 2 % (profiles/r1_j_round_end): both are far larger than L2.
+          --weak : 32^3 elements per GPU ((32,32,32) = configs[1], (64,32,32), (64,64,32), (64,64,64)), the round-1 behaviour
+          --ne E : E^3 elements (strong) or E^3 elements per GPU (--weak); the configuration sweeps use it
 One JSON line is printed by rank 0.
 """
 import argparse
@@ -37,14 +40,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ne", type=int, default=32, help="elements per direction per GPU")
+    ap.add_argument("--ne", type=int, default=0, help="elements per direction: of the whole mesh (strong scaling, default 64) or per GPU (--weak, default 32)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --ne^3 elements per GPU instead of a fixed global mesh")
+    ap.add_argument("--no-self-check", action="store_true")
     ap.add_argument("--order", type=int, default=7)
     ap.add_argument("--amp", type=float, default=0.1, help="curvature amplitude of the mesh mapping")
     ap.add_argument("--partition", default="metis", choices=["metis", "block"])
     ap.add_argument("--dt", type=float, default=1.0e-4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ref-ne", type=int, default=8, help="elements per direction of the bounded CPU sample")
+    ap.add_argument("--ref-ne", type=int, default=16, help="elements per direction of the bounded CPU sample (16^3 P=7 = 2.1 M DOF: out of the host's L3)")
     # the other configurations of SURVEY 8d (C1 P=3, C3 Euler split-form sweeps); the defaults are the headline C2 / C4
     ap.add_argument("--flow", default="NS", choices=["NS", "Euler"])
     ap.add_argument("--inviscid", default="standard", choices=["standard", "split-form"])
@@ -85,12 +90,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
 
 
+def host_threads():
+    """All the cores this process may use (the affinity mask, not os.cpu_count(): containers and launchers restrict it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(args, steps, warmup):
-    """The restated reference algorithm (oracle, g++ -O2 -fopenmp, no FMA) on a bounded sample of the same workload."""
+    """The restated reference algorithm (oracle, g++ -O3 -fopenmp, no FMA) on a bounded sample of the same workload, on ALL host
+    cores: torchrun exports OMP_NUM_THREADS=1 to its workers, so the thread count is set through the OpenMP runtime of the
+    oracle library itself and the count REPORTED is the one its parallel regions really get (orc_num_threads)."""
     from horses3d_b200.dgsem import DGSem, taylor_green_ic
     from horses3d_b200.hostmesh import GAUSS, HostMesh
     from horses3d_b200.physics import make_physics
-    from oracle.oracle_api import OracleApi
+    from oracle.oracle_api import OracleApi, library
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())      # the host-side geometry (libh3dhost) reads it when it loads
+    library().orc_set_num_threads(host_threads())
     mesh = HostMesh.box(args.ref_ne, amp=args.amp, bFaceOrder=2).connect().geometry(args.order, GAUSS)
     sem = DGSem(OracleApi(), mesh, make_physics(flow="NS", mach=0.08, reynolds=1600.0, riemann="roe"))
     sem.set_initial_condition(taylor_green_ic)
@@ -102,7 +119,7 @@ def cpu_sample(args, steps, warmup):
     dt = time.perf_counter() - t0
     value = sem.NDOF * 3 * steps / dt
     sample = "TGV P=%d, %d^3 curvilinear elements (%d DOF), %d RK3 steps" % (args.order, args.ref_ne, sem.NDOF, steps)
-    return value, dt / steps * 1e3, os.cpu_count(), sample
+    return value, dt / steps * 1e3, int(library().orc_num_threads()), sample
 
 
 def main_reference(args):
@@ -114,10 +131,10 @@ def main_reference(args):
     line = {
         "impl": "reference", "metric": "DOF-updates/s (TGV P=%d explicit RK3, NS/BR1/Roe)" % args.order, "value": value, "unit": "DOF-updates/s",
         "tpdof_s": 1.0 / value, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Taylor-Green vortex Re=1600 M=0.08, P=%d, StandardDG+BR1+Roe, RK3 (bounded CPU sample)" % args.order, "nodes_per_element": n ** 3},
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Taylor-Green vortex Re=1600 M=0.08, P=%d, StandardDG+BR1+Roe, RK3 (bounded CPU sample: %s)" % (args.order, sample), "nodes_per_element": n ** 3},
         "cpu_baseline": {"value": value, "unit": "DOF-updates/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "restated reference algorithm (oracle/h3d_oracle.cpp, g++ -O2 -fopenmp -ffp-contract=off); the Fortran reference cannot be built here"},
+                         "note": "restated reference algorithm (oracle/h3d_oracle.cpp, g++ -O3 -fopenmp -ffp-contract=off); the Fortran reference cannot be built: no gfortran / MPI here or on the GPU box (profiles/r2_a_parity_dmma/probe.txt)"},
         "e2e": {"value": value, "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -125,6 +142,24 @@ def main_reference(args):
 
 def grid_for(ngpus, ne):
     return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(ngpus, (ngpus, 1, 1))
+
+
+def source_sha():
+    """Fingerprint of the kernel sources: the committed ncu traffic figure is only quoted for the library it was captured on."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "horses3d_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+# FP64 operations per node and residual evaluation, counted by ncu on the headline instantiations (thread-level DADD / DMUL /
+# DFMA of the source page; a DFMA or DMMA lane-MAC counts 2): profiles/r2_*/flops.txt.  The peak is the measured DMUL+DADD issue
+# rate of this build (no FMA contraction: 18.5 TFLOP/s, scripts/micro/dmma_rate.cu) -- the DFMA peak (33.9) is quoted beside it.
+FP64_PEAK_NOFMA_TFLOPS = 18.5
+FP64_PEAK_DFMA_TFLOPS = 33.9
 
 
 def main_b200(args):
@@ -168,15 +203,20 @@ def main_b200(args):
     # ---- mesh: every rank builds the (cheap) global connectivity, partitions it identically, keeps its part
     N, n = args.order, args.order + 1
     px, py, pz = grid_for(world, args.ne)
-    gmesh = HostMesh.box(args.ne * px, amp=args.amp, bFaceOrder=2, ney=args.ne * py, nez=args.ne * pz).connect()
+    if args.weak:
+        nel = args.ne or 32
+        ex, ey, ez = nel * px, nel * py, nel * pz                  # nel^3 elements per GPU
+    else:
+        ex = ey = ez = args.ne or 64                               # the whole mesh, whatever N
+    gmesh = HostMesh.box(ex, amp=args.amp, bFaceOrder=2, ney=ey, nez=ez).connect()
     nElemGlobal = gmesh.nElem
     if world > 1:
         if args.partition == "metis":
             part = gmesh.partition(world, "metis")
         else:
-            ex, ey, ez = args.ne * px, args.ne * py, args.ne * pz
             idx = np.arange(nElemGlobal)
-            part = ((idx % ex) // args.ne + px * (((idx // ex) % ey) // args.ne + py * ((idx // (ex * ey)) // args.ne))).astype(np.int32)
+            bx, by, bz = ex // px, ey // py, ez // pz
+            part = ((idx % ex) // bx + px * (((idx // ex) % ey) // by + py * ((idx // (ex * ey)) // bz))).astype(np.int32)
         mesh = gmesh.extract(part, rank)
         mesh.geometry(N, nodes)
     else:
@@ -245,14 +285,29 @@ def main_b200(args):
             traffic, tsrc = None, None
             tf = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tf) and world == 1 and headline:
-                rec = json.load(open(tf)).get("ne%d_P%d" % (args.ne, args.order))
-                if rec:
-                    traffic, tsrc = rec["k_volume_bytes_per_launch"], rec["source"]
+                # per-launch DRAM bytes scale with the element count (every tile moves the same bytes): the capture is
+                # quoted per element and only for the kernel sources it was taken on
+                rec = json.load(open(tf)).get("P%d" % args.order)
+                if rec and rec.get("source_sha") == source_sha():
+                    traffic, tsrc = rec["k_volume_bytes_per_element"] * sem.nElem, rec["source"]
+                elif rec:
+                    tsrc = "stale: the committed ncu capture (%s) was taken on other kernel sources" % rec["source"]
             roof = {"bound": "hbm", "kernel": "k_volume<%d>" % n, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc, "avg_launch_ms": vol_ms,
                     "alg_bytes_per_dof": b_vol,
                     "per_kernel_ms": {"gradient": prof[0] / max(prof[1], 1), "riemann": prof[2] / max(prof[3], 1), "volume": vol_ms},
                     "stage": {"alg_bytes_per_dof_stage": b_stage, "achieved": stage_gbs, "frac": stage_gbs / peak}}
+            ff = os.path.join(ROOT, "profiles", "fp64_flops.json")
+            key = "%s_%s_P%d" % (args.flow, args.inviscid, args.order)
+            if os.path.exists(ff) and key in json.load(open(ff)):
+                rec = json.load(open(ff))[key]
+                tf64 = rec["volume_flop_per_dof"] * ndof_local / (vol_ms * 1e-3) / 1e12
+                roof["fp64"] = {"kernel_flop_per_dof": rec["volume_flop_per_dof"], "achieved_tflops": tf64, "peak_tflops": FP64_PEAK_NOFMA_TFLOPS,
+                                "frac": tf64 / FP64_PEAK_NOFMA_TFLOPS, "peak_dfma_tflops": FP64_PEAK_DFMA_TFLOPS, "source": rec["source"],
+                                "stage_flop_per_dof": rec.get("stage_flop_per_dof"),
+                                "stage_achieved_tflops": rec["stage_flop_per_dof"] * value / world / 1e12 if rec.get("stage_flop_per_dof") else None}
+                if rec.get("bound") == "fp64":
+                    roof["bound"] = "fp64"
         except Exception as ex:  # profile hooks are optional
             roof = {"bound": "hbm", "error": str(ex)}
 
@@ -292,23 +347,45 @@ def main_b200(args):
                "resident": {"value": ndof_global * 3 * nsteps / float(el2.item()), "unit": "DOF-updates/s", "d2h_bytes_per_step": 8 * (6 + 4 * 4 + 6),
                             "mode": "state resident on the device; per step h3d_rk_step + residuals + KE/KE-rate/enstrophy monitors + NaN check"}}
 
+    # ---- self-check of the run that was just timed: restart from the initial condition, two RK3 steps, and compare the max
+    # residuals, kinetic energy and enstrophy (globally reduced) with the single-GPU values of the same library committed under
+    # tests/golden/ (the single-GPU path is bit-identical to the oracle: tests/test_gpu_parity_large.py)
+    check = None
+    if headline and not args.no_self_check:
+        sem.set_Q(Q0)
+        for _ in range(2):
+            sem.TakeRK3Step(0.0, 1.0e-4)
+        got = [float(x) for x in sem.ComputeMaxResiduals()] + [float(sem.volume_monitor("kinetic energy")), float(sem.volume_monitor("enstrophy"))]
+        gf = os.path.join(ROOT, "tests", "golden", "scale_check.json")
+        key = "ne%dx%dx%d_P%d_amp%g" % (ex, ey, ez, N, args.amp)
+        ref = json.load(open(gf)).get(key) if os.path.exists(gf) else None
+        if rank == 0:
+            if ref:
+                err = max(abs(a - b) / max(abs(b), 1e-300) for a, b in zip(got, ref["values"]))
+                check = {"key": key, "max_rel_err_vs_single_gpu": err, "tolerance": 1e-11, "ok": bool(err < 1e-11)}
+                assert err < 1e-11, "self-check failed: %s" % check
+            else:
+                check = {"key": key, "values": got, "note": "no committed single-GPU values for this mesh"}
+        assert not sem.checkForNan()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cms, cores, sample = cpu_sample(args, 2, 1)
+        v, cms, cores, sample = cpu_sample(args, 10, 2)
         cpu = {"value": v, "unit": "DOF-updates/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
         line = {
             "metric": "DOF-updates/s (TGV P=%d explicit RK3, %s)" % (N, "NS/BR1/Roe" if headline else scheme), "value": value, "unit": "DOF-updates/s", "tpdof_s": 1.0 / value,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "Taylor-Green vortex Re=1600 M=0.08, %dx%dx%d curvilinear hex elements, P=%d %s, %s, RK3, fixed dt"
-                                   % (args.ne * px, args.ne * py, args.ne * pz, N, "Gauss" if args.nodes == "gauss" else "Gauss-Lobatto",
+                                   % (ex, ey, ez, N, "Gauss" if args.nodes == "gauss" else "Gauss-Lobatto",
                                       "StandardDG+BR1+Roe" if headline else scheme),
-                       "ndof": ndof_global, "elements_per_gpu": args.ne ** 3, "partition": args.partition if world > 1 else "none",
+                       "ndof": ndof_global, "elements_per_gpu": nElemGlobal // world, "partition": args.partition if world > 1 else "none",
+                       "contraction": "DMMA" if os.environ.get("H3D_USE_MMA") == "1" else "CUDA cores, bit-identical to the oracle",
                        "l2": "inputs larger than L2 (state + gradients + metrics = %.1f GB per GPU)" % (sem.NDOF * 8 * (30 + 10) / 1e9)},
             "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "self_check": check,
         }
         print(json.dumps(line))
     if world > 1:

@@ -37,75 +37,101 @@ __device__ __forceinline__ int swzR(int node) { return node ^ (((node >> 6) & 1)
 // Volume term: R[q][node] = sum_l hatD(i,l) F1_q(l,j,k) + sum_l hatD(j,l) F2_q(i,l,k) + sum_l hatD(k,l) F3_q(i,j,l)
 // (ScalarWeakIntegrals_StdVolumeGreen, DGIntegrals.f90:56-87).  sF: [15][512] = (direction, equation) fields in the swzF layout;
 // the result of equation q overwrites F1_q in the swzR layout.  sMT[l*8 + i] = hatD(i,l).  All threads of the CTA call it.
+// Every warp keeps its UPW = ceil(40 / NWARPS) tiles in flight at once (independent accumulators; a tile alone is a chain of
+// LDS -> 4 dependent DMMAs of 26 cycles each -> STS); a slot beyond the 40 tiles repeats tile 39 and drops its result.
 template <int NWARPS>
 __device__ __forceinline__ void mma_volume_contract(double* __restrict__ sF, const double* __restrict__ sMT) {
+    constexpr int UPW = (40 + NWARPS - 1) / NWARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, a = lane & 3;
     const double bx0 = sMT[(2 * a) * 8 + g], bx1 = sMT[(2 * a + 1) * 8 + g];   // B of the xi tiles: rows l = 2a + h, column i' = g
     const double ay0 = sMT[a * 8 + g], ay1 = sMT[(a + 4) * 8 + g];             // A of the eta / zeta tiles: row g, columns l = a + 4 h
-#pragma unroll 1
-    for (int u = warp; u < 40; u += NWARPS) {
-        const int k = u / 5, q = u - 5 * k;
-        const double2 f1 = *reinterpret_cast<const double2*>(sF + q * 512 + swzF(k * 64 + g * 8 + 2 * a));
-        const double* F2 = sF + (5 + q) * 512;
-        const double f20 = F2[swzF(k * 64 + a * 8 + g)], f21 = F2[swzF(k * 64 + (a + 4) * 8 + g)];
-        double c0 = 0.0, c1 = 0.0;
-        dmma884(c0, c1, f1.x, bx0);
-        dmma884(c0, c1, f1.y, bx1);
-        dmma884(c0, c1, ay0, f20);
-        dmma884(c0, c1, ay1, f21);
-        *reinterpret_cast<double2*>(sF + q * 512 + swzR(k * 64 + g * 8 + 2 * a)) = make_double2(c0, c1);
+    {
+        double2 f1[UPW]; double f20[UPW], f21[UPW], c0[UPW], c1[UPW];
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) {
+            const int u = min(warp + s * NWARPS, 39), k = u / 5, q = u - 5 * k;
+            f1[s] = *reinterpret_cast<const double2*>(sF + q * 512 + swzF(k * 64 + g * 8 + 2 * a));
+            const double* F2 = sF + (5 + q) * 512;
+            f20[s] = F2[swzF(k * 64 + a * 8 + g)]; f21[s] = F2[swzF(k * 64 + (a + 4) * 8 + g)];
+            c0[s] = 0.0; c1[s] = 0.0;
+        }
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) dmma884(c0[s], c1[s], f1[s].x, bx0);
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) dmma884(c0[s], c1[s], f1[s].y, bx1);
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) dmma884(c0[s], c1[s], ay0, f20[s]);
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) dmma884(c0[s], c1[s], ay1, f21[s]);
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) {
+            const int u = warp + s * NWARPS, k = u / 5, q = u - 5 * k;
+            if (u < 40) *reinterpret_cast<double2*>(sF + q * 512 + swzR(k * 64 + g * 8 + 2 * a)) = make_double2(c0[s], c1[s]);
+        }
     }
     __syncthreads();
-#pragma unroll 1
-    for (int u = warp; u < 40; u += NWARPS) {
-        const int j = u / 5, q = u - 5 * j;
-        double2* R = reinterpret_cast<double2*>(sF + q * 512 + swzR(g * 64 + j * 8 + 2 * a));
-        const double* F3 = sF + (10 + q) * 512;
-        const double f30 = F3[swzF(a * 64 + j * 8 + g)], f31 = F3[swzF((a + 4) * 64 + j * 8 + g)];
-        double2 c = *R;
-        dmma884(c.x, c.y, ay0, f30);
-        dmma884(c.x, c.y, ay1, f31);
-        *R = c;
+    {
+        double2 c[UPW]; double f30[UPW], f31[UPW];
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) {
+            const int u = min(warp + s * NWARPS, 39), j = u / 5, q = u - 5 * j;
+            c[s] = *reinterpret_cast<const double2*>(sF + q * 512 + swzR(g * 64 + j * 8 + 2 * a));
+            const double* F3 = sF + (10 + q) * 512;
+            f30[s] = F3[swzF(a * 64 + j * 8 + g)]; f31[s] = F3[swzF((a + 4) * 64 + j * 8 + g)];
+        }
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) dmma884(c[s].x, c[s].y, ay0, f30[s]);
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) dmma884(c[s].x, c[s].y, ay1, f31[s]);
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) {
+            const int u = warp + s * NWARPS, j = u / 5, q = u - 5 * j;
+            if (u < 40) *reinterpret_cast<double2*>(sF + q * 512 + swzR(g * 64 + j * 8 + 2 * a)) = c[s];
+        }
     }
     __syncthreads();
 }
 
-// Local gradient: G[(d*5 + q)][pidx(node)] = sum_l D(node_d, l) U_q(.. l ..) for d = xi, eta, zeta
+// Local gradient: G[(d*5 + q)][node] = sum_l D(node_d, l) U_q(.. l ..) for d = xi, eta, zeta
 // (HexElement_ComputeLocalGradient, HexElementClass.f90:484-500).  sU: [5] fields of stride US, unpadded and unswizzled (staged by
 // bulk copies); sG: [15] fields of stride GS, rows padded to 9 doubles (PSWZ false) or in the pswz layout of h3d_kernels2.cuh.
-// sDT[l*8 + i] = D(i,l).
+// sDT[l*8 + i] = D(i,l).  Per direction every warp keeps its ceil(40 / NWARPS) tiles in flight (see mma_volume_contract).
 template <int NWARPS, int US, int GS, bool PSWZ = false>
 __device__ __forceinline__ void mma_gradient_contract(const double* __restrict__ sU, double* __restrict__ sG, const double* __restrict__ sDT) {
+    constexpr int UPW = (40 + NWARPS - 1) / NWARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, a = lane & 3;
     const double bx0 = sDT[(2 * a) * 8 + g], bx1 = sDT[(2 * a + 1) * 8 + g];
     const double ay0 = sDT[a * 8 + g], ay1 = sDT[(a + 4) * 8 + g];
-#pragma unroll 1
-    for (int u = warp; u < 120; u += NWARPS) {
-        const int d = u / 40, r = u - 40 * d, pl = r / 5, q = r - 5 * pl;   // direction, plane (k for xi / eta, j for zeta), equation
-        const double* U = sU + q * US;
-        double c0 = 0.0, c1 = 0.0;
-        int node;
-        if (d == 0) {
-            node = pl * 64 + g * 8 + 2 * a;
-            const double2 f = *reinterpret_cast<const double2*>(U + node);
-            dmma884(c0, c1, f.x, bx0);
-            dmma884(c0, c1, f.y, bx1);
-        } else if (d == 1) {
-            node = pl * 64 + g * 8 + 2 * a;
-            dmma884(c0, c1, ay0, U[pl * 64 + a * 8 + g]);
-            dmma884(c0, c1, ay1, U[pl * 64 + (a + 4) * 8 + g]);
-        } else {
-            node = g * 64 + pl * 8 + 2 * a;
-            dmma884(c0, c1, ay0, U[a * 64 + pl * 8 + g]);
-            dmma884(c0, c1, ay1, U[(a + 4) * 64 + pl * 8 + g]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double f0[UPW], f1[UPW], c0[UPW], c1[UPW];
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) {
+            const int u = min(warp + s * NWARPS, 39), pl = u / 5, q = u - 5 * pl;   // plane (k for xi / eta, j for zeta), equation
+            const double* U = sU + q * US;
+            if (d == 0) { const double2 f = *reinterpret_cast<const double2*>(U + pl * 64 + g * 8 + 2 * a); f0[s] = f.x; f1[s] = f.y; }
+            else if (d == 1) { f0[s] = U[pl * 64 + a * 8 + g]; f1[s] = U[pl * 64 + (a + 4) * 8 + g]; }
+            else { f0[s] = U[a * 64 + pl * 8 + g]; f1[s] = U[(a + 4) * 64 + pl * 8 + g]; }
+            c0[s] = 0.0; c1[s] = 0.0;
         }
-        if (PSWZ) {   // node and node + 1 differ in bit 0 of i only: the swizzled positions are the two halves of one 16-byte pair
-            const int p = (node & ~63) | (((((node >> 3) & 7) ^ ((node >> 6) & 1))) << 3) | ((node & 7) ^ ((node >> 3) & 7));
-            double* o = sG + (d * 5 + q) * GS;
-            o[p] = c0; o[p ^ 1] = c1;
-        } else {
-            double* o = sG + (d * 5 + q) * GS + (node >> 3) * 9 + (node & 7);
-            o[0] = c0; o[1] = c1;
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) { if (d == 0) dmma884(c0[s], c1[s], f0[s], bx0); else dmma884(c0[s], c1[s], ay0, f0[s]); }
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) { if (d == 0) dmma884(c0[s], c1[s], f1[s], bx1); else dmma884(c0[s], c1[s], ay1, f1[s]); }
+#pragma unroll
+        for (int s = 0; s < UPW; ++s) {
+            const int u = warp + s * NWARPS, pl = u / 5, q = u - 5 * pl;
+            const int node = d == 2 ? g * 64 + pl * 8 + 2 * a : pl * 64 + g * 8 + 2 * a;
+            if (u < 40) {
+                if (PSWZ) {   // node and node + 1 differ in bit 0 of i only: the swizzled positions are the two halves of one 16-byte pair
+                    const int p = (node & ~63) | (((((node >> 3) & 7) ^ ((node >> 6) & 1))) << 3) | ((node & 7) ^ ((node >> 3) & 7));
+                    double* o = sG + (d * 5 + q) * GS;
+                    o[p] = c0[s]; o[p ^ 1] = c1[s];
+                } else {
+                    double* o = sG + (d * 5 + q) * GS + (node >> 3) * 9 + (node & 7);
+                    o[0] = c0[s]; o[1] = c1[s];
+                }
+            }
         }
     }
     __syncthreads();
