@@ -311,6 +311,22 @@ def main_b200(args):
         except Exception as ex:  # profile hooks are optional
             roof = {"bound": "hbm", "error": str(ex)}
 
+    # ---- timeline of one RK stage on both streams of every rank (h3d_stage_timeline): where the halo exchange sits
+    timeline = None
+    if world > 1:
+        api.call("set_option", b"timeline=1")
+        sem.TakeRK3Step(0.0, dt)
+        marks = (C.c_double * 11)()
+        api.binding.lib.h3d_stage_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        api.binding.lib.h3d_stage_timeline(api.handle, marks, 11)
+        api.call("set_option", b"timeline=0")
+        allm = [None] * world
+        dist.all_gather_object(allm, [round(float(x), 4) for x in marks])
+        timeline = {"marks": ["start", "q_halo_begin", "q_halo_end", "gradient_interior_end", "gradient_mpi_end", "grad_halo_begin", "grad_halo_end",
+                              "riemann_local_end", "volume_interior_end", "riemann_mpi_end", "volume_mpi_end"],
+                    "ms_per_rank": allm}
+        barrier()
+
     # ---- end-to-end through the C ABI with HOST buffers (strict drop-in: state crosses PCIe every step)
     e2e = None
     if not args.no_e2e:
@@ -349,24 +365,33 @@ def main_b200(args):
 
     # ---- self-check of the run that was just timed: restart from the initial condition, two RK3 steps, and compare the max
     # residuals, kinetic energy and enstrophy (globally reduced) with the single-GPU values of the same library committed under
-    # tests/golden/ (the single-GPU path is bit-identical to the oracle: tests/test_gpu_parity_large.py)
+    # tests/golden/ (the single-GPU path is bit-identical to the oracle: tests/test_gpu_parity_large.py).  Tolerances: a rank
+    # builds the geometry of its MPI faces from its own element, as the reference does (HexMesh.f90:3000-3030); on one of the two
+    # ranks that is the right element, and n J_f differs from the single-domain value by the round-off of the metric terms
+    # (eps (N+1)^4 L/h ~ 1e-10 at 64^3, P=7).  The surface term multiplies that by the pressure (1 / (gamma M^2) = 112 in units of
+    # the residual) and by J_f b / J ~ 300: measured 6e-6 of the largest residual at N=2 (profiles/r2_h_multirank), bound 1e-4;
+    # the kinetic energy and the enstrophy are reproduced to the last digit (bound 1e-10).  Every rank computes the same verdict
+    # from globally reduced values: nobody is left waiting in a collective.
     check = None
     if headline and not args.no_self_check:
         sem.set_Q(Q0)
         for _ in range(2):
             sem.TakeRK3Step(0.0, 1.0e-4)
         got = [float(x) for x in sem.ComputeMaxResiduals()] + [float(sem.volume_monitor("kinetic energy")), float(sem.volume_monitor("enstrophy"))]
+        nan = bool(sem.checkForNan())
         gf = os.path.join(ROOT, "tests", "golden", "scale_check.json")
         key = "ne%dx%dx%d_P%d_amp%g" % (ex, ey, ez, N, args.amp)
         ref = json.load(open(gf)).get(key) if os.path.exists(gf) else None
-        if rank == 0:
-            if ref:
-                err = max(abs(a - b) / max(abs(b), 1e-300) for a, b in zip(got, ref["values"]))
-                check = {"key": key, "max_rel_err_vs_single_gpu": err, "tolerance": 1e-11, "ok": bool(err < 1e-11)}
-                assert err < 1e-11, "self-check failed: %s" % check
-            else:
-                check = {"key": key, "values": got, "note": "no committed single-GPU values for this mesh"}
-        assert not sem.checkForNan()
+        if ref:
+            rv = ref["values"]
+            e_res = max(abs(a - b) for a, b in zip(got[:5], rv[:5])) / max(abs(b) for b in rv[:5])
+            e_int = max(abs(a - b) / abs(b) for a, b in zip(got[5:], rv[5:]))
+            tol_res = 1e-13 if world == 1 else 1e-4
+            tol_int = 1e-13 if world == 1 else 1e-10
+            check = {"key": key, "residual_err_vs_single_gpu": e_res, "integral_err_vs_single_gpu": e_int, "tolerances": [tol_res, tol_int],
+                     "ok": bool(e_res < tol_res and e_int < tol_int and not nan)}
+        else:
+            check = {"key": key, "values": got, "ok": not nan, "note": "no committed single-GPU values for this mesh"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -385,11 +410,13 @@ def main_b200(args):
                        "contraction": "DMMA" if os.environ.get("H3D_USE_MMA") == "1" else "CUDA cores, bit-identical to the oracle",
                        "l2": "inputs larger than L2 (state + gradients + metrics = %.1f GB per GPU)" % (sem.NDOF * 8 * (30 + 10) / 1e9)},
             "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "self_check": check,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "self_check": check, "timeline": timeline,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if check is not None and not check["ok"]:
+        raise SystemExit("self-check failed: %s" % check)
 
 
 if __name__ == "__main__":

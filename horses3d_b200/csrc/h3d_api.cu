@@ -60,7 +60,13 @@ struct h3d_context {
     int useGen2 = 0;     // n = 8 StandardDG / BR1: second-generation kernels (256 threads, two CTAs per SM), h3d_kernels2.cuh
     int useMma = 0;      // n = 8 staged StandardDG / BR1 kernels: contractions on the FP64 tensor cores (DMMA); not bit-identical to the oracle
     int numSMs = 148;
+    // SMs the persistent element kernels leave free when the rank has neighbours: a persistent kernel holds every SM it runs on
+    // (all registers, most of the shared memory), so the pack / NCCL / unpack kernels of the communication stream could not start
+    // before it drained and the "overlap" was a serialisation.  Option comm_sms.
+    int commSMs = 8;
     std::vector<std::pair<const void*, int>> occCache;
+    // per-stage timeline (option timeline=1): events on both streams at the phase boundaries of the last residual evaluation
+    int timeline = 0; cudaEvent_t tl[11] = {nullptr}; bool tlRecorded[11] = {false};
     int profile = 0;
     struct ProfRec { int cls; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -71,6 +77,11 @@ struct h3d_context {
     int *dHaloFace = nullptr, *dHaloSide = nullptr, *dNbrOffset = nullptr, *dNbrOfFace = nullptr;
     int *dPermE = nullptr, *dPermF = nullptr;
     double *dSend = nullptr, *dRecv = nullptr;
+    bool faceHShared = false;      // interior penalty on a partition: the MPI faces' h is the minimum over both ranks
+    int maxZone = -1, nZones = 0;  // largest boundary zone of the mesh / zones given by h3d_set_boundary_conditions
+    int nBoundaryFaces = 0;
+    bool haveVolume = false;       // element volumes and face surfaces were given (LES filter widths)
+    int* dProbeEV = nullptr; double* dProbeL = nullptr; size_t probeCap = 0;   // h3d_probe scratch, kept between calls
 };
 
 #define CTX_CHECK(call)                                                                                   \
@@ -575,11 +586,12 @@ __global__ void k_halo_unpack(DevMesh m, const int* haloFace, const int* haloSid
 // ---- launch helpers --------------------------------------------------------------------------------------
 // persistent kernels: one resident wave, sized by the occupancy the kernel really gets (cached per function)
 int persistentGrid(h3d_context* h, const void* fn, int threads, size_t smemBytes) {
-    for (auto& p : h->occCache) if (p.first == fn) return p.second;
+    const int sms = std::max(1, h->numSMs - (h->nNbr > 0 ? h->commSMs : 0));
+    for (auto& p : h->occCache) if (p.first == fn) return p.second * sms;
     int perSM = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, threads, smemBytes) != cudaSuccess || perSM < 1) perSM = 1;
-    h->occCache.push_back({fn, perSM * h->numSMs});
-    return perSM * h->numSMs;
+    h->occCache.push_back({fn, perSM});
+    return perSM * sms;
 }
 
 template <int n> Ops<n> makeOps(const h3d_context* h) {
@@ -729,6 +741,31 @@ size_t splitSmemBytes(h3d_context* h) {
 }
 
 // halo exchange of NV variables (5: Q traces, 15: gradient traces) on the comm stream
+// CommunicateMPIFaceMinimumDistance (HexMesh.f90:3059-3145): h of an MPI face = min over the two ranks that share it
+__global__ void k_face_h_pack(const double* fH, const int* haloFace, int nHalo, double* buf) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nHalo) buf[q] = fH[haloFace[q]];
+}
+__global__ void k_face_h_min(double* fH, const int* haloFace, int nHalo, const double* buf) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nHalo) fH[haloFace[q]] = fmin(fH[haloFace[q]], buf[q]);
+}
+int shareFaceH(h3d_context* h) {
+    if (h->faceHShared || h->nNbr == 0 || !h->m.fH) return 0;
+    const int nb = (h->nHaloFaces + 255) / 256;
+    k_face_h_pack<<<nb, 256, 0, h->sCompute>>>(h->m.fH, h->dHaloFace, h->nHaloFaces, h->dSend);
+    NCCL_CHECK(ncclGroupStart());
+    for (int b = 0; b < h->nNbr; ++b) {
+        NCCL_CHECK(ncclSend(h->dSend + h->nbrOffset[b], h->nbrCount[b], ncclDouble, h->nbrRank[b], h->comm, h->sCompute));
+        NCCL_CHECK(ncclRecv(h->dRecv + h->nbrOffset[b], h->nbrCount[b], ncclDouble, h->nbrRank[b], h->comm, h->sCompute));
+    }
+    NCCL_CHECK(ncclGroupEnd());
+    k_face_h_min<<<nb, 256, 0, h->sCompute>>>(const_cast<double*>(h->m.fH), h->dHaloFace, h->nHaloFaces, h->dRecv);
+    h->launches += 2;
+    h->faceHShared = true;
+    return 0;
+}
+
 int haloExchange(h3d_context* h, int NV, const double* srcField, double* dstField, const int* dNbrOffset, const int* dNbrOfFace) {
     const int n2 = h->n * h->n;
     const size_t total = (size_t)h->nHaloFaces * n2 * NV;
@@ -761,8 +798,11 @@ struct ProfScope {
 
 // One residual evaluation (ComputeTimeDerivative, SpatialDiscretization.f90:227-320) with the RK update fused
 // into its last kernel.  Stream choreography for nranks > 1 ("Distributed backend"):
-//   comm   : pack Q traces -> send/recv -> unpack            | pack grad traces -> send/recv -> unpack
-//   compute: gradient(interior elems) | wait | gradient(MPI elems) | riemann(local faces) | wait | riemann(MPI faces) | volume(all)
+//   comm   : [Q traces: pack, send/recv, unpack]                 [gradient traces: pack, send/recv, unpack]
+//   compute: gradient(interior) | wait | gradient(MPI elements) | riemann(local faces) volume(interior) | wait | riemann(MPI faces) volume(MPI elements)
+// The elements without MPI faces (elements_sequential of the reference, ReadMeshFile.f90:108-130) come first in device order and
+// need local faces only: their volume kernel runs while the 15 gradient traces of the MPI faces are in flight.  The communication
+// stream has the highest priority and the persistent kernels leave commSMs multiprocessors to it.
 int residual(h3d_context* h, const RkArgs& rk) {
     cudaStream_t sc = h->sCompute;
     const bool multi = h->nNbr > 0;
@@ -772,23 +812,37 @@ int residual(h3d_context* h, const RkArgs& rk) {
     if (h->ph.viscous == H3D_VISCOUS_IP) {
         if (!h->m.fH) { h->err = "the interior-penalty discretization needs h3d_set_face_h"; return 1; }
         h->ph.penaltyNum = 0.5 * h->physics.penaltyParameter * (h->N + 1) * (h->N + 2);   // PenaltyParameterNS, EllipticIP.f90:678-687
+        if (multi && (rc = shareFaceH(h))) return rc;   // both ranks of an MPI face must use the same penalty
     }
+    auto mark = [&](int id, cudaStream_t s) {
+        if (!h->timeline) return;
+        if (!h->tl[id]) cudaEventCreate(&h->tl[id]);
+        cudaEventRecord(h->tl[id], s); h->tlRecorded[id] = true;
+    };
+    if (h->timeline) for (bool& b : h->tlRecorded) b = false;
     if (!h->facesValid) { ProfScope ps(h, 3, sc); if ((rc = doProlong(h, 0, h->nElem, sc))) return rc; }
+    mark(0, sc);
     if (multi) {
         CTX_CHECK(cudaEventRecord(h->evFaces, sc));
         CTX_CHECK(cudaStreamWaitEvent(h->sComm, h->evFaces, 0));
+        mark(1, h->sComm);
         if ((rc = haloExchange(h, 5, h->m.fQ, h->m.fQ, h->dNbrOffset, h->dNbrOfFace))) return rc;
+        mark(2, h->sComm);
         CTX_CHECK(cudaEventRecord(h->evA, h->sComm));
     }
     if (grads) {
         { ProfScope ps(h, 0, sc); if ((rc = doGradient(h, 0, h->nSeq, sc))) return rc; }
+        mark(3, sc);
         if (multi) {
             CTX_CHECK(cudaStreamWaitEvent(sc, h->evA, 0));
             if ((rc = doGradient(h, h->nSeq, h->nElem, sc))) return rc;
+            mark(4, sc);
             if (h->ph.ns) {
                 CTX_CHECK(cudaEventRecord(h->evGrad, sc));
                 CTX_CHECK(cudaStreamWaitEvent(h->sComm, h->evGrad, 0));
+                mark(5, h->sComm);
                 if ((rc = haloExchange(h, 15, h->m.fU, h->m.fU, h->dNbrOffset, h->dNbrOfFace))) return rc;
+                mark(6, h->sComm);
                 CTX_CHECK(cudaEventRecord(h->evB, h->sComm));
             }
         }
@@ -796,11 +850,16 @@ int residual(h3d_context* h, const RkArgs& rk) {
         CTX_CHECK(cudaStreamWaitEvent(sc, h->evA, 0));
     }
     { ProfScope ps(h, 1, sc); if ((rc = doRiemann(h, 0, h->nFaceLocal, sc))) return rc; }
+    mark(7, sc);
+    { ProfScope ps(h, 2, sc); if ((rc = doVolume(h, rk, 0, multi ? h->nSeq : h->nElem, sc))) return rc; }
+    mark(8, sc);
     if (multi) {
         if (grads && h->ph.ns) CTX_CHECK(cudaStreamWaitEvent(sc, h->evB, 0));
         if ((rc = doRiemann(h, h->nFaceLocal, h->nFace, sc))) return rc;
+        mark(9, sc);
+        if ((rc = doVolume(h, rk, h->nSeq, h->nElem, sc))) return rc;
     }
-    { ProfScope ps(h, 2, sc); if ((rc = doVolume(h, rk, 0, h->nElem, sc))) return rc; }
+    mark(10, sc);
     h->facesValid = rk.prolong != 0;
     ++h->stateVersion;
     CTX_CHECK(cudaGetLastError());
@@ -839,11 +898,12 @@ int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nc
     cudaGetDeviceProperties(&prop, device);
     if (prop.major != 10) return fail(std::string("libh3dgpu is built for sm_100a only; device is ") + prop.name);
     h->numSMs = prop.multiProcessorCount;
+    if (const char* ev = std::getenv("H3D_COMM_SMS")) h->commSMs = std::max(0, std::atoi(ev));
     if (const char* ev = std::getenv("H3D_USE_MMA")) h->useMma = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_GEN2")) h->useGen2 = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_USE_TMA")) h->useTma = std::atoi(ev);   // experiments: H3D_USE_TMA=0 selects the plain-load kernels
     if (cudaStreamCreateWithFlags(&h->sCompute, cudaStreamNonBlocking) != cudaSuccess) return fail("stream creation failed");
-    cudaStreamCreateWithFlags(&h->sComm, cudaStreamNonBlocking);
+    { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); cudaStreamCreateWithPriority(&h->sComm, cudaStreamNonBlocking, hi); }   // the halo kernels go first
     for (cudaEvent_t* ev : {&h->evA, &h->evB, &h->evFaces, &h->evGrad, &h->evSent}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     cudaEventCreate(&h->evT0); cudaEventCreate(&h->evT1);
     cudaMalloc((void**)&h->dPartial, sizeof(double) * (RED_BLOCKS * 16 + 64));
@@ -851,8 +911,11 @@ int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nc
     if (nranks > 1) {
         if (!nccl_unique_id) return fail("nranks > 1 needs an ncclUniqueId");
         ncclUniqueId id; std::memcpy(&id, nccl_unique_id, 128);
-        ncclResult_t r = ncclCommInitRank(&h->comm, nranks, id, rank);
-        if (r != ncclSuccess) return fail(std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+        // the send/recv kernels of the halo exchange get the multiprocessors the persistent kernels leave free, no more
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        if (h->commSMs > 0) cfg.maxCTAs = h->commSMs;
+        ncclResult_t r = ncclCommInitRankConfig(&h->comm, nranks, id, rank, &cfg);
+        if (r != ncclSuccess) return fail(std::string("ncclCommInitRankConfig: ") + ncclGetErrorString(r));
     }
     *out = h;
     return 0;
@@ -870,6 +933,8 @@ int h3d_destroy(h3d_handle h) {
     if (h->hScalars) cudaFreeHost(h->hScalars);
     if (h->dSnap) cudaFree(h->dSnap);
     if (h->hSnap) cudaFreeHost(h->hSnap);
+    if (h->dProbeEV) cudaFree(h->dProbeEV);
+    if (h->dProbeL) cudaFree(h->dProbeL);
     if (h->sCopy) { cudaStreamDestroy(h->sCopy); cudaEventDestroy(h->evSnap); cudaEventDestroy(h->evSnapDone); }
     if (h->sXfer) { cudaStreamDestroy(h->sXfer); for (int c = 0; c < XFER_CHUNKS; ++c) cudaEventDestroy(h->evX[c]); cudaEventDestroy(h->evXfree); }
     for (cudaEvent_t ev : {h->evA, h->evB, h->evFaces, h->evGrad, h->evSent, h->evT0, h->evT1}) if (ev) cudaEventDestroy(ev);
@@ -1070,6 +1135,9 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
     }
     m.S = nullptr; m.bcType = nullptr; m.bcParams = nullptr; m.dWall = nullptr; m.fDWall = nullptr; m.fH = nullptr;
     for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_BOUNDARY && faceZone[f] < 0) { h->err = "boundary face without a zone"; return 1; }
+    h->maxZone = -1; h->nBoundaryFaces = 0;
+    for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_BOUNDARY) { ++h->nBoundaryFaces; h->maxZone = std::max(h->maxZone, faceZone[f]); }
+    h->haveVolume = volume != nullptr && faceSurface != nullptr;
     h->haveMesh = true; h->facesValid = false; ++h->stateVersion;
     return 0;
 }
@@ -1102,11 +1170,17 @@ int h3d_set_face_h(h3d_handle h, const double* faceH) {
     if (devAlloc(h, &ddf, df.size())) return 2;
     CTX_CHECK(cudaMemcpy(ddf, df.data(), df.size() * sizeof(double), cudaMemcpyHostToDevice));
     m.fH = ddf;
+    h->faceHShared = false;
     return 0;
 }
 
 int h3d_set_boundary_conditions(h3d_handle h, int nZones, const int* bcType, const double* bcParams) {
     CTX_CHECK(cudaSetDevice(h->device));
+    if (nZones <= 0 || !bcType || !bcParams) { h->err = "h3d_set_boundary_conditions: empty table"; return 1; }
+    for (int z = 0; z < nZones; ++z)
+        if (bcType[z] < H3D_BC_PERIODIC || bcType[z] > H3D_BC_OUTFLOW) { h->err = "h3d_set_boundary_conditions: unknown boundary condition type"; return 1; }
+    if (h->haveMesh && h->maxZone >= nZones) { h->err = "h3d_set_boundary_conditions: a boundary face of the mesh refers to a zone beyond this table"; return 1; }
+    h->nZones = nZones;
     int* dt; double* dp;
     if (devAlloc(h, &dt, nZones) || devAlloc(h, &dp, 16 * (size_t)nZones)) return 2;
     CTX_CHECK(cudaMemcpy(dt, bcType, nZones * sizeof(int), cudaMemcpyHostToDevice));
@@ -1247,6 +1321,9 @@ static int checkReady(h3d_handle h) {
     if (h->nFace - h->nFaceLocal > 0 && h->nNbr == 0) { h->err = "mesh has MPI faces but h3d_set_halo was not called"; return 1; }
     if (h->physics.inviscid == H3D_SPLIT_DG && h->nodeType != H3D_GAUSSLOBATTO) { h->err = "split-form discretization needs Gauss-Lobatto nodes"; return 1; }
     if (h->physics.inviscid == H3D_SPLIT_DG && splitSmemBytes(h) > SMEM_LIMIT) { h->err = "split-form Navier-Stokes at this polynomial order exceeds the 227 KB shared memory of one CTA"; return 1; }
+    if (h->nBoundaryFaces > 0 && !h->m.bcType) { h->err = "mesh has boundary faces but h3d_set_boundary_conditions was not called"; return 1; }
+    if (h->nBoundaryFaces > 0 && h->maxZone >= h->nZones) { h->err = "a boundary face refers to a zone beyond the table of h3d_set_boundary_conditions"; return 1; }
+    if (h->physics.les != H3D_LES_NONE && !h->haveVolume) { h->err = "LES needs the element volumes and face surfaces (h3d_set_mesh volume / faceSurface): the filter width would be zero"; return 1; }
     return 0;
 }
 
@@ -1454,10 +1531,16 @@ int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, c
         if (variable[p] < H3D_PROBE_PRESSURE || variable[p] > H3D_PROBE_K) { h->err = "unknown probe variable"; return 1; }
         ev[p] = h->invPermE[elem[p]]; ev[nProbes + p] = variable[p];
     }
-    int* dEV = nullptr; double* dL = nullptr;
     const size_t nl = (size_t)nProbes * n;
-    CTX_CHECK(cudaMalloc((void**)&dEV, ev.size() * sizeof(int)));
-    CTX_CHECK(cudaMalloc((void**)&dL, (3 * nl + nProbes) * sizeof(double)));
+    if ((size_t)nProbes > h->probeCap) {   // scratch kept between calls: cudaFree would synchronise the device inside the time loop
+        if (h->dProbeEV) cudaFree(h->dProbeEV);
+        if (h->dProbeL) cudaFree(h->dProbeL);
+        h->dProbeEV = nullptr; h->dProbeL = nullptr; h->probeCap = 0;
+        CTX_CHECK(cudaMalloc((void**)&h->dProbeEV, ev.size() * sizeof(int)));
+        CTX_CHECK(cudaMalloc((void**)&h->dProbeL, (3 * nl + nProbes) * sizeof(double)));
+        h->probeCap = (size_t)nProbes;
+    }
+    int* dEV = h->dProbeEV; double* dL = h->dProbeL;
     CTX_CHECK(cudaMemcpyAsync(dEV, ev.data(), ev.size() * sizeof(int), cudaMemcpyHostToDevice, h->sCompute));
     CTX_CHECK(cudaMemcpyAsync(dL, lxi, nl * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
     CTX_CHECK(cudaMemcpyAsync(dL + nl, leta, nl * sizeof(double), cudaMemcpyHostToDevice, h->sCompute));
@@ -1466,7 +1549,6 @@ int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, c
     ++h->launches;
     cudaError_t e1 = cudaMemcpyAsync(values, dL + 3 * nl, nProbes * sizeof(double), cudaMemcpyDeviceToHost, h->sCompute);
     cudaError_t e2 = cudaStreamSynchronize(h->sCompute);
-    cudaFree(dEV); cudaFree(dL);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { h->err = "probe evaluation failed"; return 2; }
     return 0;
 }
@@ -1528,6 +1610,21 @@ int h3d_kernel_profile(h3d_handle h, double* out, int len) {
     return 0;
 }
 
+// Milliseconds since the start of the last residual evaluation of the eleven phase boundaries (option timeline=1):
+//   0 start | 1, 2 Q-trace exchange begin / end (communication stream) | 3 gradient(interior) end | 4 gradient(MPI elements) end |
+//   5, 6 gradient-trace exchange begin / end (communication stream) | 7 riemann(local faces) end | 8 volume(interior) end |
+//   9 riemann(MPI faces) end | 10 volume(MPI elements) end.  -1 where a phase did not run.
+int h3d_stage_timeline(h3d_handle h, double* marks_ms, int len) {
+    double* ms = marks_ms;
+    CTX_CHECK(cudaSetDevice(h->device));
+    CTX_CHECK(cudaStreamSynchronize(h->sCompute)); CTX_CHECK(cudaStreamSynchronize(h->sComm));
+    for (int i = 0; i < len && i < 11; ++i) {
+        ms[i] = -1.0;
+        if (h->tlRecorded[i] && h->tlRecorded[0]) { float f = 0.f; if (cudaEventElapsedTime(&f, h->tl[0], h->tl[i]) == cudaSuccess) ms[i] = f; }
+    }
+    return 0;
+}
+
 int h3d_timer_begin(h3d_handle h) { CTX_CHECK(cudaSetDevice(h->device)); CTX_CHECK(cudaEventRecord(h->evT0, h->sCompute)); return 0; }
 int h3d_timer_end(h3d_handle h, double* ms) {
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1547,6 +1644,8 @@ int h3d_set_option(h3d_handle h, const char* kv) {
     if (key == "store_qdot_every_stage") { h->storeQDotAlways = val; return 0; }
     if (key == "profile_kernels") { h->profile = val; return 0; }
     if (key == "use_tma") { h->useTma = val; return 0; }
+    if (key == "comm_sms") { h->commSMs = std::max(0, val); return 0; }
+    if (key == "timeline") { h->timeline = val; return 0; }
     if (key == "mma") { h->useMma = val; return 0; }
     if (key == "gen2") { h->useGen2 = val; return 0; }
     h->err = "unknown option: " + key;

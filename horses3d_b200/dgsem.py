@@ -61,6 +61,9 @@ class DGSem:
             dw, dwf = np.ascontiguousarray(mesh.array("dWall")), np.ascontiguousarray(mesh.array("faceDWall"))
             if dw.size == 0:
                 raise ValueError("the LES wall model needs wall distances: call HostMesh.wall_distances() first")
+            if getattr(mesh, "is_partition", False) and not getattr(mesh, "wall_global", False):
+                raise ValueError("wall distances of a partition must be measured against the wall nodes of every rank "
+                                 "(HexMesh.f90:5594-5780): HostMesh.wall_distances(gather=...)")
             api.call("set_wall_distance", _ptr(dw, np.float64), _ptr(dwf, np.float64))
         if physics.viscous == P.VISCOUS["ip"]:
             api.call("set_face_h", _ptr(np.ascontiguousarray(mesh.array("faceH")), np.float64))

@@ -68,6 +68,25 @@ int h3dhost_wall_distance(void* hp) {
     return 0;
 }
 
+// The two halves of the reference's parallel wall-distance computation (HexMesh.f90:5594-5780): every rank contributes the
+// nodes of its no-slip wall faces (wall_points: count = number of points; pts may be NULL to ask for the count), the driver
+// gathers them across ranks, and every rank measures its nodes against the whole set (wall_distance_from).
+int h3dhost_wall_points(void* hp, double* pts, long long* count) {
+    Host* h = (Host*)hp;
+    if (!h->hasGeom) { g_err = "geometry has not been built"; return 1; }
+    const std::vector<double> Xw = wallCoordinates(h->mesh, h->geom);
+    *count = (long long)(Xw.size() / 3);
+    if (pts && !Xw.empty()) std::memcpy(pts, Xw.data(), Xw.size() * sizeof(double));
+    return 0;
+}
+int h3dhost_wall_distance_from(void* hp, const double* pts, long long count) {
+    Host* h = (Host*)hp;
+    if (!h->hasGeom) { g_err = "geometry has not been built"; return 1; }
+    if (count <= 0) { g_err = "no wall points: the wall model needs at least one no-slip wall face in the whole mesh"; return 1; }
+    computeWallDistances(h->mesh, h->geom, std::vector<double>(pts, pts + 3 * count));
+    return 0;
+}
+
 int h3dhost_mesh_sizes(void* hp, int* nElem, int* nFaces, int* nNodes, int* N) {
     Host* h = (Host*)hp;
     *nElem = h->mesh.nElem(); *nFaces = h->mesh.nFaces; *nNodes = h->mesh.nNodes(); *N = h->hasGeom ? h->geom.N : -1;
@@ -150,6 +169,7 @@ int h3dhost_inherit_geometry(void* childp, void* parentp) {
     gatherE(G.jac, g.jac, n3); gatherE(G.invJac, g.invJac, n3); gatherE(G.volume, g.volume, 1);
     gatherF(G.fx, g.fx, 3 * n2); gatherF(G.fnormal, g.fnormal, 3 * n2); gatherF(G.ft1, g.ft1, 3 * n2); gatherF(G.ft2, g.ft2, 3 * n2);
     gatherF(G.fjac, g.fjac, n2); gatherF(G.fsurface, g.fsurface, 1); gatherF(G.fh, g.fh, 1);
+    if (!G.dWall.empty()) { gatherE(G.dWall, g.dWall, n3); gatherF(G.fdWall, g.fdWall, n2); }   // wall distances of the global mesh
     c->hasGeom = true;
     return 0;
 }

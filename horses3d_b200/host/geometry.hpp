@@ -303,14 +303,23 @@ inline void computeFaceMinimumDistance(const HostMesh& m, HostGeometry& g) {
     }
 }
 
-// HexMesh_ComputeWallDistances / GatherAllWallCoordinates (HexMesh.f90:5594-5780): nearest no-slip wall node
-inline void computeWallDistances(const HostMesh& m, HostGeometry& g) {
-    const int n = g.n, n2 = n * n, n3 = n2 * n;
+// Coordinates of the nodes of this mesh's no-slip wall faces (the local contribution to GatherAllWallCoordinates,
+// HexMesh.f90:5696-5780)
+inline std::vector<double> wallCoordinates(const HostMesh& m, const HostGeometry& g) {
+    const int n2 = g.n * g.n;
     std::vector<double> Xw;
     for (int f = 0; f < m.nFaces; ++f) {
         if (m.faceType[f] != HMESH_BOUNDARY || m.faceZone[f] < 0 || m.bcs[m.faceZone[f]].type != "noslipwall") continue;
         Xw.insert(Xw.end(), &g.fx[3 * (size_t)f * n2], &g.fx[3 * (size_t)f * n2] + 3 * n2);
     }
+    return Xw;
+}
+
+// HexMesh_ComputeWallDistances (HexMesh.f90:5594-5692): distance of every element and face node to the nearest no-slip wall
+// node.  Xw holds the wall nodes of ALL partitions (the reference gathers them across ranks first); a partition that scanned
+// its own wall faces only would make LS = min(Cs delta, 0.4 dWall) depend on the partition.
+inline void computeWallDistances(const HostMesh& m, HostGeometry& g, const std::vector<double>& Xw) {
+    const int n = g.n, n2 = n * n, n3 = n2 * n;
     const size_t nW = Xw.size() / 3;
     auto dist = [&](const double* xP) {
         double mn = 1.7976931348623157e308;
@@ -327,5 +336,6 @@ inline void computeWallDistances(const HostMesh& m, HostGeometry& g) {
 #pragma omp parallel for schedule(static)
     for (long long q = 0; q < (long long)g.fdWall.size(); ++q) g.fdWall[q] = dist(&g.fx[3 * q]);
 }
+inline void computeWallDistances(const HostMesh& m, HostGeometry& g) { computeWallDistances(m, g, wallCoordinates(m, g)); }
 
 }  // namespace h3d

@@ -40,6 +40,8 @@ def lib():
         L.h3dhost_extract_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.h3dhost_inherit_geometry.argtypes = [C.c_void_p, C.c_void_p]
         L.h3dhost_wall_distance.argtypes = [C.c_void_p]
+        L.h3dhost_wall_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong)]
+        L.h3dhost_wall_distance_from.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
         _lib = L
     return _lib
 
@@ -80,6 +82,8 @@ class HostMesh:
             raise HostError(lib().h3dhost_last_error().decode())
         self._h = C.c_void_p(handle)
         self.halo = None
+        self.is_partition = False      # extracted from a global mesh: some faces are MPI faces
+        self.wall_global = False       # wall distances measured against the wall nodes of the whole mesh
 
     # --- constructors
     @classmethod
@@ -120,10 +124,32 @@ class HostMesh:
         self.N, self.nodes = N, nodes
         return self
 
-    def wall_distances(self):
-        """e % geom % dWall / f % geom % dWall: distance to the nearest no-slip wall node (HexMesh.f90:5594-5692)."""
-        _check(lib().h3dhost_wall_distance(self._h))
+    def wall_distances(self, gather=None):
+        """e % geom % dWall / f % geom % dWall: distance to the nearest no-slip wall node (HexMesh.f90:5594-5692).
+
+        On a partition the wall nodes of ALL ranks are needed (GatherAllWallCoordinates, HexMesh.f90:5696-5780): pass
+        `gather`, a callable that takes this rank's [k,3] wall points and returns the concatenation over the ranks (an
+        all-gather of the driver's communicator).  Without it a partition refuses: distances to the local wall nodes only
+        would make the wall model depend on the partition."""
+        if self.is_partition and gather is None:
+            raise HostError("wall distances on a partition need the wall nodes of every rank: pass gather= (or extract the "
+                            "partition with inherit_geometry=True from a global mesh that has its wall distances)")
+        if gather is None:
+            _check(lib().h3dhost_wall_distance(self._h))
+        else:
+            pts = np.ascontiguousarray(gather(self.wall_points()), dtype=np.float64).reshape(-1, 3)
+            _check(lib().h3dhost_wall_distance_from(self._h, pts.ctypes.data, len(pts)))
+        self.wall_global = True
         return self
+
+    def wall_points(self):
+        """Nodes of this mesh's no-slip wall faces, [k,3]."""
+        cnt = C.c_longlong()
+        _check(lib().h3dhost_wall_points(self._h, None, C.byref(cnt)))
+        pts = np.zeros((cnt.value, 3))
+        if cnt.value:
+            _check(lib().h3dhost_wall_points(self._h, pts.ctypes.data, C.byref(cnt)))
+        return pts
 
     def sizes(self):
         a = [C.c_int() for _ in range(4)]
@@ -160,7 +186,9 @@ class HostMesh:
         child = HostMesh(lib().h3dhost_extract_partition(self._h, part.ctypes.data, rank))
         child.bcs = getattr(self, "bcs", [])
         child.bc_params = getattr(self, "bc_params", None)
+        child.is_partition = True
         if inherit_geometry:
             _check(lib().h3dhost_inherit_geometry(child._h, self._h))
             child.N, child.nodes = self.N, self.nodes
+            child.wall_global = self.wall_global
         return child

@@ -276,7 +276,16 @@ int h3d_timer_end(h3d_handle h, double* ms);
 /* accumulated CUDA-event time per kernel class since the last call (option profile_kernels=1):
  * out = [ms, launches] x {gradient, riemann, volume, prolong} */
 int h3d_kernel_profile(h3d_handle h, double* out, int len);
-/* option string "key=value" ("store_qdot_every_stage=1", "profile_kernels=1", "use_tma=0"); unknown keys are an error */
+/* Per-stage timeline (option timeline=1): milliseconds since the start of the last residual evaluation of its eleven phase
+ * boundaries, on both streams -- 0 start | 1, 2 Q-trace exchange begin / end (communication stream) | 3 gradient(interior
+ * elements) end | 4 gradient(MPI elements) end | 5, 6 gradient-trace exchange begin / end (communication stream) | 7 riemann(local
+ * faces) end | 8 volume(interior elements) end | 9 riemann(MPI faces) end | 10 volume(MPI elements) end; -1 where a phase did
+ * not run.  Replaces the reference's Stopwatch around UpdateMPIFaces* / GatherMPIFaces* (HexMesh.f90:1199-1391). */
+int h3d_stage_timeline(h3d_handle h, double* marks_ms, int len);
+/* option string "key=value"; unknown keys are an error.  store_qdot_every_stage=1 | profile_kernels=1 | timeline=1 |
+ * use_tma=0 (plain-load kernels) | mma=1 (n = 8: contractions on the FP64 tensor cores, not bit-identical to the CUDA-core
+ * summation order) | gen2=1 (n = 8: 256-thread kernels, two CTAs per SM) | comm_sms=K (multiprocessors the persistent kernels
+ * leave to the halo exchange on a rank with neighbours, default 8) */
 int h3d_set_option(h3d_handle h, const char* key_value);
 
 #ifdef __cplusplus

@@ -1,5 +1,11 @@
-"""Two ranks, two B200s: partitioned mesh + NCCL face exchange must reproduce the single-domain oracle.
-Skipped on boxes with fewer than two GPUs (run with `gpurun --gpus 2`)."""
+"""Several ranks, several B200s: partitioned mesh + NCCL face exchange must reproduce the single-domain oracle.
+
+Covers the two halo exchanges (Q traces, gradient traces) behind HexMesh_UpdateMPIFaces* / GatherMPIFaces*
+(HexMesh.f90:1199-1391, 1590-1660), the MPI-face Riemann solver (SpatialDiscretization.f90:1801-1894), the split of the
+element kernels into interior / MPI elements, the globally reduced monitors, the wall distances gathered across the ranks
+(HexMesh.f90:5594-5780) and the minimum of the MPI faces' h over both ranks (HexMesh.f90:3059-3145).
+Skipped where the box has fewer GPUs than ranks (run with `gpurun --gpus 2|4|8`); the skip reason says so.
+"""
 import os
 import sys
 
@@ -13,8 +19,36 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, kw, method, N, inherit, q):
-    import torch
+def _case_mesh(case):
+    """The global mesh of a case (connectivity only); identical on every rank and in the parent process."""
+    from horses3d_b200.hostmesh import HostMesh
+    from horses3d_b200.physics import make_physics
+    from parity import channel_bcs
+    phys = make_physics(**case["kw"])
+    g = HostMesh.box(case["ne"], amp=0.1, bFaceOrder=2, shuffle=True, seed=11)
+    if case.get("bc") == "channel":
+        bcs, params = channel_bcs(phys)
+        g.connect(bcs, params)
+    else:
+        g.connect()
+    return g, phys
+
+
+def _ic(case, phys):
+    from parity import channel_state, perturbed_tgv
+    return (lambda x: channel_state(x, phys)) if case.get("bc") == "channel" else perturbed_tgv
+
+
+def _run(sem, ic):
+    sem.set_initial_condition(ic)
+    sem.ComputeTimeDerivative(0.0)
+    qd = sem.QDot()
+    for _ in range(3):
+        sem.TakeRK3Step(0.0, 1e-3)
+    return qd, sem.Q(), sem.ComputeMaxResiduals(), sem.volume_monitors(), sem.MaxTimeStep(0.4, 0.4)
+
+
+def _worker(rank, world, port, case, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -22,75 +56,120 @@ def _worker(rank, world, port, kw, method, N, inherit, q):
     try:
         from horses3d_b200.capi import GpuApi
         from horses3d_b200.dgsem import DGSem
-        from horses3d_b200.hostmesh import GAUSS, HostMesh
-        from horses3d_b200.physics import make_physics
-        from parity import perturbed_tgv
+        from horses3d_b200.hostmesh import GAUSS, GAUSSLOBATTO
+        nodes = GAUSSLOBATTO if case["kw"].get("inviscid") == "split-form" else GAUSS
         obj = [GpuApi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
-        g = HostMesh.box(4, amp=0.1, bFaceOrder=2, shuffle=True, seed=11).connect()
-        part = g.partition(world, method)
-        if inherit:
-            g.geometry(N, GAUSS)
+        g, phys = _case_mesh(case)
+        part = g.partition(world, case["method"])
+
+        def gather(pts):      # GatherAllWallCoordinates: the wall nodes of every rank
+            out = [None] * world
+            dist.all_gather_object(out, pts)
+            return np.concatenate(out)
+
+        if case["inherit"]:
+            g.geometry(case["N"], nodes)
+            if phys.les_wall_model:
+                g.wall_distances()
             m = g.extract(part, rank, inherit_geometry=True)     # partition-independent geometry: bit-exact parity expected
         else:
-            m = g.extract(part, rank).geometry(N, GAUSS)         # the reference's way: MPI-face geometry from the local element
-        sem = DGSem(GpuApi(rank=rank, nranks=world, device=rank, nccl_id=obj[0]), m, make_physics(**kw))
-        sem.set_initial_condition(perturbed_tgv)
-        sem.ComputeTimeDerivative(0.0)
-        qd = sem.QDot()
-        for _ in range(3):
-            sem.TakeRK3Step(0.0, 1e-3)
-        Qn = sem.Q()
-        res, mon, dts = sem.ComputeMaxResiduals(), sem.volume_monitors(), sem.MaxTimeStep(0.4, 0.4)
-        q.put((rank, m.array("globalElem").copy(), qd, Qn, res, mon, dts))
+            m = g.extract(part, rank).geometry(case["N"], nodes)  # the reference's way: MPI-face geometry from the local element
+            if phys.les_wall_model:
+                m.wall_distances(gather=gather)
+        api = GpuApi(rank=rank, nranks=world, device=rank, nccl_id=obj[0])
+        sem = DGSem(api, m, phys)
+        qd, Qn, res, mon, dts = _run(sem, _ic(case, phys))
+        nMpi = int((m.array("faceType") == 3).sum())
+        q.put((rank, m.array("globalElem").copy(), qd, Qn, res, mon, dts, nMpi, len(m.array("haloCount"))))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kw,method,inherit", [(dict(flow="NS", mach=0.08, reynolds=1600.0), "metis", True),
-                                               (dict(flow="Euler", mach=0.3, riemann="lax-friedrichs"), "block", True),
-                                               (dict(flow="NS", mach=0.08, reynolds=1600.0), "metis", False),
-                                               (dict(flow="NS", mach=0.3, reynolds=200.0, viscous="BR2"), "metis", True),
-                                               (dict(flow="NS", mach=0.3, reynolds=200.0, viscous="IP"), "block", True)])
-def test_two_ranks_reproduce_the_single_domain_oracle(kw, method, inherit):
+NS = dict(flow="NS", mach=0.08, reynolds=1600.0)
+NS3 = dict(flow="NS", mach=0.3, reynolds=200.0)
+CASES = [
+    # world, ne, N, physics, partition, inherited geometry, boundary conditions
+    dict(world=2, ne=4, N=3, kw=NS, method="metis", inherit=True),
+    dict(world=2, ne=4, N=3, kw=dict(flow="Euler", mach=0.3, riemann="lax-friedrichs"), method="block", inherit=True),
+    dict(world=2, ne=4, N=3, kw=NS, method="metis", inherit=False),
+    dict(world=2, ne=4, N=3, kw=dict(NS3, viscous="BR2"), method="metis", inherit=True),
+    dict(world=2, ne=4, N=3, kw=dict(NS3, viscous="IP"), method="block", inherit=True),
+    dict(world=2, ne=4, N=3, kw=dict(NS3, viscous="IP"), method="metis", inherit=False),           # MPI faces' h: min over both ranks
+    dict(world=2, ne=6, N=7, kw=NS, method="metis", inherit=True),                                 # the staged n = 8 kernels, several tiles per CTA
+    dict(world=2, ne=6, N=7, kw=NS, method="metis", inherit=False),
+    dict(world=2, ne=4, N=7, kw=dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli"), method="metis", inherit=True),
+    dict(world=2, ne=4, N=3, kw=NS3, method="metis", inherit=True, bc="channel"),                  # inflow, outflow, no-slip, free-slip across the cut
+    dict(world=2, ne=4, N=4, kw=dict(NS3, les="smagorinsky", les_wall_model="linear"), method="metis", inherit=False, bc="channel"),
+    dict(world=2, ne=4, N=7, kw=dict(NS3, les="smagorinsky", les_wall_model="linear"), method="block", inherit=True, bc="channel"),
+    dict(world=4, ne=6, N=7, kw=NS, method="metis", inherit=True),                                 # more than two neighbours per rank
+    dict(world=4, ne=4, N=4, kw=dict(NS3, les="smagorinsky", les_wall_model="linear"), method="metis", inherit=False, bc="channel"),
+    dict(world=8, ne=8, N=7, kw=NS, method="metis", inherit=True),
+    dict(world=8, ne=6, N=3, kw=dict(NS3, les="smagorinsky", les_wall_model="linear"), method="metis", inherit=False, bc="channel"),
+]
+
+
+def _id(case):
+    kw = case["kw"]
+    return "w%d-ne%d-N%d-%s-%s-%s%s" % (case["world"], case["ne"], case["N"], kw.get("viscous", kw.get("inviscid", kw["flow"])) + ("-les" if kw.get("les") else ""),
+                                        case["method"], "inherit" if case["inherit"] else "local", "-bc" if case.get("bc") else "")
+
+
+@pytest.mark.parametrize("case", CASES, ids=_id)
+def test_ranks_reproduce_the_single_domain_oracle(case):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    world = case["world"]
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs, this box has %d (run under gpurun --gpus %d)" % (world, torch.cuda.device_count(), world))
     from horses3d_b200.dgsem import DGSem
-    from horses3d_b200.hostmesh import GAUSS, HostMesh
-    from horses3d_b200.physics import make_physics
+    from horses3d_b200.hostmesh import GAUSS, GAUSSLOBATTO
     from oracle.oracle_api import OracleApi
-    from parity import perturbed_tgv, rel_err
-    N, world = 3, 2
+    from parity import rel_err
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kw, method, N, inherit, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=600) for _ in range(world)]
+    import queue
+    import time
+    got, t0 = [], time.time()
+    while len(got) < world:      # fail fast when a rank dies: the others would wait for it in a collective for ever
+        try:
+            got.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > 400:
+                for p in procs:
+                    p.kill()
+                pytest.fail("a rank exited with %s / timed out after %.0f s" % (dead, time.time() - t0))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    g = HostMesh.box(4, amp=0.1, bFaceOrder=2, shuffle=True, seed=11).connect().geometry(N, GAUSS)
-    sem = DGSem(OracleApi(), g, make_physics(**kw))
-    sem.set_initial_condition(perturbed_tgv)
-    sem.ComputeTimeDerivative(0.0)
-    qd = sem.QDot()
-    for _ in range(3):
-        sem.TakeRK3Step(0.0, 1e-3)
-    Qn = sem.Q()
-    res, mon, dts = sem.ComputeMaxResiduals(), sem.volume_monitors(), sem.MaxTimeStep(0.4, 0.4)
-    # locally rebuilt MPI-face geometry differs from the global one in the last bits (1e-13), which the lift amplifies
-    tol = 1e-13 if inherit else 1e-8
-    for rank, ge, qd_r, Qn_r, res_r, mon_r, dts_r in got:
-        assert rel_err(qd_r, qd[ge]) < tol
+    g, phys = _case_mesh(case)
+    g.geometry(case["N"], GAUSSLOBATTO if case["kw"].get("inviscid") == "split-form" else GAUSS)
+    if phys.les_wall_model:
+        g.wall_distances()
+    qd, Qn, res, mon, dts = _run(DGSem(OracleApi(), g, phys), _ic(case, phys))
+    # With inherited geometry both ranks of an MPI face hold the global face's geometry: bit-exact fields expected.  The reference
+    # rebuilds MPI-face geometry from the local element (HexMesh.f90:3000-3030), which on one of the two ranks is the RIGHT element:
+    # n J_f then differs from the single-domain value (always from the left element) by the round-off of the metric terms,
+    # delta ~ eps (N+1)^4 L/h (derivative matrices of size N^2 applied twice to absolute coordinates).  The surface term multiplies
+    # delta by the pressure (1 / (gamma M^2) in units of the residual) and by the lift weights.  Measured (profiles/r2_h_multirank):
+    # 4.4e-10 at M 0.08, N 3, 4^3 elements; 5.2e-8 at N 7, 6^3 elements; the bound below is 2e-13 (N+1)^4 ne / (gamma M^2) --
+    # the reference's own parallel regression tolerates 1e-7 on P=3 residuals (CI_parallel.yml:510-514).
+    tol = 1e-13 if case["inherit"] else 2e-13 * (case["N"] + 1) ** 4 * case["ne"] * max(1.0, 1.0 / phys.gammaM2)
+    assert sum(g_[7] for g_ in got) > 0 and all(g_[8] >= 1 for g_ in got)          # every rank has neighbours and MPI faces
+    worst = 0.0
+    for rank, ge, qd_r, Qn_r, res_r, mon_r, dts_r, nMpi, nNbr in got:
+        worst = max(worst, rel_err(qd_r, qd[ge]), rel_err(Qn_r, Qn[ge]))
+        assert rel_err(qd_r, qd[ge]) < tol, (rank, rel_err(qd_r, qd[ge]))
         assert rel_err(Qn_r, Qn[ge]) < tol
-        # MPI-face geometry is built from the local element (right side: rotated), so it differs from the single-domain
-        # face geometry in the last bits: reductions agree to round-off, not bit for bit
-        assert np.allclose(res_r, res, rtol=1e-11 if inherit else 1e-7, atol=0)
+        # reductions combine per-rank partial results in another order: round-off, not bit for bit
+        assert np.allclose(res_r, res, rtol=max(1e-11, 10 * tol), atol=0)
         assert np.allclose(dts_r, dts, rtol=1e-12, atol=0)
         for k in mon:
-            assert abs(mon_r[k] - mon[k]) < (1e-12 if inherit else 1e-8) * max(abs(mon[k]), 1e-30)
+            assert abs(mon_r[k] - mon[k]) < max(1e-11, tol) * max(abs(mon[k]), 1e-30), k
+    print("multirank %s: worst field error %.2e" % (_id(case), worst))

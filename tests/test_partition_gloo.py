@@ -140,3 +140,39 @@ def test_mpi_face_minimum_distance_matches_the_single_domain_value():
         p.join(timeout=300)
         assert p.exitcode == 0
     assert q.get(timeout=10) == 1
+
+
+def test_wall_distances_of_a_partition_use_the_wall_nodes_of_every_rank():
+    """HexMesh_ComputeWallDistances (HexMesh.f90:5594-5780): a partition measures its nodes against the no-slip wall nodes gathered
+    from ALL ranks; measuring against its own wall faces only is refused (the LES wall model would depend on the partition)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from horses3d_b200.dgsem import DGSem
+    from horses3d_b200.hostmesh import HostError
+    from horses3d_b200.physics import make_physics
+    from parity import channel_bcs
+
+    class NullApi:      # accepts the set-up calls of DGSem (the check under test is host-side)
+        def __getattr__(self, name):
+            return lambda *a, **k: None
+
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, les="smagorinsky", les_wall_model="linear")
+    bcs, params = channel_bcs(phys)
+    g = HostMesh.box(4, amp=0.1, bFaceOrder=2, shuffle=True, seed=11).connect(bcs, params).geometry(3, GAUSS).wall_distances()
+    world = 3
+    part = g.partition(world, "metis")
+    parts = [g.extract(part, r).geometry(3, GAUSS) for r in range(world)]
+    pts = [m.wall_points() for m in parts]
+    assert sum(len(p) for p in pts) == len(g.wall_points()) > 0
+    assert min(len(p) for p in pts) < max(len(p) for p in pts) or world == 1      # the wall is not spread evenly
+    for r, m in enumerate(parts):
+        with pytest.raises(HostError):
+            m.wall_distances()
+        with pytest.raises(ValueError, match="wall distances"):
+            DGSem(NullApi(), m, phys)
+        m.wall_distances(gather=lambda p: np.concatenate(pts))
+        ge = m.array("globalElem")
+        assert np.array_equal(m.array("dWall").reshape(len(ge), -1), g.array("dWall").reshape(g.nElem, -1)[ge])
+        local = np.sqrt(((m.array("x").reshape(-1, 1, 3) - pts[r][None]) ** 2).sum(-1).min(1)) if len(pts[r]) else np.full(m.array("dWall").shape, np.inf)
+        assert (local >= m.array("dWall") - 1e-14).all() and (local > m.array("dWall") + 1e-6).any()   # the local-only answer differs
+        mi = g.extract(part, r, inherit_geometry=True)
+        assert mi.wall_global and np.array_equal(mi.array("dWall"), m.array("dWall"))
