@@ -63,7 +63,12 @@ struct h3d_context {
     // SMs the persistent element kernels leave free when the rank has neighbours: a persistent kernel holds every SM it runs on
     // (all registers, most of the shared memory), so the pack / NCCL / unpack kernels of the communication stream could not start
     // before it drained and the "overlap" was a serialisation.  Option comm_sms.
-    int commSMs = 8;
+    int commSMs = 0;
+    // ... instead the interior-element launches are cut in two (interiorSplitPct % / rest): when the first part retires, the
+    // high-priority halo kernels take the multiprocessors they need and run beside the second part.  Measured at N=2, 64^3 P=7
+    // (profiles/r2_h_multirank): reserving 8 SMs costs 2.6 % of the step, no reservation leaves the Q-trace exchange waiting for
+    // the whole interior gradient kernel.  Options comm_sms, interior_split_pct.
+    int interiorSplitPct = 70;
     std::vector<std::pair<const void*, int>> occCache;
     // per-stage timeline (option timeline=1): events on both streams at the phase boundaries of the last residual evaluation
     int timeline = 0; cudaEvent_t tl[11] = {nullptr}; bool tlRecorded[11] = {false};
@@ -814,6 +819,8 @@ int residual(h3d_context* h, const RkArgs& rk) {
         h->ph.penaltyNum = 0.5 * h->physics.penaltyParameter * (h->N + 1) * (h->N + 2);   // PenaltyParameterNS, EllipticIP.f90:678-687
         if (multi && (rc = shareFaceH(h))) return rc;   // both ranks of an MPI face must use the same penalty
     }
+    // first part of the interior elements (see interiorSplitPct); the launch helpers skip empty ranges
+    const int nCut = (multi && h->interiorSplitPct > 0 && h->interiorSplitPct < 100) ? (int)((long long)h->nSeq * h->interiorSplitPct / 100) : (multi ? h->nSeq : h->nElem);
     auto mark = [&](int id, cudaStream_t s) {
         if (!h->timeline) return;
         if (!h->tl[id]) cudaEventCreate(&h->tl[id]);
@@ -831,7 +838,7 @@ int residual(h3d_context* h, const RkArgs& rk) {
         CTX_CHECK(cudaEventRecord(h->evA, h->sComm));
     }
     if (grads) {
-        { ProfScope ps(h, 0, sc); if ((rc = doGradient(h, 0, h->nSeq, sc))) return rc; }
+        { ProfScope ps(h, 0, sc); if ((rc = doGradient(h, 0, nCut, sc)) || (rc = doGradient(h, nCut, h->nSeq, sc))) return rc; }
         mark(3, sc);
         if (multi) {
             CTX_CHECK(cudaStreamWaitEvent(sc, h->evA, 0));
@@ -851,7 +858,7 @@ int residual(h3d_context* h, const RkArgs& rk) {
     }
     { ProfScope ps(h, 1, sc); if ((rc = doRiemann(h, 0, h->nFaceLocal, sc))) return rc; }
     mark(7, sc);
-    { ProfScope ps(h, 2, sc); if ((rc = doVolume(h, rk, 0, multi ? h->nSeq : h->nElem, sc))) return rc; }
+    { ProfScope ps(h, 2, sc); if ((rc = doVolume(h, rk, 0, nCut, sc)) || (rc = doVolume(h, rk, nCut, multi ? h->nSeq : h->nElem, sc))) return rc; }
     mark(8, sc);
     if (multi) {
         if (grads && h->ph.ns) CTX_CHECK(cudaStreamWaitEvent(sc, h->evB, 0));
@@ -899,6 +906,7 @@ int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nc
     if (prop.major != 10) return fail(std::string("libh3dgpu is built for sm_100a only; device is ") + prop.name);
     h->numSMs = prop.multiProcessorCount;
     if (const char* ev = std::getenv("H3D_COMM_SMS")) h->commSMs = std::max(0, std::atoi(ev));
+    if (const char* ev = std::getenv("H3D_INTERIOR_SPLIT_PCT")) h->interiorSplitPct = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_USE_MMA")) h->useMma = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_GEN2")) h->useGen2 = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_USE_TMA")) h->useTma = std::atoi(ev);   // experiments: H3D_USE_TMA=0 selects the plain-load kernels
@@ -913,7 +921,7 @@ int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nc
         ncclUniqueId id; std::memcpy(&id, nccl_unique_id, 128);
         // the send/recv kernels of the halo exchange get the multiprocessors the persistent kernels leave free, no more
         ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
-        if (h->commSMs > 0) cfg.maxCTAs = h->commSMs;
+        cfg.maxCTAs = h->commSMs > 0 ? h->commSMs : 8;
         ncclResult_t r = ncclCommInitRankConfig(&h->comm, nranks, id, rank, &cfg);
         if (r != ncclSuccess) return fail(std::string("ncclCommInitRankConfig: ") + ncclGetErrorString(r));
     }
@@ -1645,6 +1653,7 @@ int h3d_set_option(h3d_handle h, const char* kv) {
     if (key == "profile_kernels") { h->profile = val; return 0; }
     if (key == "use_tma") { h->useTma = val; return 0; }
     if (key == "comm_sms") { h->commSMs = std::max(0, val); return 0; }
+    if (key == "interior_split_pct") { h->interiorSplitPct = val; return 0; }
     if (key == "timeline") { h->timeline = val; return 0; }
     if (key == "mma") { h->useMma = val; return 0; }
     if (key == "gen2") { h->useGen2 = val; return 0; }

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "geometry.hpp"
+#include "gmsh.hpp"
 #include "partition.hpp"
 
 using namespace h3d;
@@ -31,7 +32,10 @@ void* h3dhost_mesh_box(int nex, int ney, int nez, double L, double amp, int bFac
 
 void* h3dhost_mesh_read(const char* path) {
     Host* h = new Host();
-    if (!readSpecMesh(path, h->mesh, g_err)) { delete h; return nullptr; }
+    // as the reference's mesh-file dispatch (ReadMeshFile.f90:37-77): the extension selects the reader
+    const std::string p(path);
+    const bool gmsh = p.size() > 4 && p.compare(p.size() - 4, 4, ".msh") == 0;
+    if (!(gmsh ? readGmsh(p, h->mesh, g_err) : readSpecMesh(p, h->mesh, g_err))) { delete h; return nullptr; }
     return h;
 }
 

@@ -11,7 +11,7 @@ import pytest
 from horses3d_b200 import build
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CYLINDER_MESH = "/root/reference/Solver/test/TestMeshes/CylinderNSpol3.mesh"
+CYLINDER_MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "CylinderNSpol3.mesh")   # the reference's Solver/test/TestMeshes/CylinderNSpol3.mesh, copied
 K1_RES = np.array([1.6417830052388520E-05, 1.2677577061211545E-01, 1.2677577048633804E-01, 2.4981129585617484E-01, 6.2174425106488129E-01])
 
 

@@ -1,4 +1,6 @@
 """Pins of the CPU oracle against the reference's own known answers.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -66,10 +68,10 @@ def test_k2_euler_taylor_green_kepec_10_steps():
     assert abs(rec["enstrophy"] - 0.37500245097897006) < 1.0e-11
 
 
-CYLINDER_MESH = "/root/reference/Solver/test/TestMeshes/CylinderNSpol3.mesh"
+CYLINDER_MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "CylinderNSpol3.mesh")   # the reference's Solver/test/TestMeshes/CylinderNSpol3.mesh, copied
 
 
-def _cylinder_100_steps(nodes=GAUSS, **phys_kw):
+def _cylinder_100_steps(nodes=GAUSS, api=None, **phys_kw):
     """Solver/test/NavierStokes/Cylinder*: Re 200, M 0.3, P=3 Gauss, Roe, BR1, RK3, cfl = dcfl = 0.3, 100 steps on the curved
     (bFaceOrder 3) cylinder mesh with no-slip wall, free-slip walls, inflow and outflow."""
     import math
@@ -93,7 +95,7 @@ def _cylinder_100_steps(nodes=GAUSS, **phys_kw):
     assert m.sizes()[:2] == (1864, 6182)
     if phys.les_wall_model:
         m.wall_distances()
-    sem = DGSem(oracle_api.OracleApi(), m, phys)
+    sem = DGSem(api if api is not None else oracle_api.OracleApi(), m, phys)
     u, v, w = math.cos(theta) * math.cos(phi), math.sin(theta) * math.cos(phi), math.sin(phi)   # ProblemFile.f90:304-322
     Q = np.zeros(sem.node_coordinates().shape[:-1] + (5,))
     Q[..., 0], Q[..., 1], Q[..., 2], Q[..., 3] = 1.0, u, v, w
@@ -289,7 +291,7 @@ def test_k11_energy_and_entropy_conserving_tests_10_steps(case):
     assert abs(wake_u - wu0) < 1.0e-11
 
 
-UNIT_CUBE_MESH = "/root/reference/Solver/test/TestMeshes/UnitCube4x4.mesh"
+UNIT_CUBE_MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "UnitCube4x4.mesh")   # the reference's Solver/test/TestMeshes/UnitCube4x4.mesh, copied
 
 
 PERIODIC_BOX = [("front", "periodic", "back"), ("back", "periodic", "front"), ("bottom", "periodic", "top"), ("top", "periodic", "bottom"),
@@ -451,7 +453,7 @@ def test_rk_step_equals_its_stages():
     assert np.array_equal(res[0], res[1])
 
 
-BOX27_MESH = "/root/reference/Solver/test/TestMeshes/Box27.mesh"
+BOX27_MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "Box27.mesh")   # the reference's Solver/test/TestMeshes/Box27.mesh, copied
 
 
 @pytest.mark.skipif(not __import__("os").path.exists(BOX27_MESH), reason="reference test mesh not available on this machine")
@@ -489,7 +491,7 @@ def test_k12_euler_uniform_flow_rusanov_iterations_to_tolerance():
     assert np.abs(sem.Q() - Q0).max() < 1.0e-10
 
 
-BOX_CIRCLE_MESH = "/root/reference/Solver/test/TestMeshes/BoxAroundCircle3D_extended_pol3.mesh"
+BOX_CIRCLE_MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "BoxAroundCircle3D_extended_pol3.mesh")   # the reference's Solver/test/TestMeshes/BoxAroundCircle3D_extended_pol3.mesh, copied
 
 
 @pytest.mark.skipif(not __import__("os").path.exists(BOX_CIRCLE_MESH), reason="reference test mesh not available on this machine")
