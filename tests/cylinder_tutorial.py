@@ -41,10 +41,11 @@ def initial_condition(x, phys):
     return Q
 
 
-def run(sem, steps):
-    """`steps` CFL-limited RK3 steps; returns the residuals and the drag / lift monitors of the control file."""
+def run(sem, steps, cfl=0.3):
+    """`steps` CFL-limited RK3 steps; returns the residuals and the drag / lift monitors of the control file.  The tutorial runs
+    cfl = dcfl = 0.6 from the converged Re 40 field (restart = .true.); the impulsive start used here (no restart file) needs 0.3."""
     sem.set_Q(initial_condition(sem.node_coordinates(), sem.physics))
-    res = sem.integrate(steps, cfl=0.6, dcfl=0.6, monitors=False)[-1]["residuals"]
+    res = sem.integrate(steps, cfl=cfl, dcfl=cfl, monitors=False)[-1]["residuals"]
     cd = sem.surface_monitor("cylinder", "drag", [1.0, 0.0, 0.0], reference_surface=1.0)
     cl = sem.surface_monitor("cylinder", "lift", [0.0, 1.0, 0.0], reference_surface=1.0)
     return np.array(res), cd, cl

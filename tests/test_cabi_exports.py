@@ -67,3 +67,38 @@ def test_fortran_interfaces_are_in_step_with_the_header():
     for name, _ in H3dPhysics._fields_:
         assert re.search(r":: %s\b" % name, text), name
     assert max(len(l) for l in text.splitlines()) <= 132
+
+
+def test_fortran_adapter_calls_match_the_interface_block():
+    """integration/H3DGpuAdapter.f90 (the module a maintainer adds to the reference; no Fortran compiler here): every h3d_*
+    entry point it calls must be declared in the generated interface block with the same number of arguments."""
+    import re
+    iface = open(os.path.join(ROOT, "integration", "h3d_gpu_interfaces.f90")).read()
+    decl = {}
+    for m in re.finditer(r"function\s+(h3d_[a-zA-Z_0-9]+)\s*\((.*?)\)\s*bind", iface.replace("&\n", " "), flags=re.S):
+        decl[m.group(1).lower()] = len([a for a in m.group(2).split(",") if a.strip()])
+    src = open(os.path.join(ROOT, "integration", "H3DGpuAdapter.f90")).read()
+    src = "\n".join(l.split("!")[0] for l in src.splitlines()).replace("&\n", " ")
+    calls = 0
+    for m in re.finditer(r"\b(h3d_[a-z_0-9]+)\s*\(", src, flags=re.I):
+        name = m.group(1).lower()
+        if name.startswith("h3d_gpu_") or name not in decl:
+            assert name.startswith("h3d_gpu_") or name == "h3d_stepper", "unknown entry point %s" % name
+            continue
+        depth, i, args, cur = 1, m.end(), [], ""
+        while depth:                                   # split the argument list at top-level commas
+            c = src[i]
+            depth += c in "([" ; depth -= c in ")]"
+            if depth == 1 and c == ",":
+                args.append(cur); cur = ""
+            elif depth:
+                cur += c
+            i += 1
+        args.append(cur)
+        assert len([a for a in args if a.strip()]) == decl[name], (name, args, decl[name])
+        calls += 1
+    assert calls >= 18
+    # the hooks the adapter exports are the ones INTEGRATION.md lists
+    for hook in ("ComputeTimeDerivative_GPU", "TakeRK3Step_GPU", "TakeRK5Step_GPU", "ComputeMaxResiduals_GPU", "MaxTimeStep_GPU",
+                 "ScalarVolumeIntegral_GPU", "checkForNan_GPU", "h3d_gpu_setup", "h3d_gpu_download_state"):
+        assert hook in src and hook in open(os.path.join(ROOT, "INTEGRATION.md")).read(), hook

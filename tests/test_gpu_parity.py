@@ -349,6 +349,31 @@ def test_k1_taylor_green_on_gpu(gpu_api_cls):
     assert abs(rec["enstrophy"] - 3.7499683882517909E-01) < 1.0e-11
 
 
+def test_k5_cylinder_regressions_on_gpu(gpu_api_cls):
+    """The reference's Cylinder and CylinderSmagorinsky regressions (K5, K5b: the curved CylinderNSpol3.mesh with no-slip, free-slip,
+    inflow and outflow zones, 100 CFL-limited RK3 steps, drag / lift monitors, wake probe) run on the DEVICE path against the values
+    and tolerances of Solver/test/NavierStokes/Cylinder*/SETUP/ProblemFile.f90 (mesh copied to tests/golden/)."""
+    from test_oracle_pins import _cylinder_100_steps
+    got, cd, cl, wake_u = _cylinder_100_steps(api=gpu_api_cls())
+    res = np.array([8.8131248889811715E+00, 1.7608838068776613E+01, 1.9037533106262516E-01, 2.4301352846288605E+01, 2.4063786464536835E+02])
+    assert np.abs((got - res) / res).max() < 1.0e-11
+    assert abs(cd - 3.4573345486345943E+01) < 1.0e-11 * 35.0 and abs(cl - (-4.6800322917661674E-04)) < 1.0e-11
+    assert abs(wake_u - 1.0965307794823676E-08) < 1.0e-11
+    got, cd, cl, wake_u = _cylinder_100_steps(api=gpu_api_cls(), les="smagorinsky", les_wall_model="linear")
+    res = np.array([7.58705681758851, 15.5542852761418, 0.231394835496677, 20.0848567943827, 207.594579145771])
+    assert np.abs(got - res).max() < 1.0e-7
+    assert abs(cd - 34.9438869828619) < 1.0e-11 * 35.0 and abs(cl - (-1.582092121135137E-004)) < 1.0e-11
+    assert abs(wake_u - 9.867445291005896E-009) < 1.0e-11
+
+
+def test_k4_box_around_circle_regressions_on_gpu(gpu_api_cls):
+    """The reference's Euler/BoxAroundCircle (StandardDG) and BoxAroundCirclePirozzoli (SplitDG) regressions (K4b, K4: 1000 steps on
+    the curved mesh around a cylinder) on the DEVICE path: final time, residuals, force and pressure monitors, wake probe."""
+    from test_oracle_pins import k4_case, k4b_case
+    k4b_case(gpu_api_cls())
+    k4_case(gpu_api_cls())
+
+
 @pytest.mark.parametrize("case", ["state", "energy", "entropy"])
 def test_k3_k10_convergence_p7_on_gpu(gpu_api_cls, case):
     """The reference's Convergence, Convergence_energy and Convergence_entropy regressions (K3, K10: P=7, manufactured solution

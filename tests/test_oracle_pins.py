@@ -494,8 +494,11 @@ def test_k12_euler_uniform_flow_rusanov_iterations_to_tolerance():
 BOX_CIRCLE_MESH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "BoxAroundCircle3D_extended_pol3.mesh")   # the reference's Solver/test/TestMeshes/BoxAroundCircle3D_extended_pol3.mesh, copied
 
 
-@pytest.mark.skipif(not __import__("os").path.exists(BOX_CIRCLE_MESH), reason="reference test mesh not available on this machine")
 def test_k4b_box_around_circle_standard_dg_1000_steps():
+    k4b_case(oracle_api.OracleApi())
+
+
+def k4b_case(api):
     """Solver/test/Euler/BoxAroundCircle: the same case with the standard DG discretization on Gauss nodes (standard Roe solver,
     RK3, cfl 0.7, 1000 steps).  Final time, residuals, wake probe and pressure average with the 1e-11 tolerance of
     SETUP/ProblemFile.f90:340-400, the drag monitor (453.58) with its 1e-10."""
@@ -510,7 +513,7 @@ def test_k4b_box_around_circle_standard_dg_1000_steps():
     params = [bc_parameters("inflow", phys, rho=rho_in, v=v_in, aoa_theta=0.0, aoa_phi=0.0, p=p_in) if t == "inflow" else bc_parameters(t, phys)
               for _, t in zones]
     m = HostMesh.read(BOX_CIRCLE_MESH).connect([(z, t, None) for z, t in zones], np.array(params)).geometry(3, GAUSS)
-    sem = DGSem(oracle_api.OracleApi(), m, phys)
+    sem = DGSem(api, m, phys)
     Q = np.zeros(sem.node_coordinates().shape[:-1] + (5,))
     Q[..., 0], Q[..., 1] = 1.0, 1.0
     Q[..., 4] = (1.0 / phys.gammaM2) / (phys.gamma - 1.0) + 0.5
@@ -529,8 +532,11 @@ def test_k4b_box_around_circle_standard_dg_1000_steps():
     assert abs(cd - 453.57879703318662) < 1.0e-10      # the reference's own tolerance
 
 
-@pytest.mark.skipif(not __import__("os").path.exists(BOX_CIRCLE_MESH), reason="reference test mesh not available on this machine")
 def test_k4_box_around_circle_pirozzoli_1000_steps():
+    k4_case(oracle_api.OracleApi())
+
+
+def k4_case(api):
     """Solver/test/Euler/BoxAroundCirclePirozzoli: Euler, M 0.3, P=3 Gauss-Lobatto, split-form with the Pirozzoli two-point
     flux, standard Roe solver, RK3, cfl 0.7, 1000 steps on the curved mesh around a cylinder (free-slip walls, inflow).
     Final time (the sum of the CFL steps) and residuals with the 1e-11 tolerance of SETUP/ProblemFile.f90:322-363."""
@@ -545,7 +551,7 @@ def test_k4_box_around_circle_pirozzoli_1000_steps():
               for _, t in zones]
     m = HostMesh.read(BOX_CIRCLE_MESH).connect([(z, t, None) for z, t in zones], np.array(params)).geometry(3, GAUSSLOBATTO)
     assert m.sizes()[0] == 400
-    sem = DGSem(oracle_api.OracleApi(), m, phys)
+    sem = DGSem(api, m, phys)
     Q = np.zeros(sem.node_coordinates().shape[:-1] + (5,))
     Q[..., 0], Q[..., 1] = 1.0, 1.0
     Q[..., 4] = (1.0 / phys.gammaM2) / (phys.gamma - 1.0) + 0.5
