@@ -60,15 +60,16 @@ struct h3d_context {
     int useGen2 = 0;     // n = 8 StandardDG / BR1: second-generation kernels (256 threads, two CTAs per SM), h3d_kernels2.cuh
     int useMma = 0;      // n = 8 staged StandardDG / BR1 kernels: contractions on the FP64 tensor cores (DMMA); not bit-identical to the oracle
     int numSMs = 148;
-    // SMs the persistent element kernels leave free when the rank has neighbours: a persistent kernel holds every SM it runs on
-    // (all registers, most of the shared memory), so the pack / NCCL / unpack kernels of the communication stream could not start
-    // before it drained and the "overlap" was a serialisation.  Option comm_sms.
-    int commSMs = 0;
-    // ... instead the interior-element launches are cut in two (interiorSplitPct % / rest): when the first part retires, the
-    // high-priority halo kernels take the multiprocessors they need and run beside the second part.  Measured at N=2, 64^3 P=7
-    // (profiles/r2_h_multirank): reserving 8 SMs costs 2.6 % of the step, no reservation leaves the Q-trace exchange waiting for
-    // the whole interior gradient kernel.  Options comm_sms, interior_split_pct.
-    int interiorSplitPct = 70;
+    // Halo overlap on a rank with neighbours.  A persistent kernel holds every SM it runs on (all registers, most of the shared
+    // memory), so the pack / NCCL / unpack kernels of the communication stream cannot start before it drains: the "overlap" of
+    // round 1 was a serialisation (timeline in profiles/r2_h_multirank: the Q-trace exchange ended 0.3 ms after
+    // the interior gradient kernel instead of 0.9 ms after the start).  Cutting the interior launch in two does not help either
+    // (profiles/r2_j_multirank): only the first kernel of the exchange finds the gap.  So the FIRST interiorSplitPct % of the interior
+    // elements run on numSMs - commSMs multiprocessors, leaving commSMs to the high-priority communication stream for as long as
+    // an exchange takes, and the rest runs on all of them.  Options comm_sms, interior_split_pct.
+    int commSMs = 8;
+    int interiorSplitPct = 30;
+    bool reserveNow = false;       // the launch being issued is such a first part
     std::vector<std::pair<const void*, int>> occCache;
     // per-stage timeline (option timeline=1): events on both streams at the phase boundaries of the last residual evaluation
     int timeline = 0; cudaEvent_t tl[11] = {nullptr}; bool tlRecorded[11] = {false};
@@ -591,7 +592,7 @@ __global__ void k_halo_unpack(DevMesh m, const int* haloFace, const int* haloSid
 // ---- launch helpers --------------------------------------------------------------------------------------
 // persistent kernels: one resident wave, sized by the occupancy the kernel really gets (cached per function)
 int persistentGrid(h3d_context* h, const void* fn, int threads, size_t smemBytes) {
-    const int sms = std::max(1, h->numSMs - (h->nNbr > 0 ? h->commSMs : 0));
+    const int sms = std::max(1, h->numSMs - (h->reserveNow ? h->commSMs : 0));
     for (auto& p : h->occCache) if (p.first == fn) return p.second * sms;
     int perSM = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, threads, smemBytes) != cudaSuccess || perSM < 1) perSM = 1;
@@ -820,7 +821,7 @@ int residual(h3d_context* h, const RkArgs& rk) {
         if (multi && (rc = shareFaceH(h))) return rc;   // both ranks of an MPI face must use the same penalty
     }
     // first part of the interior elements (see interiorSplitPct); the launch helpers skip empty ranges
-    const int nCut = (multi && h->interiorSplitPct > 0 && h->interiorSplitPct < 100) ? (int)((long long)h->nSeq * h->interiorSplitPct / 100) : (multi ? h->nSeq : h->nElem);
+    const int nCut = !multi ? h->nElem : (h->interiorSplitPct <= 0 ? 0 : (h->interiorSplitPct >= 100 ? h->nSeq : (int)((long long)h->nSeq * h->interiorSplitPct / 100)));
     auto mark = [&](int id, cudaStream_t s) {
         if (!h->timeline) return;
         if (!h->tl[id]) cudaEventCreate(&h->tl[id]);
@@ -838,7 +839,7 @@ int residual(h3d_context* h, const RkArgs& rk) {
         CTX_CHECK(cudaEventRecord(h->evA, h->sComm));
     }
     if (grads) {
-        { ProfScope ps(h, 0, sc); if ((rc = doGradient(h, 0, nCut, sc)) || (rc = doGradient(h, nCut, h->nSeq, sc))) return rc; }
+        { ProfScope ps(h, 0, sc); h->reserveNow = multi; rc = doGradient(h, 0, nCut, sc); h->reserveNow = false; if (rc || (rc = doGradient(h, nCut, h->nSeq, sc))) return rc; }
         mark(3, sc);
         if (multi) {
             CTX_CHECK(cudaStreamWaitEvent(sc, h->evA, 0));
@@ -858,7 +859,7 @@ int residual(h3d_context* h, const RkArgs& rk) {
     }
     { ProfScope ps(h, 1, sc); if ((rc = doRiemann(h, 0, h->nFaceLocal, sc))) return rc; }
     mark(7, sc);
-    { ProfScope ps(h, 2, sc); if ((rc = doVolume(h, rk, 0, nCut, sc)) || (rc = doVolume(h, rk, nCut, multi ? h->nSeq : h->nElem, sc))) return rc; }
+    { ProfScope ps(h, 2, sc); h->reserveNow = multi; rc = doVolume(h, rk, 0, nCut, sc); h->reserveNow = false; if (rc || (rc = doVolume(h, rk, nCut, multi ? h->nSeq : h->nElem, sc))) return rc; }
     mark(8, sc);
     if (multi) {
         if (grads && h->ph.ns) CTX_CHECK(cudaStreamWaitEvent(sc, h->evB, 0));

@@ -284,9 +284,9 @@ int h3d_kernel_profile(h3d_handle h, double* out, int len);
 int h3d_stage_timeline(h3d_handle h, double* marks_ms, int len);
 /* option string "key=value"; unknown keys are an error.  store_qdot_every_stage=1 | profile_kernels=1 | timeline=1 |
  * use_tma=0 (plain-load kernels) | mma=1 (n = 8: contractions on the FP64 tensor cores, not bit-identical to the CUDA-core
- * summation order) | gen2=1 (n = 8: 256-thread kernels, two CTAs per SM) | comm_sms=K (multiprocessors the persistent kernels
- * leave to the halo exchange on a rank with neighbours, default 0) | interior_split_pct=P (the interior-element launches of a
- * rank with neighbours are cut at P % so that the halo kernels can start beside the rest, default 70) */
+ * summation order) | gen2=1 (n = 8: 256-thread kernels, two CTAs per SM) | comm_sms=K, interior_split_pct=P (on a rank with
+ * neighbours the first P % of the interior elements run on all but K multiprocessors, which the halo exchange uses meanwhile;
+ * defaults 8 and 30) */
 int h3d_set_option(h3d_handle h, const char* key_value);
 
 #ifdef __cplusplus
