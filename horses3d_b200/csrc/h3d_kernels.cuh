@@ -13,9 +13,9 @@
 // Kernels per RK stage: gradient (element) -> riemann (face) -> volume+lift+RK (+ fused prolongation of the
 // updated state for the next stage).
 //
-// Element kernels: one element per group of TPE threads, NPT nodes per thread (2 at n >= 7 so that two CTAs
-// fit the register file of an SM and their load / contraction / store phases overlap), shared-memory fields
-// padded to an odd row length (conflict-free strided trace reads).  Every sum keeps the reference's order.
+// Element kernels: one node per thread, EPB elements per CTA (one where an element has 128 nodes or more); the work fields the
+// contraction reads are unpadded, the buffers the prolongation reads along lines are padded to an odd row length (conflict-free
+// strided trace reads).  Every sum keeps the reference's order.  (Two nodes per thread and two CTAs per SM: h3d_kernels2.cuh.)
 #pragma once
 #include <cuda_runtime.h>
 
@@ -62,23 +62,18 @@ struct RkArgs {
     int copyG;       // mode 2, first stage: G = Q before the update
 };
 
-#ifndef H3D_NPT_THRESHOLD
-#define H3D_NPT_THRESHOLD 100000   // nodes per element from which a thread takes two nodes (disabled: the 128-register cap spills, profiles/r1_c)
-#endif
-
 template <int n>
 struct KCfg {
     static constexpr int N2 = n * n, N3 = n * n * n;
     static constexpr int NP = (n % 2 == 0) ? n + 1 : n;       // padded row length (odd)
     static constexpr int NS = N2 * NP;                        // padded nodes per shared-memory field
-    static constexpr int NPT = (N3 >= H3D_NPT_THRESHOLD) ? 2 : 1;   // nodes per thread
-    static constexpr int TPE = (N3 + NPT - 1) / NPT;          // threads per element
+    static constexpr int TPE = N3;                            // threads per element: one node per thread
     static constexpr int EPB = (TPE >= 128) ? 1 : 256 / TPE;  // elements per CTA
     static constexpr int NT = TPE * EPB;                      // threads per CTA
     static constexpr int MINB = (NT <= 256) ? 2 : 1;          // CTAs per SM the register allocation must allow
     // Persistent variant with bulk-async (TMA) prefetch of the next tile's fields: needs 16-byte aligned, 16-byte
     // multiple runs per field (EPB*N3 even) and the staged fields to fit beside the work buffers (n <= 8).
-    static constexpr bool TMA_OK = (n % 2 == 0) && (n <= 8) && (NPT == 1);
+    static constexpr bool TMA_OK = (n % 2 == 0) && (n <= 8);
     __host__ __device__ static constexpr int pidx(int node) { return (node / n) * NP + node % n; }
 };
 
@@ -137,6 +132,39 @@ __device__ __forceinline__ void prolong_axis(const DevMesh& m, const Ops<n>& ops
     }
 }
 
+// All three axes of one field at once (EPB == 1 kernels): six independent accumulation chains per field instead of two, so the
+// 8-cycle latency of the dependent DADDs overlaps (the phase was bound by exactly that: short_sb / wait stalls at a third of the
+// FP64 and shared-memory rates, profiles/r2_f_bench_default/regions_core.txt).  Per line the summation order is unchanged.
+template <int n, int NV>
+__device__ __forceinline__ void prolong_fused(const DevMesh& m, const Ops<n>& ops, const double* __restrict__ sF, const int* __restrict__ sTr,
+                                              const int* __restrict__ sInfo, double* __restrict__ dst) {
+    using C = KCfg<n>;
+    constexpr int N2 = C::N2, NP = C::NP, NS = C::NS, NT = C::NT, ROWS = NT / N2;
+    const size_t fstride = (size_t)m.nFace * N2;
+    const int ab = threadIdx.x % N2, a = ab % n, b = ab / n;
+    const int bx = (b * n + a) * NP, by = (b * n) * NP + a, bz = b * NP + a;
+    const int lfs[6] = {5, 3, 0, 1, 2, 4};   // faces LEFT, RIGHT | FRONT, BACK | BOTTOM, TOP
+    int off[6];                              // trace offset, side in the sign bit (kept as six ints: six pointers spill)
+#pragma unroll
+    for (int s = 0; s < 6; ++s) off[s] = sTr[lfs[s] * N2 + ab] | ((sInfo[lfs[s]] & 1) << 31);
+#pragma unroll 1
+    for (int vv = threadIdx.x / N2; vv < NV; vv += ROWS) {
+        const double* src = sF + vv * NS;
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int l = 0; l < n; ++l) {
+            const double sx = src[bx + l], sy = src[by + l * NP], sz = src[bz + l * n * NP];
+            const double v0 = ops.v[l], v1 = ops.v[n + l];
+            acc[0] = acc[0] + sx * v0; acc[1] = acc[1] + sx * v1;
+            acc[2] = acc[2] + sy * v0; acc[3] = acc[3] + sy * v1;
+            acc[4] = acc[4] + sz * v0; acc[5] = acc[5] + sz * v1;
+        }
+        const size_t fo = (size_t)((vv / 5) * 10 + vv % 5) * fstride;
+#pragma unroll
+        for (int s = 0; s < 6; ++s) dst[fo + (off[s] < 0 ? 5 * fstride : 0) + (size_t)(off[s] & 0x7fffffff)] = acc[s];
+    }
+}
+
 template <int n, int NV>
 __device__ __forceinline__ void prolong_block(const DevMesh& m, const Ops<n>& ops, const double* __restrict__ sF,
                                               const int* __restrict__ sTr, const int* __restrict__ sInfo, double* __restrict__ dst, int nLocal) {
@@ -144,6 +172,7 @@ __device__ __forceinline__ void prolong_block(const DevMesh& m, const Ops<n>& op
     // memory and contracted with both end vectors, giving the traces on the two opposite faces of that axis.
     // The trace node ab of a thread is fixed (NT is a multiple of n^2); items advance over (element, field).
     static_assert(KCfg<n>::NT % KCfg<n>::N2 == 0, "threads per CTA must be a multiple of n^2");
+    if (KCfg<n>::EPB == 1) { prolong_fused<n, NV>(m, ops, sF, sTr, sInfo, dst); return; }
     prolong_axis<n, NV, 0>(m, ops, sF, sTr, sInfo, dst, nLocal);
     prolong_axis<n, NV, 1>(m, ops, sF, sTr, sInfo, dst, nLocal);
     prolong_axis<n, NV, 2>(m, ops, sF, sTr, sInfo, dst, nLocal);
@@ -199,7 +228,7 @@ __device__ __forceinline__ void load_face_tables(const DevMesh& m, int* sTr, int
 template <int n>
 __global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
-    constexpr int N3 = C::N3, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE;
+    constexpr int N3 = C::N3, NS = C::NS, EPB = C::EPB, TPE = C::TPE;
     extern __shared__ double smem[];
     double* sQ = smem;                  // [EPB][5][NS]
     double* sV = sQ + EPB * 5 * NS;     // [2][n]
@@ -212,10 +241,9 @@ __global__ void __launch_bounds__(KCfg<n>::NT) k_prolong_q(DevMesh m, const __gr
     load_face_tables<n>(m, sTr, sInfo, e0, nLocal);
     const size_t es = (size_t)m.nElem * N3;
     if (e < eEnd) {
-#pragma unroll
-        for (int r = 0; r < NPT; ++r) {
-            const int node = tn + r * TPE;
-            if (node < N3) {
+        {
+            const int node = tn;
+            {
                 const double* q = m.Q + (size_t)e * N3 + node;
 #pragma unroll
                 for (int c = 0; c < 5; ++c) sQ[(le * 5 + c) * NS + C::pidx(node)] = q[c * es];
@@ -320,8 +348,8 @@ __device__ __forceinline__ void grad_iface_store(const DevMesh& m, const Phys& p
 template <int n, bool TMA, bool VISC = false, bool MMA = false>
 __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh m, Phys ph, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
-    static_assert(!MMA || (n == 8 && TMA && !VISC && C::EPB == 1 && C::NPT == 1), "the DMMA contraction is written for the staged n = 8 BR1 kernel");
-    constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
+    static_assert(!MMA || (n == 8 && TMA && !VISC && C::EPB == 1), "the DMMA contraction is written for the staged n = 8 BR1 kernel");
+    constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;                  // nodes of one tile
     constexpr int UW = TMA ? N3 : NS;              // per-field stride of the state in shared memory
     constexpr int ULD = TMA ? n : NP;              // row length of the state in shared memory
@@ -403,10 +431,9 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
         }
         if (!TMA) {
             if (active) {
-#pragma unroll
-                for (int r = 0; r < NPT; ++r) {
-                    const int node = tn + r * TPE;
-                    if (node < N3) {
+                {
+                    const int node = tn;
+                    {
                         const double* q = m.Q + (size_t)e * N3 + node;
                         if (VISC) {   // GetGradientValues at every node (HexElementClass.f90:466-470)
                             double Qn[5], Un[5];
@@ -428,12 +455,11 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
         }
         __syncthreads();
         if constexpr (MMA) mma_gradient_contract<NT / 32, TN3, NS>(sU, sG, sDT);   // U_xi, U_eta, U_zeta of the 5 variables -> sG
-        double g[NPT][15];
+        double g[15];
         if (active) {
-#pragma unroll
-            for (int r = 0; r < NPT; ++r) {
-                const int node = tn + r * TPE;
-                if (node < N3) {
+            {
+                const int node = tn;
+                {
                     const int i = node % n, j = (node / n) % n, k = node / N2;
                     double Uxi[5] = {0, 0, 0, 0, 0}, Ueta[5] = {0, 0, 0, 0, 0}, Uzeta[5] = {0, 0, 0, 0, 0};
                     // state field q of this element: TMA [q][le][node], else [le][q][padded node]
@@ -469,9 +495,9 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                     }
 #pragma unroll
                     for (int q = 0; q < 5; ++q) {
-                        g[r][q] = (Uxi[q] * ja[0] + Ueta[q] * ja[3] + Uzeta[q] * ja[6]) * iJ;
-                        g[r][5 + q] = (Uxi[q] * ja[1] + Ueta[q] * ja[4] + Uzeta[q] * ja[7]) * iJ;
-                        g[r][10 + q] = (Uxi[q] * ja[2] + Ueta[q] * ja[5] + Uzeta[q] * ja[8]) * iJ;
+                        g[q] = (Uxi[q] * ja[0] + Ueta[q] * ja[3] + Uzeta[q] * ja[6]) * iJ;
+                        g[5 + q] = (Uxi[q] * ja[1] + Ueta[q] * ja[4] + Uzeta[q] * ja[7]) * iJ;
+                        g[10 + q] = (Uxi[q] * ja[2] + Ueta[q] * ja[5] + Uzeta[q] * ja[8]) * iJ;
                     }
                     // lift: faceInt_d = sum over faces in the order L,R,FRONT,BACK,BOTTOM,TOP of unStar_d * b
                     const int lfOrder[6] = {5, 3, 0, 1, 2, 4};
@@ -505,32 +531,32 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
                         const int p = C::pidx(node);
                         if (ph.viscous != H3D_VISCOUS_BR1) {
 #pragma unroll
-                            for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                            for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[c];
                         }
                         const double iJs = ph.ipVariant * iJ;
 #pragma unroll
                         for (int q = 0; q < 5; ++q) {
-                            if (ph.viscous == H3D_VISCOUS_BR1) { g[r][q] = g[r][q] + fx[q] * iJ; g[r][5 + q] = g[r][5 + q] + fy[q] * iJ; g[r][10 + q] = g[r][10 + q] + fz[q] * iJ; }
-                            else if (ph.viscous == H3D_VISCOUS_BR2) { g[r][q] = g[r][q] - fx[q] * iJ; g[r][5 + q] = g[r][5 + q] - fy[q] * iJ; g[r][10 + q] = g[r][10 + q] - fz[q] * iJ; }
-                            else { g[r][q] = g[r][q] + fx[q] * iJs; g[r][5 + q] = g[r][5 + q] + fy[q] * iJs; g[r][10 + q] = g[r][10 + q] + fz[q] * iJs; }
-                            ox[q * es] = g[r][q]; oy[q * es] = g[r][5 + q]; oz[q * es] = g[r][10 + q];
+                            if (ph.viscous == H3D_VISCOUS_BR1) { g[q] = g[q] + fx[q] * iJ; g[5 + q] = g[5 + q] + fy[q] * iJ; g[10 + q] = g[10 + q] + fz[q] * iJ; }
+                            else if (ph.viscous == H3D_VISCOUS_BR2) { g[q] = g[q] - fx[q] * iJ; g[5 + q] = g[5 + q] - fy[q] * iJ; g[10 + q] = g[10 + q] - fz[q] * iJ; }
+                            else { g[q] = g[q] + fx[q] * iJs; g[5 + q] = g[5 + q] + fy[q] * iJs; g[10 + q] = g[10 + q] + fz[q] * iJs; }
+                            ox[q * es] = g[q]; oy[q * es] = g[5 + q]; oz[q * es] = g[10 + q];
                         }
                         if (ph.viscous == H3D_VISCOUS_BR1) {   // BR1 prolongs the lifted gradients
 #pragma unroll
-                            for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                            for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[c];
                         }
                     } else {
 #pragma unroll
                         for (int q = 0; q < 5; ++q) {
                             // Euler with "compute gradients": local gradient only (base-class ComputeGradient, EllipticDiscretizationClass.f90:122-187)
-                            if (ph.ns) { g[r][q] = g[r][q] + fx[q] * iJ; g[r][5 + q] = g[r][5 + q] + fy[q] * iJ; g[r][10 + q] = g[r][10 + q] + fz[q] * iJ; }
-                            ox[q * es] = g[r][q]; oy[q * es] = g[r][5 + q]; oz[q * es] = g[r][10 + q];
+                            if (ph.ns) { g[q] = g[q] + fx[q] * iJ; g[5 + q] = g[5 + q] + fy[q] * iJ; g[10 + q] = g[10 + q] + fz[q] * iJ; }
+                            ox[q * es] = g[q]; oy[q * es] = g[5 + q]; oz[q * es] = g[10 + q];
                         }
                     }
                     if (TMA) {   // the gradient buffer does not alias the inputs: store right away
                         const int p = C::pidx(node);
 #pragma unroll
-                        for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                        for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[c];
                     }
                 }
             }
@@ -541,13 +567,12 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_gradient(DevMesh
             if (next < nTiles) issue(next);
         } else if (!VISC) {
             if (active) {
-#pragma unroll
-                for (int r = 0; r < NPT; ++r) {
-                    const int node = tn + r * TPE;
-                    if (node < N3) {
+                {
+                    const int node = tn;
+                    {
                         const int p = C::pidx(node);
 #pragma unroll
-                        for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[r][c];
+                        for (int c = 0; c < 15; ++c) sG[(le * 15 + c) * NS + p] = g[c];
                     }
                 }
             }
@@ -678,8 +703,8 @@ template <int n, int MODE, bool TMA, bool GV = false, bool MMA = false>
 __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m, Phys ph, RkArgs rk, const __grid_constant__ Ops<n> ops, int eBegin, int eEnd) {
     using C = KCfg<n>;
     constexpr bool SPLIT = MODE != 0, EXT = MODE == 2;
-    static_assert(!MMA || (n == 8 && MODE == 0 && TMA && C::EPB == 1 && C::NPT == 1), "the DMMA contraction is written for the staged n = 8 StandardDG kernel");
-    constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, NPT = C::NPT, TPE = C::TPE, NT = C::NT;
+    static_assert(!MMA || (n == 8 && MODE == 0 && TMA && C::EPB == 1), "the DMMA contraction is written for the staged n = 8 StandardDG kernel");
+    constexpr int N2 = C::N2, N3 = C::N3, NP = C::NP, NS = C::NS, EPB = C::EPB, TPE = C::TPE, NT = C::NT;
     constexpr int TN3 = EPB * N3;
     // Work fields (fluxes; SplitDG: state, metrics, sixth primitive) are stored UNPADDED, node = (k n + j) n + i: the lines the
     // contraction reads are then broadcasts (xi, eta) or consecutive words (zeta), free of bank conflicts; rows padded to an
@@ -796,26 +821,25 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
         // SplitDG: per-node primitives are staged instead of the conserved state where the two-point flux allows it
         // (MODE 1 serves Kennedy-Gruber and Pirozzoli only and always does; MODE 2 decides at run time)
         const bool prim = (MODE == 1) || (EXT && prim_two_point_ok(ph.averaging));
-        double Qk[NPT][5];                   // state of the thread's nodes (kept for the update)
-        double Pk[NPT][SPLIT ? 6 : 1];       // SplitDG: primitives of the thread's nodes
-        double FinvD[NPT][SPLIT ? 15 : 1];   // SplitDG: consistent (diagonal) inviscid contravariant fluxes
+        double Qk[5];                        // state of the thread's node (kept for the update)
+        double Pk[SPLIT ? 6 : 1];            // SplitDG: primitives of the thread's node
+        double FinvD[SPLIT ? 15 : 1];        // SplitDG: consistent (diagonal) inviscid contravariant fluxes
         if (active) {
-#pragma unroll
-            for (int r = 0; r < NPT; ++r) {
-                const int node = tn + r * TPE;
-                if (node < N3) {
+            {
+                const int node = tn;
+                {
                     const int p = MMA ? swzF(node) : node;
                     const size_t go = (size_t)e * N3 + node;
                     const int so = le * N3 + node;
                     double ja[9];
                     if (TMA) {
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) Qk[r][q] = sIn[q * TN3 + so];
+                        for (int q = 0; q < 5; ++q) Qk[q] = sIn[q * TN3 + so];
 #pragma unroll
                         for (int c = 0; c < 9; ++c) ja[c] = sIn[(jaOff + c) * TN3 + so];
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) Qk[r][q] = m.Q[q * es + go];
+                        for (int q = 0; q < 5; ++q) Qk[q] = m.Q[q * es + go];
 #pragma unroll
                         for (int c = 0; c < 9; ++c) ja[c] = m.Ja[c * es + go];
                     }
@@ -832,9 +856,9 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
 #pragma unroll
                             for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[q * es + go]; gy[q] = m.Uy[q * es + go]; gz[q] = m.Uz[q * es + go]; }
                         }
-                        laminar_mu_kappa(ph, Qk[r], mu, kappa);
-                        if (ph.les != H3D_LES_NONE) { const double mut = smagorinsky<GV>(ph, m.lesDelta[e], ph.wallModel ? m.dWall[go] : 0.0, Qk[r], gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
-                        viscous_flux<GV>(ph, Qk[r], gx, gy, gz, mu, 0.0, kappa, F);
+                        laminar_mu_kappa(ph, Qk, mu, kappa);
+                        if (ph.les != H3D_LES_NONE) { const double mut = smagorinsky<GV>(ph, m.lesDelta[e], ph.wallModel ? m.dWall[go] : 0.0, Qk, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+                        viscous_flux<GV>(ph, Qk, gx, gy, gz, mu, 0.0, kappa, F);
 #pragma unroll
                         for (int q = 0; q < 5; ++q)
 #pragma unroll
@@ -843,26 +867,26 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                                 if (SPLIT) sF[((le * 3 + d) * 5 + q) * WS + p] = fv[q][d];
                             }
                     }
-                    euler_flux(ph, Qk[r], F);
+                    euler_flux(ph, Qk, F);
 #pragma unroll
                     for (int q = 0; q < 5; ++q)
 #pragma unroll
                         for (int d = 0; d < 3; ++d) {
                             const double fc = F[q][0] * ja[3 * d + 0] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
-                            if (SPLIT) FinvD[r][d * 5 + q] = fc;
+                            if (SPLIT) FinvD[d * 5 + q] = fc;
                             else sF[((le * 3 + d) * 5 + q) * WS + p] = fc - (ns ? fv[q][d] : 0.0);
                         }
                     if (SPLIT) {
                         if (prim) {
-                            node_primitives(ph, Qk[r], Pk[r]);
+                            node_primitives(ph, Qk, Pk);
                             if (HALF) {   // halved primitives and metrics (two_point_flux_half)
 #pragma unroll
-                                for (int q = 0; q < 6; ++q) Pk[r][q] = 0.5 * Pk[r][q];
+                                for (int q = 0; q < 6; ++q) Pk[q] = 0.5 * Pk[q];
                             }
-                            sX[le * WS + p] = Pk[r][5];
+                            sX[le * WS + p] = Pk[5];
                         }
 #pragma unroll
-                        for (int q = 0; q < 5; ++q) sQ[(le * 5 + q) * WS + p] = prim ? Pk[r][q] : Qk[r][q];
+                        for (int q = 0; q < 5; ++q) sQ[(le * 5 + q) * WS + p] = prim ? Pk[q] : Qk[q];
 #pragma unroll
                         for (int c = 0; c < 9; ++c) sJa[(le * 9 + c) * WS + p] = HALF ? 0.5 * ja[c] : ja[c];
                     }
@@ -879,10 +903,9 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
         if constexpr (MMA) mma_volume_contract<NT / 32>(sF, sHatDT);
         if (TMA) mbar_wait(bar + 1, parity ^ 1);   // J and G of this tile (parity was flipped after the first wait)
         if (active) {
-#pragma unroll
-            for (int r = 0; r < NPT; ++r) {
-                const int node = tn + r * TPE;
-                if (node < N3) {
+            {
+                const int node = tn;
+                {
                     const int i = node % n, j = (node / n) % n, k = node / N2;
                     const size_t go = (size_t)e * N3 + node;
                     const int bx = (k * n + j) * n, by = (k * n) * n + i, bz = j * n + i;
@@ -921,7 +944,7 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                                 double fsvv[5];
                                 if (l == me) {
 #pragma unroll
-                                    for (int q = 0; q < 5; ++q) fsvv[q] = FinvD[r][d * 5 + q];
+                                    for (int q = 0; q < 5; ++q) fsvv[q] = FinvD[d * 5 + q];
                                 } else {
                                     double Qo[6], jo[3];
 #pragma unroll
@@ -930,10 +953,10 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                                     for (int c = 0; c < 3; ++c) jo[c] = sJe[(3 * d + c) * WS + other];
                                     if (prim) {
                                         Qo[5] = sX[le * WS + other];
-                                        if (HALF) { if (l > me) two_point_flux_half(ph, Pk[r], Qo, jaMe, jo, fsvv); else two_point_flux_half(ph, Qo, Pk[r], jo, jaMe, fsvv); }
-                                        else if (l > me) two_point_flux_prim<EXT>(ph, Pk[r], Qo, jaMe, jo, fsvv); else two_point_flux_prim<EXT>(ph, Qo, Pk[r], jo, jaMe, fsvv);
+                                        if (HALF) { if (l > me) two_point_flux_half(ph, Pk, Qo, jaMe, jo, fsvv); else two_point_flux_half(ph, Qo, Pk, jo, jaMe, fsvv); }
+                                        else if (l > me) two_point_flux_prim<EXT>(ph, Pk, Qo, jaMe, jo, fsvv); else two_point_flux_prim<EXT>(ph, Qo, Pk, jo, jaMe, fsvv);
                                     } else {
-                                        if (l > me) two_point_flux<EXT>(ph, Qk[r], Qo, jaMe, jo, fsvv); else two_point_flux<EXT>(ph, Qo, Qk[r], jo, jaMe, fsvv);
+                                        if (l > me) two_point_flux<EXT>(ph, Qk, Qo, jaMe, jo, fsvv); else two_point_flux<EXT>(ph, Qo, Qk, jo, jaMe, fsvv);
                                     }
                                 }
                                 const double sd = sSharpDT[l * n + me], hd = sHatDT[l * n + me];
@@ -979,14 +1002,14 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
                             if (rk.storeQDot) m.QDot[q * es + go] = res;
                             const double gg = rk.a * Gk[q] + res;
                             m.G[q * es + go] = gg;
-                            Qk[r][q] = Qk[r][q] + rk.cdt * gg;
-                            m.Q[q * es + go] = Qk[r][q];
+                            Qk[q] = Qk[q] + rk.cdt * gg;
+                            m.Q[q * es + go] = Qk[q];
                         } else {   // TakeSSPRK33Step / TakeSSPRK43Step (ExplicitMethods.f90:983-1230)
                             if (rk.storeQDot) m.QDot[q * es + go] = res;
-                            const double g0 = rk.copyG ? Qk[r][q] : Gk[q];
+                            const double g0 = rk.copyG ? Qk[q] : Gk[q];
                             if (rk.copyG) m.G[q * es + go] = g0;
-                            Qk[r][q] = rk.a * g0 + rk.b * Qk[r][q] + rk.cdt * res;
-                            m.Q[q * es + go] = Qk[r][q];
+                            Qk[q] = rk.a * g0 + rk.b * Qk[q] + rk.cdt * res;
+                            m.Q[q * es + go] = Qk[q];
                         }
                     }
                 }
@@ -995,12 +1018,11 @@ __global__ void __launch_bounds__(KCfg<n>::NT, KCfg<n>::MINB) k_volume(DevMesh m
         if (rk.prolong) {
             __syncthreads();
             if (active) {
+                {
+                    const int node = tn;
+                    {
 #pragma unroll
-                for (int r = 0; r < NPT; ++r) {
-                    const int node = tn + r * TPE;
-                    if (node < N3) {
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) sP[(le * 5 + q) * NS + C::pidx(node)] = Qk[r][q];
+                        for (int q = 0; q < 5; ++q) sP[(le * 5 + q) * NS + C::pidx(node)] = Qk[q];
                     }
                 }
             }

@@ -6,7 +6,10 @@ n = sys.argv[3] if len(sys.argv) > 3 else "8"
 os.makedirs(out, exist_ok=True)
 txt = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
-want = {"k_gradientILi%sELb1" % n: "k_gradient_tma", "k_volumeILi%sELi0ELb1" % n: "k_volume_tma", "k_volumeILi%sELi1ELb1" % n: "k_volume_split_tma",
+want = {"k_gradientILi%sELb1ELb0ELb0" % n: "k_gradient_tma", "k_volumeILi%sELi0ELb1ELb0ELb0" % n: "k_volume_tma", "k_volumeILi%sELi1ELb1" % n: "k_volume_split_tma",
+        "k_gradientILi%sELb1ELb0ELb1" % n: "k_gradient_tma_dmma", "k_volumeILi%sELi0ELb1ELb0ELb1" % n: "k_volume_tma_dmma",
+        "k_volume2ILb0": "k_volume2", "k_volume2ILb1": "k_volume2_dmma", "k_gradient2ILb0": "k_gradient2", "k_gradient2ILb1": "k_gradient2_dmma",
+        "k_face_h_pack": "k_face_h_pack", "k_face_h_min": "k_face_h_min",
         "k_riemannILi%sELb0" % n: "k_riemann", "k_riemannILi%sELb1" % n: "k_riemann_ext", "k_prolong_qILi%s" % n: "k_prolong_q", "k_red_residual": "k_red_residual",
         "k_red_timestep": "k_red_timestep", "k_red_integralsE": "k_red_integrals", "k_red_integrals2": "k_red_integrals2", "k_red_ke_balance": "k_red_ke_balance",
         "k_stage_limiter": "k_stage_limiter", "k_halo_pack": "k_halo_pack", "k_halo_unpack": "k_halo_unpack",
@@ -22,7 +25,7 @@ for f in funcs:
             with open(os.path.join(out, "sass_%s_n%s.txt" % (short, n)), "w") as fh:
                 fh.write("// %s\n// %d instructions; opcode histogram: %s\n" % (name, len(ins), dict(ops.most_common(25))))
                 fh.write("\n".join(ins) + "\n")
-            summary.append("%-22s %6d instr  DFMA %4d DMUL %4d DADD %4d LDS %4d STS %4d LDG %4d STG %4d UBLKCP %3d SYNCS %3d BAR %2d" % (
-                short, len(ins), ops["DFMA"], ops["DMUL"], ops["DADD"], ops["LDS"], ops["STS"], ops["LDG"], ops["STG"], ops["UBLKCP"], ops["SYNCS"], ops["BAR"]))
+            summary.append("%-22s %6d instr  DMMA %3d DFMA %4d DMUL %4d DADD %4d LDS %4d STS %4d LDG %4d STG %4d UBLKCP %3d SYNCS %3d BAR %2d" % (
+                short, len(ins), ops["DMMA"], ops["DFMA"], ops["DMUL"], ops["DADD"], ops["LDS"], ops["STS"], ops["LDG"], ops["STG"], ops["UBLKCP"], ops["SYNCS"], ops["BAR"]))
 open(os.path.join(out, "sass_summary.txt"), "w").write("\n".join(sorted(summary)) + "\n")
 print("\n".join(sorted(summary)))
