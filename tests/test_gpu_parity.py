@@ -475,3 +475,27 @@ def test_errors_follow_the_reference_messages(gpu_api_cls):
         sem = DGSem(gpu_api_cls(), mesh, make_physics(flow="Euler", inviscid="split-form", averaging="pirozzoli"))
         sem.set_initial_condition(taylor_green_ic)
         sem.ComputeTimeDerivative(0.0)
+
+
+def test_readiness_checks_refuse_incomplete_set_ups(gpu_api_cls):
+    """a mesh with boundary faces needs its boundary table (a null table would be dereferenced on the device), the
+    table must cover every zone of the mesh and hold known types, and LES needs the element volumes."""
+    import ctypes as C
+    from horses3d_b200.capi import H3dError, _ptr
+    from horses3d_b200.hostmesh import NodalStorage
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0)
+    mesh = get_mesh(2, 2, GAUSS, 0.1, True, bc="channel", phys=phys)
+    api = gpu_api_cls()
+    api.set_physics(phys); api.set_basis(NodalStorage(2, GAUSS)); api.set_mesh(mesh)
+    Q = np.ascontiguousarray(channel_state(mesh.array("x").reshape(mesh.nElem, 3, 3, 3, 3), phys))
+    api.call("upload_Q", _ptr(Q, np.float64))
+    with pytest.raises(H3dError, match="boundary faces but h3d_set_boundary_conditions was not called"):
+        api.call("compute_time_derivative", 0.0)
+    with pytest.raises(H3dError, match="zone beyond this table"):
+        api.set_boundary_conditions([P.BC_TYPES["inflow"]] * 2, np.zeros((2, 16)))
+    with pytest.raises(H3dError, match="unknown boundary condition type"):
+        api.set_boundary_conditions([77] * 6, np.zeros((6, 16)))
+    sem = DGSem(gpu_api_cls(), mesh, phys)                        # the complete set-up works
+    sem.set_initial_condition(lambda x: channel_state(x, phys))
+    sem.ComputeTimeDerivative(0.0)
+    assert np.isfinite(sem.QDot()).all()
