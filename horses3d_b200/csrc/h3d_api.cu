@@ -84,6 +84,12 @@ struct h3d_context {
     int *dPermE = nullptr, *dPermF = nullptr;
     double *dSend = nullptr, *dRecv = nullptr;
     bool faceHShared = false;      // interior penalty on a partition: the MPI faces' h is the minimum over both ranks
+    // The geometry of an MPI face (normal, tangents, surface Jacobian, LES width) is taken from the rank that owns its LEFT side, as a
+    // single-domain run takes it from the left element (HexMesh.f90:2990-3030).  The reference lets each rank build it from its own
+    // element, so the right-side owner holds values that differ in the last bits; the surface term amplifies that by the pressure
+    // and the lift weights up to 1e-4 of the largest residual.  With the exchange a partitioned run reproduces the
+    // single-domain one to round-off of the reductions.  Option sync_mpi_face_geometry (default 1).
+    int syncFaceGeometry = 1; bool faceGeometryShared = false;
     int maxZone = -1, nZones = 0;  // largest boundary zone of the mesh / zones given by h3d_set_boundary_conditions
     int nBoundaryFaces = 0;
     bool haveVolume = false;       // element volumes and face surfaces were given (LES filter widths)
@@ -756,6 +762,58 @@ __global__ void k_face_h_min(double* fH, const int* haloFace, int nHalo, const d
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nHalo) fH[haloFace[q]] = fmin(fH[haloFace[q]], buf[q]);
 }
+// ten geometry fields of the MPI faces (normal 3, t1 3, t2 3, J_f) + the LES width, packed like the trace exchange
+__global__ void k_geom_pack(DevMesh m, const int* haloFace, int nHalo, int n2, double* buf, const int* nbrOffset, const int* nbrOfFace) {
+    const size_t fs = (size_t)m.nFace * n2;
+    const size_t total = (size_t)nHalo * n2 * 11;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int mm = (int)(t % n2); size_t r = t / n2;
+        const int hf = (int)(r % nHalo); const int c = (int)(r / nHalo);
+        const int f = haloFace[hf];
+        const int nb = nbrOfFace[hf], off = nbrOffset[nb], cnt = nbrOffset[nb + 1] - off;
+        const size_t fo = (size_t)f * n2 + mm;
+        double v;
+        if (c < 3) v = m.fN[c * fs + fo]; else if (c < 6) v = m.fT1[(c - 3) * fs + fo]; else if (c < 9) v = m.fT2[(c - 6) * fs + fo];
+        else if (c == 9) v = m.fJ[fo]; else v = m.fDelta ? m.fDelta[f] : 0.0;
+        buf[(size_t)off * n2 * 11 + ((size_t)c * cnt + (hf - off)) * n2 + mm] = v;
+    }
+}
+__global__ void k_geom_unpack(DevMesh m, const int* haloFace, const int* haloSide, int nHalo, int n2, const double* buf, const int* nbrOffset,
+                              const int* nbrOfFace) {
+    const size_t fs = (size_t)m.nFace * n2;
+    const size_t total = (size_t)nHalo * n2 * 11;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int mm = (int)(t % n2); size_t r = t / n2;
+        const int hf = (int)(r % nHalo); const int c = (int)(r / nHalo);
+        if (haloSide[hf] != 1) continue;                       // this rank owns the left side: its values are the reference ones
+        const int f = haloFace[hf];
+        const int nb = nbrOfFace[hf], off = nbrOffset[nb], cnt = nbrOffset[nb + 1] - off;
+        const size_t fo = (size_t)f * n2 + mm;
+        const double v = buf[(size_t)off * n2 * 11 + ((size_t)c * cnt + (hf - off)) * n2 + mm];
+        if (c < 3) const_cast<double*>(m.fN)[c * fs + fo] = v; else if (c < 6) const_cast<double*>(m.fT1)[(c - 3) * fs + fo] = v;
+        else if (c < 9) const_cast<double*>(m.fT2)[(c - 6) * fs + fo] = v; else if (c == 9) const_cast<double*>(m.fJ)[fo] = v;
+        else if (m.fDelta && mm == 0) const_cast<double*>(m.fDelta)[f] = v;
+    }
+}
+int shareFaceGeometry(h3d_context* h) {
+    if (h->faceGeometryShared || h->nNbr == 0 || !h->syncFaceGeometry) return 0;
+    const int n2 = h->n * h->n;
+    const size_t total = (size_t)h->nHaloFaces * n2 * 11;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+    k_geom_pack<<<blocks, 256, 0, h->sCompute>>>(h->m, h->dHaloFace, h->nHaloFaces, n2, h->dSend, h->dNbrOffset, h->dNbrOfFace);
+    NCCL_CHECK(ncclGroupStart());
+    for (int b = 0; b < h->nNbr; ++b) {
+        const size_t off = (size_t)h->nbrOffset[b] * n2 * 11, cnt = (size_t)h->nbrCount[b] * n2 * 11;
+        NCCL_CHECK(ncclSend(h->dSend + off, cnt, ncclDouble, h->nbrRank[b], h->comm, h->sCompute));
+        NCCL_CHECK(ncclRecv(h->dRecv + off, cnt, ncclDouble, h->nbrRank[b], h->comm, h->sCompute));
+    }
+    NCCL_CHECK(ncclGroupEnd());
+    k_geom_unpack<<<blocks, 256, 0, h->sCompute>>>(h->m, h->dHaloFace, h->dHaloSide, h->nHaloFaces, n2, h->dRecv, h->dNbrOffset, h->dNbrOfFace);
+    h->launches += 2;
+    h->faceGeometryShared = true;
+    return 0;
+}
+
 int shareFaceH(h3d_context* h) {
     if (h->faceHShared || h->nNbr == 0 || !h->m.fH) return 0;
     const int nb = (h->nHaloFaces + 255) / 256;
@@ -827,6 +885,7 @@ int residual(h3d_context* h, const RkArgs& rk) {
         if (!h->tl[id]) cudaEventCreate(&h->tl[id]);
         cudaEventRecord(h->tl[id], s); h->tlRecorded[id] = true;
     };
+    if (multi && (rc = shareFaceGeometry(h))) return rc;   // once: MPI faces take the geometry of their left-side owner
     if (h->timeline) for (bool& b : h->tlRecorded) b = false;
     if (!h->facesValid) { ProfScope ps(h, 3, sc); if ((rc = doProlong(h, 0, h->nElem, sc))) return rc; }
     mark(0, sc);
@@ -907,6 +966,7 @@ int h3d_create(h3d_handle* out, int rank, int nranks, int device, const void* nc
     if (prop.major != 10) return fail(std::string("libh3dgpu is built for sm_100a only; device is ") + prop.name);
     h->numSMs = prop.multiProcessorCount;
     if (const char* ev = std::getenv("H3D_COMM_SMS")) h->commSMs = std::max(0, std::atoi(ev));
+    if (const char* ev = std::getenv("H3D_SYNC_MPI_FACE_GEOMETRY")) h->syncFaceGeometry = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_INTERIOR_SPLIT_PCT")) h->interiorSplitPct = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_USE_MMA")) h->useMma = std::atoi(ev);
     if (const char* ev = std::getenv("H3D_GEN2")) h->useGen2 = std::atoi(ev);
@@ -1207,6 +1267,7 @@ int h3d_set_halo(h3d_handle h, int nNeighbors, const int* neighborRank, const in
     for (int b = 0; b < nNeighbors; ++b) h->nbrOffset[b + 1] = h->nbrOffset[b] + faceCount[b];
     h->nHaloFaces = h->nbrOffset[nNeighbors];
     if (h->nHaloFaces != h->nFace - h->nFaceLocal) { h->err = "halo face count does not match the number of MPI faces"; return 1; }
+    h->faceGeometryShared = false; h->faceHShared = false;
     std::vector<int> hf(h->nHaloFaces), hs(thisSide, thisSide + h->nHaloFaces), nof(h->nHaloFaces);
     for (int b = 0; b < nNeighbors; ++b) for (int q = h->nbrOffset[b]; q < h->nbrOffset[b + 1]; ++q) { hf[q] = h->invPermF[faceIDs[q]]; nof[q] = b; }
     const int n2 = h->n * h->n;
@@ -1654,6 +1715,7 @@ int h3d_set_option(h3d_handle h, const char* kv) {
     if (key == "profile_kernels") { h->profile = val; return 0; }
     if (key == "use_tma") { h->useTma = val; return 0; }
     if (key == "comm_sms") { h->commSMs = std::max(0, val); return 0; }
+    if (key == "sync_mpi_face_geometry") { h->syncFaceGeometry = val; return 0; }
     if (key == "interior_split_pct") { h->interiorSplitPct = val; return 0; }
     if (key == "timeline") { h->timeline = val; return 0; }
     if (key == "mma") { h->useMma = val; return 0; }

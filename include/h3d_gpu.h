@@ -286,7 +286,9 @@ int h3d_stage_timeline(h3d_handle h, double* marks_ms, int len);
  * use_tma=0 (plain-load kernels) | mma=1 (n = 8: contractions on the FP64 tensor cores, not bit-identical to the CUDA-core
  * summation order) | gen2=1 (n = 8: 256-thread kernels, two CTAs per SM) | comm_sms=K, interior_split_pct=P (on a rank with
  * neighbours the first P % of the interior elements run on all but K multiprocessors, which the halo exchange uses meanwhile;
- * defaults 8 and 30) */
+ * defaults 8 and 30) | sync_mpi_face_geometry=0 (keep the geometry each rank built for its MPI faces from its own element, as the
+ * reference does; by default the rank that owns the left side of an MPI face sends normal, tangents, surface Jacobian and LES
+ * width to its neighbour once, so that a partitioned run uses the face geometry of the single-domain run) */
 int h3d_set_option(h3d_handle h, const char* key_value);
 
 #ifdef __cplusplus
