@@ -385,8 +385,7 @@ def main_b200(args):
             rv = ref["values"]
             e_res = max(abs(a - b) for a, b in zip(got[:5], rv[:5])) / max(abs(b) for b in rv[:5])
             e_int = max(abs(a - b) / abs(b) for a, b in zip(got[5:], rv[5:]))
-            tol_res = 1e-13 if world == 1 else 1e-11
-            tol_int = 1e-13 if world == 1 else 1e-11
+            tol_res = tol_int = 1e-11
             check = {"key": key, "residual_err_vs_single_gpu": e_res, "integral_err_vs_single_gpu": e_int, "tolerances": [tol_res, tol_int],
                      "ok": bool(e_res < tol_res and e_int < tol_int and not nan)}
         else:

@@ -60,7 +60,10 @@ int h3dhost_mesh_geometry(void* hp, int N, int nodeType) {
     Host* h = (Host*)hp;
     if (!h->connected) { g_err = "mesh connectivity has not been built"; return 1; }
     if (N < 1 || N > 15) { g_err = "polynomial order out of range"; return 1; }
-    try { buildGeometry(h->mesh, N, nodeType, h->geom); } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
+    // nodeType + 16: the metric terms are interpolated to the nodes with the reference's full triple sum (n^6 per element, for the
+    // regression pins) instead of the sum-factorised form
+    const bool referenceOrder = (nodeType & 16) != 0; nodeType &= 15;
+    try { buildGeometry(h->mesh, N, nodeType, h->geom, referenceOrder); } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
     h->hasGeom = true;
     return 0;
 }

@@ -8,10 +8,9 @@
 //   MappedGeometry.f90:82-152       node coordinates, volume
 //   MappedGeometry.f90:174-384      curl-form metrics on Chebyshev-Lobatto points, interpolated to the nodes
 //   MappedGeometry.f90:482-756      face normal, surface Jacobian, tangents (from the LEFT element, HexMesh.f90:2990-3030)
-// Deviation (round-off level only): the mapping gradient of curved elements is obtained by differentiating
-// the nodal interpolant of the mapping on the Chebyshev-Lobatto grid (exact for patch order <= N, which the
-// reference enforces by projecting patches down, HexMesh.f90:2830-2840) instead of the analytic blend
-// derivative, and the CGL->node interpolation is sum-factorised.
+//   TransfiniteMaps3D.f90:446-745   analytic derivative of the blend (GradGeneralHexTransfiniteMap), FacePatchClass.f90:312-417
+// Deviation (round-off level only): the CGL->node interpolation of the metric terms is sum-factorised (n^4 instead of the
+// reference's n^6 operations per element); `referenceOrder` restores the reference's triple sum for the regression pins.
 #pragma once
 #include <algorithm>
 #include <cstring>
@@ -41,6 +40,7 @@ struct ElemMap {
     const HostMesh* m; int e; double corners[8][3];
     std::vector<double> wb[6][2];  // barycentric weights of the patch knots
     std::vector<double> knots[6][2];
+    std::vector<double> Dk[6][2];  // derivative matrices on the patch knots (FacePatch % Du, Dv)
     void init(const HostMesh& mesh, int e_) {
         m = &mesh; e = e_;
         for (int k = 0; k < 8; ++k) for (int c = 0; c < 3; ++c) corners[k][c] = mesh.nodes[3 * mesh.elemNodes[8 * e + k] + c];
@@ -51,7 +51,80 @@ struct ElemMap {
                 knots[f][d].resize(nn[d]); wb[f][d].resize(nn[d]);
                 for (int i = 0; i < nn[d]; ++i) knots[f][d][i] = (nn[d] == 2) ? (i ? 1.0 : -1.0) : -std::cos(i * PI_RP / (nn[d] - 1.0));
                 barycentricWeights(nn[d] - 1, knots[f][d].data(), wb[f][d].data());
+                Dk[f][d].resize((size_t)nn[d] * nn[d]);
+                polynomialDerivativeMatrix(nn[d] - 1, knots[f][d].data(), Dk[f][d].data());
             }
+        }
+    }
+    // ComputeFaceDerivative (FacePatchClass.f90:312-351, Compute2DPolyDeriv :364-417): g[c][0] = d x_c / du, g[c][1] = d x_c / dv
+    void faceDerivative(int f, double u, double v, double g[3][2]) const {
+        const FacePatch& fp = m->patches[e][f];
+        if (fp.nu == 2 && fp.nv == 2) {
+            for (int c = 0; c < 3; ++c) {
+                const double p11 = fp.pts[0 * 3 + c], p21 = fp.pts[1 * 3 + c], p22 = fp.pts[3 * 3 + c], p12 = fp.pts[2 * 3 + c];
+                g[c][0] = 0.25 * (-p11 * (1.0 - v) + p21 * (1.0 - v) + p22 * (1.0 + v) - p12 * (1.0 + v));
+                g[c][1] = 0.25 * (-p11 * (1.0 - u) - p21 * (1.0 + u) + p22 * (1.0 + u) + p12 * (1.0 - u));
+            }
+            return;
+        }
+        double li[32], lj[32], dli[32], dlj[32];
+        interpolatingPolynomialVector(u, fp.nu - 1, knots[f][0].data(), wb[f][0].data(), li);
+        interpolatingPolynomialVector(v, fp.nv - 1, knots[f][1].data(), wb[f][1].data(), lj);
+        for (int i = 0; i < fp.nu; ++i) { dli[i] = 0.0; for (int j = 0; j < fp.nu; ++j) dli[i] += Dk[f][0][j * fp.nu + i] * li[j]; }
+        for (int i = 0; i < fp.nv; ++i) { dlj[i] = 0.0; for (int j = 0; j < fp.nv; ++j) dlj[i] += Dk[f][1][j * fp.nv + i] * lj[j]; }
+        for (int c = 0; c < 3; ++c) g[c][0] = g[c][1] = 0.0;
+        for (int j = 0; j < fp.nv; ++j) for (int i = 0; i < fp.nu; ++i)
+            for (int c = 0; c < 3; ++c) {
+                const double pt = fp.pts[(j * fp.nu + i) * 3 + c];
+                g[c][0] += pt * dli[i] * lj[j];
+                g[c][1] += pt * li[i] * dlj[j];
+            }
+    }
+    // GradGeneralHexTransfiniteMap + ComputeGradHexTransfiniteMap (TransfiniteMaps3D.f90:446-600, 617-745): the analytic derivative of
+    // the blend of the six face patches, gg[i][j] = d x_i / d xi_j; entries below 100 eps are set to zero as the reference does
+    void gradGeneral(const double* u, double gg[3][3]) const {
+        double face[6][3], edge[12][3], fd[6][3][2], ed[12][3], g2[3][2];
+        facePoint(0, u[0], -1.0, edge[0]); facePoint(0, 1.0, u[2], edge[1]); facePoint(0, u[0], 1.0, edge[2]); facePoint(0, -1.0, u[2], edge[3]);
+        facePoint(1, u[0], -1.0, edge[4]); facePoint(1, 1.0, u[2], edge[5]); facePoint(1, u[0], 1.0, edge[6]); facePoint(1, -1.0, u[2], edge[7]);
+        facePoint(3, u[1], -1.0, edge[9]); facePoint(5, u[1], -1.0, edge[8]); facePoint(3, u[1], 1.0, edge[10]); facePoint(5, u[1], 1.0, edge[11]);
+        facePoint(0, u[0], u[2], face[0]); facePoint(1, u[0], u[2], face[1]); facePoint(2, u[0], u[1], face[2]);
+        facePoint(3, u[1], u[2], face[3]); facePoint(4, u[0], u[1], face[4]); facePoint(5, u[1], u[2], face[5]);
+        auto edgeDer = [&](int k, int f, double a, double b, int which) {
+            faceDerivative(f, a, b, g2);
+            for (int c = 0; c < 3; ++c) ed[k][c] = 2.0 * g2[c][which];
+        };
+        edgeDer(0, 0, u[0], -1.0, 0); edgeDer(1, 0, 1.0, u[2], 1); edgeDer(2, 0, u[0], 1.0, 0); edgeDer(3, 0, -1.0, u[2], 1);
+        edgeDer(4, 1, u[0], -1.0, 0); edgeDer(5, 1, 1.0, u[2], 1); edgeDer(6, 1, u[0], 1.0, 0); edgeDer(7, 1, -1.0, u[2], 1);
+        edgeDer(8, 5, u[1], -1.0, 0); edgeDer(9, 3, u[1], -1.0, 0); edgeDer(10, 3, u[1], 1.0, 0); edgeDer(11, 5, u[1], 1.0, 0);
+        const double fu[6][2] = {{u[0], u[2]}, {u[0], u[2]}, {u[0], u[1]}, {u[1], u[2]}, {u[0], u[1]}, {u[1], u[2]}};
+        for (int f = 0; f < 6; ++f) {
+            faceDerivative(f, fu[f][0], fu[f][1], g2);
+            for (int c = 0; c < 3; ++c) { fd[f][c][0] = 2.0 * g2[c][0]; fd[f][c][1] = 2.0 * g2[c][1]; }
+        }
+        const double x1 = 0.5 * (u[0] + 1.0), x2 = 0.5 * (u[1] + 1.0), x3 = 0.5 * (u[2] + 1.0);
+        const double eps = 100.0 * 2.220446049250313e-16;
+        for (int j = 0; j < 3; ++j) {
+            const double c1 = corners[0][j], c2 = corners[1][j], c3 = corners[2][j], c4 = corners[3][j], c5 = corners[4][j], c6 = corners[5][j], c7 = corners[6][j], c8 = corners[7][j];
+            double g1 = -face[5][j] + face[3][j] + fd[0][j][0] * (1.0 - x2) + fd[1][j][0] * x2 + fd[2][j][0] * (1.0 - x3) + fd[4][j][0] * x3;
+            g1 = g1 - ed[0][j] * (1.0 - x2) * (1.0 - x3) - ed[2][j] * (1.0 - x2) * x3 - ed[4][j] * x2 * (1.0 - x3) - ed[6][j] * x2 * x3
+                    + edge[8][j] * (1.0 - x3) + edge[11][j] * x3 - edge[9][j] * (1.0 - x3) - edge[10][j] * x3
+                    + edge[3][j] * (1.0 - x2) + edge[7][j] * x2 - edge[1][j] * (1.0 - x2) - edge[5][j] * x2;
+            g1 = g1 - c1 * (1.0 - x2) * (1.0 - x3) - c5 * (1.0 - x2) * x3 - c4 * x2 * (1.0 - x3) - c8 * x2 * x3
+                    + c2 * (1.0 - x2) * (1.0 - x3) + c6 * (1.0 - x2) * x3 + c3 * x2 * (1.0 - x3) + c7 * x2 * x3;
+            double g2_ = fd[5][j][0] * (1.0 - x1) + fd[3][j][0] * x1 - face[0][j] + face[1][j] + fd[2][j][1] * (1.0 - x3) + fd[4][j][1] * x3;
+            g2_ = g2_ + edge[0][j] * (1.0 - x3) + edge[2][j] * x3 - edge[4][j] * (1.0 - x3) - edge[6][j] * x3
+                      - ed[8][j] * (1.0 - x1) * (1.0 - x3) - ed[11][j] * (1.0 - x1) * x3 - ed[9][j] * (1.0 - x3) * x1 - ed[10][j] * x1 * x3
+                      + edge[3][j] * (1.0 - x1) - edge[7][j] * (1.0 - x1) + edge[1][j] * x1 - edge[5][j] * x1;
+            g2_ = g2_ - c1 * (1.0 - x1) * (1.0 - x3) - c5 * (1.0 - x1) * x3 + c4 * (1.0 - x1) * (1.0 - x3) + c8 * (1.0 - x1) * x3
+                      - c2 * x1 * (1.0 - x3) - c6 * x1 * x3 + c3 * x1 * (1.0 - x3) + c7 * x1 * x3;
+            double g3 = fd[5][j][1] * (1.0 - x1) + fd[3][j][1] * x1 + fd[0][j][1] * (1.0 - x2) + fd[1][j][1] * x2 - face[2][j] + face[4][j];
+            g3 = g3 + edge[0][j] * (1.0 - x2) - edge[2][j] * (1.0 - x2) + edge[4][j] * x2 - edge[6][j] * x2
+                    + edge[8][j] * (1.0 - x1) - edge[11][j] * (1.0 - x1) + edge[9][j] * x1 - edge[10][j] * x1
+                    - ed[3][j] * (1.0 - x1) * (1.0 - x2) - ed[7][j] * (1.0 - x1) * x2 - ed[1][j] * x1 * (1.0 - x2) - ed[5][j] * x1 * x2;
+            g3 = g3 - c1 * (1.0 - x1) * (1.0 - x2) + c5 * (1.0 - x1) * (1.0 - x2) - c4 * (1.0 - x1) * x2 + c8 * (1.0 - x1) * x2
+                    - c2 * x1 * (1.0 - x2) + c6 * x1 * (1.0 - x2) - c3 * x1 * x2 + c7 * x1 * x2;
+            gg[j][0] = 0.5 * g1; gg[j][1] = 0.5 * g2_; gg[j][2] = 0.5 * g3;
+            for (int d = 0; d < 3; ++d) if (std::fabs(gg[j][d]) <= eps) gg[j][d] = 0.0;
         }
     }
     void facePoint(int f, double u, double v, double* p) const {
@@ -119,7 +192,7 @@ inline void faceNodeToElem(int f, int a, int b, int nrm, int& i, int& j, int& k)
     i = idx[0]; j = idx[1]; k = idx[2];
 }
 
-inline void buildGeometry(const HostMesh& m, int N, int nodeType, HostGeometry& g) {
+inline void buildGeometry(const HostMesh& m, int N, int nodeType, HostGeometry& g, bool referenceOrder = false) {
     g.N = N; g.n = N + 1; g.nodeType = nodeType; g.sp.construct(nodeType, N);
     const NodalStorage& sp = g.sp;
     const int n = g.n, n3 = n * n * n, n2 = n * n;
@@ -152,16 +225,10 @@ inline void buildGeometry(const HostMesh& m, int N, int nodeType, HostGeometry& 
                     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) gradx[9 * I(i, j, k) + 3 * a + b] = gg[a][b];
                 }
             } else {
-                const double eps = 100.0 * 2.220446049250313e-16;
-                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) {
-                    double d0 = 0, d1 = 0, d2 = 0;
-                    for (int l = 0; l < n; ++l) {
-                        d0 += sp.DCGL[i * n + l] * xC[3 * I(l, j, k) + a];
-                        d1 += sp.DCGL[j * n + l] * xC[3 * I(i, l, k) + a];
-                        d2 += sp.DCGL[k * n + l] * xC[3 * I(i, j, l) + a];
-                    }
-                    double* gp = &gradx[9 * I(i, j, k) + 3 * a];
-                    gp[0] = std::fabs(d0) <= eps ? 0.0 : d0; gp[1] = std::fabs(d1) <= eps ? 0.0 : d1; gp[2] = std::fabs(d2) <= eps ? 0.0 : d2;
+                for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                    double u[3] = {sp.xCGL[i], sp.xCGL[j], sp.xCGL[k]}, gg[3][3];
+                    map.gradGeneral(u, gg);
+                    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) gradx[9 * I(i, j, k) + 3 * a + b] = gg[a][b];
                 }
             }
             // curl form: component c of Ja^d = -1/2 [curl( X_l grad X_m - X_m grad X_l )]_d, (c,m,l) cyclic
@@ -191,6 +258,16 @@ inline void buildGeometry(const HostMesh& m, int N, int nodeType, HostGeometry& 
             }
             // back to the solution nodes (sum-factorised TCheb2Gauss in xi, eta, zeta)
             auto interp3 = [&](const double* src, int nc, double* dst) {
+                if (referenceOrder) {   // MappedGeometry.f90:336-361: the full triple sum, l fastest, products left to right
+                    for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+                        double acc[3] = {0.0, 0.0, 0.0};
+                        for (int nn = 0; nn < n; ++nn) for (int mm = 0; mm < n; ++mm) for (int l = 0; l < n; ++l)
+                            for (int c = 0; c < nc; ++c)
+                                acc[c] = acc[c] + src[nc * I(l, mm, nn) + c] * sp.TCheb2Gauss[i * n + l] * sp.TCheb2Gauss[j * n + mm] * sp.TCheb2Gauss[k * n + nn];
+                        for (int c = 0; c < nc; ++c) dst[nc * I(i, j, k) + c] = acc[c];
+                    }
+                    return;
+                }
                 double* t1 = tmp1.data(); double* t2 = tmp2.data();
                 for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) for (int c = 0; c < nc; ++c) {
                     double s = 0; for (int l = 0; l < n; ++l) s += src[nc * I(l, j, k) + c] * sp.TCheb2Gauss[i * n + l];

@@ -119,8 +119,11 @@ class HostMesh:
         self.bc_params = p
         return self
 
-    def geometry(self, N, nodes=GAUSS):
-        _check(lib().h3dhost_mesh_geometry(self._h, N, nodes))
+    def geometry(self, N, nodes=GAUSS, reference_order=False):
+        """Metric terms (MappedGeometry.f90:174-384).  reference_order=True interpolates them from the Chebyshev-Lobatto grid to the
+        nodes with the reference's full triple sum (n^6 operations per element) instead of the sum-factorised form: same values to
+        round-off, the reference's rounding -- for the regression pins that run a thousand steps."""
+        _check(lib().h3dhost_mesh_geometry(self._h, N, nodes + (16 if reference_order else 0)))
         self.N, self.nodes = N, nodes
         return self
 
