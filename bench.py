@@ -387,7 +387,7 @@ def main_b200(args):
             e_int = max(abs(a - b) / abs(b) for a, b in zip(got[5:], rv[5:]))
             tol_res = tol_int = 1e-11
             check = {"key": key, "residual_err_vs_single_gpu": e_res, "integral_err_vs_single_gpu": e_int, "tolerances": [tol_res, tol_int],
-                     "ok": bool(e_res < tol_res and e_int < tol_int and not nan)}
+                     "ok": bool(e_res < tol_res and e_int < tol_int and not nan), "values": got}
         else:
             check = {"key": key, "values": got, "ok": not nan, "note": "no committed single-GPU values for this mesh"}
 
