@@ -106,8 +106,10 @@ def cpu_sample(args, steps, warmup):
     from horses3d_b200.hostmesh import GAUSS, HostMesh
     from horses3d_b200.physics import make_physics
     from oracle.oracle_api import OracleApi, library
-    os.environ["OMP_NUM_THREADS"] = str(host_threads())      # the host-side geometry (libh3dhost) reads it when it loads
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
     library().orc_set_num_threads(host_threads())
+    from horses3d_b200 import hostmesh as _hm
+    _hm.set_num_threads(host_threads())                      # the host-side geometry of the sample
     mesh = HostMesh.box(args.ref_ne, amp=args.amp, bFaceOrder=2).connect().geometry(args.order, GAUSS)
     sem = DGSem(OracleApi(), mesh, make_physics(flow="NS", mach=0.08, reynolds=1600.0, riemann="roe"))
     sem.set_initial_condition(taylor_green_ic)
@@ -184,7 +186,10 @@ def main_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     # torchrun pins OMP_NUM_THREADS=1; the host-side metric construction is OpenMP code: give each rank its share of the cores
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(world, 1)))
+    # (the environment variable alone does not do it: importing torch has already started the OpenMP runtime with torchrun's value)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // max(world, 1)))
+    from horses3d_b200 import hostmesh as _hm
+    host_omp_threads = _hm.set_num_threads(max(1, host_threads() // max(world, 1)))
     if world != args.gpus and world > 1:
         raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
     torch.cuda.set_device(local)
@@ -405,6 +410,7 @@ def main_b200(args):
                                    % (ex, ey, ez, N, "Gauss" if args.nodes == "gauss" else "Gauss-Lobatto",
                                       "StandardDG+BR1+Roe" if headline else scheme),
                        "ndof": ndof_global, "elements_per_gpu": nElemGlobal // world, "partition": args.partition if world > 1 else "none",
+                       "host_threads_per_rank": host_omp_threads,
                        "contraction": "DMMA" if os.environ.get("H3D_USE_MMA") == "1" else "CUDA cores, bit-identical to the oracle",
                        "l2": "inputs larger than L2 (state + gradients + metrics = %.1f GB per GPU)" % (sem.NDOF * 8 * (30 + 10) / 1e9)},
             "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,

@@ -2,6 +2,9 @@
 // partitioning.  Consumed by the Python/ctypes front end and by C++ drivers; the arrays it produces are
 // exactly the inputs of the device C-ABI (include/h3d_gpu.h).
 #include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <string>
 
 #include "geometry.hpp"
@@ -23,6 +26,24 @@ struct Host {
 extern "C" {
 
 const char* h3dhost_last_error() { return g_err.c_str(); }
+
+// Threads of the OpenMP loops of this library (metric terms, wall distances).  Launchers such as torchrun export
+// OMP_NUM_THREADS=1 and the OpenMP runtime reads it once, when the first library that uses it is loaded -- changing the
+// environment afterwards has no effect, this call has.  Returns the number of threads a parallel region gets.
+int h3dhost_set_num_threads(int nt) {
+#ifdef _OPENMP
+    if (nt > 0) omp_set_num_threads(nt);
+    int got = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        got = omp_get_num_threads();
+    }
+    return got;
+#else
+    (void)nt; return 1;
+#endif
+}
 
 void* h3dhost_mesh_box(int nex, int ney, int nez, double L, double amp, int bFaceOrder, int shuffle, unsigned seed) {
     Host* h = new Host();

@@ -40,10 +40,17 @@ def lib():
         L.h3dhost_extract_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.h3dhost_inherit_geometry.argtypes = [C.c_void_p, C.c_void_p]
         L.h3dhost_wall_distance.argtypes = [C.c_void_p]
+        L.h3dhost_set_num_threads.argtypes = [C.c_int]
         L.h3dhost_wall_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong)]
         L.h3dhost_wall_distance_from.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
         _lib = L
     return _lib
+
+
+def set_num_threads(n):
+    """Threads of the host library's OpenMP loops; returns what a parallel region really gets.  Needed under launchers that pin
+    OMP_NUM_THREADS=1 (torchrun): the OpenMP runtime has read the environment long before this module can change it."""
+    return int(lib().h3dhost_set_num_threads(int(n)))
 
 
 class HostError(RuntimeError):
