@@ -99,7 +99,7 @@ def build_gpu_fma(force=False):
 
 
 def build_oracle(force=False):
-    srcs = _sources(ORACLE_DIR, (".cpp", ".hpp"))
+    srcs = _sources(ORACLE_DIR, (".cpp", ".hpp", ".inc"))
     if force or _newer(ORACLE_LIB, srcs):
         # -ffp-contract=off: the reference's gfortran RELEASE build (-O3, no -march, no -ffast-math) emits no FMA
         cmd = ["g++", "-O3", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared",

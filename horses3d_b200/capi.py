@@ -34,6 +34,8 @@ class Binding:
         "set_physics": [C.POINTER(H3dPhysics)],
         "set_basis": [C.c_int, C.c_int] + [_D] * 7,
         "set_mesh": [C.c_int, C.c_int] + [_D] * 19,
+        "set_interpolation": [C.c_int, C.c_int, _D],
+        "set_mesh_p": [C.c_int, C.c_int] + [_D] * 20,
         "set_boundary_conditions": [C.c_int, _D, _D],
         "set_wall_distance": [_D, _D],
         "set_face_h": [_D],
@@ -96,6 +98,15 @@ class Api:
         Dp = lambda k: _ptr(m.array(k), np.float64)
         self.call("set_mesh", nE, nF, I("elemFace"), I("elemFaceSide"), I("faceElem"), I("faceElemSide"), I("faceRot"), I("faceType"),
                   I("faceZone"), Dp("jGradXi"), Dp("jGradEta"), Dp("jGradZeta"), Dp("jacobian"), Dp("x"), Dp("volume"),
+                  Dp("faceNormal"), Dp("faceT1"), Dp("faceT2"), Dp("faceJacobian"), Dp("faceX"), Dp("faceSurface"))
+
+    def set_mesh_p(self, m):
+        """p-nonconforming mesh: as set_mesh with the elements' orders; arrays packed at the elements' / faces' own sizes."""
+        nE, nF = m.nElem, m.nFaces
+        I = lambda k: _ptr(m.array(k), np.int32)
+        Dp = lambda k: _ptr(m.array(k), np.float64)
+        self.call("set_mesh_p", nE, nF, I("elemOrder"), I("elemFace"), I("elemFaceSide"), I("faceElem"), I("faceElemSide"), I("faceRot"),
+                  I("faceType"), I("faceZone"), Dp("jGradXi"), Dp("jGradEta"), Dp("jGradZeta"), Dp("jacobian"), Dp("x"), Dp("volume"),
                   Dp("faceNormal"), Dp("faceT1"), Dp("faceT2"), Dp("faceJacobian"), Dp("faceX"), Dp("faceSurface"))
 
     def set_boundary_conditions(self, types, params):

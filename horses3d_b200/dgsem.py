@@ -45,13 +45,18 @@ def taylor_green_ic(x, gamma=1.4, L=1.0, u0=1.0, rho0=1.0, p0=100.0):
 class DGSem:
     def __init__(self, api, mesh, physics):
         self.api, self.mesh, self.physics = api, mesh, physics
-        self.N, self.n = mesh.N, mesh.N + 1
         self.nElem, self.nFaces = mesh.nElem, mesh.nFaces
-        self.NDOF = self.nElem * self.n ** 3            # nodes, as the reference counts them (main.f90:360)
-        self.sp = NodalStorage(mesh.N, mesh.nodes)
+        self.mixed = bool(getattr(mesh, "mixed", False))
         api.set_physics(physics)
-        api.set_basis(self.sp)
-        api.set_mesh(mesh)
+        if self.mixed:
+            self._construct_mixed(api, mesh)
+        else:
+            self.N, self.n = mesh.N, mesh.N + 1
+            self.NDOF = self.nElem * self.n ** 3            # nodes, as the reference counts them (main.f90:360)
+            self.sp = NodalStorage(mesh.N, mesh.nodes)
+            api.set_basis(self.sp)
+            api.set_mesh(mesh)
+            self._shape = (self.nElem, self.n, self.n, self.n, 5)
         bcs = getattr(mesh, "bcs", [])
         if bcs:
             types = [P.BC_TYPES[b[1].lower()] for b in bcs]
@@ -70,10 +75,42 @@ class DGSem:
         counts = mesh.array("haloCount")
         if len(counts) and hasattr(api, "set_halo"):
             api.set_halo(mesh.array("haloRank"), counts, mesh.array("haloFace"), mesh.array("haloSide"))
-        self._shape = (self.nElem, self.n, self.n, self.n, 5)
+
+    def _construct_mixed(self, api, mesh):
+        """p-nonconforming mesh: NodalStorage(N) of every order in use (DGSEMClass.f90:215-228), Tset(N, M) of every
+        pair of orders that meet at a face (Face_LinkWithElements, FaceClass.f90:236-251), then the mesh with its orders.  Element
+        arrays are packed element after element at their own sizes, as the reference's global2LocalQ (StorageClass.f90:423-429)."""
+        from .hostmesh import interpolation_matrix
+        self.orders = np.array(mesh.array("elemOrder")).reshape(-1, 3)
+        self.face_orders = np.array(mesh.array("faceOrder")).reshape(-1, 6)
+        self.N = self.n = None
+        self.sps = {int(N): NodalStorage(int(N), mesh.nodes) for N in sorted(set(self.orders.ravel()) | set(self.face_orders.ravel()))}
+        for sp in self.sps.values():
+            api.set_basis(sp)
+        pairs = set()
+        for s in (2, 4):
+            for d in (0, 1):
+                a, b = self.face_orders[:, s + d], self.face_orders[:, d]
+                pairs |= {(int(x), int(y)) for x, y in zip(a[a != b], b[a != b])}
+        for a, b in sorted(pairs):
+            for No, Nd in ((a, b), (b, a)):
+                T = interpolation_matrix(No, Nd, mesh.nodes)
+                api.call("set_interpolation", No, Nd, _ptr(T, np.float64))
+        api.set_mesh_p(mesh)
+        sizes = np.prod(self.orders + 1, axis=1)
+        self.elem_offset = np.concatenate([[0], np.cumsum(sizes)])
+        self.NDOF = int(self.elem_offset[-1])
+        self._shape = (self.NDOF, 5)
+
+    def element_view(self, A, e):
+        """Element e of a packed array of a p-nonconforming mesh, as [k][j][i][...]."""
+        nx, ny, nz = self.orders[e] + 1
+        return A[self.elem_offset[e]:self.elem_offset[e + 1]].reshape((nz, ny, nx) + A.shape[1:])
 
     # ---- state
     def node_coordinates(self):
+        if self.mixed:
+            return self.mesh.array("x").reshape(self.NDOF, 3)
         return self.mesh.array("x").reshape(self.nElem, self.n, self.n, self.n, 3)
 
     def set_Q(self, Q):

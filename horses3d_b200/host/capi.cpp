@@ -8,6 +8,7 @@
 #include <string>
 
 #include "geometry.hpp"
+#include "geometry_p.hpp"
 #include "gmsh.hpp"
 #include "partition.hpp"
 
@@ -18,8 +19,9 @@ thread_local std::string g_err;
 struct Host {
     HostMesh mesh;
     HostGeometry geom;
+    HostGeometryP geomP;      // p-nonconforming meshes (geometry_p.hpp)
     HaloInfo halo;
-    bool connected = false, hasGeom = false;
+    bool connected = false, hasGeom = false, mixed = false;
 };
 }  // namespace
 
@@ -89,8 +91,30 @@ int h3dhost_mesh_geometry(void* hp, int N, int nodeType) {
     return 0;
 }
 
+// Geometry of a p-nonconforming mesh: Nxyz[nElem][3] are the elements' polynomial orders (the reference's "polynomial order
+// file", ReadOrderFile, libs/io/ReadInputFile.f90:132-153).  Afterwards h3dhost_get_array serves the packed arrays of
+// geometry_p.hpp under the usual names, plus "elemOrder" [e][3] and "faceOrder" [f][6] = Nf, NfLeft, NfRight.
+int h3dhost_mesh_geometry_p(void* hp, int nodeType, const int* Nxyz) {
+    Host* h = (Host*)hp;
+    if (!h->connected) { g_err = "mesh connectivity has not been built"; return 1; }
+    try { if (!buildGeometryP(h->mesh, Nxyz, nodeType, h->geomP, g_err)) return 1; } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
+    h->hasGeom = true; h->mixed = true;
+    return 0;
+}
+
+// Tset(Norigin, Ndest) % T (libs/spectral/InterpolationMatrices.f90:42-107), row-major [(Ndest+1)][(Norigin+1)]
+int h3dhost_interpolation_matrix(int Norigin, int Ndest, int nodeType, double* T) {
+    try {
+        NodalStorage a, b; a.construct(nodeType, Norigin); b.construct(nodeType, Ndest);
+        std::vector<double> M; interpolationMatrix(a, b, M);
+        std::memcpy(T, M.data(), M.size() * sizeof(double));
+    } catch (const std::exception& ex) { g_err = ex.what(); return 1; }
+    return 0;
+}
+
 int h3dhost_wall_distance(void* hp) {
     Host* h = (Host*)hp;
+    if (h->mixed) { g_err = "wall distances are not available on p-nonconforming meshes"; return 1; }
     if (!h->hasGeom) { g_err = "geometry has not been built"; return 1; }
     computeWallDistances(h->mesh, h->geom);
     return 0;
@@ -101,6 +125,7 @@ int h3dhost_wall_distance(void* hp) {
 // gathers them across ranks, and every rank measures its nodes against the whole set (wall_distance_from).
 int h3dhost_wall_points(void* hp, double* pts, long long* count) {
     Host* h = (Host*)hp;
+    if (h->mixed) { g_err = "wall distances are not available on p-nonconforming meshes"; return 1; }
     if (!h->hasGeom) { g_err = "geometry has not been built"; return 1; }
     const std::vector<double> Xw = wallCoordinates(h->mesh, h->geom);
     *count = (long long)(Xw.size() / 3);
@@ -109,6 +134,7 @@ int h3dhost_wall_points(void* hp, double* pts, long long* count) {
 }
 int h3dhost_wall_distance_from(void* hp, const double* pts, long long count) {
     Host* h = (Host*)hp;
+    if (h->mixed) { g_err = "wall distances are not available on p-nonconforming meshes"; return 1; }
     if (!h->hasGeom) { g_err = "geometry has not been built"; return 1; }
     if (count <= 0) { g_err = "no wall points: the wall model needs at least one no-slip wall face in the whole mesh"; return 1; }
     computeWallDistances(h->mesh, h->geom, std::vector<double>(pts, pts + 3 * count));
@@ -131,6 +157,14 @@ int h3dhost_get_array(void* hp, const char* name, void** ptr, long long* count, 
     IARR("faceNodes", h->mesh.faceNodes) IARR("faceElem", h->mesh.faceElem) IARR("faceElemSide", h->mesh.faceElemSide)
     IARR("faceRot", h->mesh.faceRot) IARR("faceType", h->mesh.faceType) IARR("faceZone", h->mesh.faceZone)
     IARR("elemFace", h->mesh.elemFace) IARR("elemFaceSide", h->mesh.elemFaceSide)
+    if (h->mixed) {
+        HostGeometryP& G = h->geomP;
+        IARR("elemOrder", G.elemOrder) IARR("faceOrder", G.faceOrder)
+        DARR("x", G.x) DARR("jGradXi", G.jGradXi) DARR("jGradEta", G.jGradEta) DARR("jGradZeta", G.jGradZeta)
+        DARR("jacobian", G.jac) DARR("invJacobian", G.invJac) DARR("volume", G.volume)
+        DARR("faceX", G.fx) DARR("faceNormal", G.fnormal) DARR("faceT1", G.ft1) DARR("faceT2", G.ft2)
+        DARR("faceJacobian", G.fjac) DARR("faceSurface", G.fsurface)
+    }
     DARR("x", h->geom.x) DARR("jGradXi", h->geom.jGradXi) DARR("jGradEta", h->geom.jGradEta) DARR("jGradZeta", h->geom.jGradZeta)
     DARR("jacobian", h->geom.jac) DARR("invJacobian", h->geom.invJac) DARR("volume", h->geom.volume)
     DARR("faceX", h->geom.fx) DARR("faceNormal", h->geom.fnormal) DARR("faceT1", h->geom.ft1) DARR("faceT2", h->geom.ft2)

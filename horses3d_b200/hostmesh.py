@@ -32,6 +32,8 @@ def lib():
         L.h3dhost_mesh_free.argtypes = [C.c_void_p]
         L.h3dhost_mesh_connect.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p]
         L.h3dhost_mesh_geometry.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.h3dhost_mesh_geometry_p.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.h3dhost_interpolation_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.h3dhost_mesh_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
         L.h3dhost_get_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
         L.h3dhost_nodal.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7
@@ -81,6 +83,22 @@ class NodalStorage:
         _check(lib().h3dhost_nodal(N, nodes, *[a.ctypes.data for a in (self.x, self.w, self.D, self.hatD, self.sharpD, self.v, self.b)]))
 
 
+def interpolation_matrix(Norigin, Ndest, nodes=GAUSS):
+    """Tset(Norigin, Ndest) % T (InterpolationMatrices.f90:42-107): [Ndest+1, Norigin+1]; Lagrange interpolation when Norigin < Ndest,
+    the L2 projection (its weighted transpose) otherwise."""
+    T = np.zeros((Ndest + 1, Norigin + 1))
+    _check(lib().h3dhost_interpolation_matrix(Norigin, Ndest, nodes, T.ctypes.data))
+    return T
+
+
+def read_order_file(path):
+    """ReadOrderFile (libs/io/ReadInputFile.f90:132-153): number of elements, then Nx Ny Nz per element."""
+    with open(path) as f:
+        tok = f.read().replace(",", " ").split()
+    n = int(tok[0])
+    return np.array(tok[1:1 + 3 * n], dtype=np.int32).reshape(n, 3)
+
+
 class HostMesh:
     """Driver-side HexMesh: raw mesh -> connectivity -> geometry (flat numpy views on C++ storage)."""
 
@@ -89,6 +107,7 @@ class HostMesh:
             raise HostError(lib().h3dhost_last_error().decode())
         self._h = C.c_void_p(handle)
         self.halo = None
+        self.mixed = False             # p-nonconforming: per-element polynomial orders (geometry_p)
         self.is_partition = False      # extracted from a global mesh: some faces are MPI faces
         self.wall_global = False       # wall distances measured against the wall nodes of the whole mesh
 
@@ -132,6 +151,15 @@ class HostMesh:
         round-off, the reference's rounding -- for the regression pins that run a thousand steps."""
         _check(lib().h3dhost_mesh_geometry(self._h, N, nodes + (16 if reference_order else 0)))
         self.N, self.nodes = N, nodes
+        return self
+
+    def geometry_p(self, orders, nodes=GAUSS):
+        """Geometry of a p-nonconforming mesh: orders[e] = (Nx, Ny, Nz) of every element, as the reference's
+        "polynomial order file".  Faces get the maximum order of their two sides per direction (FaceClass.f90:187-282)."""
+        orders = np.ascontiguousarray(np.broadcast_to(np.asarray(orders, dtype=np.int32), (self.nElem, 3)))
+        _check(lib().h3dhost_mesh_geometry_p(self._h, nodes, orders.ctypes.data))
+        self.N, self.nodes, self.mixed = None, nodes, True
+        self.orders = orders
         return self
 
     def wall_distances(self, gather=None):

@@ -33,8 +33,9 @@ def lagrange_vectors(nodes, xi):
 def find_point_in_element(X, nodes, x, tol=1.0e-12, inside_tol=1.0e-8, max_iter=50):
     """X: node coordinates of one element [k][j][i][3].  Returns (inside, xi)."""
     xi = np.zeros(3)
+    nodes3 = nodes if isinstance(nodes, (tuple, list)) else (nodes, nodes, nodes)     # anisotropic elements: one node set per direction
     for _ in range(max_iter):
-        (lx, dlx), (ly, dly), (lz, dlz) = (lagrange_vectors(nodes, xi[d]) for d in range(3))
+        (lx, dlx), (ly, dly), (lz, dlz) = (lagrange_vectors(nodes3[d], xi[d]) for d in range(3))
         F = np.einsum("kjic,i,j,k->c", X, lx, ly, lz) - x
         if np.abs(F).max() < tol or np.abs(xi).max() >= 2.5:
             break
@@ -48,6 +49,17 @@ def find_point(sem, x):
     """(element id, xi) of the first element containing x, or (None, None)."""
     x = np.asarray(x, dtype=np.float64)
     X = sem.node_coordinates()
+    if getattr(sem, "mixed", False):
+        for e in range(sem.nElem):
+            Xe = sem.element_view(X, e)
+            lo, hi = Xe.min(axis=(0, 1, 2)), Xe.max(axis=(0, 1, 2))
+            pad = 0.5 * (hi - lo).max() + 1e-8
+            if not ((x >= lo - pad) & (x <= hi + pad)).all():
+                continue
+            inside, xi = find_point_in_element(Xe, tuple(sem.sps[int(N)].x for N in sem.orders[e]), x)
+            if inside:
+                return int(e), xi
+        return None, None
     lo, hi = X.min(axis=(1, 2, 3)), X.max(axis=(1, 2, 3))
     pad = 0.5 * (hi - lo).max(axis=1, keepdims=True) + 1e-8      # Gauss nodes do not reach the element boundary
     for e in np.nonzero(((x >= lo - pad) & (x <= hi + pad)).all(axis=1))[0]:
@@ -62,7 +74,16 @@ class Probe:
         self.variable = VARIABLES[variable.lower()]
         self.eID, self.xi = find_point(sem, position)
         self.active = self.eID is not None
-        if self.active:
+        if self.active and getattr(sem, "mixed", False):
+            # rows padded to the largest number of nodes per direction of the mesh (include/h3d_gpu.h, h3d_probe)
+            ld = int(sem.orders.max()) + 1
+            self.l = []
+            for d in range(3):
+                row = np.zeros(ld)
+                lv = lagrange_vectors(sem.sps[int(sem.orders[self.eID][d])].x, self.xi[d])[0]
+                row[:len(lv)] = lv
+                self.l.append(row)
+        elif self.active:
             self.l = [np.ascontiguousarray(lagrange_vectors(sem.sp.x, self.xi[d])[0]) for d in range(3)]
 
 

@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <string>
 #include <vector>
 #ifdef _OPENMP
@@ -74,6 +75,8 @@ struct Oracle {
     std::vector<double> fQ, fUx, fUy, fUz, fStar, fmu, unStar;  // unStar: [f][side][j][i][3][5]
     int n2() const { return n * n; }
     int n3() const { return n * n * n; }
+    // p-nonconforming meshes (h3d_oracle_p.inc): per-element orders; the element fields above keep the reference's packed order
+    bool mixed = false; void* pdata = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1412,13 +1415,17 @@ void computeQDot(Oracle& o, double time) {
 }
 
 // ComputeTimeDerivative (SpatialDiscretization.f90:227-320)
+void computeTimeDerivativeP(Oracle& o, double time);   // h3d_oracle_p.inc
 void computeTimeDerivative(Oracle& o, double time) {
+    if (o.mixed) { computeTimeDerivativeP(o, time); return; }
     prolongToFaces(o, 5, o.Q, o.fQ);
     if (o.ph.computeGradients) computeGradient(o, time);
     computeQDot(o, time);
 }
 
 }  // namespace
+
+#include "h3d_oracle_p.inc"
 
 // ====================================================================================================
 //  C API (mirrors include/h3d_gpu.h with the prefix orc_)
@@ -1450,7 +1457,7 @@ void orc_set_num_threads(int nt) {
 
 void* orc_create() { return new Oracle(); }
 int orc_create_handle(void** out, int, int, int, const void*) { *out = new Oracle(); return 0; }   // the signature of h3d_create
-void orc_destroy(void* p) { delete (Oracle*)p; }
+void orc_destroy(void* p) { Oracle* o = (Oracle*)p; delete (PData*)o->pdata; delete o; }
 const char* orc_last_error(void* p) { return ((Oracle*)p)->err.c_str(); }
 
 int orc_set_physics(void* p, const H3dPhysics* ph) { ((Oracle*)p)->ph = *ph; return 0; }
@@ -1461,6 +1468,79 @@ int orc_set_basis(void* p, int N, int nodeType, const double* x, const double* w
     o.N = N; o.n = n; o.nodeType = nodeType;
     o.x.assign(x, x + n); o.w.assign(w, w + n); o.D.assign(D, D + n * n); o.hatD.assign(hatD, hatD + n * n);
     o.sharpD.assign(sharpD, sharpD + n * n); o.v.assign(v, v + 2 * n); o.b.assign(b, b + 2 * n);
+    // every order set so far stays registered: NodalStorage(N) of a p-nonconforming mesh
+    if (!o.pdata) o.pdata = new PData();
+    Basis1& bs = PD(o).sp[N];
+    bs.N = N; bs.n = n; bs.x = o.x; bs.w = o.w; bs.D = o.D; bs.hatD = o.hatD; bs.v = o.v; bs.b = o.b;
+    return 0;
+}
+
+// Tset(Norigin, Ndest) % T (libs/spectral/InterpolationMatrices.f90:42-107), row-major [(Ndest+1)][(Norigin+1)]
+int orc_set_interpolation(void* p, int Norigin, int Ndest, const double* T) {
+    Oracle& o = *(Oracle*)p;
+    if (!o.pdata) o.pdata = new PData();
+    PD(o).T[{Norigin, Ndest}].assign(T, T + (size_t)(Norigin + 1) * (Ndest + 1));
+    return 0;
+}
+
+// h3d_set_mesh_p: as orc_set_mesh with the elements' orders elemOrder[nElem][3]; geometry arrays packed element after element /
+// face after face at their own sizes (faces at the face order, FaceClass.f90:187-282)
+int orc_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+                   const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone,
+                   const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,
+                   const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
+                   const double* faceJacobian, const double* faceX, const double* faceSurface) {
+    Oracle& o = *(Oracle*)p;
+    if (!o.pdata) { o.err = "set_basis must precede set_mesh_p"; return 1; }
+    if (o.ph.inviscid != H3D_STANDARD_DG || o.ph.les != H3D_LES_NONE || (o.ph.flowIsNavierStokes && o.ph.viscous != H3D_VISCOUS_BR1)) {
+        o.err = "p-nonconforming meshes: StandardDG with BR1 (or Euler), no LES"; return 1; }
+    PData& P = PD(o);
+    o.mixed = true; o.nElem = nElem; o.nFace = nFace;
+    o.elemFace.assign(elemFace, elemFace + 6 * (size_t)nElem); o.elemFaceSide.assign(elemFaceSide, elemFaceSide + 6 * (size_t)nElem);
+    o.faceElem.assign(faceElem, faceElem + 2 * (size_t)nFace); o.faceElemSide.assign(faceElemSide, faceElemSide + 2 * (size_t)nFace);
+    o.faceRot.assign(faceRot, faceRot + nFace); o.faceType.assign(faceType, faceType + nFace); o.faceZone.assign(faceZone, faceZone + nFace);
+    for (int f = 0; f < nFace; ++f) if (faceType[f] == H3D_FACE_MPI) { o.err = "the oracle is single-domain: MPI faces are not supported"; return 1; }
+    P.Nxyz.assign(elemOrder, elemOrder + 3 * (size_t)nElem);
+    P.eOff.assign(nElem + 1, 0); P.tOff.assign(6 * (size_t)nElem + 1, 0);
+    for (int e = 0; e < nElem; ++e) {
+        for (int d = 0; d < 3; ++d) if (!P.sp.count(elemOrder[3 * e + d])) { o.err = "set_basis has not been called for every polynomial order of the mesh"; return 1; }
+        P.eOff[e + 1] = P.eOff[e] + (size_t)(elemOrder[3 * e] + 1) * (elemOrder[3 * e + 1] + 1) * (elemOrder[3 * e + 2] + 1);
+        for (int lf = 0; lf < 6; ++lf) { int Nel[2]; elemFaceOrders(P, e, lf, Nel); P.tOff[6 * e + lf + 1] = P.tOff[6 * e + lf] + (size_t)(Nel[0] + 1) * (Nel[1] + 1); }
+    }
+    // Face_LinkWithElements (FaceClass.f90:187-282)
+    P.fo.assign(6 * (size_t)nFace, 0); P.proj.assign(2 * (size_t)nFace, 0); P.fOff.assign(nFace + 1, 0);
+    for (int f = 0; f < nFace; ++f) {
+        int NelL[2], NelR[2];
+        elemFaceOrders(P, faceElem[2 * f], faceElemSide[2 * f], NelL);
+        NelR[0] = NelL[0]; NelR[1] = NelL[1];
+        if (faceType[f] == H3D_FACE_INTERIOR) elemFaceOrders(P, faceElem[2 * f + 1], faceElemSide[2 * f + 1], NelR);
+        int NfR[2] = {NelR[0], NelR[1]};
+        const int rot = faceRot[f];
+        if (rot == 1 || rot == 3 || rot == 4 || rot == 6) { NfR[0] = NelR[1]; NfR[1] = NelR[0]; }
+        int* fo = &P.fo[6 * (size_t)f];
+        fo[0] = std::max(NelL[0], NfR[0]); fo[1] = std::max(NelL[1], NfR[1]); fo[2] = NelL[0]; fo[3] = NelL[1]; fo[4] = NfR[0]; fo[5] = NfR[1];
+        for (int s = 0; s < 2; ++s) {
+            P.proj[2 * f + s] = (fo[2 + 2 * s] != fo[0] ? 1 : 0) + (fo[3 + 2 * s] != fo[1] ? 2 : 0);
+            for (int d = 0; d < 2; ++d) if (fo[2 + 2 * s + d] != fo[d] && (!P.T.count({fo[2 + 2 * s + d], fo[d]}) || !P.T.count({fo[d], fo[2 + 2 * s + d]}))) {
+                o.err = "set_interpolation has not been called for every pair of orders that meet at a face"; return 1; }
+        }
+        if (!P.sp.count(fo[0]) || !P.sp.count(fo[1])) { o.err = "set_basis has not been called for every face order"; return 1; }
+        P.fOff[f + 1] = P.fOff[f] + (size_t)(fo[0] + 1) * (fo[1] + 1);
+    }
+    const size_t ne = P.eOff[nElem], nfn = P.fOff[nFace], nt = P.tOff[6 * (size_t)nElem];
+    o.JaXi.assign(jGradXi, jGradXi + 3 * ne); o.JaEta.assign(jGradEta, jGradEta + 3 * ne); o.JaZeta.assign(jGradZeta, jGradZeta + 3 * ne);
+    o.jac.assign(jacobian, jacobian + ne); o.invJac.resize(ne);
+    for (size_t q = 0; q < ne; ++q) o.invJac[q] = 1.0 / o.jac[q];
+    if (x) o.xyz.assign(x, x + 3 * ne);
+    if (volume) o.volume.assign(volume, volume + nElem);
+    o.fNormal.assign(faceNormal, faceNormal + 3 * nfn); o.fT1.assign(faceT1, faceT1 + 3 * nfn); o.fT2.assign(faceT2, faceT2 + 3 * nfn);
+    o.fJac.assign(faceJacobian, faceJacobian + nfn);
+    if (faceX) o.fX.assign(faceX, faceX + 3 * nfn);
+    if (faceSurface) o.fSurface.assign(faceSurface, faceSurface + nFace);
+    o.Q.assign(5 * ne, 0.0); o.QDot.assign(5 * ne, 0.0); o.G.assign(5 * ne, 0.0); o.S.assign(5 * ne, 0.0);
+    o.Ux.assign(5 * ne, 0.0); o.Uy.assign(5 * ne, 0.0); o.Uz.assign(5 * ne, 0.0); o.mu.assign(2 * ne, 0.0);
+    o.fQ.assign(10 * nfn, 0.0); o.fUx.assign(10 * nfn, 0.0); o.fUy.assign(10 * nfn, 0.0); o.fUz.assign(10 * nfn, 0.0); o.fmu.assign(4 * nfn, 0.0);
+    P.fStarE.assign(5 * nt, 0.0); P.unStarE.assign(15 * nt, 0.0);
     return 0;
 }
 
@@ -1501,6 +1581,7 @@ int orc_set_boundary_conditions(void* p, int nZones, const int* bcType, const do
 }
 
 int orc_set_wall_distance(void* p, const double* dWallElem, const double* dWallFace) {
+    if (((Oracle*)p)->mixed) { ((Oracle*)p)->err = "the wall distance is not available on p-nonconforming meshes"; return 1; }
     Oracle& o = *(Oracle*)p;
     o.dWall.assign(dWallElem, dWallElem + (size_t)o.nElem * o.n3()); o.fdWall.assign(dWallFace, dWallFace + (size_t)o.nFace * o.n * o.n);
     return 0;
@@ -1522,6 +1603,7 @@ int orc_download(void* p, double* Q, double* QDot, double* Ux, double* Uy, doubl
 
 // face traces of the last residual evaluation, for unit parity of the prolongation: [f][side][j][i][5]
 int orc_download_faces(void* p, double* fQ, double* fUx, double* fUy, double* fUz, double* fStar) {
+    if (((Oracle*)p)->mixed) { ((Oracle*)p)->err = "download_faces is not available on p-nonconforming meshes"; return 1; }
     Oracle& o = *(Oracle*)p; const size_t b = o.fQ.size() * sizeof(double);
     if (fQ) std::memcpy(fQ, o.fQ.data(), b);
     if (fUx) std::memcpy(fUx, o.fUx.data(), b);
@@ -1634,6 +1716,7 @@ double rkStage(Oracle& o, int scheme, int k, double t, double dt) {   // loop bo
 }  // namespace
 
 int orc_enable_limiter(void* p, int enabled, double minimum) {
+    if (((Oracle*)p)->mixed) { ((Oracle*)p)->err = "the stage limiter is not available on p-nonconforming meshes"; return 1; }
     Oracle& o = *(Oracle*)p;
     if (enabled && o.volume.empty()) { o.err = "the limiter needs the element volumes"; return 1; }
     o.limited = enabled != 0; if (minimum > 0.0) o.limiterMin = minimum;
@@ -1672,10 +1755,20 @@ int orc_max_residuals(void* p, double out[5]) {
 int orc_max_timestep(void* p, double cfl, double dcfl, double* dt_conv, double* dt_visc) {
     Oracle& o = *(Oracle*)p;
     double TimeStep_Conv = std::numeric_limits<double>::max(), TimeStep_Visc = std::numeric_limits<double>::max();
-    const double dcsi = o.N != 0 ? 1.0 / std::fabs(o.x[1] - o.x[0]) : 0.0, deta = dcsi, dzet = dcsi;
-    const double dcsi2 = dcsi * dcsi, deta2 = deta * deta, dzet2 = dzet * dzet;
-    const size_t nn = (size_t)o.n3() * o.nElem;
+    double dcsi = o.N != 0 ? 1.0 / std::fabs(o.x[1] - o.x[0]) : 0.0, deta = dcsi, dzet = dcsi;
+    double dcsi2 = dcsi * dcsi, deta2 = deta * deta, dzet2 = dzet * dzet;
+    const size_t nn = o.mixed ? PD(o).eOff[o.nElem] : (size_t)o.n3() * o.nElem;
+    int eCur = -1;
     for (size_t g = 0; g < nn; ++g) {
+        if (o.mixed) {   // the spacings of the element's own nodal storages (:915-939)
+            const PData& P = PD(o);
+            while (g >= P.eOff[eCur + 1]) {
+                ++eCur;
+                auto spacing = [&](int N) { const Basis1& b = P.sp.at(N); return N != 0 ? 1.0 / std::fabs(b.x[1] - b.x[0]) : 0.0; };
+                dcsi = spacing(P.Nxyz[3 * eCur]); deta = spacing(P.Nxyz[3 * eCur + 1]); dzet = spacing(P.Nxyz[3 * eCur + 2]);
+                dcsi2 = dcsi * dcsi; deta2 = deta * deta; dzet2 = dzet * dzet;
+            }
+        }
         const double* Q = &o.Q[5 * g];
         double u = std::fabs(Q[1] / Q[0]), v = std::fabs(Q[2] / Q[0]), w = std::fabs(Q[3] / Q[0]);
         double pr = Pressure(o, Q);
@@ -1704,30 +1797,39 @@ int orc_max_timestep(void* p, double cfl, double dcfl, double* dt_conv, double* 
 // ScalarSurfaceIntegral / VectorSurfaceIntegral (libs/monitors/SurfaceIntegrals.f90:40-445) with getStressTensor
 // (Physics_NS.f90:822-886); the state (and gradients) are prolonged anew as the reference does (:57-77)
 int orc_surface_integral(void* p, int zone, int kind, double* out) {
-    Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
+    Oracle& o = *(Oracle*)p; Idx ix{o.n};
     if (kind < H3D_SURF_SURFACE || kind > H3D_SURF_VISCOUS_FORCE) { o.err = "unknown surface integral"; return 1; }
     const bool viscous = kind == H3D_SURF_TOTAL_FORCE || kind == H3D_SURF_VISCOUS_FORCE;
     if (viscous && !o.ph.computeGradients) { o.err = "surface integral needs gradients"; return 1; }
-    prolongToFaces(o, 5, o.Q, o.fQ);
-    if (o.ph.computeGradients) { prolongToFaces(o, 5, o.Ux, o.fUx); prolongToFaces(o, 5, o.Uy, o.fUy); prolongToFaces(o, 5, o.Uz, o.fUz); }
+    if (o.mixed) {
+        prolongToFacesP(o, 5, o.Q, o.fQ);
+        if (o.ph.computeGradients) { prolongToFacesP(o, 5, o.Ux, o.fUx); prolongToFacesP(o, 5, o.Uy, o.fUy); prolongToFacesP(o, 5, o.Uz, o.fUz); }
+    } else {
+        prolongToFaces(o, 5, o.Q, o.fQ);
+        if (o.ph.computeGradients) { prolongToFaces(o, 5, o.Ux, o.fUx); prolongToFaces(o, 5, o.Uy, o.fUy); prolongToFaces(o, 5, o.Uz, o.fUz); }
+    }
     double val[3] = {0, 0, 0};
     for (int f = 0; f < o.nFace; ++f) {
         if (o.faceType[f] != H3D_FACE_BOUNDARY || o.faceZone[f] != zone) continue;
         double fv[3] = {0, 0, 0};
-        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
-            const double* Q = &o.fQ[ix.fnode(f, 0, i, j) * 5];
-            const double* nh = &o.fNormal[3 * ix.gnode(f, i, j)];
-            const double Jf = o.fJac[ix.gnode(f, i, j)];
+        // a p-nonconforming mesh integrates with the nodal storages of the face orders (SurfaceIntegrals.f90:100-104)
+        const int n1 = o.mixed ? PD(o).fo[6 * f] + 1 : o.n, n2 = o.mixed ? PD(o).fo[6 * f + 1] + 1 : o.n;
+        const double* w1 = o.mixed ? PD(o).sp.at(n1 - 1).w.data() : o.w.data(); const double* w2 = o.mixed ? PD(o).sp.at(n2 - 1).w.data() : o.w.data();
+        for (int j = 0; j < n2; ++j) for (int i = 0; i < n1; ++i) {
+            const size_t gL = o.mixed ? PD(o).fnode(f, 0, i, j) : ix.fnode(f, 0, i, j), gg = o.mixed ? PD(o).gnode(f, i, j) : ix.gnode(f, i, j);
+            const double* Q = &o.fQ[gL * 5];
+            const double* nh = &o.fNormal[3 * gg];
+            const double Jf = o.fJac[gg];
             switch (kind) {
-                case H3D_SURF_SURFACE: fv[0] = fv[0] + o.w[i] * o.w[j] * Jf; break;
-                case H3D_SURF_MASS_FLOW: fv[0] = fv[0] + (Q[IRHOU] * nh[0] + Q[IRHOV] * nh[1] + Q[IRHOW] * nh[2]) * o.w[i] * o.w[j] * Jf; break;
-                case H3D_SURF_FLOW_RATE: fv[0] = fv[0] + (1.0 / Q[IRHO]) * (Q[IRHOU] * nh[0] + Q[IRHOV] * nh[1] + Q[IRHOW] * nh[2]) * o.w[i] * o.w[j] * Jf; break;
-                case H3D_SURF_PRESSURE: { double pr = Pressure(o, Q); fv[0] = fv[0] + pr * o.w[i] * o.w[j] * Jf; } break;
-                case H3D_SURF_VEC_SURFACE: for (int d = 0; d < 3; ++d) fv[d] = fv[d] + o.w[i] * o.w[j] * Jf * nh[d]; break;
-                case H3D_SURF_PRESSURE_FORCE: { double pr = Pressure(o, Q); for (int d = 0; d < 3; ++d) fv[d] = fv[d] + (pr * nh[d]) * Jf * o.w[i] * o.w[j]; } break;
+                case H3D_SURF_SURFACE: fv[0] = fv[0] + w1[i] * w2[j] * Jf; break;
+                case H3D_SURF_MASS_FLOW: fv[0] = fv[0] + (Q[IRHOU] * nh[0] + Q[IRHOV] * nh[1] + Q[IRHOW] * nh[2]) * w1[i] * w2[j] * Jf; break;
+                case H3D_SURF_FLOW_RATE: fv[0] = fv[0] + (1.0 / Q[IRHO]) * (Q[IRHOU] * nh[0] + Q[IRHOV] * nh[1] + Q[IRHOW] * nh[2]) * w1[i] * w2[j] * Jf; break;
+                case H3D_SURF_PRESSURE: { double pr = Pressure(o, Q); fv[0] = fv[0] + pr * w1[i] * w2[j] * Jf; } break;
+                case H3D_SURF_VEC_SURFACE: for (int d = 0; d < 3; ++d) fv[d] = fv[d] + w1[i] * w2[j] * Jf * nh[d]; break;
+                case H3D_SURF_PRESSURE_FORCE: { double pr = Pressure(o, Q); for (int d = 0; d < 3; ++d) fv[d] = fv[d] + (pr * nh[d]) * Jf * w1[i] * w2[j]; } break;
                 default: {
                     double U_x[3], U_y[3], U_z[3], tau[3][3], mu, kappa;
-                    const double* gx = &o.fUx[ix.fnode(f, 0, i, j) * 5]; const double* gy = &o.fUy[ix.fnode(f, 0, i, j) * 5]; const double* gz = &o.fUz[ix.fnode(f, 0, i, j) * 5];
+                    const double* gx = &o.fUx[gL * 5]; const double* gy = &o.fUy[gL * 5]; const double* gz = &o.fUz[gL * 5];
                     if (o.ph.gradientVariables == H3D_GRADVARS_ENTROPY) {   // getStressTensor's own entropy branch (Physics_NS.f90:858-866)
                         double invRho = 1.0 / Q[IRHO];
                         double p_div_rho = o.ph.gammaMinus1 * invRho * (Q[IRHOE] - 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) * invRho);
@@ -1752,8 +1854,8 @@ int orc_surface_integral(void* p, int zone, int kind, double* out) {
                     double pr = Pressure(o, Q);
                     for (int d = 0; d < 3; ++d) {
                         double tn = tau[d][0] * nh[0] + tau[d][1] * nh[1] + tau[d][2] * nh[2];   // matmul(tau, n)
-                        if (kind == H3D_SURF_TOTAL_FORCE) fv[d] = fv[d] + (pr * nh[d] - tn) * Jf * o.w[i] * o.w[j];
-                        else fv[d] = fv[d] - tn * Jf * o.w[i] * o.w[j];
+                        if (kind == H3D_SURF_TOTAL_FORCE) fv[d] = fv[d] + (pr * nh[d] - tn) * Jf * w1[i] * w2[j];
+                        else fv[d] = fv[d] - tn * Jf * w1[i] * w2[j];
                     }
                 }
             }
@@ -1768,11 +1870,15 @@ int orc_surface_integral(void* p, int zone, int kind, double* out) {
 int orc_probe(void* p, int nProbes, const int* elem, const int* variable, const double* lxi, const double* leta, const double* lzeta, double* values) {
     Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
     const double gamma = o.ph.gamma;
+    // p-nonconforming meshes: the Lagrange vectors of probe pr are lxi[pr*ld + i] with ld = the largest number of nodes per direction
+    int ld = n;
+    if (o.mixed) { ld = 0; for (int q : PD(o).Nxyz) ld = std::max(ld, q + 1); }
     for (int pr = 0; pr < nProbes; ++pr) {
         if (elem[pr] < 0 || elem[pr] >= o.nElem) { o.err = "probe element out of range"; return 1; }
         double value = 0.0;
-        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
-            const double* Q = &o.Q[5 * ix.node(elem[pr], i, j, k)];
+        const int nx = o.mixed ? PD(o).Nxyz[3 * elem[pr]] + 1 : n, ny = o.mixed ? PD(o).Nxyz[3 * elem[pr] + 1] + 1 : n, nz = o.mixed ? PD(o).Nxyz[3 * elem[pr] + 2] + 1 : n;
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            const double* Q = &o.Q[5 * (o.mixed ? PD(o).eOff[elem[pr]] + (size_t)(k * ny + j) * nx + i : ix.node(elem[pr], i, j, k))];
             double var;
             switch (variable[pr]) {
                 case H3D_PROBE_PRESSURE: var = Pressure(o, Q); break;
@@ -1787,7 +1893,7 @@ int orc_probe(void* p, int nProbes, const int* elem, const int* variable, const 
                 case H3D_PROBE_K: var = 0.5 * (POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO]; break;
                 default: o.err = "unknown probe variable"; return 1;
             }
-            value = value + var * lxi[pr * n + i] * leta[pr * n + j] * lzeta[pr * n + k];
+            value = value + var * lxi[pr * ld + i] * leta[pr * ld + j] * lzeta[pr * ld + k];
         }
         values[pr] = value;
     }
@@ -1804,6 +1910,7 @@ int orc_snapshot_end(void* p, double* Q) {
     return 0;
 }
 int orc_statistics_update(void* p, int reset) {
+    if (((Oracle*)p)->mixed) { ((Oracle*)p)->err = "the statistics monitor is not available on p-nonconforming meshes"; return 1; }
     Oracle& o = *(Oracle*)p;
     const int nv = o.ph.computeGradients ? 29 : 14;
     const size_t nn = (size_t)o.nElem * o.n3();
@@ -1843,12 +1950,17 @@ int orc_statistics_download(void* p, double* data, int* nVars, int* nSamples) {
 int orc_volume_integral(void* p, int kind, double* out) {
     Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
     double val = 0.0;
+    if (o.mixed && kind == H3D_INT_KINETIC_ENERGY_BALANCE) { o.err = "kinetic energy balance is not available on p-nonconforming meshes"; return 1; }
     for (int e = 0; e < o.nElem; ++e) {
         double loc = 0.0;
-        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
-            size_t g = ix.node(e, i, j, k);
+        // p-nonconforming meshes: the element's own nodal storages (VolumeIntegrals.f90:190-196)
+        const int nx = o.mixed ? PD(o).Nxyz[3 * e] + 1 : n, ny = o.mixed ? PD(o).Nxyz[3 * e + 1] + 1 : n, nz = o.mixed ? PD(o).Nxyz[3 * e + 2] + 1 : n;
+        const double* wx = o.mixed ? PD(o).sp.at(nx - 1).w.data() : o.w.data(); const double* wy = o.mixed ? PD(o).sp.at(ny - 1).w.data() : o.w.data();
+        const double* wz = o.mixed ? PD(o).sp.at(nz - 1).w.data() : o.w.data();
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            size_t g = o.mixed ? PD(o).eOff[e] + (size_t)(k * ny + j) * nx + i : ix.node(e, i, j, k);
             const double* Q = &o.Q[5 * g]; const double* QD = &o.QDot[5 * g];
-            double wJ = o.w[i] * o.w[j] * o.w[k] * o.jac[g];
+            double wJ = wx[i] * wy[j] * wz[k] * o.jac[g];
             switch (kind) {
                 case H3D_INT_VOLUME: loc = loc + wJ; break;
                 case H3D_INT_KINETIC_ENERGY: {
@@ -1896,7 +2008,7 @@ int orc_volume_integral(void* p, int kind, double* out) {
                     loc = loc + o.w[i] * o.w[j] * o.w[k] * (o.jac[g] * (KinEn + work - p3 * (gx[IRHOU] + gy[IRHOV] + gz[IRHOW])) + corr);
                 } break;
                 case H3D_INT_VELOCITY:
-                    loc = loc + o.w[i] * o.w[j] * o.w[k] * std::sqrt(POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] * o.jac[g];
+                    loc = loc + wx[i] * wy[j] * wz[k] * std::sqrt(POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] * o.jac[g];
                     break;
                 case H3D_INT_ENTROPY: {
                     double pr = Pressure(o, Q);

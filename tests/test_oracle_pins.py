@@ -641,3 +641,83 @@ def test_split_form_standard_average_equals_standard_dg_on_lobatto():
         sem.set_Q(Q); sem.ComputeTimeDerivative(0.0)
         qd.append(sem.QDot())
     assert np.abs(qd[0]).max() < 1e-11 and np.abs(qd[1]).max() < 1e-11
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def cylinder_different_orders(api=None, steps=100):
+    """Solver/test/NavierStokes/CylinderDifferentOrders: the cylinder case on CylinderNSpol3_1elem_y.mesh with the element-wise
+    anisotropic polynomial orders of MESH/OrdersN2N3N4N5_anisotropy.csv ((2,2,1) ... (5,5,1)): p-nonconforming faces with mortar
+    projections.  Re 45, M 0.3, Roe, BR1, RK3, cfl = dcfl = 0.2 (CylinderDifferentOrders.control)."""
+    import math
+    from horses3d_b200.hostmesh import read_order_file
+    from horses3d_b200.physics import bc_parameters
+    from horses3d_b200 import probes
+    phys = make_physics(flow="NS", mach=0.3, reynolds=45.0, riemann="roe")
+    theta, phi = 0.0, 90.0 * (math.pi / 180.0)
+    zones = [("innercylinder", "noslipwall"), ("bottom", "freeslipwall"), ("top", "freeslipwall"), ("back", "inflow"),
+             ("left", "inflow"), ("front", "inflow"), ("right", "outflow")]
+    p_in, rho_in = 1.0 / phys.gammaM2, 1.0
+    v_in = phys.Mach * math.sqrt(phys.gamma * p_in / rho_in)
+    params = []
+    for _, t in zones:
+        if t == "inflow":
+            params.append(bc_parameters("inflow", phys, rho=rho_in, v=v_in, aoa_theta=theta, aoa_phi=phi, p=p_in))
+        elif t == "outflow":
+            params.append(bc_parameters("outflow", phys, p=1.0 / phys.gammaM2))
+        else:
+            params.append(bc_parameters(t, phys))
+    orders = read_order_file(os.path.join(GOLDEN, "OrdersN2N3N4N5_anisotropy.csv"))
+    m = HostMesh.read(os.path.join(GOLDEN, "CylinderNSpol3_1elem_y.mesh")).connect([(z, t, None) for z, t in zones], np.array(params))
+    m.geometry_p(orders, GAUSS)
+    assert m.sizes()[:2] == (466, 1895) and len(orders) == 466
+    sem = DGSem(api if api is not None else oracle_api.OracleApi(), m, phys)
+    assert sem.NDOF == 15480
+    u, v, w = math.cos(theta) * math.cos(phi), math.sin(theta) * math.cos(phi), math.sin(phi)
+    Q = np.zeros((sem.NDOF, 5))
+    Q[:, 0], Q[:, 1], Q[:, 2], Q[:, 3] = 1.0, u, v, w
+    Q[:, 4] = (1.0 / phys.gammaM2) / (phys.gamma - 1.0) + 0.5 * (u ** 2 + v ** 2 + w ** 2)
+    sem.set_Q(Q)
+    res = sem.integrate(steps, cfl=0.2, dcfl=0.2, monitors=False)[-1]["residuals"]
+    cd = sem.surface_monitor("innercylinder", "drag", [0.0, 0.0, 1.0], reference_surface=1.0)
+    cl = sem.surface_monitor("innercylinder", "lift", [1.0, 0.0, 0.0], reference_surface=1.0)
+    wake_u = probes.evaluate(sem, [probes.Probe(sem, [0.0, 0.5, 4.0], "u")])[0]
+    return sem, res, cd, cl, wake_u
+
+
+K13 = dict(residuals=np.array([9.5806856005342933E+00, 2.0804408993372231E+01, 3.7668665836122439E-01, 2.8294964263463125E+01, 2.6470704194989690E+02]),
+           wake_u=7.0745334553937767E-12, cd=1.1700328563228789E+01, cl=2.1473912634295544E-05)
+
+
+def test_k13_cylinder_different_orders_100_steps():
+    """K13: expected values and the 1e-11 tolerance from test/NavierStokes/CylinderDifferentOrders/SETUP/ProblemFile.f90:553-614.
+    Pins the p-nonconforming path: per-element anisotropic orders, face orders and projection types (FaceClass.f90:187-282), the
+    interpolation of the traces to the face order and the L2 projection of the interface fluxes back (:284-381, :596-696,
+    :865-961), the re-sampled curved patches and the anisotropic metric terms (HexMesh.f90:2797-2960, MappedGeometry.f90)."""
+    _, res, cd, cl, wake_u = cylinder_different_orders()
+    print("K13 rel", (res - K13["residuals"]) / K13["residuals"], "cd", cd - K13["cd"], "cl", cl - K13["cl"], "wake_u", wake_u - K13["wake_u"])
+    assert np.abs(res - K13["residuals"]).max() < 1.0e-11                    # residual + 1 compared to 1e-11
+    assert abs(cd - K13["cd"]) < 1.0e-11 * 12.0
+    assert abs(cl - K13["cl"]) < 1.0e-11
+    assert abs(wake_u - K13["wake_u"]) < 1.0e-11
+
+
+def test_mixed_oracle_with_uniform_orders_equals_the_uniform_oracle():
+    """The p-nonconforming restatement fed with one order for every element must reproduce the uniform-order oracle bit for bit
+    (same loops, same order of sums) -- on a curved, randomly re-oriented box with all eight face rotations."""
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")
+    out = []
+    for mixed in (False, True):
+        m = HostMesh.box(3, amp=0.15, shuffle=True).connect()
+        m = m.geometry_p([3, 3, 3], GAUSS) if mixed else m.geometry(3, GAUSS, reference_order=True)
+        sem = DGSem(oracle_api.OracleApi(), m, phys)
+        x = sem.node_coordinates().reshape(-1, 3)
+        sem.set_Q(taylor_green_ic(x, p0=1.0 / (1.4 * 0.3 ** 2)).reshape(-1, 5))
+        sem.TakeRK3Step(0.0, 1.0e-3, ctd_after_step=True)
+        d = sem.download(Q=True, QDot=True, gradients=True)
+        out.append({k: v.reshape(-1, 5) for k, v in d.items()})
+        out[-1]["dt"] = np.array(sem.MaxTimeStep(0.3, 0.3))
+        out[-1]["ke"] = np.array([sem.ScalarVolumeIntegral(P.INT_KINETIC_ENERGY), sem.ScalarVolumeIntegral(P.INT_ENSTROPHY)])
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k]), k
