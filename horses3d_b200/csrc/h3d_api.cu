@@ -13,8 +13,45 @@
 
 #include "h3d_gpu.h"
 #include "h3d_kernels2.cuh"
+#include "h3d_mixed.cuh"
 
 using namespace h3d;
+
+// ---- p-nonconforming meshes: the CUDA backend of MixedSolver (h3d_mixed.cuh) -----------------------------------------------
+namespace h3d {
+template <class F>
+__global__ void __launch_bounds__(256) k_mx(const F f, long long count) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) f(t);
+}
+struct CudaBackend {
+    cudaStream_t stream = nullptr;
+    std::vector<void*>* allocs = nullptr;    // freed with the context
+    std::string msg; bool failed = false;
+    void note(cudaError_t e, const char* what) { if (e != cudaSuccess && !failed) { failed = true; msg = std::string(what) + ": " + cudaGetErrorString(e); } }
+    template <class T> T* alloc(size_t count) {
+        void* q = nullptr;
+        const cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+        note(e, "cudaMalloc");
+        if (e != cudaSuccess) return nullptr;
+        allocs->push_back(q);
+        return (T*)q;
+    }
+    template <class T> void upload(T* dst, const T* src, size_t count) {
+        note(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync (upload)");
+        note(cudaStreamSynchronize(stream), "cudaStreamSynchronize");      // the caller may reuse src
+    }
+    template <class T> void download(T* dst, const T* src, size_t count) {
+        note(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync (download)");
+        note(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    }
+    template <class F> void launch(const F& f, long long count) {
+        k_mx<F><<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(f, count);
+        note(cudaGetLastError(), "kernel launch");
+    }
+    const char* error() { return failed ? msg.c_str() : nullptr; }
+};
+}  // namespace h3d
 
 namespace {
 thread_local std::string g_create_err;
@@ -94,6 +131,9 @@ struct h3d_context {
     int nBoundaryFaces = 0;
     bool haveVolume = false;       // element volumes and face surfaces were given (LES filter widths)
     int* dProbeEV = nullptr; double* dProbeL = nullptr; size_t probeCap = 0;   // h3d_probe scratch, kept between calls
+    // p-nonconforming meshes (h3d_set_mesh_p): the solver of h3d_mixed.cuh; mixedMode routes every entry point to it
+    MixedSolver<CudaBackend>* mx = nullptr; bool mixedMode = false;
+    std::vector<int> hBcType; std::vector<double> hBcParams;
 };
 
 #define CTX_CHECK(call)                                                                                   \
@@ -114,6 +154,15 @@ struct h3d_context {
     } while (0)
 
 namespace {
+
+MixedSolver<CudaBackend>* ensureMx(h3d_context* h) {
+    if (!h->mx) { CudaBackend be; be.stream = h->sCompute; be.allocs = &h->allocs; h->mx = new MixedSolver<CudaBackend>(be); }
+    return h->mx;
+}
+// result of a MixedSolver call -> the context's error state
+int mxDone(h3d_context* h, int rc) { if (rc) h->err = h->mx->err; return rc; }
+#define MX_UNSUPPORTED(what)                                                                               \
+    do { if (h->mixedMode) { h->err = std::string(what) + " is not available on p-nonconforming meshes (h3d_set_mesh_p)"; return 1; } } while (0)
 
 template <typename T>
 int devAlloc(h3d_context* h, T** p, size_t count) {
@@ -1009,6 +1058,7 @@ int h3d_destroy(h3d_handle h) {
     for (cudaEvent_t ev : {h->evA, h->evB, h->evFaces, h->evGrad, h->evSent, h->evT0, h->evT1}) if (ev) cudaEventDestroy(ev);
     if (h->sCompute) cudaStreamDestroy(h->sCompute);
     if (h->sComm) cudaStreamDestroy(h->sComm);
+    delete h->mx;
     delete h;
     return 0;
 }
@@ -1023,33 +1073,23 @@ int h3d_last_error_copy(h3d_handle h, char* buf, int len) {
 }
 
 int h3d_set_physics(h3d_handle h, const H3dPhysics* p) {
-    if (p->riemann < H3D_RIEMANN_ROE || p->riemann > H3D_RIEMANN_MATRIXDISS) { h->err = "Riemann Solver not recognized."; return 1; }
-    if (p->averaging < H3D_AVG_STANDARD || p->averaging > H3D_AVG_CHANDRASEKAR) { h->err = "Averaging not recognized."; return 1; }
-    if (p->inviscid != H3D_STANDARD_DG && p->inviscid != H3D_SPLIT_DG) { h->err = "Requested inviscid discretization is not implemented."; return 1; }
+    if (physFromH3dPhysics(p, h->ph, h->err)) return 1;   // validation + the trimmed kernel parameter (h3d_physics.cuh)
     h->physics = *p;
-    Phys& q = h->ph;
-    q.gamma = p->gamma; q.gm1 = p->gammaMinus1; q.gammaM2 = p->gammaM2; q.mu = p->mu; q.mu_to_kappa = p->mu_to_kappa;
-    q.S_div_Tref = p->S_div_Tref; q.T_renorm = p->T_renorm; q.lambdaStab = p->lambdaStab; q.Cs = p->smagorinsky_Cs;
-    q.ns = p->flowIsNavierStokes; q.riemann = p->riemann; q.averaging = p->averaging; q.les = p->les;
-    if (p->viscous < H3D_VISCOUS_BR1 || p->viscous > H3D_VISCOUS_IP) { h->err = "Requested viscous discretization is not implemented."; return 1; }
-    if (p->ipVariant < -1 || p->ipVariant > 1) { h->err = "Unknown selected IP variant."; return 1; }
-    if (p->gradientVariables < H3D_GRADVARS_STATE || p->gradientVariables > H3D_GRADVARS_ENERGY) { h->err = "Gradient variables are not currently implemented."; return 1; }
-    q.viscous = p->flowIsNavierStokes ? p->viscous : H3D_VISCOUS_BR1; q.ipVariant = p->ipVariant; q.eta = p->penaltyParameter;
-    q.gradVars = p->flowIsNavierStokes ? p->gradientVariables : H3D_GRADVARS_STATE;
-    if (p->les < H3D_LES_NONE || p->les > H3D_LES_VREMAN) { h->err = "LES model not recognized."; return 1; }
+    const Phys& q = h->ph;
     h->genGrad = q.gradVars != H3D_GRADVARS_STATE || p->les > H3D_LES_SMAGORINSKY;   // WALE / Vreman live in the general instantiations
     // anything outside the base set runs in the general instantiations so that it costs the headline kernels nothing
     h->extPhysics = p->riemann > H3D_RIEMANN_CENTRAL || p->averaging > H3D_AVG_PIROZZOLI || h->genGrad ||
                     (p->inviscid == H3D_SPLIT_DG && p->averaging == H3D_AVG_STANDARD);   // k_volume<n,1> stages primitives: KG / Pirozzoli only
-    q.wallModel = (p->les != H3D_LES_NONE && p->les_wall_model == 1) ? 1 : 0;
-    if (p->les_wall_model != 0 && p->les_wall_model != 1) { h->err = "LES wall model not recognized."; return 1; }
     h->havePhysics = true;
     return 0;
 }
 
 int h3d_set_basis(h3d_handle h, int N, int nodeType, const double* x, const double* w, const double* D, const double* hatD,
                   const double* sharpD, const double* v, const double* b) {
-    if (N < 1 || N > 9) { h->err = "polynomial order not instantiated (supported N = 1..9)"; return 1; }
+    if (N < 1 || N >= MX_MAXN) { h->err = "polynomial order out of range (1..15)"; return 1; }
+    // every order given stays registered: NodalStorage(N) of a p-nonconforming mesh (h3d_set_mesh_p)
+    ensureMx(h)->setBasis(N, x, w, D, hatD, v, b);
+    if (N > 9) { h->haveBasis = false; return 0; }   // usable by h3d_set_mesh_p only: the uniform-order kernels are instantiated for N = 1..9
     CTX_CHECK(cudaSetDevice(h->device));
     const int n = N + 1;
     h->N = N; h->n = n; h->nodeType = nodeType; h->hx.assign(x, x + n);
@@ -1096,6 +1136,7 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
                  const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
                  const double* faceJacobian, const double* faceX, const double* faceSurface) {
     (void)x; (void)faceX; (void)faceElemSide;
+    if (h->mixedMode) { h->err = "the context already holds a p-nonconforming mesh"; return 1; }
     if (!h->haveBasis) { h->err = "h3d_set_basis must precede h3d_set_mesh"; return 1; }
     if (h->haveMesh) { h->err = "h3d_set_mesh may be called once per context"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1211,7 +1252,35 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
     return 0;
 }
 
+int h3d_set_interpolation(h3d_handle h, int Norigin, int Ndest, const double* T) {
+    if (!T) { h->err = "h3d_set_interpolation: null matrix"; return 1; }
+    return mxDone(h, ensureMx(h)->setInterpolation(Norigin, Ndest, T));
+}
+
+int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+                   const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone,
+                   const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,
+                   const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
+                   const double* faceJacobian, const double* faceX, const double* faceSurface) {
+    (void)x; (void)volume; (void)faceX; (void)faceSurface;   // sources and LES widths are not part of this path
+    if (!h->havePhysics) { h->err = "h3d_set_physics must precede h3d_set_mesh_p"; return 1; }
+    if (h->haveMesh || h->mixedMode) { h->err = "the context already holds a mesh"; return 1; }
+    if (h->nranks > 1) { h->err = "p-nonconforming meshes are single-domain"; return 1; }
+    if (!elemOrder || !elemFace || !elemFaceSide || !faceElem || !faceElemSide || !faceRot || !faceType || !faceZone || !jGradXi || !jGradEta ||
+        !jGradZeta || !jacobian || !faceNormal || !faceT1 || !faceT2 || !faceJacobian) { h->err = "h3d_set_mesh_p: null array"; return 1; }
+    CTX_CHECK(cudaSetDevice(h->device));
+    MixedSolver<CudaBackend>* mx = ensureMx(h);
+    mx->ph = h->ph;
+    int rc = mx->setMesh(h->physics, nElem, nFace, elemOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone,
+                         jGradXi, jGradEta, jGradZeta, jacobian, faceNormal, faceT1, faceT2, faceJacobian);
+    if (rc) return mxDone(h, rc);
+    h->mixedMode = true; h->nElem = nElem; h->nFace = nFace;
+    if (!h->hBcType.empty()) rc = mx->setBoundaryConditions((int)h->hBcType.size(), h->hBcType.data(), h->hBcParams.data());
+    return mxDone(h, rc);
+}
+
 int h3d_set_wall_distance(h3d_handle h, const double* dWallElem, const double* dWallFace) {
+    MX_UNSUPPORTED("the LES wall distance");
     CTX_CHECK(cudaSetDevice(h->device));
     if (!h->haveMesh) { h->err = "h3d_set_wall_distance: set the mesh first"; return 1; }
     if (!dWallElem || !dWallFace) { h->err = "h3d_set_wall_distance: null array"; return 1; }
@@ -1229,6 +1298,7 @@ int h3d_set_wall_distance(h3d_handle h, const double* dWallElem, const double* d
 }
 
 int h3d_set_face_h(h3d_handle h, const double* faceH) {
+    MX_UNSUPPORTED("the interior-penalty face distance");
     CTX_CHECK(cudaSetDevice(h->device));
     if (!h->haveMesh) { h->err = "h3d_set_face_h: set the mesh first"; return 1; }
     if (!faceH) { h->err = "h3d_set_face_h: null array"; return 1; }
@@ -1249,6 +1319,8 @@ int h3d_set_boundary_conditions(h3d_handle h, int nZones, const int* bcType, con
     for (int z = 0; z < nZones; ++z)
         if (bcType[z] < H3D_BC_PERIODIC || bcType[z] > H3D_BC_OUTFLOW) { h->err = "h3d_set_boundary_conditions: unknown boundary condition type"; return 1; }
     if (h->haveMesh && h->maxZone >= nZones) { h->err = "h3d_set_boundary_conditions: a boundary face of the mesh refers to a zone beyond this table"; return 1; }
+    h->hBcType.assign(bcType, bcType + nZones); h->hBcParams.assign(bcParams, bcParams + 16 * (size_t)nZones);
+    if (h->mixedMode) return mxDone(h, h->mx->setBoundaryConditions(nZones, bcType, bcParams));
     h->nZones = nZones;
     int* dt; double* dp;
     if (devAlloc(h, &dt, nZones) || devAlloc(h, &dp, 16 * (size_t)nZones)) return 2;
@@ -1259,6 +1331,7 @@ int h3d_set_boundary_conditions(h3d_handle h, int nZones, const int* bcType, con
 }
 
 int h3d_set_halo(h3d_handle h, int nNeighbors, const int* neighborRank, const int* faceCount, const int* faceIDs, const int* thisSide) {
+    MX_UNSUPPORTED("the MPI face exchange");
     if (!h->haveMesh) { h->err = "h3d_set_mesh must precede h3d_set_halo"; return 1; }
     if (nNeighbors > 0 && h->nranks < 2) { h->err = "halo given but the context has a single rank"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1281,6 +1354,7 @@ int h3d_set_halo(h3d_handle h, int nNeighbors, const int* neighborRank, const in
 }
 
 int h3d_upload_Q(h3d_handle h, const double* Q) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); return mxDone(h, h->mx->uploadQ(Q)); }
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t ne = (size_t)h->nElem * h->n * h->n * h->n;
@@ -1302,10 +1376,12 @@ int h3d_upload_Q(h3d_handle h, const double* Q) {
     }
     h->facesValid = false; ++h->stateVersion;
     CTX_CHECK(cudaGetLastError());
+    CTX_CHECK(cudaStreamSynchronize(h->sXfer));   // the caller may reuse or free Q (pinned memory is not staged by the driver)
     return 0;
 }
 
 int h3d_download(h3d_handle h, double* Q, double* QDot, double* Ux, double* Uy, double* Uz) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); return mxDone(h, h->mx->download(Q, QDot, Ux, Uy, Uz)); }
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     const int n3 = h->n * h->n * h->n;
@@ -1333,6 +1409,7 @@ int h3d_download(h3d_handle h, double* Q, double* QDot, double* Ux, double* Uy, 
 }
 
 int h3d_snapshot_begin(h3d_handle h) {
+    MX_UNSUPPORTED("the asynchronous snapshot");
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
     if (h->snapPending) { h->err = "a snapshot is already in flight: call h3d_snapshot_end first"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1362,6 +1439,7 @@ int h3d_snapshot_begin(h3d_handle h) {
 }
 
 int h3d_snapshot_end(h3d_handle h, double* Q) {
+    MX_UNSUPPORTED("the asynchronous snapshot");
     if (!h->snapPending) { h->err = "no snapshot in flight"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     CTX_CHECK(cudaEventSynchronize(h->evSnapDone));
@@ -1371,6 +1449,7 @@ int h3d_snapshot_end(h3d_handle h, double* Q) {
 }
 
 int h3d_set_source(h3d_handle h, const double* S) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); return mxDone(h, h->mx->setSource(S)); }
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     if (!S) { h->m.S = nullptr; return 0; }
@@ -1398,6 +1477,7 @@ static int checkReady(h3d_handle h) {
 }
 
 int h3d_compute_time_derivative(h3d_handle h, double time) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); h->mx->ph = h->ph; return mxDone(h, h->mx->residual(h->physics, MxRk{0, 0.0, 0.0, 0.0, 0})); }
     (void)time;   // no time-dependent boundary condition or source is evaluated on the device
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1446,6 +1526,7 @@ int rkStage(h3d_context* h, int scheme, int k, double dt) {
 }  // namespace
 
 int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_step) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); h->mx->ph = h->ph; return mxDone(h, h->mx->rkStep(h->physics, scheme, dt, ctd_after_step)); }
     (void)t;
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1457,6 +1538,7 @@ int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_ste
 }
 
 int h3d_enable_limiter(h3d_handle h, int enabled, double minimum) {
+    MX_UNSUPPORTED("the stage limiter");
     if (!h->haveMesh) { h->err = "h3d_enable_limiter: set the mesh first"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     if (enabled && !h->dVolume) {
@@ -1470,6 +1552,7 @@ int h3d_enable_limiter(h3d_handle h, int enabled, double minimum) {
 }
 
 int h3d_rk_stage(h3d_handle h, int scheme, int stage, double t, double dt) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); h->mx->ph = h->ph; return mxDone(h, h->mx->rkStage(h->physics, scheme, stage, dt)); }
     (void)t;
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1480,6 +1563,7 @@ int h3d_rk_stage(h3d_handle h, int scheme, int stage, double t, double dt) {
 }
 
 int h3d_max_residuals(h3d_handle h, double out[5]) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); int nan = 0; return mxDone(h, h->mx->maxResiduals(out, &nan)); }
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
@@ -1495,6 +1579,7 @@ int h3d_max_residuals(h3d_handle h, double out[5]) {
 }
 
 int h3d_has_nan(h3d_handle h, int* flag) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); double r5[5]; return mxDone(h, h->mx->maxResiduals(r5, flag)); }
     double r[5];
     int rc = h3d_max_residuals(h, r);
     if (rc) return rc;
@@ -1503,6 +1588,7 @@ int h3d_has_nan(h3d_handle h, int* flag) {
 }
 
 int h3d_max_timestep(h3d_handle h, double cfl, double dcfl, double* dt_conv, double* dt_visc) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); h->mx->ph = h->ph; return mxDone(h, h->mx->maxTimestep(cfl, dcfl, dt_conv, dt_visc)); }
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
@@ -1518,6 +1604,7 @@ int h3d_max_timestep(h3d_handle h, double cfl, double dcfl, double* dt_conv, dou
 }
 
 int h3d_volume_integral(h3d_handle h, int kind, double* val) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); h->mx->ph = h->ph; return mxDone(h, h->mx->volumeIntegral(h->physics, kind, val)); }
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
     if (kind < 0 || kind > H3D_INT_KINETIC_ENERGY_BALANCE) { h->err = "unknown volume integral"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1563,6 +1650,7 @@ int h3d_volume_integral(h3d_handle h, int kind, double* val) {
 }
 
 int h3d_surface_integral(h3d_handle h, int zone, int kind, double out[3]) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); h->mx->ph = h->ph; return mxDone(h, h->mx->surfaceIntegral(h->physics, zone, kind, out)); }
     if (checkReady(h)) return 1;
     if (kind < H3D_SURF_SURFACE || kind > H3D_SURF_VISCOUS_FORCE) { h->err = "unknown surface integral"; return 1; }
     const bool viscous = kind == H3D_SURF_TOTAL_FORCE || kind == H3D_SURF_VISCOUS_FORCE;
@@ -1591,6 +1679,7 @@ int h3d_surface_integral(h3d_handle h, int zone, int kind, double out[3]) {
 }
 
 int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, const double* lxi, const double* leta, const double* lzeta, double* values) {
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); h->mx->ph = h->ph; return mxDone(h, h->mx->probe(nProbes, elem, variable, lxi, leta, lzeta, values)); }
     if (checkReady(h)) return 1;
     if (nProbes <= 0) return 0;
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1624,6 +1713,7 @@ int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, c
 }
 
 int h3d_statistics_update(h3d_handle h, int reset) {
+    MX_UNSUPPORTED("the statistics monitor");
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
@@ -1641,6 +1731,7 @@ int h3d_statistics_update(h3d_handle h, int reset) {
 }
 
 int h3d_statistics_download(h3d_handle h, double* data, int* nVars, int* nSamples) {
+    MX_UNSUPPORTED("the statistics monitor");
     if (!h->dStats) { h->err = "no statistics have been accumulated"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     *nVars = h->statVars; *nSamples = h->statSamples;
@@ -1664,7 +1755,7 @@ int h3d_synchronize(h3d_handle h) {
     return 0;
 }
 
-long long h3d_kernel_launches(h3d_handle h) { return h->launches; }
+long long h3d_kernel_launches(h3d_handle h) { return h->launches + (h->mx ? h->mx->launches : 0); }
 
 int h3d_kernel_profile(h3d_handle h, double* out, int len) {
     CTX_CHECK(cudaSetDevice(h->device));

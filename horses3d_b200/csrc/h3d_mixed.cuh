@@ -1,0 +1,908 @@
+// p-nonconforming meshes on the device: every element has its own polynomial orders (Nx, Ny, Nz), every face the
+// orders of its two sides and its own, Nf = max per direction.  The element traces are interpolated to the face order, the
+// interface fluxes are computed there and projected back to each element (mortars).
+//
+//   Face_LinkWithElements                  FaceClass.f90:187-282     (orders, projection types: host, MixedSolver::setMesh)
+//   HexElement_ProlongSolutionToFaces      HexElementClass.f90:233-372   MxTrace  (element -> its own face order)
+//   Face_AdaptSolutionToFace / ...Gradients FaceClass.f90:284-512    MxAdapt  (rotation + Tset interpolation to the face order)
+//   HexElement_ComputeLocalGradient        HexElementClass.f90:427-531   MxLocalGrad
+//   BR1_ComputeElementInterfaceAverage / BR1_ComputeBoundaryFlux  EllipticBR1.f90:571-736   MxGradFace
+//   Face_ProjectFluxToElements / Face_ProjectGradientFluxToElements  FaceClass.f90:596-696, 865-961   MxProject
+//   BR1_GradientFaceLoop -> VectorWeakIntegrals_StdFace   EllipticBR1.f90:531-569, DGIntegrals.f90:365-443   MxLift
+//   BaseClass_ComputeInnerFluxes / BR1_ComputeInnerFluxes  HyperbolicDiscretizationClass.f90:83-152, EllipticBR1.f90:740-814   MxFlux
+//   computeElementInterfaceFlux / computeBoundaryFlux     SpatialDiscretization.f90:1710-2028   MxRiemann
+//   ScalarWeakIntegrals_StdVolumeGreen + StdFace, /J, +S, RK update   DGIntegrals.f90:56-87, 214-273   MxVolume
+//
+// Design: the orders are run-time data, so these are plain gather kernels -- one thread per output node (element node, element
+// trace node or face node), every sum in the reference's order, no shared memory and no synchronisation; the uniform-order
+// path (h3d_kernels.cuh) stays the tuned one.  Layout: structure of arrays over the CONCATENATED nodes of all elements / faces
+// (A[c][node]), with offset tables per element, element side and face.  Every kernel body is a functor over the thread index
+// and the orchestration is a template over a backend (allocate / copy / launch): libh3dgpu.so instantiates it with the CUDA
+// backend; tests/emu instantiates the SAME functors and orchestration with a host loop as the launcher, which is how this path
+// is checked against the oracle where no GPU is present (test infrastructure, never shipped).
+// Scope: StandardDG, BR1 (or Euler), any Riemann solver / boundary condition / gradient variables of h3d_physics.cuh, no LES,
+// single domain.  Reductions are computed per element (face) in the reference's node order and finished on the host in element
+// order, so that they reproduce the oracle's sums bit for bit.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "h3d_physics.cuh"
+
+namespace h3d {
+
+constexpr int MX_MAXN = 16;   // polynomial orders 0 .. 15
+
+struct MixedDev {
+    int nElem, nFace;
+    long long nNodes, nFaceNodes, nTrace;
+    // ---- tables
+    const long long* eOff;       // [nElem + 1]      first node of every element
+    const int* eN;               // [nElem][3]       nodes per direction (Nx+1, Ny+1, Nz+1)
+    const int* nodeElem;         // [nNodes]         element of every node
+    const long long* tOff;       // [6 nElem + 1]    first trace node of element side 6 e + lf (at the ELEMENT's face order)
+    const int* traceOwner;       // [nTrace]         6 e + lf
+    const long long* fOff;       // [nFace + 1]      first node of every face (at the FACE order)
+    const int* faceNodeFace;     // [nFaceNodes]     face of every face node
+    const int* fo;               // [nFace][6]       Nf(1:2), NfLeft(1:2), NfRight(1:2)
+    const int* proj;             // [nFace][2]       projectionType of the two sides
+    const int *elemFace, *elemFaceSide;     // [nElem][6]
+    const int *faceElem, *faceElemSide;     // [nFace][2]
+    const int *faceRot, *faceType, *faceZone;
+    // ---- operators: per order N the block D[n n] hatD[n n] v[2 n] b[2 n] w[n] x[n] at ops + opBase[N] (row-major M[i n + l] = M(i,l))
+    const double* ops; int opBase[MX_MAXN];
+    // Tset(Norigin, Ndest) % T at tset + tBase[Norigin][Ndest], [(Ndest+1)][(Norigin+1)]
+    const double* tset; int tBase[MX_MAXN][MX_MAXN];
+    // ---- element fields [c][nNodes]
+    double *Q, *G, *QDot, *Ux, *Uy, *Uz;    // 5 each
+    double* Fc;                             // 15: contravariant flux (d*5 + q)
+    const double* S;                        // 5 or nullptr
+    const double *Ja, *J, *invJ;            // 9 (3 d + c), 1, 1
+    // ---- element-side fields at the element's face order [c][nTrace]
+    double *tr;                             // 15: traces before the adaption to the face order
+    double *fStarE, *unStarE;               // 5 / 15 (d*5 + q)
+    // ---- face fields at the face order [c][nFaceNodes]
+    double *fQ;                             // 10: side*5 + q
+    double *fU;                             // 30: dir*10 + side*5 + q
+    double *fFlux;                          // 15: interface flux (5) or gradient flux (d*5 + q)
+    const double *fN, *fT1, *fT2, *fJ;      // 3, 3, 3, 1
+    const int* bcType; const double* bcParams;
+    // ---- reductions
+    double* partial;                        // [max(nElem, nFace)][8]
+};
+
+struct MxRk { int mode; double a, cdt, b; int copyG; };   // as RkArgs (h3d_kernels.cuh): 0 residual only, 1 low storage, 2 SSP
+
+// ---- index helpers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mxAxis0(int lf) { return (lf == 3 || lf == 5) ? 1 : 0; }            // axisMap(1, lf)
+__device__ __forceinline__ int mxAxis1(int lf) { return (lf == 2 || lf == 4) ? 1 : 2; }            // axisMap(2, lf)
+__device__ __forceinline__ int mxAxisN(int lf) { return (lf < 2) ? 1 : ((lf == 2 || lf == 4) ? 2 : 0); }
+__device__ __forceinline__ int mxEnd(int lf) { return (lf == 1 || lf == 3 || lf == 4) ? 1 : 0; }
+__device__ __forceinline__ const double* mxD(const MixedDev& m, int N) { return m.ops + m.opBase[N]; }
+__device__ __forceinline__ const double* mxHatD(const MixedDev& m, int N) { return m.ops + m.opBase[N] + (N + 1) * (N + 1); }
+__device__ __forceinline__ const double* mxV(const MixedDev& m, int N) { return m.ops + m.opBase[N] + 2 * (N + 1) * (N + 1); }
+__device__ __forceinline__ const double* mxB(const MixedDev& m, int N) { return m.ops + m.opBase[N] + 2 * (N + 1) * (N + 1) + 2 * (N + 1); }
+__device__ __forceinline__ const double* mxW(const MixedDev& m, int N) { return m.ops + m.opBase[N] + 2 * (N + 1) * (N + 1) + 4 * (N + 1); }
+__device__ __forceinline__ const double* mxX(const MixedDev& m, int N) { return m.ops + m.opBase[N] + 2 * (N + 1) * (N + 1) + 5 * (N + 1); }
+__device__ __forceinline__ const double* mxT(const MixedDev& m, int No, int Nd) { return m.tset + m.tBase[No][Nd]; }
+// MeshTypes.f90:70-108 and its inverse
+__device__ __forceinline__ void mxLeft2Right(int i, int j, int Nx, int Ny, int rot, int& ii, int& jj) {
+    switch (rot) {
+        case 0: ii = i; jj = j; break;
+        case 1: ii = Ny - j; jj = i; break;
+        case 2: ii = Nx - i; jj = Ny - j; break;
+        case 3: ii = j; jj = Nx - i; break;
+        case 4: ii = j; jj = i; break;
+        case 5: ii = Nx - i; jj = j; break;
+        case 6: ii = Ny - j; jj = Nx - i; break;
+        default: ii = i; jj = Ny - j; break;
+    }
+}
+__device__ __forceinline__ void mxRight2Left(int ii, int jj, int Nx, int Ny, int rot, int& i, int& j) {
+    switch (rot) {
+        case 0: i = ii; j = jj; break;
+        case 1: i = jj; j = Ny - ii; break;
+        case 2: i = Nx - ii; j = Ny - jj; break;
+        case 3: i = Nx - jj; j = ii; break;
+        case 4: i = jj; j = ii; break;
+        case 5: i = Nx - ii; j = jj; break;
+        case 6: i = Nx - jj; j = Ny - ii; break;
+        default: i = ii; j = Ny - jj; break;
+    }
+}
+struct MxNode { int e, i, j, k, nx, ny, nz; long long base; };
+__device__ __forceinline__ MxNode mxNode(const MixedDev& m, long long g) {
+    MxNode t; t.e = m.nodeElem[g]; t.base = m.eOff[t.e];
+    t.nx = m.eN[3 * t.e]; t.ny = m.eN[3 * t.e + 1]; t.nz = m.eN[3 * t.e + 2];
+    const int l = (int)(g - t.base);
+    t.i = l % t.nx; t.j = (l / t.nx) % t.ny; t.k = l / (t.nx * t.ny);
+    return t;
+}
+
+// ---- HexElement_ProlongSolutionToFaces: trace of 5 fields on every element side, at the element's own face order ----------
+struct MxTrace {
+    MixedDev m; const double* src; double* dst;   // src [5][nNodes], dst [5][nTrace]
+    __device__ void operator()(long long t) const {
+        const int owner = m.traceOwner[t], e = owner / 6, lf = owner % 6;
+        const int nn[3] = {m.eN[3 * e], m.eN[3 * e + 1], m.eN[3 * e + 2]};
+        const int a0 = mxAxis0(lf), a1 = mxAxis1(lf), an = mxAxisN(lf);
+        const int local = (int)(t - m.tOff[owner]);
+        int idx[3]; idx[a0] = local % nn[a0]; idx[a1] = local / nn[a0]; idx[an] = 0;
+        const double* v = mxV(m, nn[an] - 1) + mxEnd(lf) * nn[an];
+        const long long stride = an == 0 ? 1 : (an == 1 ? nn[0] : (long long)nn[0] * nn[1]);
+        const long long g0 = m.eOff[e] + ((long long)idx[2] * nn[1] + idx[1]) * nn[0] + idx[0];
+        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int l = 0; l < nn[an]; ++l) {
+            const double vl = v[l];
+            for (int c = 0; c < 5; ++c) acc[c] = acc[c] + src[(long long)c * m.nNodes + g0 + l * stride] * vl;
+        }
+        for (int c = 0; c < 5; ++c) dst[(long long)c * m.nTrace + t] = acc[c];
+    }
+};
+
+// ---- Face_AdaptSolutionToFace: 5 traces -> side `side` of the face storage at the face order -----------------------------
+struct MxAdapt {
+    MixedDev m; const double* src; double* dst;   // src [5][nTrace]; dst [10][nFaceNodes] (side*5 + c)
+    __device__ void operator()(long long t) const {
+        const int side = (int)(t / m.nFaceNodes); const long long g = t % m.nFaceNodes;
+        const int f = m.faceNodeFace[g];
+        if (side == 1 && m.faceType[f] != H3D_FACE_INTERIOR) return;
+        const int* fo = m.fo + 6 * f;
+        const int Nf1 = fo[0], Ns1 = fo[2 + 2 * side], Ns2 = fo[3 + 2 * side];
+        const int local = (int)(g - m.fOff[f]), i = local % (Nf1 + 1), j = local / (Nf1 + 1);
+        const int rot = side ? m.faceRot[f] : 0;
+        const bool swap = rot == 1 || rot == 3 || rot == 4 || rot == 6;
+        const int ne1 = (swap ? Ns2 : Ns1) + 1;
+        const long long base = m.tOff[6 * m.faceElem[2 * f + side] + m.faceElemSide[2 * f + side]];
+        auto at = [&](int a, int b) { int ii, jj; mxLeft2Right(a, b, Ns1, Ns2, rot, ii, jj); return base + (long long)jj * ne1 + ii; };
+        const int pt = m.proj[2 * f + side];
+        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (pt == 0) {
+            const long long s = at(i, j);
+            for (int c = 0; c < 5; ++c) acc[c] = src[(long long)c * m.nTrace + s];
+        } else if (pt == 1) {
+            const double* T1 = mxT(m, Ns1, Nf1) + i * (Ns1 + 1);
+            for (int l = 0; l <= Ns1; ++l) { const long long s = at(l, j); for (int c = 0; c < 5; ++c) acc[c] = acc[c] + T1[l] * src[(long long)c * m.nTrace + s]; }
+        } else if (pt == 2) {
+            const double* T2 = mxT(m, Ns2, fo[1]) + j * (Ns2 + 1);
+            for (int l = 0; l <= Ns2; ++l) { const long long s = at(i, l); for (int c = 0; c < 5; ++c) acc[c] = acc[c] + T2[l] * src[(long long)c * m.nTrace + s]; }
+        } else {
+            const double* T1 = mxT(m, Ns1, Nf1) + i * (Ns1 + 1); const double* T2 = mxT(m, Ns2, fo[1]) + j * (Ns2 + 1);
+            for (int l = 0; l <= Ns2; ++l) for (int mm = 0; mm <= Ns1; ++mm) {
+                const long long s = at(mm, l); const double tt = T1[mm] * T2[l];
+                for (int c = 0; c < 5; ++c) acc[c] = acc[c] + tt * src[(long long)c * m.nTrace + s];
+            }
+        }
+        for (int c = 0; c < 5; ++c) dst[(long long)(side * 5 + c) * m.nFaceNodes + g] = acc[c];
+    }
+};
+
+// ---- HexElement_ComputeLocalGradient --------------------------------------------------------------------------------------
+struct MxLocalGrad {
+    MixedDev m; Phys ph;
+    __device__ void operator()(long long g) const {
+        const MxNode t = mxNode(m, g);
+        const double* Dx = mxD(m, t.nx - 1) + t.i * t.nx; const double* Dy = mxD(m, t.ny - 1) + t.j * t.ny; const double* Dz = mxD(m, t.nz - 1) + t.k * t.nz;
+        auto load = [&](long long gg, double* U) {
+            double Q[5];
+            for (int q = 0; q < 5; ++q) Q[q] = m.Q[(long long)q * m.nNodes + gg];
+            if (ph.gradVars == H3D_GRADVARS_STATE) { for (int q = 0; q < 5; ++q) U[q] = Q[q]; } else get_gradients(ph, Q, U);
+        };
+        double a[5] = {0, 0, 0, 0, 0}, b[5] = {0, 0, 0, 0, 0}, c[5] = {0, 0, 0, 0, 0}, U[5];
+        for (int l = 0; l < t.nx; ++l) { load(t.base + ((long long)t.k * t.ny + t.j) * t.nx + l, U); for (int q = 0; q < 5; ++q) a[q] = a[q] + U[q] * Dx[l]; }
+        for (int l = 0; l < t.ny; ++l) { load(t.base + ((long long)t.k * t.ny + l) * t.nx + t.i, U); for (int q = 0; q < 5; ++q) b[q] = b[q] + U[q] * Dy[l]; }
+        for (int l = 0; l < t.nz; ++l) { load(t.base + ((long long)l * t.ny + t.j) * t.nx + t.i, U); for (int q = 0; q < 5; ++q) c[q] = c[q] + U[q] * Dz[l]; }
+        double ja[9];
+        for (int q = 0; q < 9; ++q) ja[q] = m.Ja[(long long)q * m.nNodes + g];
+        const double iJ = m.invJ[g];
+        for (int q = 0; q < 5; ++q) {
+            m.Ux[(long long)q * m.nNodes + g] = (a[q] * ja[0] + b[q] * ja[3] + c[q] * ja[6]) * iJ;
+            m.Uy[(long long)q * m.nNodes + g] = (a[q] * ja[1] + b[q] * ja[4] + c[q] * ja[7]) * iJ;
+            m.Uz[(long long)q * m.nNodes + g] = (a[q] * ja[2] + b[q] * ja[5] + c[q] * ja[8]) * iJ;
+        }
+    }
+};
+
+// ---- BR1 interface average / boundary flux at the face order: fFlux[d*5 + q] = u* n_d J_f --------------------------------
+struct MxGradFace {
+    MixedDev m; Phys ph;
+    __device__ void operator()(long long g) const {
+        const int f = m.faceNodeFace[g];
+        double QL[5], nh[3], UL[5], UR[5];
+        for (int q = 0; q < 5; ++q) QL[q] = m.fQ[(long long)q * m.nFaceNodes + g];
+        for (int d = 0; d < 3; ++d) nh[d] = m.fN[(long long)d * m.nFaceNodes + g];
+        const double Jf = m.fJ[g];
+        get_gradients(ph, QL, UL);
+        if (m.faceType[f] == H3D_FACE_INTERIOR) {
+            double QR[5];
+            for (int q = 0; q < 5; ++q) QR[q] = m.fQ[(long long)(5 + q) * m.nFaceNodes + g];
+            get_gradients(ph, QR, UR);
+            for (int q = 0; q < 5; ++q) {
+                const double uStar = 0.5 * (UR[q] - UL[q]) * Jf;
+                for (int d = 0; d < 3; ++d) m.fFlux[(long long)(d * 5 + q) * m.nFaceNodes + g] = uStar * nh[d];
+            }
+        } else {
+            const int zone = m.faceZone[f];
+            for (int q = 0; q < 5; ++q) UR[q] = UL[q];
+            bc_grad_vars<true>(ph, m.bcType[zone], m.bcParams + 16 * zone, nh, QL, UR);
+            for (int q = 0; q < 5; ++q) for (int d = 0; d < 3; ++d) m.fFlux[(long long)(d * 5 + q) * m.nFaceNodes + g] = (UR[q] - UL[q]) * nh[d] * Jf;
+        }
+    }
+};
+
+// ---- Face_ProjectFluxToElements / ...GradientFluxToElements: nv face fields -> the element side's storage at ITS order -----
+struct MxProject {
+    MixedDev m; int nv; const double* src; double* dst; double factor;   // src [nv][nFaceNodes], dst [nv][nTrace]; right side *= factor
+    __device__ void operator()(long long t) const {
+        const int owner = m.traceOwner[t], e = owner / 6, lf = owner % 6;
+        const int f = m.elemFace[6 * e + lf], side = m.elemFaceSide[6 * e + lf];
+        const int* fo = m.fo + 6 * f;
+        const int Nf1 = fo[0], Nf2 = fo[1], Ns1 = fo[2 + 2 * side], Ns2 = fo[3 + 2 * side];
+        const int local = (int)(t - m.tOff[owner]);
+        int i, j;
+        if (side == 0) { i = local % (Ns1 + 1); j = local / (Ns1 + 1); }
+        else {
+            const int rot = m.faceRot[f];
+            const bool swap = rot == 1 || rot == 3 || rot == 4 || rot == 6;
+            const int ne1 = (swap ? Ns2 : Ns1) + 1;
+            mxRight2Left(local % ne1, local / ne1, Ns1, Ns2, rot, i, j);
+        }
+        const int pt = m.proj[2 * f + side];
+        const long long fb = m.fOff[f];
+        const double* T1 = (pt & 1) ? mxT(m, Nf1, Ns1) + i * (Nf1 + 1) : nullptr;
+        const double* T2 = (pt & 2) ? mxT(m, Nf2, Ns2) + j * (Nf2 + 1) : nullptr;
+        for (int c = 0; c < nv; ++c) {
+            const double* F = src + (long long)c * m.nFaceNodes + fb;
+            double acc = 0.0;
+            if (pt == 0) acc = F[j * (Nf1 + 1) + i];
+            else if (pt == 1) { for (int l = 0; l <= Nf1; ++l) acc = acc + T1[l] * F[j * (Nf1 + 1) + l]; }
+            else if (pt == 2) { for (int l = 0; l <= Nf2; ++l) acc = acc + T2[l] * F[l * (Nf1 + 1) + i]; }
+            else { for (int l = 0; l <= Nf2; ++l) for (int mm = 0; mm <= Nf1; ++mm) acc = acc + T1[mm] * T2[l] * F[l * (Nf1 + 1) + mm]; }
+            dst[(long long)c * m.nTrace + t] = side ? factor * acc : acc;
+        }
+    }
+};
+
+// the six element sides of a node in the order of the reference's face integrals: LEFT, RIGHT, FRONT, BACK, BOTTOM, TOP
+struct MxSides { long long s[6]; double b[6]; };
+__device__ __forceinline__ MxSides mxSides(const MixedDev& m, const MxNode& t) {
+    MxSides r;
+    const long long* to = m.tOff + 6 * (long long)t.e;
+    const double* bx = mxB(m, t.nx - 1); const double* by = mxB(m, t.ny - 1); const double* bz = mxB(m, t.nz - 1);
+    r.s[0] = to[5] + t.k * t.ny + t.j; r.b[0] = bx[t.i];            // ELEFT
+    r.s[1] = to[3] + t.k * t.ny + t.j; r.b[1] = bx[t.nx + t.i];     // ERIGHT
+    r.s[2] = to[0] + t.k * t.nx + t.i; r.b[2] = by[t.j];            // EFRONT
+    r.s[3] = to[1] + t.k * t.nx + t.i; r.b[3] = by[t.ny + t.j];     // EBACK
+    r.s[4] = to[2] + t.j * t.nx + t.i; r.b[4] = bz[t.k];            // EBOTTOM
+    r.s[5] = to[4] + t.j * t.nx + t.i; r.b[5] = bz[t.nz + t.k];     // ETOP
+    return r;
+}
+
+// ---- BR1_GradientFaceLoop: U_d += (sum over the six sides of unStar_d b) / J ----------------------------------------------
+struct MxLift {
+    MixedDev m;
+    __device__ void operator()(long long g) const {
+        const MxNode t = mxNode(m, g);
+        const MxSides sd = mxSides(m, t);
+        const double iJ = m.invJ[g];
+        for (int d = 0; d < 3; ++d) {
+            double* Ud = d == 0 ? m.Ux : (d == 1 ? m.Uy : m.Uz);
+            for (int q = 0; q < 5; ++q) {
+                const double* H = m.unStarE + (long long)(d * 5 + q) * m.nTrace;
+                double fi = H[sd.s[0]] * sd.b[0];
+                for (int s = 1; s < 6; ++s) fi = fi + H[sd.s[s]] * sd.b[s];
+                Ud[(long long)q * m.nNodes + g] = Ud[(long long)q * m.nNodes + g] + fi * iJ;
+            }
+        }
+    }
+};
+
+// ---- contravariant fluxes at the nodes: Fc[d*5 + q] = inviscid - viscous ---------------------------------------------------
+struct MxFlux {
+    MixedDev m; Phys ph;
+    __device__ void operator()(long long g) const {
+        double Q[5], ja[9], F[5][3], Fi[15], Fv[15];
+        for (int q = 0; q < 5; ++q) Q[q] = m.Q[(long long)q * m.nNodes + g];
+        for (int q = 0; q < 9; ++q) ja[q] = m.Ja[(long long)q * m.nNodes + g];
+        euler_flux(ph, Q, F);
+        for (int d = 0; d < 3; ++d) for (int q = 0; q < 5; ++q) Fi[d * 5 + q] = F[q][0] * ja[3 * d] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
+        for (int q = 0; q < 15; ++q) Fv[q] = 0.0;
+        if (ph.ns) {
+            double gx[5], gy[5], gz[5], mu, kappa;
+            for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[(long long)q * m.nNodes + g]; gy[q] = m.Uy[(long long)q * m.nNodes + g]; gz[q] = m.Uz[(long long)q * m.nNodes + g]; }
+            laminar_mu_kappa(ph, Q, mu, kappa);
+            viscous_flux<true>(ph, Q, gx, gy, gz, mu, 0.0, kappa, F);
+            for (int d = 0; d < 3; ++d) for (int q = 0; q < 5; ++q) Fv[d * 5 + q] = F[q][0] * ja[3 * d] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
+        }
+        for (int q = 0; q < 15; ++q) m.Fc[(long long)q * m.nNodes + g] = Fi[q] - Fv[q];
+    }
+};
+
+// ---- interface and boundary fluxes at the face order: fFlux[q] = (F*_inv - F*_visc) J_f ------------------------------------
+struct MxRiemann {
+    MixedDev m; Phys ph;
+    __device__ void operator()(long long g) const {
+        const int f = m.faceNodeFace[g];
+        const long long fs = m.nFaceNodes;
+        double nh[3], t1[3], t2[3], QL[5], QR[5], visc[5] = {0, 0, 0, 0, 0}, inv[5];
+        for (int d = 0; d < 3; ++d) { nh[d] = m.fN[d * fs + g]; t1[d] = m.fT1[d * fs + g]; t2[d] = m.fT2[d * fs + g]; }
+        const double Jf = m.fJ[g];
+        for (int q = 0; q < 5; ++q) QL[q] = m.fQ[q * fs + g];
+        double gx[5], gy[5], gz[5], mu, kappa;
+        if (m.faceType[f] == H3D_FACE_INTERIOR) {
+            for (int q = 0; q < 5; ++q) QR[q] = m.fQ[(5 + q) * fs + g];
+            if (ph.ns) {   // BR1_RiemannSolver (EllipticBR1.f90:816-868)
+                double FL[5][3], FR[5][3];
+                for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(0 * 10 + q) * fs + g]; gy[q] = m.fU[(1 * 10 + q) * fs + g]; gz[q] = m.fU[(2 * 10 + q) * fs + g]; }
+                laminar_mu_kappa(ph, QL, mu, kappa);
+                viscous_flux<true>(ph, QL, gx, gy, gz, mu, 0.0, kappa, FL);
+                for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(0 * 10 + 5 + q) * fs + g]; gy[q] = m.fU[(1 * 10 + 5 + q) * fs + g]; gz[q] = m.fU[(2 * 10 + 5 + q) * fs + g]; }
+                laminar_mu_kappa(ph, QR, mu, kappa);
+                viscous_flux<true>(ph, QR, gx, gy, gz, mu, 0.0, kappa, FR);
+                for (int q = 0; q < 5; ++q) {
+                    const double fx = 0.5 * (FL[q][0] + FR[q][0]), fy = 0.5 * (FL[q][1] + FR[q][1]), fz = 0.5 * (FL[q][2] + FR[q][2]);
+                    visc[q] = fx * nh[0] + fy * nh[1] + fz * nh[2];
+                }
+            }
+        } else {
+            const int zone = m.faceZone[f]; const int btype = m.bcType[zone]; const double* P = m.bcParams + 16 * zone;
+            for (int q = 0; q < 5; ++q) QR[q] = QL[q];
+            bc_flow_state(ph, btype, P, nh, QR);
+            if (ph.ns) {
+                double F[5][3];
+                for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(0 * 10 + q) * fs + g]; gy[q] = m.fU[(1 * 10 + q) * fs + g]; gz[q] = m.fU[(2 * 10 + q) * fs + g]; }
+                laminar_mu_kappa(ph, QL, mu, kappa);
+                viscous_flux<true>(ph, QL, gx, gy, gz, mu, 0.0, kappa, F);
+                for (int q = 0; q < 5; ++q) visc[q] = F[q][0] * nh[0] + F[q][1] * nh[1] + F[q][2] * nh[2];
+                bc_neumann(btype, P, QL, visc);
+            }
+        }
+        riemann_solver<true>(ph, QL, QR, nh, t1, t2, inv);
+        for (int q = 0; q < 5; ++q) m.fFlux[q * fs + g] = (inv[q] - visc[q]) * Jf;
+    }
+};
+
+// ---- weak volume integral + surface integral, /J, +S, Runge-Kutta update ---------------------------------------------------
+struct MxVolume {
+    MixedDev m; MxRk rk;
+    __device__ void operator()(long long g) const {
+        const MxNode t = mxNode(m, g);
+        const MxSides sd = mxSides(m, t);
+        const double* hx = mxHatD(m, t.nx - 1) + t.i * t.nx; const double* hy = mxHatD(m, t.ny - 1) + t.j * t.ny; const double* hz = mxHatD(m, t.nz - 1) + t.k * t.nz;
+        const double Jn = m.J[g];
+        for (int q = 0; q < 5; ++q) {
+            const double* Fx = m.Fc + (long long)(0 * 5 + q) * m.nNodes + t.base; const double* Fy = m.Fc + (long long)(1 * 5 + q) * m.nNodes + t.base;
+            const double* Fz = m.Fc + (long long)(2 * 5 + q) * m.nNodes + t.base;
+            double vol = 0.0;
+            for (int l = 0; l < t.nx; ++l) vol = vol + hx[l] * Fx[((long long)t.k * t.ny + t.j) * t.nx + l];
+            for (int l = 0; l < t.ny; ++l) vol = vol + hy[l] * Fy[((long long)t.k * t.ny + l) * t.nx + t.i];
+            for (int l = 0; l < t.nz; ++l) vol = vol + hz[l] * Fz[((long long)l * t.ny + t.j) * t.nx + t.i];
+            const double* Fs = m.fStarE + (long long)q * m.nTrace;
+            double fi = Fs[sd.s[0]] * sd.b[0];
+            for (int s = 1; s < 6; ++s) fi = fi + Fs[sd.s[s]] * sd.b[s];
+            double res = vol - fi;
+            res = res / Jn;
+            if (m.S) res = res + m.S[(long long)q * m.nNodes + g];
+            const long long o = (long long)q * m.nNodes + g;
+            m.QDot[o] = res;
+            if (rk.mode == 1) {
+                const double gg = rk.a * m.G[o] + res;
+                m.G[o] = gg;
+                m.Q[o] = m.Q[o] + rk.cdt * gg;
+            } else if (rk.mode == 2) {   // TakeSSPRK33Step / TakeSSPRK43Step
+                const double Qk = m.Q[o];
+                const double g0 = rk.copyG ? Qk : m.G[o];
+                if (rk.copyG) m.G[o] = g0;
+                m.Q[o] = rk.a * g0 + rk.b * Qk + rk.cdt * res;
+            }
+        }
+    }
+};
+
+// ---- reductions: one thread per element (face), nodes in the reference's order; partial[e][8] --------------------------------
+struct MxRedResidual {   // ComputeMaxResiduals (DGSEMClass.f90:770-856) + checkForNan on Q
+    MixedDev m;
+    __device__ void operator()(long long e) const {
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        for (long long g = m.eOff[e]; g < m.eOff[e + 1]; ++g) for (int q = 0; q < 5; ++q) {
+            v[q] = fmax(v[q], fabs(m.QDot[(long long)q * m.nNodes + g]));
+            if (isnan(m.Q[(long long)q * m.nNodes + g])) v[5] = 1.0;
+        }
+        for (int q = 0; q < 6; ++q) m.partial[8 * e + q] = v[q];
+    }
+};
+struct MxRedTimestep {   // MaxTimeStep (DGSEMClass.f90:870-1034): the spacings of the element's own nodal storages
+    MixedDev m; Phys ph; double cfl, dcfl;
+    __device__ void operator()(long long e) const {
+        double dxi[3];
+        for (int d = 0; d < 3; ++d) { const int N = m.eN[3 * e + d] - 1; const double* x = mxX(m, N); dxi[d] = N != 0 ? 1.0 / fabs(x[1] - x[0]) : 0.0; }
+        double vc = 1.7976931348623157e308, vv = 1.7976931348623157e308;
+        for (long long g = m.eOff[e]; g < m.eOff[e + 1]; ++g) {
+            double Q[5], ja[9];
+            for (int q = 0; q < 5; ++q) Q[q] = m.Q[(long long)q * m.nNodes + g];
+            for (int c = 0; c < 9; ++c) ja[c] = m.Ja[(long long)c * m.nNodes + g];
+            const double u = fabs(Q[1] / Q[0]), v = fabs(Q[2] / Q[0]), w = fabs(Q[3] / Q[0]);
+            const double p = pressure(ph, Q);
+            const double a = sqrt(ph.gamma * p / Q[0]);
+            const double e0 = u + a, e1 = v + a, e2 = w + a;
+            const double jac = m.J[g];
+            const double l1 = fabs(ja[0] * e0 + ja[1] * e1 + ja[2] * e2) * dxi[0];
+            const double l2 = fabs(ja[3] * e0 + ja[4] * e1 + ja[5] * e2) * dxi[1];
+            const double l3 = fabs(ja[6] * e0 + ja[7] * e1 + ja[8] * e2) * dxi[2];
+            vc = fmin(vc, cfl * fabs(jac) / (l1 + l2 + l3));
+            if (ph.ns) {
+                const double T = ph.gammaM2 * p / Q[0];
+                const double mu = sutherland(ph, T);
+                const double v1 = mu * (dxi[0] * dxi[0]) * fabs(ja[0] + ja[1] + ja[2]);
+                const double v2 = mu * (dxi[1] * dxi[1]) * fabs(ja[3] + ja[4] + ja[5]);
+                const double v3 = mu * (dxi[2] * dxi[2]) * fabs(ja[6] + ja[7] + ja[8]);
+                vv = fmin(vv, dcfl * fabs(jac) / (v1 + v2 + v3));
+            }
+        }
+        m.partial[8 * e] = vc; m.partial[8 * e + 1] = vv;
+    }
+};
+struct MxRedIntegral {   // ScalarVolumeIntegral (VolumeIntegrals.f90:76-120, 167-286), the kinds that need Q, QDot and gradients only
+    MixedDev m; Phys ph; int kind;
+    __device__ void operator()(long long e) const {
+        const int nx = m.eN[3 * e], ny = m.eN[3 * e + 1], nz = m.eN[3 * e + 2];
+        const double* wx = mxW(m, nx - 1); const double* wy = mxW(m, ny - 1); const double* wz = mxW(m, nz - 1);
+        double loc = 0.0;
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            const long long g = m.eOff[e] + ((long long)k * ny + j) * nx + i;
+            double Q[5], QD[5];
+            for (int q = 0; q < 5; ++q) { Q[q] = m.Q[(long long)q * m.nNodes + g]; QD[q] = m.QDot[(long long)q * m.nNodes + g]; }
+            const double wJ = wx[i] * wy[j] * wz[k] * m.J[g];
+            switch (kind) {
+                case H3D_INT_VOLUME: loc = loc + wJ; break;
+                case H3D_INT_KINETIC_ENERGY: {
+                    double KinEn = pow2(Q[1]); KinEn = KinEn + pow2(Q[2]); KinEn = KinEn + pow2(Q[3]);
+                    KinEn = 0.5 * KinEn / Q[0];
+                    loc = loc + wJ * KinEn;
+                } break;
+                case H3D_INT_KINETIC_ENERGY_RATE: {
+                    double uvw = Q[1] / Q[0];
+                    double KinEn = uvw * QD[1] - 0.5 * pow2(uvw) * QD[0];
+                    uvw = Q[2] / Q[0]; KinEn = KinEn + uvw * QD[2] - 0.5 * pow2(uvw) * QD[0];
+                    uvw = Q[3] / Q[0]; KinEn = KinEn + uvw * QD[3] - 0.5 * pow2(uvw) * QD[0];
+                    loc = loc + wJ * KinEn;
+                } break;
+                case H3D_INT_ENSTROPHY: {
+                    double gx[5], gy[5], gz[5], U_x[3], U_y[3], U_z[3];
+                    for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[(long long)q * m.nNodes + g]; gy[q] = m.Uy[(long long)q * m.nNodes + g]; gz[q] = m.Uz[(long long)q * m.nNodes + g]; }
+                    velocity_gradients_gv<true>(ph, Q, gx, gy, gz, U_x, U_y, U_z);
+                    const double KinEn = pow2(U_y[2] - U_z[1]) + pow2(U_z[0] - U_x[2]) + pow2(U_x[1] - U_y[0]);
+                    loc = loc + wJ * KinEn;
+                } break;
+                case H3D_INT_VELOCITY: loc = loc + wx[i] * wy[j] * wz[k] * sqrt(pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) / Q[0] * m.J[g]; break;
+                case H3D_INT_INTERNAL_ENERGY: loc = loc + wJ * Q[4]; break;
+                default: break;
+            }
+        }
+        m.partial[8 * e] = loc;
+    }
+};
+struct MxRedSurface {   // ScalarSurfaceIntegral / VectorSurfaceIntegral (SurfaceIntegrals.f90:40-445) on the faces of one zone
+    MixedDev m; Phys ph; int zone, kind;
+    __device__ void operator()(long long f) const {
+        double fv[3] = {0, 0, 0};
+        if (m.faceType[f] == H3D_FACE_BOUNDARY && m.faceZone[f] == zone) {
+            const int n1 = m.fo[6 * f] + 1, n2 = m.fo[6 * f + 1] + 1;
+            const double* w1 = mxW(m, n1 - 1); const double* w2 = mxW(m, n2 - 1);
+            const long long fs = m.nFaceNodes;
+            for (int j = 0; j < n2; ++j) for (int i = 0; i < n1; ++i) {
+                const long long g = m.fOff[f] + (long long)j * n1 + i;
+                double Q[5], nh[3];
+                for (int q = 0; q < 5; ++q) Q[q] = m.fQ[q * fs + g];
+                for (int d = 0; d < 3; ++d) nh[d] = m.fN[d * fs + g];
+                const double Jf = m.fJ[g];
+                switch (kind) {
+                    case H3D_SURF_SURFACE: fv[0] = fv[0] + w1[i] * w2[j] * Jf; break;
+                    case H3D_SURF_MASS_FLOW: fv[0] = fv[0] + (Q[1] * nh[0] + Q[2] * nh[1] + Q[3] * nh[2]) * w1[i] * w2[j] * Jf; break;
+                    case H3D_SURF_FLOW_RATE: fv[0] = fv[0] + (1.0 / Q[0]) * (Q[1] * nh[0] + Q[2] * nh[1] + Q[3] * nh[2]) * w1[i] * w2[j] * Jf; break;
+                    case H3D_SURF_PRESSURE: { const double pr = pressure(ph, Q); fv[0] = fv[0] + pr * w1[i] * w2[j] * Jf; } break;
+                    case H3D_SURF_VEC_SURFACE: for (int d = 0; d < 3; ++d) fv[d] = fv[d] + w1[i] * w2[j] * Jf * nh[d]; break;
+                    case H3D_SURF_PRESSURE_FORCE: { const double pr = pressure(ph, Q); for (int d = 0; d < 3; ++d) fv[d] = fv[d] + (pr * nh[d]) * Jf * w1[i] * w2[j]; } break;
+                    default: {   // total / viscous force: getStressTensor (Physics_NS.f90:822-886)
+                        double gx[5], gy[5], gz[5], U_x[3], U_y[3], U_z[3], tau[3][3], mu, kappa;
+                        for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(0 * 10 + q) * fs + g]; gy[q] = m.fU[(1 * 10 + q) * fs + g]; gz[q] = m.fU[(2 * 10 + q) * fs + g]; }
+                        stress_velocity_gradients(ph, Q, gx, gy, gz, U_x, U_y, U_z);
+                        laminar_mu_kappa(ph, Q, mu, kappa);
+                        const double divV = U_x[0] + U_y[1] + U_z[2];
+                        tau[0][0] = mu * (2.0 * U_x[0] - 2.0 / 3.0 * divV);
+                        tau[1][0] = mu * (U_x[1] + U_y[0]);
+                        tau[2][0] = mu * (U_x[2] + U_z[0]);
+                        tau[0][1] = tau[1][0];
+                        tau[1][1] = mu * (2.0 * U_y[1] - 2.0 / 3.0 * divV);
+                        tau[2][1] = mu * (U_y[2] + U_z[1]);
+                        tau[0][2] = tau[2][0];
+                        tau[1][2] = tau[2][1];
+                        tau[2][2] = mu * (2.0 * U_z[2] - 2.0 / 3.0 * divV);
+                        const double pr = pressure(ph, Q);
+                        for (int d = 0; d < 3; ++d) {
+                            const double tn = tau[d][0] * nh[0] + tau[d][1] * nh[1] + tau[d][2] * nh[2];
+                            if (kind == H3D_SURF_TOTAL_FORCE) fv[d] = fv[d] + (pr * nh[d] - tn) * Jf * w1[i] * w2[j];
+                            else fv[d] = fv[d] - tn * Jf * w1[i] * w2[j];
+                        }
+                    }
+                }
+            }
+        }
+        for (int d = 0; d < 3; ++d) m.partial[8 * f + d] = fv[d];
+    }
+};
+struct MxProbe {   // Probe_Update (Probe.f90:330-420); Lagrange vectors padded to ld values per direction
+    MixedDev m; Phys ph; const int* elem; const int* variable; const double* L; int nProbes, ld; double* values;
+    __device__ void operator()(long long pr) const {
+        const int e = elem[pr], nx = m.eN[3 * e], ny = m.eN[3 * e + 1], nz = m.eN[3 * e + 2];
+        const double* lx = L + (long long)pr * ld; const double* ly = L + (long long)(nProbes + pr) * ld; const double* lz = L + (long long)(2 * nProbes + pr) * ld;
+        double value = 0.0;
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            const long long g = m.eOff[e] + ((long long)k * ny + j) * nx + i;
+            double Q[5], var;
+            for (int q = 0; q < 5; ++q) Q[q] = m.Q[(long long)q * m.nNodes + g];
+            switch (variable[pr]) {
+                case H3D_PROBE_PRESSURE: var = pressure(ph, Q); break;
+                case H3D_PROBE_VELOCITY: var = sqrt(pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) / Q[0]; break;
+                case H3D_PROBE_U: var = Q[1] / Q[0]; break;
+                case H3D_PROBE_V: var = Q[2] / Q[0]; break;
+                case H3D_PROBE_W: var = Q[3] / Q[0]; break;
+                case H3D_PROBE_MACH: {
+                    var = pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3]) / pow2(Q[0]);
+                    var = sqrt(var / (ph.gamma * (ph.gamma - 1.0) * (Q[4] / Q[0] - 0.5 * var)));
+                } break;
+                default: var = 0.5 * (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) / Q[0]; break;   // H3D_PROBE_K
+            }
+            value = value + var * lx[i] * ly[j] * lz[k];
+        }
+        values[pr] = value;
+    }
+};
+
+// ============================================================================================================================
+//  Orchestration, shared by the CUDA backend (libh3dgpu.so) and the host-loop backend of tests/emu.
+//  Backend B:  template <class T> T* alloc(size_t);  void upload(T* dst, const T* src, size_t);  void download(T* dst, const T* src, size_t)
+//              (both synchronous);  template <class F> void launch(const F&, long long count);  const char* error()  (nullptr = ok)
+// ============================================================================================================================
+struct MxBasis { int N = -1; std::vector<double> x, w, D, hatD, v, b; };
+
+inline bool mxRkCoefficients(int scheme, int k, MxRk& rk, double dt) {
+    static const double A3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, C3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
+    static const double A5[5] = {0.0, -0.4178904745, -1.192151694643, -1.697784692471, -1.514183444257};
+    static const double C5[5] = {0.1496590219993, 0.3792103129999, 0.8229550293869, 0.6994504559488, 0.1530572479681};
+    static const double A14[14] = {0.0000000000000000, -0.7188012108672410, -0.7785331173421570, -0.0053282796654044, -0.8552979934029281, -3.9564138245774565, -1.5780575380587385,
+                                   -2.0837094552574054, -0.7483334182761610, -0.7032861106563359, +0.0013917096117681, -0.0932075369637460, -0.9514200470875948, -7.1151571693922548};
+    static const double C14[14] = {0.0367762454319673, 0.3136296607553959, 0.1531848691869027, 0.0030097086818182, 0.3326293790646110, 0.2440251405350864, 0.3718879239592277,
+                                   0.6204126221582444, 0.1524043173028741, 0.0760894927419266, 0.0077604214040978, 0.0024647284755382, 0.0780348340049386, 5.5059777270269628};
+    static const double S33A[3] = {1.0, 3.0 / 4.0, 1.0 / 3.0}, S33B[3] = {0.0, 1.0 / 4.0, 2.0 / 3.0}, S33C[3] = {1.0, 1.0 / 4.0, 2.0 / 3.0};
+    static const double S43A[4] = {1.0, 0.0, 2.0 / 3.0, 0.0}, S43B[4] = {0.0, 1.0, 1.0 / 3.0, 1.0}, S43C[4] = {0.5, 0.5, 1.0 / 6.0, 0.5};
+    switch (scheme) {
+        case H3D_EULER: if (k >= 1) return false; rk = MxRk{1, 0.0, dt, 0.0, 0}; return true;
+        case H3D_RK3: if (k >= 3) return false; rk = MxRk{1, A3[k], C3[k] * dt, 0.0, 0}; return true;
+        case H3D_RK5: if (k >= 5) return false; rk = MxRk{1, A5[k], C5[k] * dt, 0.0, 0}; return true;
+        case H3D_LSERK14_4: if (k >= 14) return false; rk = MxRk{1, A14[k], C14[k] * dt, 0.0, 0}; return true;
+        case H3D_SSPRK33: if (k >= 3) return false; rk = MxRk{2, S33A[k], S33C[k] * dt, S33B[k], k == 0 ? 1 : 0}; return true;
+        case H3D_SSPRK43: if (k >= 4) return false; rk = MxRk{2, S43A[k], S43C[k] * dt, S43B[k], k == 0 ? 1 : 0}; return true;
+        default: return false;
+    }
+}
+inline int mxRkStages(int scheme) {
+    switch (scheme) { case H3D_EULER: return 1; case H3D_RK3: return 3; case H3D_RK5: return 5; case H3D_LSERK14_4: return 14; case H3D_SSPRK33: return 3; case H3D_SSPRK43: return 4; default: return 0; }
+}
+
+template <class B>
+struct MixedSolver {
+    B be;
+    MixedDev m{};
+    Phys ph{};
+    std::string err;
+    std::map<int, MxBasis> sp;                                   // NodalStorage(N)
+    std::map<std::pair<int, int>, std::vector<double>> T;        // Tset(Norigin, Ndest)
+    bool haveMesh = false, haveBC = false;
+    int nBoundaryFaces = 0, maxZone = -1, nZones = 0, maxNodes1D = 0;
+    long long launches = 0;
+    std::vector<long long> hEOff;
+    std::vector<double> hPartial, hBuf;
+    double* dSource = nullptr;
+    int* dProbeI = nullptr; double* dProbeD = nullptr; size_t probeCap = 0;
+
+    explicit MixedSolver(const B& b) : be(b) {}
+
+    int fail(const std::string& s) { err = s; return 1; }
+    int check() { const char* e = be.error(); if (e) { err = e; return 2; } return 0; }
+    template <class F> void launch(const F& f, long long n) { if (n > 0) { be.launch(f, n); ++launches; } }
+
+    void setBasis(int N, const double* x, const double* w, const double* D, const double* hatD, const double* v, const double* b) {
+        MxBasis& s = sp[N]; const int n = N + 1;
+        s.N = N; s.x.assign(x, x + n); s.w.assign(w, w + n); s.D.assign(D, D + n * n); s.hatD.assign(hatD, hatD + n * n); s.v.assign(v, v + 2 * n); s.b.assign(b, b + 2 * n);
+    }
+    int setInterpolation(int No, int Nd, const double* Tm) {
+        if (No < 0 || Nd < 0 || No >= MX_MAXN || Nd >= MX_MAXN) return fail("h3d_set_interpolation: polynomial order out of range");
+        T[{No, Nd}].assign(Tm, Tm + (size_t)(No + 1) * (Nd + 1));
+        return 0;
+    }
+    template <class U> int up(const std::vector<U>& src, const U** dst) {
+        U* d = be.template alloc<U>(std::max<size_t>(src.size(), 1));
+        if (!d) return check() ? 2 : fail("device allocation failed");
+        if (!src.empty()) be.upload(d, src.data(), src.size());
+        *dst = d;
+        return check();
+    }
+    int field(double** dst, size_t count) {
+        double* d = be.template alloc<double>(std::max<size_t>(count, 1));
+        if (!d) return check() ? 2 : fail("device allocation failed");
+        std::vector<double> z(count, 0.0);
+        if (count) be.upload(d, z.data(), count);
+        *dst = d;
+        return check();
+    }
+    // [node][C] (the reference's packed order) -> [c][node]
+    static void toSoA(const double* src, size_t nn, int C, std::vector<double>& out) {
+        out.resize(nn * C);
+        for (size_t g = 0; g < nn; ++g) for (int c = 0; c < C; ++c) out[(size_t)c * nn + g] = src[g * C + c];
+    }
+
+    int setMesh(const H3dPhysics& physics, int nElem, int nFace, const int* elemOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+                const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone, const double* jGradXi, const double* jGradEta,
+                const double* jGradZeta, const double* jacobian, const double* faceNormal, const double* faceT1, const double* faceT2, const double* faceJacobian) {
+        if (physics.inviscid != H3D_STANDARD_DG) return fail("p-nonconforming meshes: the split-form discretization is not available (StandardDG only)");
+        if (physics.les != H3D_LES_NONE) return fail("p-nonconforming meshes: LES models are not available");
+        if (physics.flowIsNavierStokes && physics.viscous != H3D_VISCOUS_BR1) return fail("p-nonconforming meshes: BR1 is the only viscous discretization available");
+        if (nElem < 1 || nFace < 1) return fail("h3d_set_mesh_p: empty mesh");
+        m.nElem = nElem; m.nFace = nFace;
+        std::vector<int> eN(3 * (size_t)nElem), nodeElem, traceOwner, faceNodeFace, fo(6 * (size_t)nFace), proj(2 * (size_t)nFace);
+        std::vector<long long> eOff(nElem + 1, 0), tOff(6 * (size_t)nElem + 1, 0), fOff(nFace + 1, 0);
+        for (int e = 0; e < nElem; ++e) {
+            for (int d = 0; d < 3; ++d) {
+                const int N = elemOrder[3 * e + d];
+                if (N < 1 || N >= MX_MAXN) return fail("h3d_set_mesh_p: polynomial orders must lie in 1..15");
+                if (!sp.count(N)) return fail("h3d_set_mesh_p: h3d_set_basis has not been called for every polynomial order of the mesh");
+                eN[3 * e + d] = N + 1; maxNodes1D = std::max(maxNodes1D, N + 1);
+            }
+            eOff[e + 1] = eOff[e] + (long long)eN[3 * e] * eN[3 * e + 1] * eN[3 * e + 2];
+            static const int ax[6][2] = {{0, 2}, {0, 2}, {0, 1}, {1, 2}, {0, 1}, {1, 2}};
+            for (int lf = 0; lf < 6; ++lf) tOff[6 * e + lf + 1] = tOff[6 * e + lf] + (long long)eN[3 * e + ax[lf][0]] * eN[3 * e + ax[lf][1]];
+        }
+        nBoundaryFaces = 0; maxZone = -1;
+        for (int f = 0; f < nFace; ++f) {   // Face_LinkWithElements (FaceClass.f90:187-282)
+            if (faceType[f] == H3D_FACE_MPI) return fail("p-nonconforming meshes are single-domain: MPI faces are not supported");
+            if (faceType[f] != H3D_FACE_INTERIOR && faceType[f] != H3D_FACE_BOUNDARY) return fail("h3d_set_mesh_p: unknown face type");
+            static const int ax[6][2] = {{0, 2}, {0, 2}, {0, 1}, {1, 2}, {0, 1}, {1, 2}};
+            const int eL = faceElem[2 * f], lfL = faceElemSide[2 * f];
+            if (eL < 0 || eL >= nElem || lfL < 0 || lfL > 5) return fail("h3d_set_mesh_p: face without a left element");
+            int NelL[2] = {elemOrder[3 * eL + ax[lfL][0]], elemOrder[3 * eL + ax[lfL][1]]}, NelR[2] = {NelL[0], NelL[1]};
+            if (faceType[f] == H3D_FACE_INTERIOR) {
+                const int eR = faceElem[2 * f + 1], lfR = faceElemSide[2 * f + 1];
+                if (eR < 0 || eR >= nElem || lfR < 0 || lfR > 5) return fail("h3d_set_mesh_p: interior face without a right element");
+                NelR[0] = elemOrder[3 * eR + ax[lfR][0]]; NelR[1] = elemOrder[3 * eR + ax[lfR][1]];
+            } else { ++nBoundaryFaces; maxZone = std::max(maxZone, faceZone[f]); if (faceZone[f] < 0) return fail("h3d_set_mesh_p: boundary face without a zone"); }
+            const int rot = faceRot[f];
+            if (rot < 0 || rot > 7) return fail("h3d_set_mesh_p: face rotation out of range");
+            int NfR[2] = {NelR[0], NelR[1]};
+            if (rot == 1 || rot == 3 || rot == 4 || rot == 6) { NfR[0] = NelR[1]; NfR[1] = NelR[0]; }
+            int* o = &fo[6 * (size_t)f];
+            o[0] = std::max(NelL[0], NfR[0]); o[1] = std::max(NelL[1], NfR[1]); o[2] = NelL[0]; o[3] = NelL[1]; o[4] = NfR[0]; o[5] = NfR[1];
+            for (int s = 0; s < 2; ++s) {
+                proj[2 * f + s] = (o[2 + 2 * s] != o[0] ? 1 : 0) + (o[3 + 2 * s] != o[1] ? 2 : 0);
+                for (int d = 0; d < 2; ++d) if (o[2 + 2 * s + d] != o[d] && (!T.count({o[2 + 2 * s + d], o[d]}) || !T.count({o[d], o[2 + 2 * s + d]})))
+                    return fail("h3d_set_mesh_p: h3d_set_interpolation has not been called for every pair of orders that meet at a face");
+            }
+            if (!sp.count(o[0]) || !sp.count(o[1])) return fail("h3d_set_mesh_p: h3d_set_basis has not been called for every face order");
+            fOff[f + 1] = fOff[f] + (long long)(o[0] + 1) * (o[1] + 1);
+        }
+        m.nNodes = eOff[nElem]; m.nTrace = tOff[6 * (size_t)nElem]; m.nFaceNodes = fOff[nFace];
+        nodeElem.resize(m.nNodes); traceOwner.resize(m.nTrace); faceNodeFace.resize(m.nFaceNodes);
+        for (int e = 0; e < nElem; ++e) for (long long g = eOff[e]; g < eOff[e + 1]; ++g) nodeElem[g] = e;
+        for (int s = 0; s < 6 * nElem; ++s) for (long long g = tOff[s]; g < tOff[s + 1]; ++g) traceOwner[g] = s;
+        for (int f = 0; f < nFace; ++f) for (long long g = fOff[f]; g < fOff[f + 1]; ++g) faceNodeFace[g] = f;
+        hEOff = eOff;
+        // operators and interpolation matrices
+        std::vector<double> ops, ts;
+        for (int N = 0; N < MX_MAXN; ++N) {
+            m.opBase[N] = -1;
+            auto it = sp.find(N);
+            if (it == sp.end()) continue;
+            m.opBase[N] = (int)ops.size();
+            const MxBasis& s = it->second;
+            ops.insert(ops.end(), s.D.begin(), s.D.end()); ops.insert(ops.end(), s.hatD.begin(), s.hatD.end());
+            ops.insert(ops.end(), s.v.begin(), s.v.end()); ops.insert(ops.end(), s.b.begin(), s.b.end());
+            ops.insert(ops.end(), s.w.begin(), s.w.end()); ops.insert(ops.end(), s.x.begin(), s.x.end());
+        }
+        for (int a = 0; a < MX_MAXN; ++a) for (int b = 0; b < MX_MAXN; ++b) {
+            m.tBase[a][b] = -1;
+            auto it = T.find({a, b});
+            if (it == T.end()) continue;
+            m.tBase[a][b] = (int)ts.size();
+            ts.insert(ts.end(), it->second.begin(), it->second.end());
+        }
+        std::vector<int> vElemFace(elemFace, elemFace + 6 * (size_t)nElem), vElemFaceSide(elemFaceSide, elemFaceSide + 6 * (size_t)nElem);
+        std::vector<int> vFaceElem(faceElem, faceElem + 2 * (size_t)nFace), vFaceElemSide(faceElemSide, faceElemSide + 2 * (size_t)nFace);
+        std::vector<int> vRot(faceRot, faceRot + nFace), vType(faceType, faceType + nFace), vZone(faceZone, faceZone + nFace);
+        if (up(eOff, &m.eOff) || up(eN, &m.eN) || up(nodeElem, &m.nodeElem) || up(tOff, &m.tOff) || up(traceOwner, &m.traceOwner) || up(fOff, &m.fOff) ||
+            up(faceNodeFace, &m.faceNodeFace) || up(fo, &m.fo) || up(proj, &m.proj) || up(vElemFace, &m.elemFace) || up(vElemFaceSide, &m.elemFaceSide) ||
+            up(vFaceElem, &m.faceElem) || up(vFaceElemSide, &m.faceElemSide) || up(vRot, &m.faceRot) || up(vType, &m.faceType) || up(vZone, &m.faceZone) ||
+            up(ops, &m.ops) || up(ts, &m.tset)) return 2;
+        // geometry: [node][3] x three directions -> Ja [9][nNodes]
+        const size_t nn = (size_t)m.nNodes, nf = (size_t)m.nFaceNodes;
+        std::vector<double> ja(9 * nn), iJ(nn), tmp;
+        for (size_t g = 0; g < nn; ++g) for (int c = 0; c < 3; ++c) {
+            ja[(size_t)(0 + c) * nn + g] = jGradXi[3 * g + c]; ja[(size_t)(3 + c) * nn + g] = jGradEta[3 * g + c]; ja[(size_t)(6 + c) * nn + g] = jGradZeta[3 * g + c];
+        }
+        for (size_t g = 0; g < nn; ++g) iJ[g] = 1.0 / jacobian[g];   // MappedGeometry.f90:382
+        std::vector<double> vJ(jacobian, jacobian + nn), vfJ(faceJacobian, faceJacobian + nf);
+        if (up(ja, &m.Ja) || up(vJ, &m.J) || up(iJ, &m.invJ) || up(vfJ, &m.fJ)) return 2;
+        toSoA(faceNormal, nf, 3, tmp); if (up(tmp, &m.fN)) return 2;
+        toSoA(faceT1, nf, 3, tmp); if (up(tmp, &m.fT1)) return 2;
+        toSoA(faceT2, nf, 3, tmp); if (up(tmp, &m.fT2)) return 2;
+        if (field(&m.Q, 5 * nn) || field(&m.G, 5 * nn) || field(&m.QDot, 5 * nn) || field(&m.Ux, 5 * nn) || field(&m.Uy, 5 * nn) || field(&m.Uz, 5 * nn) ||
+            field(&m.Fc, 15 * nn) || field(&m.tr, 15 * (size_t)m.nTrace) || field(&m.fStarE, 5 * (size_t)m.nTrace) || field(&m.unStarE, 15 * (size_t)m.nTrace) ||
+            field(&m.fQ, 10 * nf) || field(&m.fU, 30 * nf) || field(&m.fFlux, 15 * nf) || field(&m.partial, 8 * (size_t)std::max(nElem, nFace))) return 2;
+        m.S = nullptr;
+        haveMesh = true;
+        return 0;
+    }
+    int setBoundaryConditions(int nZ, const int* bcType, const double* bcParams) {
+        for (int z = 0; z < nZ; ++z) if (bcType[z] < H3D_BC_PERIODIC || bcType[z] > H3D_BC_OUTFLOW) return fail("h3d_set_boundary_conditions: unknown boundary condition type");
+        std::vector<int> t(bcType, bcType + nZ); std::vector<double> p(bcParams, bcParams + 16 * (size_t)nZ);
+        if (up(t, &m.bcType) || up(p, &m.bcParams)) return 2;
+        nZones = nZ; haveBC = true;
+        return 0;
+    }
+    int ready() {
+        if (!haveMesh) return fail("no mesh");
+        if (nBoundaryFaces > 0 && !haveBC) return fail("mesh has boundary faces but h3d_set_boundary_conditions was not called");
+        if (nBoundaryFaces > 0 && maxZone >= nZones) return fail("a boundary face refers to a zone beyond the table of h3d_set_boundary_conditions");
+        return 0;
+    }
+    int uploadField(double* dst, const double* src) {
+        toSoA(src, (size_t)m.nNodes, 5, hBuf);
+        be.upload(dst, hBuf.data(), hBuf.size());
+        return check();
+    }
+    int downloadField(double* dst, const double* src) {
+        const size_t nn = (size_t)m.nNodes;
+        hBuf.resize(5 * nn);
+        be.download(hBuf.data(), src, hBuf.size());
+        if (check()) return 2;
+        for (size_t g = 0; g < nn; ++g) for (int c = 0; c < 5; ++c) dst[g * 5 + c] = hBuf[(size_t)c * nn + g];
+        return 0;
+    }
+    int uploadQ(const double* Q) { if (!haveMesh) return fail("no mesh"); return uploadField(m.Q, Q); }
+    int download(double* Q, double* QDot, double* Ux, double* Uy, double* Uz) {
+        if (!haveMesh) return fail("no mesh");
+        double* dst[5] = {Q, QDot, Ux, Uy, Uz}; const double* src[5] = {m.Q, m.QDot, m.Ux, m.Uy, m.Uz};
+        for (int a = 0; a < 5; ++a) if (dst[a] && downloadField(dst[a], src[a])) return 2;
+        return 0;
+    }
+    int setSource(const double* S) {
+        if (!haveMesh) return fail("no mesh");
+        if (!S) { m.S = nullptr; return 0; }
+        if (!dSource && field(&dSource, 5 * (size_t)m.nNodes)) return 2;
+        if (uploadField(dSource, S)) return 2;
+        m.S = dSource;
+        return 0;
+    }
+    // HexMesh_ProlongSolutionToFaces / ProlongGradientsToFaces: traces at the element order, then adaption to the face order
+    void prolong(const double* src, double* dstFace) {
+        launch(MxTrace{m, src, m.tr}, m.nTrace);
+        launch(MxAdapt{m, m.tr, dstFace}, 2 * m.nFaceNodes);
+    }
+    void prolongGradients() {
+        prolong(m.Ux, m.fU); prolong(m.Uy, m.fU + 10 * m.nFaceNodes); prolong(m.Uz, m.fU + 20 * m.nFaceNodes);
+    }
+    // ComputeTimeDerivative (SpatialDiscretization.f90:227-320) followed by the update of one Runge-Kutta stage
+    int residual(const H3dPhysics& physics, const MxRk& rk) {
+        if (ready()) return 1;
+        prolong(m.Q, m.fQ);
+        if (physics.computeGradients) {
+            launch(MxLocalGrad{m, ph}, m.nNodes);
+            if (physics.flowIsNavierStokes) {
+                launch(MxGradFace{m, ph}, m.nFaceNodes);
+                launch(MxProject{m, 15, m.fFlux, m.unStarE, 1.0}, m.nTrace);
+                launch(MxLift{m}, m.nNodes);
+            }
+            prolongGradients();
+        }
+        launch(MxFlux{m, ph}, m.nNodes);
+        launch(MxRiemann{m, ph}, m.nFaceNodes);
+        launch(MxProject{m, 5, m.fFlux, m.fStarE, -1.0}, m.nTrace);
+        launch(MxVolume{m, rk}, m.nNodes);
+        return check();
+    }
+    int rkStage(const H3dPhysics& physics, int scheme, int k, double dt) {
+        MxRk rk;
+        if (!mxRkStages(scheme)) return fail("unknown Runge-Kutta scheme");
+        if (!mxRkCoefficients(scheme, k, rk, dt)) return fail("Runge-Kutta stage out of range");
+        return residual(physics, rk);
+    }
+    int rkStep(const H3dPhysics& physics, int scheme, double dt, int ctdAfterStep) {
+        const int ns = mxRkStages(scheme);
+        if (!ns) return fail("unknown Runge-Kutta scheme");
+        for (int k = 0; k < ns; ++k) { const int rc = rkStage(physics, scheme, k, dt); if (rc) return rc; }
+        if (ctdAfterStep) return residual(physics, MxRk{0, 0.0, 0.0, 0.0, 0});
+        return 0;
+    }
+    int partials(int count) {
+        hPartial.resize(8 * (size_t)count);
+        be.download(hPartial.data(), m.partial, hPartial.size());
+        return check();
+    }
+    int maxResiduals(double out[5], int* nanFlag) {
+        if (!haveMesh) return fail("no mesh");
+        launch(MxRedResidual{m}, m.nElem);
+        if (partials(m.nElem)) return 2;
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        for (int e = 0; e < m.nElem; ++e) for (int q = 0; q < 6; ++q) v[q] = std::fmax(v[q], hPartial[8 * (size_t)e + q]);
+        for (int q = 0; q < 5; ++q) out[q] = v[q];
+        *nanFlag = v[5] > 0.5 ? 1 : 0;
+        return 0;
+    }
+    int maxTimestep(double cfl, double dcfl, double* dtConv, double* dtVisc) {
+        if (ready()) return 1;
+        launch(MxRedTimestep{m, ph, cfl, dcfl}, m.nElem);
+        if (partials(m.nElem)) return 2;
+        double a = 1.7976931348623157e308, b = 1.7976931348623157e308;
+        for (int e = 0; e < m.nElem; ++e) { a = std::fmin(a, hPartial[8 * (size_t)e]); b = std::fmin(b, hPartial[8 * (size_t)e + 1]); }
+        *dtConv = a; *dtVisc = b;
+        return 0;
+    }
+    int volumeIntegral(const H3dPhysics& physics, int kind, double* val) {
+        if (!haveMesh) return fail("no mesh");
+        switch (kind) {
+            case H3D_INT_VOLUME: case H3D_INT_KINETIC_ENERGY: case H3D_INT_KINETIC_ENERGY_RATE: case H3D_INT_VELOCITY: case H3D_INT_INTERNAL_ENERGY: break;
+            case H3D_INT_ENSTROPHY: if (!physics.computeGradients) return fail("volume integral needs gradients"); break;
+            default: return fail("this volume integral is not available on p-nonconforming meshes");
+        }
+        launch(MxRedIntegral{m, ph, kind}, m.nElem);
+        if (partials(m.nElem)) return 2;
+        double v = 0.0;
+        for (int e = 0; e < m.nElem; ++e) v = v + hPartial[8 * (size_t)e];
+        *val = v;
+        return 0;
+    }
+    int surfaceIntegral(const H3dPhysics& physics, int zone, int kind, double out[3]) {
+        if (ready()) return 1;
+        if (kind < H3D_SURF_SURFACE || kind > H3D_SURF_VISCOUS_FORCE) return fail("unknown surface integral");
+        if (zone < 0 || zone >= nZones) return fail("surface integral: zone out of range");
+        const bool viscous = kind == H3D_SURF_TOTAL_FORCE || kind == H3D_SURF_VISCOUS_FORCE;
+        if (viscous && !physics.computeGradients) return fail("surface integral needs gradients");
+        prolong(m.Q, m.fQ);   // the state (and gradients) are prolonged anew, as the reference does (SurfaceIntegrals.f90:57-77)
+        if (physics.computeGradients) prolongGradients();
+        launch(MxRedSurface{m, ph, zone, kind}, m.nFace);
+        if (partials(m.nFace)) return 2;
+        double v[3] = {0, 0, 0};
+        for (int f = 0; f < m.nFace; ++f) for (int d = 0; d < 3; ++d) v[d] = v[d] + hPartial[8 * (size_t)f + d];
+        for (int d = 0; d < 3; ++d) out[d] = v[d];
+        return 0;
+    }
+    int probe(int nProbes, const int* elem, const int* variable, const double* lxi, const double* leta, const double* lzeta, double* values) {
+        if (!haveMesh) return fail("no mesh");
+        if (nProbes <= 0) return 0;
+        const int ld = maxNodes1D;
+        for (int p = 0; p < nProbes; ++p) {
+            if (elem[p] < 0 || elem[p] >= m.nElem) return fail("probe element out of range");
+            if (variable[p] < H3D_PROBE_PRESSURE || variable[p] > H3D_PROBE_K) return fail("unknown probe variable");
+        }
+        if (probeCap < (size_t)nProbes) {
+            dProbeI = be.template alloc<int>(2 * (size_t)nProbes); dProbeD = be.template alloc<double>((3 * (size_t)ld + 1) * nProbes);
+            if (!dProbeI || !dProbeD) return check() ? 2 : fail("device allocation failed");
+            probeCap = nProbes;
+        }
+        std::vector<int> iv(2 * (size_t)nProbes); std::vector<double> L(3 * (size_t)ld * nProbes);
+        for (int p = 0; p < nProbes; ++p) { iv[p] = elem[p]; iv[nProbes + p] = variable[p]; }
+        std::memcpy(&L[0], lxi, (size_t)ld * nProbes * sizeof(double)); std::memcpy(&L[(size_t)ld * nProbes], leta, (size_t)ld * nProbes * sizeof(double));
+        std::memcpy(&L[2 * (size_t)ld * nProbes], lzeta, (size_t)ld * nProbes * sizeof(double));
+        be.upload(dProbeI, iv.data(), iv.size()); be.upload(dProbeD, L.data(), L.size());
+        double* dVal = dProbeD + 3 * (size_t)ld * nProbes;
+        launch(MxProbe{m, ph, dProbeI, dProbeI + nProbes, dProbeD, nProbes, ld, dVal}, nProbes);
+        be.download(values, dVal, (size_t)nProbes);
+        return check();
+    }
+};
+
+}  // namespace h3d

@@ -148,7 +148,8 @@ int h3d_last_error_copy(h3d_handle h, char* buf, int len); /* Fortran-friendly c
 int h3d_set_physics(h3d_handle h, const H3dPhysics* p);
 
 /* NodalStorage(N) (libs/spectral/NodalStorageClass.f90:24-52).  Matrices row-major M[i*(N+1)+l] = M(i,l);
- * v,b: [side*(N+1)+i], side 0 = LEFT/FRONT/BOTTOM (-1 end), 1 = RIGHT/BACK/TOP (+1 end).  Uniform order only. */
+ * v,b: [side*(N+1)+i], side 0 = LEFT/FRONT/BOTTOM (-1 end), 1 = RIGHT/BACK/TOP (+1 end).  h3d_set_mesh uses the last order given
+ * (N = 1..9); every order given stays registered for h3d_set_mesh_p (N = 1..15). */
 int h3d_set_basis(h3d_handle h, int N, int nodeType, const double* x, const double* w, const double* D,
                   const double* hatD, const double* sharpD, const double* v, const double* b);
 
@@ -170,6 +171,33 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace,
                  const double* faceJacobian, /* [f][j][i]                                                       */
                  const double* faceX,      /* [f][j][i][3]  may be NULL                                        */
                  const double* faceSurface /* [f]           f % geom % surface (LES) - may be NULL             */);
+
+/* ---- p-nonconforming meshes ---------------------------------------------------------------------------------
+ * Every element has its own polynomial orders (Nx, Ny, Nz) -- the reference's "polynomial order file" (ReadOrderFile,
+ * libs/io/ReadInputFile.f90:132-153) or the result of a p-adaptation -- and every face the orders of its two sides and its own,
+ * Nf = max per direction (Face_LinkWithElements, libs/mesh/FaceClass.f90:187-282).  Set-up: h3d_set_physics, then h3d_set_basis once
+ * for EVERY order that occurs in an element or on a face (NodalStorage(N), DGSEMClass.f90:215-228; orders up to 15),
+ * h3d_set_interpolation for every pair of different orders (N, M) and (M, N) that meet at a face, then h3d_set_mesh_p instead of
+ * h3d_set_mesh.  All element arrays of the ABI are then packed element after element at the elements' own sizes, A[e][k][j][i][c]
+ * with (Nx+1)(Ny+1)(Nz+1) nodes in element e (StorageClass.f90:423-429), and face arrays face after face at the face orders.
+ * Available on such a mesh: StandardDG with BR1 (or Euler), every Riemann solver, boundary condition and gradient-variable set,
+ * all Runge-Kutta schemes, h3d_max_residuals / _max_timestep / _has_nan, h3d_volume_integral (volume, kinetic energy and its
+ * rate, enstrophy, mean velocity, internal energy), h3d_surface_integral, h3d_probe (Lagrange vectors padded to rows of
+ * max(N)+1 values); one rank.  The other entry points return an error. */
+
+/* Tset(Norigin, Ndest) % T (libs/spectral/InterpolationMatrices.f90:42-107): row-major T[i*(Norigin+1) + l] = T(i,l),
+ * (Ndest+1) x (Norigin+1); Lagrange interpolation for Norigin < Ndest, the L2 projection (weighted transpose) otherwise. */
+int h3d_set_interpolation(h3d_handle h, int Norigin, int Ndest, const double* T);
+
+/* h3d_set_mesh for a p-nonconforming mesh: elemOrder[nElem][3] = e % Nxyz (HexElementClass.f90:60-75); the other arguments as
+ * h3d_set_mesh with the packed sizes described above (face geometry from MappedGeometryFace at the face order,
+ * MappedGeometry.f90:482-756). */
+int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder,
+                   const int* elemFace, const int* elemFaceSide, const int* faceElem, const int* faceElemSide,
+                   const int* faceRot, const int* faceType, const int* faceZone,
+                   const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,
+                   const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
+                   const double* faceJacobian, const double* faceX, const double* faceSurface);
 
 /* e % geom % dWall, f % geom % dWall (HexMesh_ComputeWallDistances, libs/mesh/HexMesh.f90:5594-5692): distance to the
  * nearest no-slip wall node, [e][k][j][i] and [f][j][i].  Needed only with les_wall_model = 1. */

@@ -22,6 +22,7 @@ module H3DGpuAdapter
    use ElementClass
    use FaceClass
    use NodalStorageClass
+   use InterpolationMatrices,      only: Tset
    use PhysicsStorage
    use FluidData,                  only: thermodynamics, dimensionless, refValues
    use RiemannSolvers_NS,          only: whichRiemannSolver, whichAverage, lambdaStab, &
@@ -97,7 +98,8 @@ contains
 !
 !  ----------------------------------------------------------------------------------------------------------------
 !  Once, after sem % construct and Initialize_SpaceAndTimeMethods (main.f90:117-144): physics, basis, mesh, boundary
-!  table, wall distances, halo, state.  Uniform polynomial order only (the library refuses anything else).
+!  table, wall distances, halo, state.  A mesh whose elements do not all have the order N (a polynomial order file, a
+!  p-adapted mesh) takes the p-nonconforming branch (setup_basis_and_mesh_p, below).
 !  ----------------------------------------------------------------------------------------------------------------
    subroutine h3d_gpu_setup(mesh, N, viscousDiscretization, penaltyParameter, ipVariant, gradientVariables, inviscidIsSplitForm, ctdAfterSteps)
       type(HexMesh), target, intent(inout) :: mesh
@@ -168,6 +170,10 @@ contains
 !
 !     2. Basis: the header wants row-major M(i,l) -> the transposes of the Fortran column-major arrays
 !     ----------------------------------------------------------------------------------------------
+      if ( any(mesh % Nx /= N) .or. any(mesh % Ny /= N) .or. any(mesh % Nz /= N) ) then
+         call setup_basis_and_mesh_p(mesh)
+         goto 400                                                          ! boundary table, state
+      end if
       sp => NodalStorage(N)
       allocate(Dt((N+1)**2), hatDt((N+1)**2), sharpDt((N+1)**2), vv(2*(N+1)), bb(2*(N+1)))
       Dt      = reshape(transpose(sp % D),      [(N+1)**2])
@@ -222,6 +228,7 @@ contains
 !
 !     4. Boundary table: one type and 16 parameters per zone (include/h3d_gpu.h, H3D_BC_*)
 !     --------------------------------------------------------------------------------------
+400   continue
       nZones = size(mesh % zones)
       if ( nZones > 0 ) then
          allocate(bcType(nZones), bcPar(16*nZones));  bcPar = 0.0_RP
@@ -289,6 +296,92 @@ contains
       call mesh % storage % local2GlobalQ(mesh % storage % NDOF)
       call check(h3d_upload_Q(h3d, mesh % storage % Q), "h3d_upload_Q")
    end subroutine h3d_gpu_setup
+!
+!  ----------------------------------------------------------------------------------------------------------------
+!  Steps 2 and 3 of the set-up on a p-nonconforming mesh (include/h3d_gpu.h, h3d_set_mesh_p): NodalStorage(N) of every
+!  constructed order (DGSEMClass.f90:215-228, FaceClass.f90:226-232), Tset(N,M) of every constructed pair of orders
+!  (FaceClass.f90:236-251), and the mesh with the elements' orders; arrays packed at the elements' / faces' own sizes.
+!  ----------------------------------------------------------------------------------------------------------------
+   subroutine setup_basis_and_mesh_p(mesh)
+      type(HexMesh), target, intent(inout) :: mesh
+      integer                              :: N, M, eID, fID, s, k, nE, nF, n3, n2, posE, posF
+      integer(c_int), allocatable          :: elemOrder(:), elemFace(:), elemFaceSide(:), faceElem(:), faceElemSide(:), faceRot(:), faceType(:), faceZone(:)
+      real(c_double), allocatable          :: jGradXi(:), jGradEta(:), jGradZeta(:), jac(:), x(:), vol(:)
+      real(c_double), allocatable          :: fN(:), fT1(:), fT2(:), fJ(:), fX(:), fS(:)
+      real(c_double), allocatable          :: Dt(:), hatDt(:), sharpDt(:), vv(:), bb(:), Tt(:)
+      type(NodalStorage_t), pointer        :: sp
+
+      if ( MPI_Process % doMPIAction ) then
+         print*, "The GPU path runs p-nonconforming meshes on one rank."
+         errorMessage(STD_OUT) ; error stop
+      end if
+      do N = 1, ubound(NodalStorage, 1)
+         if ( .not. NodalStorage(N) % Constructed ) cycle
+         sp => NodalStorage(N)
+         allocate(Dt((N+1)**2), hatDt((N+1)**2), sharpDt((N+1)**2), vv(2*(N+1)), bb(2*(N+1)))
+         Dt      = reshape(transpose(sp % D),    [(N+1)**2])
+         hatDt   = reshape(transpose(sp % hatD), [(N+1)**2])
+         sharpDt = 0.0_RP
+         vv = reshape(sp % v, [2*(N+1)]);   bb = reshape(sp % b, [2*(N+1)])
+         call check(h3d_set_basis(h3d, int(N, c_int), int(mesh % nodeType, c_int), sp % x, sp % w, Dt, hatDt, sharpDt, vv, bb), "h3d_set_basis")
+         deallocate(Dt, hatDt, sharpDt, vv, bb)
+      end do
+      do M = 1, ubound(Tset, 2) ; do N = 1, ubound(Tset, 1)                  ! Tset(Norigin, Ndest) % T(0:Ndest, 0:Norigin)
+         if ( N == M ) cycle
+         if ( .not. Tset(N, M) % Constructed ) cycle
+         allocate(Tt((N+1)*(M+1)))
+         Tt = reshape(transpose(Tset(N, M) % T), [(N+1)*(M+1)])             ! row-major T(i,l) as the header asks
+         call check(h3d_set_interpolation(h3d, int(N, c_int), int(M, c_int), Tt), "h3d_set_interpolation")
+         deallocate(Tt)
+      end do                    ; end do
+
+      nE = size(mesh % elements);  nF = size(mesh % faces)
+      posE = 0
+      do eID = 1, nE ; posE = posE + product(mesh % elements(eID) % Nxyz + 1) ; end do
+      posF = 0
+      do fID = 1, nF ; posF = posF + product(mesh % faces(fID) % Nf + 1) ; end do
+      allocate(elemOrder(3*nE), elemFace(6*nE), elemFaceSide(6*nE), faceElem(2*nF), faceElemSide(2*nF), faceRot(nF), faceType(nF), faceZone(nF))
+      allocate(jGradXi(3*posE), jGradEta(3*posE), jGradZeta(3*posE), jac(posE), x(3*posE), vol(nE))
+      allocate(fN(3*posF), fT1(3*posF), fT2(3*posF), fJ(posF), fX(3*posF), fS(nF))
+      posE = 0
+      do eID = 1, nE
+         associate ( e => mesh % elements(eID) )
+         n3 = product(e % Nxyz + 1)
+         elemOrder(3*(eID-1)+1 : 3*eID) = e % Nxyz
+         do s = 1, 6
+            elemFace(6*(eID-1)+s)     = e % faceIDs(s) - 1
+            elemFaceSide(6*(eID-1)+s) = e % faceSide(s) - 1
+         end do
+         jGradXi  (3*posE+1 : 3*(posE+n3)) = reshape(e % geom % jGradXi,   [3*n3])
+         jGradEta (3*posE+1 : 3*(posE+n3)) = reshape(e % geom % jGradEta,  [3*n3])
+         jGradZeta(3*posE+1 : 3*(posE+n3)) = reshape(e % geom % jGradZeta, [3*n3])
+         x        (3*posE+1 : 3*(posE+n3)) = reshape(e % geom % x,         [3*n3])
+         jac      (  posE+1 :    posE+n3 ) = reshape(e % geom % jacobian,  [n3])
+         vol(eID) = e % geom % volume
+         posE = posE + n3
+         end associate
+      end do
+      posF = 0
+      do fID = 1, nF
+         associate ( f => mesh % faces(fID) )
+         n2 = product(f % Nf + 1)
+         do k = 1, 2
+            faceElem(2*(fID-1)+k)     = f % elementIDs(k) - 1
+            faceElemSide(2*(fID-1)+k) = f % elementSide(k) - 1
+         end do
+         faceRot(fID) = f % rotation;  faceType(fID) = f % faceType;  faceZone(fID) = f % zone - 1
+         fN (3*posF+1 : 3*(posF+n2)) = reshape(f % geom % normal,   [3*n2])
+         fT1(3*posF+1 : 3*(posF+n2)) = reshape(f % geom % t1,       [3*n2])
+         fT2(3*posF+1 : 3*(posF+n2)) = reshape(f % geom % t2,       [3*n2])
+         fX (3*posF+1 : 3*(posF+n2)) = reshape(f % geom % x,        [3*n2])
+         fJ (  posF+1 :    posF+n2 ) = reshape(f % geom % jacobian, [n2])
+         fS(fID) = f % geom % surface
+         posF = posF + n2
+         end associate
+      end do
+      call check(h3d_set_mesh_p(h3d, int(nE, c_int), int(nF, c_int), elemOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, &
+                                faceZone, jGradXi, jGradEta, jGradZeta, jac, x, vol, fN, fT1, fT2, fJ, fX, fS), "h3d_set_mesh_p")
+   end subroutine setup_basis_and_mesh_p
 !
 !  ----------------------------------------------------------------------------------------------------------------
 !  Host copy of the state for SaveSolution / restart / host-side monitors (TimeIntegrator.f90:924, main.f90:207)

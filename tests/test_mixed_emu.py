@@ -1,0 +1,70 @@
+"""p-nonconforming path on the CPU: the kernel functors and the orchestration of horses3d_b200/csrc/h3d_mixed.cuh,
+built for the host with a loop as the launcher (tests/emu), against the oracle.  Bit-exact: the functors keep the reference's
+order of every sum and the host build disables FMA contraction as the device build does."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import mixed_cases as MC                                   # noqa: E402
+from emu.emu_api import EmuApi                             # noqa: E402
+from horses3d_b200.hostmesh import GAUSS, GAUSSLOBATTO     # noqa: E402
+from horses3d_b200.physics import make_physics             # noqa: E402
+from oracle import oracle_api                              # noqa: E402
+
+
+def both(mesh_fn, phys, **kw):
+    _, a = MC.run_case(oracle_api.OracleApi(), mesh_fn(), phys, **kw)
+    _, b = MC.run_case(EmuApi(), mesh_fn(), phys, **kw)
+    worst, bad = MC.compare(a, b)
+    print(worst)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("riemann", ["roe", "lax-friedrichs", "standard roe", "central"])
+def test_navier_stokes_periodic_box_random_anisotropic_orders(riemann):
+    both(lambda: MC.periodic_box(3, 2, 5, seed=7), make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann=riemann), source=True)
+
+
+def test_euler_with_and_without_gradients():
+    both(lambda: MC.periodic_box(3, 1, 4, seed=5), make_physics(flow="Euler", mach=0.3, riemann="roe"))
+    both(lambda: MC.periodic_box(3, 1, 4, seed=5), make_physics(flow="Euler", mach=0.3, riemann="rusanov", compute_gradients=True))
+
+
+def test_gauss_lobatto_nodes_and_isotropic_orders():
+    both(lambda: MC.periodic_box(3, 2, 6, seed=9, nodes=GAUSSLOBATTO, anisotropic=False), make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe"))
+
+
+@pytest.mark.parametrize("scheme", ["euler", "rk5", "lserk14-4", "ssprk33", "ssprk43"])
+def test_runge_kutta_schemes(scheme):
+    both(lambda: MC.periodic_box(2, 2, 4, seed=13), make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe"), scheme=scheme)
+
+
+@pytest.mark.parametrize("gradvars", ["state", "entropy", "energy"])
+def test_boundary_conditions_and_gradient_variables(gradvars):
+    phys = make_physics(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", gradient_variables=gradvars)
+    for zone in (2, 4):      # no-slip wall, inflow
+        both(lambda: MC.channel(phys), phys, zone=zone)
+
+
+def test_k13_cylinder_different_orders_through_the_device_functors():
+    """The reference's CylinderDifferentOrders regression (K13) through the emulated device path: 100 steps, residuals, drag, lift
+    and the wake probe at the reference's tolerance -- and identical to the oracle."""
+    from test_oracle_pins import K13, cylinder_different_orders
+    api = EmuApi()
+    _, res, cd, cl, wake_u = cylinder_different_orders(api)
+    _, res0, cd0, cl0, wake0 = cylinder_different_orders()
+    assert api.kernel_launches() >= 100 * 3 * 17
+    assert np.abs(res - K13["residuals"]).max() < 1.0e-11 and abs(cd - K13["cd"]) < 1.2e-10 and abs(cl - K13["cl"]) < 1.0e-11 and abs(wake_u - K13["wake_u"]) < 1.0e-11
+    assert np.array_equal(res, res0) and cd == cd0 and cl == cl0 and wake_u == wake0
+
+
+def test_unsupported_configurations_are_refused():
+    from horses3d_b200.capi import H3dError
+    from horses3d_b200.dgsem import DGSem
+    for kw in (dict(inviscid="split-form", averaging="pirozzoli"), dict(viscous="br2"), dict(les="smagorinsky")):
+        with pytest.raises(H3dError):
+            DGSem(EmuApi(), MC.periodic_box(2, 2, 3, seed=1, nodes=GAUSSLOBATTO), make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe", **kw))
