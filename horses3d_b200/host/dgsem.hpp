@@ -17,6 +17,7 @@
 
 #include "../../include/h3d_gpu.h"
 #include "geometry.hpp"
+#include "geometry_p.hpp"
 
 namespace h3d {
 
@@ -35,6 +36,10 @@ struct Backend {
     int (*set_mesh)(h3d_handle, int, int, const int*, const int*, const int*, const int*, const int*, const int*, const int*, const double*, const double*,
                     const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*,
                     const double*) = nullptr;
+    int (*set_interpolation)(h3d_handle, int, int, const double*) = nullptr;
+    int (*set_mesh_p)(h3d_handle, int, int, const int*, const int*, const int*, const int*, const int*, const int*, const int*, const int*, const double*,
+                      const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*,
+                      const double*, const double*) = nullptr;
     int (*set_wall_distance)(h3d_handle, const double*, const double*) = nullptr;
     int (*set_face_h)(h3d_handle, const double*) = nullptr;
     int (*set_boundary_conditions)(h3d_handle, int, const int*, const double*) = nullptr;
@@ -57,6 +62,7 @@ struct Backend {
         if (!create) create = sym<decltype(create)>("create");
         destroy = sym<decltype(destroy)>("destroy"); last_error = sym<decltype(last_error)>("last_error");
         set_physics = sym<decltype(set_physics)>("set_physics"); set_basis = sym<decltype(set_basis)>("set_basis"); set_mesh = sym<decltype(set_mesh)>("set_mesh");
+        set_interpolation = sym<decltype(set_interpolation)>("set_interpolation"); set_mesh_p = sym<decltype(set_mesh_p)>("set_mesh_p");
         set_wall_distance = sym<decltype(set_wall_distance)>("set_wall_distance"); set_face_h = sym<decltype(set_face_h)>("set_face_h");
         set_boundary_conditions = sym<decltype(set_boundary_conditions)>("set_boundary_conditions");
         upload_Q = sym<decltype(upload_Q)>("upload_Q"); download = sym<decltype(download)>("download");
@@ -118,6 +124,7 @@ class DGSem {
 public:
     Backend& api; h3d_handle h = nullptr;
     HostMesh mesh; HostGeometry geom; H3dPhysics phys{};
+    HostGeometryP geomP; bool mixed = false;      // p-nonconforming mesh: element-wise polynomial orders (constructP)
     int N = 0, n = 0; long long NDOF = 0;
 
     explicit DGSem(Backend& b) : api(b) {}
@@ -139,24 +146,57 @@ public:
                            mesh.faceRot.data(), mesh.faceType.data(), mesh.faceZone.data(), geom.jGradXi.data(), geom.jGradEta.data(), geom.jGradZeta.data(),
                            geom.jac.data(), geom.x.data(), geom.volume.data(), geom.fnormal.data(), geom.ft1.data(), geom.ft2.data(), geom.fjac.data(),
                            geom.fx.data(), geom.fsurface.data()));
-        if (!mesh.bcs.empty()) {
-            std::vector<int> types; std::vector<double> params;
-            for (auto& bc : mesh.bcs) {
-                types.push_back(lookup("boundary condition", bc.type, {{"periodic", H3D_BC_PERIODIC}, {"noslipwall", H3D_BC_NOSLIPWALL},
-                                       {"freeslipwall", H3D_BC_FREESLIPWALL}, {"inflow", H3D_BC_INFLOW}, {"outflow", H3D_BC_OUTFLOW}}));
-                params.insert(params.end(), bc.params, bc.params + 16);
-            }
-            check(api.set_boundary_conditions(h, (int)types.size(), types.data(), params.data()));
-        }
+        setBoundaryTable();
         if (phys.les_wall_model) check(api.set_wall_distance(h, geom.dWall.data(), geom.fdWall.data()));
         if (phys.viscous == H3D_VISCOUS_IP) check(api.set_face_h(h, geom.fh.data()));
+    }
+
+    void setBoundaryTable() {
+        if (mesh.bcs.empty()) return;
+        std::vector<int> types; std::vector<double> params;
+        for (auto& bc : mesh.bcs) {
+            types.push_back(lookup("boundary condition", bc.type, {{"periodic", H3D_BC_PERIODIC}, {"noslipwall", H3D_BC_NOSLIPWALL},
+                                   {"freeslipwall", H3D_BC_FREESLIPWALL}, {"inflow", H3D_BC_INFLOW}, {"outflow", H3D_BC_OUTFLOW}}));
+            params.insert(params.end(), bc.params, bc.params + 16);
+        }
+        check(api.set_boundary_conditions(h, (int)types.size(), types.data(), params.data()));
+    }
+
+    // sem % construct with a polynomial order file (DGSEMClass.f90:195-228, pAdaptationClass.f90:218-220): orders[e][3]; nodal storages of
+    // every order, interpolation matrices of every pair of orders that meet at a face (FaceClass.f90:236-251), h3d_set_mesh_p
+    void constructP(const std::vector<int>& orders, int nodeType, const H3dPhysics& physics, int device = 0) {
+        phys = physics; mixed = true; N = -1; n = 0;
+        if ((int)orders.size() != 3 * mesh.nElem()) throw std::runtime_error("the polynomial order file does not match the number of elements of the mesh");
+        std::string err;
+        if (!buildGeometryP(mesh, orders.data(), nodeType, geomP, err)) throw std::runtime_error(err);
+        NDOF = geomP.eOff[mesh.nElem()];
+        int rc = api.create(&h, 0, 1, device, nullptr);
+        if (rc != 0) throw std::runtime_error(std::string("h3d_create failed: ") + (api.last_error(nullptr) ? api.last_error(nullptr) : "?"));
+        check(api.set_physics(h, &phys));
+        for (auto& kv : geomP.sp) {
+            const NodalStorage& sp = kv.second;
+            check(api.set_basis(h, sp.N, nodeType, sp.x.data(), sp.w.data(), sp.D.data(), sp.hatD.data(), sp.sharpD.data(), sp.v.data(), sp.b.data()));
+        }
+        std::vector<double> T;
+        for (int f = 0; f < mesh.nFaces; ++f) for (int s = 2; s <= 4; s += 2) for (int d = 0; d < 2; ++d) {
+            const int a = geomP.faceOrder[6 * f + s + d], b = geomP.faceOrder[6 * f + d];
+            if (a == b) continue;
+            interpolationMatrix(geomP.sp.at(a), geomP.sp.at(b), T); check(api.set_interpolation(h, a, b, T.data()));
+            interpolationMatrix(geomP.sp.at(b), geomP.sp.at(a), T); check(api.set_interpolation(h, b, a, T.data()));
+        }
+        check(api.set_mesh_p(h, mesh.nElem(), mesh.nFaces, geomP.elemOrder.data(), mesh.elemFace.data(), mesh.elemFaceSide.data(), mesh.faceElem.data(),
+                             mesh.faceElemSide.data(), mesh.faceRot.data(), mesh.faceType.data(), mesh.faceZone.data(), geomP.jGradXi.data(), geomP.jGradEta.data(),
+                             geomP.jGradZeta.data(), geomP.jac.data(), geomP.x.data(), geomP.volume.data(), geomP.fnormal.data(), geomP.ft1.data(), geomP.ft2.data(),
+                             geomP.fjac.data(), geomP.fx.data(), geomP.fsurface.data()));
+        setBoundaryTable();
     }
 
     // UserDefinedInitialCondition: fn(x[3], Q[5]) at every node
     void setInitialCondition(const std::function<void(const double*, double*)>& fn) {
         std::vector<double> Q((size_t)NDOF * 5);
+        const std::vector<double>& xn = mixed ? geomP.x : geom.x;
 #pragma omp parallel for schedule(static)
-        for (long long g = 0; g < NDOF; ++g) fn(&geom.x[3 * g], &Q[5 * g]);
+        for (long long g = 0; g < NDOF; ++g) fn(&xn[3 * g], &Q[5 * g]);
         check(api.upload_Q(h, Q.data()));
     }
     std::vector<double> Q() { std::vector<double> q((size_t)NDOF * 5); check(api.download(h, q.data(), nullptr, nullptr, nullptr, nullptr)); return q; }

@@ -1,7 +1,7 @@
 // Native host-side driver above the C ABI: what NavierStokesSolver/main.f90 does around the hot path, for the cases the
 // control-file keys below can express (the reference's control-file parser itself is out of scope).
 //
-//   h3d_driver --lib PATH [--prefix h3d_] [--mesh FILE | --ne 32 [--amp 0.1]] --order 3 [--nodes gauss|gauss-lobatto]
+//   h3d_driver --lib PATH [--prefix h3d_] [--mesh FILE | --ne 32 [--amp 0.1]] --order 3 | --order-file FILE [--nodes gauss|gauss-lobatto]
 //              [--flow NS|Euler] [--mach 0.08] [--reynolds 1600] [--riemann roe] [--inviscid standard|split-form] [--averaging standard]
 //              [--viscous BR1|BR2|IP] [--gradient-variables state|entropy|energy] [--les none|smagorinsky] [--lambda-stab 1]
 //              [--bc name:type[:coupled]]... [--ic tgv|uniform] [--aoa-theta 0 --aoa-phi 0]
@@ -24,7 +24,7 @@ int main(int argc, char** argv) {
     std::map<std::string, std::string> opt = {{"prefix", "h3d_"}, {"ne", "8"}, {"amp", "0"}, {"order", "3"}, {"nodes", "gauss"}, {"flow", "NS"}, {"mach", "0.08"},
         {"reynolds", "1600"}, {"riemann", "roe"}, {"inviscid", "standard"}, {"averaging", "standard"}, {"viscous", "BR1"}, {"gradient-variables", "state"},
         {"les", "none"}, {"lambda-stab", "1"}, {"ic", "tgv"}, {"aoa-theta", "0"}, {"aoa-phi", "0"}, {"scheme", "rk3"}, {"steps", "5"}, {"cfl", "0.4"},
-        {"dcfl", "0.4"}, {"dt", "0"}, {"device", "0"}, {"limiter", "0"}, {"lib", ""}, {"mesh", ""}};
+        {"dcfl", "0.4"}, {"dt", "0"}, {"device", "0"}, {"limiter", "0"}, {"lib", ""}, {"mesh", ""}, {"order-file", ""}};
     std::vector<std::string> bcArgs;
     for (int a = 1; a < argc; ++a) {
         std::string key = argv[a];
@@ -72,7 +72,15 @@ int main(int argc, char** argv) {
         }
         if (!buildConnectivity(sem.mesh, bcs, err)) throw std::runtime_error(err);
         const int nodeType = toLower(opt["nodes"]) == "gauss" ? GAUSS : GAUSSLOBATTO;
-        sem.construct(std::atoi(opt["order"].c_str()), nodeType, phys, std::atoi(opt["device"].c_str()));
+        if (!opt["order-file"].empty()) {                              // "polynomial order file" (ReadOrderFile, ReadInputFile.f90:132-153)
+            std::ifstream of(opt["order-file"]);
+            if (!of) throw std::runtime_error("Error opening file: " + opt["order-file"]);
+            int nelem = 0; of >> nelem;
+            std::vector<int> orders(3 * (size_t)std::max(nelem, 0));
+            for (auto& q : orders) if (!(of >> q)) throw std::runtime_error("bad polynomial order file");
+            sem.constructP(orders, nodeType, phys, std::atoi(opt["device"].c_str()));
+        } else
+            sem.construct(std::atoi(opt["order"].c_str()), nodeType, phys, std::atoi(opt["device"].c_str()));
         // ---- UserDefinedInitialCondition
         if (toLower(opt["ic"]) == "tgv") {                             // test/NavierStokes/TaylorGreen/SETUP/ProblemFile.f90:107-138
             sem.setInitialCondition([&](const double* x, double* Q) {

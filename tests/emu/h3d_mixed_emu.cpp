@@ -11,11 +11,17 @@
 // ======================================================================================================
 #include <math.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <map>
 #include <numeric>
 #include <random>
-#define __noinline__ __attribute__((noinline))
+#include <string>
+#include <utility>
+#include <vector>
+#define __noinline__      // a CUDA function qualifier of h3d_physics.cuh; empty so that no standard header can trip over it
 #include "h3d_mixed.cuh"
 
 using namespace h3d;

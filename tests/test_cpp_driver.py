@@ -68,6 +68,26 @@ def test_cpp_driver_reproduces_the_cylinder_wale_regression_with_the_oracle_back
     assert np.abs(final_line(r)["residuals"] - res).max() < 1.0e-7
 
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+K13_ARGS = ["--mesh", os.path.join(GOLDEN, "CylinderNSpol3_1elem_y.mesh"), "--order-file", os.path.join(GOLDEN, "OrdersN2N3N4N5_anisotropy.csv"), "--steps", 100,
+            "--cfl", 0.2, "--dcfl", 0.2, "--mach", 0.3, "--reynolds", 45, "--aoa-phi", 90, "--ic", "uniform", "--bc", "innercylinder:noslipwall",
+            "--bc", "bottom:freeslipwall", "--bc", "top:freeslipwall", "--bc", "back:inflow", "--bc", "left:inflow", "--bc", "front:inflow", "--bc", "right:outflow"]
+K13_RES = np.array([9.5806856005342933E+00, 2.0804408993372231E+01, 3.7668665836122439E-01, 2.8294964263463125E+01, 2.6470704194989690E+02])
+
+
+def test_cpp_driver_reproduces_the_different_orders_regression_with_the_oracle_backend():
+    """test/NavierStokes/CylinderDifferentOrders (K13) through the C++ driver: polynomial order file, p-nonconforming geometry, nodal
+    storages and interpolation matrices, h3d_set_mesh_p -- all built natively."""
+    f = final_line(run_driver("--lib", build.build_oracle(), "--prefix", "orc_", *K13_ARGS))
+    assert f["iter"] == 100 and np.abs(f["residuals"] - K13_RES).max() < 1.0e-11
+
+
+@pytest.mark.gpu
+def test_cpp_driver_reproduces_the_different_orders_regression_on_the_device():
+    f = final_line(run_driver("--lib", build.build_gpu(), *K13_ARGS))
+    assert f["iter"] == 100 and np.abs(f["residuals"] - K13_RES).max() < 1.0e-11
+
+
 def test_cpp_driver_fails_loudly_without_a_device_or_with_bad_options():
     import torch
     r = run_driver("--lib", "/nonexistent/libh3dgpu.so", check=False)
