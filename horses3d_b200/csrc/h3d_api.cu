@@ -1089,7 +1089,7 @@ int h3d_set_basis(h3d_handle h, int N, int nodeType, const double* x, const doub
     if (N < 1 || N >= MX_MAXN) { h->err = "polynomial order out of range (1..15)"; return 1; }
     // every order given stays registered: NodalStorage(N) of a p-nonconforming mesh (h3d_set_mesh_p)
     ensureMx(h)->setBasis(N, x, w, D, hatD, v, b);
-    if (N > 9) { h->haveBasis = false; return 0; }   // usable by h3d_set_mesh_p only: the uniform-order kernels are instantiated for N = 1..9
+    if (N > 9) { h->haveBasis = false; h->N = N; return 0; }   // usable by h3d_set_mesh_p only: the uniform-order kernels are instantiated for N = 1..9
     CTX_CHECK(cudaSetDevice(h->device));
     const int n = N + 1;
     h->N = N; h->n = n; h->nodeType = nodeType; h->hx.assign(x, x + n);
@@ -1137,6 +1137,7 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace, const int* elemFace, const 
                  const double* faceJacobian, const double* faceX, const double* faceSurface) {
     (void)x; (void)faceX; (void)faceElemSide;
     if (h->mixedMode) { h->err = "the context already holds a p-nonconforming mesh"; return 1; }
+    if (!h->haveBasis && h->N > 9) { h->err = "h3d_set_mesh: the uniform-order kernels are instantiated for N = 1..9 (h3d_set_mesh_p takes orders up to 15)"; return 1; }
     if (!h->haveBasis) { h->err = "h3d_set_basis must precede h3d_set_mesh"; return 1; }
     if (h->haveMesh) { h->err = "h3d_set_mesh may be called once per context"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));

@@ -13,7 +13,7 @@
 //  force monitor of the latter to 5e-10 where the reference asserts 1e-10), Euler/UniformFlow (K12, iterations to tolerance), NavierStokes/Cylinder, CylinderSmagorinsky, CylinderWALE and CylinderVreman (K5, K5b, K5e),
 //  CylinderDucros and CylinderChandrasekarRoe (K5c, K5d), CylinderBR2 and CylinderIP (K7, K8), TaylorGreenKEP_BR2 and
 //  TaylorGreenKEPEC_IP (K9), Convergence_energy and Convergence_entropy (K10, P=7), EnergyConservingTest and
-//  EntropyConservingTest (K11).  The reference itself cannot be built in this container (no Fortran compiler), so there is
+//  EntropyConservingTest (K11), NavierStokes/CylinderDifferentOrders (K13: element-wise anisotropic orders, h3d_oracle_p.inc).  The reference itself cannot be built in this container (no Fortran compiler), so there is
 //  no oracle/_ref; parity with the reference rests on those pins.
 // ======================================================================================================
 #include <algorithm>

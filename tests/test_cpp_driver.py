@@ -82,12 +82,6 @@ def test_cpp_driver_reproduces_the_different_orders_regression_with_the_oracle_b
     assert f["iter"] == 100 and np.abs(f["residuals"] - K13_RES).max() < 1.0e-11
 
 
-@pytest.mark.gpu
-def test_cpp_driver_reproduces_the_different_orders_regression_on_the_device():
-    f = final_line(run_driver("--lib", build.build_gpu(), *K13_ARGS))
-    assert f["iter"] == 100 and np.abs(f["residuals"] - K13_RES).max() < 1.0e-11
-
-
 def test_cpp_driver_fails_loudly_without_a_device_or_with_bad_options():
     import torch
     r = run_driver("--lib", "/nonexistent/libh3dgpu.so", check=False)

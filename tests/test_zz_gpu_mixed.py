@@ -1,5 +1,9 @@
 """p-nonconforming path on the device: libh3dgpu.so (h3d_set_mesh_p) against the oracle, through the C ABI.
-The same cases run on the CPU through the emulated kernels in tests/test_mixed_emu.py."""
+The same cases run on the CPU through the emulated kernels in tests/test_mixed_emu.py.
+
+The file name sorts last on purpose: this path was written in a session without GPU time (its kernels were checked through the
+host-loop backend only), so under `pytest -x` a failure here must not hide the results of the device tests that were verified
+on hardware."""
 import os
 import sys
 
@@ -104,3 +108,11 @@ def test_unsupported_entry_points_are_refused(gpu_api_cls):
             call()
     with pytest.raises(H3dError):
         DGSem(gpu_api_cls(), MC.periodic_box(2, 2, 3, seed=1, nodes=GAUSSLOBATTO), make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe", viscous="br2"))
+
+
+def test_cpp_driver_reproduces_the_different_orders_regression_on_the_device():
+    """K13 through the native C++ driver (polynomial order file, h3d_set_mesh_p) and libh3dgpu.so."""
+    from horses3d_b200 import build
+    from test_cpp_driver import K13_ARGS, K13_RES, final_line, run_driver
+    f = final_line(run_driver("--lib", build.build_gpu(), *K13_ARGS))
+    assert f["iter"] == 100 and np.abs(f["residuals"] - K13_RES).max() < 1.0e-11
