@@ -1,3 +1,11 @@
+"""Runs the emulated kernels of the p-nonconforming path (tests/emu) under AddressSanitizer:
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python scripts/asan_mixed_emu.py
+No report = no out-of-bounds access in the functors or the orchestration of horses3d_b200/csrc/h3d_mixed.cuh."""
+import subprocess
+ROOT = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-attributes",
+                       "-Wno-unknown-pragmas", "-I", "/usr/local/cuda/include", "-I", ROOT + "/include", "-I", ROOT + "/horses3d_b200/csrc",
+                       ROOT + "/tests/emu/h3d_mixed_emu.cpp", "-o", "/tmp/libh3dmixedemu_asan.so"])
 import sys, os
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 from emu import emu_api

@@ -31,7 +31,31 @@ CASES = {
 }
 
 
+# p-nonconforming meshes: random anisotropic element orders on the curved, re-oriented box (tests/mixed_cases.py)
+CASES_MIXED = {
+    "box_ns_mixed_p2to4": dict(bc=None, lo=2, hi=4, kw=dict(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")),
+    "channel_ns_mixed_p2to4": dict(bc="channel", lo=2, hi=4, kw=dict(flow="NS", mach=0.3, reynolds=150.0, riemann="roe")),
+    "box_euler_mixed_p1to5": dict(bc=None, lo=1, hi=5, kw=dict(flow="Euler", mach=0.3, riemann="standard roe")),
+}
+
+
+def run_mixed(api, name):
+    import mixed_cases as MC
+    c = CASES_MIXED[name]
+    phys = make_physics(**c["kw"])
+    mesh = MC.channel(phys, 2, c["lo"], c["hi"], seed=3) if c["bc"] else MC.periodic_box(2, c["lo"], c["hi"], seed=5)
+    sem = DGSem(api, mesh, phys)
+    sem.set_Q(MC.smooth_state(sem, phys.Mach))
+    sem.ComputeTimeDerivative(0.0)
+    out = sem.download(Q=True, QDot=True, gradients=bool(phys.computeGradients))
+    sem.TakeRK3Step(0.0, 1.0e-3)
+    out["Q_after_rk3"] = sem.Q()
+    return out
+
+
 def run(api, name):
+    if name in CASES_MIXED:
+        return run_mixed(api, name)
     c = CASES[name]
     phys = make_physics(**c["kw"])
     mesh = get_mesh(c["ne"], c["N"], c["nodes"], 0.1, True, bc=c["bc"], phys=phys)
@@ -46,7 +70,9 @@ def run(api, name):
 
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
-    for name in CASES:
+    for name in list(CASES) + list(CASES_MIXED):
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         out = run(OracleApi(), name)
         np.savez_compressed(os.path.join(here, name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items()})

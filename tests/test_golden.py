@@ -6,8 +6,9 @@ import sys
 import numpy as np
 import pytest
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_golden import CASES, run  # noqa: E402
+from make_golden import CASES, CASES_MIXED, run  # noqa: E402
 from oracle.oracle_api import OracleApi  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -27,6 +28,15 @@ def check(api, name, exact):
 @pytest.mark.parametrize("name", list(CASES))
 def test_oracle_reproduces_golden(name):
     check(OracleApi(), name, exact=True)
+
+
+@pytest.mark.parametrize("name", list(CASES_MIXED))
+def test_oracle_and_emulated_kernels_reproduce_golden_mixed(name):
+    """p-nonconforming fixtures: the oracle and the device functors on the host-loop backend (tests/emu), bit for bit.  The device
+    itself is checked against the same fixtures in tests/test_zz_gpu_mixed.py."""
+    from emu.emu_api import EmuApi
+    check(OracleApi(), name, exact=True)
+    check(EmuApi(), name, exact=True)
 
 
 @pytest.mark.gpu

@@ -116,3 +116,10 @@ def test_cpp_driver_reproduces_the_different_orders_regression_on_the_device():
     from test_cpp_driver import K13_ARGS, K13_RES, final_line, run_driver
     f = final_line(run_driver("--lib", build.build_gpu(), *K13_ARGS))
     assert f["iter"] == 100 and np.abs(f["residuals"] - K13_RES).max() < 1.0e-11
+
+
+@pytest.mark.parametrize("name", ["box_ns_mixed_p2to4", "channel_ns_mixed_p2to4", "box_euler_mixed_p1to5"])
+def test_device_reproduces_golden_mixed(gpu_api_cls, name):
+    """The frozen oracle outputs of tests/golden (made by make_golden.py) through libh3dgpu.so."""
+    from test_golden import check
+    check(gpu_api_cls(), name, exact=False)
