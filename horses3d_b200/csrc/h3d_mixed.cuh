@@ -32,6 +32,7 @@
 #include <utility>
 #include <vector>
 
+#include "h3d_phys_host.hpp"
 #include "h3d_physics.cuh"
 
 namespace h3d {

@@ -6,8 +6,6 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include <string>
-
 #include "h3d_gpu.h"
 
 namespace h3d {
@@ -20,25 +18,6 @@ struct Phys {   // by-value kernel parameter (a trimmed H3dPhysics)
     int viscous, ipVariant;   // H3D_VISCOUS_*, IP variant -1 / 0 / 1
     int gradVars;             // H3D_GRADVARS_*
 };
-
-// h3d_set_physics: validation of the run-time physics (the reference's error messages) and the kernel parameter made from it
-inline int physFromH3dPhysics(const H3dPhysics* p, Phys& q, std::string& err) {
-    if (p->riemann < H3D_RIEMANN_ROE || p->riemann > H3D_RIEMANN_MATRIXDISS) { err = "Riemann Solver not recognized."; return 1; }
-    if (p->averaging < H3D_AVG_STANDARD || p->averaging > H3D_AVG_CHANDRASEKAR) { err = "Averaging not recognized."; return 1; }
-    if (p->inviscid != H3D_STANDARD_DG && p->inviscid != H3D_SPLIT_DG) { err = "Requested inviscid discretization is not implemented."; return 1; }
-    if (p->viscous < H3D_VISCOUS_BR1 || p->viscous > H3D_VISCOUS_IP) { err = "Requested viscous discretization is not implemented."; return 1; }
-    if (p->ipVariant < -1 || p->ipVariant > 1) { err = "Unknown selected IP variant."; return 1; }
-    if (p->gradientVariables < H3D_GRADVARS_STATE || p->gradientVariables > H3D_GRADVARS_ENERGY) { err = "Gradient variables are not currently implemented."; return 1; }
-    if (p->les < H3D_LES_NONE || p->les > H3D_LES_VREMAN) { err = "LES model not recognized."; return 1; }
-    if (p->les_wall_model != 0 && p->les_wall_model != 1) { err = "LES wall model not recognized."; return 1; }
-    q.gamma = p->gamma; q.gm1 = p->gammaMinus1; q.gammaM2 = p->gammaM2; q.mu = p->mu; q.mu_to_kappa = p->mu_to_kappa;
-    q.S_div_Tref = p->S_div_Tref; q.T_renorm = p->T_renorm; q.lambdaStab = p->lambdaStab; q.Cs = p->smagorinsky_Cs;
-    q.ns = p->flowIsNavierStokes; q.riemann = p->riemann; q.averaging = p->averaging; q.les = p->les;
-    q.viscous = p->flowIsNavierStokes ? p->viscous : H3D_VISCOUS_BR1; q.ipVariant = p->ipVariant; q.eta = p->penaltyParameter;
-    q.gradVars = p->flowIsNavierStokes ? p->gradientVariables : H3D_GRADVARS_STATE;
-    q.wallModel = (p->les != H3D_LES_NONE && p->les_wall_model == 1) ? 1 : 0;
-    return 0;
-}
 
 __device__ __forceinline__ double pow2(double x) { return x * x; }
 
