@@ -35,7 +35,7 @@ class Binding:
         "set_basis": [C.c_int, C.c_int] + [_D] * 7,
         "set_mesh": [C.c_int, C.c_int] + [_D] * 19,
         "set_interpolation": [C.c_int, C.c_int, _D],
-        "set_mesh_p": [C.c_int, C.c_int] + [_D] * 20,
+        "set_mesh_p": [C.c_int, C.c_int] + [_D] * 21,
         "set_boundary_conditions": [C.c_int, _D, _D],
         "set_wall_distance": [_D, _D],
         "set_face_h": [_D],
@@ -107,7 +107,7 @@ class Api:
         nE, nF = m.nElem, m.nFaces
         I = lambda k: _ptr(m.array(k), np.int32)
         Dp = lambda k: _ptr(m.array(k), np.float64)
-        self.call("set_mesh_p", nE, nF, I("elemOrder"), I("elemFace"), I("elemFaceSide"), I("faceElem"), I("faceElemSide"), I("faceRot"),
+        self.call("set_mesh_p", nE, nF, I("elemOrder"), I("faceOrder"), I("elemFace"), I("elemFaceSide"), I("faceElem"), I("faceElemSide"), I("faceRot"),
                   I("faceType"), I("faceZone"), Dp("jGradXi"), Dp("jGradEta"), Dp("jGradZeta"), Dp("jacobian"), Dp("x"), Dp("volume"),
                   Dp("faceNormal"), Dp("faceT1"), Dp("faceT2"), Dp("faceJacobian"), Dp("faceX"), Dp("faceSurface"))
 

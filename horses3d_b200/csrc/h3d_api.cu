@@ -49,6 +49,26 @@ struct CudaBackend {
         k_mx<F><<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(f, count);
         note(cudaGetLastError(), "kernel launch");
     }
+    // MPI faces: one ncclSend / ncclRecv pair per neighbour in a group, in stream order with the pack and unpack kernels
+    ncclComm_t comm = nullptr; double* dScal = nullptr;
+    void noteNccl(ncclResult_t r, const char* what) { if (r != ncclSuccess && !failed) { failed = true; msg = std::string(what) + ": " + ncclGetErrorString(r); } }
+    void exchange(const double* send, double* recv, int nNbr, const int* ranks, const long long* off, const long long* cnt) {
+        if (nNbr == 0) return;
+        noteNccl(ncclGroupStart(), "ncclGroupStart");
+        for (int b = 0; b < nNbr; ++b) {
+            noteNccl(ncclSend(send + off[b], (size_t)cnt[b], ncclDouble, ranks[b], comm, stream), "ncclSend");
+            noteNccl(ncclRecv(recv + off[b], (size_t)cnt[b], ncclDouble, ranks[b], comm, stream), "ncclRecv");
+        }
+        noteNccl(ncclGroupEnd(), "ncclGroupEnd");
+    }
+    void allreduce(double* v, int n, int op) {   // host scalars: through a small device buffer
+        if (!dScal) dScal = alloc<double>(16);
+        if (!dScal || n > 16) { if (!failed) { failed = true; msg = "allreduce scratch"; } return; }
+        note(cudaMemcpyAsync(dScal, v, n * sizeof(double), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync (allreduce)");
+        noteNccl(ncclAllReduce(dScal, dScal, n, ncclDouble, op == 0 ? ncclMax : (op == 1 ? ncclMin : ncclSum), comm, stream), "ncclAllReduce");
+        note(cudaMemcpyAsync(v, dScal, n * sizeof(double), cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync (allreduce)");
+        note(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    }
     const char* error() { return failed ? msg.c_str() : nullptr; }
 };
 }  // namespace h3d
@@ -156,7 +176,10 @@ struct h3d_context {
 namespace {
 
 MixedSolver<CudaBackend>* ensureMx(h3d_context* h) {
-    if (!h->mx) { CudaBackend be; be.stream = h->sCompute; be.allocs = &h->allocs; h->mx = new MixedSolver<CudaBackend>(be); }
+    if (!h->mx) {
+        CudaBackend be; be.stream = h->sCompute; be.allocs = &h->allocs; be.comm = h->comm;
+        h->mx = new MixedSolver<CudaBackend>(be); h->mx->nranks = h->nranks;
+    }
     return h->mx;
 }
 // result of a MixedSolver call -> the context's error state
@@ -1258,7 +1281,7 @@ int h3d_set_interpolation(h3d_handle h, int Norigin, int Ndest, const double* T)
     return mxDone(h, ensureMx(h)->setInterpolation(Norigin, Ndest, T));
 }
 
-int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder, const int* faceOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
                    const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone,
                    const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,
                    const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
@@ -1266,13 +1289,12 @@ int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder, con
     (void)x; (void)volume; (void)faceX; (void)faceSurface;   // sources and LES widths are not part of this path
     if (!h->havePhysics) { h->err = "h3d_set_physics must precede h3d_set_mesh_p"; return 1; }
     if (h->haveMesh || h->mixedMode) { h->err = "the context already holds a mesh"; return 1; }
-    if (h->nranks > 1) { h->err = "p-nonconforming meshes are single-domain"; return 1; }
     if (!elemOrder || !elemFace || !elemFaceSide || !faceElem || !faceElemSide || !faceRot || !faceType || !faceZone || !jGradXi || !jGradEta ||
         !jGradZeta || !jacobian || !faceNormal || !faceT1 || !faceT2 || !faceJacobian) { h->err = "h3d_set_mesh_p: null array"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     MixedSolver<CudaBackend>* mx = ensureMx(h);
     mx->ph = h->ph;
-    int rc = mx->setMesh(h->physics, nElem, nFace, elemOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone,
+    int rc = mx->setMesh(h->physics, nElem, nFace, elemOrder, faceOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone,
                          jGradXi, jGradEta, jGradZeta, jacobian, faceNormal, faceT1, faceT2, faceJacobian);
     if (rc) return mxDone(h, rc);
     h->mixedMode = true; h->nElem = nElem; h->nFace = nFace;
@@ -1332,7 +1354,11 @@ int h3d_set_boundary_conditions(h3d_handle h, int nZones, const int* bcType, con
 }
 
 int h3d_set_halo(h3d_handle h, int nNeighbors, const int* neighborRank, const int* faceCount, const int* faceIDs, const int* thisSide) {
-    MX_UNSUPPORTED("the MPI face exchange");
+    if (h->mixedMode) {
+        if (nNeighbors > 0 && h->nranks < 2) { h->err = "halo given but the context has a single rank"; return 1; }
+        CTX_CHECK(cudaSetDevice(h->device));
+        return mxDone(h, h->mx->setHalo(nNeighbors, neighborRank, faceCount, faceIDs, thisSide));
+    }
     if (!h->haveMesh) { h->err = "h3d_set_mesh must precede h3d_set_halo"; return 1; }
     if (nNeighbors > 0 && h->nranks < 2) { h->err = "halo given but the context has a single rank"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));

@@ -20,8 +20,8 @@
 // and the orchestration is a template over a backend (allocate / copy / launch): libh3dgpu.so instantiates it with the CUDA
 // backend; tests/emu instantiates the SAME functors and orchestration with a host loop as the launcher, which is how this path
 // is checked against the oracle where no GPU is present (test infrastructure, never shipped).
-// Scope: StandardDG, BR1 (or Euler), any Riemann solver / boundary condition / gradient variables of h3d_physics.cuh, no LES,
-// single domain.  Reductions are computed per element (face) in the reference's node order and finished on the host in element
+// Scope: StandardDG, BR1 (or Euler), any Riemann solver / boundary condition / gradient variables of h3d_physics.cuh, no LES.
+// Partitioned meshes: the traces of the MPI faces are exchanged at the face order (h3d_set_halo), scalars are all-reduced.  Reductions are computed per element (face) in the reference's node order and finished on the host in element
 // order, so that they reproduce the oracle's sums bit for bit.
 #pragma once
 #include <algorithm>
@@ -75,6 +75,14 @@ struct MixedDev {
     const int* bcType; const double* bcParams;
     // ---- reductions
     double* partial;                        // [max(nElem, nFace)][8]
+    // ---- MPI faces (h3d_set_halo): halo face k = haloFace[k], local side haloSide[k]; its nodes are the halo nodes
+    //      [hOff[k], hOff[k+1]); neighbour b owns the halo nodes [nbrNodeOff[b], nbrNodeOff[b+1]) (faces in exchange order)
+    int nHalo, nNbr; long long nHaloNodes;
+    const int *haloFace, *haloSide, *haloNbr;   // [nHalo]
+    const long long* hOff;                      // [nHalo + 1]
+    const int* hNodeFace;                       // [nHaloNodes] halo face of every halo node
+    const long long* nbrNodeOff;                // [nNbr + 1]
+    double *sendBuf, *recvBuf;                  // [15 nHaloNodes]
 };
 
 struct MxRk { int mode; double a, cdt, b; int copyG; };   // as RkArgs (h3d_kernels.cuh): 0 residual only, 1 low storage, 2 SSP
@@ -152,7 +160,7 @@ struct MxAdapt {
     __device__ void operator()(long long t) const {
         const int side = (int)(t / m.nFaceNodes); const long long g = t % m.nFaceNodes;
         const int f = m.faceNodeFace[g];
-        if (side == 1 && m.faceType[f] != H3D_FACE_INTERIOR) return;
+        if (m.faceElem[2 * f + side] < 0) return;      // boundary face, or the remote side of an MPI face (filled by the exchange)
         const int* fo = m.fo + 6 * f;
         const int Nf1 = fo[0], Ns1 = fo[2 + 2 * side], Ns2 = fo[3 + 2 * side];
         const int local = (int)(g - m.fOff[f]), i = local % (Nf1 + 1), j = local / (Nf1 + 1);
@@ -219,7 +227,7 @@ struct MxGradFace {
         for (int d = 0; d < 3; ++d) nh[d] = m.fN[(long long)d * m.nFaceNodes + g];
         const double Jf = m.fJ[g];
         get_gradients(ph, QL, UL);
-        if (m.faceType[f] == H3D_FACE_INTERIOR) {
+        if (m.faceType[f] != H3D_FACE_BOUNDARY) {      // interior and MPI faces (BR1_ComputeMPIFaceAverage, EllipticBR1.f90:629-684)
             double QR[5];
             for (int q = 0; q < 5; ++q) QR[q] = m.fQ[(long long)(5 + q) * m.nFaceNodes + g];
             get_gradients(ph, QR, UR);
@@ -335,7 +343,7 @@ struct MxRiemann {
         const double Jf = m.fJ[g];
         for (int q = 0; q < 5; ++q) QL[q] = m.fQ[q * fs + g];
         double gx[5], gy[5], gz[5], mu, kappa;
-        if (m.faceType[f] == H3D_FACE_INTERIOR) {
+        if (m.faceType[f] != H3D_FACE_BOUNDARY) {      // interior and MPI faces (computeMPIFaceFlux, SpatialDiscretization.f90:1801-1894)
             for (int q = 0; q < 5; ++q) QR[q] = m.fQ[(5 + q) * fs + g];
             if (ph.ns) {   // BR1_RiemannSolver (EllipticBR1.f90:816-868)
                 double FL[5][3], FR[5][3];
@@ -365,6 +373,23 @@ struct MxRiemann {
         }
         riemann_solver<true>(ph, QL, QR, nh, t1, t2, inv);
         for (int q = 0; q < 5; ++q) m.fFlux[q * fs + g] = (inv[q] - visc[q]) * Jf;
+    }
+};
+
+// ---- MPI faces: HexMesh_UpdateMPIFacesSolution / ...Gradients (HexMesh.f90:1199-1391): the local side's traces at the face
+//      order go to the neighbour, which stores them as ITS remote side (both ranks hold the face frame of the global face).
+//      nSets field sets of 5 (Q: 1; gradients: 3, set stride 10 fields).  Message of neighbour b: [set][c][node of b].
+struct MxHaloPack {
+    MixedDev m; int nSets; const double* src; double* buf; int remote;   // remote = 0: pack the local side; 1: unpack into the remote side
+    __device__ void operator()(long long hn) const {
+        const int k = m.hNodeFace[hn], f = m.haloFace[k], side = remote ? 1 - m.haloSide[k] : m.haloSide[k], b = m.haloNbr[k];
+        const long long g = m.fOff[f] + (hn - m.hOff[k]);
+        const long long nb = m.nbrNodeOff[b + 1] - m.nbrNodeOff[b], base = (long long)nSets * 5 * m.nbrNodeOff[b] + (hn - m.nbrNodeOff[b]);
+        for (int st = 0; st < nSets; ++st) for (int c = 0; c < 5; ++c) {
+            double* fld = const_cast<double*>(src) + (long long)(st * 10 + side * 5 + c) * m.nFaceNodes + g;
+            double* msg = buf + base + (long long)(st * 5 + c) * nb;
+            if (remote) *fld = *msg; else *msg = *fld;
+        }
     }
 };
 
@@ -569,6 +594,8 @@ struct MxProbe {   // Probe_Update (Probe.f90:330-420); Lagrange vectors padded 
 //  Orchestration, shared by the CUDA backend (libh3dgpu.so) and the host-loop backend of tests/emu.
 //  Backend B:  template <class T> T* alloc(size_t);  void upload(T* dst, const T* src, size_t);  void download(T* dst, const T* src, size_t)
 //              (both synchronous);  template <class F> void launch(const F&, long long count);  const char* error()  (nullptr = ok)
+//              void exchange(const double* send, double* recv, int nNbr, const int* ranks, const long long* offset, const long long* count)
+//              (device buffers, doubles; in order with the launches);  void allreduce(double* hostValues, int n, int op)  (0 max, 1 min, 2 sum)
 // ============================================================================================================================
 struct MxBasis { int N = -1; std::vector<double> x, w, D, hatD, v, b; };
 
@@ -604,10 +631,12 @@ struct MixedSolver {
     std::string err;
     std::map<int, MxBasis> sp;                                   // NodalStorage(N)
     std::map<std::pair<int, int>, std::vector<double>> T;        // Tset(Norigin, Ndest)
-    bool haveMesh = false, haveBC = false;
-    int nBoundaryFaces = 0, maxZone = -1, nZones = 0, maxNodes1D = 0;
+    bool haveMesh = false, haveBC = false, haveHalo = false;
+    int nBoundaryFaces = 0, maxZone = -1, nZones = 0, maxNodes1D = 0, nMpiFaces = 0, nranks = 1;
+    std::vector<int> nbrRank; std::vector<long long> nbrNodeOff;   // neighbours and their halo-node ranges (host copies)
     long long launches = 0;
-    std::vector<long long> hEOff;
+    std::vector<long long> hEOff, hFOff;
+    std::vector<int> hFo, hFaceType, hFaceElem;
     std::vector<double> hPartial, hBuf;
     double* dSource = nullptr;
     int* dProbeI = nullptr; double* dProbeD = nullptr; size_t probeCap = 0;
@@ -648,7 +677,9 @@ struct MixedSolver {
         for (size_t g = 0; g < nn; ++g) for (int c = 0; c < C; ++c) out[(size_t)c * nn + g] = src[g * C + c];
     }
 
-    int setMesh(const H3dPhysics& physics, int nElem, int nFace, const int* elemOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+    // faceOrder (may be null on a single rank): f % Nf, NfLeft, NfRight of every face, [nFace][6]; needed for MPI faces, whose remote
+    // element is not in this partition (the reference exchanges it, HexMesh_UpdateMPIFacesPolynomial)
+    int setMesh(const H3dPhysics& physics, int nElem, int nFace, const int* elemOrder, const int* faceOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
                 const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone, const double* jGradXi, const double* jGradEta,
                 const double* jGradZeta, const double* jacobian, const double* faceNormal, const double* faceT1, const double* faceT2, const double* faceJacobian) {
         if (physics.inviscid != H3D_STANDARD_DG) return fail("p-nonconforming meshes: the split-form discretization is not available (StandardDG only)");
@@ -669,25 +700,42 @@ struct MixedSolver {
             static const int ax[6][2] = {{0, 2}, {0, 2}, {0, 1}, {1, 2}, {0, 1}, {1, 2}};
             for (int lf = 0; lf < 6; ++lf) tOff[6 * e + lf + 1] = tOff[6 * e + lf] + (long long)eN[3 * e + ax[lf][0]] * eN[3 * e + ax[lf][1]];
         }
-        nBoundaryFaces = 0; maxZone = -1;
+        nBoundaryFaces = 0; maxZone = -1; nMpiFaces = 0;
         for (int f = 0; f < nFace; ++f) {   // Face_LinkWithElements (FaceClass.f90:187-282)
-            if (faceType[f] == H3D_FACE_MPI) return fail("p-nonconforming meshes are single-domain: MPI faces are not supported");
-            if (faceType[f] != H3D_FACE_INTERIOR && faceType[f] != H3D_FACE_BOUNDARY) return fail("h3d_set_mesh_p: unknown face type");
+            if (faceType[f] != H3D_FACE_INTERIOR && faceType[f] != H3D_FACE_BOUNDARY && faceType[f] != H3D_FACE_MPI) return fail("h3d_set_mesh_p: unknown face type");
             static const int ax[6][2] = {{0, 2}, {0, 2}, {0, 1}, {1, 2}, {0, 1}, {1, 2}};
-            const int eL = faceElem[2 * f], lfL = faceElemSide[2 * f];
-            if (eL < 0 || eL >= nElem || lfL < 0 || lfL > 5) return fail("h3d_set_mesh_p: face without a left element");
-            int NelL[2] = {elemOrder[3 * eL + ax[lfL][0]], elemOrder[3 * eL + ax[lfL][1]]}, NelR[2] = {NelL[0], NelL[1]};
-            if (faceType[f] == H3D_FACE_INTERIOR) {
-                const int eR = faceElem[2 * f + 1], lfR = faceElemSide[2 * f + 1];
-                if (eR < 0 || eR >= nElem || lfR < 0 || lfR > 5) return fail("h3d_set_mesh_p: interior face without a right element");
-                NelR[0] = elemOrder[3 * eR + ax[lfR][0]]; NelR[1] = elemOrder[3 * eR + ax[lfR][1]];
-            } else { ++nBoundaryFaces; maxZone = std::max(maxZone, faceZone[f]); if (faceZone[f] < 0) return fail("h3d_set_mesh_p: boundary face without a zone"); }
             const int rot = faceRot[f];
             if (rot < 0 || rot > 7) return fail("h3d_set_mesh_p: face rotation out of range");
-            int NfR[2] = {NelR[0], NelR[1]};
-            if (rot == 1 || rot == 3 || rot == 4 || rot == 6) { NfR[0] = NelR[1]; NfR[1] = NelR[0]; }
+            const bool swapR = rot == 1 || rot == 3 || rot == 4 || rot == 6;
             int* o = &fo[6 * (size_t)f];
-            o[0] = std::max(NelL[0], NfR[0]); o[1] = std::max(NelL[1], NfR[1]); o[2] = NelL[0]; o[3] = NelL[1]; o[4] = NfR[0]; o[5] = NfR[1];
+            // the orders of a side from its element: side 0 as they are, side 1 in the face frame (swapped for the odd rotations)
+            auto sideOrders = [&](int side, int out[2]) -> bool {
+                const int e = faceElem[2 * f + side], lf = faceElemSide[2 * f + side];
+                if (e < 0 || e >= nElem || lf < 0 || lf > 5) return false;
+                const int a = elemOrder[3 * e + ax[lf][0]], b = elemOrder[3 * e + ax[lf][1]];
+                out[0] = (side && swapR) ? b : a; out[1] = (side && swapR) ? a : b;
+                return true;
+            };
+            int NfL[2], NfR[2];
+            if (faceType[f] == H3D_FACE_MPI) {
+                if (nranks < 2) return fail("h3d_set_mesh_p: MPI faces on a single rank");
+                if (!faceOrder) return fail("h3d_set_mesh_p: a mesh with MPI faces needs the face orders (faceOrder): the remote element is not in this partition");
+                ++nMpiFaces;
+                const bool hasL = faceElem[2 * f] >= 0, hasR = faceElem[2 * f + 1] >= 0;
+                if (hasL == hasR) return fail("h3d_set_mesh_p: an MPI face has exactly one local side");
+                for (int q = 0; q < 6; ++q) o[q] = faceOrder[6 * (size_t)f + q];
+                int own[2];
+                if (!sideOrders(hasL ? 0 : 1, own) || own[0] != o[hasL ? 2 : 4] || own[1] != o[hasL ? 3 : 5]) return fail("h3d_set_mesh_p: faceOrder of an MPI face contradicts the order of its local element");
+                for (int q = 0; q < 6; ++q) if (o[q] < 1 || o[q] >= MX_MAXN) return fail("h3d_set_mesh_p: face orders must lie in 1..15");
+                if (o[0] != std::max(o[2], o[4]) || o[1] != std::max(o[3], o[5])) return fail("h3d_set_mesh_p: the order of a face is the maximum of its two sides");
+            } else {
+                if (!sideOrders(0, NfL)) return fail("h3d_set_mesh_p: face without a left element");
+                NfR[0] = NfL[0]; NfR[1] = NfL[1];                         // boundary: NelRight = NelLeft (HexMesh.f90:2470-2472)
+                if (faceType[f] == H3D_FACE_INTERIOR) { if (!sideOrders(1, NfR)) return fail("h3d_set_mesh_p: interior face without a right element"); }
+                else { ++nBoundaryFaces; maxZone = std::max(maxZone, faceZone[f]); if (faceZone[f] < 0) return fail("h3d_set_mesh_p: boundary face without a zone"); }
+                o[0] = std::max(NfL[0], NfR[0]); o[1] = std::max(NfL[1], NfR[1]); o[2] = NfL[0]; o[3] = NfL[1]; o[4] = NfR[0]; o[5] = NfR[1];
+                if (faceOrder) for (int q = 0; q < 6; ++q) if (faceOrder[6 * (size_t)f + q] != o[q]) return fail("h3d_set_mesh_p: faceOrder contradicts the orders of the elements");
+            }
             for (int s = 0; s < 2; ++s) {
                 proj[2 * f + s] = (o[2 + 2 * s] != o[0] ? 1 : 0) + (o[3 + 2 * s] != o[1] ? 2 : 0);
                 for (int d = 0; d < 2; ++d) if (o[2 + 2 * s + d] != o[d] && (!T.count({o[2 + 2 * s + d], o[d]}) || !T.count({o[d], o[2 + 2 * s + d]})))
@@ -701,7 +749,8 @@ struct MixedSolver {
         for (int e = 0; e < nElem; ++e) for (long long g = eOff[e]; g < eOff[e + 1]; ++g) nodeElem[g] = e;
         for (int s = 0; s < 6 * nElem; ++s) for (long long g = tOff[s]; g < tOff[s + 1]; ++g) traceOwner[g] = s;
         for (int f = 0; f < nFace; ++f) for (long long g = fOff[f]; g < fOff[f + 1]; ++g) faceNodeFace[g] = f;
-        hEOff = eOff;
+        hEOff = eOff; hFOff = fOff; hFo = fo; hFaceType.assign(faceType, faceType + nFace); hFaceElem.assign(faceElem, faceElem + 2 * (size_t)nFace);
+        m.nHalo = 0; m.nNbr = 0; m.nHaloNodes = 0;
         // operators and interpolation matrices
         std::vector<double> ops, ts;
         for (int N = 0; N < MX_MAXN; ++N) {
@@ -754,8 +803,49 @@ struct MixedSolver {
         nZones = nZ; haveBC = true;
         return 0;
     }
+    // MPIfaces (MPI_Face.f90:16-57; HexMesh.f90:2571-2668): per neighbour the local MPI faces in exchange order and the local side
+    int setHalo(int nNeighbors, const int* neighborRank, const int* faceCount, const int* faceIDs, const int* thisSide) {
+        if (!haveMesh) return fail("h3d_set_mesh_p must precede h3d_set_halo");
+        const std::vector<long long>& fOff = hFOff; const std::vector<int>& faceType = hFaceType; const std::vector<int>& faceElem = hFaceElem;
+        int nHalo = 0;
+        for (int b = 0; b < nNeighbors; ++b) { if (faceCount[b] < 1 || neighborRank[b] < 0 || neighborRank[b] >= nranks) return fail("h3d_set_halo: bad neighbour table"); nHalo += faceCount[b]; }
+        if (nHalo != nMpiFaces) return fail("h3d_set_halo: the halo must list every MPI face of the mesh exactly once");
+        std::vector<int> hFace(faceIDs, faceIDs + nHalo), hSide(thisSide, thisSide + nHalo), hNbr(nHalo), hNodeFace;
+        std::vector<long long> hOff(nHalo + 1, 0);
+        std::vector<char> seen(m.nFace, 0);
+        nbrRank.assign(neighborRank, neighborRank + nNeighbors); nbrNodeOff.assign(nNeighbors + 1, 0);
+        int k = 0;
+        for (int b = 0; b < nNeighbors; ++b) {
+            for (int q = 0; q < faceCount[b]; ++q, ++k) {
+                const int f = hFace[k];
+                if (f < 0 || f >= m.nFace || faceType[f] != H3D_FACE_MPI || seen[f]) return fail("h3d_set_halo: a halo face is not an MPI face of the mesh (or is listed twice)");
+                if (hSide[k] < 0 || hSide[k] > 1 || faceElem[2 * f + hSide[k]] < 0) return fail("h3d_set_halo: thisSide is not the side of the local element");
+                seen[f] = 1; hNbr[k] = b;
+                hOff[k + 1] = hOff[k] + (fOff[f + 1] - fOff[f]);
+                for (long long g = hOff[k]; g < hOff[k + 1]; ++g) hNodeFace.push_back(k);
+            }
+            nbrNodeOff[b + 1] = hOff[k];
+        }
+        m.nHalo = nHalo; m.nNbr = nNeighbors; m.nHaloNodes = hOff[nHalo];
+        if (up(hFace, &m.haloFace) || up(hSide, &m.haloSide) || up(hNbr, &m.haloNbr) || up(hOff, &m.hOff) || up(hNodeFace, &m.hNodeFace) || up(nbrNodeOff, &m.nbrNodeOff)) return 2;
+        if (field(&m.sendBuf, 15 * (size_t)m.nHaloNodes) || field(&m.recvBuf, 15 * (size_t)m.nHaloNodes)) return 2;
+        haveHalo = true;
+        return 0;
+    }
+    // the local side's traces of every MPI face to the neighbours, theirs into the remote side (nSets field sets of 5, set stride 10 fields)
+    int exchange(int nSets, double* faceField) {
+        if (nranks < 2) return 0;
+        // every rank calls the backend, also one without neighbours (a backend may synchronise all ranks)
+        if (haveHalo) launch(MxHaloPack{m, nSets, faceField, m.sendBuf, 0}, m.nHaloNodes);
+        std::vector<long long> off(nbrRank.size()), cnt(nbrRank.size());
+        for (size_t b = 0; b < nbrRank.size(); ++b) { off[b] = (long long)nSets * 5 * nbrNodeOff[b]; cnt[b] = (long long)nSets * 5 * (nbrNodeOff[b + 1] - nbrNodeOff[b]); }
+        be.exchange(m.sendBuf, m.recvBuf, (int)nbrRank.size(), nbrRank.data(), off.data(), cnt.data());
+        if (haveHalo) launch(MxHaloPack{m, nSets, faceField, m.recvBuf, 1}, m.nHaloNodes);
+        return check();
+    }
     int ready() {
         if (!haveMesh) return fail("no mesh");
+        if (nMpiFaces > 0 && !haveHalo) return fail("mesh has MPI faces but h3d_set_halo was not called");
         if (nBoundaryFaces > 0 && !haveBC) return fail("mesh has boundary faces but h3d_set_boundary_conditions was not called");
         if (nBoundaryFaces > 0 && maxZone >= nZones) return fail("a boundary face refers to a zone beyond the table of h3d_set_boundary_conditions");
         return 0;
@@ -800,6 +890,7 @@ struct MixedSolver {
     int residual(const H3dPhysics& physics, const MxRk& rk) {
         if (ready()) return 1;
         prolong(m.Q, m.fQ);
+        if (exchange(1, m.fQ)) return 2;
         if (physics.computeGradients) {
             launch(MxLocalGrad{m, ph}, m.nNodes);
             if (physics.flowIsNavierStokes) {
@@ -808,6 +899,7 @@ struct MixedSolver {
                 launch(MxLift{m}, m.nNodes);
             }
             prolongGradients();
+            if (exchange(3, m.fU)) return 2;
         }
         launch(MxFlux{m, ph}, m.nNodes);
         launch(MxRiemann{m, ph}, m.nFaceNodes);
@@ -839,6 +931,7 @@ struct MixedSolver {
         if (partials(m.nElem)) return 2;
         double v[6] = {0, 0, 0, 0, 0, 0};
         for (int e = 0; e < m.nElem; ++e) for (int q = 0; q < 6; ++q) v[q] = std::fmax(v[q], hPartial[8 * (size_t)e + q]);
+        if (nranks > 1) { be.allreduce(v, 6, 0); if (check()) return 2; }
         for (int q = 0; q < 5; ++q) out[q] = v[q];
         *nanFlag = v[5] > 0.5 ? 1 : 0;
         return 0;
@@ -849,6 +942,7 @@ struct MixedSolver {
         if (partials(m.nElem)) return 2;
         double a = 1.7976931348623157e308, b = 1.7976931348623157e308;
         for (int e = 0; e < m.nElem; ++e) { a = std::fmin(a, hPartial[8 * (size_t)e]); b = std::fmin(b, hPartial[8 * (size_t)e + 1]); }
+        if (nranks > 1) { double ab[2] = {a, b}; be.allreduce(ab, 2, 1); if (check()) return 2; a = ab[0]; b = ab[1]; }
         *dtConv = a; *dtVisc = b;
         return 0;
     }
@@ -863,6 +957,7 @@ struct MixedSolver {
         if (partials(m.nElem)) return 2;
         double v = 0.0;
         for (int e = 0; e < m.nElem; ++e) v = v + hPartial[8 * (size_t)e];
+        if (nranks > 1) { be.allreduce(&v, 1, 2); if (check()) return 2; }
         *val = v;
         return 0;
     }
@@ -878,6 +973,7 @@ struct MixedSolver {
         if (partials(m.nFace)) return 2;
         double v[3] = {0, 0, 0};
         for (int f = 0; f < m.nFace; ++f) for (int d = 0; d < 3; ++d) v[d] = v[d] + hPartial[8 * (size_t)f + d];
+        if (nranks > 1) { be.allreduce(v, 3, 2); if (check()) return 2; }
         for (int d = 0; d < 3; ++d) out[d] = v[d];
         return 0;
     }

@@ -197,6 +197,11 @@ int h3dhost_partition(void* hp, int nparts, int method, int* part) {
     return partitionElements(h->mesh, nparts, method, part, g_err) ? 0 : 1;
 }
 
+int h3dhost_partition_weighted(void* hp, int nparts, int method, const int* vwgt, int* part) {
+    Host* h = (Host*)hp;
+    return partitionElements(h->mesh, nparts, method, part, g_err, vwgt) ? 0 : 1;
+}
+
 // Extracts the local mesh of `rank`: returns a new handle whose faces on partition cuts are HMESH_MPI
 // (single local side, rotation kept), with geometry rebuilt when the parent has it.  Halo tables are
 // exposed through h3dhost_get_array on the child: "haloRank","haloCount","haloFace","haloSide","globalElem".
@@ -215,6 +220,38 @@ void* h3dhost_extract_partition(void* hp, const int* part, int rank) {
 int h3dhost_inherit_geometry(void* childp, void* parentp) {
     Host* c = (Host*)childp; Host* p = (Host*)parentp;
     if (!p->hasGeom) { g_err = "parent mesh has no geometry"; return 1; }
+    if (p->mixed) {   // p-nonconforming: orders and packed arrays of the local elements / faces, cut faces keep the global face's orders
+        const HostGeometryP& G = p->geomP; HostGeometryP& g = c->geomP;
+        g = HostGeometryP(); g.nodeType = G.nodeType; g.meshIs2D = G.meshIs2D; g.anisotropic = G.anisotropic; g.sp = G.sp;
+        const size_t nE = c->halo.globalElem.size(), nF = c->halo.globalFace.size();
+        g.eOff.assign(nE + 1, 0); g.fOff.assign(nF + 1, 0);
+        for (size_t l = 0; l < nE; ++l) {
+            const int e = c->halo.globalElem[l];
+            g.elemOrder.insert(g.elemOrder.end(), &G.elemOrder[3 * (size_t)e], &G.elemOrder[3 * (size_t)e] + 3);
+            g.eOff[l + 1] = g.eOff[l] + (G.eOff[e + 1] - G.eOff[e]);
+            g.volume.push_back(G.volume[e]);
+        }
+        for (size_t l = 0; l < nF; ++l) {
+            const int f = c->halo.globalFace[l];
+            g.faceOrder.insert(g.faceOrder.end(), &G.faceOrder[6 * (size_t)f], &G.faceOrder[6 * (size_t)f] + 6);
+            g.fOff[l + 1] = g.fOff[l] + (G.fOff[f + 1] - G.fOff[f]);
+            g.fsurface.push_back(G.fsurface[f]);
+        }
+        auto gather = [&](const std::vector<double>& src, std::vector<double>& dst, const std::vector<long long>& offG, const std::vector<long long>& offL,
+                          const std::vector<int>& ids, size_t w) {
+            dst.resize((size_t)offL.back() * w);
+            for (size_t l = 0; l < ids.size(); ++l)
+                std::memcpy(&dst[(size_t)offL[l] * w], &src[(size_t)offG[ids[l]] * w], (size_t)(offL[l + 1] - offL[l]) * w * sizeof(double));
+        };
+        gather(G.x, g.x, G.eOff, g.eOff, c->halo.globalElem, 3); gather(G.jGradXi, g.jGradXi, G.eOff, g.eOff, c->halo.globalElem, 3);
+        gather(G.jGradEta, g.jGradEta, G.eOff, g.eOff, c->halo.globalElem, 3); gather(G.jGradZeta, g.jGradZeta, G.eOff, g.eOff, c->halo.globalElem, 3);
+        gather(G.jac, g.jac, G.eOff, g.eOff, c->halo.globalElem, 1); gather(G.invJac, g.invJac, G.eOff, g.eOff, c->halo.globalElem, 1);
+        gather(G.fx, g.fx, G.fOff, g.fOff, c->halo.globalFace, 3); gather(G.fnormal, g.fnormal, G.fOff, g.fOff, c->halo.globalFace, 3);
+        gather(G.ft1, g.ft1, G.fOff, g.fOff, c->halo.globalFace, 3); gather(G.ft2, g.ft2, G.fOff, g.fOff, c->halo.globalFace, 3);
+        gather(G.fjac, g.fjac, G.fOff, g.fOff, c->halo.globalFace, 1);
+        c->hasGeom = true; c->mixed = true;
+        return 0;
+    }
     const HostGeometry& G = p->geom; HostGeometry& g = c->geom;
     g.N = G.N; g.n = G.n; g.nodeType = G.nodeType; g.sp = G.sp;
     const size_t n3 = (size_t)G.n * G.n * G.n, n2 = (size_t)G.n * G.n;

@@ -37,7 +37,7 @@ struct Backend {
                     const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*,
                     const double*) = nullptr;
     int (*set_interpolation)(h3d_handle, int, int, const double*) = nullptr;
-    int (*set_mesh_p)(h3d_handle, int, int, const int*, const int*, const int*, const int*, const int*, const int*, const int*, const int*, const double*,
+    int (*set_mesh_p)(h3d_handle, int, int, const int*, const int*, const int*, const int*, const int*, const int*, const int*, const int*, const int*, const double*,
                       const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*, const double*,
                       const double*, const double*) = nullptr;
     int (*set_wall_distance)(h3d_handle, const double*, const double*) = nullptr;
@@ -184,7 +184,7 @@ public:
             interpolationMatrix(geomP.sp.at(a), geomP.sp.at(b), T); check(api.set_interpolation(h, a, b, T.data()));
             interpolationMatrix(geomP.sp.at(b), geomP.sp.at(a), T); check(api.set_interpolation(h, b, a, T.data()));
         }
-        check(api.set_mesh_p(h, mesh.nElem(), mesh.nFaces, geomP.elemOrder.data(), mesh.elemFace.data(), mesh.elemFaceSide.data(), mesh.faceElem.data(),
+        check(api.set_mesh_p(h, mesh.nElem(), mesh.nFaces, geomP.elemOrder.data(), geomP.faceOrder.data(), mesh.elemFace.data(), mesh.elemFaceSide.data(), mesh.faceElem.data(),
                              mesh.faceElemSide.data(), mesh.faceRot.data(), mesh.faceType.data(), mesh.faceZone.data(), geomP.jGradXi.data(), geomP.jGradEta.data(),
                              geomP.jGradZeta.data(), geomP.jac.data(), geomP.x.data(), geomP.volume.data(), geomP.fnormal.data(), geomP.ft1.data(), geomP.ft2.data(),
                              geomP.fjac.data(), geomP.fx.data(), geomP.fsurface.data()));

@@ -27,12 +27,17 @@ struct HaloInfo {
     std::vector<int> globalElem, globalFace;
 };
 
-inline bool partitionElements(const HostMesh& m, int nparts, int method, int* part, std::string& err) {
+// vwgt (may be null): one weight per element -- the reference passes the degrees of freedom of every element when the polynomial
+// orders are not uniform (METISPartitioning.f90:125-151)
+inline bool partitionElements(const HostMesh& m, int nparts, int method, int* part, std::string& err, const int* vwgt = nullptr) {
     const int nE = m.nElem();
     if (nparts < 1) { err = "nparts must be >= 1"; return false; }
     if (nparts == 1) { std::fill(part, part + nE, 0); return true; }
     if (method == 1) {
-        for (int e = 0; e < nE; ++e) part[e] = (int)(((long long)e * nparts) / nE);
+        if (!vwgt) { for (int e = 0; e < nE; ++e) part[e] = (int)(((long long)e * nparts) / nE); return true; }
+        long long total = 0, acc = 0;                        // contiguous blocks of (nearly) equal weight
+        for (int e = 0; e < nE; ++e) total += vwgt[e];
+        for (int e = 0; e < nE; ++e) { part[e] = (int)std::min<long long>(nparts - 1, (acc * nparts) / total); acc += vwgt[e]; }
         return true;
     }
 #ifdef H3D_HAS_METIS
@@ -40,7 +45,8 @@ inline bool partitionElements(const HostMesh& m, int nparts, int method, int* pa
     std::vector<int64_t> eptr(nE + 1), eind(m.elemNodes.begin(), m.elemNodes.end()), npart(nn), epart(nE), options(40);
     for (int e = 0; e <= nE; ++e) eptr[e] = 8 * (int64_t)e;
     METIS_SetDefaultOptions(options.data());
-    int rc = METIS_PartMeshDual(&ne, &nn, eptr.data(), eind.data(), nullptr, nullptr, &ncommon, &np, nullptr, options.data(), &objval, epart.data(), npart.data());
+    std::vector<int64_t> w; if (vwgt) w.assign(vwgt, vwgt + nE);
+    int rc = METIS_PartMeshDual(&ne, &nn, eptr.data(), eind.data(), vwgt ? w.data() : nullptr, nullptr, &ncommon, &np, nullptr, options.data(), &objval, epart.data(), npart.data());
     if (rc != 1) { err = "METIS_PartMeshDual failed"; return false; }
     for (int e = 0; e < nE; ++e) part[e] = (int)epart[e];
     return true;

@@ -38,6 +38,7 @@ def lib():
         L.h3dhost_get_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
         L.h3dhost_nodal.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 7
         L.h3dhost_partition.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.h3dhost_partition_weighted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.h3dhost_extract_partition.restype = C.c_void_p
         L.h3dhost_extract_partition.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.h3dhost_inherit_geometry.argtypes = [C.c_void_p, C.c_void_p]
@@ -213,8 +214,14 @@ class HostMesh:
 
     # --- partitioning
     def partition(self, nparts, method="metis"):
+        """Element -> rank.  A p-nonconforming mesh is partitioned with the elements' degrees of freedom as weights, as the reference
+        does when the orders are not uniform (METISPartitioning.f90:125-151)."""
         part = np.zeros(self.nElem, dtype=np.int32)
-        _check(lib().h3dhost_partition(self._h, nparts, 0 if method == "metis" else 1, part.ctypes.data))
+        if self.mixed:
+            w = np.ascontiguousarray(np.prod(self.orders + 1, axis=1), dtype=np.int32)
+            _check(lib().h3dhost_partition_weighted(self._h, nparts, 0 if method == "metis" else 1, w.ctypes.data, part.ctypes.data))
+        else:
+            _check(lib().h3dhost_partition(self._h, nparts, 0 if method == "metis" else 1, part.ctypes.data))
         return part
 
     def extract(self, part, rank, inherit_geometry=False):
@@ -225,8 +232,13 @@ class HostMesh:
         child.bcs = getattr(self, "bcs", [])
         child.bc_params = getattr(self, "bc_params", None)
         child.is_partition = True
+        if self.mixed and not inherit_geometry:
+            raise HostError("a partition of a p-nonconforming mesh takes its geometry from the global mesh: extract(..., inherit_geometry=True)")
         if inherit_geometry:
             _check(lib().h3dhost_inherit_geometry(child._h, self._h))
             child.N, child.nodes = self.N, self.nodes
             child.wall_global = self.wall_global
+            child.mixed = self.mixed
+            if self.mixed:
+                child.orders = np.array(child.array("elemOrder")).reshape(-1, 3)
         return child

@@ -183,7 +183,8 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace,
  * Available on such a mesh: StandardDG with BR1 (or Euler), every Riemann solver, boundary condition and gradient-variable set,
  * all Runge-Kutta schemes, h3d_max_residuals / _max_timestep / _has_nan, h3d_volume_integral (volume, kinetic energy and its
  * rate, enstrophy, mean velocity, internal energy), h3d_surface_integral, h3d_probe (Lagrange vectors padded to rows of
- * max(N)+1 values); one rank.  The other entry points return an error. */
+ * max(N)+1 values), and h3d_set_halo on partitioned meshes: the traces of the MPI faces are exchanged at the face order.  The
+ * other entry points return an error. */
 
 /* Tset(Norigin, Ndest) % T (libs/spectral/InterpolationMatrices.f90:42-107): row-major T[i*(Norigin+1) + l] = T(i,l),
  * (Ndest+1) x (Norigin+1); Lagrange interpolation for Norigin < Ndest, the L2 projection (weighted transpose) otherwise. */
@@ -193,6 +194,9 @@ int h3d_set_interpolation(h3d_handle h, int Norigin, int Ndest, const double* T)
  * h3d_set_mesh with the packed sizes described above (face geometry from MappedGeometryFace at the face order,
  * MappedGeometry.f90:482-756). */
 int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder,
+                   const int* faceOrder,     /* [nFace][6] f % Nf(1:2), f % NfLeft(1:2), f % NfRight(1:2) (FaceClass.f90:69-71); may be NULL on a
+                                                single rank (derived from the elements); required with MPI faces, whose remote element belongs to
+                                                another rank (the reference exchanges it: HexMesh_UpdateMPIFacesPolynomial, HexMesh.f90:2425) */
                    const int* elemFace, const int* elemFaceSide, const int* faceElem, const int* faceElemSide,
                    const int* faceRot, const int* faceType, const int* faceZone,
                    const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,

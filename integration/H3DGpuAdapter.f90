@@ -116,6 +116,8 @@ contains
       integer(c_int), allocatable          :: bcType(:), nbrRank(:), nbrCount(:), haloFace(:), haloSide(:)
       real(c_double), allocatable          :: bcPar(:), Dt(:), hatDt(:), sharpDt(:), vv(:), bb(:)
       type(NodalStorage_t), pointer        :: sp
+      logical                              :: isMixed
+      integer                              :: ierr
 
       ctd_after_steps = ctdAfterSteps
 !
@@ -170,7 +172,11 @@ contains
 !
 !     2. Basis: the header wants row-major M(i,l) -> the transposes of the Fortran column-major arrays
 !     ----------------------------------------------------------------------------------------------
-      if ( any(mesh % Nx /= N) .or. any(mesh % Ny /= N) .or. any(mesh % Nz /= N) ) then
+      isMixed = any(mesh % Nx /= N) .or. any(mesh % Ny /= N) .or. any(mesh % Nz /= N)
+#ifdef _HAS_MPI_
+      if ( MPI_Process % doMPIAction ) call mpi_allreduce(MPI_IN_PLACE, isMixed, 1, MPI_LOGICAL, MPI_LOR, MPI_COMM_WORLD, ierr)   ! one decision for all ranks
+#endif
+      if ( isMixed ) then
          call setup_basis_and_mesh_p(mesh)
          goto 400                                                          ! boundary table, state
       end if
@@ -305,16 +311,12 @@ contains
    subroutine setup_basis_and_mesh_p(mesh)
       type(HexMesh), target, intent(inout) :: mesh
       integer                              :: N, M, eID, fID, s, k, nE, nF, n3, n2, posE, posF
-      integer(c_int), allocatable          :: elemOrder(:), elemFace(:), elemFaceSide(:), faceElem(:), faceElemSide(:), faceRot(:), faceType(:), faceZone(:)
+      integer(c_int), allocatable          :: elemOrder(:), faceOrder(:), elemFace(:), elemFaceSide(:), faceElem(:), faceElemSide(:), faceRot(:), faceType(:), faceZone(:)
       real(c_double), allocatable          :: jGradXi(:), jGradEta(:), jGradZeta(:), jac(:), x(:), vol(:)
       real(c_double), allocatable          :: fN(:), fT1(:), fT2(:), fJ(:), fX(:), fS(:)
       real(c_double), allocatable          :: Dt(:), hatDt(:), sharpDt(:), vv(:), bb(:), Tt(:)
       type(NodalStorage_t), pointer        :: sp
 
-      if ( MPI_Process % doMPIAction ) then
-         print*, "The GPU path runs p-nonconforming meshes on one rank."
-         errorMessage(STD_OUT) ; error stop
-      end if
       do N = 1, ubound(NodalStorage, 1)
          if ( .not. NodalStorage(N) % Constructed ) cycle
          sp => NodalStorage(N)
@@ -340,7 +342,7 @@ contains
       do eID = 1, nE ; posE = posE + product(mesh % elements(eID) % Nxyz + 1) ; end do
       posF = 0
       do fID = 1, nF ; posF = posF + product(mesh % faces(fID) % Nf + 1) ; end do
-      allocate(elemOrder(3*nE), elemFace(6*nE), elemFaceSide(6*nE), faceElem(2*nF), faceElemSide(2*nF), faceRot(nF), faceType(nF), faceZone(nF))
+      allocate(elemOrder(3*nE), faceOrder(6*nF), elemFace(6*nE), elemFaceSide(6*nE), faceElem(2*nF), faceElemSide(2*nF), faceRot(nF), faceType(nF), faceZone(nF))
       allocate(jGradXi(3*posE), jGradEta(3*posE), jGradZeta(3*posE), jac(posE), x(3*posE), vol(nE))
       allocate(fN(3*posF), fT1(3*posF), fT2(3*posF), fJ(posF), fX(3*posF), fS(nF))
       posE = 0
@@ -370,6 +372,7 @@ contains
             faceElemSide(2*(fID-1)+k) = f % elementSide(k) - 1
          end do
          faceRot(fID) = f % rotation;  faceType(fID) = f % faceType;  faceZone(fID) = f % zone - 1
+         faceOrder(6*(fID-1)+1 : 6*fID) = [f % Nf, f % NfLeft, f % NfRight]       ! MPI faces: after UpdateMPIFacesPolynomial (HexMesh.f90:2425)
          fN (3*posF+1 : 3*(posF+n2)) = reshape(f % geom % normal,   [3*n2])
          fT1(3*posF+1 : 3*(posF+n2)) = reshape(f % geom % t1,       [3*n2])
          fT2(3*posF+1 : 3*(posF+n2)) = reshape(f % geom % t2,       [3*n2])
@@ -379,7 +382,7 @@ contains
          posF = posF + n2
          end associate
       end do
-      call check(h3d_set_mesh_p(h3d, int(nE, c_int), int(nF, c_int), elemOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, &
+      call check(h3d_set_mesh_p(h3d, int(nE, c_int), int(nF, c_int), elemOrder, faceOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, &
                                 faceZone, jGradXi, jGradEta, jGradZeta, jac, x, vol, fN, fT1, fT2, fJ, fX, fS), "h3d_set_mesh_p")
    end subroutine setup_basis_and_mesh_p
 !

@@ -1485,7 +1485,7 @@ int orc_set_interpolation(void* p, int Norigin, int Ndest, const double* T) {
 
 // h3d_set_mesh_p: as orc_set_mesh with the elements' orders elemOrder[nElem][3]; geometry arrays packed element after element /
 // face after face at their own sizes (faces at the face order, FaceClass.f90:187-282)
-int orc_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+int orc_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const int* faceOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
                    const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone,
                    const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,
                    const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
@@ -1525,6 +1525,7 @@ int orc_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const in
                 o.err = "set_interpolation has not been called for every pair of orders that meet at a face"; return 1; }
         }
         if (!P.sp.count(fo[0]) || !P.sp.count(fo[1])) { o.err = "set_basis has not been called for every face order"; return 1; }
+        if (faceOrder) for (int q = 0; q < 6; ++q) if (faceOrder[6 * (size_t)f + q] != fo[q]) { o.err = "faceOrder contradicts the orders of the elements"; return 1; }
         P.fOff[f + 1] = P.fOff[f] + (size_t)(fo[0] + 1) * (fo[1] + 1);
     }
     const size_t ne = P.eOff[nElem], nfn = P.fOff[nFace], nt = P.tOff[6 * (size_t)nElem];

@@ -30,18 +30,50 @@ def build(force=False):
     return LIB
 
 
+def _lib():
+    lib = C.CDLL(build())
+    lib.emu_create.restype = C.c_void_p
+    lib.emu_create_rank.restype = C.c_void_p
+    lib.emu_create_rank.argtypes = [C.c_void_p, C.c_int]
+    lib.emu_world_create.restype = C.c_void_p
+    lib.emu_world_create.argtypes = [C.c_int]
+    lib.emu_world_destroy.argtypes = [C.c_void_p]
+    lib.emu_destroy.argtypes = [C.c_void_p]
+    lib.emu_kernel_launches.argtypes = [C.c_void_p]
+    lib.emu_kernel_launches.restype = C.c_longlong
+    return lib
+
+
+class EmuWorld:
+    """The ranks of one emulated partitioned run: one EmuApi(world, rank) per rank, each driven from its own Python thread (the
+    exchange and the all-reduce of the host-loop backend meet at a barrier inside the library)."""
+
+    def __init__(self, nranks):
+        self._lib = _lib()
+        self.nranks = nranks
+        self.handle = C.c_void_p(self._lib.emu_world_create(nranks))
+
+    def __del__(self):
+        try:
+            self._lib.emu_world_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class EmuApi(Api):
     name = "emu"
 
-    def __init__(self):
-        lib = C.CDLL(build())
-        lib.emu_create.restype = C.c_void_p
-        lib.emu_destroy.argtypes = [C.c_void_p]
-        lib.emu_kernel_launches.argtypes = [C.c_void_p]
-        lib.emu_kernel_launches.restype = C.c_longlong
-        self.binding = Binding(lib, "emu_", names=NAMES)
-        self.handle = C.c_void_p(lib.emu_create())
+    def __init__(self, world=None, rank=0):
+        lib = _lib()
+        self.binding = Binding(lib, "emu_", extra={"set_halo": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]}, names=NAMES + ["set_halo"])
+        self.world = world         # keeps the world alive
+        self.handle = C.c_void_p(lib.emu_create_rank(world.handle, rank) if world is not None else lib.emu_create())
         self._lib = lib
+
+    def set_halo(self, ranks, counts, faces, sides):
+        import numpy as np
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (ranks, counts, faces, sides)]
+        self.call("set_halo", len(a[0]), *[x.ctypes.data for x in a])
 
     def kernel_launches(self):
         return int(self._lib.emu_kernel_launches(self.handle))

@@ -26,8 +26,49 @@
 
 using namespace h3d;
 
+#include <condition_variable>
+#include <mutex>
+
 namespace {
+// Ranks of one emulated run live in one process, one thread each (the Python test calls the entry points from threads; ctypes
+// releases the interpreter lock).  exchange / allreduce meet at a barrier and copy through the posted pointers.
+struct World {
+    int nranks; std::mutex mu; std::condition_variable cv; int arrived = 0; long long generation = 0;
+    std::vector<const double*> sendBuf; std::vector<std::vector<int>> nbrRanks; std::vector<std::vector<long long>> nbrOff;
+    std::vector<const double*> scal;
+    explicit World(int n) : nranks(n), sendBuf(n), nbrRanks(n), nbrOff(n), scal(n) {}
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const long long gen = generation;
+        if (++arrived == nranks) { arrived = 0; ++generation; cv.notify_all(); } else cv.wait(lk, [&] { return generation != gen; });
+    }
+};
 struct HostBackend {
+    World* world = nullptr; int rank = 0;
+    void exchange(const double* send, double* recv, int nNbr, const int* ranks, const long long* off, const long long* cnt) {
+        world->sendBuf[rank] = send; world->nbrRanks[rank].assign(ranks, ranks + nNbr); world->nbrOff[rank].assign(off, off + nNbr);
+        world->barrier();
+        for (int b = 0; b < nNbr; ++b) {   // my message from neighbour r = the part of r's send buffer addressed to me
+            const int r = ranks[b]; long long roff = -1;
+            for (size_t q = 0; q < world->nbrRanks[r].size(); ++q) if (world->nbrRanks[r][q] == rank) roff = world->nbrOff[r][q];
+            if (roff < 0) std::abort();
+            std::memcpy(recv + off[b], world->sendBuf[r] + roff, (size_t)cnt[b] * sizeof(double));
+        }
+        world->barrier();
+    }
+    void allreduce(double* v, int n, int op) {
+        world->scal[rank] = v;
+        world->barrier();
+        std::vector<double> out(v, v + n);
+        for (int q = 0; q < n; ++q) {
+            double acc = world->scal[0][q];
+            for (int r = 1; r < world->nranks; ++r) { const double x = world->scal[r][q]; acc = op == 0 ? std::fmax(acc, x) : (op == 1 ? std::fmin(acc, x) : acc + x); }
+            out[q] = acc;
+        }
+        world->barrier();
+        std::memcpy(v, out.data(), n * sizeof(double));
+        world->barrier();
+    }
     std::vector<void*>* allocs = nullptr;
     template <class T> T* alloc(size_t count) { void* q = std::malloc(std::max<size_t>(count, 1) * sizeof(T)); allocs->push_back(q); return (T*)q; }
     template <class T> void upload(T* dst, const T* src, size_t count) { std::memcpy(dst, src, count * sizeof(T)); }
@@ -48,7 +89,11 @@ struct Emu {
     H3dPhysics physics{}; Phys ph{}; bool havePhysics = false;
     MixedSolver<HostBackend>* mx = nullptr;
     std::string err;
-    Emu() { HostBackend be; be.allocs = &allocs; mx = new MixedSolver<HostBackend>(be); }
+    explicit Emu(World* w = nullptr, int rank = 0) {
+        HostBackend be; be.allocs = &allocs; be.world = w; be.rank = rank;
+        mx = new MixedSolver<HostBackend>(be);
+        if (w) mx->nranks = w->nranks;
+    }
     ~Emu() { delete mx; for (void* p : allocs) std::free(p); }
 };
 int done(Emu* h, int rc) { if (rc) h->err = h->mx->err; return rc; }
@@ -57,6 +102,10 @@ int done(Emu* h, int rc) { if (rc) h->err = h->mx->err; return rc; }
 extern "C" {
 int emu_create_handle(void** out, int, int, int, const void*) { *out = new Emu(); return 0; }
 void* emu_create() { return new Emu(); }
+void* emu_world_create(int nranks) { return new World(nranks); }
+void emu_world_destroy(void* w) { delete (World*)w; }
+void* emu_create_rank(void* world, int rank) { return new Emu((World*)world, rank); }
+int emu_set_halo(void* p, int nNbr, const int* ranks, const int* counts, const int* faces, const int* sides) { Emu* h = (Emu*)p; return done(h, h->mx->setHalo(nNbr, ranks, counts, faces, sides)); }
 void emu_destroy(void* p) { delete (Emu*)p; }
 const char* emu_last_error(void* p) { return ((Emu*)p)->err.c_str(); }
 int emu_set_physics(void* p, const H3dPhysics* ph) {
@@ -69,14 +118,14 @@ int emu_set_basis(void* p, int N, int, const double* x, const double* w, const d
     ((Emu*)p)->mx->setBasis(N, x, w, D, hatD, v, b); return 0;
 }
 int emu_set_interpolation(void* p, int No, int Nd, const double* T) { Emu* h = (Emu*)p; return done(h, h->mx->setInterpolation(No, Nd, T)); }
-int emu_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
+int emu_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const int* faceOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
                    const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone, const double* jGradXi, const double* jGradEta,
                    const double* jGradZeta, const double* jacobian, const double*, const double*, const double* faceNormal, const double* faceT1,
                    const double* faceT2, const double* faceJacobian, const double*, const double*) {
     Emu* h = (Emu*)p;
     if (!h->havePhysics) { h->err = "set_physics must precede set_mesh_p"; return 1; }
     h->mx->ph = h->ph;
-    return done(h, h->mx->setMesh(h->physics, nElem, nFace, elemOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone, jGradXi,
+    return done(h, h->mx->setMesh(h->physics, nElem, nFace, elemOrder, faceOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone, jGradXi,
                                    jGradEta, jGradZeta, jacobian, faceNormal, faceT1, faceT2, faceJacobian));
 }
 int emu_set_boundary_conditions(void* p, int nZones, const int* bcType, const double* bcParams) { Emu* h = (Emu*)p; return done(h, h->mx->setBoundaryConditions(nZones, bcType, bcParams)); }

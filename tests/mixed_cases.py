@@ -48,10 +48,18 @@ def smooth_state(sem, mach):
     return Q
 
 
-def run_case(api, mesh, phys, scheme="rk3", dt=2.0e-3, source=False, zone=None):
-    """One residual, one RK step with a residual after it, the reductions; returns everything that is compared."""
+def run_case(api, mesh, phys, scheme="rk3", dt=2.0e-3, source=False, zone=None, state_from=None):
+    """One residual, one RK step with a residual after it, the reductions; returns everything that is compared.  state_from =
+    (single-domain DGSem, global element ids of this partition): the initial state is taken from the global one, element by element
+    (periodic images of a node have different coordinates in different elements' patches only through the element that owns them, so
+    evaluating the state function on the partition gives the same values -- this just makes it explicit)."""
     sem = DGSem(api, mesh, phys)
-    sem.set_Q(smooth_state(sem, phys.Mach))
+    if state_from is None:
+        sem.set_Q(smooth_state(sem, phys.Mach))
+    else:
+        sem0, ge = state_from
+        Q0 = smooth_state(sem0, phys.Mach)
+        sem.set_Q(np.concatenate([Q0[sem0.elem_offset[e]:sem0.elem_offset[e + 1]] for e in ge]))
     if source:
         rng = np.random.default_rng(11)
         sem.set_source(0.01 * rng.standard_normal((sem.NDOF, 5)))

@@ -68,3 +68,68 @@ def test_unsupported_configurations_are_refused():
     for kw in (dict(inviscid="split-form", averaging="pirozzoli"), dict(viscous="br2"), dict(les="smagorinsky")):
         with pytest.raises(H3dError):
             DGSem(EmuApi(), MC.periodic_box(2, 2, 3, seed=1, nodes=GAUSSLOBATTO), make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe", **kw))
+
+
+def _partitioned(world_size, mesh_fn, phys, method, zone=None, scheme="rk3"):
+    """The same case on the single-domain oracle and on `world_size` emulated ranks (threads); returns both result sets with the
+    partitioned element fields gathered into the global element order."""
+    import threading
+    from emu.emu_api import EmuWorld
+    sem0, ref = MC.run_case(oracle_api.OracleApi(), mesh_fn(), phys, zone=zone, scheme=scheme)
+    g = mesh_fn()
+    part = g.partition(world_size, method)
+    assert len(set(part)) == world_size
+    world = EmuWorld(world_size)
+    outs, errs = [None] * world_size, []
+
+    def work(rank):
+        try:
+            m = g.extract(part, rank, inherit_geometry=True)
+            sem, out = MC.run_case(EmuApi(world, rank), m, phys, zone=zone, scheme=scheme, state_from=(sem0, m.array("globalElem").copy()))
+            outs[rank] = (sem, out, m.array("globalElem").copy(), int((m.array("faceType") == 3).sum()))
+        except Exception as ex:      # a dead rank would leave the others at the barrier
+            errs.append(ex)
+            os._exit(1)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world_size)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    assert all(o[3] > 0 for o in outs)            # every rank has MPI faces
+    got = {}
+    for k, v in ref.items():
+        if v.ndim == 2 and v.shape[0] == sem0.NDOF:        # element field: gather
+            a = np.empty_like(v)
+            for sem, out, ge, _ in outs:
+                for l, e in enumerate(ge):
+                    a[sem0.elem_offset[e]:sem0.elem_offset[e + 1]] = out[k][sem.elem_offset[l]:sem.elem_offset[l + 1]]
+            got[k] = a
+        else:                                               # reduced over the ranks: the same on all of them
+            for _, out, _, _ in outs[1:]:
+                assert np.array_equal(out[k], outs[0][1][k]), k
+            got[k] = outs[0][1][k]
+    return ref, got
+
+
+@pytest.mark.parametrize("world_size,method", [(2, "metis"), (3, "block"), (4, "metis")])
+def test_partitioned_mesh_reproduces_the_single_domain_oracle(world_size, method):
+    """MPI faces of a p-nonconforming mesh: traces exchanged at the face order, mortar projection on each side's rank.  Element fields
+    are bit-identical to the single-domain oracle (the partitions inherit the global geometry); the all-reduced scalars agree to
+    the round-off of a different summation order."""
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")
+    ref, got = _partitioned(world_size, lambda: MC.periodic_box(4, 2, 5, seed=7), phys, method)
+    worst, _ = MC.compare(ref, got)
+    print(worst)
+    for k, v in worst.items():
+        assert v <= (1e-13 if k in ("integrals", "surface") else 0.0), (k, v)
+
+
+def test_partitioned_channel_with_boundaries_and_surface_integrals():
+    phys = make_physics(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", gradient_variables="energy")
+    ref, got = _partitioned(2, lambda: MC.channel(phys, ne=4), phys, "metis", zone=2, scheme="ssprk33")
+    worst, _ = MC.compare(ref, got)
+    print(worst)
+    for k, v in worst.items():
+        assert v <= (1e-13 if k in ("integrals", "surface") else 0.0), (k, v)

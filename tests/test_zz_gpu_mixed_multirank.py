@@ -1,0 +1,102 @@
+"""p-nonconforming meshes on several B200s: partitioned mesh (element weights = degrees of freedom), NCCL exchange of the MPI faces'
+traces at the face order, all-reduced scalars -- against the single-domain oracle.  The same partitioned cases run on the CPU
+through the emulated kernels with threads as ranks (tests/test_mixed_emu.py).  Skipped where the box has fewer GPUs than ranks.
+Sorts last: not yet run on hardware (see tests/test_zz_gpu_mixed.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = pytest.mark.gpu
+
+CASES = [dict(world=2, kind="box", method="metis", kw=dict(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")),
+         dict(world=2, kind="channel", method="block", kw=dict(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", gradient_variables="energy")),
+         dict(world=4, kind="box", method="metis", kw=dict(flow="Euler", mach=0.3, riemann="standard roe")),
+         dict(world=8, kind="box", method="metis", kw=dict(flow="NS", mach=0.3, reynolds=200.0, riemann="roe"))]
+
+
+def _mesh(case, phys):
+    import mixed_cases as MC
+    return MC.channel(phys, ne=4) if case["kind"] == "channel" else MC.periodic_box(6 if case["world"] == 8 else 4, 2, 5, seed=7)
+
+
+def _worker(rank, world, port, case, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import mixed_cases as MC
+        from horses3d_b200.capi import GpuApi
+        from horses3d_b200.dgsem import DGSem
+        from horses3d_b200.physics import make_physics
+        phys = make_physics(**case["kw"])
+        obj = [GpuApi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        g = _mesh(case, phys)
+        part = g.partition(world, case["method"])
+        m = g.extract(part, rank, inherit_geometry=True)
+        ge = m.array("globalElem").copy()
+        # the initial state of the global mesh, element by element
+        off = np.concatenate([[0], np.cumsum(np.prod(g.orders + 1, axis=1))])
+
+        class Glob:      # what smooth_state needs of a DGSem of the global mesh
+            NDOF = int(off[-1]); elem_offset = off
+            @staticmethod
+            def node_coordinates():
+                return g.array("x").reshape(-1, 3)
+        api = GpuApi(rank=rank, nranks=world, device=rank, nccl_id=obj[0])
+        sem, out = MC.run_case(api, m, phys, zone=2 if case["kind"] == "channel" else None, state_from=(Glob, ge))
+        q.put((rank, ge, sem.elem_offset.copy(), out, int((m.array("faceType") == 3).sum())))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "w%d-%s-%s-%s" % (c["world"], c["kind"], c["method"], c["kw"]["flow"]))
+def test_ranks_reproduce_the_single_domain_oracle_on_a_p_nonconforming_mesh(case):
+    import queue
+    import time
+    import torch
+    import torch.multiprocessing as mp
+    world = case["world"]
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs, this box has %d (run under gpurun --gpus %d)" % (world, torch.cuda.device_count(), world))
+    import mixed_cases as MC
+    from horses3d_b200.physics import make_physics
+    from oracle.oracle_api import OracleApi
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, t0 = [], time.time()
+    while len(got) < world:
+        try:
+            got.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > 400:
+                for p in procs:
+                    p.kill()
+                pytest.fail("a rank exited with %s / timed out after %.0f s" % (dead, time.time() - t0))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    phys = make_physics(**case["kw"])
+    sem0, ref = MC.run_case(OracleApi(), _mesh(case, phys), phys, zone=2 if case["kind"] == "channel" else None)
+    assert all(g_[4] > 0 for g_ in got)
+    for rank, ge, offl, out, _ in got:
+        for k, v in ref.items():
+            scale = max(np.abs(v).max(), 1e-300)
+            if v.ndim == 2 and v.shape[0] == sem0.NDOF:
+                mine = np.concatenate([v[sem0.elem_offset[e]:sem0.elem_offset[e + 1]] for e in ge])
+                assert np.abs(out[k] - mine).max() <= 1e-13 * scale, (rank, k)
+            else:
+                assert np.abs(np.asarray(out[k], dtype=float) - np.asarray(v, dtype=float)).max() <= 1e-12 * scale, (rank, k)
