@@ -1111,7 +1111,7 @@ int h3d_set_basis(h3d_handle h, int N, int nodeType, const double* x, const doub
                   const double* sharpD, const double* v, const double* b) {
     if (N < 1 || N >= MX_MAXN) { h->err = "polynomial order out of range (1..15)"; return 1; }
     // every order given stays registered: NodalStorage(N) of a p-nonconforming mesh (h3d_set_mesh_p)
-    ensureMx(h)->setBasis(N, x, w, D, hatD, v, b);
+    ensureMx(h)->setBasis(N, nodeType, x, w, D, hatD, sharpD, v, b);
     if (N > 9) { h->haveBasis = false; h->N = N; return 0; }   // usable by h3d_set_mesh_p only: the uniform-order kernels are instantiated for N = 1..9
     CTX_CHECK(cudaSetDevice(h->device));
     const int n = N + 1;
@@ -1286,7 +1286,7 @@ int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder, con
                    const double* jGradXi, const double* jGradEta, const double* jGradZeta, const double* jacobian,
                    const double* x, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
                    const double* faceJacobian, const double* faceX, const double* faceSurface) {
-    (void)x; (void)volume; (void)faceX; (void)faceSurface;   // sources and LES widths are not part of this path
+    (void)x; (void)faceX;
     if (!h->havePhysics) { h->err = "h3d_set_physics must precede h3d_set_mesh_p"; return 1; }
     if (h->haveMesh || h->mixedMode) { h->err = "the context already holds a mesh"; return 1; }
     if (!elemOrder || !elemFace || !elemFaceSide || !faceElem || !faceElemSide || !faceRot || !faceType || !faceZone || !jGradXi || !jGradEta ||
@@ -1295,7 +1295,7 @@ int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder, con
     MixedSolver<CudaBackend>* mx = ensureMx(h);
     mx->ph = h->ph;
     int rc = mx->setMesh(h->physics, nElem, nFace, elemOrder, faceOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone,
-                         jGradXi, jGradEta, jGradZeta, jacobian, faceNormal, faceT1, faceT2, faceJacobian);
+                         jGradXi, jGradEta, jGradZeta, jacobian, volume, faceNormal, faceT1, faceT2, faceJacobian, faceSurface);
     if (rc) return mxDone(h, rc);
     h->mixedMode = true; h->nElem = nElem; h->nFace = nFace;
     if (!h->hBcType.empty()) rc = mx->setBoundaryConditions((int)h->hBcType.size(), h->hBcType.data(), h->hBcParams.data());
@@ -1303,7 +1303,7 @@ int h3d_set_mesh_p(h3d_handle h, int nElem, int nFace, const int* elemOrder, con
 }
 
 int h3d_set_wall_distance(h3d_handle h, const double* dWallElem, const double* dWallFace) {
-    MX_UNSUPPORTED("the LES wall distance");
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); return mxDone(h, h->mx->setWallDistance(dWallElem, dWallFace)); }
     CTX_CHECK(cudaSetDevice(h->device));
     if (!h->haveMesh) { h->err = "h3d_set_wall_distance: set the mesh first"; return 1; }
     if (!dWallElem || !dWallFace) { h->err = "h3d_set_wall_distance: null array"; return 1; }

@@ -20,7 +20,8 @@
 // and the orchestration is a template over a backend (allocate / copy / launch): libh3dgpu.so instantiates it with the CUDA
 // backend; tests/emu instantiates the SAME functors and orchestration with a host loop as the launcher, which is how this path
 // is checked against the oracle where no GPU is present (test infrastructure, never shipped).
-// Scope: StandardDG, BR1 (or Euler), any Riemann solver / boundary condition / gradient variables of h3d_physics.cuh, no LES.
+// Scope: StandardDG and SplitDG (any two-point flux), BR1 (or Euler), any Riemann solver / boundary condition / gradient variables / LES
+// model of h3d_physics.cuh.
 // Partitioned meshes: the traces of the MPI faces are exchanged at the face order (h3d_set_halo), scalars are all-reduced.  Reductions are computed per element (face) in the reference's node order and finished on the host in element
 // order, so that they reproduce the oracle's sums bit for bit.
 #pragma once
@@ -55,7 +56,7 @@ struct MixedDev {
     const int *elemFace, *elemFaceSide;     // [nElem][6]
     const int *faceElem, *faceElemSide;     // [nFace][2]
     const int *faceRot, *faceType, *faceZone;
-    // ---- operators: per order N the block D[n n] hatD[n n] v[2 n] b[2 n] w[n] x[n] at ops + opBase[N] (row-major M[i n + l] = M(i,l))
+    // ---- operators: per order N the block D[n n] hatD[n n] v[2 n] b[2 n] w[n] x[n] sharpD[n n] at ops + opBase[N] (row-major M[i n + l] = M(i,l))
     const double* ops; int opBase[MX_MAXN];
     // Tset(Norigin, Ndest) % T at tset + tBase[Norigin][Ndest], [(Ndest+1)][(Norigin+1)]
     const double* tset; int tBase[MX_MAXN][MX_MAXN];
@@ -64,6 +65,8 @@ struct MixedDev {
     double* Fc;                             // 15: contravariant flux (d*5 + q)
     const double* S;                        // 5 or nullptr
     const double *Ja, *J, *invJ;            // 9 (3 d + c), 1, 1
+    const double *lesDelta, *fDelta;        // [nElem] (V / product(Nxyz+1))^(1/3), [nFace] sqrt(surface / product(Nf+1)) (SpatialDiscretization.f90:420, 1378)
+    const double *dWall, *fDWall;           // [nNodes], [nFaceNodes] wall distances (LES wall model) or nullptr
     // ---- element-side fields at the element's face order [c][nTrace]
     double *tr;                             // 15: traces before the adaption to the face order
     double *fStarE, *unStarE;               // 5 / 15 (d*5 + q)
@@ -98,6 +101,7 @@ __device__ __forceinline__ const double* mxV(const MixedDev& m, int N) { return 
 __device__ __forceinline__ const double* mxB(const MixedDev& m, int N) { return m.ops + m.opBase[N] + 2 * (N + 1) * (N + 1) + 2 * (N + 1); }
 __device__ __forceinline__ const double* mxW(const MixedDev& m, int N) { return m.ops + m.opBase[N] + 2 * (N + 1) * (N + 1) + 4 * (N + 1); }
 __device__ __forceinline__ const double* mxX(const MixedDev& m, int N) { return m.ops + m.opBase[N] + 2 * (N + 1) * (N + 1) + 5 * (N + 1); }
+__device__ __forceinline__ const double* mxSharpD(const MixedDev& m, int N) { return m.ops + m.opBase[N] + 2 * (N + 1) * (N + 1) + 6 * (N + 1); }
 __device__ __forceinline__ const double* mxT(const MixedDev& m, int No, int Nd) { return m.tset + m.tBase[No][Nd]; }
 // MeshTypes.f90:70-108 and its inverse
 __device__ __forceinline__ void mxLeft2Right(int i, int j, int Nx, int Ny, int rot, int& ii, int& jj) {
@@ -313,7 +317,7 @@ struct MxLift {
 
 // ---- contravariant fluxes at the nodes: Fc[d*5 + q] = inviscid - viscous ---------------------------------------------------
 struct MxFlux {
-    MixedDev m; Phys ph;
+    MixedDev m; Phys ph; int split;   // split form: Fc = the viscous contravariant flux alone (the inviscid part is formed pairwise in MxVolumeSplit)
     __device__ void operator()(long long g) const {
         double Q[5], ja[9], F[5][3], Fi[15], Fv[15];
         for (int q = 0; q < 5; ++q) Q[q] = m.Q[(long long)q * m.nNodes + g];
@@ -325,10 +329,14 @@ struct MxFlux {
             double gx[5], gy[5], gz[5], mu, kappa;
             for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[(long long)q * m.nNodes + g]; gy[q] = m.Uy[(long long)q * m.nNodes + g]; gz[q] = m.Uz[(long long)q * m.nNodes + g]; }
             laminar_mu_kappa(ph, Q, mu, kappa);
+            if (ph.les != H3D_LES_NONE) {
+                const double mut = smagorinsky<true>(ph, m.lesDelta[m.nodeElem[g]], ph.wallModel ? m.dWall[g] : 0.0, Q, gx, gy, gz);
+                mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa;
+            }
             viscous_flux<true>(ph, Q, gx, gy, gz, mu, 0.0, kappa, F);
             for (int d = 0; d < 3; ++d) for (int q = 0; q < 5; ++q) Fv[d * 5 + q] = F[q][0] * ja[3 * d] + F[q][1] * ja[3 * d + 1] + F[q][2] * ja[3 * d + 2];
         }
-        for (int q = 0; q < 15; ++q) m.Fc[(long long)q * m.nNodes + g] = Fi[q] - Fv[q];
+        for (int q = 0; q < 15; ++q) m.Fc[(long long)q * m.nNodes + g] = split ? Fv[q] : Fi[q] - Fv[q];
     }
 };
 
@@ -343,15 +351,19 @@ struct MxRiemann {
         const double Jf = m.fJ[g];
         for (int q = 0; q < 5; ++q) QL[q] = m.fQ[q * fs + g];
         double gx[5], gy[5], gz[5], mu, kappa;
+        const bool les = ph.les != H3D_LES_NONE;
+        const double dW = (les && ph.wallModel) ? m.fDWall[g] : 0.0;
         if (m.faceType[f] != H3D_FACE_BOUNDARY) {      // interior and MPI faces (computeMPIFaceFlux, SpatialDiscretization.f90:1801-1894)
             for (int q = 0; q < 5; ++q) QR[q] = m.fQ[(5 + q) * fs + g];
             if (ph.ns) {   // BR1_RiemannSolver (EllipticBR1.f90:816-868)
                 double FL[5][3], FR[5][3];
                 for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(0 * 10 + q) * fs + g]; gy[q] = m.fU[(1 * 10 + q) * fs + g]; gz[q] = m.fU[(2 * 10 + q) * fs + g]; }
                 laminar_mu_kappa(ph, QL, mu, kappa);
+                if (les) { const double mut = smagorinsky<true>(ph, m.fDelta[f], dW, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
                 viscous_flux<true>(ph, QL, gx, gy, gz, mu, 0.0, kappa, FL);
                 for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(0 * 10 + 5 + q) * fs + g]; gy[q] = m.fU[(1 * 10 + 5 + q) * fs + g]; gz[q] = m.fU[(2 * 10 + 5 + q) * fs + g]; }
                 laminar_mu_kappa(ph, QR, mu, kappa);
+                if (les) { const double mut = smagorinsky<true>(ph, m.fDelta[f], dW, QR, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
                 viscous_flux<true>(ph, QR, gx, gy, gz, mu, 0.0, kappa, FR);
                 for (int q = 0; q < 5; ++q) {
                     const double fx = 0.5 * (FL[q][0] + FR[q][0]), fy = 0.5 * (FL[q][1] + FR[q][1]), fz = 0.5 * (FL[q][2] + FR[q][2]);
@@ -366,6 +378,7 @@ struct MxRiemann {
                 double F[5][3];
                 for (int q = 0; q < 5; ++q) { gx[q] = m.fU[(0 * 10 + q) * fs + g]; gy[q] = m.fU[(1 * 10 + q) * fs + g]; gz[q] = m.fU[(2 * 10 + q) * fs + g]; }
                 laminar_mu_kappa(ph, QL, mu, kappa);
+                if (les) { const double mut = smagorinsky<true>(ph, m.fDelta[f], dW, QL, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
                 viscous_flux<true>(ph, QL, gx, gy, gz, mu, 0.0, kappa, F);
                 for (int q = 0; q < 5; ++q) visc[q] = F[q][0] * nh[0] + F[q][1] * nh[1] + F[q][2] * nh[2];
                 bc_neumann(btype, P, QL, visc);
@@ -394,6 +407,28 @@ struct MxHaloPack {
 };
 
 // ---- weak volume integral + surface integral, /J, +S, Runge-Kutta update ---------------------------------------------------
+// surface integral of the six sides, /J, +S, and the update of one Runge-Kutta stage for equation q of node g
+__device__ __forceinline__ void mxSurfaceAndUpdate(const MixedDev& m, const MxRk& rk, const MxSides& sd, long long g, int q, double vol, double Jn) {
+    const double* Fs = m.fStarE + (long long)q * m.nTrace;
+    double fi = Fs[sd.s[0]] * sd.b[0];
+    for (int s = 1; s < 6; ++s) fi = fi + Fs[sd.s[s]] * sd.b[s];
+    double res = vol - fi;
+    res = res / Jn;
+    if (m.S) res = res + m.S[(long long)q * m.nNodes + g];
+    const long long o = (long long)q * m.nNodes + g;
+    m.QDot[o] = res;
+    if (rk.mode == 1) {
+        const double gg = rk.a * m.G[o] + res;
+        m.G[o] = gg;
+        m.Q[o] = m.Q[o] + rk.cdt * gg;
+    } else if (rk.mode == 2) {   // TakeSSPRK33Step / TakeSSPRK43Step
+        const double Qk = m.Q[o];
+        const double g0 = rk.copyG ? Qk : m.G[o];
+        if (rk.copyG) m.G[o] = g0;
+        m.Q[o] = rk.a * g0 + rk.b * Qk + rk.cdt * res;
+    }
+}
+
 struct MxVolume {
     MixedDev m; MxRk rk;
     __device__ void operator()(long long g) const {
@@ -408,25 +443,65 @@ struct MxVolume {
             for (int l = 0; l < t.nx; ++l) vol = vol + hx[l] * Fx[((long long)t.k * t.ny + t.j) * t.nx + l];
             for (int l = 0; l < t.ny; ++l) vol = vol + hy[l] * Fy[((long long)t.k * t.ny + l) * t.nx + t.i];
             for (int l = 0; l < t.nz; ++l) vol = vol + hz[l] * Fz[((long long)l * t.ny + t.j) * t.nx + t.i];
-            const double* Fs = m.fStarE + (long long)q * m.nTrace;
-            double fi = Fs[sd.s[0]] * sd.b[0];
-            for (int s = 1; s < 6; ++s) fi = fi + Fs[sd.s[s]] * sd.b[s];
-            double res = vol - fi;
-            res = res / Jn;
-            if (m.S) res = res + m.S[(long long)q * m.nNodes + g];
-            const long long o = (long long)q * m.nNodes + g;
-            m.QDot[o] = res;
-            if (rk.mode == 1) {
-                const double gg = rk.a * m.G[o] + res;
-                m.G[o] = gg;
-                m.Q[o] = m.Q[o] + rk.cdt * gg;
-            } else if (rk.mode == 2) {   // TakeSSPRK33Step / TakeSSPRK43Step
-                const double Qk = m.Q[o];
-                const double g0 = rk.copyG ? Qk : m.G[o];
-                if (rk.copyG) m.G[o] = g0;
-                m.Q[o] = rk.a * g0 + rk.b * Qk + rk.cdt * res;
+            mxSurfaceAndUpdate(m, rk, sd, g, q, vol, Jn);
+        }
+    }
+};
+
+// ---- split form: SplitDG_ComputeSplitFormFluxes (HyperbolicSplitForm.f90:64-116) + ScalarWeakIntegrals_SplitVolumeDivergence
+//      (DGIntegrals.f90:92-129), QDot = -volInt (SpatialDiscretization.f90:1678).  A pair (a < b) of nodes of a line has ONE two-point
+//      flux, F#(Q_a, Q_b): both nodes evaluate it with the lower node first, as the reference computes it once and mirrors it.
+//      The pair fluxes read the state of OTHER nodes, so the Runge-Kutta update cannot be fused here (a thread would overwrite Q
+//      while another still reads it): this functor stores QDot and MxUpdate applies the stage update afterwards.
+struct MxUpdate {
+    MixedDev m; MxRk rk;
+    __device__ void operator()(long long t) const {      // t over 5 nNodes: one value of the state
+        const double res = m.QDot[t];
+        if (rk.mode == 1) {
+            const double gg = rk.a * m.G[t] + res;
+            m.G[t] = gg;
+            m.Q[t] = m.Q[t] + rk.cdt * gg;
+        } else if (rk.mode == 2) {
+            const double Qk = m.Q[t];
+            const double g0 = rk.copyG ? Qk : m.G[t];
+            if (rk.copyG) m.G[t] = g0;
+            m.Q[t] = rk.a * g0 + rk.b * Qk + rk.cdt * res;
+        }
+    }
+};
+struct MxVolumeSplit {
+    MixedDev m; Phys ph;
+    __device__ void operator()(long long g) const {
+        const MxNode t = mxNode(m, g);
+        const MxSides sd = mxSides(m, t);
+        const int nn[3] = {t.nx, t.ny, t.nz}, ijk[3] = {t.i, t.j, t.k};
+        const long long stride[3] = {1, t.nx, (long long)t.nx * t.ny};
+        double Q[5], vol[5] = {0, 0, 0, 0, 0};
+        for (int q = 0; q < 5; ++q) Q[q] = m.Q[(long long)q * m.nNodes + g];
+        for (int d = 0; d < 3; ++d) {
+            const int n = nn[d], me = ijk[d];
+            const double* sharp = mxSharpD(m, n - 1) + me * n; const double* hat = mxHatD(m, n - 1) + me * n;
+            double ja[3];
+            for (int c = 0; c < 3; ++c) ja[c] = m.Ja[(long long)(3 * d + c) * m.nNodes + g];
+            for (int l = 0; l < n; ++l) {
+                const long long g2 = g + (long long)(l - me) * stride[d];
+                double fs[5];
+                if (l == me) {   // the consistent flux on the diagonal: the contravariant Euler flux of the node
+                    double F[5][3];
+                    euler_flux(ph, Q, F);
+                    for (int q = 0; q < 5; ++q) fs[q] = F[q][0] * ja[0] + F[q][1] * ja[1] + F[q][2] * ja[2];
+                } else {
+                    double Q2[5], ja2[3];
+                    for (int q = 0; q < 5; ++q) Q2[q] = m.Q[(long long)q * m.nNodes + g2];
+                    for (int c = 0; c < 3; ++c) ja2[c] = m.Ja[(long long)(3 * d + c) * m.nNodes + g2];
+                    if (l > me) two_point_flux<true>(ph, Q, Q2, ja, ja2, fs); else two_point_flux<true>(ph, Q2, Q, ja2, ja, fs);
+                }
+                for (int q = 0; q < 5; ++q) vol[q] = vol[q] + sharp[l] * fs[q] + hat[l] * m.Fc[(long long)(d * 5 + q) * m.nNodes + g2];
             }
         }
+        const double Jn = m.J[g];
+        const MxRk none{0, 0.0, 0.0, 0.0, 0};
+        for (int q = 0; q < 5; ++q) mxSurfaceAndUpdate(m, none, sd, g, q, -vol[q], Jn);
     }
 };
 
@@ -597,7 +672,7 @@ struct MxProbe {   // Probe_Update (Probe.f90:330-420); Lagrange vectors padded 
 //              void exchange(const double* send, double* recv, int nNbr, const int* ranks, const long long* offset, const long long* count)
 //              (device buffers, doubles; in order with the launches);  void allreduce(double* hostValues, int n, int op)  (0 max, 1 min, 2 sum)
 // ============================================================================================================================
-struct MxBasis { int N = -1; std::vector<double> x, w, D, hatD, v, b; };
+struct MxBasis { int N = -1, nodeType = 0; std::vector<double> x, w, D, hatD, sharpD, v, b; };
 
 inline bool mxRkCoefficients(int scheme, int k, MxRk& rk, double dt) {
     static const double A3[3] = {0.0, -5.0 / 9.0, -153.0 / 128.0}, C3[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
@@ -631,7 +706,7 @@ struct MixedSolver {
     std::string err;
     std::map<int, MxBasis> sp;                                   // NodalStorage(N)
     std::map<std::pair<int, int>, std::vector<double>> T;        // Tset(Norigin, Ndest)
-    bool haveMesh = false, haveBC = false, haveHalo = false;
+    bool haveMesh = false, haveBC = false, haveHalo = false, splitForm = false, lesWallModel = false;
     int nBoundaryFaces = 0, maxZone = -1, nZones = 0, maxNodes1D = 0, nMpiFaces = 0, nranks = 1;
     std::vector<int> nbrRank; std::vector<long long> nbrNodeOff;   // neighbours and their halo-node ranges (host copies)
     long long launches = 0;
@@ -647,9 +722,11 @@ struct MixedSolver {
     int check() { const char* e = be.error(); if (e) { err = e; return 2; } return 0; }
     template <class F> void launch(const F& f, long long n) { if (n > 0) { be.launch(f, n); ++launches; } }
 
-    void setBasis(int N, const double* x, const double* w, const double* D, const double* hatD, const double* v, const double* b) {
+    void setBasis(int N, int nodeType, const double* x, const double* w, const double* D, const double* hatD, const double* sharpD, const double* v, const double* b) {
         MxBasis& s = sp[N]; const int n = N + 1;
-        s.N = N; s.x.assign(x, x + n); s.w.assign(w, w + n); s.D.assign(D, D + n * n); s.hatD.assign(hatD, hatD + n * n); s.v.assign(v, v + 2 * n); s.b.assign(b, b + 2 * n);
+        s.N = N; s.nodeType = nodeType; s.x.assign(x, x + n); s.w.assign(w, w + n); s.D.assign(D, D + n * n); s.hatD.assign(hatD, hatD + n * n);
+        s.sharpD.assign(n * n, 0.0); if (sharpD) s.sharpD.assign(sharpD, sharpD + n * n);
+        s.v.assign(v, v + 2 * n); s.b.assign(b, b + 2 * n);
     }
     int setInterpolation(int No, int Nd, const double* Tm) {
         if (No < 0 || Nd < 0 || No >= MX_MAXN || Nd >= MX_MAXN) return fail("h3d_set_interpolation: polynomial order out of range");
@@ -681,9 +758,10 @@ struct MixedSolver {
     // element is not in this partition (the reference exchanges it, HexMesh_UpdateMPIFacesPolynomial)
     int setMesh(const H3dPhysics& physics, int nElem, int nFace, const int* elemOrder, const int* faceOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
                 const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone, const double* jGradXi, const double* jGradEta,
-                const double* jGradZeta, const double* jacobian, const double* faceNormal, const double* faceT1, const double* faceT2, const double* faceJacobian) {
-        if (physics.inviscid != H3D_STANDARD_DG) return fail("p-nonconforming meshes: the split-form discretization is not available (StandardDG only)");
-        if (physics.les != H3D_LES_NONE) return fail("p-nonconforming meshes: LES models are not available");
+                const double* jGradZeta, const double* jacobian, const double* volume, const double* faceNormal, const double* faceT1, const double* faceT2,
+                const double* faceJacobian, const double* faceSurface) {
+        splitForm = physics.inviscid == H3D_SPLIT_DG;
+        if (physics.les != H3D_LES_NONE && (!volume || !faceSurface)) return fail("LES needs the element volumes and face surfaces (h3d_set_mesh_p volume / faceSurface): the filter width would be zero");
         if (physics.flowIsNavierStokes && physics.viscous != H3D_VISCOUS_BR1) return fail("p-nonconforming meshes: BR1 is the only viscous discretization available");
         if (nElem < 1 || nFace < 1) return fail("h3d_set_mesh_p: empty mesh");
         m.nElem = nElem; m.nFace = nFace;
@@ -694,6 +772,7 @@ struct MixedSolver {
                 const int N = elemOrder[3 * e + d];
                 if (N < 1 || N >= MX_MAXN) return fail("h3d_set_mesh_p: polynomial orders must lie in 1..15");
                 if (!sp.count(N)) return fail("h3d_set_mesh_p: h3d_set_basis has not been called for every polynomial order of the mesh");
+                if (splitForm && sp[N].nodeType != H3D_GAUSSLOBATTO) return fail("split-form discretization needs Gauss-Lobatto nodes");
                 eN[3 * e + d] = N + 1; maxNodes1D = std::max(maxNodes1D, N + 1);
             }
             eOff[e + 1] = eOff[e] + (long long)eN[3 * e] * eN[3 * e + 1] * eN[3 * e + 2];
@@ -762,6 +841,7 @@ struct MixedSolver {
             ops.insert(ops.end(), s.D.begin(), s.D.end()); ops.insert(ops.end(), s.hatD.begin(), s.hatD.end());
             ops.insert(ops.end(), s.v.begin(), s.v.end()); ops.insert(ops.end(), s.b.begin(), s.b.end());
             ops.insert(ops.end(), s.w.begin(), s.w.end()); ops.insert(ops.end(), s.x.begin(), s.x.end());
+            ops.insert(ops.end(), s.sharpD.begin(), s.sharpD.end());
         }
         for (int a = 0; a < MX_MAXN; ++a) for (int b = 0; b < MX_MAXN; ++b) {
             m.tBase[a][b] = -1;
@@ -792,8 +872,23 @@ struct MixedSolver {
         if (field(&m.Q, 5 * nn) || field(&m.G, 5 * nn) || field(&m.QDot, 5 * nn) || field(&m.Ux, 5 * nn) || field(&m.Uy, 5 * nn) || field(&m.Uz, 5 * nn) ||
             field(&m.Fc, 15 * nn) || field(&m.tr, 15 * (size_t)m.nTrace) || field(&m.fStarE, 5 * (size_t)m.nTrace) || field(&m.unStarE, 15 * (size_t)m.nTrace) ||
             field(&m.fQ, 10 * nf) || field(&m.fU, 30 * nf) || field(&m.fFlux, 15 * nf) || field(&m.partial, 8 * (size_t)std::max(nElem, nFace))) return 2;
-        m.S = nullptr;
+        m.S = nullptr; m.dWall = nullptr; m.fDWall = nullptr; m.lesDelta = nullptr; m.fDelta = nullptr;
+        if (volume && faceSurface) {
+            std::vector<double> dl(nElem), fd(nFace);
+            for (int e = 0; e < nElem; ++e) dl[e] = std::pow(volume[e] / (double)(eN[3 * e] * eN[3 * e + 1] * eN[3 * e + 2]), 1.0 / 3.0);
+            for (int f = 0; f < nFace; ++f) fd[f] = std::sqrt(faceSurface[f] / (double)((fo[6 * f] + 1) * (fo[6 * f + 1] + 1)));
+            if (up(dl, &m.lesDelta) || up(fd, &m.fDelta)) return 2;
+        }
+        lesWallModel = physics.les != H3D_LES_NONE && physics.les_wall_model == 1;
         haveMesh = true;
+        return 0;
+    }
+    // e % geom % dWall, f % geom % dWall (HexMesh.f90:5594-5692) in the packed sizes of this mesh
+    int setWallDistance(const double* dWallElem, const double* dWallFace) {
+        if (!haveMesh) return fail("h3d_set_wall_distance: set the mesh first");
+        if (!dWallElem || !dWallFace) return fail("h3d_set_wall_distance: null array");
+        std::vector<double> a(dWallElem, dWallElem + m.nNodes), b(dWallFace, dWallFace + m.nFaceNodes);
+        if (up(a, &m.dWall) || up(b, &m.fDWall)) return 2;
         return 0;
     }
     int setBoundaryConditions(int nZ, const int* bcType, const double* bcParams) {
@@ -846,6 +941,7 @@ struct MixedSolver {
     int ready() {
         if (!haveMesh) return fail("no mesh");
         if (nMpiFaces > 0 && !haveHalo) return fail("mesh has MPI faces but h3d_set_halo was not called");
+        if (lesWallModel && !m.dWall) return fail("the LES wall model needs the wall distances (h3d_set_wall_distance)");
         if (nBoundaryFaces > 0 && !haveBC) return fail("mesh has boundary faces but h3d_set_boundary_conditions was not called");
         if (nBoundaryFaces > 0 && maxZone >= nZones) return fail("a boundary face refers to a zone beyond the table of h3d_set_boundary_conditions");
         return 0;
@@ -901,10 +997,13 @@ struct MixedSolver {
             prolongGradients();
             if (exchange(3, m.fU)) return 2;
         }
-        launch(MxFlux{m, ph}, m.nNodes);
+        launch(MxFlux{m, ph, splitForm ? 1 : 0}, m.nNodes);
         launch(MxRiemann{m, ph}, m.nFaceNodes);
         launch(MxProject{m, 5, m.fFlux, m.fStarE, -1.0}, m.nTrace);
-        launch(MxVolume{m, rk}, m.nNodes);
+        if (splitForm) {
+            launch(MxVolumeSplit{m, ph}, m.nNodes);
+            if (rk.mode != 0) launch(MxUpdate{m, rk}, 5 * m.nNodes);
+        } else launch(MxVolume{m, rk}, m.nNodes);
         return check();
     }
     int rkStage(const H3dPhysics& physics, int scheme, int k, double dt) {

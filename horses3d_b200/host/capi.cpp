@@ -114,7 +114,13 @@ int h3dhost_interpolation_matrix(int Norigin, int Ndest, int nodeType, double* T
 
 int h3dhost_wall_distance(void* hp) {
     Host* h = (Host*)hp;
-    if (h->mixed) { g_err = "wall distances are not available on p-nonconforming meshes"; return 1; }
+    if (h->mixed) {
+        if (!h->hasGeom) { g_err = "geometry has not been built"; return 1; }
+        const std::vector<double> Xw = wallCoordinatesP(h->mesh, h->geomP);
+        if (Xw.empty()) { g_err = "no wall points: the wall model needs at least one no-slip wall face in the whole mesh"; return 1; }
+        computeWallDistancesP(h->geomP, Xw);
+        return 0;
+    }
     if (!h->hasGeom) { g_err = "geometry has not been built"; return 1; }
     computeWallDistances(h->mesh, h->geom);
     return 0;
@@ -163,7 +169,7 @@ int h3dhost_get_array(void* hp, const char* name, void** ptr, long long* count, 
         DARR("x", G.x) DARR("jGradXi", G.jGradXi) DARR("jGradEta", G.jGradEta) DARR("jGradZeta", G.jGradZeta)
         DARR("jacobian", G.jac) DARR("invJacobian", G.invJac) DARR("volume", G.volume)
         DARR("faceX", G.fx) DARR("faceNormal", G.fnormal) DARR("faceT1", G.ft1) DARR("faceT2", G.ft2)
-        DARR("faceJacobian", G.fjac) DARR("faceSurface", G.fsurface)
+        DARR("faceJacobian", G.fjac) DARR("faceSurface", G.fsurface) DARR("dWall", G.dWall) DARR("faceDWall", G.fdWall)
     }
     DARR("x", h->geom.x) DARR("jGradXi", h->geom.jGradXi) DARR("jGradEta", h->geom.jGradEta) DARR("jGradZeta", h->geom.jGradZeta)
     DARR("jacobian", h->geom.jac) DARR("invJacobian", h->geom.invJac) DARR("volume", h->geom.volume)
@@ -249,6 +255,7 @@ int h3dhost_inherit_geometry(void* childp, void* parentp) {
         gather(G.fx, g.fx, G.fOff, g.fOff, c->halo.globalFace, 3); gather(G.fnormal, g.fnormal, G.fOff, g.fOff, c->halo.globalFace, 3);
         gather(G.ft1, g.ft1, G.fOff, g.fOff, c->halo.globalFace, 3); gather(G.ft2, g.ft2, G.fOff, g.fOff, c->halo.globalFace, 3);
         gather(G.fjac, g.fjac, G.fOff, g.fOff, c->halo.globalFace, 1);
+        if (!G.dWall.empty()) { gather(G.dWall, g.dWall, G.eOff, g.eOff, c->halo.globalElem, 1); gather(G.fdWall, g.fdWall, G.fOff, g.fOff, c->halo.globalFace, 1); }
         c->hasGeom = true; c->mixed = true;
         return 0;
     }

@@ -46,6 +46,7 @@ struct HostGeometryP {
     std::vector<double> x, jGradXi, jGradEta, jGradZeta, jac, invJac, volume;
     // face arrays at the face order: [j][i][c]
     std::vector<double> fx, fnormal, ft1, ft2, fjac, fsurface;
+    std::vector<double> dWall, fdWall;          // distance of every element / face node to the nearest no-slip wall node (optional)
     const NodalStorage& S(int N) { auto it = sp.find(N); if (it == sp.end()) { sp[N].construct(nodeType, N); return sp[N]; } return it->second; }
 };
 
@@ -300,6 +301,33 @@ inline bool buildGeometryP(const HostMesh& m0, const int* Nxyz, int nodeType, Ho
         }
     }
     return true;
+}
+
+// HexMesh_ComputeWallDistances (HexMesh.f90:5594-5692) on a p-nonconforming mesh: the wall nodes are the nodes of the no-slip faces at
+// their face orders
+inline std::vector<double> wallCoordinatesP(const HostMesh& m, const HostGeometryP& g) {
+    std::vector<double> Xw;
+    for (int f = 0; f < m.nFaces; ++f) {
+        if (m.faceType[f] != HMESH_BOUNDARY || m.faceZone[f] < 0 || m.bcs[m.faceZone[f]].type != "noslipwall") continue;
+        Xw.insert(Xw.end(), &g.fx[3 * (size_t)g.fOff[f]], &g.fx[3 * (size_t)g.fOff[f + 1]]);
+    }
+    return Xw;
+}
+inline void computeWallDistancesP(HostGeometryP& g, const std::vector<double>& Xw) {
+    const size_t nW = Xw.size() / 3;
+    auto dist = [&](const double* xP) {
+        double mn = 1.7976931348623157e308;
+        for (size_t q = 0; q < nW; ++q) {
+            const double d0 = xP[0] - Xw[3 * q], d1 = xP[1] - Xw[3 * q + 1], d2 = xP[2] - Xw[3 * q + 2];
+            mn = std::fmin(mn, d0 * d0 + d1 * d1 + d2 * d2);
+        }
+        return std::sqrt(mn);
+    };
+    g.dWall.resize(g.x.size() / 3); g.fdWall.resize(g.fx.size() / 3);
+#pragma omp parallel for schedule(static)
+    for (long long q = 0; q < (long long)g.dWall.size(); ++q) g.dWall[q] = dist(&g.x[3 * q]);
+#pragma omp parallel for schedule(static)
+    for (long long q = 0; q < (long long)g.fdWall.size(); ++q) g.fdWall[q] = dist(&g.fx[3 * q]);
 }
 
 }  // namespace h3d

@@ -269,10 +269,24 @@ contains
       end if
 !
 !     LES wall model: distances computed by the reference over ALL ranks (HexMesh.f90:5594-5780)
-      if ( p % les_wall_model == 1 ) then
-         allocate(dWe(n3*nE), dWf(n2*nF))
-         do eID = 1, nE ; dWe(n3*(eID-1)+1 : n3*eID) = reshape(mesh % elements(eID) % geom % dWall, [n3]) ; end do
-         do fID = 1, nF ; dWf(n2*(fID-1)+1 : n2*fID) = reshape(mesh % faces(fID) % geom % dWall, [n2]) ; end do
+      if ( p % les_wall_model == 1 ) then                               ! packed at the elements' / faces' own sizes (uniform or not)
+         nE = size(mesh % elements);  nF = size(mesh % faces)
+         pos = 0
+         do eID = 1, nE ; pos = pos + size(mesh % elements(eID) % geom % dWall) ; end do
+         allocate(dWe(pos))
+         pos = 0
+         do fID = 1, nF ; pos = pos + size(mesh % faces(fID) % geom % dWall) ; end do
+         allocate(dWf(pos))
+         pos = 0
+         do eID = 1, nE
+            k = size(mesh % elements(eID) % geom % dWall)
+            dWe(pos+1 : pos+k) = reshape(mesh % elements(eID) % geom % dWall, [k]);  pos = pos + k
+         end do
+         pos = 0
+         do fID = 1, nF
+            k = size(mesh % faces(fID) % geom % dWall)
+            dWf(pos+1 : pos+k) = reshape(mesh % faces(fID) % geom % dWall, [k]);  pos = pos + k
+         end do
          call check(h3d_set_wall_distance(h3d, dWe, dWf), "h3d_set_wall_distance")
       end if
 !

@@ -1471,7 +1471,7 @@ int orc_set_basis(void* p, int N, int nodeType, const double* x, const double* w
     // every order set so far stays registered: NodalStorage(N) of a p-nonconforming mesh
     if (!o.pdata) o.pdata = new PData();
     Basis1& bs = PD(o).sp[N];
-    bs.N = N; bs.n = n; bs.x = o.x; bs.w = o.w; bs.D = o.D; bs.hatD = o.hatD; bs.v = o.v; bs.b = o.b;
+    bs.N = N; bs.n = n; bs.nodeType = nodeType; bs.x = o.x; bs.w = o.w; bs.D = o.D; bs.hatD = o.hatD; bs.sharpD = o.sharpD; bs.v = o.v; bs.b = o.b;
     return 0;
 }
 
@@ -1492,9 +1492,13 @@ int orc_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const in
                    const double* faceJacobian, const double* faceX, const double* faceSurface) {
     Oracle& o = *(Oracle*)p;
     if (!o.pdata) { o.err = "set_basis must precede set_mesh_p"; return 1; }
-    if (o.ph.inviscid != H3D_STANDARD_DG || o.ph.les != H3D_LES_NONE || (o.ph.flowIsNavierStokes && o.ph.viscous != H3D_VISCOUS_BR1)) {
-        o.err = "p-nonconforming meshes: StandardDG with BR1 (or Euler), no LES"; return 1; }
+    if (o.ph.flowIsNavierStokes && o.ph.viscous != H3D_VISCOUS_BR1) { o.err = "p-nonconforming meshes: BR1 (or Euler)"; return 1; }
+    if (o.ph.les != H3D_LES_NONE && (!volume || !faceSurface)) { o.err = "LES needs the element volumes and face surfaces"; return 1; }
     PData& P = PD(o);
+    if (o.ph.inviscid == H3D_SPLIT_DG) for (int q = 0; q < 3 * nElem; ++q) {
+        auto it = P.sp.find(elemOrder[q]);
+        if (it != P.sp.end() && it->second.nodeType != H3D_GAUSSLOBATTO) { o.err = "split-form discretization needs Gauss-Lobatto nodes"; return 1; }
+    }
     o.mixed = true; o.nElem = nElem; o.nFace = nFace;
     o.elemFace.assign(elemFace, elemFace + 6 * (size_t)nElem); o.elemFaceSide.assign(elemFaceSide, elemFaceSide + 6 * (size_t)nElem);
     o.faceElem.assign(faceElem, faceElem + 2 * (size_t)nFace); o.faceElemSide.assign(faceElemSide, faceElemSide + 2 * (size_t)nFace);
@@ -1582,8 +1586,8 @@ int orc_set_boundary_conditions(void* p, int nZones, const int* bcType, const do
 }
 
 int orc_set_wall_distance(void* p, const double* dWallElem, const double* dWallFace) {
-    if (((Oracle*)p)->mixed) { ((Oracle*)p)->err = "the wall distance is not available on p-nonconforming meshes"; return 1; }
     Oracle& o = *(Oracle*)p;
+    if (o.mixed) { o.dWall.assign(dWallElem, dWallElem + PD(o).eOff[o.nElem]); o.fdWall.assign(dWallFace, dWallFace + PD(o).fOff[o.nFace]); return 0; }
     o.dWall.assign(dWallElem, dWallElem + (size_t)o.nElem * o.n3()); o.fdWall.assign(dWallFace, dWallFace + (size_t)o.nFace * o.n * o.n);
     return 0;
 }

@@ -114,20 +114,21 @@ int emu_set_physics(void* p, const H3dPhysics* ph) {
     h->physics = *ph; h->havePhysics = true;
     return 0;
 }
-int emu_set_basis(void* p, int N, int, const double* x, const double* w, const double* D, const double* hatD, const double*, const double* v, const double* b) {
-    ((Emu*)p)->mx->setBasis(N, x, w, D, hatD, v, b); return 0;
+int emu_set_basis(void* p, int N, int nodeType, const double* x, const double* w, const double* D, const double* hatD, const double* sharpD, const double* v, const double* b) {
+    ((Emu*)p)->mx->setBasis(N, nodeType, x, w, D, hatD, sharpD, v, b); return 0;
 }
 int emu_set_interpolation(void* p, int No, int Nd, const double* T) { Emu* h = (Emu*)p; return done(h, h->mx->setInterpolation(No, Nd, T)); }
 int emu_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const int* faceOrder, const int* elemFace, const int* elemFaceSide, const int* faceElem,
                    const int* faceElemSide, const int* faceRot, const int* faceType, const int* faceZone, const double* jGradXi, const double* jGradEta,
-                   const double* jGradZeta, const double* jacobian, const double*, const double*, const double* faceNormal, const double* faceT1,
-                   const double* faceT2, const double* faceJacobian, const double*, const double*) {
+                   const double* jGradZeta, const double* jacobian, const double*, const double* volume, const double* faceNormal, const double* faceT1,
+                   const double* faceT2, const double* faceJacobian, const double*, const double* faceSurface) {
     Emu* h = (Emu*)p;
     if (!h->havePhysics) { h->err = "set_physics must precede set_mesh_p"; return 1; }
     h->mx->ph = h->ph;
     return done(h, h->mx->setMesh(h->physics, nElem, nFace, elemOrder, faceOrder, elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone, jGradXi,
-                                   jGradEta, jGradZeta, jacobian, faceNormal, faceT1, faceT2, faceJacobian));
+                                   jGradEta, jGradZeta, jacobian, volume, faceNormal, faceT1, faceT2, faceJacobian, faceSurface));
 }
+int emu_set_wall_distance(void* p, const double* a, const double* b) { Emu* h = (Emu*)p; return done(h, h->mx->setWallDistance(a, b)); }
 int emu_set_boundary_conditions(void* p, int nZones, const int* bcType, const double* bcParams) { Emu* h = (Emu*)p; return done(h, h->mx->setBoundaryConditions(nZones, bcType, bcParams)); }
 int emu_upload_Q(void* p, const double* Q) { Emu* h = (Emu*)p; return done(h, h->mx->uploadQ(Q)); }
 int emu_download(void* p, double* Q, double* QDot, double* Ux, double* Uy, double* Uz) { Emu* h = (Emu*)p; return done(h, h->mx->download(Q, QDot, Ux, Uy, Uz)); }

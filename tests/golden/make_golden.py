@@ -36,6 +36,7 @@ CASES_MIXED = {
     "box_ns_mixed_p2to4": dict(bc=None, lo=2, hi=4, kw=dict(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")),
     "channel_ns_mixed_p2to4": dict(bc="channel", lo=2, hi=4, kw=dict(flow="NS", mach=0.3, reynolds=150.0, riemann="roe")),
     "box_euler_mixed_p1to5": dict(bc=None, lo=1, hi=5, kw=dict(flow="Euler", mach=0.3, riemann="standard roe")),
+    "box_euler_split_pirozzoli_mixed_p2to5": dict(bc=None, lo=2, hi=5, nodes=GAUSSLOBATTO, kw=dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli", riemann="roe")),
 }
 
 
@@ -43,7 +44,7 @@ def run_mixed(api, name):
     import mixed_cases as MC
     c = CASES_MIXED[name]
     phys = make_physics(**c["kw"])
-    mesh = MC.channel(phys, 2, c["lo"], c["hi"], seed=3) if c["bc"] else MC.periodic_box(2, c["lo"], c["hi"], seed=5)
+    mesh = MC.channel(phys, 2, c["lo"], c["hi"], seed=3) if c["bc"] else MC.periodic_box(2, c["lo"], c["hi"], seed=5, nodes=c.get("nodes", GAUSS))
     sem = DGSem(api, mesh, phys)
     sem.set_Q(MC.smooth_state(sem, phys.Mach))
     sem.ComputeTimeDerivative(0.0)

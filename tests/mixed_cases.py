@@ -24,8 +24,9 @@ CHANNEL_BCS = [("front", "periodic", "back"), ("back", "periodic", "front"), ("b
                ("left", "inflow", None), ("right", "outflow", None)]
 
 
-def channel(phys, ne=3, lo=2, hi=4, seed=3, nodes=GAUSS):
-    """Box with the four boundary conditions of the reference's cylinder cases and random element orders."""
+def channel(phys, ne=3, lo=2, hi=4, seed=3, nodes=GAUSS, uniform=None):
+    """Box with the four boundary conditions of the reference's cylinder cases and random element orders (uniform=N: the same mesh
+    through the uniform-order geometry).  With the LES wall model the wall distances are computed too."""
     params = []
     for _, t, _c in CHANNEL_BCS:
         if t == "inflow":
@@ -37,7 +38,10 @@ def channel(phys, ne=3, lo=2, hi=4, seed=3, nodes=GAUSS):
         else:
             params.append(bc_parameters(t, phys))
     m = HostMesh.box(ne, amp=0.1, shuffle=True, seed=seed).connect(CHANNEL_BCS, np.array(params))
-    return m.geometry_p(random_orders(m.nElem, lo, hi, seed), nodes)
+    m = m.geometry(uniform, nodes, reference_order=True) if uniform else m.geometry_p(random_orders(m.nElem, lo, hi, seed), nodes)
+    if phys.les_wall_model:
+        m.wall_distances()
+    return m
 
 
 def smooth_state(sem, mach):

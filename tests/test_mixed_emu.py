@@ -62,12 +62,67 @@ def test_k13_cylinder_different_orders_through_the_device_functors():
     assert np.array_equal(res, res0) and cd == cd0 and cl == cl0 and wake_u == wake0
 
 
+SPLIT = [dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli", riemann="roe"),
+         dict(flow="Euler", mach=0.3, inviscid="split-form", averaging="standard", riemann="lax-friedrichs"),
+         dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="kennedy-gruber", riemann="roe"),
+         dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="chandrasekar", riemann="central", gradient_variables="entropy"),
+         dict(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="ducros", riemann="standard roe")]
+
+
+@pytest.mark.parametrize("kw", SPLIT, ids=lambda k: k["flow"] + "-" + k["averaging"])
+def test_split_form_on_random_orders(kw):
+    """SplitDG on a p-nonconforming mesh: the two-point fluxes of every line with the element's own sharpD per direction."""
+    both(lambda: MC.periodic_box(3, 2, 5, seed=17, nodes=GAUSSLOBATTO), make_physics(**kw))
+
+
+def test_mixed_oracle_split_form_with_uniform_orders_equals_the_uniform_oracle():
+    """Anchor of the split form on such meshes: with one order for every element the restatement is bit-identical to the uniform-order
+    oracle, whose split form is pinned by the reference's TaylorGreenKEPEC, BoxAroundCirclePirozzoli and Convergence_* cases."""
+    from horses3d_b200.dgsem import DGSem, taylor_green_ic
+    from horses3d_b200.hostmesh import HostMesh
+    for kw in SPLIT[::2]:
+        phys, out = make_physics(**kw), []
+        for mixed in (False, True):
+            m = HostMesh.box(3, amp=0.15, shuffle=True).connect()
+            m = m.geometry_p([4, 4, 4], GAUSSLOBATTO) if mixed else m.geometry(4, GAUSSLOBATTO, reference_order=True)
+            sem = DGSem(oracle_api.OracleApi(), m, phys)
+            sem.set_Q(taylor_green_ic(sem.node_coordinates().reshape(-1, 3), p0=1.0 / (1.4 * 0.3 ** 2)).reshape(sem._shape))
+            sem.TakeRK3Step(0.0, 1.0e-3, ctd_after_step=True)
+            out.append({k: v.reshape(-1, 5) for k, v in sem.download(Q=True, QDot=True).items()})
+        assert all(np.array_equal(out[0][k], out[1][k]) for k in out[0]), kw
+
+
+LES = [dict(les="smagorinsky", les_wall_model="linear"), dict(les="smagorinsky"), dict(les="wale"), dict(les="vreman")]
+
+
+@pytest.mark.parametrize("kw", LES, ids=lambda k: k["les"] + ("-wall" if k.get("les_wall_model") else ""))
+def test_les_models_on_random_orders(kw):
+    """Filter widths from the element's / face's own orders (SpatialDiscretization.f90:420, 1378), wall distances at the packed nodes."""
+    phys = make_physics(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", **kw)
+    both(lambda: MC.channel(phys), phys, zone=2)
+
+
+def test_mixed_oracle_les_with_uniform_orders_equals_the_uniform_oracle():
+    """Anchor of the LES models on such meshes: bit-identical to the uniform-order oracle (pinned by CylinderSmagorinsky / WALE / Vreman)."""
+    from horses3d_b200.dgsem import DGSem
+    for kw in LES[::2]:
+        phys, out = make_physics(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", **kw), []
+        for uniform in (3, None):
+            sem = DGSem(oracle_api.OracleApi(), MC.channel(phys, lo=3, hi=3, uniform=uniform), phys)
+            sem.set_Q(MC.smooth_state(sem, 0.3).reshape(sem._shape))
+            sem.TakeRK3Step(0.0, 1.0e-3, ctd_after_step=True)
+            out.append({k: v.reshape(-1, 5) for k, v in sem.download(Q=True, QDot=True, gradients=True).items()})
+        assert all(np.array_equal(out[0][k], out[1][k]) for k in out[0]), kw
+
+
 def test_unsupported_configurations_are_refused():
     from horses3d_b200.capi import H3dError
     from horses3d_b200.dgsem import DGSem
-    for kw in (dict(inviscid="split-form", averaging="pirozzoli"), dict(viscous="br2"), dict(les="smagorinsky")):
+    for kw in (dict(viscous="br2"), dict(viscous="ip")):
         with pytest.raises(H3dError):
             DGSem(EmuApi(), MC.periodic_box(2, 2, 3, seed=1, nodes=GAUSSLOBATTO), make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe", **kw))
+    with pytest.raises(H3dError):      # the split form needs Gauss-Lobatto nodes
+        DGSem(EmuApi(), MC.periodic_box(2, 2, 3, seed=1), make_physics(flow="Euler", mach=0.3, inviscid="split-form", averaging="pirozzoli"))
 
 
 def _partitioned(world_size, mesh_fn, phys, method, zone=None, scheme="rk3"):
