@@ -1565,7 +1565,7 @@ int h3d_rk_step(h3d_handle h, int scheme, double t, double dt, int ctd_after_ste
 }
 
 int h3d_enable_limiter(h3d_handle h, int enabled, double minimum) {
-    MX_UNSUPPORTED("the stage limiter");
+    if (h->mixedMode) return mxDone(h, h->mx->enableLimiter(enabled, minimum));
     if (!h->haveMesh) { h->err = "h3d_enable_limiter: set the mesh first"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     if (enabled && !h->dVolume) {
@@ -1740,7 +1740,7 @@ int h3d_probe(h3d_handle h, int nProbes, const int* elem, const int* variable, c
 }
 
 int h3d_statistics_update(h3d_handle h, int reset) {
-    MX_UNSUPPORTED("the statistics monitor");
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); return mxDone(h, h->mx->statisticsUpdate(h->physics, reset)); }
     if (checkReady(h)) return 1;
     CTX_CHECK(cudaSetDevice(h->device));
     const size_t nn = (size_t)h->nElem * h->n * h->n * h->n;
@@ -1758,7 +1758,7 @@ int h3d_statistics_update(h3d_handle h, int reset) {
 }
 
 int h3d_statistics_download(h3d_handle h, double* data, int* nVars, int* nSamples) {
-    MX_UNSUPPORTED("the statistics monitor");
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); return mxDone(h, h->mx->statisticsDownload(data, nVars, nSamples)); }
     if (!h->dStats) { h->err = "no statistics have been accumulated"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     *nVars = h->statVars; *nSamples = h->statSamples;

@@ -67,6 +67,7 @@ struct MixedDev {
     const double *Ja, *J, *invJ;            // 9 (3 d + c), 1, 1
     const double *lesDelta, *fDelta;        // [nElem] (V / product(Nxyz+1))^(1/3), [nFace] sqrt(surface / product(Nf+1)) (SpatialDiscretization.f90:420, 1378)
     const double *dWall, *fDWall;           // [nNodes], [nFaceNodes] wall distances (LES wall model) or nullptr
+    const double *volume;                   // [nElem] e % geom % volume (stage limiter) or nullptr
     // ---- element-side fields at the element's face order [c][nTrace]
     double *tr;                             // 15: traces before the adaption to the face order
     double *fStarE, *unStarE;               // 5 / 15 (d*5 + q)
@@ -505,6 +506,75 @@ struct MxVolumeSplit {
     }
 };
 
+// ---- stage_limiter (ExplicitMethods.f90:1755-1847): one thread per element; density, then pressure, scaled towards the element
+//      average so that they stay above min(minimum, average)
+struct MxLimiter {
+    MixedDev m; Phys ph; double limiterMin;
+    __device__ void operator()(long long e) const {
+        const int nx = m.eN[3 * e], ny = m.eN[3 * e + 1], nz = m.eN[3 * e + 2];
+        const double* wx = mxW(m, nx - 1); const double* wy = mxW(m, ny - 1); const double* wz = mxW(m, nz - 1);
+        const long long g0 = m.eOff[e], g1 = m.eOff[e + 1];
+        double Qavg[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            const long long g = g0 + ((long long)k * ny + j) * nx + i;
+            for (int q = 0; q < 5; ++q) Qavg[q] = Qavg[q] + m.Q[(long long)q * m.nNodes + g] * wx[i] * wy[j] * wz[k] * m.J[g];
+        }
+        for (int q = 0; q < 5; ++q) Qavg[q] = Qavg[q] / m.volume[e];
+        double minrho = 1.7976931348623157e308;
+        for (long long g = g0; g < g1; ++g) { const double rho = m.Q[g]; if (rho < minrho) minrho = rho; }
+        if (Qavg[0] != minrho) {
+            const double mm = fmin(limiterMin, Qavg[0]);
+            const double theta = fabs((Qavg[0] - mm) / (Qavg[0] - minrho));
+            if (theta <= 1.0) for (long long g = g0; g < g1; ++g) m.Q[g] = theta * (m.Q[g] - Qavg[0]) + Qavg[0];
+        }
+        double minp = 1.7976931348623157e308, pavg = 0.0;
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            const long long g = g0 + ((long long)k * ny + j) * nx + i;
+            double Q[5];
+            for (int q = 0; q < 5; ++q) Q[q] = m.Q[(long long)q * m.nNodes + g];
+            const double p = ph.gm1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
+            pavg = pavg + p * wx[i] * wy[j] * wz[k] * m.J[g];
+            if (p < minp) minp = p;
+        }
+        pavg = pavg / m.volume[e];
+        if (pavg != minp) {
+            const double mm = fmin(limiterMin, pavg);
+            const double theta = fabs((pavg - mm) / (pavg - minp));
+            if (theta <= 1.0) for (long long g = g0; g < g1; ++g) for (int q = 0; q < 5; ++q) {
+                double& v = m.Q[(long long)q * m.nNodes + g];
+                v = theta * (v - Qavg[q]) + Qavg[q];
+            }
+        }
+    }
+};
+
+// ---- StatisticsMonitor_UpdateValues (StatisticsMonitor.f90:279-540): running averages, data [var][nNodes] -----------------------
+struct MxStatistics {
+    MixedDev m; int nv; double ratio, inv; double* data;
+    __device__ void operator()(long long t) const {
+        const long long nn = m.nNodes;
+        double Q[5];
+        for (int q = 0; q < 5; ++q) Q[q] = m.Q[(long long)q * nn + t];
+        const double r1 = inv / Q[0], r2 = inv / pow2(Q[0]);
+        double* d = data + t;
+        d[0 * nn] = d[0 * nn] * ratio + Q[1] * r1;
+        d[1 * nn] = d[1 * nn] * ratio + Q[2] * r1;
+        d[2 * nn] = d[2 * nn] * ratio + Q[3] * r1;
+        d[3 * nn] = d[3 * nn] * ratio + pow2(Q[1]) * r2;
+        d[4 * nn] = d[4 * nn] * ratio + pow2(Q[2]) * r2;
+        d[5 * nn] = d[5 * nn] * ratio + pow2(Q[3]) * r2;
+        d[6 * nn] = d[6 * nn] * ratio + Q[1] * Q[2] * r2;
+        d[7 * nn] = d[7 * nn] * ratio + Q[1] * Q[3] * r2;
+        d[8 * nn] = d[8 * nn] * ratio + Q[2] * Q[3] * r2;
+        for (int q = 0; q < 5; ++q) d[(long long)(9 + q) * nn] = d[(long long)(9 + q) * nn] * ratio + Q[q] * inv;
+        if (nv == 29) for (int q = 0; q < 5; ++q) {
+            d[(long long)(14 + q) * nn] = d[(long long)(14 + q) * nn] * ratio + m.Ux[(long long)q * nn + t] * inv;
+            d[(long long)(19 + q) * nn] = d[(long long)(19 + q) * nn] * ratio + m.Uy[(long long)q * nn + t] * inv;
+            d[(long long)(24 + q) * nn] = d[(long long)(24 + q) * nn] * ratio + m.Uz[(long long)q * nn + t] * inv;
+        }
+    }
+};
+
 // ---- reductions: one thread per element (face), nodes in the reference's order; partial[e][8] --------------------------------
 struct MxRedResidual {   // ComputeMaxResiduals (DGSEMClass.f90:770-856) + checkForNan on Q
     MixedDev m;
@@ -582,6 +652,20 @@ struct MxRedIntegral {   // ScalarVolumeIntegral (VolumeIntegrals.f90:76-120, 16
                 } break;
                 case H3D_INT_VELOCITY: loc = loc + wx[i] * wy[j] * wz[k] * sqrt(pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) / Q[0] * m.J[g]; break;
                 case H3D_INT_INTERNAL_ENERGY: loc = loc + wJ * Q[4]; break;
+                case H3D_INT_ENTROPY: { const double pr = pressure(ph, Q); const double sp = log(pr) - ph.gamma * log(Q[0]); loc = loc + wJ * sp; } break;
+                case H3D_INT_MATH_ENTROPY: {
+                    const double pr = pressure(ph, Q); const double sp = log(pr) - ph.gamma * log(Q[0]);
+                    const double ms = -Q[0] * sp / ph.gm1;
+                    loc = loc + wJ * ms;
+                } break;
+                case H3D_INT_ENTROPY_RATE: {      // NSGradientVariables_ENTROPY whatever the gradient variables of the run
+                    Phys pe = ph; pe.gradVars = H3D_GRADVARS_ENTROPY;
+                    double EV[5];
+                    get_gradients(pe, Q, EV);
+                    double dot = 0.0;
+                    for (int q = 0; q < 5; ++q) dot = dot + QD[q] * EV[q];
+                    loc = loc + wJ * dot;
+                } break;
                 default: break;
             }
         }
@@ -706,7 +790,9 @@ struct MixedSolver {
     std::string err;
     std::map<int, MxBasis> sp;                                   // NodalStorage(N)
     std::map<std::pair<int, int>, std::vector<double>> T;        // Tset(Norigin, Ndest)
-    bool haveMesh = false, haveBC = false, haveHalo = false, splitForm = false, lesWallModel = false;
+    bool haveMesh = false, haveBC = false, haveHalo = false, splitForm = false, lesWallModel = false, limited = false;
+    double limiterMin = 1e-13;                 // LIMITED, LIMITER_MIN (ExplicitMethods.f90:28-29)
+    double* dStats = nullptr; int statVars = 0, statSamples = 0;
     int nBoundaryFaces = 0, maxZone = -1, nZones = 0, maxNodes1D = 0, nMpiFaces = 0, nranks = 1;
     std::vector<int> nbrRank; std::vector<long long> nbrNodeOff;   // neighbours and their halo-node ranges (host copies)
     long long launches = 0;
@@ -879,6 +965,8 @@ struct MixedSolver {
             for (int f = 0; f < nFace; ++f) fd[f] = std::sqrt(faceSurface[f] / (double)((fo[6 * f] + 1) * (fo[6 * f + 1] + 1)));
             if (up(dl, &m.lesDelta) || up(fd, &m.fDelta)) return 2;
         }
+        m.volume = nullptr;
+        if (volume) { std::vector<double> v(volume, volume + nElem); if (up(v, &m.volume)) return 2; }
         lesWallModel = physics.les != H3D_LES_NONE && physics.les_wall_model == 1;
         haveMesh = true;
         return 0;
@@ -1010,7 +1098,38 @@ struct MixedSolver {
         MxRk rk;
         if (!mxRkStages(scheme)) return fail("unknown Runge-Kutta scheme");
         if (!mxRkCoefficients(scheme, k, rk, dt)) return fail("Runge-Kutta stage out of range");
-        return residual(physics, rk);
+        const int rc = residual(physics, rk);
+        if (rc || !limited || rk.mode != 2) return rc;
+        launch(MxLimiter{m, ph, limiterMin}, m.nElem);      // stage_limiter after every SSPRK stage (ExplicitMethods.f90:1050-1052, 1177-1179)
+        return check();
+    }
+    int enableLimiter(int enabled, double minimum) {
+        if (!haveMesh) return fail("h3d_enable_limiter: set the mesh first");
+        if (enabled && !m.volume) return fail("the limiter needs the element volumes (h3d_set_mesh_p: volume)");
+        limited = enabled != 0;
+        if (minimum > 0.0) limiterMin = minimum;
+        return 0;
+    }
+    int statisticsUpdate(const H3dPhysics& physics, int reset) {
+        if (ready()) return 1;
+        const int nv = physics.computeGradients ? 29 : 14;
+        if (!dStats || statVars != nv) { if (field(&dStats, (size_t)nv * m.nNodes)) return 2; statVars = nv; statSamples = 0; reset = 0; }
+        if (reset) { std::vector<double> z((size_t)nv * m.nNodes, 0.0); be.upload(dStats, z.data(), z.size()); statSamples = 0; }
+        const double inv = 1.0 / (statSamples + 1), ratio = statSamples * inv;
+        launch(MxStatistics{m, nv, ratio, inv, dStats}, m.nNodes);
+        ++statSamples;
+        return check();
+    }
+    int statisticsDownload(double* data, int* nVars, int* nSamples) {
+        if (!dStats) return fail("no statistics have been accumulated");
+        *nVars = statVars; *nSamples = statSamples;
+        if (!data) return 0;
+        const size_t nn = (size_t)m.nNodes;
+        hBuf.resize((size_t)statVars * nn);
+        be.download(hBuf.data(), dStats, hBuf.size());
+        if (check()) return 2;
+        for (size_t g = 0; g < nn; ++g) for (int c = 0; c < statVars; ++c) data[g * statVars + c] = hBuf[(size_t)c * nn + g];
+        return 0;
     }
     int rkStep(const H3dPhysics& physics, int scheme, double dt, int ctdAfterStep) {
         const int ns = mxRkStages(scheme);
@@ -1048,7 +1167,8 @@ struct MixedSolver {
     int volumeIntegral(const H3dPhysics& physics, int kind, double* val) {
         if (!haveMesh) return fail("no mesh");
         switch (kind) {
-            case H3D_INT_VOLUME: case H3D_INT_KINETIC_ENERGY: case H3D_INT_KINETIC_ENERGY_RATE: case H3D_INT_VELOCITY: case H3D_INT_INTERNAL_ENERGY: break;
+            case H3D_INT_VOLUME: case H3D_INT_KINETIC_ENERGY: case H3D_INT_KINETIC_ENERGY_RATE: case H3D_INT_VELOCITY: case H3D_INT_INTERNAL_ENERGY:
+            case H3D_INT_ENTROPY: case H3D_INT_MATH_ENTROPY: case H3D_INT_ENTROPY_RATE: break;
             case H3D_INT_ENSTROPHY: if (!physics.computeGradients) return fail("volume integral needs gradients"); break;
             default: return fail("this volume integral is not available on p-nonconforming meshes");
         }

@@ -1651,30 +1651,36 @@ int rkStages(int scheme) {
 }
 // stage_limiter (ExplicitMethods.f90:1755-1847)
 void stageLimiter(Oracle& o) {
-    const int n = o.n; Idx ix{n};
+    Idx ix{o.n};
     const double gm1 = o.ph.gammaMinus1, LIMITER_MIN = o.limiterMin;
 #pragma omp parallel for schedule(static)
     for (int e = 0; e < o.nElem; ++e) {
+        // p-nonconforming meshes: the element's own nodal storages (ExplicitMethods.f90:1776-1779)
+        const int nx = o.mixed ? PD(o).Nxyz[3 * e] + 1 : o.n, ny = o.mixed ? PD(o).Nxyz[3 * e + 1] + 1 : o.n, nz = o.mixed ? PD(o).Nxyz[3 * e + 2] + 1 : o.n;
+        const double* wx = o.mixed ? PD(o).sp.at(nx - 1).w.data() : o.w.data(); const double* wy = o.mixed ? PD(o).sp.at(ny - 1).w.data() : o.w.data();
+        const double* wz = o.mixed ? PD(o).sp.at(nz - 1).w.data() : o.w.data();
+        const size_t g0 = o.mixed ? PD(o).eOff[e] : ix.node(e, 0, 0, 0);
+        const int n3 = nx * ny * nz;
         double Qavg[5] = {0, 0, 0, 0, 0};
-        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
-            size_t g = ix.node(e, i, j, k);
-            for (int q = 0; q < 5; ++q) Qavg[q] = Qavg[q] + o.Q[5 * g + q] * o.w[i] * o.w[j] * o.w[k] * o.jac[g];
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            size_t g = g0 + (size_t)(k * ny + j) * nx + i;
+            for (int q = 0; q < 5; ++q) Qavg[q] = Qavg[q] + o.Q[5 * g + q] * wx[i] * wy[j] * wz[k] * o.jac[g];
         }
         for (int q = 0; q < 5; ++q) Qavg[q] = Qavg[q] / o.volume[e];
         double minrho = std::numeric_limits<double>::max();
-        for (int t = 0; t < n * n * n; ++t) { double rho = o.Q[5 * (ix.node(e, 0, 0, 0) + t)]; if (rho < minrho) minrho = rho; }
+        for (int t = 0; t < n3; ++t) { double rho = o.Q[5 * (g0 + t)]; if (rho < minrho) minrho = rho; }
         if (Qavg[0] != minrho) {
             double m = std::fmin(LIMITER_MIN, Qavg[0]);
             double theta = std::fabs((Qavg[0] - m) / (Qavg[0] - minrho));
             if (theta <= 1.0)
-                for (int t = 0; t < n * n * n; ++t) { double& r = o.Q[5 * (ix.node(e, 0, 0, 0) + t)]; r = theta * (r - Qavg[0]) + Qavg[0]; }
+                for (int t = 0; t < n3; ++t) { double& r = o.Q[5 * (g0 + t)]; r = theta * (r - Qavg[0]) + Qavg[0]; }
         }
         double minp = std::numeric_limits<double>::max(), pavg = 0.0;
-        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
-            size_t g = ix.node(e, i, j, k);
+        for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+            size_t g = g0 + (size_t)(k * ny + j) * nx + i;
             const double* Q = &o.Q[5 * g];
             double p = gm1 * (Q[4] - 0.5 * (Q[1] * Q[1] + Q[2] * Q[2] + Q[3] * Q[3]) / Q[0]);
-            pavg = pavg + p * o.w[i] * o.w[j] * o.w[k] * o.jac[g];
+            pavg = pavg + p * wx[i] * wy[j] * wz[k] * o.jac[g];
             if (p < minp) minp = p;
         }
         pavg = pavg / o.volume[e];
@@ -1682,7 +1688,7 @@ void stageLimiter(Oracle& o) {
             double m = std::fmin(LIMITER_MIN, pavg);
             double theta = std::fabs((pavg - m) / (pavg - minp));
             if (theta <= 1.0)
-                for (int t = 0; t < n * n * n; ++t) { double* Q = &o.Q[5 * (ix.node(e, 0, 0, 0) + t)]; for (int q = 0; q < 5; ++q) Q[q] = theta * (Q[q] - Qavg[q]) + Qavg[q]; }
+                for (int t = 0; t < n3; ++t) { double* Q = &o.Q[5 * (g0 + t)]; for (int q = 0; q < 5; ++q) Q[q] = theta * (Q[q] - Qavg[q]) + Qavg[q]; }
         }
     }
 }
@@ -1721,7 +1727,6 @@ double rkStage(Oracle& o, int scheme, int k, double t, double dt) {   // loop bo
 }  // namespace
 
 int orc_enable_limiter(void* p, int enabled, double minimum) {
-    if (((Oracle*)p)->mixed) { ((Oracle*)p)->err = "the stage limiter is not available on p-nonconforming meshes"; return 1; }
     Oracle& o = *(Oracle*)p;
     if (enabled && o.volume.empty()) { o.err = "the limiter needs the element volumes"; return 1; }
     o.limited = enabled != 0; if (minimum > 0.0) o.limiterMin = minimum;
@@ -1915,10 +1920,9 @@ int orc_snapshot_end(void* p, double* Q) {
     return 0;
 }
 int orc_statistics_update(void* p, int reset) {
-    if (((Oracle*)p)->mixed) { ((Oracle*)p)->err = "the statistics monitor is not available on p-nonconforming meshes"; return 1; }
     Oracle& o = *(Oracle*)p;
     const int nv = o.ph.computeGradients ? 29 : 14;
-    const size_t nn = (size_t)o.nElem * o.n3();
+    const size_t nn = o.mixed ? PD(o).eOff[o.nElem] : (size_t)o.nElem * o.n3();
     if (reset || o.stats.size() != nn * nv) { o.stats.assign(nn * nv, 0.0); o.statSamples = 0; }
     const double inv_nsamples_plus_1 = 1.0 / (o.statSamples + 1);
     const double ratio = o.statSamples * inv_nsamples_plus_1;
@@ -1947,7 +1951,7 @@ int orc_statistics_update(void* p, int reset) {
 int orc_statistics_download(void* p, double* data, int* nVars, int* nSamples) {
     Oracle& o = *(Oracle*)p;
     if (o.stats.empty()) { o.err = "no statistics have been accumulated"; return 1; }
-    *nVars = (int)(o.stats.size() / ((size_t)o.nElem * o.n3())); *nSamples = o.statSamples;
+    *nVars = (int)(o.stats.size() / (o.mixed ? PD(o).eOff[o.nElem] : (size_t)o.nElem * o.n3())); *nSamples = o.statSamples;
     if (data) std::memcpy(data, o.stats.data(), o.stats.size() * sizeof(double));
     return 0;
 }

@@ -144,5 +144,8 @@ int emu_surface_integral(void* p, int zone, int kind, double* out) { Emu* h = (E
 int emu_probe(void* p, int n, const int* elem, const int* var, const double* lx, const double* ly, const double* lz, double* values) {
     Emu* h = (Emu*)p; return done(h, h->mx->probe(n, elem, var, lx, ly, lz, values));
 }
+int emu_enable_limiter(void* p, int enabled, double minimum) { Emu* h = (Emu*)p; return done(h, h->mx->enableLimiter(enabled, minimum)); }
+int emu_statistics_update(void* p, int reset) { Emu* h = (Emu*)p; return done(h, h->mx->statisticsUpdate(h->physics, reset)); }
+int emu_statistics_download(void* p, double* data, int* nVars, int* nSamples) { Emu* h = (Emu*)p; return done(h, h->mx->statisticsDownload(data, nVars, nSamples)); }
 long long emu_kernel_launches(void* p) { return ((Emu*)p)->mx->launches; }
 }

@@ -78,7 +78,8 @@ def run_case(api, mesh, phys, scheme="rk3", dt=2.0e-3, source=False, zone=None, 
     out["Q1"], out["QDot1"] = d["Q"], d["QDot"]
     out["residuals"] = sem.ComputeMaxResiduals()
     out["dt"] = np.array(sem.MaxTimeStep(0.3, 0.2))
-    kinds = [P.INT_VOLUME, P.INT_KINETIC_ENERGY, P.INT_KINETIC_ENERGY_RATE, P.INT_VELOCITY, P.INT_INTERNAL_ENERGY]
+    kinds = [P.INT_VOLUME, P.INT_KINETIC_ENERGY, P.INT_KINETIC_ENERGY_RATE, P.INT_VELOCITY, P.INT_INTERNAL_ENERGY, P.INT_ENTROPY, P.INT_MATH_ENTROPY,
+             P.INT_ENTROPY_RATE]
     if phys.computeGradients:
         kinds.append(P.INT_ENSTROPHY)
     out["integrals"] = np.array([sem.ScalarVolumeIntegral(k) for k in kinds])
@@ -99,3 +100,34 @@ def compare(a, b, tol=0.0):
         worst[k] = float(np.abs(np.asarray(a[k], dtype=float) - np.asarray(b[k], dtype=float)).max() / scale)
     bad = {k: v for k, v in worst.items() if v > tol}
     return worst, bad
+
+
+def limiter_and_statistics_case(api, limited=True, minimum=0.05, scheme="ssprk33"):
+    """Gauss-Lobatto mesh with random orders; a deep density pit and a pressure pit at corner nodes of a few elements (face nodes: the
+    traces stay positive).  One SSPRK stage and two steps with the stage limiter, then three samples of the statistics monitor."""
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")
+    sem = DGSem(api, periodic_box(3, 2, 4, seed=5, nodes=GAUSSLOBATTO, amp=0.1), phys)
+    Q = smooth_state(sem, phys.Mach)
+    for e in (0, 5, 13):
+        a, b = sem.elem_offset[e], sem.elem_offset[e + 1] - 1          # first and last node of the element: corners
+        vel, pr = Q[a, 1:4] / Q[a, 0], 0.4 * (Q[a, 4] - 0.5 * (Q[a, 1:4] ** 2).sum() / Q[a, 0])
+        Q[a, :] = [1.0e-3, *(1.0e-3 * vel), pr / 0.4 + 0.5 * 1.0e-3 * (vel ** 2).sum()]
+        Q[b, 4] = 0.5 * (Q[b, 1:4] ** 2).sum() / Q[b, 0] + 1.0e-4 / 0.4
+    sem.set_Q(Q)
+    if limited:
+        sem.enable_limiter(True, minimum)
+    code = sem.SCHEMES[scheme]
+    sem.api.call("rk_stage", code, 0, 0.0, 1.0e-5)
+    out = {"Q_one_stage": sem.Q()}
+    if not limited:
+        return sem, out          # the pits are not survivable without the limiter
+    sem.set_Q(Q)
+    sem.integrate(2, dt=1.0e-5, scheme=scheme, monitors=False)
+    out["Q_two_steps"] = sem.Q()
+    for k in range(3):
+        sem.UpdateStatistics(reset=(k == 0))
+        sem.TakeRK3Step(0.0, 1.0e-5)
+    data, ns = sem.Statistics()
+    out["statistics"] = data
+    out["samples"] = np.array([ns])
+    return sem, out

@@ -115,6 +115,19 @@ def test_mixed_oracle_les_with_uniform_orders_equals_the_uniform_oracle():
         assert all(np.array_equal(out[0][k], out[1][k]) for k in out[0]), kw
 
 
+@pytest.mark.parametrize("scheme", ["ssprk33", "ssprk43"])
+def test_stage_limiter_and_statistics(scheme):
+    _, a = MC.limiter_and_statistics_case(oracle_api.OracleApi(), scheme=scheme)
+    _, b = MC.limiter_and_statistics_case(EmuApi(), scheme=scheme)
+    _, c = MC.limiter_and_statistics_case(oracle_api.OracleApi(), limited=False, scheme=scheme)
+    p = lambda A: 0.4 * (A[:, 4] - 0.5 * (A[:, 1:4] ** 2).sum(-1) / A[:, 0])
+    assert c["Q_one_stage"][:, 0].min() < 0.01 and p(c["Q_one_stage"]).min() < 0.01            # without the limiter the pits survive the stage
+    assert a["Q_one_stage"][:, 0].min() >= 0.05 * (1 - 1e-12) and p(a["Q_one_stage"]).min() >= 0.05 * (1 - 1e-9)
+    assert a["samples"][0] == 3 and a["statistics"].shape[1] == 29
+    worst, bad = MC.compare(a, b)
+    assert not bad, bad
+
+
 def test_unsupported_configurations_are_refused():
     from horses3d_b200.capi import H3dError
     from horses3d_b200.dgsem import DGSem
