@@ -1321,7 +1321,7 @@ int h3d_set_wall_distance(h3d_handle h, const double* dWallElem, const double* d
 }
 
 int h3d_set_face_h(h3d_handle h, const double* faceH) {
-    MX_UNSUPPORTED("the interior-penalty face distance");
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); return mxDone(h, h->mx->setFaceH(h->physics, faceH)); }
     CTX_CHECK(cudaSetDevice(h->device));
     if (!h->haveMesh) { h->err = "h3d_set_face_h: set the mesh first"; return 1; }
     if (!faceH) { h->err = "h3d_set_face_h: null array"; return 1; }

@@ -20,7 +20,7 @@
 // and the orchestration is a template over a backend (allocate / copy / launch): libh3dgpu.so instantiates it with the CUDA
 // backend; tests/emu instantiates the SAME functors and orchestration with a host loop as the launcher, which is how this path
 // is checked against the oracle where no GPU is present (test infrastructure, never shipped).
-// Scope: StandardDG and SplitDG (any two-point flux), BR1 (or Euler), any Riemann solver / boundary condition / gradient variables / LES
+// Scope: StandardDG and SplitDG (any two-point flux), BR1 or interior penalty (or Euler), any Riemann solver / boundary condition / gradient variables / LES
 // model of h3d_physics.cuh.
 // Partitioned meshes: the traces of the MPI faces are exchanged at the face order (h3d_set_halo), scalars are all-reduced.  Reductions are computed per element (face) in the reference's node order and finished on the host in element
 // order, so that they reproduce the oracle's sums bit for bit.
@@ -68,6 +68,7 @@ struct MixedDev {
     const double *lesDelta, *fDelta;        // [nElem] (V / product(Nxyz+1))^(1/3), [nFace] sqrt(surface / product(Nf+1)) (SpatialDiscretization.f90:420, 1378)
     const double *dWall, *fDWall;           // [nNodes], [nFaceNodes] wall distances (LES wall model) or nullptr
     const double *volume;                   // [nElem] e % geom % volume (stage limiter) or nullptr
+    const double *fPenalty;                 // [nFace] interior penalty: 1/2 sigma (max Nf + 1)(max Nf + 2) / h (EllipticIP.f90:678-687) or nullptr
     // ---- element-side fields at the element's face order [c][nTrace]
     double *tr;                             // 15: traces before the adaption to the face order
     double *fStarE, *unStarE;               // 5 / 15 (d*5 + q)
@@ -232,13 +233,24 @@ struct MxGradFace {
         for (int d = 0; d < 3; ++d) nh[d] = m.fN[(long long)d * m.nFaceNodes + g];
         const double Jf = m.fJ[g];
         get_gradients(ph, QL, UL);
+        const bool ip = ph.viscous == H3D_VISCOUS_IP;  // IP_GradientInterfaceSolution[Boundary] (EllipticIP.f90:410-585): Uhat = 1/2 (UL - UR) J_f
         if (m.faceType[f] != H3D_FACE_BOUNDARY) {      // interior and MPI faces (BR1_ComputeMPIFaceAverage, EllipticBR1.f90:629-684)
             double QR[5];
             for (int q = 0; q < 5; ++q) QR[q] = m.fQ[(long long)(5 + q) * m.nFaceNodes + g];
             get_gradients(ph, QR, UR);
             for (int q = 0; q < 5; ++q) {
-                const double uStar = 0.5 * (UR[q] - UL[q]) * Jf;
+                const double uStar = ip ? 0.5 * (UL[q] - UR[q]) * Jf : 0.5 * (UR[q] - UL[q]) * Jf;
                 for (int d = 0; d < 3; ++d) m.fFlux[(long long)(d * 5 + q) * m.nFaceNodes + g] = uStar * nh[d];
+            }
+        } else if (ip) {                                // the boundary state comes from StateForEqn (FlowState)
+            const int zone = m.faceZone[f];
+            double Qe[5];
+            for (int q = 0; q < 5; ++q) Qe[q] = QL[q];
+            bc_flow_state(ph, m.bcType[zone], m.bcParams + 16 * zone, nh, Qe);
+            get_gradients(ph, Qe, UR);
+            for (int q = 0; q < 5; ++q) {
+                const double Uhat = 0.5 * (UL[q] - UR[q]) * Jf;
+                for (int d = 0; d < 3; ++d) m.fFlux[(long long)(d * 5 + q) * m.nFaceNodes + g] = Uhat * nh[d];
             }
         } else {
             const int zone = m.faceZone[f];
@@ -299,11 +311,12 @@ __device__ __forceinline__ MxSides mxSides(const MixedDev& m, const MxNode& t) {
 
 // ---- BR1_GradientFaceLoop: U_d += (sum over the six sides of unStar_d b) / J ----------------------------------------------
 struct MxLift {
-    MixedDev m;
+    MixedDev m; int ipVariant;   // 0: BR1 (U += faceInt / J); otherwise the interior-penalty variant: U += faceInt * (IPmethod / J) (EllipticIP.f90:366-406)
+    int ip;
     __device__ void operator()(long long g) const {
         const MxNode t = mxNode(m, g);
         const MxSides sd = mxSides(m, t);
-        const double iJ = m.invJ[g];
+        const double iJ = ip ? ipVariant * m.invJ[g] : m.invJ[g];
         for (int d = 0; d < 3; ++d) {
             double* Ud = d == 0 ? m.Ux : (d == 1 ? m.Uy : m.Uz);
             for (int q = 0; q < 5; ++q) {
@@ -369,6 +382,10 @@ struct MxRiemann {
                 for (int q = 0; q < 5; ++q) {
                     const double fx = 0.5 * (FL[q][0] + FR[q][0]), fy = 0.5 * (FL[q][1] + FR[q][1]), fz = 0.5 * (FL[q][2] + FR[q][2]);
                     visc[q] = fx * nh[0] + fy * nh[1] + fz * nh[2];
+                }
+                if (ph.viscous == H3D_VISCOUS_IP) {   // IP_RiemannSolver (EllipticIP.f90:704-761)
+                    const double penalty = m.fPenalty[f];
+                    for (int q = 0; q < 5; ++q) visc[q] = visc[q] - penalty * ph.mu * (QL[q] - QR[q]);
                 }
             }
         } else {
@@ -790,7 +807,7 @@ struct MixedSolver {
     std::string err;
     std::map<int, MxBasis> sp;                                   // NodalStorage(N)
     std::map<std::pair<int, int>, std::vector<double>> T;        // Tset(Norigin, Ndest)
-    bool haveMesh = false, haveBC = false, haveHalo = false, splitForm = false, lesWallModel = false, limited = false;
+    bool haveMesh = false, haveBC = false, haveHalo = false, splitForm = false, lesWallModel = false, limited = false, interiorPenalty = false;
     double limiterMin = 1e-13;                 // LIMITED, LIMITER_MIN (ExplicitMethods.f90:28-29)
     double* dStats = nullptr; int statVars = 0, statSamples = 0;
     int nBoundaryFaces = 0, maxZone = -1, nZones = 0, maxNodes1D = 0, nMpiFaces = 0, nranks = 1;
@@ -848,7 +865,8 @@ struct MixedSolver {
                 const double* faceJacobian, const double* faceSurface) {
         splitForm = physics.inviscid == H3D_SPLIT_DG;
         if (physics.les != H3D_LES_NONE && (!volume || !faceSurface)) return fail("LES needs the element volumes and face surfaces (h3d_set_mesh_p volume / faceSurface): the filter width would be zero");
-        if (physics.flowIsNavierStokes && physics.viscous != H3D_VISCOUS_BR1) return fail("p-nonconforming meshes: BR1 is the only viscous discretization available");
+        if (physics.flowIsNavierStokes && physics.viscous == H3D_VISCOUS_BR2) return fail("p-nonconforming meshes: BR1 and the interior penalty are the viscous discretizations available (not BR2)");
+        interiorPenalty = physics.flowIsNavierStokes && physics.viscous == H3D_VISCOUS_IP;
         if (nElem < 1 || nFace < 1) return fail("h3d_set_mesh_p: empty mesh");
         m.nElem = nElem; m.nFace = nFace;
         std::vector<int> eN(3 * (size_t)nElem), nodeElem, traceOwner, faceNodeFace, fo(6 * (size_t)nFace), proj(2 * (size_t)nFace);
@@ -965,11 +983,22 @@ struct MixedSolver {
             for (int f = 0; f < nFace; ++f) fd[f] = std::sqrt(faceSurface[f] / (double)((fo[6 * f] + 1) * (fo[6 * f + 1] + 1)));
             if (up(dl, &m.lesDelta) || up(fd, &m.fDelta)) return 2;
         }
-        m.volume = nullptr;
+        m.volume = nullptr; m.fPenalty = nullptr;
         if (volume) { std::vector<double> v(volume, volume + nElem); if (up(v, &m.volume)) return 2; }
         lesWallModel = physics.les != H3D_LES_NONE && physics.les_wall_model == 1;
         haveMesh = true;
         return 0;
+    }
+    // f % geom % h (HexMesh.f90:3016-3041) -> the penalty of every face, PenaltyParameterNS with maxval(f % Nf) (EllipticIP.f90:678-687)
+    int setFaceH(const H3dPhysics& physics, const double* faceH) {
+        if (!haveMesh) return fail("h3d_set_face_h: set the mesh first");
+        if (!faceH) return fail("h3d_set_face_h: null array");
+        std::vector<double> pen(m.nFace);
+        for (int f = 0; f < m.nFace; ++f) {
+            const int Nmax = std::max(hFo[6 * (size_t)f], hFo[6 * (size_t)f + 1]);
+            pen[f] = 0.5 * physics.penaltyParameter * (Nmax + 1) * (Nmax + 2) / faceH[f];
+        }
+        return up(pen, &m.fPenalty);
     }
     // e % geom % dWall, f % geom % dWall (HexMesh.f90:5594-5692) in the packed sizes of this mesh
     int setWallDistance(const double* dWallElem, const double* dWallFace) {
@@ -1030,6 +1059,7 @@ struct MixedSolver {
         if (!haveMesh) return fail("no mesh");
         if (nMpiFaces > 0 && !haveHalo) return fail("mesh has MPI faces but h3d_set_halo was not called");
         if (lesWallModel && !m.dWall) return fail("the LES wall model needs the wall distances (h3d_set_wall_distance)");
+        if (interiorPenalty && !m.fPenalty) return fail("the interior penalty needs the faces' h (h3d_set_face_h)");
         if (nBoundaryFaces > 0 && !haveBC) return fail("mesh has boundary faces but h3d_set_boundary_conditions was not called");
         if (nBoundaryFaces > 0 && maxZone >= nZones) return fail("a boundary face refers to a zone beyond the table of h3d_set_boundary_conditions");
         return 0;
@@ -1077,13 +1107,14 @@ struct MixedSolver {
         if (exchange(1, m.fQ)) return 2;
         if (physics.computeGradients) {
             launch(MxLocalGrad{m, ph}, m.nNodes);
+            // IP_ComputeGradient (EllipticIP.f90:189-362) prolongs the LOCAL gradients, then lifts the interface jumps; BR1 lifts first
+            if (interiorPenalty) { prolongGradients(); if (exchange(3, m.fU)) return 2; }
             if (physics.flowIsNavierStokes) {
                 launch(MxGradFace{m, ph}, m.nFaceNodes);
                 launch(MxProject{m, 15, m.fFlux, m.unStarE, 1.0}, m.nTrace);
-                launch(MxLift{m}, m.nNodes);
+                launch(MxLift{m, physics.ipVariant, interiorPenalty ? 1 : 0}, m.nNodes);
             }
-            prolongGradients();
-            if (exchange(3, m.fU)) return 2;
+            if (!interiorPenalty) { prolongGradients(); if (exchange(3, m.fU)) return 2; }
         }
         launch(MxFlux{m, ph, splitForm ? 1 : 0}, m.nNodes);
         launch(MxRiemann{m, ph}, m.nFaceNodes);

@@ -169,7 +169,7 @@ int h3dhost_get_array(void* hp, const char* name, void** ptr, long long* count, 
         DARR("x", G.x) DARR("jGradXi", G.jGradXi) DARR("jGradEta", G.jGradEta) DARR("jGradZeta", G.jGradZeta)
         DARR("jacobian", G.jac) DARR("invJacobian", G.invJac) DARR("volume", G.volume)
         DARR("faceX", G.fx) DARR("faceNormal", G.fnormal) DARR("faceT1", G.ft1) DARR("faceT2", G.ft2)
-        DARR("faceJacobian", G.fjac) DARR("faceSurface", G.fsurface) DARR("dWall", G.dWall) DARR("faceDWall", G.fdWall)
+        DARR("faceJacobian", G.fjac) DARR("faceSurface", G.fsurface) DARR("faceH", G.fh) DARR("dWall", G.dWall) DARR("faceDWall", G.fdWall)
     }
     DARR("x", h->geom.x) DARR("jGradXi", h->geom.jGradXi) DARR("jGradEta", h->geom.jGradEta) DARR("jGradZeta", h->geom.jGradZeta)
     DARR("jacobian", h->geom.jac) DARR("invJacobian", h->geom.invJac) DARR("volume", h->geom.volume)
@@ -241,7 +241,7 @@ int h3dhost_inherit_geometry(void* childp, void* parentp) {
             const int f = c->halo.globalFace[l];
             g.faceOrder.insert(g.faceOrder.end(), &G.faceOrder[6 * (size_t)f], &G.faceOrder[6 * (size_t)f] + 6);
             g.fOff[l + 1] = g.fOff[l] + (G.fOff[f + 1] - G.fOff[f]);
-            g.fsurface.push_back(G.fsurface[f]);
+            g.fsurface.push_back(G.fsurface[f]); g.fh.push_back(G.fh[f]);
         }
         auto gather = [&](const std::vector<double>& src, std::vector<double>& dst, const std::vector<long long>& offG, const std::vector<long long>& offL,
                           const std::vector<int>& ids, size_t w) {

@@ -189,6 +189,7 @@ public:
                              geomP.jGradZeta.data(), geomP.jac.data(), geomP.x.data(), geomP.volume.data(), geomP.fnormal.data(), geomP.ft1.data(), geomP.ft2.data(),
                              geomP.fjac.data(), geomP.fx.data(), geomP.fsurface.data()));
         setBoundaryTable();
+        if (phys.viscous == H3D_VISCOUS_IP) check(api.set_face_h(h, geomP.fh.data()));
         if (phys.les_wall_model) {
             computeWallDistancesP(geomP, wallCoordinatesP(mesh, geomP));
             check(api.set_wall_distance(h, geomP.dWall.data(), geomP.fdWall.data()));

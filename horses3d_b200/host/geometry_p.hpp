@@ -46,6 +46,7 @@ struct HostGeometryP {
     std::vector<double> x, jGradXi, jGradEta, jGradZeta, jac, invJac, volume;
     // face arrays at the face order: [j][i][c]
     std::vector<double> fx, fnormal, ft1, ft2, fjac, fsurface;
+    std::vector<double> fh;                     // f % geom % h (HexMesh.f90:3016-3041): min(J) of the adjacent elements / max(J_f)
     std::vector<double> dWall, fdWall;          // distance of every element / face node to the nearest no-slip wall node (optional)
     const NodalStorage& S(int N) { auto it = sp.find(N); if (it == sp.end()) { sp[N].construct(nodeType, N); return sp[N]; } return it->second; }
 };
@@ -299,6 +300,15 @@ inline bool buildGeometryP(const HostMesh& m0, const int* Nxyz, int nodeType, Ho
             }
             g.fsurface[f] = surf;
         }
+    }
+    // faces' minimum orthogonal distance estimate (HexMesh.f90:3016-3041)
+    std::vector<double> minJ(nE);
+    for (int e = 0; e < nE; ++e) minJ[e] = *std::min_element(g.jac.begin() + g.eOff[e], g.jac.begin() + g.eOff[e + 1]);
+    g.fh.assign(nF, 0.0);
+    for (int f = 0; f < nF; ++f) {
+        const int e1 = m.faceElem[2 * f], e2 = m.faceElem[2 * f + 1];
+        const double num = (e1 >= 0 && e2 >= 0) ? std::min(minJ[e1], minJ[e2]) : minJ[std::max(e1, e2)];
+        g.fh[f] = num / *std::max_element(g.fjac.begin() + g.fOff[f], g.fjac.begin() + g.fOff[f + 1]);
     }
     return true;
 }

@@ -180,14 +180,15 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace,
  * h3d_set_interpolation for every pair of different orders (N, M) and (M, N) that meet at a face, then h3d_set_mesh_p instead of
  * h3d_set_mesh.  All element arrays of the ABI are then packed element after element at the elements' own sizes, A[e][k][j][i][c]
  * with (Nx+1)(Ny+1)(Nz+1) nodes in element e (StorageClass.f90:423-429), and face arrays face after face at the face orders.
- * Available on such a mesh: StandardDG and SplitDG (every two-point flux; Gauss-Lobatto nodes) with BR1 (or Euler), every Riemann
+ * Available on such a mesh: StandardDG and SplitDG (every two-point flux; Gauss-Lobatto nodes) with BR1 or the interior penalty
+ * (h3d_set_face_h; penalty with maxval(f % Nf), EllipticIP.f90:678-687) (or Euler), every Riemann
  * solver, boundary condition and gradient-variable set, the LES models (filter widths from the element's / face's own orders,
  * SpatialDiscretization.f90:420,1378; h3d_set_wall_distance in the packed sizes),
  * all Runge-Kutta schemes with the stage limiter, h3d_max_residuals / _max_timestep / _has_nan, h3d_volume_integral (volume,
  * kinetic energy and its rate, enstrophy, mean velocity, internal energy, entropy, math entropy, entropy rate),
  * h3d_surface_integral, h3d_probe (Lagrange vectors padded to rows of max(N)+1 values), h3d_statistics_*, and h3d_set_halo on
- * partitioned meshes: the traces of the MPI faces are exchanged at the face order.  Refused with a message: BR2 / IP,
- * h3d_set_face_h, the entropy / kinetic-energy balance integrals, h3d_snapshot_*. */
+ * partitioned meshes: the traces of the MPI faces are exchanged at the face order.  Refused with a message: BR2, the entropy /
+ * kinetic-energy balance integrals, h3d_snapshot_*. */
 
 /* Tset(Norigin, Ndest) % T (libs/spectral/InterpolationMatrices.f90:42-107): row-major T[i*(Norigin+1) + l] = T(i,l),
  * (Ndest+1) x (Norigin+1); Lagrange interpolation for Norigin < Ndest, the L2 projection (weighted transpose) otherwise. */

@@ -230,11 +230,15 @@ contains
       end do
       call check(h3d_set_mesh(h3d, int(nE, c_int), int(nF, c_int), elemFace, elemFaceSide, faceElem, faceElemSide, faceRot, faceType, faceZone, &
                               jGradXi, jGradEta, jGradZeta, jac, x, vol, fN, fT1, fT2, fJ, fX, fS), "h3d_set_mesh")
-      if ( viscousDiscretization == H3D_VISCOUS_IP ) call check(h3d_set_face_h(h3d, fH), "h3d_set_face_h")      ! HexMesh.f90:3016-3041
 !
 !     4. Boundary table: one type and 16 parameters per zone (include/h3d_gpu.h, H3D_BC_*)
 !     --------------------------------------------------------------------------------------
 400   continue
+      if ( viscousDiscretization == H3D_VISCOUS_IP ) then                ! f % geom % h (HexMesh.f90:3016-3041), uniform or not
+         if ( .not. allocated(fH) ) allocate(fH(size(mesh % faces)))
+         do fID = 1, size(mesh % faces) ; fH(fID) = mesh % faces(fID) % geom % h ; end do
+         call check(h3d_set_face_h(h3d, fH), "h3d_set_face_h")
+      end if
       nZones = size(mesh % zones)
       if ( nZones > 0 ) then
          allocate(bcType(nZones), bcPar(16*nZones));  bcPar = 0.0_RP

@@ -1492,7 +1492,7 @@ int orc_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const in
                    const double* faceJacobian, const double* faceX, const double* faceSurface) {
     Oracle& o = *(Oracle*)p;
     if (!o.pdata) { o.err = "set_basis must precede set_mesh_p"; return 1; }
-    if (o.ph.flowIsNavierStokes && o.ph.viscous != H3D_VISCOUS_BR1) { o.err = "p-nonconforming meshes: BR1 (or Euler)"; return 1; }
+    if (o.ph.flowIsNavierStokes && o.ph.viscous == H3D_VISCOUS_BR2) { o.err = "p-nonconforming meshes: BR1 or interior penalty (or Euler)"; return 1; }
     if (o.ph.les != H3D_LES_NONE && (!volume || !faceSurface)) { o.err = "LES needs the element volumes and face surfaces"; return 1; }
     PData& P = PD(o);
     if (o.ph.inviscid == H3D_SPLIT_DG) for (int q = 0; q < 3 * nElem; ++q) {

@@ -129,6 +129,7 @@ int emu_set_mesh_p(void* p, int nElem, int nFace, const int* elemOrder, const in
                                    jGradEta, jGradZeta, jacobian, volume, faceNormal, faceT1, faceT2, faceJacobian, faceSurface));
 }
 int emu_set_wall_distance(void* p, const double* a, const double* b) { Emu* h = (Emu*)p; return done(h, h->mx->setWallDistance(a, b)); }
+int emu_set_face_h(void* p, const double* fH) { Emu* h = (Emu*)p; return done(h, h->mx->setFaceH(h->physics, fH)); }
 int emu_set_boundary_conditions(void* p, int nZones, const int* bcType, const double* bcParams) { Emu* h = (Emu*)p; return done(h, h->mx->setBoundaryConditions(nZones, bcType, bcParams)); }
 int emu_upload_Q(void* p, const double* Q) { Emu* h = (Emu*)p; return done(h, h->mx->uploadQ(Q)); }
 int emu_download(void* p, double* Q, double* QDot, double* Ux, double* Uy, double* Uz) { Emu* h = (Emu*)p; return done(h, h->mx->download(Q, QDot, Ux, Uy, Uz)); }

@@ -128,10 +128,38 @@ def test_stage_limiter_and_statistics(scheme):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("kw", [dict(viscous="ip"), dict(viscous="ip", ip_variant="NIPG", penalty_parameter=3.0, gradient_variables="energy")],
+                         ids=["sipg", "nipg-energy"])
+def test_interior_penalty_on_random_orders(kw):
+    """IP on a p-nonconforming mesh: local gradients prolonged before the lift, jumps 1/2 (UL - UR), penalty with max(Nf) and the faces' h
+    (EllipticIP.f90:189-406, 678-761); anchored on the uniform oracle (CylinderIP, TaylorGreenKEPEC_IP) for uniform orders."""
+    from horses3d_b200.dgsem import DGSem
+    phys = make_physics(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", **kw)
+    both(lambda: MC.channel(phys), phys, zone=2)
+    out = []
+    for uniform in (3, None):
+        sem = DGSem(oracle_api.OracleApi(), MC.channel(phys, lo=3, hi=3, uniform=uniform), phys)
+        sem.set_Q(MC.smooth_state(sem, 0.3).reshape(sem._shape))
+        sem.TakeRK3Step(0.0, 1.0e-3, ctd_after_step=True)
+        out.append({k: v.reshape(-1, 5) for k, v in sem.download(Q=True, QDot=True, gradients=True).items()})
+    assert all(np.array_equal(out[0][k], out[1][k]) for k in out[0])
+
+
+def test_partitioned_interior_penalty_and_les():
+    """Two more partitioned cases: the interior penalty (the MPI faces' h is the global face's) and Smagorinsky with the wall model (wall
+    distances inherited from the global mesh)."""
+    for kw in (dict(viscous="ip"), dict(les="smagorinsky", les_wall_model="linear")):
+        phys = make_physics(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", **kw)
+        ref, got = _partitioned(2, lambda: MC.channel(phys, ne=4), phys, "metis", zone=2)
+        worst, _ = MC.compare(ref, got)
+        for k, v in worst.items():
+            assert v <= (1e-13 if k in ("integrals", "surface") else 0.0), (kw, k, v)
+
+
 def test_unsupported_configurations_are_refused():
     from horses3d_b200.capi import H3dError
     from horses3d_b200.dgsem import DGSem
-    for kw in (dict(viscous="br2"), dict(viscous="ip")):
+    for kw in (dict(viscous="br2"),):
         with pytest.raises(H3dError):
             DGSem(EmuApi(), MC.periodic_box(2, 2, 3, seed=1, nodes=GAUSSLOBATTO), make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe", **kw))
     with pytest.raises(H3dError):      # the split form needs Gauss-Lobatto nodes

@@ -148,3 +148,9 @@ def test_stage_limiter_and_statistics(gpu_api_cls, scheme):
     worst, bad = MC.compare(a, b, TOL)
     print(worst)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("kw", [dict(viscous="ip"), dict(viscous="ip", ip_variant="NIPG", penalty_parameter=3.0, gradient_variables="energy")], ids=["sipg", "nipg-energy"])
+def test_interior_penalty_on_random_orders(gpu_api_cls, kw):
+    phys = make_physics(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", **kw)
+    both(gpu_api_cls, lambda: MC.channel(phys), phys, zone=2)
