@@ -229,3 +229,51 @@ def test_partitioned_channel_with_boundaries_and_surface_integrals():
     print(worst)
     for k, v in worst.items():
         assert v <= (1e-13 if k in ("integrals", "surface") else 0.0), (k, v)
+
+
+def test_set_up_errors_are_reported():
+    """The set-up checks of h3d_set_mesh_p / h3d_set_halo (shared by the device library and the host-loop backend)."""
+    import ctypes as C
+    from horses3d_b200.capi import H3dError, _ptr
+    from horses3d_b200.dgsem import DGSem
+    from horses3d_b200.hostmesh import NodalStorage
+    phys = make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe")
+    mesh = MC.periodic_box(2, 2, 4, seed=1)
+
+    def attempt(skip_basis=None, skip_interp=False, face_order=None, msg=""):
+        api = EmuApi()
+        api.set_physics(phys)
+        orders = np.array(mesh.array("elemOrder")).reshape(-1, 3); fo = np.array(mesh.array("faceOrder")).reshape(-1, 6)
+        for N in sorted(set(orders.ravel()) | set(fo.ravel())):
+            if N != skip_basis:
+                api.set_basis(NodalStorage(int(N), mesh.nodes))
+        if not skip_interp:
+            from horses3d_b200.hostmesh import interpolation_matrix
+            for a in range(2, 5):
+                for b in range(2, 5):
+                    if a != b:
+                        api.call("set_interpolation", a, b, _ptr(interpolation_matrix(a, b, mesh.nodes), np.float64))
+        if face_order is not None:
+            saved = mesh.array("faceOrder").copy()
+            mesh.array("faceOrder")[:] = face_order(saved)
+        try:
+            with pytest.raises(H3dError, match=msg):
+                api.set_mesh_p(mesh)
+        finally:
+            if face_order is not None:
+                mesh.array("faceOrder")[:] = saved
+
+    attempt(skip_basis=3, msg="h3d_set_basis has not been called")
+    attempt(skip_interp=True, msg="h3d_set_interpolation has not been called")
+    attempt(face_order=lambda fo: np.where(np.arange(fo.size) == 0, fo + 1, fo), msg="faceOrder contradicts")
+    # a partition on a single-rank context: MPI faces are refused
+    part = mesh.partition(2, "block")
+    with pytest.raises(H3dError, match="MPI faces on a single rank"):
+        DGSem(EmuApi(), mesh.extract(part, 0, inherit_geometry=True), phys)
+    # boundary faces without a boundary table
+    ch = MC.channel(phys)
+    ch.bcs = []
+    sem = DGSem(EmuApi(), ch, phys)
+    sem.set_Q(MC.smooth_state(sem, 0.3))
+    with pytest.raises(H3dError, match="h3d_set_boundary_conditions was not called"):
+        sem.ComputeTimeDerivative(0.0)
