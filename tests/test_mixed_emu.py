@@ -29,6 +29,10 @@ def test_navier_stokes_periodic_box_random_anisotropic_orders(riemann):
     both(lambda: MC.periodic_box(3, 2, 5, seed=7), make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann=riemann), source=True)
 
 
+def test_larger_mesh_with_orders_up_to_nine():
+    both(lambda: MC.periodic_box(6, 1, 9, seed=21), make_physics(flow="NS", mach=0.3, reynolds=400.0, riemann="roe"))
+
+
 def test_euler_with_and_without_gradients():
     both(lambda: MC.periodic_box(3, 1, 4, seed=5), make_physics(flow="Euler", mach=0.3, riemann="roe"))
     both(lambda: MC.periodic_box(3, 1, 4, seed=5), make_physics(flow="Euler", mach=0.3, riemann="rusanov", compute_gradients=True))
@@ -209,7 +213,7 @@ def _partitioned(world_size, mesh_fn, phys, method, zone=None, scheme="rk3"):
     return ref, got
 
 
-@pytest.mark.parametrize("world_size,method", [(2, "metis"), (3, "block"), (4, "metis")])
+@pytest.mark.parametrize("world_size,method", [(2, "metis"), (3, "block"), (4, "metis"), (8, "metis")])
 def test_partitioned_mesh_reproduces_the_single_domain_oracle(world_size, method):
     """MPI faces of a p-nonconforming mesh: traces exchanged at the face order, mortar projection on each side's rank.  Element fields
     are bit-identical to the single-domain oracle (the partitions inherit the global geometry); the all-reduced scalars agree to
