@@ -1436,7 +1436,7 @@ int h3d_download(h3d_handle h, double* Q, double* QDot, double* Ux, double* Uy, 
 }
 
 int h3d_snapshot_begin(h3d_handle h) {
-    MX_UNSUPPORTED("the asynchronous snapshot");
+    if (h->mixedMode) { CTX_CHECK(cudaSetDevice(h->device)); return mxDone(h, h->mx->snapshotBegin()); }
     if (!h->haveMesh) { h->err = "no mesh"; return 1; }
     if (h->snapPending) { h->err = "a snapshot is already in flight: call h3d_snapshot_end first"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
@@ -1466,7 +1466,7 @@ int h3d_snapshot_begin(h3d_handle h) {
 }
 
 int h3d_snapshot_end(h3d_handle h, double* Q) {
-    MX_UNSUPPORTED("the asynchronous snapshot");
+    if (h->mixedMode) return mxDone(h, h->mx->snapshotEnd(Q));
     if (!h->snapPending) { h->err = "no snapshot in flight"; return 1; }
     CTX_CHECK(cudaSetDevice(h->device));
     CTX_CHECK(cudaEventSynchronize(h->evSnapDone));

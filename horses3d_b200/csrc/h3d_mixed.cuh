@@ -1084,6 +1084,22 @@ struct MixedSolver {
         for (int a = 0; a < 5; ++a) if (dst[a] && downloadField(dst[a], src[a])) return 2;
         return 0;
     }
+    // h3d_snapshot_begin / _end on such meshes: the copy is taken (synchronously) at the point of the time loop where _begin is called
+    std::vector<double> snapshot; bool snapPending = false;
+    int snapshotBegin() {
+        if (!haveMesh) return fail("no mesh");
+        if (snapPending) return fail("a snapshot is already in flight: call h3d_snapshot_end first");
+        snapshot.resize(5 * (size_t)m.nNodes);
+        if (downloadField(snapshot.data(), m.Q)) return 2;
+        snapPending = true;
+        return 0;
+    }
+    int snapshotEnd(double* Q) {
+        if (!snapPending) return fail("no snapshot in flight");
+        snapPending = false;
+        if (Q) std::memcpy(Q, snapshot.data(), snapshot.size() * sizeof(double));
+        return 0;
+    }
     int setSource(const double* S) {
         if (!haveMesh) return fail("no mesh");
         if (!S) { m.S = nullptr; return 0; }

@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libh3dmixedemu.so")
 SRC = os.path.join(HERE, "h3d_mixed_emu.cpp")
 NAMES = ["set_physics", "set_wall_distance", "set_face_h", "set_basis", "set_interpolation", "set_mesh_p", "set_boundary_conditions", "upload_Q", "download", "set_source",
          "compute_time_derivative", "rk_step", "rk_stage", "max_residuals", "max_timestep", "volume_integral", "has_nan",
-         "surface_integral", "probe", "enable_limiter", "statistics_update", "statistics_download"]
+         "surface_integral", "probe", "enable_limiter", "statistics_update", "statistics_download", "snapshot_begin", "snapshot_end"]
 
 
 def build(force=False):

@@ -148,5 +148,7 @@ int emu_probe(void* p, int n, const int* elem, const int* var, const double* lx,
 int emu_enable_limiter(void* p, int enabled, double minimum) { Emu* h = (Emu*)p; return done(h, h->mx->enableLimiter(enabled, minimum)); }
 int emu_statistics_update(void* p, int reset) { Emu* h = (Emu*)p; return done(h, h->mx->statisticsUpdate(h->physics, reset)); }
 int emu_statistics_download(void* p, double* data, int* nVars, int* nSamples) { Emu* h = (Emu*)p; return done(h, h->mx->statisticsDownload(data, nVars, nSamples)); }
+int emu_snapshot_begin(void* p) { Emu* h = (Emu*)p; return done(h, h->mx->snapshotBegin()); }
+int emu_snapshot_end(void* p, double* Q) { Emu* h = (Emu*)p; return done(h, h->mx->snapshotEnd(Q)); }
 long long emu_kernel_launches(void* p) { return ((Emu*)p)->mx->launches; }
 }

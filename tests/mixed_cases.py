@@ -126,7 +126,13 @@ def limiter_and_statistics_case(api, limited=True, minimum=0.05, scheme="ssprk33
     out["Q_two_steps"] = sem.Q()
     for k in range(3):
         sem.UpdateStatistics(reset=(k == 0))
+        if k == 1:
+            sem.snapshot_begin()                       # autosave beside the time loop: the state at this point ...
+            before = sem.Q()
         sem.TakeRK3Step(0.0, 1.0e-5)
+        if k == 1:
+            out["snapshot"] = sem.snapshot_end()       # ... delivered after the loop has moved on
+            assert np.array_equal(out["snapshot"], before) and not np.array_equal(out["snapshot"], sem.Q())
     data, ns = sem.Statistics()
     out["statistics"] = data
     out["samples"] = np.array([ns])
