@@ -38,6 +38,7 @@ def _lib():
     lib.emu_world_create.restype = C.c_void_p
     lib.emu_world_create.argtypes = [C.c_int]
     lib.emu_world_destroy.argtypes = [C.c_void_p]
+    lib.emu_world_abort.argtypes = [C.c_void_p]
     lib.emu_destroy.argtypes = [C.c_void_p]
     lib.emu_kernel_launches.argtypes = [C.c_void_p]
     lib.emu_kernel_launches.restype = C.c_longlong
@@ -52,6 +53,10 @@ class EmuWorld:
         self._lib = _lib()
         self.nranks = nranks
         self.handle = C.c_void_p(self._lib.emu_world_create(nranks))
+
+    def abort(self):
+        """A rank failed: open the barriers so that the other ranks finish and the error can be reported."""
+        self._lib.emu_world_abort(self.handle)
 
     def __del__(self):
         try:

@@ -187,9 +187,9 @@ def _partitioned(world_size, mesh_fn, phys, method, zone=None, scheme="rk3"):
             m = g.extract(part, rank, inherit_geometry=True)
             sem, out = MC.run_case(EmuApi(world, rank), m, phys, zone=zone, scheme=scheme, state_from=(sem0, m.array("globalElem").copy()))
             outs[rank] = (sem, out, m.array("globalElem").copy(), int((m.array("faceType") == 3).sum()))
-        except Exception as ex:      # a dead rank would leave the others at the barrier
+        except Exception as ex:      # a dead rank would leave the others at the barrier: open it
             errs.append(ex)
-            os._exit(1)
+            world.abort()
 
     threads = [threading.Thread(target=work, args=(r,)) for r in range(world_size)]
     for t in threads:
