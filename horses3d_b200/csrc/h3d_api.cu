@@ -37,6 +37,7 @@ struct CudaBackend {
         allocs->push_back(q);
         return (T*)q;
     }
+    template <class T> void zero(T* dst, size_t count) { note(cudaMemsetAsync(dst, 0, count * sizeof(T), stream), "cudaMemsetAsync"); }
     template <class T> void upload(T* dst, const T* src, size_t count) {
         note(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync (upload)");
         note(cudaStreamSynchronize(stream), "cudaStreamSynchronize");      // the caller may reuse src

@@ -523,6 +523,16 @@ struct MxVolumeSplit {
     }
 };
 
+// ---- global2LocalQ / local2GlobalQ (StorageClass.f90:390-440, 549-579): the reference's packed [node][C] <-> the device's [c][node]
+struct MxAosToSoa {
+    MixedDev m; int C; const double* src; double* dst;
+    __device__ void operator()(long long t) const { for (int c = 0; c < C; ++c) dst[(long long)c * m.nNodes + t] = src[t * C + c]; }
+};
+struct MxSoaToAos {
+    MixedDev m; int C; const double* src; double* dst;
+    __device__ void operator()(long long t) const { for (int c = 0; c < C; ++c) dst[t * C + c] = src[(long long)c * m.nNodes + t]; }
+};
+
 // ---- stage_limiter (ExplicitMethods.f90:1755-1847): one thread per element; density, then pressure, scaled towards the element
 //      average so that they stay above min(minimum, average)
 struct MxLimiter {
@@ -768,7 +778,7 @@ struct MxProbe {   // Probe_Update (Probe.f90:330-420); Lagrange vectors padded 
 
 // ============================================================================================================================
 //  Orchestration, shared by the CUDA backend (libh3dgpu.so) and the host-loop backend of tests/emu.
-//  Backend B:  template <class T> T* alloc(size_t);  void upload(T* dst, const T* src, size_t);  void download(T* dst, const T* src, size_t)
+//  Backend B:  template <class T> T* alloc(size_t);  void zero(T*, size_t);  void upload(T* dst, const T* src, size_t);  void download(T* dst, const T* src, size_t)
 //              (both synchronous);  template <class F> void launch(const F&, long long count);  const char* error()  (nullptr = ok)
 //              void exchange(const double* send, double* recv, int nNbr, const int* ranks, const long long* offset, const long long* count)
 //              (device buffers, doubles; in order with the launches);  void allreduce(double* hostValues, int n, int op)  (0 max, 1 min, 2 sum)
@@ -816,7 +826,7 @@ struct MixedSolver {
     std::vector<long long> hEOff, hFOff;
     std::vector<int> hFo, hFaceType, hFaceElem;
     std::vector<double> hPartial, hBuf;
-    double* dSource = nullptr;
+    double* dSource = nullptr; double* stage = nullptr;
     int* dProbeI = nullptr; double* dProbeD = nullptr; size_t probeCap = 0;
 
     explicit MixedSolver(const B& b) : be(b) {}
@@ -846,8 +856,7 @@ struct MixedSolver {
     int field(double** dst, size_t count) {
         double* d = be.template alloc<double>(std::max<size_t>(count, 1));
         if (!d) return check() ? 2 : fail("device allocation failed");
-        std::vector<double> z(count, 0.0);
-        if (count) be.upload(d, z.data(), count);
+        if (count) be.zero(d, count);
         *dst = d;
         return check();
     }
@@ -1064,18 +1073,18 @@ struct MixedSolver {
         if (nBoundaryFaces > 0 && maxZone >= nZones) return fail("a boundary face refers to a zone beyond the table of h3d_set_boundary_conditions");
         return 0;
     }
+    // the packed host array crosses PCIe as it is; the transposition runs on the device (staging buffer of one 5-vector field)
     int uploadField(double* dst, const double* src) {
-        toSoA(src, (size_t)m.nNodes, 5, hBuf);
-        be.upload(dst, hBuf.data(), hBuf.size());
+        if (!stage && field(&stage, 5 * (size_t)m.nNodes)) return 2;
+        be.upload(stage, src, 5 * (size_t)m.nNodes);
+        launch(MxAosToSoa{m, 5, stage, dst}, m.nNodes);
         return check();
     }
     int downloadField(double* dst, const double* src) {
-        const size_t nn = (size_t)m.nNodes;
-        hBuf.resize(5 * nn);
-        be.download(hBuf.data(), src, hBuf.size());
-        if (check()) return 2;
-        for (size_t g = 0; g < nn; ++g) for (int c = 0; c < 5; ++c) dst[g * 5 + c] = hBuf[(size_t)c * nn + g];
-        return 0;
+        if (!stage && field(&stage, 5 * (size_t)m.nNodes)) return 2;
+        launch(MxSoaToAos{m, 5, src, stage}, m.nNodes);
+        be.download(dst, stage, 5 * (size_t)m.nNodes);
+        return check();
     }
     int uploadQ(const double* Q) { if (!haveMesh) return fail("no mesh"); return uploadField(m.Q, Q); }
     int download(double* Q, double* QDot, double* Ux, double* Uy, double* Uz) {
@@ -1161,7 +1170,7 @@ struct MixedSolver {
         if (ready()) return 1;
         const int nv = physics.computeGradients ? 29 : 14;
         if (!dStats || statVars != nv) { if (field(&dStats, (size_t)nv * m.nNodes)) return 2; statVars = nv; statSamples = 0; reset = 0; }
-        if (reset) { std::vector<double> z((size_t)nv * m.nNodes, 0.0); be.upload(dStats, z.data(), z.size()); statSamples = 0; }
+        if (reset) { be.zero(dStats, (size_t)nv * m.nNodes); statSamples = 0; }
         const double inv = 1.0 / (statSamples + 1), ratio = statSamples * inv;
         launch(MxStatistics{m, nv, ratio, inv, dStats}, m.nNodes);
         ++statSamples;

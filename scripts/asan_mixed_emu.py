@@ -20,3 +20,17 @@ from horses3d_b200 import probes
 from test_oracle_pins import cylinder_different_orders
 print(cylinder_different_orders(emu_api.EmuApi(), steps=2)[1:])
 print("asan run complete")
+# the later additions: split form, interior penalty, LES with the wall model, limiter / statistics / snapshot, two emulated ranks
+from horses3d_b200.hostmesh import GAUSSLOBATTO
+MC.run_case(emu_api.EmuApi(), MC.periodic_box(3, 2, 5, seed=17, nodes=GAUSSLOBATTO), make_physics(flow="NS", mach=0.3, reynolds=200.0, inviscid="split-form", averaging="chandrasekar", riemann="central"))
+for kw in (dict(viscous="ip"), dict(les="smagorinsky", les_wall_model="linear")):
+    ph2 = make_physics(flow="NS", mach=0.3, reynolds=150.0, riemann="roe", **kw)
+    MC.run_case(emu_api.EmuApi(), MC.channel(ph2), ph2, zone=2)
+MC.limiter_and_statistics_case(emu_api.EmuApi())
+import threading
+g = MC.periodic_box(4, 2, 5, seed=7)
+part = g.partition(2, "metis")
+world = emu_api.EmuWorld(2)
+ts = [threading.Thread(target=lambda r=r: MC.run_case(emu_api.EmuApi(world, r), g.extract(part, r, inherit_geometry=True), phys)) for r in range(2)]
+[t.start() for t in ts]; [t.join() for t in ts]
+print("asan run (second part) complete")

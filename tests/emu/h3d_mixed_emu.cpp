@@ -74,6 +74,7 @@ struct HostBackend {
     }
     std::vector<void*>* allocs = nullptr;
     template <class T> T* alloc(size_t count) { void* q = std::malloc(std::max<size_t>(count, 1) * sizeof(T)); allocs->push_back(q); return (T*)q; }
+    template <class T> void zero(T* dst, size_t count) { std::memset(dst, 0, count * sizeof(T)); }
     template <class T> void upload(T* dst, const T* src, size_t count) { std::memcpy(dst, src, count * sizeof(T)); }
     template <class T> void download(T* dst, const T* src, size_t count) { std::memcpy(dst, src, count * sizeof(T)); }
     template <class F> void launch(const F& f, long long count) {
