@@ -79,7 +79,7 @@ struct MixedDev {
     const double *fN, *fT1, *fT2, *fJ;      // 3, 3, 3, 1
     const int* bcType; const double* bcParams;
     // ---- reductions
-    double* partial;                        // [max(nElem, nFace)][8]
+    double* partial; long long partialStride;   // [8][partialStride], partialStride = max(nElem, nFace): column q of element / face e at q * stride + e
     // ---- MPI faces (h3d_set_halo): halo face k = haloFace[k], local side haloSide[k]; its nodes are the halo nodes
     //      [hOff[k], hOff[k+1]); neighbour b owns the halo nodes [nbrNodeOff[b], nbrNodeOff[b+1]) (faces in exchange order)
     int nHalo, nNbr; long long nHaloNodes;
@@ -602,7 +602,7 @@ struct MxStatistics {
     }
 };
 
-// ---- reductions: one thread per element (face), nodes in the reference's order; partial[e][8] --------------------------------
+// ---- reductions: one thread per element (face), nodes in the reference's order; partial[q][e] ---------------------------------
 struct MxRedResidual {   // ComputeMaxResiduals (DGSEMClass.f90:770-856) + checkForNan on Q
     MixedDev m;
     __device__ void operator()(long long e) const {
@@ -611,7 +611,7 @@ struct MxRedResidual {   // ComputeMaxResiduals (DGSEMClass.f90:770-856) + check
             v[q] = fmax(v[q], fabs(m.QDot[(long long)q * m.nNodes + g]));
             if (isnan(m.Q[(long long)q * m.nNodes + g])) v[5] = 1.0;
         }
-        for (int q = 0; q < 6; ++q) m.partial[8 * e + q] = v[q];
+        for (int q = 0; q < 6; ++q) m.partial[q * m.partialStride + e] = v[q];
     }
 };
 struct MxRedTimestep {   // MaxTimeStep (DGSEMClass.f90:870-1034): the spacings of the element's own nodal storages
@@ -642,7 +642,7 @@ struct MxRedTimestep {   // MaxTimeStep (DGSEMClass.f90:870-1034): the spacings 
                 vv = fmin(vv, dcfl * fabs(jac) / (v1 + v2 + v3));
             }
         }
-        m.partial[8 * e] = vc; m.partial[8 * e + 1] = vv;
+        m.partial[e] = vc; m.partial[m.partialStride + e] = vv;
     }
 };
 struct MxRedIntegral {   // ScalarVolumeIntegral (VolumeIntegrals.f90:76-120, 167-286), the kinds that need Q, QDot and gradients only
@@ -696,7 +696,7 @@ struct MxRedIntegral {   // ScalarVolumeIntegral (VolumeIntegrals.f90:76-120, 16
                 default: break;
             }
         }
-        m.partial[8 * e] = loc;
+        m.partial[e] = loc;
     }
 };
 struct MxRedSurface {   // ScalarSurfaceIntegral / VectorSurfaceIntegral (SurfaceIntegrals.f90:40-445) on the faces of one zone
@@ -745,7 +745,7 @@ struct MxRedSurface {   // ScalarSurfaceIntegral / VectorSurfaceIntegral (Surfac
                 }
             }
         }
-        for (int d = 0; d < 3; ++d) m.partial[8 * f + d] = fv[d];
+        for (int d = 0; d < 3; ++d) m.partial[d * m.partialStride + f] = fv[d];
     }
 };
 struct MxProbe {   // Probe_Update (Probe.f90:330-420); Lagrange vectors padded to ld values per direction
@@ -985,6 +985,7 @@ struct MixedSolver {
         if (field(&m.Q, 5 * nn) || field(&m.G, 5 * nn) || field(&m.QDot, 5 * nn) || field(&m.Ux, 5 * nn) || field(&m.Uy, 5 * nn) || field(&m.Uz, 5 * nn) ||
             field(&m.Fc, 15 * nn) || field(&m.tr, 15 * (size_t)m.nTrace) || field(&m.fStarE, 5 * (size_t)m.nTrace) || field(&m.unStarE, 15 * (size_t)m.nTrace) ||
             field(&m.fQ, 10 * nf) || field(&m.fU, 30 * nf) || field(&m.fFlux, 15 * nf) || field(&m.partial, 8 * (size_t)std::max(nElem, nFace))) return 2;
+        m.partialStride = std::max(nElem, nFace);
         m.S = nullptr; m.dWall = nullptr; m.fDWall = nullptr; m.lesDelta = nullptr; m.fDelta = nullptr;
         if (volume && faceSurface) {
             std::vector<double> dl(nElem), fd(nFace);
@@ -1194,17 +1195,19 @@ struct MixedSolver {
         if (ctdAfterStep) return residual(physics, MxRk{0, 0.0, 0.0, 0.0, 0});
         return 0;
     }
-    int partials(int count) {
-        hPartial.resize(8 * (size_t)count);
+    // the first nCols columns of the per-element (per-face) results: hPartial[q * partialStride + e]
+    int partials(int nCols) {
+        hPartial.resize((size_t)nCols * m.partialStride);
         be.download(hPartial.data(), m.partial, hPartial.size());
         return check();
     }
+    double part(int q, long long e) const { return hPartial[(size_t)q * m.partialStride + e]; }
     int maxResiduals(double out[5], int* nanFlag) {
         if (!haveMesh) return fail("no mesh");
         launch(MxRedResidual{m}, m.nElem);
-        if (partials(m.nElem)) return 2;
+        if (partials(6)) return 2;
         double v[6] = {0, 0, 0, 0, 0, 0};
-        for (int e = 0; e < m.nElem; ++e) for (int q = 0; q < 6; ++q) v[q] = std::fmax(v[q], hPartial[8 * (size_t)e + q]);
+        for (int e = 0; e < m.nElem; ++e) for (int q = 0; q < 6; ++q) v[q] = std::fmax(v[q], part(q, e));
         if (nranks > 1) { be.allreduce(v, 6, 0); if (check()) return 2; }
         for (int q = 0; q < 5; ++q) out[q] = v[q];
         *nanFlag = v[5] > 0.5 ? 1 : 0;
@@ -1213,9 +1216,9 @@ struct MixedSolver {
     int maxTimestep(double cfl, double dcfl, double* dtConv, double* dtVisc) {
         if (ready()) return 1;
         launch(MxRedTimestep{m, ph, cfl, dcfl}, m.nElem);
-        if (partials(m.nElem)) return 2;
+        if (partials(2)) return 2;
         double a = 1.7976931348623157e308, b = 1.7976931348623157e308;
-        for (int e = 0; e < m.nElem; ++e) { a = std::fmin(a, hPartial[8 * (size_t)e]); b = std::fmin(b, hPartial[8 * (size_t)e + 1]); }
+        for (int e = 0; e < m.nElem; ++e) { a = std::fmin(a, part(0, e)); b = std::fmin(b, part(1, e)); }
         if (nranks > 1) { double ab[2] = {a, b}; be.allreduce(ab, 2, 1); if (check()) return 2; a = ab[0]; b = ab[1]; }
         *dtConv = a; *dtVisc = b;
         return 0;
@@ -1229,9 +1232,9 @@ struct MixedSolver {
             default: return fail("this volume integral is not available on p-nonconforming meshes");
         }
         launch(MxRedIntegral{m, ph, kind}, m.nElem);
-        if (partials(m.nElem)) return 2;
+        if (partials(1)) return 2;
         double v = 0.0;
-        for (int e = 0; e < m.nElem; ++e) v = v + hPartial[8 * (size_t)e];
+        for (int e = 0; e < m.nElem; ++e) v = v + part(0, e);
         if (nranks > 1) { be.allreduce(&v, 1, 2); if (check()) return 2; }
         *val = v;
         return 0;
@@ -1245,9 +1248,9 @@ struct MixedSolver {
         prolong(m.Q, m.fQ);   // the state (and gradients) are prolonged anew, as the reference does (SurfaceIntegrals.f90:57-77)
         if (physics.computeGradients) prolongGradients();
         launch(MxRedSurface{m, ph, zone, kind}, m.nFace);
-        if (partials(m.nFace)) return 2;
+        if (partials(3)) return 2;
         double v[3] = {0, 0, 0};
-        for (int f = 0; f < m.nFace; ++f) for (int d = 0; d < 3; ++d) v[d] = v[d] + hPartial[8 * (size_t)f + d];
+        for (int f = 0; f < m.nFace; ++f) for (int d = 0; d < 3; ++d) v[d] = v[d] + part(d, f);
         if (nranks > 1) { be.allreduce(v, 3, 2); if (check()) return 2; }
         for (int d = 0; d < 3; ++d) out[d] = v[d];
         return 0;
