@@ -141,7 +141,7 @@ __device__ __forceinline__ MxNode mxNode(const MixedDev& m, long long g) {
 
 // ---- HexElement_ProlongSolutionToFaces: trace of 5 fields on every element side, at the element's own face order ----------
 struct MxTrace {
-    MixedDev m; const double* src; double* dst;   // src [5][nNodes], dst [5][nTrace]
+    MixedDev m; int nSets; const double* src[3]; double* dst;   // nSets fields of 5 (Q: 1; U_x, U_y, U_z: 3): src[s] [5][nNodes], dst [s*5 + c][nTrace]
     __device__ void operator()(long long t) const {
         const int owner = m.traceOwner[t], e = owner / 6, lf = owner % 6;
         const int nn[3] = {m.eN[3 * e], m.eN[3 * e + 1], m.eN[3 * e + 2]};
@@ -151,18 +151,21 @@ struct MxTrace {
         const double* v = mxV(m, nn[an] - 1) + mxEnd(lf) * nn[an];
         const long long stride = an == 0 ? 1 : (an == 1 ? nn[0] : (long long)nn[0] * nn[1]);
         const long long g0 = m.eOff[e] + ((long long)idx[2] * nn[1] + idx[1]) * nn[0] + idx[0];
-        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int l = 0; l < nn[an]; ++l) {
-            const double vl = v[l];
-            for (int c = 0; c < 5; ++c) acc[c] = acc[c] + src[(long long)c * m.nNodes + g0 + l * stride] * vl;
+        for (int st = 0; st < nSets; ++st) {
+            const double* f = src[st];
+            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int l = 0; l < nn[an]; ++l) {
+                const double vl = v[l];
+                for (int c = 0; c < 5; ++c) acc[c] = acc[c] + f[(long long)c * m.nNodes + g0 + l * stride] * vl;
+            }
+            for (int c = 0; c < 5; ++c) dst[(long long)(st * 5 + c) * m.nTrace + t] = acc[c];
         }
-        for (int c = 0; c < 5; ++c) dst[(long long)c * m.nTrace + t] = acc[c];
     }
 };
 
-// ---- Face_AdaptSolutionToFace: 5 traces -> side `side` of the face storage at the face order -----------------------------
+// ---- Face_AdaptSolutionToFace / ...GradientsToFace: the traces -> side `side` of the face storage at the face order -------------
 struct MxAdapt {
-    MixedDev m; const double* src; double* dst;   // src [5][nTrace]; dst [10][nFaceNodes] (side*5 + c)
+    MixedDev m; int nSets; const double* src; double* dst;   // src [s*5 + c][nTrace]; dst [s*10 + side*5 + c][nFaceNodes]
     __device__ void operator()(long long t) const {
         const int side = (int)(t / m.nFaceNodes); const long long g = t % m.nFaceNodes;
         const int f = m.faceNodeFace[g];
@@ -176,24 +179,26 @@ struct MxAdapt {
         const long long base = m.tOff[6 * m.faceElem[2 * f + side] + m.faceElemSide[2 * f + side]];
         auto at = [&](int a, int b) { int ii, jj; mxLeft2Right(a, b, Ns1, Ns2, rot, ii, jj); return base + (long long)jj * ne1 + ii; };
         const int pt = m.proj[2 * f + side];
-        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        if (pt == 0) {
-            const long long s = at(i, j);
-            for (int c = 0; c < 5; ++c) acc[c] = src[(long long)c * m.nTrace + s];
-        } else if (pt == 1) {
-            const double* T1 = mxT(m, Ns1, Nf1) + i * (Ns1 + 1);
-            for (int l = 0; l <= Ns1; ++l) { const long long s = at(l, j); for (int c = 0; c < 5; ++c) acc[c] = acc[c] + T1[l] * src[(long long)c * m.nTrace + s]; }
-        } else if (pt == 2) {
-            const double* T2 = mxT(m, Ns2, fo[1]) + j * (Ns2 + 1);
-            for (int l = 0; l <= Ns2; ++l) { const long long s = at(i, l); for (int c = 0; c < 5; ++c) acc[c] = acc[c] + T2[l] * src[(long long)c * m.nTrace + s]; }
-        } else {
-            const double* T1 = mxT(m, Ns1, Nf1) + i * (Ns1 + 1); const double* T2 = mxT(m, Ns2, fo[1]) + j * (Ns2 + 1);
-            for (int l = 0; l <= Ns2; ++l) for (int mm = 0; mm <= Ns1; ++mm) {
-                const long long s = at(mm, l); const double tt = T1[mm] * T2[l];
-                for (int c = 0; c < 5; ++c) acc[c] = acc[c] + tt * src[(long long)c * m.nTrace + s];
+        const double* T1 = (pt & 1) ? mxT(m, Ns1, Nf1) + i * (Ns1 + 1) : nullptr;
+        const double* T2 = (pt & 2) ? mxT(m, Ns2, fo[1]) + j * (Ns2 + 1) : nullptr;
+        for (int st = 0; st < nSets; ++st) {
+            const double* sf = src + (long long)(st * 5) * m.nTrace;
+            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            if (pt == 0) {
+                const long long s = at(i, j);
+                for (int c = 0; c < 5; ++c) acc[c] = sf[(long long)c * m.nTrace + s];
+            } else if (pt == 1) {
+                for (int l = 0; l <= Ns1; ++l) { const long long s = at(l, j); for (int c = 0; c < 5; ++c) acc[c] = acc[c] + T1[l] * sf[(long long)c * m.nTrace + s]; }
+            } else if (pt == 2) {
+                for (int l = 0; l <= Ns2; ++l) { const long long s = at(i, l); for (int c = 0; c < 5; ++c) acc[c] = acc[c] + T2[l] * sf[(long long)c * m.nTrace + s]; }
+            } else {
+                for (int l = 0; l <= Ns2; ++l) for (int mm = 0; mm <= Ns1; ++mm) {
+                    const long long s = at(mm, l); const double tt = T1[mm] * T2[l];
+                    for (int c = 0; c < 5; ++c) acc[c] = acc[c] + tt * sf[(long long)c * m.nTrace + s];
+                }
             }
+            for (int c = 0; c < 5; ++c) dst[(long long)(st * 10 + side * 5 + c) * m.nFaceNodes + g] = acc[c];
         }
-        for (int c = 0; c < 5; ++c) dst[(long long)(side * 5 + c) * m.nFaceNodes + g] = acc[c];
     }
 };
 
@@ -1120,11 +1125,12 @@ struct MixedSolver {
     }
     // HexMesh_ProlongSolutionToFaces / ProlongGradientsToFaces: traces at the element order, then adaption to the face order
     void prolong(const double* src, double* dstFace) {
-        launch(MxTrace{m, src, m.tr}, m.nTrace);
-        launch(MxAdapt{m, m.tr, dstFace}, 2 * m.nFaceNodes);
+        launch(MxTrace{m, 1, {src, nullptr, nullptr}, m.tr}, m.nTrace);
+        launch(MxAdapt{m, 1, m.tr, dstFace}, 2 * m.nFaceNodes);
     }
-    void prolongGradients() {
-        prolong(m.Ux, m.fU); prolong(m.Uy, m.fU + 10 * m.nFaceNodes); prolong(m.Uz, m.fU + 20 * m.nFaceNodes);
+    void prolongGradients() {      // the three gradients in one pass: 15 traces per node
+        launch(MxTrace{m, 3, {m.Ux, m.Uy, m.Uz}, m.tr}, m.nTrace);
+        launch(MxAdapt{m, 3, m.tr, m.fU}, 2 * m.nFaceNodes);
     }
     // ComputeTimeDerivative (SpatialDiscretization.f90:227-320) followed by the update of one Runge-Kutta stage
     int residual(const H3dPhysics& physics, const MxRk& rk) {
