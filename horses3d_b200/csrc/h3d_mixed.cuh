@@ -941,6 +941,11 @@ struct MixedSolver {
             if (!sp.count(o[0]) || !sp.count(o[1])) return fail("h3d_set_mesh_p: h3d_set_basis has not been called for every face order");
             fOff[f + 1] = fOff[f] + (long long)(o[0] + 1) * (o[1] + 1);
         }
+        for (int e = 0; e < nElem; ++e) for (int lf = 0; lf < 6; ++lf) {   // e % faceIDs / faceSide must mirror f % elementIDs / elementSide
+            const int f = elemFace[6 * e + lf], sd = elemFaceSide[6 * e + lf];
+            if (f < 0 || f >= nFace || sd < 0 || sd > 1 || faceElem[2 * f + sd] != e || faceElemSide[2 * f + sd] != lf)
+                return fail("h3d_set_mesh_p: elemFace / elemFaceSide do not mirror faceElem / faceElemSide");
+        }
         m.nNodes = eOff[nElem]; m.nTrace = tOff[6 * (size_t)nElem]; m.nFaceNodes = fOff[nFace];
         nodeElem.resize(m.nNodes); traceOwner.resize(m.nTrace); faceNodeFace.resize(m.nFaceNodes);
         for (int e = 0; e < nElem; ++e) for (long long g = eOff[e]; g < eOff[e + 1]; ++g) nodeElem[g] = e;
