@@ -690,13 +690,56 @@ struct MxRedIntegral {   // ScalarVolumeIntegral (VolumeIntegrals.f90:76-120, 16
                     const double ms = -Q[0] * sp / ph.gm1;
                     loc = loc + wJ * ms;
                 } break;
-                case H3D_INT_ENTROPY_RATE: {      // NSGradientVariables_ENTROPY whatever the gradient variables of the run
+                case H3D_INT_ENTROPY_RATE: case H3D_INT_ENTROPY_BALANCE: {      // NSGradientVariables_ENTROPY whatever the gradient variables of the run
                     Phys pe = ph; pe.gradVars = H3D_GRADVARS_ENTROPY;
                     double EV[5];
                     get_gradients(pe, Q, EV);
                     double dot = 0.0;
                     for (int q = 0; q < 5; ++q) dot = dot + QD[q] * EV[q];
+                    if (kind == H3D_INT_ENTROPY_BALANCE) {      // + the viscous work with the run's gradient variables (:335-370)
+                        double gx[5], gy[5], gz[5], F[5][3], mu, kappa, work = 0.0;
+                        for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[(long long)q * m.nNodes + g]; gy[q] = m.Uy[(long long)q * m.nNodes + g]; gz[q] = m.Uz[(long long)q * m.nNodes + g]; }
+                        laminar_mu_kappa(ph, Q, mu, kappa);
+                        if (ph.les != H3D_LES_NONE) { const double mut = smagorinsky<true>(ph, m.lesDelta[e], ph.wallModel ? m.dWall[g] : 0.0, Q, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+                        viscous_flux<true>(ph, Q, gx, gy, gz, mu, 0.0, kappa, F);
+                        for (int q = 0; q < 5; ++q) work = work + (F[q][0] * gx[q] + F[q][1] * gy[q] + F[q][2] * gz[q]);
+                        dot = dot + work;
+                    }
                     loc = loc + wJ * dot;
+                } break;
+                case H3D_INT_KINETIC_ENERGY_BALANCE: {      // kinetic energy rate + viscous work - pressure work + de-aliasing correction (:220-265, 724-764)
+                    const int nn3[3] = {nx, ny, nz}, ijk[3] = {i, j, k};
+                    const long long stride[3] = {1, nx, (long long)nx * ny};
+                    double gMp[3] = {0, 0, 0}, Mgp[3] = {0, 0, 0};
+                    for (int ax = 0; ax < 3; ++ax) {
+                        const double* Dr = mxD(m, nn3[ax] - 1) + ijk[ax] * nn3[ax];
+                        for (int l = 0; l < nn3[ax]; ++l) {
+                            const long long gl = g + (long long)(l - ijk[ax]) * stride[ax];
+                            double Ql[5];
+                            for (int q = 0; q < 5; ++q) Ql[q] = m.Q[(long long)q * m.nNodes + gl];
+                            const double pl = pressure(ph, Ql);
+                            for (int c = 0; c < 3; ++c) {
+                                gMp[c] = gMp[c] + pl * m.Ja[(long long)(3 * ax + c) * m.nNodes + gl] * Dr[l];
+                                Mgp[c] = Mgp[c] + pl * m.Ja[(long long)(3 * ax + c) * m.nNodes + g] * Dr[l];
+                            }
+                        }
+                    }
+                    double gx[5], gy[5], gz[5], F[5][3], mu, kappa;
+                    for (int q = 0; q < 5; ++q) { gx[q] = m.Ux[(long long)q * m.nNodes + g]; gy[q] = m.Uy[(long long)q * m.nNodes + g]; gz[q] = m.Uz[(long long)q * m.nNodes + g]; }
+                    const double inv_rho = 1.0 / Q[0];
+                    double uvw = Q[1] * inv_rho;
+                    double ke = uvw * QD[1] - 0.5 * pow2(uvw) * QD[0];
+                    uvw = Q[2] * inv_rho; ke = ke + uvw * QD[2] - 0.5 * pow2(uvw) * QD[0];
+                    uvw = Q[3] * inv_rho; ke = ke + uvw * QD[3] - 0.5 * pow2(uvw) * QD[0];
+                    const double p3 = ph.gm1 * (Q[4] - 0.5 * (pow2(Q[1]) + pow2(Q[2]) + pow2(Q[3])) * inv_rho);
+                    const double corr = 0.5 * (Q[1] * (Mgp[0] - gMp[0]) + Q[2] * (Mgp[1] - gMp[1]) + Q[3] * (Mgp[2] - gMp[2])) * inv_rho;
+                    Phys pE = ph; pE.gradVars = H3D_GRADVARS_ENERGY;
+                    laminar_mu_kappa(ph, Q, mu, kappa);
+                    if (ph.les != H3D_LES_NONE) { const double mut = smagorinsky<true>(ph, m.lesDelta[e], ph.wallModel ? m.dWall[g] : 0.0, Q, gx, gy, gz); mu = mu + mut; kappa = kappa + mut * ph.mu_to_kappa; }
+                    viscous_flux<true>(pE, Q, gx, gy, gz, mu, 0.0, kappa, F);
+                    double work = 0.0;
+                    for (int q = 1; q < 4; ++q) work = work + (F[q][0] * gx[q] + F[q][1] * gy[q] + F[q][2] * gz[q]);
+                    loc = loc + wx[i] * wy[j] * wz[k] * (m.J[g] * (ke + work - p3 * (gx[1] + gy[2] + gz[3])) + corr);
                 } break;
                 default: break;
             }
@@ -1239,8 +1282,10 @@ struct MixedSolver {
         switch (kind) {
             case H3D_INT_VOLUME: case H3D_INT_KINETIC_ENERGY: case H3D_INT_KINETIC_ENERGY_RATE: case H3D_INT_VELOCITY: case H3D_INT_INTERNAL_ENERGY:
             case H3D_INT_ENTROPY: case H3D_INT_MATH_ENTROPY: case H3D_INT_ENTROPY_RATE: break;
-            case H3D_INT_ENSTROPHY: if (!physics.computeGradients) return fail("volume integral needs gradients"); break;
-            default: return fail("this volume integral is not available on p-nonconforming meshes");
+            case H3D_INT_ENSTROPHY: case H3D_INT_ENTROPY_BALANCE: case H3D_INT_KINETIC_ENERGY_BALANCE:
+                if (!physics.computeGradients) return fail("volume integral needs gradients");
+                break;
+            default: return fail("unknown volume integral");
         }
         launch(MxRedIntegral{m, ph, kind}, m.nElem);
         if (partials(1)) return 2;

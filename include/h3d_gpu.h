@@ -185,10 +185,11 @@ int h3d_set_mesh(h3d_handle h, int nElem, int nFace,
  * solver, boundary condition and gradient-variable set, the LES models (filter widths from the element's / face's own orders,
  * SpatialDiscretization.f90:420,1378; h3d_set_wall_distance in the packed sizes),
  * all Runge-Kutta schemes with the stage limiter, h3d_max_residuals / _max_timestep / _has_nan, h3d_volume_integral (volume,
- * kinetic energy and its rate, enstrophy, mean velocity, internal energy, entropy, math entropy, entropy rate),
+ * kinetic energy and its rate, enstrophy, mean velocity, internal energy, entropy, math entropy, entropy rate, entropy and
+ * kinetic-energy balance),
  * h3d_surface_integral, h3d_probe (Lagrange vectors padded to rows of max(N)+1 values), h3d_statistics_*, and h3d_set_halo on
- * partitioned meshes: the traces of the MPI faces are exchanged at the face order.  Refused with a message: BR2, the entropy /
- * kinetic-energy balance integrals.  h3d_snapshot_begin takes its copy synchronously on such meshes. */
+ * partitioned meshes: the traces of the MPI faces are exchanged at the face order.  Refused with a message: BR2.
+ * h3d_snapshot_begin takes its copy synchronously on such meshes. */
 
 /* Tset(Norigin, Ndest) % T (libs/spectral/InterpolationMatrices.f90:42-107): row-major T[i*(Norigin+1) + l] = T(i,l),
  * (Ndest+1) x (Norigin+1); Lagrange interpolation for Norigin < Ndest, the L2 projection (weighted transpose) otherwise. */

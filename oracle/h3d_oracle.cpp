@@ -1959,7 +1959,6 @@ int orc_statistics_download(void* p, double* data, int* nVars, int* nSamples) {
 int orc_volume_integral(void* p, int kind, double* out) {
     Oracle& o = *(Oracle*)p; const int n = o.n; Idx ix{n};
     double val = 0.0;
-    if (o.mixed && kind == H3D_INT_KINETIC_ENERGY_BALANCE) { o.err = "kinetic energy balance is not available on p-nonconforming meshes"; return 1; }
     for (int e = 0; e < o.nElem; ++e) {
         double loc = 0.0;
         // p-nonconforming meshes: the element's own nodal storages (VolumeIntegrals.f90:190-196)
@@ -1994,14 +1993,17 @@ int orc_volume_integral(void* p, int kind, double* out) {
                 } break;
                 case H3D_INT_KINETIC_ENERGY_BALANCE: {
                     // kinetic energy rate + viscous work - pressure work + de-aliasing correction (:220-265)
-                    auto pressureAt = [&](int a, int b, int c) { return Pressure(o, &o.Q[5 * ix.node(e, a, b, c)]); };
+                    auto nodeAt = [&](int a, int b, int c) { return o.mixed ? PD(o).eOff[e] + (size_t)(c * ny + b) * nx + a : ix.node(e, a, b, c); };
+                    auto pressureAt = [&](int a, int b, int c) { return Pressure(o, &o.Q[5 * nodeAt(a, b, c)]); };
+                    const double* Dx = o.mixed ? PD(o).sp.at(nx - 1).D.data() : o.D.data(); const double* Dy = o.mixed ? PD(o).sp.at(ny - 1).D.data() : o.D.data();
+                    const double* Dz = o.mixed ? PD(o).sp.at(nz - 1).D.data() : o.D.data();
                     double grad_Mp[3] = {0, 0, 0}, M_grad_p[3] = {0, 0, 0};     // GetPressureLocalGradient (:724-764)
-                    for (int l = 0; l < n; ++l) { double pl = pressureAt(l, j, k); size_t gl = ix.node(e, l, j, k);
-                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaXi[3 * gl + d] * o.D[i * n + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaXi[3 * g + d] * o.D[i * n + l]; } }
-                    for (int l = 0; l < n; ++l) { double pl = pressureAt(i, l, k); size_t gl = ix.node(e, i, l, k);
-                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaEta[3 * gl + d] * o.D[j * n + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaEta[3 * g + d] * o.D[j * n + l]; } }
-                    for (int l = 0; l < n; ++l) { double pl = pressureAt(i, j, l); size_t gl = ix.node(e, i, j, l);
-                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaZeta[3 * gl + d] * o.D[k * n + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaZeta[3 * g + d] * o.D[k * n + l]; } }
+                    for (int l = 0; l < nx; ++l) { double pl = pressureAt(l, j, k); size_t gl = nodeAt(l, j, k);
+                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaXi[3 * gl + d] * Dx[i * nx + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaXi[3 * g + d] * Dx[i * nx + l]; } }
+                    for (int l = 0; l < ny; ++l) { double pl = pressureAt(i, l, k); size_t gl = nodeAt(i, l, k);
+                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaEta[3 * gl + d] * Dy[j * ny + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaEta[3 * g + d] * Dy[j * ny + l]; } }
+                    for (int l = 0; l < nz; ++l) { double pl = pressureAt(i, j, l); size_t gl = nodeAt(i, j, l);
+                        for (int d = 0; d < 3; ++d) { grad_Mp[d] = grad_Mp[d] + pl * o.JaZeta[3 * gl + d] * Dz[k * nz + l]; M_grad_p[d] = M_grad_p[d] + pl * o.JaZeta[3 * g + d] * Dz[k * nz + l]; } }
                     double inv_rho = 1.0 / Q[IRHO];
                     double uvw = Q[IRHOU] * inv_rho;
                     double KinEn = uvw * QD[IRHOU] - 0.5 * POW2(uvw) * QD[IRHO];
@@ -2014,7 +2016,7 @@ int orc_volume_integral(void* p, int kind, double* out) {
                     ViscousFlux_ENERGY(o, Q, gx, gy, gz, o.mu[2 * g], 0.0, o.mu[2 * g + 1], F);
                     double work = 0.0;
                     for (int q = IRHOU; q <= IRHOW; ++q) work = work + (F[q][IX] * gx[q] + F[q][IY] * gy[q] + F[q][IZ] * gz[q]);
-                    loc = loc + o.w[i] * o.w[j] * o.w[k] * (o.jac[g] * (KinEn + work - p3 * (gx[IRHOU] + gy[IRHOV] + gz[IRHOW])) + corr);
+                    loc = loc + wx[i] * wy[j] * wz[k] * (o.jac[g] * (KinEn + work - p3 * (gx[IRHOU] + gy[IRHOV] + gz[IRHOW])) + corr);
                 } break;
                 case H3D_INT_VELOCITY:
                     loc = loc + wx[i] * wy[j] * wz[k] * std::sqrt(POW2(Q[IRHOU]) + POW2(Q[IRHOV]) + POW2(Q[IRHOW])) / Q[IRHO] * o.jac[g];

@@ -81,7 +81,7 @@ def run_case(api, mesh, phys, scheme="rk3", dt=2.0e-3, source=False, zone=None, 
     kinds = [P.INT_VOLUME, P.INT_KINETIC_ENERGY, P.INT_KINETIC_ENERGY_RATE, P.INT_VELOCITY, P.INT_INTERNAL_ENERGY, P.INT_ENTROPY, P.INT_MATH_ENTROPY,
              P.INT_ENTROPY_RATE]
     if phys.computeGradients:
-        kinds.append(P.INT_ENSTROPHY)
+        kinds += [P.INT_ENSTROPHY, P.INT_ENTROPY_BALANCE, P.INT_KINETIC_ENERGY_BALANCE]
     out["integrals"] = np.array([sem.ScalarVolumeIntegral(k) for k in kinds])
     out["nan"] = np.array([sem.checkForNan()])
     if zone is not None:

@@ -104,7 +104,7 @@ def test_unsupported_entry_points_are_refused(gpu_api_cls):
     phys = make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe")
     sem = DGSem(gpu_api_cls(), MC.periodic_box(2, 2, 3, seed=1), phys)
     with pytest.raises(H3dError):
-        sem.ScalarVolumeIntegral(10)      # kinetic energy balance
+        sem.ScalarVolumeIntegral(99)      # unknown kind
     with pytest.raises(H3dError):
         DGSem(gpu_api_cls(), MC.periodic_box(2, 2, 3, seed=1, nodes=GAUSSLOBATTO), make_physics(flow="NS", mach=0.3, reynolds=100.0, riemann="roe", viscous="br2"))
     with pytest.raises(H3dError):      # the split form needs Gauss-Lobatto nodes
