@@ -31,6 +31,22 @@ def both(gpu_api_cls, mesh_fn, phys, tol=TOL, **kw):
     assert not bad, bad
 
 
+def test_state_round_trip_and_euler_residual(gpu_api_cls):
+    """The smallest steps first, so that a failure on a new device is easy to place: set-up, upload / download of the packed state
+    (device-side transposition), then the Euler residual without gradients (trace, adaption, Riemann, projection, volume)."""
+    from horses3d_b200.dgsem import DGSem
+    phys = make_physics(flow="Euler", mach=0.3, riemann="roe")
+    sem = DGSem(gpu_api_cls(), MC.periodic_box(2, 1, 4, seed=3), phys)
+    Q = MC.smooth_state(sem, 0.3)
+    sem.set_Q(Q)
+    assert np.array_equal(sem.Q(), Q)
+    ref = DGSem(oracle_api.OracleApi(), MC.periodic_box(2, 1, 4, seed=3), phys)
+    ref.set_Q(Q)
+    sem.ComputeTimeDerivative(0.0); ref.ComputeTimeDerivative(0.0)
+    a, b = ref.QDot(), sem.QDot()
+    assert np.abs(a - b).max() <= TOL * np.abs(a).max()
+
+
 @pytest.mark.parametrize("riemann", ["roe", "lax-friedrichs", "standard roe", "central"])
 def test_navier_stokes_periodic_box_random_anisotropic_orders(gpu_api_cls, riemann):
     both(gpu_api_cls, lambda: MC.periodic_box(3, 2, 5, seed=7), make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann=riemann), source=True)
