@@ -52,6 +52,11 @@ def test_oracle_is_not_reachable_from_the_product_package():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_api" not in text and "h3d_oracle" not in text and "orc_" not in text, os.path.join(dirpath, f)
+                # nor the host-loop backend of the p-nonconforming kernels (tests/emu): the device library has the CUDA backend only
+                assert "emu_api" not in text and "h3d_mixed_emu" not in text and "emu_" not in text and "HostBackend" not in text, os.path.join(dirpath, f)
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", os.path.join(pkg, "csrc", "libh3dgpu.so")], stdout=subprocess.PIPE, text=True).stdout
+    assert "emu_" not in syms and "HostBackend" not in syms
 
 
 def test_fortran_interfaces_are_in_step_with_the_header():
