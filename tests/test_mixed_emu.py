@@ -281,3 +281,33 @@ def test_set_up_errors_are_reported():
     sem.set_Q(MC.smooth_state(sem, 0.3))
     with pytest.raises(H3dError, match="h3d_set_boundary_conditions was not called"):
         sem.ComputeTimeDerivative(0.0)
+
+
+def test_k13_on_four_emulated_ranks():
+    """The reference runs CylinderDifferentOrders under MPI in its parallel CI with the same expected values: the partitioned run
+    (METIS weighted with the elements' degrees of freedom, four ranks as threads over the host-loop backend) meets them too."""
+    import threading
+    from emu.emu_api import EmuWorld
+    from test_oracle_pins import K13, cylinder_different_orders
+    world, out, errs = EmuWorld(4), [None] * 4, []
+    part = cylinder_different_orders(steps=None).partition(4, "metis")      # once, before the threads: METIS is not re-entrant
+    assert len(set(part)) == 4
+
+    def work(rank):
+        try:
+            out[rank] = cylinder_different_orders(EmuApi(world, rank), partition=(part, rank))[1:]
+        except Exception as ex:
+            errs.append(ex)
+            world.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    probes_found = [o[3] for o in out if o[3] is not None]
+    assert len(probes_found) >= 1
+    for res, cd, cl, _ in out:
+        assert np.abs(res - K13["residuals"]).max() < 1.0e-11 and abs(cd - K13["cd"]) < 1.2e-10 and abs(cl - K13["cl"]) < 1.0e-11
+    assert abs(probes_found[0] - K13["wake_u"]) < 1.0e-11

@@ -100,3 +100,56 @@ def test_ranks_reproduce_the_single_domain_oracle_on_a_p_nonconforming_mesh(case
                 assert np.abs(out[k] - mine).max() <= 1e-13 * scale, (rank, k)
             else:
                 assert np.abs(np.asarray(out[k], dtype=float) - np.asarray(v, dtype=float)).max() <= 1e-12 * scale, (rank, k)
+
+
+def _worker_k13(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from horses3d_b200.capi import GpuApi
+        from test_oracle_pins import cylinder_different_orders
+        obj = [GpuApi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        api = GpuApi(rank=rank, nranks=world, device=rank, nccl_id=obj[0])
+        _, res, cd, cl, wake_u = cylinder_different_orders(api, partition=(world, rank))
+        q.put((rank, res, cd, cl, wake_u))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_k13_cylinder_different_orders_on_several_gpus(world):
+    """The reference's CylinderDifferentOrders regression partitioned over several B200s (its parallel CI runs it under MPI with the same
+    expected values, SETUP/ProblemFile.f90:553-614)."""
+    import queue
+    import time
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs, this box has %d (run under gpurun --gpus %d)" % (world, torch.cuda.device_count(), world))
+    from test_oracle_pins import K13
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_k13, args=(r, world, 29900 + (os.getpid() % 1000), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, t0 = [], time.time()
+    while len(got) < world:
+        try:
+            got.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > 600:
+                for p in procs:
+                    p.kill()
+                pytest.fail("a rank exited with %s / timed out after %.0f s" % (dead, time.time() - t0))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    wakes = [g[4] for g in got if g[4] is not None]
+    assert wakes and abs(wakes[0] - K13["wake_u"]) < 1.0e-11
+    for _, res, cd, cl, _w in got:
+        assert np.abs(res - K13["residuals"]).max() < 1.0e-11 and abs(cd - K13["cd"]) < 1.2e-10 and abs(cl - K13["cl"]) < 1.0e-11
