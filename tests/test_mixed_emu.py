@@ -33,6 +33,13 @@ def test_larger_mesh_with_orders_up_to_nine():
     both(lambda: MC.periodic_box(6, 1, 9, seed=21), make_physics(flow="NS", mach=0.3, reynolds=400.0, riemann="roe"))
 
 
+def test_edge_cases_self_periodic_element_and_orders_up_to_fifteen():
+    """An element that is its own periodic neighbour on all six faces (one-element mesh), and the highest orders the path takes."""
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")
+    both(lambda: MC.periodic_box(1, 2, 5, seed=3), phys)
+    both(lambda: MC.periodic_box(2, 10, 15, seed=5), phys)
+
+
 def test_euler_with_and_without_gradients():
     both(lambda: MC.periodic_box(3, 1, 4, seed=5), make_physics(flow="Euler", mach=0.3, riemann="roe"))
     both(lambda: MC.periodic_box(3, 1, 4, seed=5), make_physics(flow="Euler", mach=0.3, riemann="rusanov", compute_gradients=True))

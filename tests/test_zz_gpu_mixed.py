@@ -56,6 +56,12 @@ def test_larger_mesh_with_orders_up_to_nine(gpu_api_cls):
     both(gpu_api_cls, lambda: MC.periodic_box(6, 1, 9, seed=21), make_physics(flow="NS", mach=0.3, reynolds=400.0, riemann="roe"))
 
 
+def test_edge_cases_self_periodic_element_and_orders_up_to_fifteen(gpu_api_cls):
+    phys = make_physics(flow="NS", mach=0.3, reynolds=200.0, riemann="roe")
+    both(gpu_api_cls, lambda: MC.periodic_box(1, 2, 5, seed=3), phys)
+    both(gpu_api_cls, lambda: MC.periodic_box(2, 10, 15, seed=5), phys)      # beyond the orders the uniform kernels are instantiated for
+
+
 def test_euler_with_and_without_gradients(gpu_api_cls):
     both(gpu_api_cls, lambda: MC.periodic_box(3, 1, 4, seed=5), make_physics(flow="Euler", mach=0.3, riemann="roe"))
     both(gpu_api_cls, lambda: MC.periodic_box(3, 1, 4, seed=5), make_physics(flow="Euler", mach=0.3, riemann="rusanov", compute_gradients=True))
